@@ -1,0 +1,193 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+Imports /root/reference/allrank behind oracle/_stubs (gcsfs / tensorboardX / flatten_dict are the
+only missing deps) with CUDA hidden (model_utils.get_torch_device() hard-wires cuda:0), runs the
+reference on seeded inputs and stores inputs + outputs.  /root/reference does not exist on the GPU
+box, so tests only ever read the committed .npz files.
+"""
+import os
+import sys
+
+os.environ["CUDA_VISIBLE_DEVICES"] = ""
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path[:0] = [os.path.join(HERE, "_stubs"), "/root/reference", ROOT]
+sys.dont_write_bytecode = True
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from allrank.models import losses as ref_losses  # noqa: E402
+from allrank.models import metrics as ref_metrics  # noqa: E402
+from allrank.models.model import make_model as ref_make_model  # noqa: E402
+from allrank.config import TransformerConfig  # noqa: E402
+from allrank_b200.synth import make_slates, make_scores  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+LOSS_CASES = [
+    ("listNet", {}),
+    ("approxNDCGLoss", {}),
+    ("approxNDCGLoss", {"alpha": 2.5}),
+    ("lambdaLoss", {}),
+    ("lambdaLoss", {"weighing_scheme": "ndcgLoss1_scheme"}),
+    ("lambdaLoss", {"weighing_scheme": "ndcgLoss2_scheme"}),
+    ("lambdaLoss", {"weighing_scheme": "lambdaRank_scheme"}),
+    ("lambdaLoss", {"weighing_scheme": "ndcgLoss2PP_scheme"}),
+    ("lambdaLoss", {"weighing_scheme": "ndcgLoss2PP_scheme", "k": 10, "mu": 5.0, "sigma": 0.7}),
+    ("lambdaLoss", {"weighing_scheme": "rankNet_scheme", "reduction_log": "natural", "reduction": "mean"}),
+    ("lambdaLoss", {"weighing_scheme": "rankNetWeightedByGTDiff_scheme"}),
+    ("lambdaLoss", {"weighing_scheme": "rankNetWeightedByGTDiffPowed_scheme", "k": 5}),
+    ("neuralNDCG", {}),
+    ("neuralNDCG", {"temperature": 0.1, "k": 10}),
+    ("neuralNDCG", {"powered_relevancies": False, "temperature": 3.0}),
+]
+SHAPES = [(5, 7), (4, 33), (3, 120), (3, 240)]
+
+
+def case_inputs(b, s, seed):
+    _, y, _ = make_slates(b, s, n_features=1, seed=seed)
+    if s >= 33:
+        y[0] = torch.where(y[0] >= 0, torch.zeros_like(y[0]), y[0])   # one slate without relevant items
+    yp = make_scores(b, s, seed=seed + 7)
+    return yp, y
+
+
+def run_loss(fn, yp, y, kw, dtype):
+    p = yp.to(dtype).clone().requires_grad_(True)
+    val = fn(p, y.to(dtype), **kw)
+    if val.requires_grad:
+        val.backward()
+        grad = p.grad
+    else:
+        grad = torch.zeros_like(p)
+    return val.detach(), grad
+
+
+def gen_losses():
+    blob = {}
+    names = []
+    for ci, (name, kw) in enumerate(LOSS_CASES):
+        fn = getattr(ref_losses, name)
+        for (b, s) in SHAPES:
+            if name == "neuralNDCG" and s > 120:
+                continue
+            key = f"c{ci}_s{s}"
+            yp, y = case_inputs(b, s, seed=100 * ci + s)
+            v32, g32 = run_loss(fn, yp, y, kw, torch.float32)
+            blob[key + "_pred"] = yp.numpy()
+            blob[key + "_true"] = y.numpy()
+            blob[key + "_loss32"] = v32.numpy()
+            blob[key + "_grad32"] = g32.numpy()
+            if name != "neuralNDCG":   # reference neuralNDCG builds fp32 helpers internally; no fp64 run
+                v64, g64 = run_loss(fn, yp, y, kw, torch.float64)
+                blob[key + "_loss64"] = v64.numpy()
+                blob[key + "_grad64"] = g64.numpy()
+            names.append(key)
+    blob["cases"] = np.array([repr(c) for c in LOSS_CASES])
+    blob["keys"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **blob)
+    print("losses:", len(names), "cases")
+
+
+def gen_listmle():
+    blob = {}
+    keys = []
+    for (b, s) in SHAPES:
+        for tie_free in (True, False):
+            yp, y = case_inputs(b, s, seed=900 + s)
+            if tie_free:   # distinct labels -> value independent of the (unstable) tie order
+                g = torch.Generator().manual_seed(s)
+                distinct = torch.rand(b, s, generator=g) * 4.0
+                y = torch.where(y >= 0, distinct, y)
+            torch.manual_seed(4242 + s)
+            state = torch.get_rng_state()
+            perm = torch.randperm(s)              # what listMLE.py:17 will draw
+            torch.set_rng_state(state)
+            p = yp.clone().requires_grad_(True)
+            val = ref_losses.listMLE(p, y)
+            val.backward()
+            order = y[:, perm].sort(descending=True, dim=-1).indices   # realised tie order on this host
+            key = f"s{s}_{'distinct' if tie_free else 'ties'}"
+            blob[key + "_pred"] = yp.numpy()
+            blob[key + "_true"] = y.numpy()
+            blob[key + "_perm"] = perm.numpy()
+            blob[key + "_order"] = order.numpy()
+            blob[key + "_loss32"] = val.detach().numpy()
+            blob[key + "_grad32"] = p.grad.numpy()
+            keys.append(key)
+    blob["keys"] = np.array(keys)
+    np.savez_compressed(os.path.join(OUT, "listmle.npz"), **blob)
+    print("listMLE:", len(keys), "cases")
+
+
+def gen_metrics():
+    blob = {}
+    keys = []
+    ats = [1, 5, 10, 30, 60, 1000]
+    for (b, s) in SHAPES + [(2, 1251)]:
+        yp, y = case_inputs(b, s, seed=500 + s)
+        key = f"s{s}"
+        blob[key + "_pred"] = yp.numpy()
+        blob[key + "_true"] = y.numpy()
+        blob[key + "_ndcg"] = ref_metrics.ndcg(yp, y, ats=ats).numpy()
+        blob[key + "_dcg"] = ref_metrics.dcg(yp, y, ats=ats).numpy()
+        blob[key + "_mrr"] = ref_metrics.mrr(yp, y, ats=ats).numpy()
+        blob[key + "_ndcg_none"] = ref_metrics.ndcg(yp, y).numpy()
+        blob[key + "_dcg_identity"] = ref_metrics.dcg(yp, y, ats=[3, 10], gain_function=lambda x: x).numpy()
+        masked = yp.clone()
+        masked[y == -1] = float("-inf")
+        blob[key + "_order"] = masked.sort(descending=True, dim=-1).indices.numpy()
+        keys.append(key)
+    blob["ats"] = np.array(ats)
+    blob["keys"] = np.array(keys)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **blob)
+    print("metrics:", len(keys), "cases")
+
+
+SCORER_CASES = {
+    # name: (F, fc_sizes, N, h, d_ff, B, S, output_activation)
+    "tiny": (20, [32], 1, 2, 64, 3, 20, None),
+    "mid": (136, [64], 2, 2, 128, 2, 50, "Tanh"),
+    "cfg2": (136, [128], 2, 4, 512, 2, 240, None),
+}
+
+
+def gen_scorer():
+    for name, (F, sizes, N, h, dff, B, S, act) in SCORER_CASES.items():
+        torch.manual_seed(7)
+        model = ref_make_model(
+            fc_model={"sizes": list(sizes), "input_norm": False, "activation": None, "dropout": 0.0},
+            transformer=TransformerConfig(N=N, d_ff=dff, h=h, positional_encoding=None, dropout=0.0),
+            post_model={"d_output": 1, "output_activation": act}, n_features=F)
+        # perturb the norm gains/biases and linear biases so parity exercises them
+        g = torch.Generator().manual_seed(11)
+        with torch.no_grad():
+            for n_, p in model.named_parameters():
+                if p.dim() == 1:
+                    p.add_(0.1 * torch.randn(p.shape, generator=g))
+        model.eval()
+        x, y, idx = make_slates(B, S, n_features=F, seed=31, mean_len=0.6 * S, std_len=0.3 * S)
+        mask = y == -1
+        scores = model(x, mask, idx)
+        w = torch.randn(scores.shape, generator=g)
+        (scores * w).sum().backward()
+        blob = {"x": x.numpy(), "y": y.numpy(), "scores": scores.detach().numpy(), "w": w.numpy(),
+                "meta": np.array([F, sizes[0], N, h, dff, B, S]), "act": np.array(str(act))}
+        for k_, v in model.state_dict().items():
+            blob["p:" + k_] = v.numpy()
+        for k_, p in model.named_parameters():
+            blob["g:" + k_] = p.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, f"scorer_{name}.npz"), **blob)
+        print("scorer", name, "scores", tuple(scores.shape))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    gen_losses()
+    gen_listmle()
+    gen_metrics()
+    gen_scorer()
