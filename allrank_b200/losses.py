@@ -1,0 +1,172 @@
+"""Drop-in replacements for the listwise members of allrank.models.losses -- same names, positional
+order, keyword arguments and defaults as the reference:
+
+    listNet         /root/reference/allrank/models/losses/listNet.py:8
+    listMLE         .../listMLE.py:7
+    approxNDCGLoss  .../approxNDCG.py:7
+    lambdaLoss      .../lambdaLoss.py:7   (7 weighing schemes :84-114)
+    neuralNDCG      .../neuralNDCG.py:10  (deterministic NeuralSort + Sinkhorn, loss_utils.py:8-67)
+
+Each call is ONE fused forward+backward kernel launch (+ a tiny batch-finalise launch) through the C ABI;
+the result is a 0-dim tensor on y_pred's device attached to autograd (gradient w.r.t. y_pred only), which is
+what allrank/training/train_utils.py:20-29 needs (`loss.backward()`, `loss.item()`).
+No CPU fallback: CPU tensors raise.
+"""
+import torch
+
+from . import _lib
+from .metrics import discount_table
+
+PADDED_Y_VALUE = -1   # allrank/data/dataset_loading.py:15
+DEFAULT_EPS = 1e-10   # allrank/models/losses/__init__.py:1
+
+_SCHEMES = {
+    None: 0,
+    "ndcgLoss1_scheme": 1,
+    "ndcgLoss2_scheme": 2,
+    "lambdaRank_scheme": 3,
+    "ndcgLoss2PP_scheme": 4,
+    "rankNet_scheme": 5,
+    "rankNetWeightedByGTDiff_scheme": 6,
+    "rankNetWeightedByGTDiffPowed_scheme": 7,
+}
+
+
+class _FusedLoss(torch.autograd.Function):
+    """forward runs the fused kernel (loss + d loss/d y_pred); backward scales the saved gradient."""
+
+    @staticmethod
+    def forward(ctx, y_pred, launcher):
+        need_grad = ctx.needs_input_grad[0]
+        scores = y_pred.detach().float().contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=y_pred.device)
+        grad = torch.empty_like(scores) if need_grad else None
+        with torch.cuda.device(y_pred.device):
+            launcher(scores, loss, grad)
+        ctx.in_dtype = y_pred.dtype
+        if need_grad:
+            ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, upstream):
+        (grad,) = ctx.saved_tensors
+        return (upstream * grad).to(ctx.in_dtype), None
+
+
+def _run(y_pred, y_true, launcher):
+    _lib.require_cuda(y_pred, y_true)
+    if y_pred.dim() != 2 or y_pred.shape != y_true.shape:
+        raise ValueError("y_pred and y_true must both be [batch_size, slate_length]")
+    if y_pred.shape[0] == 0:
+        raise ValueError("empty batch")
+    labels = y_true.detach().float().contiguous()
+    B, S = labels.shape
+    scratch = torch.empty(2 * B, dtype=torch.float32, device=labels.device)
+
+    def bound(scores, loss, grad):
+        launcher(scores, labels, B, S, loss, grad, scratch)
+
+    # needs_input_grad is decided by autograd; grad is only computed when y_pred requires it
+    return _FusedLoss.apply(y_pred, bound)
+
+
+def listNet(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE):
+    """ListNet loss -- listNet.py:8-30."""
+
+    def launch(s, t, B, S, loss, grad, scratch):
+        rc = _lib.lib().arb_listnet(_lib.ptr(s), _lib.ptr(t), B, S, float(eps), float(padded_value_indicator),
+                                    _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(scratch), _lib.stream_ptr(s.device))
+        _lib.check(rc, "arb_listnet")
+
+    return _run(y_pred, y_true, launch)
+
+
+def listMLE(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE, perm=None, order=None):
+    """ListMLE loss -- listMLE.py:7-38.
+
+    The reference shuffles columns with `torch.randperm(S)` drawn from the global CPU RNG (:17) before its
+    (unstable) label sort; we draw the same permutation from the same RNG.  Extensions (not in the reference
+    signature): `perm` fixes the shuffle, `order` ([B,S] int) feeds a realised sort order of the shuffled
+    labels (parity hook).
+    """
+    S = y_pred.shape[-1]
+    if perm is None:
+        perm = torch.randperm(S)
+    perm_dev = perm.to(device=y_pred.device, dtype=torch.int64).contiguous()
+    order_dev = None if order is None else order.to(device=y_pred.device, dtype=torch.int32).contiguous()
+
+    def launch(s, t, B, S_, loss, grad, scratch):
+        rc = _lib.lib().arb_listmle(_lib.ptr(s), _lib.ptr(t), B, S_, float(eps), float(padded_value_indicator),
+                                    _lib.ptr(perm_dev), _lib.ptr(order_dev), _lib.ptr(loss), _lib.ptr(grad),
+                                    _lib.ptr(scratch), _lib.stream_ptr(s.device))
+        _lib.check(rc, "arb_listmle")
+
+    return _run(y_pred, y_true, launch)
+
+
+def approxNDCGLoss(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE, alpha=1.):
+    """ApproxNDCG loss (no @k truncation) -- approxNDCG.py:7-53."""
+
+    def launch(s, t, B, S, loss, grad, scratch):
+        rc = _lib.lib().arb_approx_ndcg(_lib.ptr(s), _lib.ptr(t), B, S, float(eps), float(padded_value_indicator),
+                                        float(alpha), _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(scratch),
+                                        _lib.stream_ptr(s.device))
+        _lib.check(rc, "arb_approx_ndcg")
+
+    return _run(y_pred, y_true, launch)
+
+
+def lambdaLoss(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE, weighing_scheme=None, k=None,
+               sigma=1., mu=10., reduction="sum", reduction_log="binary"):
+    """LambdaLoss framework -- lambdaLoss.py:7-81; same error conventions (:72, :79, KeyError at :61)."""
+    if weighing_scheme not in _SCHEMES:
+        raise KeyError(weighing_scheme)
+    if reduction_log not in ("natural", "binary"):
+        raise ValueError("Reduction logarithm base can be either natural or binary")
+    if reduction not in ("sum", "mean"):
+        raise ValueError("Reduction method can be either sum or mean")
+    scheme = _SCHEMES[weighing_scheme]
+    kk = 0 if k is None else int(k)
+    if k is not None and kk <= 0:
+        raise ValueError("k must be a positive rank or None")
+
+    def launch(s, t, B, S, loss, grad, scratch):
+        rc = _lib.lib().arb_lambda_loss(_lib.ptr(s), _lib.ptr(t), B, S, float(eps), float(padded_value_indicator),
+                                        scheme, kk, float(sigma), float(mu), 1 if reduction == "mean" else 0,
+                                        1 if reduction_log == "natural" else 0, _lib.ptr(loss), _lib.ptr(grad),
+                                        _lib.ptr(scratch), _lib.stream_ptr(s.device))
+        _lib.check(rc, "arb_lambda_loss")
+
+    return _run(y_pred, y_true, launch)
+
+
+def neuralNDCG(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE, temperature=1., powered_relevancies=True, k=None,
+               stochastic=False, n_samples=32, beta=0.1, log_scores=True, max_iter=50, tol=1e-6):
+    """NeuralNDCG loss -- neuralNDCG.py:10-70.
+
+    `max_iter` / `tol` are the Sinkhorn parameters the reference hard-codes to 50 / 1e-6 (:41-42); they are
+    exposed here (defaults unchanged) because BASELINE.json also quotes a 30-iteration configuration.
+    The stochastic (Gumbel) variant is a SURVEY.md 8(f) "next" row and is not built yet.
+    """
+    if stochastic:
+        raise NotImplementedError("stochastic NeuralSort is not implemented in allrank_b200 yet (no CPU fallback)")
+    kk = 0 if k is None else int(k)
+    S = y_pred.shape[-1]
+    dev = y_pred.device
+    disc = discount_table(S, dev)
+    ws_bytes = int(_lib.lib().arb_neural_ndcg_workspace_bytes(y_pred.shape[0], S, int(max_iter)))
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+
+    def launch(s, t, B, S_, loss, grad, scratch):
+        rc = _lib.lib().arb_neural_ndcg(_lib.ptr(s), _lib.ptr(t), B, S_, _lib.ptr(disc),
+                                        float(padded_value_indicator), float(temperature),
+                                        1 if powered_relevancies else 0, kk, int(max_iter), float(tol),
+                                        _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(scratch), _lib.ptr(ws), ws_bytes,
+                                        _lib.stream_ptr(s.device))
+        _lib.check(rc, "arb_neural_ndcg")
+
+    return _run(y_pred, y_true, launch)
+
+
+__all__ = ["listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "DEFAULT_EPS", "PADDED_Y_VALUE"]

@@ -1,0 +1,122 @@
+/* allrank_b200 -- C ABI of the B200 (sm_100a) scoring + listwise-loss + metric path.
+ *
+ * This is the drop-in boundary.  allRank is pure Python, so there is no
+ * existing FFI to mirror; each entry point below replaces one *Python call surface* of the
+ * reference and cites it.  The Python host layer (allrank_b200/{losses,metrics,model}.py) binds
+ * these with ctypes and re-exports the reference's names/signatures; INTEGRATION.md shows the
+ * stub a maintainer adds on the allRank side.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; no torch types.  All pointers are DEVICE pointers unless the
+ *     parameter name ends in `_host`.  Tensors are row-major, contiguous, fp32 unless stated.
+ *   - the library never allocates or frees device memory: outputs and workspaces are caller-owned
+ *     (the host layer allocates them with PyTorch's caching allocator).
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) of the CURRENT device and returns without synchronising; calls are re-entrant.
+ *   - return value: 0 = ok, <0 = ARB_E_* below; arb_last_error() gives a thread-local message.
+ *   - inputs are const: the caller's y_pred / y_true / x / mask are never modified
+ *     (the reference clones before masking: listNet.py:17-18, lambdaLoss.py:25-26, metrics.py:53-54).
+ */
+#ifndef ALLRANK_B200_H
+#define ALLRANK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARB_OK 0
+#define ARB_E_INVALID_ARG (-1)
+#define ARB_E_UNSUPPORTED (-2)
+#define ARB_E_CUDA (-3)
+#define ARB_E_WORKSPACE (-4)
+
+#define ARB_MAX_ATS 32
+
+/* lambdaLoss weighing schemes: allrank/models/losses/lambdaLoss.py:84-114 (selected by name at :61) */
+#define ARB_SCHEME_NONE 0
+#define ARB_SCHEME_NDCGLOSS1 1
+#define ARB_SCHEME_NDCGLOSS2 2
+#define ARB_SCHEME_LAMBDARANK 3
+#define ARB_SCHEME_NDCGLOSS2PP 4
+#define ARB_SCHEME_RANKNET 5
+#define ARB_SCHEME_RANKNET_GTDIFF 6
+#define ARB_SCHEME_RANKNET_GTDIFF_POWED 7
+
+#define ARB_REDUCTION_SUM 0
+#define ARB_REDUCTION_MEAN 1
+#define ARB_LOG_BINARY 0
+#define ARB_LOG_NATURAL 1
+
+#define ARB_GAIN_POW2 0     /* 2^x - 1 : default gain_function of metrics.dcg (metrics.py:41)          */
+#define ARB_GAIN_IDENTITY 1 /* x       : what neuralNDCG passes when powered_relevancies=False (:58)   */
+
+const char* arb_last_error(void);
+int32_t arb_abi_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t arb_launch_count(void);
+
+/* ---------------------------------------------------------------- metrics
+ * Replaces allrank.models.metrics.{dcg,ndcg,mrr} (allrank/models/metrics.py:41-77, :7-28, :80-113),
+ * called from train_utils.metric_on_batch (allrank/training/train_utils.py:32-34).
+ * One launch computes any subset of the outputs (NULL pointer = not wanted):
+ *   out_dcg   [B,n_ats]  DCG@at of labels ranked by y_pred          (ats_dcg_host: already min(at,S))
+ *   out_idcg  [B,n_ats]  DCG@at of labels ranked by themselves
+ *   out_ndcg  [B,n_ats]  out_dcg/out_idcg, `filler` where out_idcg == 0
+ *   out_mrr   [B,n_ats]  reciprocal rank of the first max-label item if rank < at (ats_mrr_host, unclipped);
+ *                        all zeros if the batch-wide sum of per-slate max labels is 0 (metrics.py:108-109)
+ *   out_order [B,S] i32  the descending argsort of the masked scores (stable; bit-exact on tie-free input)
+ * `discounts` is the [S] fp32 table 1/log2(j+2) that the reference evaluates on the HOST (metrics.py:64);
+ * the host layer builds it the same way so DCG values can match bit for bit.
+ * `mrr_scratch` : >= 2*B floats. */
+int32_t arb_rank_metrics(const float* y_pred, const float* y_true, int32_t B, int32_t S,
+                         const float* discounts, const int32_t* ats_dcg_host, const int32_t* ats_mrr_host,
+                         int32_t n_ats, int32_t gain_mode, float pad_value, float filler,
+                         float* out_dcg, float* out_idcg, float* out_ndcg, float* out_mrr, int32_t* out_order,
+                         float* mrr_scratch, void* stream);
+
+/* ---------------------------------------------------------------- losses (forward + backward in one launch)
+ * Each replaces `loss_func(y_pred, y_true)` at allrank/training/train_utils.py:20 for one member of
+ * allrank.models.losses.  `loss` is a device scalar; `grad` ([B,S], may be NULL for eval) receives
+ * d loss / d y_pred.  `scratch` : >= 2*B floats. */
+
+/* listNet(y_pred, y_true, eps, padded_value_indicator)            allrank/models/losses/listNet.py:8-30 */
+int32_t arb_listnet(const float* y_pred, const float* y_true, int32_t B, int32_t S, float eps, float pad_value,
+                    float* loss, float* grad, float* scratch, void* stream);
+
+/* listMLE(...)                                                    allrank/models/losses/listMLE.py:7-38
+ * `perm` [S] i64: the column shuffle the reference draws with torch.randperm (:17) -- drawn by the host
+ * layer from the same global CPU RNG.  `order` (nullable [B,S] i32): debug hook feeding a realised sort
+ * order of the shuffled labels; NULL = stable descending sort on the device. */
+int32_t arb_listmle(const float* y_pred, const float* y_true, int32_t B, int32_t S, float eps, float pad_value,
+                    const int64_t* perm, const int32_t* order, float* loss, float* grad, float* scratch,
+                    void* stream);
+
+/* approxNDCGLoss(y_pred, y_true, eps, padded_value_indicator, alpha)   .../losses/approxNDCG.py:7-53 */
+int32_t arb_approx_ndcg(const float* y_pred, const float* y_true, int32_t B, int32_t S, float eps,
+                        float pad_value, float alpha, float* loss, float* grad, float* scratch, void* stream);
+
+/* lambdaLoss(y_pred, y_true, eps, pad, weighing_scheme, k, sigma, mu, reduction, reduction_log)
+ *                                                                  .../losses/lambdaLoss.py:7-114
+ * k <= 0 means "None" (no truncation). */
+int32_t arb_lambda_loss(const float* y_pred, const float* y_true, int32_t B, int32_t S, float eps,
+                        float pad_value, int32_t scheme, int32_t k, float sigma, float mu, int32_t reduction,
+                        int32_t log_base, float* loss, float* grad, float* scratch, void* stream);
+
+/* neuralNDCG(y_pred, y_true, pad, temperature, powered_relevancies, k, stochastic=False)
+ *                            .../losses/neuralNDCG.py:10-70 + loss_utils.py:8-67 (NeuralSort, Sinkhorn)
+ * max_iter / tol are the Sinkhorn parameters the reference hard-codes to 50 / 1e-6 (neuralNDCG.py:41-42).
+ * `discounts`: the same host-evaluated [S] table 1/log2(j+2) as arb_rank_metrics (neuralNDCG.py:52).
+ * `workspace`: arb_neural_ndcg_workspace_bytes(B,S,max_iter) bytes (0 when every slate fits in shared memory). */
+size_t arb_neural_ndcg_workspace_bytes(int32_t B, int32_t S, int32_t max_iter);
+int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int32_t B, int32_t S,
+                        const float* discounts, float pad_value, float temperature, int32_t powered_relevancies, int32_t k, int32_t max_iter, float tol,
+                        float* loss, float* grad, float* scratch, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALLRANK_B200_H */
