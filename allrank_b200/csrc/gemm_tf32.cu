@@ -1,0 +1,371 @@
+// Batched TF32 GEMM on the 5th-generation tensor cores:  C[M,N] = epilogue(alpha * A * B^T)
+//
+//   * operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a STAGES-deep shared-memory ring,
+//   * tcgen05.mma.kind::tf32 issued by one elected thread, fp32 accumulator tile [128 x BLOCK_N] in TMEM,
+//   * epilogue warps read TMEM (tcgen05.ld 32x32b), apply bias / ReLU / residual / ReLU-mask, stage the tile in
+//     swizzled shared memory and write it with one TMA store per 32-column slab (TMA clips ragged edges, so a
+//     240-row slate or a 136-wide feature matrix needs no masking code),
+//   * either operand may be "K-major" (rows of K contiguous, e.g. nn.Linear weights [out,in]) or "MN-major"
+//     (the transpose), which is what the backward GEMMs dX = dY W and dW = dY^T X need,
+//   * split-K with red.global.add for the weight gradients (K = all rows of the batch).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
+// (warp w owns TMEM lanes 32*(w%4) .. +31, i.e. 32 rows of the tile).
+//
+// This one kernel is the tensor-core workhorse of the scorer: every nn.Linear forward/backward and the
+// generic (unfused) attention contractions go through it.  Reference ops replaced: aten::addmm / aten::bmm
+// issued from allrank/models/transformer.py:148,156,193-195,203,227 and allrank/models/model.py:41-44,117.
+#include <cstdio>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.h"
+#include "gemm_tf32.h"
+#include "sm100_ptx.cuh"
+
+namespace arb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                    // 32 fp32 = one 128-byte swizzle row
+constexpr int UMMA_K = 8;                      // kind::tf32: 8 elements (32 bytes) per instruction
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  int M, N, K;
+  int nb2;
+  int a_b2, a_b3, b_b2, b_b3, c_b2, c_b3;
+  int flags;
+  int kb_per_split;   // k-blocks per split (split-K), or total k-blocks
+  float alpha;
+  const float* bias;
+  float* atomic_out;
+  long long atomic_ld;
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGING_BYTES = BLOCK_M * BLOCK_N * 4;
+  static constexpr int stages() { return BLOCK_N <= 64 ? 4 : 3; }
+  static constexpr int total() { return stages() * STAGE_BYTES + STAGING_BYTES + 256 + BLOCK_N * 4 + 1024; }
+};
+
+template <int BLOCK_N, int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const __grid_constant__ CUtensorMap tmC,
+                                                                 const __grid_constant__ CUtensorMap tmAux,
+                                                                 const GemmParams p) {
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int STAGES = L::stages();
+  constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr int N_SLABS = BLOCK_N / 32;
+
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * L::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + L::STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* aux_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 1);
+  float* bias_s = reinterpret_cast<float*>(staging + L::STAGING_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
+  const bool split = (p.flags & EPI_ATOMIC) != 0;
+  const int b2 = split ? 0 : int(blockIdx.z) % p.nb2, b3 = split ? 0 : int(blockIdx.z) / p.nb2;
+  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_begin = split ? int(blockIdx.z) * p.kb_per_split : 0;
+  const int kb_end = split ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
+  const int nkb = kb_end - kb_begin;
+  const bool has_aux = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    if (!split) ptx::prefetch_tmap(&tmC);
+    if (has_aux) ptx::prefetch_tmap(&tmAux);
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::mbar_init(aux_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (has_aux) {
+        ptx::mbar_expect_tx(aux_bar, L::STAGING_BYTES);
+        for (int c = 0; c < N_SLABS; ++c)
+          ptx::tma_load_4d(staging + c * (BLOCK_M * 128), &tmAux, aux_bar, n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
+      }
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, round = i / STAGES;
+        if (round > 0) ptx::mbar_wait(&empty_bar[s], (round - 1) & 1);
+        uint8_t* a_s = smem + s * L::STAGE_BYTES;
+        uint8_t* b_s = a_s + A_STAGE_BYTES;
+        const int k0 = (kb_begin + i) * BLOCK_K;
+        ptx::mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        if (A_MN) {
+          for (int c = 0; c < BLOCK_M / 32; ++c)
+            ptx::tma_load_4d(a_s + c * 4096, &tmA, &full_bar[s], m0 + 32 * c, k0, b2 * p.a_b2, b3 * p.a_b3);
+        } else {
+          ptx::tma_load_4d(a_s, &tmA, &full_bar[s], k0, m0, b2 * p.a_b2, b3 * p.a_b3);
+        }
+        if (B_MN) {
+          for (int c = 0; c < N_SLABS; ++c)
+            ptx::tma_load_4d(b_s + c * 4096, &tmB, &full_bar[s], n0 + 32 * c, k0, b2 * p.b_b2, b3 * p.b_b3);
+        } else {
+          ptx::tma_load_4d(b_s, &tmB, &full_bar[s], k0, n0, b2 * p.b_b2, b3 * p.b_b3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_tf32(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, round = i / STAGES;
+        ptx::mbar_wait(&full_bar[s], round & 1);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); advance 32 B per K step inside the swizzle row
+          // MN-major: 32-wide slabs of [32 k-rows x 128 B] 4096 B apart (LBO); swizzle atom = 4 k-rows (512 B, SBO);
+          //           8 k-rows (1024 B) per K step
+          const uint64_t da = A_MN ? ptx::smem_desc_sw128<1>(a_addr + k * 1024, 4096, 512)
+                                   : ptx::smem_desc_sw128<2>(a_addr + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? ptx::smem_desc_sw128<1>(b_addr + k * 1024, 4096, 512)
+                                   : ptx::smem_desc_sw128<2>(b_addr + k * 32, 16, 1024);
+          ptx::mma_tf32_ss(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(&empty_bar[s]);     // frees the stage when these MMAs have read it
+      }
+      ptx::mma_commit(tmem_full_bar);       // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = 32 * q + lane;          // row of the tile owned by this thread
+    const int et = threadIdx.x - 64;        // 0..127
+    if (p.flags & EPI_BIAS) {
+      for (int j = et; j < BLOCK_N; j += 128) bias_s[j] = (n0 + j < p.N) ? p.bias[n0 + j] : 0.0f;
+    }
+    ptx::named_bar_sync(1, 128);
+    if (nkb > 0) {
+      ptx::mbar_wait(tmem_full_bar, 0);
+      ptx::tc_fence_after();
+    }
+    if (has_aux) ptx::mbar_wait(aux_bar, 0);
+#pragma unroll 1
+    for (int c = 0; c < N_SLABS; ++c) {
+      uint32_t v[32];
+      if (nkb > 0) {
+        ptx::tmem_ld_32x32(tmem_base + (uint32_t(32 * q) << 16) + uint32_t(32 * c), v);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
+#pragma unroll
+      for (int piece = 0; piece < 8; ++piece) {
+        float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = piece * 4 + e;
+          float x = __uint_as_float(v[j]) * p.alpha;
+          if (p.flags & EPI_BIAS) x += bias_s[32 * c + j];
+          if (p.flags & EPI_RELU) x = fmaxf(x, 0.0f);
+          o[e] = x;
+        }
+        if (has_aux) {
+          const float4 a = *dst;
+          if (p.flags & EPI_ADD_AUX) { o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w; }
+          if (p.flags & EPI_MASK_AUX) {
+            o[0] = a.x > 0.f ? o[0] : 0.f; o[1] = a.y > 0.f ? o[1] : 0.f;
+            o[2] = a.z > 0.f ? o[2] : 0.f; o[3] = a.w > 0.f ? o[3] : 0.f;
+          }
+        }
+        if (split) {
+          const int gm = m0 + row;
+          if (gm < p.M) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int gn = n0 + 32 * c + piece * 4 + e;
+              if (gn < p.N) atomicAdd(p.atomic_out + (long long)gm * p.atomic_ld + gn, o[e]);
+            }
+          }
+        } else {
+          *dst = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    if (!split) {
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(1, 128);
+      if (et == 0) {
+        for (int c = 0; c < N_SLABS; ++c)
+          ptx::tma_store_4d(&tmC, staging + c * (BLOCK_M * 128), n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_all();
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int g_round_on_load = 0;
+void set_tf32_round_on_load(int enable) { g_round_on_load = enable; }
+
+int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { arb_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ARB_E_CUDA; }
+  cuuint64_t gdim[4], gstride[3];
+  cuuint32_t bx[4], estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) { gdim[i] = cuuint64_t(t.dim[i] > 0 ? t.dim[i] : 1); bx[i] = box.b[i]; }
+  for (int i = 1; i < 4; ++i) {
+    // a broadcast / unused dimension (extent 1) still needs a legal (multiple of 16 B) stride
+    int64_t s = t.stride[i];
+    if (gdim[i] == 1 && (s <= 0 || (s * 4) % 16 != 0)) s = int64_t(gdim[0]) * 4 >= 16 ? ((int64_t(gdim[0]) + 3) / 4) * 4 : 4;
+    gstride[i - 1] = cuuint64_t(s) * 4;
+    if (gstride[i - 1] % 16 != 0) { arb_set_error("tensor map: strides must be multiples of 16 bytes"); return ARB_E_INVALID_ARG; }
+  }
+  if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) { arb_set_error("tensor map: base must be 16-byte aligned"); return ARB_E_INVALID_ARG; }
+  for (int i = 0; i < 4; ++i) if (bx[i] > gdim[i] && i > 0) bx[i] = bx[i];   // boxes may exceed the extent (OOB fill)
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t.ptr),
+                   gdim, gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[256];
+    std::snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d): dim=(%llu,%llu,%llu,%llu) box=(%u,%u,%u,%u)", int(r),
+                  (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+                  (unsigned long long)gdim[3], bx[0], bx[1], bx[2], bx[3]);
+    arb_set_error(msg);
+    return ARB_E_CUDA;
+  }
+  return ARB_OK;
+}
+
+template <int BLOCK_N, int A_MN, int B_MN>
+static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
+                    const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
+  constexpr int smem = SmemLayout<BLOCK_N>::total();
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      arb_set_error("gemm_tf32: cannot raise the dynamic shared memory limit");
+      return ARB_E_CUDA;
+    }
+    configured = true;
+  }
+  kern<<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tX, p);
+  arb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { arb_set_error(cudaGetErrorString(e)); return ARB_E_CUDA; }
+  return ARB_OK;
+}
+
+int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
+  if (d.M <= 0 || d.N <= 0 || d.K < 0) { arb_set_error("gemm_tf32: bad shape"); return ARB_E_INVALID_ARG; }
+  if (d.block_n != 32 && d.block_n != 64 && d.block_n != 128) { arb_set_error("gemm_tf32: block_n must be 32/64/128"); return ARB_E_INVALID_ARG; }
+  const bool split = (d.flags & EPI_ATOMIC) != 0;
+  if (split && (d.nb2 != 1 || d.nb3 != 1 || !d.atomic_out)) { arb_set_error("gemm_tf32: split-K needs an unbatched problem and atomic_out"); return ARB_E_INVALID_ARG; }
+  if (!split && d.split_k != 1) { arb_set_error("gemm_tf32: split_k > 1 needs EPI_ATOMIC"); return ARB_E_INVALID_ARG; }
+  alignas(64) CUtensorMap tA, tB, tC, tX;
+  int rc;
+  if ((rc = make_tmap_4d(&tA, d.A, d.a_mn ? TmapBox{{32, 32, 1, 1}} : TmapBox{{32, 128, 1, 1}}, d.a_mn))) return rc;
+  if ((rc = make_tmap_4d(&tB, d.B, d.b_mn ? TmapBox{{32, 32, 1, 1}} : TmapBox{{32, uint32_t(d.block_n), 1, 1}}, d.b_mn))) return rc;
+  if (!split) {
+    if ((rc = make_tmap_4d(&tC, d.C, TmapBox{{32, 128, 1, 1}}, 0))) return rc;
+  } else {
+    tC = tA;
+  }
+  if (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) {
+    if ((rc = make_tmap_4d(&tX, d.Aux, TmapBox{{32, 128, 1, 1}}, 0))) return rc;
+  } else {
+    tX = tA;
+  }
+  const int total_kb = (d.K + BLOCK_K - 1) / BLOCK_K;
+  const int splits = split ? std::max(1, std::min(d.split_k, total_kb)) : 1;
+  GemmParams p;
+  p.M = d.M; p.N = d.N; p.K = d.K; p.nb2 = d.nb2;
+  p.a_b2 = d.a_b2; p.a_b3 = d.a_b3; p.b_b2 = d.b_b2; p.b_b3 = d.b_b3; p.c_b2 = d.c_b2; p.c_b3 = d.c_b3;
+  p.flags = d.flags; p.alpha = d.alpha; p.bias = d.bias; p.atomic_out = d.atomic_out; p.atomic_ld = d.atomic_ld;
+  p.kb_per_split = (total_kb + splits - 1) / splits;
+  const int eff_splits = split ? (total_kb + p.kb_per_split - 1) / std::max(1, p.kb_per_split) : 1;
+  dim3 grid((d.N + d.block_n - 1) / d.block_n, (d.M + BLOCK_M - 1) / BLOCK_M, split ? std::max(1, eff_splits) : d.nb2 * d.nb3);
+#define ARB_GEMM_CASE(BN, AM, BM) \
+  if (d.block_n == BN && d.a_mn == AM && d.b_mn == BM) return launch_t<BN, AM, BM>(d, tA, tB, tC, tX, p, grid, st);
+  ARB_GEMM_CASE(32, 0, 0) ARB_GEMM_CASE(32, 0, 1) ARB_GEMM_CASE(32, 1, 0) ARB_GEMM_CASE(32, 1, 1)
+  ARB_GEMM_CASE(64, 0, 0) ARB_GEMM_CASE(64, 0, 1) ARB_GEMM_CASE(64, 1, 0) ARB_GEMM_CASE(64, 1, 1)
+  ARB_GEMM_CASE(128, 0, 0) ARB_GEMM_CASE(128, 0, 1) ARB_GEMM_CASE(128, 1, 0) ARB_GEMM_CASE(128, 1, 1)
+#undef ARB_GEMM_CASE
+  arb_set_error("gemm_tf32: unsupported configuration");
+  return ARB_E_UNSUPPORTED;
+}
+
+}  // namespace arb
+
+// ------------------------------------------------------------------------------------------------ C ABI (unit-test / building-block entry)
+// C[b][M,N] = epilogue(alpha * A[b] op B[b]) on plain row-major fp32 matrices.
+//   a_mn = 0: A is [M,K] row-major;  a_mn = 1: A is stored transposed, [K,M] row-major.
+//   b_mn = 0: B is [N,K] row-major (an nn.Linear weight);  b_mn = 1: B is [K,N] row-major.
+//   batch > 1: operands are `batch` consecutive matrices (stride = rows*cols), unless the stride argument is 0.
+extern "C" int32_t arb_gemm_tf32(const float* A, const float* B, float* C, const float* aux, const float* bias,
+                                 int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t batch,
+                                 int64_t a_bstride, int64_t b_bstride, int64_t c_bstride, int32_t block_n,
+                                 int32_t flags, float alpha, int32_t split_k, void* stream) {
+  using namespace arb;
+  if (!A || !B || !C) { arb_set_error("arb_gemm_tf32: null pointer"); return ARB_E_INVALID_ARG; }
+  GemmDesc d;
+  d.M = M; d.N = N; d.K = K; d.a_mn = a_mn; d.b_mn = b_mn; d.block_n = block_n; d.flags = flags; d.alpha = alpha;
+  d.bias = bias; d.nb2 = batch; d.nb3 = 1; d.split_k = split_k;
+  d.a_b2 = a_bstride != 0; d.b_b2 = b_bstride != 0; d.c_b2 = c_bstride != 0;
+  auto mat = [](const float* p, int64_t inner, int64_t rows, int64_t nb, int64_t bstride) {
+    TRef t; t.ptr = p; t.dim[0] = inner; t.dim[1] = rows; t.dim[2] = bstride ? nb : 1; t.dim[3] = 1;
+    t.stride[0] = 1; t.stride[1] = inner; t.stride[2] = bstride; t.stride[3] = 0; return t;
+  };
+  d.A = a_mn ? mat(A, M, K, batch, a_bstride) : mat(A, K, M, batch, a_bstride);
+  d.B = b_mn ? mat(B, N, K, batch, b_bstride) : mat(B, K, N, batch, b_bstride);
+  d.C = mat(C, N, M, batch, c_bstride);
+  if (aux) d.Aux = mat(aux, N, M, batch, c_bstride);
+  if (flags & EPI_ATOMIC) { d.atomic_out = C; d.atomic_ld = N; }
+  return launch_gemm_tf32(d, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,48 @@
+// Host-side description of one (batched) TF32 tensor-core GEMM launch.  See gemm_tf32.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace arb {
+
+// A strided view of up to 4 dimensions, dim[0] contiguous (stride[0] == 1), strides in elements.
+struct TRef {
+  const float* ptr = nullptr;
+  int64_t dim[4] = {1, 1, 1, 1};
+  int64_t stride[4] = {1, 0, 0, 0};
+};
+
+enum : int {
+  EPI_BIAS = 1,       // + bias[n]
+  EPI_RELU = 2,       // max(., 0)
+  EPI_ADD_AUX = 4,    // + Aux[m,n]          (residual; Aux may alias C)
+  EPI_MASK_AUX = 8,   // . * (Aux[m,n] > 0)  (ReLU backward)
+  EPI_ATOMIC = 16,    // red.add into atomic_out instead of storing C (split-K weight gradients)
+};
+
+struct GemmDesc {
+  int M = 0, N = 0, K = 0;      // C[M,N] = alpha * sum_k A[m,k] B[n,k]
+  int a_mn = 0, b_mn = 0;       // 0: operand stored K-contiguous ("K-major"); 1: stored M/N-contiguous ("MN-major")
+  TRef A, B, C, Aux;            // K-major operand: dim = (K, rows, b2, b3); MN-major: dim = (rows, K, b2, b3);
+                                // C/Aux: dim = (N, M, b2, b3)
+  int nb2 = 1, nb3 = 1;         // batch grid: blockIdx.z = b3 * nb2 + b2
+  int a_b2 = 0, a_b3 = 0, b_b2 = 0, b_b3 = 0, c_b2 = 0, c_b3 = 0;   // does the operand move with b2 / b3 ?
+  int block_n = 64;             // 32, 64 or 128 output columns per CTA
+  int split_k = 1;              // >1 only with EPI_ATOMIC and nb2 == nb3 == 1
+  int flags = 0;
+  float alpha = 1.0f;
+  const float* bias = nullptr;  // [N]
+  float* atomic_out = nullptr;  // row-major [M, atomic_ld]
+  int64_t atomic_ld = 0;
+};
+
+int launch_gemm_tf32(const GemmDesc& d, cudaStream_t stream);   // 0 or ARB_E_*
+
+// 4-D tiled tensor map with 128-byte swizzle over fp32 data; box[0] must be 32 (=128 bytes).
+struct TmapBox { uint32_t b[4]; };
+// atom32 = 0: SWIZZLE_128B (16-byte chunks); 1: SWIZZLE_128B_ATOM_32B (MN-major tf32 operands)
+int make_tmap_4d(void* out_CUtensorMap, const TRef& t, TmapBox box, int atom32);
+
+void set_tf32_round_on_load(int enable);
+
+}  // namespace arb
