@@ -249,10 +249,12 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int g_round_on_load = 0;
+// MMA operands are loaded through TFLOAT32 tensor maps: the TMA unit rounds fp32 -> tf32 (instead of the tensor
+// core truncating the mantissa), which removes the systematic bias truncation puts on gradients.
+static int g_round_on_load = 1;
 void set_tf32_round_on_load(int enable) { g_round_on_load = enable; }
 
-int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32) {
+int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32, int as_tf32) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { arb_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ARB_E_CUDA; }
   cuuint64_t gdim[4], gstride[3];
@@ -267,7 +269,8 @@ int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32) {
   }
   if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) { arb_set_error("tensor map: base must be 16-byte aligned"); return ARB_E_INVALID_ARG; }
   for (int i = 0; i < 4; ++i) if (bx[i] > gdim[i] && i > 0) bx[i] = bx[i];   // boxes may exceed the extent (OOB fill)
-  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t.ptr),
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out),
+                   (as_tf32 && g_round_on_load) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t.ptr),
                    gdim, gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -310,15 +313,15 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
   if (!split && d.split_k != 1) { arb_set_error("gemm_tf32: split_k > 1 needs EPI_ATOMIC"); return ARB_E_INVALID_ARG; }
   alignas(64) CUtensorMap tA, tB, tC, tX;
   int rc;
-  if ((rc = make_tmap_4d(&tA, d.A, d.a_mn ? TmapBox{{32, 32, 1, 1}} : TmapBox{{32, 128, 1, 1}}, d.a_mn))) return rc;
-  if ((rc = make_tmap_4d(&tB, d.B, d.b_mn ? TmapBox{{32, 32, 1, 1}} : TmapBox{{32, uint32_t(d.block_n), 1, 1}}, d.b_mn))) return rc;
+  if ((rc = make_tmap_4d(&tA, d.A, d.a_mn ? TmapBox{{32, 32, 1, 1}} : TmapBox{{32, 128, 1, 1}}, d.a_mn, 1))) return rc;
+  if ((rc = make_tmap_4d(&tB, d.B, d.b_mn ? TmapBox{{32, 32, 1, 1}} : TmapBox{{32, uint32_t(d.block_n), 1, 1}}, d.b_mn, 1))) return rc;
   if (!split) {
-    if ((rc = make_tmap_4d(&tC, d.C, TmapBox{{32, 128, 1, 1}}, 0))) return rc;
+    if ((rc = make_tmap_4d(&tC, d.C, TmapBox{{32, 128, 1, 1}}, 0, 0))) return rc;
   } else {
     tC = tA;
   }
   if (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) {
-    if ((rc = make_tmap_4d(&tX, d.Aux, TmapBox{{32, 128, 1, 1}}, 0))) return rc;
+    if ((rc = make_tmap_4d(&tX, d.Aux, TmapBox{{32, 128, 1, 1}}, 0, 0))) return rc;
   } else {
     tX = tA;
   }
@@ -348,6 +351,8 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
 //   a_mn = 0: A is [M,K] row-major;  a_mn = 1: A is stored transposed, [K,M] row-major.
 //   b_mn = 0: B is [N,K] row-major (an nn.Linear weight);  b_mn = 1: B is [K,N] row-major.
 //   batch > 1: operands are `batch` consecutive matrices (stride = rows*cols), unless the stride argument is 0.
+extern "C" void arb_set_tf32_round_on_load(int32_t enable) { arb::set_tf32_round_on_load(enable); }
+
 extern "C" int32_t arb_gemm_tf32(const float* A, const float* B, float* C, const float* aux, const float* bias,
                                  int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t batch,
                                  int64_t a_bstride, int64_t b_bstride, int64_t c_bstride, int32_t block_n,

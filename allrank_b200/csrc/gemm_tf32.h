@@ -41,7 +41,8 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t stream);   // 0 or ARB_E_*
 // 4-D tiled tensor map with 128-byte swizzle over fp32 data; box[0] must be 32 (=128 bytes).
 struct TmapBox { uint32_t b[4]; };
 // atom32 = 0: SWIZZLE_128B (16-byte chunks); 1: SWIZZLE_128B_ATOM_32B (MN-major tf32 operands)
-int make_tmap_4d(void* out_CUtensorMap, const TRef& t, TmapBox box, int atom32);
+// as_tf32 = 1: MMA operand (TFLOAT32 map, rounded on load when enabled); 0: plain fp32 (stores, epilogue tiles)
+int make_tmap_4d(void* out_CUtensorMap, const TRef& t, TmapBox box, int atom32, int as_tf32);
 
 void set_tf32_round_on_load(int enable);
 

@@ -1,0 +1,392 @@
+// Scorer orchestration: LTRModel forward and backward as a fixed sequence of kernel launches on one stream.
+//
+//   forward : x -> FC -> N x [ LN -> QKV -> (Q K^T / sqrt(dk), key mask, softmax, P V) -> O + residual
+//                               -> LN -> W1 + ReLU -> W2 + residual ] -> LN -> head
+//   backward: the exact reverse, parameter gradients accumulated into a flat buffer.
+//
+// Reference: allrank/models/model.py:62-92 (LTRModel), allrank/models/transformer.py:43-56,126-134,178-203,227.
+// Every contraction is a launch of the tcgen05 TF32 GEMM (gemm_tf32.cu) -- per-head attention products are
+// batched launches over 4-D tensor maps (head and slate are TMA coordinates, so no transposes/copies exist:
+// the reference's `transpose(1,2).contiguous()` at transformer.py:201 vanishes).  The host sequence contains no
+// synchronisation and no allocation, so a training step can be captured into a CUDA graph by the host layer.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "common.h"
+#include "gemm_tf32.h"
+#include "scorer_kernels.h"
+
+namespace arb {
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct ParamLayout {
+  int64_t fc_w, fc_b;
+  struct Layer { int64_t wqkv, bqkv, wo, bo, w1, b1, w2, b2, ln1_a, ln1_b, ln2_a, ln2_b; };
+  Layer layer[64];
+  int64_t lnf_a, lnf_b, head_w, head_b, total;
+};
+
+static int make_param_layout(const arb_scorer_config& c, ParamLayout& L) {
+  if (c.n_layers < 0 || c.n_layers > 64) { arb_set_error("scorer: n_layers must be in [0,64]"); return ARB_E_UNSUPPORTED; }
+  if (c.d_model <= 0 || c.d_model % 4 || c.n_features <= 0 || c.n_features % 4) {
+    arb_set_error("scorer: d_model and (padded) n_features must be positive multiples of 4");
+    return ARB_E_UNSUPPORTED;
+  }
+  if (c.n_layers > 0) {
+    if (c.n_heads <= 0 || c.d_model % c.n_heads || (c.d_model / c.n_heads) % 4 || c.d_ff <= 0 || c.d_ff % 4) {
+      arb_set_error("scorer: need d_model % h == 0, (d_model/h) % 4 == 0 and d_ff % 4 == 0");
+      return ARB_E_UNSUPPORTED;
+    }
+    if (c.d_model / c.n_heads > 128) { arb_set_error("scorer: head width above 128 is not supported"); return ARB_E_UNSUPPORTED; }
+  }
+  if (c.d_model > 1024) { arb_set_error("scorer: d_model above 1024 is not supported"); return ARB_E_UNSUPPORTED; }
+  const int64_t d = c.d_model, F = c.n_features, f = c.d_ff;
+  int64_t o = 0;
+  L.fc_w = o; o += d * F;
+  L.fc_b = o; o += d;
+  for (int l = 0; l < c.n_layers; ++l) {
+    auto& y = L.layer[l];
+    y.wqkv = o; o += 3 * d * d;
+    y.bqkv = o; o += 3 * d;
+    y.wo = o; o += d * d;
+    y.bo = o; o += d;
+    y.w1 = o; o += f * d;
+    y.b1 = o; o += f;
+    y.w2 = o; o += d * f;
+    y.b2 = o; o += d;
+    y.ln1_a = o; o += d;
+    y.ln1_b = o; o += d;
+    y.ln2_a = o; o += d;
+    y.ln2_b = o; o += d;
+  }
+  if (c.n_layers > 0) { L.lnf_a = o; o += d; L.lnf_b = o; o += d; } else { L.lnf_a = L.lnf_b = -1; }
+  L.head_w = o; o += d;
+  L.head_b = o; o += 1;
+  L.total = o;
+  return ARB_OK;
+}
+
+struct WsLayout {
+  int64_t x0;
+  struct Layer { int64_t xn1, mean1, std1, qkv, prob, ctx, xmid, xn2, mean2, std2, hdn, xout; };
+  Layer layer[64];
+  int64_t meanf, stdf, total;
+  int Sp;
+};
+
+static void make_ws_layout(const arb_scorer_config& c, int B, int S, int training, WsLayout& W) {
+  const int64_t R = int64_t(B) * S, d = c.d_model, f = c.d_ff, h = c.n_heads;
+  W.Sp = int(align_up(S, 4));
+  int64_t o = 0;
+  auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
+  W.x0 = take(R * d);
+  WsLayout::Layer shared{};
+  for (int l = 0; l < c.n_layers; ++l) {
+    auto& y = W.layer[l];
+    if (training || l == 0) {
+      y.xn1 = take(R * d); y.mean1 = take(R); y.std1 = take(R);
+      y.qkv = take(R * 3 * d);
+      y.prob = take(int64_t(B) * h * S * W.Sp);
+      y.ctx = take(R * d);
+      y.xn2 = training ? take(R * d) : y.xn1;
+      y.mean2 = training ? take(R) : y.mean1;
+      y.std2 = training ? take(R) : y.std1;
+      y.hdn = take(R * f);
+      y.xmid = training ? take(R * d) : W.x0;    // eval: the residual stream is updated in place
+      y.xout = training ? take(R * d) : W.x0;
+      shared = y;
+    } else {
+      y = shared;
+    }
+  }
+  W.meanf = take(R);
+  W.stdf = take(R);
+  W.total = o;
+}
+
+struct Ctx {
+  const arb_scorer_config& c;
+  int B, S;
+  int64_t R;
+  cudaStream_t st;
+};
+
+// ---- GEMM helpers ------------------------------------------------------------------------------
+static TRef rows_view(const float* p, int64_t inner, int64_t rows, int64_t pitch) {
+  TRef t; t.ptr = p; t.dim[0] = inner; t.dim[1] = rows; t.stride[0] = 1; t.stride[1] = pitch; return t;
+}
+static int pick_block_n(int n) { return n <= 32 ? 32 : 64; }
+
+// Y[R,out] = epi( X[R,in] W[out,in]^T + bias )
+static int linear_fwd(const Ctx& k, const float* X, int64_t x_pitch, int in, const float* Wt, const float* bias, int out,
+                      float* Y, int64_t y_pitch, int flags, const float* aux, int64_t aux_pitch) {
+  GemmDesc g;
+  g.M = int(k.R); g.N = out; g.K = in;
+  g.A = rows_view(X, in, k.R, x_pitch);
+  g.B = rows_view(Wt, in, out, in);
+  g.C = rows_view(Y, out, k.R, y_pitch);
+  if (aux) g.Aux = rows_view(aux, out, k.R, aux_pitch);
+  g.bias = bias; g.flags = flags | (bias ? EPI_BIAS : 0);
+  g.block_n = pick_block_n(out);
+  return launch_gemm_tf32(g, k.st);
+}
+// dX[R,in] = epi( dY[R,out] W[out,in] )      (W read as an MN-major B operand)
+static int linear_bwd_input(const Ctx& k, const float* dY, int64_t dy_pitch, int out, const float* Wt, int in, float* dX,
+                            int64_t dx_pitch, int flags, const float* aux, int64_t aux_pitch) {
+  GemmDesc g;
+  g.M = int(k.R); g.N = in; g.K = out; g.b_mn = 1;
+  g.A = rows_view(dY, out, k.R, dy_pitch);
+  g.B = rows_view(Wt, in, out, in);          // dim0 = in (N, contiguous), dim1 = out (K)
+  g.C = rows_view(dX, in, k.R, dx_pitch);
+  if (aux) g.Aux = rows_view(aux, in, k.R, aux_pitch);
+  g.flags = flags;
+  g.block_n = pick_block_n(in);
+  return launch_gemm_tf32(g, k.st);
+}
+// dW[out,in] += dY[R,out]^T X[R,in]          (both operands MN-major, reduction over all rows, split-K)
+static int linear_bwd_weight(const Ctx& k, const float* dY, int64_t dy_pitch, int out, const float* X, int64_t x_pitch,
+                             int in, float* dW) {
+  GemmDesc g;
+  g.M = out; g.N = in; g.K = int(k.R); g.a_mn = 1; g.b_mn = 1;
+  g.A = rows_view(dY, out, k.R, dy_pitch);
+  g.B = rows_view(X, in, k.R, x_pitch);
+  g.flags = EPI_ATOMIC; g.atomic_out = dW; g.atomic_ld = in;
+  g.block_n = pick_block_n(in);
+  const int tiles = ((out + 127) / 128) * ((in + g.block_n - 1) / g.block_n);
+  const int kb = int((k.R + 31) / 32);
+  g.split_k = std::max(1, std::min(kb / 4 + 1, (148 * 3 + tiles - 1) / tiles));
+  return launch_gemm_tf32(g, k.st);
+}
+
+// per-head strided view of a [R, pitch] activation: dims (dk, S, h, B)
+static TRef head_view(const float* p, int dk, int S, int h, int B, int64_t pitch) {
+  TRef t; t.ptr = p;
+  t.dim[0] = dk; t.dim[1] = S; t.dim[2] = h; t.dim[3] = B;
+  t.stride[0] = 1; t.stride[1] = pitch; t.stride[2] = dk; t.stride[3] = int64_t(S) * pitch;
+  return t;
+}
+// [B,h,S,Sp] probability / logit buffers: dims (S, S, h, B)
+static TRef prob_view(const float* p, int S, int Sp, int h, int B) {
+  TRef t; t.ptr = p;
+  t.dim[0] = S; t.dim[1] = S; t.dim[2] = h; t.dim[3] = B;
+  t.stride[0] = 1; t.stride[1] = Sp; t.stride[2] = int64_t(S) * Sp; t.stride[3] = int64_t(h) * S * Sp;
+  return t;
+}
+static void batch_all(GemmDesc& g, int h, int B) {
+  g.nb2 = h; g.nb3 = B;
+  g.a_b2 = g.a_b3 = g.b_b2 = g.b_b3 = g.c_b2 = g.c_b3 = 1;
+}
+
+#define ARB_TRY(expr) do { int rc__ = (expr); if (rc__ != ARB_OK) return rc__; } while (0)
+
+static int forward_impl(const arb_scorer_config& c, const float* P, const float* x, const uint8_t* mask, int B, int S,
+                        float* scores, float* ws, int64_t ws_floats, int training, cudaStream_t st) {
+  ParamLayout L;
+  ARB_TRY(make_param_layout(c, L));
+  WsLayout W;
+  make_ws_layout(c, B, S, training, W);
+  if (ws_floats < W.total) { arb_set_error("arb_scorer_forward: workspace too small"); return ARB_E_WORKSPACE; }
+  Ctx k{c, B, S, int64_t(B) * S, st};
+  const int d = c.d_model, F = c.n_features, f = c.d_ff, h = c.n_heads;
+  const int dk = c.n_layers > 0 ? d / h : 0;
+
+  float* xcur = ws + W.x0;
+  ARB_TRY(linear_fwd(k, x, F, F, P + L.fc_w, P + L.fc_b, d, xcur, d, 0, nullptr, 0));
+  for (int l = 0; l < c.n_layers; ++l) {
+    const auto& pl = L.layer[l];
+    const auto& wl = W.layer[l];
+    float* xn1 = ws + wl.xn1; float* qkv = ws + wl.qkv; float* prob = ws + wl.prob; float* ctx = ws + wl.ctx;
+    float* xmid = ws + wl.xmid; float* xn2 = ws + wl.xn2; float* hdn = ws + wl.hdn; float* xout = ws + wl.xout;
+    // ---- self-attention sublayer: x + O(attn(LN(x)))   (transformer.py:133, :105-106)
+    ARB_TRY(ln_forward(xcur, P + pl.ln1_a, P + pl.ln1_b, c.ln_eps, k.R, d, xn1, ws + wl.mean1, ws + wl.std1, st));
+    ARB_TRY(linear_fwd(k, xn1, d, d, P + pl.wqkv, P + pl.bqkv, 3 * d, qkv, 3 * d, 0, nullptr, 0));
+    {
+      GemmDesc g;   // logits = Q K^T / sqrt(dk)      (transformer.py:148)
+      g.M = S; g.N = S; g.K = dk; g.alpha = 1.0f / sqrtf(float(dk));
+      g.A = head_view(qkv, dk, S, h, B, 3 * d);
+      g.B = head_view(qkv + d, dk, S, h, B, 3 * d);
+      g.C = prob_view(prob, S, W.Sp, h, B);
+      batch_all(g, h, B); g.block_n = 64;
+      ARB_TRY(launch_gemm_tf32(g, st));
+    }
+    ARB_TRY(softmax_forward(prob, mask, B, h, S, W.Sp, st));   // key mask + softmax (transformer.py:150-153)
+    {
+      GemmDesc g;   // ctx = P V, written straight into the concatenated-heads layout (transformer.py:156, :201-202)
+      g.M = S; g.N = dk; g.K = S; g.b_mn = 1;
+      g.A = prob_view(prob, S, W.Sp, h, B);
+      g.B = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
+      g.C = head_view(ctx, dk, S, h, B, d);
+      batch_all(g, h, B); g.block_n = pick_block_n(dk);
+      ARB_TRY(launch_gemm_tf32(g, st));
+    }
+    ARB_TRY(linear_fwd(k, ctx, d, d, P + pl.wo, P + pl.bo, d, xmid, d, EPI_ADD_AUX, xcur, d));
+    // ---- feed-forward sublayer: x + W2 relu(W1 LN(x))   (transformer.py:134, :227)
+    ARB_TRY(ln_forward(xmid, P + pl.ln2_a, P + pl.ln2_b, c.ln_eps, k.R, d, xn2, ws + wl.mean2, ws + wl.std2, st));
+    ARB_TRY(linear_fwd(k, xn2, d, d, P + pl.w1, P + pl.b1, f, hdn, f, EPI_RELU, nullptr, 0));
+    ARB_TRY(linear_fwd(k, hdn, f, f, P + pl.w2, P + pl.b2, d, xout, d, EPI_ADD_AUX, xmid, d));
+    xcur = xout;
+  }
+  const int has_norm = c.n_layers > 0;
+  ARB_TRY(head_forward(xcur, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr, c.ln_eps, P + L.head_w,
+                       P + L.head_b, has_norm, c.out_act, k.R, d, scores, ws + W.meanf, ws + W.stdf, st));
+  return ARB_OK;
+}
+
+struct ScratchLayout { int64_t dxa, dxb, dxn, dqkv, dctx, dprob, total; };
+static void make_scratch_layout(const arb_scorer_config& c, int B, int S, ScratchLayout& Z) {
+  const int64_t R = int64_t(B) * S, d = c.d_model;
+  const int Sp = int(align_up(S, 4));
+  int64_t o = 0;
+  auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
+  Z.dxa = take(R * d); Z.dxb = take(R * d); Z.dxn = take(R * d);
+  if (c.n_layers > 0) {
+    Z.dqkv = take(R * 3 * d); Z.dctx = take(R * d); Z.dprob = take(int64_t(B) * c.n_heads * S * Sp);
+  } else {
+    Z.dqkv = Z.dctx = Z.dprob = 0;
+  }
+  Z.total = o;
+}
+
+static int backward_impl(const arb_scorer_config& c, const float* P, const float* x, const uint8_t* mask, int B, int S,
+                         const float* scores, const float* dscores, float* G, float* ws, int64_t ws_floats,
+                         float* scratch, int64_t scratch_floats, cudaStream_t st) {
+  ParamLayout L;
+  ARB_TRY(make_param_layout(c, L));
+  WsLayout W;
+  make_ws_layout(c, B, S, 1, W);
+  ScratchLayout Z;
+  make_scratch_layout(c, B, S, Z);
+  if (ws_floats < W.total) { arb_set_error("arb_scorer_backward: workspace too small"); return ARB_E_WORKSPACE; }
+  if (scratch_floats < Z.total) { arb_set_error("arb_scorer_backward: scratch too small"); return ARB_E_WORKSPACE; }
+  Ctx k{c, B, S, int64_t(B) * S, st};
+  const int d = c.d_model, F = c.n_features, f = c.d_ff, h = c.n_heads;
+  const int dk = c.n_layers > 0 ? d / h : 0;
+  const float alpha = c.n_layers > 0 ? 1.0f / sqrtf(float(dk)) : 1.0f;
+  float* dx = scratch + Z.dxa;      // gradient w.r.t. the residual stream at the current depth
+  float* dx_alt = scratch + Z.dxb;
+  float* dxn = scratch + Z.dxn;
+  float* dqkv = scratch + Z.dqkv;
+  float* dctx = scratch + Z.dctx;
+  float* dprob = scratch + Z.dprob;
+
+  const int has_norm = c.n_layers > 0;
+  const float* xlast = c.n_layers > 0 ? ws + W.layer[c.n_layers - 1].xout : ws + W.x0;
+  ARB_TRY(head_backward(dscores, scores, xlast, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr,
+                        ws + W.meanf, ws + W.stdf, c.ln_eps, P + L.head_w, P + L.head_b, has_norm, c.out_act, k.R, d, dx,
+                        has_norm ? G + L.lnf_a : nullptr, has_norm ? G + L.lnf_b : nullptr, G + L.head_w, G + L.head_b,
+                        st));
+  for (int l = c.n_layers - 1; l >= 0; --l) {
+    const auto& pl = L.layer[l];
+    const auto& wl = W.layer[l];
+    const float* xin = (l == 0) ? ws + W.x0 : ws + W.layer[l - 1].xout;
+    float* xn1 = ws + wl.xn1; float* qkv = ws + wl.qkv; float* prob = ws + wl.prob; float* ctx = ws + wl.ctx;
+    float* xmid = ws + wl.xmid; float* xn2 = ws + wl.xn2; float* hdn = ws + wl.hdn;
+    // ---- feed-forward sublayer backward:  xout = xmid + W2 relu(W1 xn2 + b1) + b2
+    ARB_TRY(linear_bwd_weight(k, dx, d, d, hdn, f, f, G + pl.w2));
+    ARB_TRY(colsum_accumulate(dx, k.R, d, d, G + pl.b2, st));
+    ARB_TRY(linear_bwd_input(k, dx, d, d, P + pl.w2, f, hdn, f, EPI_MASK_AUX, hdn, f));   // hdn <- d hdn (in place)
+    ARB_TRY(linear_bwd_weight(k, hdn, f, f, xn2, d, d, G + pl.w1));
+    ARB_TRY(colsum_accumulate(hdn, k.R, f, f, G + pl.b1, st));
+    ARB_TRY(linear_bwd_input(k, hdn, f, f, P + pl.w1, d, dxn, d, 0, nullptr, 0));
+    ARB_TRY(ln_backward(dxn, xmid, P + pl.ln2_a, ws + wl.mean2, ws + wl.std2, c.ln_eps, dx, k.R, d, dx_alt,
+                        G + pl.ln2_a, G + pl.ln2_b, st));
+    // dx_alt = d loss / d xmid
+    // ---- attention sublayer backward:  xmid = xin + Wo ctx + bo
+    ARB_TRY(linear_bwd_weight(k, dx_alt, d, d, ctx, d, d, G + pl.wo));
+    ARB_TRY(colsum_accumulate(dx_alt, k.R, d, d, G + pl.bo, st));
+    ARB_TRY(linear_bwd_input(k, dx_alt, d, d, P + pl.wo, d, dctx, d, 0, nullptr, 0));
+    {
+      GemmDesc g;   // dP = dctx V^T
+      g.M = S; g.N = S; g.K = dk;
+      g.A = head_view(dctx, dk, S, h, B, d);
+      g.B = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
+      g.C = prob_view(dprob, S, W.Sp, h, B);
+      batch_all(g, h, B); g.block_n = 64;
+      ARB_TRY(launch_gemm_tf32(g, st));
+    }
+    {
+      GemmDesc g;   // dV = P^T dctx     (P read as an MN-major A operand, dctx as an MN-major B operand)
+      g.M = S; g.N = dk; g.K = S; g.a_mn = 1; g.b_mn = 1;
+      g.A = prob_view(prob, S, W.Sp, h, B);
+      g.B = head_view(dctx, dk, S, h, B, d);
+      g.C = head_view(dqkv + 2 * d, dk, S, h, B, 3 * d);
+      batch_all(g, h, B); g.block_n = pick_block_n(dk);
+      ARB_TRY(launch_gemm_tf32(g, st));
+    }
+    ARB_TRY(softmax_backward(dprob, prob, int64_t(B) * h * S, S, W.Sp, st));   // dprob <- dS (pre-scale)
+    {
+      GemmDesc g;   // dQ = alpha dS K
+      g.M = S; g.N = dk; g.K = S; g.b_mn = 1; g.alpha = alpha;
+      g.A = prob_view(dprob, S, W.Sp, h, B);
+      g.B = head_view(qkv + d, dk, S, h, B, 3 * d);
+      g.C = head_view(dqkv, dk, S, h, B, 3 * d);
+      batch_all(g, h, B); g.block_n = pick_block_n(dk);
+      ARB_TRY(launch_gemm_tf32(g, st));
+    }
+    {
+      GemmDesc g;   // dK = alpha dS^T Q
+      g.M = S; g.N = dk; g.K = S; g.a_mn = 1; g.b_mn = 1; g.alpha = alpha;
+      g.A = prob_view(dprob, S, W.Sp, h, B);
+      g.B = head_view(qkv, dk, S, h, B, 3 * d);
+      g.C = head_view(dqkv + d, dk, S, h, B, 3 * d);
+      batch_all(g, h, B); g.block_n = pick_block_n(dk);
+      ARB_TRY(launch_gemm_tf32(g, st));
+    }
+    ARB_TRY(linear_bwd_weight(k, dqkv, 3 * d, 3 * d, xn1, d, d, G + pl.wqkv));
+    ARB_TRY(colsum_accumulate(dqkv, k.R, 3 * d, 3 * d, G + pl.bqkv, st));
+    ARB_TRY(linear_bwd_input(k, dqkv, 3 * d, 3 * d, P + pl.wqkv, d, dxn, d, 0, nullptr, 0));
+    ARB_TRY(ln_backward(dxn, xin, P + pl.ln1_a, ws + wl.mean1, ws + wl.std1, c.ln_eps, dx_alt, k.R, d, dx,
+                        G + pl.ln1_a, G + pl.ln1_b, st));
+    // dx = d loss / d xin
+  }
+  // ---- input FC backward (x is data: no input gradient)
+  ARB_TRY(linear_bwd_weight(k, dx, d, d, x, F, F, G + L.fc_w));
+  ARB_TRY(colsum_accumulate(dx, k.R, d, d, G + L.fc_b, st));
+  return ARB_OK;
+}
+
+}  // namespace arb
+
+using namespace arb;
+
+extern "C" int64_t arb_scorer_param_count(const arb_scorer_config* cfg) {
+  ParamLayout L;
+  if (!cfg || make_param_layout(*cfg, L) != ARB_OK) return -1;
+  return L.total;
+}
+extern "C" int64_t arb_scorer_workspace_floats(const arb_scorer_config* cfg, int32_t B, int32_t S, int32_t training) {
+  ParamLayout L;
+  if (!cfg || B <= 0 || S <= 0 || make_param_layout(*cfg, L) != ARB_OK) return -1;
+  WsLayout W;
+  make_ws_layout(*cfg, B, S, training, W);
+  return W.total;
+}
+extern "C" int64_t arb_scorer_backward_scratch_floats(const arb_scorer_config* cfg, int32_t B, int32_t S) {
+  ParamLayout L;
+  if (!cfg || B <= 0 || S <= 0 || make_param_layout(*cfg, L) != ARB_OK) return -1;
+  ScratchLayout Z;
+  make_scratch_layout(*cfg, B, S, Z);
+  return Z.total;
+}
+extern "C" int32_t arb_scorer_forward(const arb_scorer_config* cfg, const float* params, const float* x,
+                                      const uint8_t* mask, int32_t B, int32_t S, float* scores, float* workspace,
+                                      int64_t workspace_floats, int32_t training, void* stream) {
+  if (!cfg || !params || !x || !mask || !scores || !workspace || B <= 0 || S <= 0) {
+    arb_set_error("arb_scorer_forward: null pointer or bad shape");
+    return ARB_E_INVALID_ARG;
+  }
+  return forward_impl(*cfg, params, x, mask, B, S, scores, workspace, workspace_floats, training,
+                      static_cast<cudaStream_t>(stream));
+}
+extern "C" int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, const float* x,
+                                       const uint8_t* mask, int32_t B, int32_t S, const float* scores,
+                                       const float* d_scores, float* grads, float* workspace, int64_t workspace_floats,
+                                       float* scratch, int64_t scratch_floats, void* stream) {
+  if (!cfg || !params || !x || !mask || !scores || !d_scores || !grads || !workspace || !scratch || B <= 0 || S <= 0) {
+    arb_set_error("arb_scorer_backward: null pointer or bad shape");
+    return ARB_E_INVALID_ARG;
+  }
+  return backward_impl(*cfg, params, x, mask, B, S, scores, d_scores, grads, workspace, workspace_floats, scratch,
+                       scratch_floats, static_cast<cudaStream_t>(stream));
+}

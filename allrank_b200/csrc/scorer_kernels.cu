@@ -1,0 +1,503 @@
+// SIMT kernels of the scorer (everything that is not a tensor-core contraction):
+//   row LayerNorm forward / backward (the reference's custom LayerNorm: unbiased std, eps added to the std,
+//   allrank/models/transformer.py:59-81), key-masked row softmax forward / backward (transformer.py:148-153),
+//   bias-gradient column sums, final LayerNorm + linear head forward / backward (model.py:111-117).
+// All are one-warp-per-row, coalesced 128-bit accesses where the width allows, warp-shuffle reductions;
+// they are HBM-bound (DESIGN.md section 3 lists bytes per row).
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "block_utils.cuh"
+#include "common.h"
+#include "scorer_kernels.h"
+
+namespace arb {
+
+constexpr int ROWS_PER_BLOCK = 8;   // 8 warps
+constexpr int MAX_VEC = 8;          // width <= 32 * 4 * MAX_VEC/4 ... each lane holds up to 4*MAX_VEC/4 floats
+
+// Each lane owns columns lane*4 + 128*k .. +3 (float4), k < NV; width must be a multiple of 4 and <= 128*NV.
+template <int NV>
+struct RowRegs {
+  float4 v[NV];
+};
+
+template <int NV>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, int width, int lane, RowRegs<NV>& r) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + 128 * k;
+    r.v[k] = (c < width) ? *reinterpret_cast<const float4*>(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void store_row(float* __restrict__ p, int width, int lane, const RowRegs<NV>& r) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + 128 * k;
+    if (c < width) *reinterpret_cast<float4*>(p + c) = r.v[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm fwd
+// y = a * (x - mean) / (std_unbiased + eps) + b ; saves mean and std per row.
+template <int NV>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ a,
+                                                                    const float* __restrict__ b, float eps,
+                                                                    long long rows, int width,
+                                                                    float* __restrict__ y, float* __restrict__ mean_o,
+                                                                    float* __restrict__ std_o) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  RowRegs<NV> r, ga, gb;
+  load_row<NV>(x + row * width, width, lane, r);
+  load_row<NV>(a, width, lane, ga);
+  load_row<NV>(b, width, lane, gb);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) s += r.v[k].x + r.v[k].y + r.v[k].z + r.v[k].w;
+  const float mean = warp_sum(s) / float(width);
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + 128 * k;
+    if (c < width) {
+      const float d0 = r.v[k].x - mean, d1 = r.v[k].y - mean, d2 = r.v[k].z - mean, d3 = r.v[k].w - mean;
+      ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+  }
+  const float sd = sqrtf(warp_sum(ss) / float(width - 1));
+  const float denom = sd + eps;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    r.v[k].x = ga.v[k].x * (r.v[k].x - mean) / denom + gb.v[k].x;
+    r.v[k].y = ga.v[k].y * (r.v[k].y - mean) / denom + gb.v[k].y;
+    r.v[k].z = ga.v[k].z * (r.v[k].z - mean) / denom + gb.v[k].z;
+    r.v[k].w = ga.v[k].w * (r.v[k].w - mean) / denom + gb.v[k].w;
+  }
+  store_row<NV>(y + row * width, width, lane, r);
+  if (lane == 0) { mean_o[row] = mean; std_o[row] = sd; }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm bwd
+// dx = [dres +] r (dxh - mean(dxh)) - r^2 (sum_k dxh_k c_k) / ((d-1) std) * c,   dxh = dy * a, c = x - mean,
+// r = 1/(std+eps).   grad_a += sum_rows dy * xhat,  grad_b += sum_rows dy  (block partials -> atomicAdd).
+template <int NV>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float* __restrict__ dy,
+                                                                    const float* __restrict__ x,
+                                                                    const float* __restrict__ a,
+                                                                    const float* __restrict__ mean_i,
+                                                                    const float* __restrict__ std_i, float eps,
+                                                                    const float* __restrict__ dres, long long rows,
+                                                                    int width, int rows_per_warp,
+                                                                    float* __restrict__ dx, float* __restrict__ grad_a,
+                                                                    float* __restrict__ grad_b) {
+  __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  RowRegs<NV> ga, acc_a, acc_b;
+  load_row<NV>(a, width, lane, ga);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
+  for (int it = 0; it < rows_per_warp; ++it) {
+    const long long row = first + it;
+    if (row >= rows) break;
+    RowRegs<NV> g, xr;
+    load_row<NV>(dy + row * width, width, lane, g);
+    load_row<NV>(x + row * width, width, lane, xr);
+    const float mean = mean_i[row], sd = std_i[row];
+    const float r = 1.0f / (sd + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + 128 * k;
+      float* gv = &g.v[k].x;
+      float* xv = &xr.v[k].x;
+      const float* av = &ga.v[k].x;
+      float* aa = &acc_a.v[k].x;
+      float* ab = &acc_b.v[k].x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float cc = (c < width) ? xv[e] - mean : 0.f;
+        const float dyv = gv[e];
+        aa[e] += dyv * cc * r;     // dy * xhat
+        ab[e] += dyv;
+        const float dxh = dyv * av[e];
+        gv[e] = dxh;
+        xv[e] = cc;
+        s1 += dxh;
+        s2 += dxh * cc;
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    const float m1 = s1 / float(width);
+    const float coef = (sd > 0.f) ? r * r * s2 / (float(width - 1) * sd) : 0.f;
+    RowRegs<NV> res;
+    if (dres) load_row<NV>(dres + row * width, width, lane, res);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float* gv = &g.v[k].x;
+      const float* xv = &xr.v[k].x;
+      const float* rv = &res.v[k].x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float o = r * (gv[e] - m1) - coef * xv[e];
+        if (dres) o += rv[e];
+        gv[e] = o;
+      }
+    }
+    store_row<NV>(dx + row * width, width, lane, g);
+  }
+  // block-level reduction of the gain/bias gradients
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const RowRegs<NV>& src = pass == 0 ? acc_a : acc_b;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) *reinterpret_cast<float4*>(&sh[wid][lane * 4 + 128 * k]) = src.v[k];
+    __syncthreads();
+    float* dst = pass == 0 ? grad_a : grad_b;
+    for (int c = threadIdx.x; c < width; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < ROWS_PER_BLOCK; ++w) t += sh[w][c];
+      atomicAdd(dst + c, t);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ softmax fwd
+// In place on the attention logits [B, h, S, pitch]: key-masked row softmax (padded keys -> probability 0).
+// A slate whose keys are all padded yields NaN rows, as the reference does (quirk Q2).
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(float* __restrict__ sc, const uint8_t* __restrict__ mask,
+                                                          int B, int h, int S, int pitch) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long total = (long long)B * h * S;
+  if (row >= total) return;
+  const int b = int(row / ((long long)h * S));
+  float* p = sc + row * pitch;
+  const uint8_t* mk = mask + (long long)b * S;
+  constexpr int MAXE = 48;   // S <= 1536 in registers
+  float v[MAXE];
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int k = 0; k < MAXE; ++k) {
+    const int j = lane + 32 * k;
+    v[k] = -CUDART_INF_F;
+    if (j < S) {
+      v[k] = mk[j] ? -CUDART_INF_F : p[j];
+      mx = fmaxf(mx, v[k]);
+    }
+  }
+  mx = warp_max(mx);
+  float z = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXE; ++k) {
+    const int j = lane + 32 * k;
+    if (j < S) { v[k] = expf(v[k] - mx); z += v[k]; }
+  }
+  z = warp_sum(z);
+#pragma unroll
+  for (int k = 0; k < MAXE; ++k) {
+    const int j = lane + 32 * k;
+    if (j < S) p[j] = v[k] / z;
+  }
+}
+
+// In place on dP: dS = P * (dP - sum_j P_j dP_j)
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(float* __restrict__ dp, const float* __restrict__ prob,
+                                                          long long rows, int S, int pitch) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* g = dp + row * pitch;
+  const float* p = prob + row * pitch;
+  constexpr int MAXE = 48;
+  float pv[MAXE], gv[MAXE];
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXE; ++k) {
+    const int j = lane + 32 * k;
+    pv[k] = gv[k] = 0.f;
+    if (j < S) { pv[k] = p[j]; gv[k] = g[j]; t += pv[k] * gv[k]; }
+  }
+  t = warp_sum(t);
+#pragma unroll
+  for (int k = 0; k < MAXE; ++k) {
+    const int j = lane + 32 * k;
+    if (j < S) g[j] = pv[k] * (gv[k] - t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// out[c] += sum_rows in[row, c]   (bias gradients).  grid.x = row chunks, threads over columns.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, long long rows, int width,
+                                                     long long ld, int rows_per_block, float* __restrict__ out) {
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) acc += in[r * ld + c];
+    atomicAdd(out + c, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ head fwd
+// score = act( w . LN(x) + bias )  (final encoder LayerNorm fused; has_norm = 0 for FC-only models)
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == ARB_ACT_TANH) return tanhf(z);
+  if (act == ARB_ACT_SIGMOID) return 1.0f / (1.0f + expf(-z));
+  if (act == ARB_ACT_RELU) return fmaxf(z, 0.f);
+  return z;
+}
+__device__ __forceinline__ float act_bwd(float out, float z, int act) {
+  if (act == ARB_ACT_TANH) return 1.0f - out * out;
+  if (act == ARB_ACT_SIGMOID) return out * (1.0f - out);
+  if (act == ARB_ACT_RELU) return z > 0.f ? 1.0f : 0.0f;
+  return 1.0f;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const float* __restrict__ x,
+                                                                      const float* __restrict__ a,
+                                                                      const float* __restrict__ b, float eps,
+                                                                      const float* __restrict__ w,
+                                                                      const float* __restrict__ wb, int has_norm,
+                                                                      int act, long long rows, int width,
+                                                                      float* __restrict__ score,
+                                                                      float* __restrict__ mean_o,
+                                                                      float* __restrict__ std_o) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  RowRegs<NV> r, ga, gb, gw;
+  load_row<NV>(x + row * width, width, lane, r);
+  load_row<NV>(w, width, lane, gw);
+  float mean = 0.f, sd = 0.f;
+  if (has_norm) {
+    load_row<NV>(a, width, lane, ga);
+    load_row<NV>(b, width, lane, gb);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s += r.v[k].x + r.v[k].y + r.v[k].z + r.v[k].w;
+    mean = warp_sum(s) / float(width);
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + 128 * k;
+      if (c < width) {
+        const float d0 = r.v[k].x - mean, d1 = r.v[k].y - mean, d2 = r.v[k].z - mean, d3 = r.v[k].w - mean;
+        ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      }
+    }
+    sd = sqrtf(warp_sum(ss) / float(width - 1));
+    const float denom = sd + eps;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      r.v[k].x = ga.v[k].x * (r.v[k].x - mean) / denom + gb.v[k].x;
+      r.v[k].y = ga.v[k].y * (r.v[k].y - mean) / denom + gb.v[k].y;
+      r.v[k].z = ga.v[k].z * (r.v[k].z - mean) / denom + gb.v[k].z;
+      r.v[k].w = ga.v[k].w * (r.v[k].w - mean) / denom + gb.v[k].w;
+    }
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + 128 * k;
+    if (c < width) dot += r.v[k].x * gw.v[k].x + r.v[k].y * gw.v[k].y + r.v[k].z * gw.v[k].z + r.v[k].w * gw.v[k].w;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    score[row] = act_fwd(dot + wb[0], act);
+    if (has_norm && mean_o) { mean_o[row] = mean; std_o[row] = sd; }
+  }
+}
+
+// head backward: dz = dscore * act'(z);  d xf = dz * w;  grad_w += dz * xf;  grad_wb += dz;  then LayerNorm bwd.
+template <int NV>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
+    const float* __restrict__ dscore, const float* __restrict__ score, const float* __restrict__ x,
+    const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean_i,
+    const float* __restrict__ std_i, float eps, const float* __restrict__ w, const float* __restrict__ wb,
+    int has_norm, int act, long long rows, int width, int rows_per_warp, float* __restrict__ dx,
+    float* __restrict__ grad_a, float* __restrict__ grad_b, float* __restrict__ grad_w, float* __restrict__ grad_wb) {
+  __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
+  __shared__ float shb[ROWS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  RowRegs<NV> ga, gb, gw, acc_a, acc_b, acc_w;
+  load_row<NV>(w, width, lane, gw);
+  if (has_norm) { load_row<NV>(a, width, lane, ga); load_row<NV>(b, width, lane, gb); }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = acc_w.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc_wb = 0.f;
+  const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
+  for (int it = 0; it < rows_per_warp; ++it) {
+    const long long row = first + it;
+    if (row >= rows) break;
+    RowRegs<NV> xr, g;
+    load_row<NV>(x + row * width, width, lane, xr);
+    const float out = score[row];
+    float z = 0.f;
+    if (act == ARB_ACT_RELU) z = out;   // relu: out > 0 <=> z > 0
+    const float dz = dscore[row] * act_bwd(out, z, act);
+    if (lane == 0) acc_wb += dz;
+    if (!has_norm) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const float* xv = &xr.v[k].x;
+        const float* wv = &gw.v[k].x;
+        float* gv = &g.v[k].x;
+        float* aw = &acc_w.v[k].x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { gv[e] = dz * wv[e]; aw[e] += dz * xv[e]; }
+      }
+      store_row<NV>(dx + row * width, width, lane, g);
+      continue;
+    }
+    const float mean = mean_i[row], sd = std_i[row];
+    const float r = 1.0f / (sd + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + 128 * k;
+      float* xv = &xr.v[k].x;
+      const float* wv = &gw.v[k].x;
+      const float* av = &ga.v[k].x;
+      const float* bv = &gb.v[k].x;
+      float* gv = &g.v[k].x;
+      float* aa = &acc_a.v[k].x;
+      float* ab = &acc_b.v[k].x;
+      float* aw = &acc_w.v[k].x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float cc = (c < width) ? xv[e] - mean : 0.f;
+        const float xh = cc * r;
+        const float xf = av[e] * cc / (sd + eps) + bv[e];
+        const float dyv = dz * wv[e];          // d loss / d xf
+        aw[e] += dz * xf;
+        aa[e] += dyv * xh;
+        ab[e] += dyv;
+        const float dxh = dyv * av[e];
+        gv[e] = dxh;
+        xv[e] = cc;
+        s1 += dxh;
+        s2 += dxh * cc;
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    const float m1 = s1 / float(width);
+    const float coef = (sd > 0.f) ? r * r * s2 / (float(width - 1) * sd) : 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float* gv = &g.v[k].x;
+      const float* xv = &xr.v[k].x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gv[e] = r * (gv[e] - m1) - coef * xv[e];
+    }
+    store_row<NV>(dx + row * width, width, lane, g);
+  }
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    if (!has_norm && pass < 2) continue;
+    const RowRegs<NV>& src = pass == 0 ? acc_a : (pass == 1 ? acc_b : acc_w);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) *reinterpret_cast<float4*>(&sh[wid][lane * 4 + 128 * k]) = src.v[k];
+    __syncthreads();
+    float* dst = pass == 0 ? grad_a : (pass == 1 ? grad_b : grad_w);
+    for (int c = threadIdx.x; c < width; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < ROWS_PER_BLOCK; ++ww) t += sh[ww][c];
+      atomicAdd(dst + c, t);
+    }
+    __syncthreads();
+  }
+  acc_wb = warp_sum(acc_wb);
+  if (lane == 0) shb[wid] = acc_wb;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int ww = 0; ww < ROWS_PER_BLOCK; ++ww) t += shb[ww];
+    atomicAdd(grad_wb, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host launchers
+static int nv_for(int width) { return (width + 127) / 128; }
+
+#define ARB_DISPATCH_NV(width, CALL)                                  \
+  switch (nv_for(width)) {                                            \
+    case 1: { constexpr int NV = 1; CALL; } break;                    \
+    case 2: { constexpr int NV = 2; CALL; } break;                    \
+    case 3: case 4: { constexpr int NV = 4; CALL; } break;            \
+    case 5: case 6: case 7: case 8: { constexpr int NV = 8; CALL; } break; \
+    default: arb_set_error("row kernels support widths up to 1024"); return ARB_E_UNSUPPORTED; \
+  }
+
+static int check_launch() {
+  arb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { arb_set_error(cudaGetErrorString(e)); return ARB_E_CUDA; }
+  return ARB_OK;
+}
+
+int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
+               float* mean, float* sd, cudaStream_t st) {
+  if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
+  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  ARB_DISPATCH_NV(width, (ln_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, rows, width, y, mean, sd)));
+  return check_launch();
+}
+
+int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
+                const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
+                cudaStream_t st) {
+  const int rpw = 8;
+  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
+  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b)));
+  return check_launch();
+}
+
+int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pitch, cudaStream_t st) {
+  if (S > 32 * 48) { arb_set_error("attention softmax supports slate_length <= 1536"); return ARB_E_UNSUPPORTED; }
+  const long long rows = (long long)B * h * S;
+  softmax_fwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(sc, mask, B, h, S, pitch);
+  return check_launch();
+}
+
+int softmax_backward(float* dp, const float* prob, long long rows, int S, int pitch, cudaStream_t st) {
+  softmax_bwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(dp, prob, rows, S, pitch);
+  return check_launch();
+}
+
+int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st) {
+  const int rpb = 128;
+  colsum_kernel<<<unsigned((rows + rpb - 1) / rpb), 256, 0, st>>>(in, rows, width, ld, rpb, out);
+  return check_launch();
+}
+
+int head_forward(const float* x, const float* a, const float* b, float eps, const float* w, const float* wb,
+                 int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,
+                 cudaStream_t st) {
+  if (width % 4) { arb_set_error("model width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
+  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  ARB_DISPATCH_NV(width, (head_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd)));
+  return check_launch();
+}
+
+int head_backward(const float* dscore, const float* score, const float* x, const float* a, const float* b,
+                  const float* mean, const float* sd, float eps, const float* w, const float* wb, int has_norm,
+                  int act, long long rows, int width, float* dx, float* grad_a, float* grad_b, float* grad_w,
+                  float* grad_wb, cudaStream_t st) {
+  const int rpw = 8;
+  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
+  ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb)));
+  return check_launch();
+}
+
+}  // namespace arb

@@ -1,0 +1,329 @@
+"""Drop-in replacement for allrank.models.model.make_model / LTRModel on B200.
+
+Same call surface as the reference (/root/reference/allrank/models/model.py):
+
+    model = make_model(fc_model=..., transformer=..., post_model=..., n_features=...)      # model.py:131
+    scores = model(x, mask, indices)            # [B,S]   (model.py:72-80,  train_utils.py:20)
+    scores = model.score(x, mask, indices)      # [B,S]   (model.py:82-92,  train_utils.py:34)
+    model.parameters() / .state_dict() / .load_state_dict() / .train() / .eval() / .to(device)
+
+and the same state_dict keys and shapes as the reference's module tree (so a reference `model.pkl` loads):
+`input_layer.layers.0.{weight,bias}`, `encoder.layers.{l}.self_attn.linears.{0..3}.{weight,bias}`,
+`encoder.layers.{l}.feed_forward.w_{1,2}.{weight,bias}`, `encoder.layers.{l}.sublayer.{0,1}.norm.{a_2,b_2}`,
+`encoder.norm.{a_2,b_2}`, `output_layer.w_1.{weight,bias}`; same initialisation order (nn.Linear defaults,
+clones share the prototype's bias, xavier_uniform_ on every parameter with dim > 1: model.py:148-150).
+
+The forward and backward passes are fixed launch sequences inside liballrank_b200.so (csrc/scorer.cu): tcgen05
+TF32 GEMMs + fp32 SIMT kernels.  The nn.Parameters are views of ONE flat fp32 buffer and their .grad are views of
+one flat gradient buffer -- which is what makes the single-bucket NCCL all-reduce (allrank_b200/ddp.py) and
+flat optimisers possible.  There is no eager fallback: CPU tensors raise.
+
+Not built yet (raise NotImplementedError rather than fall back): dropout > 0 in training mode, positional
+encodings, multi-layer / activated / input-normed FC blocks, d_output > 1.
+"""
+import copy
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_ACTS = {None: 0, "Tanh": 1, "Sigmoid": 2, "ReLU": 3}
+
+
+class ScorerConfig(ctypes.Structure):
+    _fields_ = [("n_features", ctypes.c_int32), ("d_model", ctypes.c_int32), ("n_layers", ctypes.c_int32),
+                ("n_heads", ctypes.c_int32), ("d_ff", ctypes.c_int32), ("out_act", ctypes.c_int32),
+                ("ln_eps", ctypes.c_float)]
+
+
+c_p, c_i, c_i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+_lib.register("arb_scorer_param_count", c_i64, [c_p])
+_lib.register("arb_scorer_workspace_floats", c_i64, [c_p, c_i, c_i, c_i])
+_lib.register("arb_scorer_backward_scratch_floats", c_i64, [c_p, c_i, c_i])
+_lib.register("arb_scorer_forward", c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i64, c_i, c_p])
+_lib.register("arb_scorer_backward", c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p])
+
+
+# ------------------------------------------------------------------------------------------------ module tree
+class _Norm(nn.Module):
+    """Parameter holder for the reference's custom LayerNorm (transformer.py:59-81)."""
+
+    def __init__(self, width):
+        super().__init__()
+        self.a_2 = nn.Parameter(torch.ones(width))
+        self.b_2 = nn.Parameter(torch.zeros(width))
+
+
+class _Sublayer(nn.Module):
+    def __init__(self, width):
+        super().__init__()
+        self.norm = _Norm(width)
+
+
+class _SelfAttn(nn.Module):
+    def __init__(self, proto):
+        super().__init__()
+        self.linears = nn.ModuleList([_clone_linear(proto) for _ in range(4)])
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, w1, w2):
+        super().__init__()
+        self.w_1 = _clone_linear(w1)
+        self.w_2 = _clone_linear(w2)
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, width, attn_proto, w1, w2):
+        super().__init__()
+        self.self_attn = _SelfAttn(attn_proto)
+        self.feed_forward = _FeedForward(w1, w2)
+        self.sublayer = nn.ModuleList([_Sublayer(width), _Sublayer(width)])
+
+
+class _Encoder(nn.Module):
+    def __init__(self, n_layers, width, attn_proto, w1, w2):
+        super().__init__()
+        self.layers = nn.ModuleList([_EncoderLayer(width, attn_proto, w1, w2) for _ in range(n_layers)])
+        self.norm = _Norm(width)
+
+
+class _InputFC(nn.Module):
+    def __init__(self, lin):
+        super().__init__()
+        self.layers = nn.ModuleList([lin])
+        self.output_size = lin.out_features
+
+
+class _Head(nn.Module):
+    def __init__(self, lin):
+        super().__init__()
+        self.w_1 = lin
+        self.d_output = 1
+
+
+def _clone_linear(proto):
+    return copy.deepcopy(proto)   # like the reference's clones(): no RNG draw, clones share the prototype's init
+
+
+# ------------------------------------------------------------------------------------------------ autograd glue
+class _ScorerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, x, mask, model):
+        training = ctx.needs_input_grad[0]
+        scores, ws = model._launch_forward(x, mask, training)
+        if training:
+            ctx.model = model
+            ctx.ws = ws
+            ctx.save_for_backward(x, mask, scores)
+        return scores
+
+    @staticmethod
+    def backward(ctx, d_scores):
+        x, mask, scores = ctx.saved_tensors
+        ctx.model._launch_backward(x, mask, scores, d_scores.contiguous().float(), ctx.ws)
+        ctx.ws = None
+        return None, None, None, None
+
+
+class LTRModel(nn.Module):
+    """B200 scorer with the reference LTRModel's surface (model.py:47-92)."""
+
+    def __init__(self, n_features, d_model, n_layers, n_heads, d_ff, dropout, output_activation):
+        super().__init__()
+        if output_activation not in _ACTS:
+            raise NotImplementedError(f"output activation {output_activation!r}: supported {sorted(map(str, _ACTS))}")
+        self.n_features, self.d_model, self.n_layers = int(n_features), int(d_model), int(n_layers)
+        self.n_heads, self.d_ff, self.dropout_p = int(n_heads), int(d_ff), float(dropout or 0.0)
+        self.output_activation = output_activation
+        if n_layers > 0:
+            assert d_model % n_heads == 0   # transformer.py:170
+        # --- build in the reference's construction order so that a seeded init reproduces (model.py:139-150)
+        fc = nn.Linear(n_features, d_model)
+        self.input_layer = _InputFC(fc)
+        if n_layers > 0:
+            attn_proto = nn.Linear(d_model, d_model)
+            w1 = nn.Linear(d_model, d_ff)
+            w2 = nn.Linear(d_ff, d_model)
+            self.encoder = _Encoder(n_layers, d_model, attn_proto, w1, w2)
+        else:
+            self.encoder = None
+        self.output_layer = _Head(nn.Linear(d_model, 1))
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        self._Fp = (self.n_features + 3) // 4 * 4
+        self._cfg = ScorerConfig(self._Fp, self.d_model, self.n_layers, max(self.n_heads, 1), max(self.d_ff, 4),
+                                 _ACTS[output_activation], 1e-6)
+        self._flat = None
+        self._flat_grad = None
+        self._views = None
+        self._anchor = None
+
+    # ---- flat parameter storage -------------------------------------------------------------------
+    def _ordered(self):
+        """(parameter, flat shape) in the C ABI's layout order (include/allrank_b200.h)."""
+        d, Fp = self.d_model, self._Fp
+        out = [(self.input_layer.layers[0].weight, (d, Fp)), (self.input_layer.layers[0].bias, (d,))]
+        if self.encoder is not None:
+            for lyr in self.encoder.layers:
+                lin = lyr.self_attn.linears
+                out += [(lin[0].weight, None), (lin[1].weight, None), (lin[2].weight, None),
+                        (lin[0].bias, None), (lin[1].bias, None), (lin[2].bias, None),
+                        (lin[3].weight, None), (lin[3].bias, None),
+                        (lyr.feed_forward.w_1.weight, None), (lyr.feed_forward.w_1.bias, None),
+                        (lyr.feed_forward.w_2.weight, None), (lyr.feed_forward.w_2.bias, None),
+                        (lyr.sublayer[0].norm.a_2, None), (lyr.sublayer[0].norm.b_2, None),
+                        (lyr.sublayer[1].norm.a_2, None), (lyr.sublayer[1].norm.b_2, None)]
+            out += [(self.encoder.norm.a_2, None), (self.encoder.norm.b_2, None)]
+        out += [(self.output_layer.w_1.weight, None), (self.output_layer.w_1.bias, None)]
+        return out
+
+    def _view_of(self, flat, offset, p, flat_shape):
+        if flat_shape is None or tuple(flat_shape) == tuple(p.shape):
+            return flat[offset:offset + p.numel()].view(p.shape), p.numel()
+        n = 1
+        for s in flat_shape:
+            n *= s
+        full = flat[offset:offset + n].view(flat_shape)
+        return full[..., :p.shape[-1]], n
+
+    def _pack(self, device):
+        total = int(_lib.lib().arb_scorer_param_count(ctypes.byref(self._cfg)))
+        if total <= 0:
+            raise NotImplementedError("unsupported scorer shape: " + _lib.lib().arb_last_error().decode())
+        flat = torch.zeros(total, dtype=torch.float32, device=device)
+        grad = torch.zeros(total, dtype=torch.float32, device=device)
+        views, off = [], 0
+        for p, shape in self._ordered():
+            v, n = self._view_of(flat, off, p, shape)
+            gv, _ = self._view_of(grad, off, p, shape)
+            with torch.no_grad():
+                v.copy_(p.detach().to(device=device, dtype=torch.float32))
+            old_grad = p.grad
+            p.data = v
+            if old_grad is not None:
+                gv.copy_(old_grad.to(device))
+                p.grad = gv
+            views.append((p, v, gv))
+            off += n
+        assert off == total, (off, total)
+        self._flat, self._flat_grad, self._views = flat, grad, views
+        self._anchor = torch.zeros(1, device=device, requires_grad=True)
+
+    def _ensure_packed(self, device):
+        if self._flat is None or self._flat.device != device:
+            self._pack(device)
+            return
+        for p, v, _ in self._views:
+            if p.data_ptr() != v.data_ptr() or p.device != device:
+                self._pack(device)      # e.g. after model.to(...) replaced the parameter storage
+                return
+
+    @property
+    def flat_parameters(self):
+        return self._flat
+
+    @property
+    def flat_gradients(self):
+        return self._flat_grad
+
+    # ---- launches -----------------------------------------------------------------------------------
+    def _prep_inputs(self, x, mask):
+        _lib.require_cuda(x, mask)
+        if x.dim() != 3 or x.shape[-1] != self.n_features:
+            raise ValueError(f"x must be [batch, slate, {self.n_features}]")
+        if mask.shape != x.shape[:2]:
+            raise ValueError("mask must be [batch, slate]")
+        x = x.detach().float()
+        if self._Fp != self.n_features:
+            x = torch.nn.functional.pad(x, (0, self._Fp - self.n_features))
+        return x.contiguous(), mask.detach().to(torch.uint8).contiguous()
+
+    def _launch_forward(self, x, mask, training):
+        B, S = x.shape[0], x.shape[1]
+        dev = x.device
+        cfg = ctypes.byref(self._cfg)
+        n_ws = int(_lib.lib().arb_scorer_workspace_floats(cfg, B, S, 1 if training else 0))
+        ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
+        scores = torch.empty((B, S), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().arb_scorer_forward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask), B, S,
+                                               _lib.ptr(scores), _lib.ptr(ws), n_ws, 1 if training else 0,
+                                               _lib.stream_ptr(dev))
+        _lib.check(rc, "arb_scorer_forward")
+        return scores, (ws if training else None)
+
+    def _launch_backward(self, x, mask, scores, d_scores, ws):
+        B, S = x.shape[0], x.shape[1]
+        dev = x.device
+        cfg = ctypes.byref(self._cfg)
+        fresh = any(p.grad is None or p.grad.data_ptr() != gv.data_ptr() for p, _, gv in self._views)
+        if fresh:                      # after optimizer.zero_grad(set_to_none=True): start from zero
+            self._flat_grad.zero_()
+        n_sc = int(_lib.lib().arb_scorer_backward_scratch_floats(cfg, B, S))
+        scratch = torch.empty(n_sc, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().arb_scorer_backward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask), B, S,
+                                                _lib.ptr(scores), _lib.ptr(d_scores), _lib.ptr(self._flat_grad),
+                                                _lib.ptr(ws), ws.numel(), _lib.ptr(scratch), n_sc,
+                                                _lib.stream_ptr(dev))
+        _lib.check(rc, "arb_scorer_backward")
+        if fresh:
+            for p, _, gv in self._views:
+                if p.requires_grad:
+                    p.grad = gv
+
+    # ---- public surface (model.py:62-92) ---------------------------------------------------------------
+    def prepare_for_output(self, x, mask, indices):
+        raise NotImplementedError("the fused scorer does not expose the encoder output; use forward()/score()")
+
+    def forward(self, x, mask, indices=None):
+        if self.training and self.dropout_p > 0.0:
+            raise NotImplementedError("dropout > 0 in training mode is not implemented in allrank_b200 yet "
+                                      "(no eager fallback); use dropout 0.0 or eval()")
+        xin, m = self._prep_inputs(x, mask)
+        self._ensure_packed(xin.device)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if needs_grad:
+            return _ScorerFn.apply(self._anchor, xin, m, self)
+        scores, _ = self._launch_forward(xin, m, False)
+        return scores
+
+    def score(self, x, mask, indices=None):
+        return self.forward(x, mask, indices)
+
+
+def _get(cfg, name, default=None):
+    if cfg is None:
+        return default
+    if isinstance(cfg, dict):
+        return cfg.get(name, default)
+    return getattr(cfg, name, default)
+
+
+def make_model(fc_model, transformer, post_model, n_features):
+    """Same arguments as allrank.models.model.make_model (model.py:131-151): `fc_model` dict
+    {sizes, input_norm, activation, dropout}, `transformer` config object/dict {N, d_ff, h, dropout,
+    positional_encoding} or None, `post_model` dict {d_output, output_activation}."""
+    if not fc_model:
+        raise NotImplementedError("allrank_b200 needs an input FC block (fc_model.sizes = [d_model])")
+    sizes = list(_get(fc_model, "sizes"))
+    if len(sizes) != 1:
+        raise NotImplementedError("allrank_b200 fuses a single input Linear; multi-layer FC blocks are a next item")
+    if _get(fc_model, "input_norm", False) or _get(fc_model, "activation", None) is not None:
+        raise NotImplementedError("input_norm / FC activation are not built into the fused scorer yet")
+    if int(_get(post_model, "d_output", 1)) != 1:
+        raise NotImplementedError("d_output > 1 (ordinal loss) is a SURVEY 8(f) next item")
+    d_model = int(sizes[0])
+    if transformer:
+        if _get(transformer, "positional_encoding", None) is not None:
+            raise NotImplementedError("positional encodings are a SURVEY 8(f) next item")
+        n_layers, heads, d_ff = int(_get(transformer, "N")), int(_get(transformer, "h")), int(_get(transformer, "d_ff"))
+        dropout = float(_get(transformer, "dropout", 0.0) or 0.0)
+    else:
+        n_layers, heads, d_ff, dropout = 0, 1, 4, 0.0
+    dropout = max(dropout, float(_get(fc_model, "dropout", 0.0) or 0.0))
+    return LTRModel(n_features, d_model, n_layers, heads, d_ff, dropout, _get(post_model, "output_activation", None))

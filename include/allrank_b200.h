@@ -116,6 +116,62 @@ int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int32_t B, int
                         float* loss, float* grad, float* scratch, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* ---------------------------------------------------------------- scorer: LTRModel(x, mask, indices) -> scores
+ * Replaces allrank.models.model.LTRModel.forward / .score (allrank/models/model.py:72-92) for the model family
+ * make_model builds (model.py:131-151): one input Linear (FCModel, model.py:12-44) -> N pre-norm Transformer
+ * encoder blocks (allrank/models/transformer.py:28-227: custom LayerNorm, MultiHeadedAttention with key-padding
+ * mask, PositionwiseFeedForward, residuals) -> final LayerNorm -> Linear(d_model -> 1) head (model.py:95-128).
+ * Called from allrank/training/train_utils.py:20 (`model(xb, mask, indices)`) and :34 (`model.score`).
+ *
+ * Every matrix product runs on the tcgen05 tensor cores in TF32 with fp32 accumulation (csrc/gemm_tf32.cu);
+ * LayerNorm / softmax / head are fp32 SIMT kernels (csrc/scorer_kernels.cu).  Dropout must be 0 (eval, or
+ * configs with dropout 0.0): a fused Philox dropout is a "next" item.
+ *
+ * Parameters live in ONE flat fp32 buffer (the host layer makes the nn.Parameters views of it), laid out as
+ *   fc_w[d,F] fc_b[d] | per layer: wq wk wv [3d,d] bq bk bv [3d] wo[d,d] bo[d] w1[dff,d] b1[dff] w2[d,dff] b2[d]
+ *   ln1_a ln1_b ln2_a ln2_b [d each] | lnf_a lnf_b [d] head_w[d] head_b[1]
+ * arb_scorer_param_count() gives the total; gradients use the same layout and are ACCUMULATED into `grads`.
+ */
+#define ARB_ACT_NONE 0
+#define ARB_ACT_TANH 1
+#define ARB_ACT_SIGMOID 2
+#define ARB_ACT_RELU 3
+
+typedef struct arb_scorer_config {
+  int32_t n_features;   /* F (row pitch of x; must be a multiple of 4 -- the host layer pads)            */
+  int32_t d_model;      /* fc_model.sizes[-1] (model.py:142); multiple of 32 * n_heads                    */
+  int32_t n_layers;     /* transformer N; 0 = FC-only model (no encoder, no final LayerNorm)              */
+  int32_t n_heads;      /* h                                                                             */
+  int32_t d_ff;         /* PositionwiseFeedForward hidden width                                           */
+  int32_t out_act;      /* ARB_ACT_*: post_model.output_activation (model.py:105-107)                     */
+  float ln_eps;         /* 1e-6 (transformer.py:63)                                                       */
+} arb_scorer_config;
+
+int64_t arb_scorer_param_count(const arb_scorer_config* cfg);
+/* floats of activation workspace for a [B,S] batch; `training` != 0 keeps what backward needs */
+int64_t arb_scorer_workspace_floats(const arb_scorer_config* cfg, int32_t B, int32_t S, int32_t training);
+/* x [B,S,F] fp32, mask [B,S] uint8 (1 = padded, train_utils.py:19) -> scores [B,S] fp32 */
+int32_t arb_scorer_forward(const arb_scorer_config* cfg, const float* params, const float* x, const uint8_t* mask,
+                           int32_t B, int32_t S, float* scores, float* workspace, int64_t workspace_floats,
+                           int32_t training, void* stream);
+/* d_scores [B,S] -> grads += d loss / d params.  `workspace` is the one the training forward filled;
+ * `scratch`: arb_scorer_backward_scratch_floats(cfg,B,S) floats. */
+int64_t arb_scorer_backward_scratch_floats(const arb_scorer_config* cfg, int32_t B, int32_t S);
+int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, const float* x, const uint8_t* mask,
+                            int32_t B, int32_t S, const float* scores, const float* d_scores, float* grads,
+                            float* workspace, int64_t workspace_floats, float* scratch, int64_t scratch_floats,
+                            void* stream);
+
+/* 1 (default): MMA operands are rounded fp32 -> tf32 by the TMA unit (TFLOAT32 tensor maps); 0: the tensor core
+ * truncates.  Process-wide; exists for the precision tests. */
+void arb_set_tf32_round_on_load(int32_t enable);
+
+/* Building block exposed for tests: C = epilogue(alpha * A op B) on row-major fp32 matrices (csrc/gemm_tf32.cu). */
+int32_t arb_gemm_tf32(const float* A, const float* B, float* C, const float* aux, const float* bias, int32_t M,
+                      int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t batch, int64_t a_bstride,
+                      int64_t b_bstride, int64_t c_bstride, int32_t block_n, int32_t flags, float alpha,
+                      int32_t split_k, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

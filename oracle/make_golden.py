@@ -185,9 +185,22 @@ def gen_scorer():
         print("scorer", name, "scores", tuple(scores.shape))
 
 
+def gen_init():
+    """Seeded initialisation of the reference's make_model (model.py:131-151): pins construction order."""
+    torch.manual_seed(123)
+    model = ref_make_model(
+        fc_model={"sizes": [32], "input_norm": False, "activation": None, "dropout": 0.0},
+        transformer=TransformerConfig(N=2, d_ff=64, h=2, positional_encoding=None, dropout=0.0),
+        post_model={"d_output": 1, "output_activation": None}, n_features=20)
+    blob = {"p:" + k_: v.numpy() for k_, v in model.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "init_seed123.npz"), **blob)
+    print("init:", len(blob), "tensors")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     gen_losses()
     gen_listmle()
     gen_metrics()
     gen_scorer()
+    gen_init()

@@ -1,0 +1,96 @@
+"""TF32-faithful variant of the oracle scorer (TEST INFRASTRUCTURE).
+
+Same maths as oracle/scorer_ref.py (reference: allrank/models/{model,transformer}.py), but every matrix
+product -- forward and backward -- sees its operands with the mantissa cut to 10 bits, which is what the
+tcgen05 kind::tf32 datapath does to fp32 operands; accumulation stays fp32/fp64.  It separates "TF32 rounding"
+from "kernel bug" when the CUDA scorer is compared with the fp32 reference: the CUDA path must agree with this
+emulation much more tightly than with the fp32 oracle.
+"""
+import math
+
+import torch
+
+
+def tf32_trunc(t, mode="trunc"):
+    """Cut an fp32 tensor to TF32 precision (1+8+10 bits). mode: 'trunc' (toward zero) or 'rna' (round to nearest)."""
+    t = t.float().contiguous()
+    bits = t.view(torch.int32)
+    if mode == "rna":
+        bits = bits + 0x1000
+    return (bits & ~0x1FFF).view(torch.float32)
+
+
+class _MM(torch.autograd.Function):
+    """C = A @ B with TF32 operands in the forward and in both backward products."""
+
+    @staticmethod
+    def forward(ctx, a, b, mode, acc_dtype):
+        ctx.save_for_backward(a, b)
+        ctx.mode, ctx.acc = mode, acc_dtype
+        return (tf32_trunc(a, mode).to(acc_dtype) @ tf32_trunc(b, mode).to(acc_dtype)).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        m, acc = ctx.mode, ctx.acc
+        gt = tf32_trunc(g, m).to(acc)
+        da = (gt @ tf32_trunc(b, m).to(acc).transpose(-1, -2)).float()
+        db = (tf32_trunc(a, m).to(acc).transpose(-1, -2) @ gt).float()
+        while da.dim() > a.dim():
+            da = da.sum(0)
+        while db.dim() > b.dim():
+            db = db.sum(0)
+        if da.shape != a.shape:
+            da = da.sum(tuple(range(da.dim() - a.dim())) or 0).reshape(a.shape) if da.numel() != a.numel() else da.reshape(a.shape)
+        if db.shape != b.shape:
+            # weight shared across a leading batch of rows: reduce the broadcast dimensions
+            extra = db.dim() - b.dim()
+            db = db.sum(tuple(range(extra))) if extra > 0 else db
+            if db.shape != b.shape:
+                db = db.reshape(-1, *b.shape).sum(0)
+        return da, db, None, None
+
+
+def mm(a, b, mode="trunc", acc_dtype=torch.float64):
+    return _MM.apply(a, b, mode, acc_dtype)
+
+
+def row_norm(x, a, b, eps=1e-6):
+    mu = x.mean(-1, keepdim=True)
+    sd = x.std(-1, keepdim=True)
+    return a * (x - mu) / (sd + eps) + b
+
+
+def scorer_forward(sd, x, mask, n_layers, heads, out_act=None, mode="trunc"):
+    """Functional forward from a reference-keyed state_dict (tensors may require grad)."""
+    B, S, F = x.shape
+    R = B * S
+
+    def lin(inp, w, b):   # inp [R, in]
+        return mm(inp, w.t(), mode) + b
+
+    h = lin(x.reshape(R, F), sd["input_layer.layers.0.weight"], sd["input_layer.layers.0.bias"])
+    d = h.shape[-1]
+    dk = d // heads if n_layers else 0
+    for l in range(n_layers):
+        p = f"encoder.layers.{l}."
+        xn = row_norm(h, sd[p + "sublayer.0.norm.a_2"], sd[p + "sublayer.0.norm.b_2"])
+        q, k, v = (lin(xn, sd[p + f"self_attn.linears.{i}.weight"], sd[p + f"self_attn.linears.{i}.bias"])
+                   .view(B, S, heads, dk).transpose(1, 2) for i in range(3))
+        logits = mm(q, k.transpose(-1, -2), mode) * (1.0 / math.sqrt(dk))
+        logits = logits.masked_fill(mask[:, None, None, :], float("-inf"))
+        prob = torch.softmax(logits, dim=-1)
+        ctx = mm(prob, v, mode).transpose(1, 2).reshape(R, d)
+        h = h + lin(ctx, sd[p + "self_attn.linears.3.weight"], sd[p + "self_attn.linears.3.bias"])
+        xn = row_norm(h, sd[p + "sublayer.1.norm.a_2"], sd[p + "sublayer.1.norm.b_2"])
+        hid = torch.relu(lin(xn, sd[p + "feed_forward.w_1.weight"], sd[p + "feed_forward.w_1.bias"]))
+        h = h + lin(hid, sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"])
+    if n_layers:
+        h = row_norm(h, sd["encoder.norm.a_2"], sd["encoder.norm.b_2"])
+    z = (h * sd["output_layer.w_1.weight"].reshape(1, -1)).sum(-1) + sd["output_layer.w_1.bias"]   # fp32 head (SIMT)
+    z = z.view(B, S)
+    if out_act == "Tanh":
+        z = torch.tanh(z)
+    elif out_act == "Sigmoid":
+        z = torch.sigmoid(z)
+    return z
