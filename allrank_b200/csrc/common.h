@@ -12,3 +12,14 @@ void arb_count_launch(int n = 1);
 // loss = sum(val)/sum(cnt), grad *= 1/sum(cnt); an all-zero count gives loss 0 and zero grad (slate_kernels.cu)
 int arb_finalize_mean_over_count(const float* val, const float* cnt, int B, float* loss, float* grad, size_t n_grad,
                                  cudaStream_t st);
+
+// Optional per-launch device timing (bench.py roofline): when enabled, every launch made inside a ProfScope is
+// bracketed by CUDA events on its own stream; arb_prof_collect sums durations and work units per kernel class.
+enum { ARB_PROF_GEMM = 0, ARB_PROF_SCORER_SIMT = 1, ARB_PROF_LOSS = 2, ARB_PROF_METRICS = 3, ARB_PROF_OPTIM = 4,
+       ARB_PROF_CLASSES = 5 };
+struct ProfScope {
+  ProfScope(int cls, double work, cudaStream_t st);
+  ~ProfScope();
+  int idx;
+  cudaStream_t st;
+};

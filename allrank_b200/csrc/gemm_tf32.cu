@@ -298,7 +298,10 @@ static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap&
     }
     configured = true;
   }
-  kern<<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tX, p);
+  {
+    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * double(d.nb2) * double(d.nb3), st);
+    kern<<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tX, p);
+  }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { arb_set_error(cudaGetErrorString(e)); return ARB_E_CUDA; }

@@ -359,6 +359,7 @@ extern "C" int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int
   }
   NeuralCfg cfg{pad_value, temperature, tol, powered_relevancies, k, max_iter};
   const size_t ws_stride = nn_big_floats(S, max_iter, true);
+  ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
   neural_ndcg_kernel<<<B, NN_THREADS, smem, st>>>(y_pred, y_true, B, S, discounts, cfg, scratch, scratch + B, grad,
                                                   static_cast<float*>(workspace), ws_stride, smem_big_floats);
   arb_count_launch();

@@ -450,6 +450,7 @@ int ln_forward(const float* x, const float* a, const float* b, float eps, long l
                float* mean, float* sd, cudaStream_t st) {
   if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 8), st);
   ARB_DISPATCH_NV(width, (ln_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, rows, width, y, mean, sd)));
   return check_launch();
 }
@@ -459,6 +460,7 @@ int ln_backward(const float* dy, const float* x, const float* a, const float* me
                 cudaStream_t st) {
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((dres ? 16.0 : 12.0) * width + 8), st);
   ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b)));
   return check_launch();
 }
@@ -466,17 +468,20 @@ int ln_backward(const float* dy, const float* x, const float* a, const float* me
 int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pitch, cudaStream_t st) {
   if (S > 32 * 48) { arb_set_error("attention softmax supports slate_length <= 1536"); return ARB_E_UNSUPPORTED; }
   const long long rows = (long long)B * h * S;
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 8.0 * S, st);
   softmax_fwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(sc, mask, B, h, S, pitch);
   return check_launch();
 }
 
 int softmax_backward(float* dp, const float* prob, long long rows, int S, int pitch, cudaStream_t st) {
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 12.0 * S, st);
   softmax_bwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(dp, prob, rows, S, pitch);
   return check_launch();
 }
 
 int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st) {
   const int rpb = 128;
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 4.0 * width, st);
   colsum_kernel<<<unsigned((rows + rpb - 1) / rpb), 256, 0, st>>>(in, rows, width, ld, rpb, out);
   return check_launch();
 }
@@ -486,6 +491,7 @@ int head_forward(const float* x, const float* a, const float* b, float eps, cons
                  cudaStream_t st) {
   if (width % 4) { arb_set_error("model width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (4.0 * width + 12), st);
   ARB_DISPATCH_NV(width, (head_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd)));
   return check_launch();
 }
@@ -496,6 +502,7 @@ int head_backward(const float* dscore, const float* score, const float* x, const
                   float* grad_wb, cudaStream_t st) {
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 16), st);
   ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb)));
   return check_launch();
 }

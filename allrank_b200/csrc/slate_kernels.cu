@@ -720,6 +720,7 @@ extern "C" int32_t arb_rank_metrics(const float* y_pred, const float* y_true, in
   const size_t smem = slate_smem_bytes(S);
   int rc = set_smem((const void*)metrics_kernel, smem);
   if (rc) { arb_set_error("arb_rank_metrics: slate too long for shared memory"); return rc; }
+  ProfScope ps(ARB_PROF_METRICS, double(B) * (8.0 * S + 4.0 * n_ats), st);
   metrics_kernel<<<B, 256, smem, st>>>(y_pred, y_true, B, S, discounts, ats, gain_mode, pad_value, filler, out_dcg,
                                       out_idcg, out_ndcg, out_mrr ? mrr_scratch : nullptr,
                                       out_mrr ? mrr_scratch + B : nullptr, out_order);
@@ -756,7 +757,8 @@ extern "C" int32_t arb_listnet(const float* y_pred, const float* y_true, int32_t
   const float inv_B = 1.0f / float(B);
   if (S <= 32 * LISTNET_MAX_PER_LANE) {
     const int wpb = 4;
-    listnet_warp_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(y_pred, y_true, B, S, eps, pad_value, inv_B,
+    ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
+  listnet_warp_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(y_pred, y_true, B, S, eps, pad_value, inv_B,
                                                                  scratch, grad);
   } else {
     const size_t smem = size_t(S) * 8 + 128;
@@ -778,6 +780,7 @@ extern "C" int32_t arb_listmle(const float* y_pred, const float* y_true, int32_t
   const size_t smem = size_t(next_pow2(S)) * 8 + size_t(S) * 16 + 256 * 4 + 64;
   int rc = set_smem((const void*)listmle_kernel, smem);
   if (rc) { arb_set_error("arb_listmle: slate too long"); return rc; }
+  ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
   listmle_kernel<<<B, 256, smem, st>>>(y_pred, y_true, B, S, eps, pad_value, perm, order, 1.0f / float(B), scratch,
                                       grad);
   arb_count_launch();
@@ -794,6 +797,7 @@ extern "C" int32_t arb_approx_ndcg(const float* y_pred, const float* y_true, int
   const size_t smem = slate_smem_bytes(S);
   int rc = set_smem((const void*)approx_ndcg_kernel, smem);
   if (rc) { arb_set_error("arb_approx_ndcg: slate too long"); return rc; }
+  ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
   approx_ndcg_kernel<<<B, 256, smem, st>>>(y_pred, y_true, B, S, eps, pad_value, alpha, 1.0f / float(B), scratch,
                                           grad);
   arb_count_launch();
@@ -817,6 +821,7 @@ extern "C" int32_t arb_lambda_loss(const float* y_pred, const float* y_true, int
   int rc = set_smem((const void*)lambda_loss_kernel, smem);
   if (rc) { arb_set_error("arb_lambda_loss: slate too long"); return rc; }
   LambdaCfg cfg{scheme, k, log_base, sigma, mu, eps};
+  ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
   lambda_loss_kernel<<<B, 256, smem, st>>>(y_pred, y_true, B, S, pad_value, cfg, scratch, scratch + B, grad);
   arb_count_launch();
   ARB_LAUNCH_OK();

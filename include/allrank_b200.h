@@ -172,6 +172,19 @@ int32_t arb_gemm_tf32(const float* A, const float* B, float* C, const float* aux
                       int64_t b_bstride, int64_t c_bstride, int32_t block_n, int32_t flags, float alpha,
                       int32_t split_k, void* stream);
 
+/* ---------------------------------------------------------------- optimiser + profiling helpers
+ * Flat Adam over the scorer's flat parameter/gradient buffers: torch.optim.Adam semantics (the optimiser the
+ * reference instantiates from its config, allrank/main.py:82), one launch.  grads are multiplied by grad_scale
+ * first (1/world_size after a sum all-reduce).  `step` is the 1-based step count. */
+int32_t arb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                      void* stream);
+
+/* Per-launch device timing for bench.py's roofline: enable, run steps, collect per kernel class
+ * (0 = tcgen05 GEMM [work = flops], 1 = scorer SIMT, 2 = losses, 3 = metrics, 4 = optimiser [work = bytes]). */
+void arb_prof_enable(int32_t on);
+int32_t arb_prof_collect(int32_t cls, double* total_ms, double* total_work, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif
