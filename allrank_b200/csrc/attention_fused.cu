@@ -1,0 +1,267 @@
+// Fused self-attention core for slates of up to 256 items:  ctx = softmax(mask(Q K^T / sqrt(dk))) V
+// in ONE kernel, the [S,S] score / probability tile living only in tensor memory.
+//
+// Reference: attention() allrank/models/transformer.py:137-156 (+ the head split / concat of
+// MultiHeadedAttention.forward :193-202, which here are just TMA coordinates).
+//
+// One CTA = one (slate b, head, 128-query tile).  Q (128 x dk), K and V (S x dk) are staged by TMA straight
+// out of the packed [B*S, 3*d_model] QKV activation (4-D tensor maps: dk, item, head, slate).
+//   warp 0    : TMA producer
+//   warp 1    : TMEM allocation + tcgen05.mma issue
+//                 S[128 x S]  = Q K^T          (kind::tf32, A/B from shared memory, accumulator in TMEM cols 0..S)
+//                 O[128 x dk] = P V            (A = P read back from TMEM, B = V as an MN-major smem operand)
+//   warps 2-5 : one thread per query row (= one TMEM lane): key mask, row max, exp2, row sum, P written back to
+//               TMEM in place (rounded to tf32), then the O epilogue (1/rowsum) and a TMA store into the
+//               concatenated-heads layout.
+// Nothing of size S^2 touches HBM: per (slate, head) the kernel reads 3*S*dk*4 bytes and writes S*dk*4 (+ 8*S
+// of softmax statistics for the backward pass) -- versus ~5*S^2*4 bytes for the unfused sequence.
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "attention_fused.h"
+#include "common.h"
+#include "sm100_ptx.cuh"
+
+namespace arb {
+
+constexpr int ATT_THREADS = 192;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t round_tf32(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return y;
+}
+
+template <int DK>
+struct AttFwdSmem {
+  static constexpr int NKB = (DK + 31) / 32;            // 32-wide k-blocks of the Q K^T contraction / V slabs
+  static constexpr int Q_BYTES = NKB * 128 * 128;       // [kb][128 rows][128 B]
+  static constexpr int K_BYTES = NKB * 256 * 128;       // [kb][256 rows][128 B]
+  static constexpr int V_BYTES = NKB * 256 * 128;       // [slab][256 key rows][128 B]
+  static constexpr int O_BYTES = NKB * 128 * 128;       // staging [slab][128 rows][128 B]
+  static constexpr int total() { return Q_BYTES + K_BYTES + V_BYTES + O_BYTES + 256 + 1024; }
+};
+
+template <int DK>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                  const __grid_constant__ CUtensorMap tmK,
+                                                                  const __grid_constant__ CUtensorMap tmV,
+                                                                  const __grid_constant__ CUtensorMap tmO,
+                                                                  const uint8_t* __restrict__ mask,
+                                                                  float* __restrict__ stat_max,
+                                                                  float* __restrict__ stat_sum, int S, int n_heads,
+                                                                  float scale_log2e) {
+  using L = AttFwdSmem<DK>;
+  constexpr int NKB = L::NKB;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + L::Q_BYTES;
+  uint8_t* v_s = k_s + L::K_BYTES;
+  uint8_t* o_s = v_s + L::V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_s + L::O_BYTES);
+  uint64_t* load_bar = bars;        // Q, K, V landed
+  uint64_t* s_bar = bars + 1;       // S = Q K^T complete
+  uint64_t* p_bar = bars + 2;       // P written to TMEM by all 128 softmax threads
+  uint64_t* o_bar = bars + 3;       // O = P V complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* mask_bits = tmem_slot + 2;   // 8 words: bit j of word w = key 32w+j is a real (unpadded, < S) item
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int S16 = (S + 15) & ~15;       // UMMA N of the score tile
+  const int S8 = (S + 7) & ~7;          // contraction length of P V
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmO);
+    ptx::mbar_init(load_bar, 1);
+    ptx::mbar_init(s_bar, 1);
+    ptx::mbar_init(p_bar, 128);
+    ptx::mbar_init(o_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  if (warp >= 2) {
+    const int et = threadIdx.x - 64;
+    if (et < 8) {
+      uint32_t w = 0;
+      for (int j = 0; j < 32; ++j) {
+        const int key = 32 * et + j;
+        if (key < S && mask[size_t(b) * S + key] == 0) w |= (1u << j);
+      }
+      mask_bits[et] = w;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;            // columns [0, 256)
+  const uint32_t tmem_O = tmem_base + 256;      // columns [256, 256 + DK)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(load_bar, L::Q_BYTES + L::K_BYTES + L::V_BYTES);
+      for (int kb = 0; kb < NKB; ++kb) {
+        ptx::tma_load_4d(q_s + kb * (128 * 128), &tmQ, load_bar, 32 * kb, m0, head, b);
+        ptx::tma_load_4d(k_s + kb * (256 * 128), &tmK, load_bar, 32 * kb, 0, head, b);
+        ptx::tma_load_4d(v_s + kb * (256 * 128), &tmV, load_bar, 32 * kb, 0, head, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      ptx::mbar_wait(load_bar, 0);
+      ptx::tc_fence_after();
+      // ---- S = Q K^T
+      const uint32_t idesc_s = ptx::idesc_tf32(128, S16, 0, 0);
+      uint32_t acc = 0;
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int ksteps = (DK - 32 * kb >= 32) ? 4 : (DK - 32 * kb + 7) / 8;
+        const uint32_t qa = ptx::smem_u32(q_s + kb * (128 * 128));
+        const uint32_t ka = ptx::smem_u32(k_s + kb * (256 * 128));
+        for (int k = 0; k < ksteps; ++k) {
+          ptx::mma_tf32_ss(tmem_S, ptx::smem_desc_sw128<2>(qa + k * 32, 16, 1024),
+                           ptx::smem_desc_sw128<2>(ka + k * 32, 16, 1024), idesc_s, acc);
+          acc = 1;
+        }
+      }
+      ptx::mma_commit(s_bar);
+      // ---- O = P V   (A = P from TMEM, B = V MN-major: 8 key rows = 1024 B per K step, 4-row swizzle atoms)
+      ptx::mbar_wait(p_bar, 0);
+      ptx::tc_fence_after();
+      const uint32_t idesc_o = ptx::idesc_tf32(128, DK < 16 ? 16 : DK, 0, 1);
+      const uint32_t va = ptx::smem_u32(v_s);
+      for (int i = 0; i < S8 / 8; ++i) {
+        ptx::mma_tf32_ts(tmem_O, tmem_S + 8 * i, ptx::smem_desc_sw128<1>(va + i * 1024, 256 * 128, 512), idesc_o,
+                         i > 0 ? 1u : 0u);
+      }
+      ptx::mma_commit(o_bar);
+    }
+  } else {
+    // ===================== softmax + epilogue: thread = query row =====================
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const int qidx = m0 + row;
+    const uint32_t lane_addr = uint32_t(32 * q) << 16;
+    ptx::mbar_wait(s_bar, 0);
+    ptx::tc_fence_after();
+    const int nchunks = (S8 + 31) / 32;
+    float mx = -CUDART_INF_F;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
+      ptx::tmem_ld_wait();
+      const uint32_t bits = mask_bits[c];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (bits & (1u << j)) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    float sum = 0.f;
+    const float mxs = mx * scale_log2e;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
+      ptx::tmem_ld_wait();
+      const uint32_t bits = mask_bits[c];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        // exp((s - max)/sqrt(dk)) as exp2; padded keys contribute exactly 0.  An all-padded slate gives
+        // (-inf) - (-inf) = NaN like the reference (quirk Q2).
+        const float e = (bits & (1u << j)) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs)) : 0.0f;
+        sum += e;
+        v[j] = round_tf32(e);
+      }
+      ptx::tmem_st_32x32(tmem_S + lane_addr + 32 * c, v);
+    }
+    ptx::tmem_st_wait();
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(p_bar);
+    if (qidx < S) {
+      const size_t so = (size_t(b) * n_heads + head) * S + qidx;
+      stat_max[so] = mx;
+      stat_sum[so] = sum;
+    }
+    const float inv = 1.0f / sum;
+    ptx::mbar_wait(o_bar, 0);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int sl = 0; sl < NKB; ++sl) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_O + lane_addr + 32 * sl, v);
+      ptx::tmem_ld_wait();
+      uint8_t* slab_row = o_s + sl * (128 * 128) + row * 128;
+#pragma unroll
+      for (int piece = 0; piece < 8; ++piece) {
+        float4 o;
+        o.x = __uint_as_float(v[piece * 4 + 0]) * inv;
+        o.y = __uint_as_float(v[piece * 4 + 1]) * inv;
+        o.z = __uint_as_float(v[piece * 4 + 2]) * inv;
+        o.w = __uint_as_float(v[piece * 4 + 3]) * inv;
+        *reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4)) = o;
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::named_bar_sync(1, 128);
+    if (threadIdx.x == 64) {
+      for (int sl = 0; sl < NKB; ++sl) ptx::tma_store_4d(&tmO, o_s + sl * (128 * 128), 32 * sl, m0, head, b);
+      ptx::tma_store_commit();
+      ptx::tma_store_wait_all();
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int DK>
+static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
+  using L = AttFwdSmem<DK>;
+  alignas(64) CUtensorMap tQ, tK, tV, tO;
+  int rc;
+  if ((rc = make_tmap_4d(&tQ, a.q, TmapBox{{32, 128, 1, 1}}, 0, 1))) return rc;
+  if ((rc = make_tmap_4d(&tK, a.k, TmapBox{{32, 256, 1, 1}}, 0, 1))) return rc;
+  if ((rc = make_tmap_4d(&tV, a.v, TmapBox{{32, 256, 1, 1}}, 1, 1))) return rc;
+  if ((rc = make_tmap_4d(&tO, a.o, TmapBox{{32, 128, 1, 1}}, 0, 0))) return rc;
+  auto kern = attn_fwd_kernel<DK>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total()) != cudaSuccess) {
+      arb_set_error("attn_fwd: cannot raise the dynamic shared memory limit");
+      return ARB_E_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((a.S + 127) / 128, a.h, a.B);
+  {
+    ProfScope ps(ARB_PROF_GEMM, 4.0 * double(a.S) * a.S * a.dk * a.h * a.B, st);
+    kern<<<grid, ATT_THREADS, L::total(), st>>>(tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
+                                               a.scale * 1.4426950408889634f);
+  }
+  arb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { arb_set_error(cudaGetErrorString(e)); return ARB_E_CUDA; }
+  return ARB_OK;
+}
+
+bool attn_fused_supported(int S, int dk) { return S >= 1 && S <= 256 && (dk == 16 || dk == 32 || dk == 64); }
+
+int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st) {
+  if (!attn_fused_supported(a.S, a.dk)) { arb_set_error("fused attention: unsupported shape"); return ARB_E_UNSUPPORTED; }
+  switch (a.dk) {
+    case 16: return launch_fwd_t<16>(a, st);
+    case 32: return launch_fwd_t<32>(a, st);
+    default: return launch_fwd_t<64>(a, st);
+  }
+}
+
+}  // namespace arb

@@ -1,0 +1,43 @@
+// Fused attention core (attention_fused.cu): launch descriptors.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "gemm_tf32.h"
+
+namespace arb {
+
+struct AttnFwdArgs {
+  TRef q, k, v, o;            // per-head views: dim = (dk, S, h, B)
+  const uint8_t* mask;        // [B,S], 1 = padded key
+  float* stat_max;            // [B,h,S] row max of the raw logits Q K^T (before the 1/sqrt(dk) scale)
+  float* stat_sum;            // [B,h,S] sum_j exp((s_j - max)/sqrt(dk)) over real keys
+  int B, h, S, dk;
+  float scale;                // 1/sqrt(dk)
+};
+
+bool attn_fused_supported(int S, int dk);
+int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st);
+
+}  // namespace arb
+
+namespace arb {
+
+struct AttnBwdArgs {
+  TRef q, k, v, d_o;          // per-head views (dk, S, h, B): saved Q/K/V and the incoming d ctx
+  TRef dq, dk_, dv;           // per-head views of the outputs (into the packed d qkv buffer)
+  const float* o_ptr;         // ctx [B*S, d_model] (for delta = rowsum(dO * O))
+  const float* do_ptr;        // d ctx [B*S, d_model]
+  int64_t o_pitch;
+  const uint8_t* mask;        // [B,S]
+  const float* stat_max;      // [B,h,S] from the fused forward
+  const float* stat_sum;      // [B,h,S]
+  float* delta;               // [B,h,S] scratch
+  int B, h, S, dk;
+  float scale;
+};
+
+bool attn_fused_bwd_supported(int S, int dk);
+int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
+
+}  // namespace arb

@@ -1,0 +1,353 @@
+// Fused self-attention backward for slates of up to 256 items and head width <= 32.
+//
+// Reference: autograd of attention() allrank/models/transformer.py:137-156.  Given d ctx it produces dQ, dK, dV
+// without ever materialising the S x S probabilities in HBM: they are recomputed from Q, K and the row statistics
+// (max, sum) the fused forward kernel saved.
+//
+// One CTA = one (slate, head).  Everything is computed in the TRANSPOSED orientation (TMEM lane = key), because the
+// tensor core takes its A operand from TMEM with lane = M:
+//     S^T  = K Q^T   , dP^T = V dO^T                       (tcgen05.mma kind::tf32, smem x smem -> TMEM)
+//     P^T  = exp2(S^T c - m_q c - log2 l_q)                 (one thread per key row; statistics per query column)
+//     dS^T = P^T * (dP^T - delta_q),  delta_q = sum_e dO[q,e] O[q,e]
+//     dV  += P^T  dO        (A = P^T  from TMEM, B = dO as MN-major smem operand)
+//     dK  += dS^T Q  * a    (A = dS^T from TMEM, B = Q  as MN-major smem operand)
+//     dQ  += dS   K  * a    (A = dS^T staged to smem and read as an MN-major A operand, B = K MN-major)
+// over 128-key tiles (outer) and 128-query chunks (inner); dV/dK accumulate in TMEM across query chunks, the two dQ
+// chunks accumulate in TMEM across key tiles.  TMEM columns: S^T [0,128) dP^T [128,256) dV [256..) dK [320..)
+// dQ0 [384..) dQ1 [448..).
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issue   warps 2-9: 256 compute/epilogue threads
+//   (warp w owns TMEM lanes 32*(w%4).., query-column half (w-2)/4).
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "attention_fused.h"
+#include "block_utils.cuh"
+#include "common.h"
+#include "sm100_ptx.cuh"
+
+namespace arb {
+
+constexpr int BWD_THREADS = 320;
+constexpr int TILE_BYTES = 128 * 128;     // one [128 rows][128 B] operand tile
+
+__device__ __forceinline__ float ex2_approx_b(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t round_tf32_b(float x) {
+  uint32_t y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
+  return y;
+}
+
+// delta[b,h,q] = sum_e dO[b,q,h,e] * O[b,q,h,e]        (one warp per row of the [B*S, d_model] activations)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict__ d_o, const float* __restrict__ o,
+                                                         long long pitch, int B, int S, int h, int dk,
+                                                         float* __restrict__ delta) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)B * S) return;
+  const int b = int(row / S), qi = int(row % S);
+  for (int hh = 0; hh < h; ++hh) {
+    float acc = 0.f;
+    for (int e = lane; e < dk; e += 32) acc += d_o[row * pitch + hh * dk + e] * o[row * pitch + hh * dk + e];
+    acc = warp_sum(acc);
+    if (lane == 0) delta[((long long)b * h + hh) * S + qi] = acc;
+  }
+}
+
+struct BwdSmem {
+  // operand tiles (DK <= 32 -> one 32-wide k-block / slab each)
+  static constexpr int K_KM = 0;                    // K tile, K-major   (A of S^T)
+  static constexpr int K_MN = 1;                    // K tile, MN-major  (B of dQ)
+  static constexpr int V_KM = 2;                    // V tile, K-major   (A of dP^T)
+  static constexpr int Q_KM = 3;                    // Q chunk, K-major  (B of S^T)
+  static constexpr int Q_MN = 4;                    // Q chunk, MN-major (B of dK)
+  static constexpr int DO_KM = 5;                   // dO chunk, K-major (B of dP^T)
+  static constexpr int DO_MN = 6;                   // dO chunk, MN-major(B of dV)
+  static constexpr int N_TILES = 7;
+  static constexpr int STAGE_OFF = N_TILES * TILE_BYTES;          // dS^T staging: 4 slabs x [128 key rows][128 B]
+  static constexpr int STAGE_BYTES = 4 * TILE_BYTES;
+  static constexpr int STATS_OFF = STAGE_OFF + STAGE_BYTES;       // float2 {nm_q, delta_q} x 128
+  static constexpr int BARS_OFF = STATS_OFF + 128 * 8;
+  static constexpr int total() { return BARS_OFF + 256 + 1024; }
+};
+
+template <int DK>
+__global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
+    const __grid_constant__ CUtensorMap tmQk, const __grid_constant__ CUtensorMap tmQm,
+    const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmKm,
+    const __grid_constant__ CUtensorMap tmVk, const __grid_constant__ CUtensorMap tmDOk,
+    const __grid_constant__ CUtensorMap tmDOm, const __grid_constant__ CUtensorMap tmDQ,
+    const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
+    const uint8_t* __restrict__ mask, const float* __restrict__ stat_max, const float* __restrict__ stat_sum,
+    const float* __restrict__ delta, int S, int n_heads, float scale) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  auto tile = [&](int t) { return smem + t * TILE_BYTES; };
+  uint8_t* stage = smem + BwdSmem::STAGE_OFF;
+  float2* qstats = reinterpret_cast<float2*>(smem + BwdSmem::STATS_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS_OFF);
+  uint64_t* kv_bar = bars;          // K/V tiles of this key tile landed        (one phase per key tile)
+  uint64_t* q_bar = bars + 1;       // Q/dO tiles of this iteration landed        (one phase per iteration)
+  uint64_t* s_bar = bars + 2;       // S^T and dP^T complete                      (per iteration)
+  uint64_t* p_bar = bars + 3;       // P^T / dS^T written by the 256 compute threads (per iteration)
+  uint64_t* mma_bar = bars + 4;     // trailing MMAs (dV, dK, dQ) complete        (per iteration)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int n_kt = (S + 127) / 128;     // key tiles == query chunks
+  const float c_log2e = scale * 1.4426950408889634f;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQk); ptx::prefetch_tmap(&tmQm); ptx::prefetch_tmap(&tmKk); ptx::prefetch_tmap(&tmKm);
+    ptx::prefetch_tmap(&tmVk); ptx::prefetch_tmap(&tmDOk); ptx::prefetch_tmap(&tmDOm);
+    ptx::mbar_init(kv_bar, 1);
+    ptx::mbar_init(q_bar, 1);
+    ptx::mbar_init(s_bar, 1);
+    ptx::mbar_init(p_bar, 256);
+    ptx::mbar_init(mma_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 320;
+  const uint32_t T_DQ0 = tmem_base + 384;   // + 64 * qc
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int jt = 0; jt < n_kt; ++jt) {
+        for (int qc = 0; qc < n_kt; ++qc, ++it) {
+          if (it > 0) ptx::mbar_wait(mma_bar, (it - 1) & 1);   // previous iteration's MMAs have consumed the tiles
+          if (qc == 0) {
+            ptx::mbar_expect_tx(kv_bar, 3 * TILE_BYTES);
+            ptx::tma_load_4d(tile(BwdSmem::K_KM), &tmKk, kv_bar, 0, 128 * jt, head, b);
+            ptx::tma_load_4d(tile(BwdSmem::K_MN), &tmKm, kv_bar, 0, 128 * jt, head, b);
+            ptx::tma_load_4d(tile(BwdSmem::V_KM), &tmVk, kv_bar, 0, 128 * jt, head, b);
+          }
+          ptx::mbar_expect_tx(q_bar, 4 * TILE_BYTES);
+          ptx::tma_load_4d(tile(BwdSmem::Q_KM), &tmQk, q_bar, 0, 128 * qc, head, b);
+          ptx::tma_load_4d(tile(BwdSmem::Q_MN), &tmQm, q_bar, 0, 128 * qc, head, b);
+          ptx::tma_load_4d(tile(BwdSmem::DO_KM), &tmDOk, q_bar, 0, 128 * qc, head, b);
+          ptx::tma_load_4d(tile(BwdSmem::DO_MN), &tmDOm, q_bar, 0, 128 * qc, head, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr int KSTEPS = (DK + 7) / 8;                 // contraction steps over the head width
+      constexpr int DKN = DK < 16 ? 16 : DK;               // UMMA N of the dk-wide outputs
+      const uint32_t id_st = ptx::idesc_tf32(128, 128, 0, 0);
+      const uint32_t id_ts = ptx::idesc_tf32(128, DKN, 0, 1);     // A from TMEM, B MN-major
+      const uint32_t id_dq = ptx::idesc_tf32(128, DKN, 1, 1);     // A MN-major (staged dS^T), B MN-major
+      const uint32_t kk = ptx::smem_u32(tile(BwdSmem::K_KM)), km = ptx::smem_u32(tile(BwdSmem::K_MN));
+      const uint32_t vk = ptx::smem_u32(tile(BwdSmem::V_KM));
+      const uint32_t qk = ptx::smem_u32(tile(BwdSmem::Q_KM)), qm = ptx::smem_u32(tile(BwdSmem::Q_MN));
+      const uint32_t dok = ptx::smem_u32(tile(BwdSmem::DO_KM)), dom = ptx::smem_u32(tile(BwdSmem::DO_MN));
+      const uint32_t sg = ptx::smem_u32(stage);
+      int it = 0;
+      for (int jt = 0; jt < n_kt; ++jt) {
+        for (int qc = 0; qc < n_kt; ++qc, ++it) {
+          if (qc == 0) ptx::mbar_wait(kv_bar, jt & 1);
+          ptx::mbar_wait(q_bar, it & 1);
+          ptx::tc_fence_after();
+          for (int k = 0; k < KSTEPS; ++k) {
+            ptx::mma_tf32_ss(T_ST, ptx::smem_desc_sw128<2>(kk + k * 32, 16, 1024),
+                             ptx::smem_desc_sw128<2>(qk + k * 32, 16, 1024), id_st, k > 0);
+          }
+          for (int k = 0; k < KSTEPS; ++k) {
+            ptx::mma_tf32_ss(T_DPT, ptx::smem_desc_sw128<2>(vk + k * 32, 16, 1024),
+                             ptx::smem_desc_sw128<2>(dok + k * 32, 16, 1024), id_st, k > 0);
+          }
+          ptx::mma_commit(s_bar);
+          ptx::mbar_wait(p_bar, it & 1);
+          ptx::tc_fence_after();
+          for (int i = 0; i < 16; ++i) {     // contraction over the 128 queries of this chunk
+            ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, ptx::smem_desc_sw128<1>(dom + i * 1024, TILE_BYTES, 512), id_ts,
+                             (qc > 0 || i > 0) ? 1u : 0u);
+          }
+          for (int i = 0; i < 16; ++i) {
+            ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, ptx::smem_desc_sw128<1>(qm + i * 1024, TILE_BYTES, 512), id_ts,
+                             (qc > 0 || i > 0) ? 1u : 0u);
+          }
+          for (int i = 0; i < 16; ++i) {     // contraction over the 128 keys of this tile
+            ptx::mma_tf32_ss(T_DQ0 + 64 * qc, ptx::smem_desc_sw128<1>(sg + i * 1024, TILE_BYTES, 512),
+                             ptx::smem_desc_sw128<1>(km + i * 1024, TILE_BYTES, 512), id_dq,
+                             (jt > 0 || i > 0) ? 1u : 0u);
+          }
+          ptx::mma_commit(mma_bar);
+        }
+      }
+    }
+  } else {
+    // ===================== compute + epilogue (256 threads) =====================
+    const int ct = threadIdx.x - 64;            // 0..255
+    const int quad = warp & 3;
+    const int row = 32 * quad + lane;           // key row inside the tile == TMEM lane
+    const int half = (warp - 2) >> 2;           // which 64 query columns of the chunk this warp handles
+    const uint32_t lane_addr = uint32_t(32 * quad) << 16;
+    int it = 0;
+    for (int jt = 0; jt < n_kt; ++jt) {
+      const int key = 128 * jt + row;
+      const bool key_ok = key < S && mask[size_t(b) * S + key] == 0;
+      for (int qc = 0; qc < n_kt; ++qc, ++it) {
+        // per-query statistics of this chunk -> smem (nm = -max*c - log2(sum); -inf for query rows past S)
+        if (it > 0) ptx::named_bar_sync(1, 256);          // everyone finished reading the previous chunk's stats
+        if (ct < 128) {
+          const int qi = 128 * qc + ct;
+          float2 st = make_float2(-CUDART_INF_F, 0.f);
+          if (qi < S) {
+            const size_t so = (size_t(b) * n_heads + head) * S + qi;
+            st.x = -(stat_max[so] * c_log2e) - log2f(stat_sum[so]);
+            st.y = delta[so];
+          }
+          qstats[ct] = st;
+        }
+        ptx::named_bar_sync(1, 256);
+        ptx::mbar_wait(s_bar, it & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int col0 = 64 * half + 32 * cc;           // first query column of this 32-wide piece
+          uint32_t sv[32], dv[32];
+          ptx::tmem_ld_32x32(T_ST + lane_addr + col0, sv);
+          ptx::tmem_ld_32x32(T_DPT + lane_addr + col0, dv);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 st = qstats[col0 + j];
+            const float p = key_ok ? ex2_approx_b(fmaf(__uint_as_float(sv[j]), c_log2e, st.x)) : 0.0f;
+            const float ds = p * (__uint_as_float(dv[j]) - st.y);
+            sv[j] = round_tf32_b(p);
+            dv[j] = round_tf32_b(ds);
+          }
+          ptx::tmem_st_32x32(T_ST + lane_addr + col0, sv);
+          ptx::tmem_st_32x32(T_DPT + lane_addr + col0, dv);
+          // dS^T also goes to shared memory as the MN-major A operand of dQ: slab = 32-query group, row = key
+          uint8_t* srow = stage + (col0 >> 5) * TILE_BYTES + row * 128;
+#pragma unroll
+          for (int piece = 0; piece < 8; ++piece) {
+            const int phys = (((piece >> 1) ^ (row & 3)) << 5) + ((piece & 1) << 4);
+            *reinterpret_cast<uint4*>(srow + phys) =
+                make_uint4(dv[piece * 4], dv[piece * 4 + 1], dv[piece * 4 + 2], dv[piece * 4 + 3]);
+          }
+        }
+        ptx::tmem_st_wait();
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(p_bar);
+
+        const bool last_qc = (qc == n_kt - 1);
+        const bool last_jt = (jt == n_kt - 1);
+        if (last_qc || last_jt) {
+          // ---- epilogue(s): accumulators that are now final
+          ptx::mbar_wait(mma_bar, it & 1);
+          ptx::tc_fence_after();
+          // up to 3 output tiles: dV_jt, dK_jt (when last_qc) and dQ_qc (when last_jt); warps of column-half 0
+          // read TMEM lanes, half 1 idles (DK <= 32 columns per tile)
+          for (int which = 0; which < 3; ++which) {
+            const bool do_it = (which < 2) ? last_qc : last_jt;
+            if (!do_it) continue;
+            const uint32_t src = which == 0 ? T_DV : (which == 1 ? T_DK : T_DQ0 + 64 * qc);
+            const float mul = which == 0 ? 1.0f : scale;
+            if (half == 0) {
+              uint32_t v[32];
+              ptx::tmem_ld_32x32(src + lane_addr, v);
+              ptx::tmem_ld_wait();
+              uint8_t* orow = stage + which * TILE_BYTES + row * 128;
+#pragma unroll
+              for (int piece = 0; piece < 8; ++piece) {
+                float4 o;
+                o.x = __uint_as_float(v[piece * 4 + 0]) * mul;
+                o.y = __uint_as_float(v[piece * 4 + 1]) * mul;
+                o.z = __uint_as_float(v[piece * 4 + 2]) * mul;
+                o.w = __uint_as_float(v[piece * 4 + 3]) * mul;
+                *reinterpret_cast<float4*>(orow + ((piece ^ (row & 7)) << 4)) = o;
+              }
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1, 256);
+          if (ct == 0) {
+            if (last_qc) {
+              ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * jt, head, b);
+              ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES, 0, 128 * jt, head, b);
+            }
+            if (last_jt) ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES, 0, 128 * qc, head, b);
+            ptx::tma_store_commit();
+            ptx::tma_store_wait_read();      // staging is reused by the next iteration
+          }
+          ptx::tc_fence_before();
+        }
+      }
+    }
+    if (ct == 0) ptx::tma_store_wait_all();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int DK>
+static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
+  alignas(64) CUtensorMap tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV;
+  int rc;
+  const TmapBox box{{32, 128, 1, 1}};
+  if ((rc = make_tmap_4d(&tQk, a.q, box, 0, 1))) return rc;
+  if ((rc = make_tmap_4d(&tQm, a.q, box, 1, 1))) return rc;
+  if ((rc = make_tmap_4d(&tKk, a.k, box, 0, 1))) return rc;
+  if ((rc = make_tmap_4d(&tKm, a.k, box, 1, 1))) return rc;
+  if ((rc = make_tmap_4d(&tVk, a.v, box, 0, 1))) return rc;
+  if ((rc = make_tmap_4d(&tDOk, a.d_o, box, 0, 1))) return rc;
+  if ((rc = make_tmap_4d(&tDOm, a.d_o, box, 1, 1))) return rc;
+  if ((rc = make_tmap_4d(&tDQ, a.dq, box, 0, 0))) return rc;
+  if ((rc = make_tmap_4d(&tDK, a.dk_, box, 0, 0))) return rc;
+  if ((rc = make_tmap_4d(&tDV, a.dv, box, 0, 0))) return rc;
+  {
+    ProfScope ps(ARB_PROF_SCORER_SIMT, double(a.B) * a.S * (8.0 * a.h * a.dk + 4.0 * a.h), st);
+    const long long rows = (long long)a.B * a.S;
+    attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(a.do_ptr, a.o_ptr, a.o_pitch, a.B, a.S, a.h, a.dk,
+                                                                a.delta);
+  }
+  arb_count_launch();
+  auto kern = attn_bwd_kernel<DK>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::total()) != cudaSuccess) {
+      arb_set_error("attn_bwd: cannot raise the dynamic shared memory limit");
+      return ARB_E_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid(a.h, a.B);
+  {
+    ProfScope ps(ARB_PROF_GEMM, 10.0 * double(a.S) * a.S * a.dk * a.h * a.B, st);
+    kern<<<grid, BWD_THREADS, BwdSmem::total(), st>>>(tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
+                                                      a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale);
+  }
+  arb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { arb_set_error(cudaGetErrorString(e)); return ARB_E_CUDA; }
+  return ARB_OK;
+}
+
+bool attn_fused_bwd_supported(int S, int dk) { return S >= 1 && S <= 256 && (dk == 16 || dk == 32); }
+
+int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t st) {
+  if (!attn_fused_bwd_supported(a.S, a.dk)) { arb_set_error("fused attention backward: unsupported shape"); return ARB_E_UNSUPPORTED; }
+  return a.dk == 16 ? launch_bwd_t<16>(a, st) : launch_bwd_t<32>(a, st);
+}
+
+}  // namespace arb

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "attention_fused.h"
 #include "common.h"
 #include "gemm_tf32.h"
 #include "scorer_kernels.h"
@@ -19,6 +20,16 @@
 namespace arb {
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// 0: unfused attention (materialised [B,h,S,S] logits, generic GEMMs)   1: fused forward kernel, unfused backward
+// 2 (default): fused forward and fused backward kernels
+static int g_attn_mode = 2;
+static bool use_fused(const arb_scorer_config& c, int S) {
+  return g_attn_mode >= 1 && c.n_layers > 0 && attn_fused_supported(S, c.d_model / c.n_heads);
+}
+static bool use_fused_bwd(const arb_scorer_config& c, int S) {
+  return g_attn_mode >= 2 && use_fused(c, S) && attn_fused_bwd_supported(S, c.d_model / c.n_heads);
+}
 
 struct ParamLayout {
   int64_t fc_w, fc_b;
@@ -69,15 +80,17 @@ static int make_param_layout(const arb_scorer_config& c, ParamLayout& L) {
 
 struct WsLayout {
   int64_t x0;
-  struct Layer { int64_t xn1, mean1, std1, qkv, prob, ctx, xmid, xn2, mean2, std2, hdn, xout; };
+  struct Layer { int64_t xn1, mean1, std1, qkv, prob, smax, ssum, ctx, xmid, xn2, mean2, std2, hdn, xout; };
   Layer layer[64];
   int64_t meanf, stdf, total;
   int Sp;
+  bool fused;
 };
 
 static void make_ws_layout(const arb_scorer_config& c, int B, int S, int training, WsLayout& W) {
   const int64_t R = int64_t(B) * S, d = c.d_model, f = c.d_ff, h = c.n_heads;
   W.Sp = int(align_up(S, 4));
+  W.fused = use_fused(c, S);
   int64_t o = 0;
   auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
   W.x0 = take(R * d);
@@ -87,7 +100,9 @@ static void make_ws_layout(const arb_scorer_config& c, int B, int S, int trainin
     if (training || l == 0) {
       y.xn1 = take(R * d); y.mean1 = take(R); y.std1 = take(R);
       y.qkv = take(R * 3 * d);
-      y.prob = take(int64_t(B) * h * S * W.Sp);
+      y.prob = W.fused ? 0 : take(int64_t(B) * h * S * W.Sp);
+      y.smax = take(int64_t(B) * h * S);
+      y.ssum = take(int64_t(B) * h * S);
       y.ctx = take(R * d);
       y.xn2 = training ? take(R * d) : y.xn1;
       y.mean2 = training ? take(R) : y.mean1;
@@ -201,24 +216,35 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     // ---- self-attention sublayer: x + O(attn(LN(x)))   (transformer.py:133, :105-106)
     ARB_TRY(ln_forward(xcur, P + pl.ln1_a, P + pl.ln1_b, c.ln_eps, k.R, d, xn1, ws + wl.mean1, ws + wl.std1, st));
     ARB_TRY(linear_fwd(k, xn1, d, d, P + pl.wqkv, P + pl.bqkv, 3 * d, qkv, 3 * d, 0, nullptr, 0));
-    {
-      GemmDesc g;   // logits = Q K^T / sqrt(dk)      (transformer.py:148)
-      g.M = S; g.N = S; g.K = dk; g.alpha = 1.0f / sqrtf(float(dk));
-      g.A = head_view(qkv, dk, S, h, B, 3 * d);
-      g.B = head_view(qkv + d, dk, S, h, B, 3 * d);
-      g.C = prob_view(prob, S, W.Sp, h, B);
-      batch_all(g, h, B); g.block_n = 64;
-      ARB_TRY(launch_gemm_tf32(g, st));
-    }
-    ARB_TRY(softmax_forward(prob, mask, B, h, S, W.Sp, st));   // key mask + softmax (transformer.py:150-153)
-    {
-      GemmDesc g;   // ctx = P V, written straight into the concatenated-heads layout (transformer.py:156, :201-202)
-      g.M = S; g.N = dk; g.K = S; g.b_mn = 1;
-      g.A = prob_view(prob, S, W.Sp, h, B);
-      g.B = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
-      g.C = head_view(ctx, dk, S, h, B, d);
-      batch_all(g, h, B); g.block_n = pick_block_n(dk);
-      ARB_TRY(launch_gemm_tf32(g, st));
+    if (W.fused) {
+      AttnFwdArgs a;   // QK^T, key mask, softmax, PV in one kernel; the S x S tile never leaves TMEM
+      a.q = head_view(qkv, dk, S, h, B, 3 * d);
+      a.k = head_view(qkv + d, dk, S, h, B, 3 * d);
+      a.v = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
+      a.o = head_view(ctx, dk, S, h, B, d);
+      a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum;
+      a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = 1.0f / sqrtf(float(dk));
+      ARB_TRY(launch_attn_fwd(a, st));
+    } else {
+      {
+        GemmDesc g;   // logits = Q K^T / sqrt(dk)      (transformer.py:148)
+        g.M = S; g.N = S; g.K = dk; g.alpha = 1.0f / sqrtf(float(dk));
+        g.A = head_view(qkv, dk, S, h, B, 3 * d);
+        g.B = head_view(qkv + d, dk, S, h, B, 3 * d);
+        g.C = prob_view(prob, S, W.Sp, h, B);
+        batch_all(g, h, B); g.block_n = 64;
+        ARB_TRY(launch_gemm_tf32(g, st));
+      }
+      ARB_TRY(softmax_forward(prob, mask, B, h, S, W.Sp, st));   // key mask + softmax (transformer.py:150-153)
+      {
+        GemmDesc g;   // ctx = P V, written straight into the concatenated-heads layout (transformer.py:156, :201-202)
+        g.M = S; g.N = dk; g.K = S; g.b_mn = 1;
+        g.A = prob_view(prob, S, W.Sp, h, B);
+        g.B = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
+        g.C = head_view(ctx, dk, S, h, B, d);
+        batch_all(g, h, B); g.block_n = pick_block_n(dk);
+        ARB_TRY(launch_gemm_tf32(g, st));
+      }
     }
     ARB_TRY(linear_fwd(k, ctx, d, d, P + pl.wo, P + pl.bo, d, xmid, d, EPI_ADD_AUX, xcur, d));
     // ---- feed-forward sublayer: x + W2 relu(W1 LN(x))   (transformer.py:134, :227)
@@ -233,7 +259,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   return ARB_OK;
 }
 
-struct ScratchLayout { int64_t dxa, dxb, dxn, dqkv, dctx, dprob, total; };
+struct ScratchLayout { int64_t dxa, dxb, dxn, dqkv, dctx, dprob, prob, delta, total; };
 static void make_scratch_layout(const arb_scorer_config& c, int B, int S, ScratchLayout& Z) {
   const int64_t R = int64_t(B) * S, d = c.d_model;
   const int Sp = int(align_up(S, 4));
@@ -241,9 +267,13 @@ static void make_scratch_layout(const arb_scorer_config& c, int B, int S, Scratc
   auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
   Z.dxa = take(R * d); Z.dxb = take(R * d); Z.dxn = take(R * d);
   if (c.n_layers > 0) {
-    Z.dqkv = take(R * 3 * d); Z.dctx = take(R * d); Z.dprob = take(int64_t(B) * c.n_heads * S * Sp);
+    Z.dqkv = take(R * 3 * d); Z.dctx = take(R * d);
+    const bool fb = use_fused_bwd(c, S);
+    Z.dprob = fb ? 0 : take(int64_t(B) * c.n_heads * S * Sp);
+    Z.prob = (use_fused(c, S) && !fb) ? take(int64_t(B) * c.n_heads * S * Sp) : 0;
+    Z.delta = fb ? take(int64_t(B) * c.n_heads * S) : 0;
   } else {
-    Z.dqkv = Z.dctx = Z.dprob = 0;
+    Z.dqkv = Z.dctx = Z.dprob = Z.prob = Z.delta = 0;
   }
   Z.total = o;
 }
@@ -280,7 +310,8 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     const auto& pl = L.layer[l];
     const auto& wl = W.layer[l];
     const float* xin = (l == 0) ? ws + W.x0 : ws + W.layer[l - 1].xout;
-    float* xn1 = ws + wl.xn1; float* qkv = ws + wl.qkv; float* prob = ws + wl.prob; float* ctx = ws + wl.ctx;
+    float* xn1 = ws + wl.xn1; float* qkv = ws + wl.qkv; float* ctx = ws + wl.ctx;
+    float* prob = W.fused ? scratch + Z.prob : ws + wl.prob;
     float* xmid = ws + wl.xmid; float* xn2 = ws + wl.xn2; float* hdn = ws + wl.hdn;
     // ---- feed-forward sublayer backward:  xout = xmid + W2 relu(W1 xn2 + b1) + b2
     ARB_TRY(linear_bwd_weight(k, dx, d, d, hdn, f, f, G + pl.w2));
@@ -296,42 +327,67 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(linear_bwd_weight(k, dx_alt, d, d, ctx, d, d, G + pl.wo));
     ARB_TRY(colsum_accumulate(dx_alt, k.R, d, d, G + pl.bo, st));
     ARB_TRY(linear_bwd_input(k, dx_alt, d, d, P + pl.wo, d, dctx, d, 0, nullptr, 0));
-    {
-      GemmDesc g;   // dP = dctx V^T
-      g.M = S; g.N = S; g.K = dk;
-      g.A = head_view(dctx, dk, S, h, B, d);
-      g.B = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
-      g.C = prob_view(dprob, S, W.Sp, h, B);
-      batch_all(g, h, B); g.block_n = 64;
-      ARB_TRY(launch_gemm_tf32(g, st));
-    }
-    {
-      GemmDesc g;   // dV = P^T dctx     (P read as an MN-major A operand, dctx as an MN-major B operand)
-      g.M = S; g.N = dk; g.K = S; g.a_mn = 1; g.b_mn = 1;
-      g.A = prob_view(prob, S, W.Sp, h, B);
-      g.B = head_view(dctx, dk, S, h, B, d);
-      g.C = head_view(dqkv + 2 * d, dk, S, h, B, 3 * d);
-      batch_all(g, h, B); g.block_n = pick_block_n(dk);
-      ARB_TRY(launch_gemm_tf32(g, st));
-    }
-    ARB_TRY(softmax_backward(dprob, prob, int64_t(B) * h * S, S, W.Sp, st));   // dprob <- dS (pre-scale)
-    {
-      GemmDesc g;   // dQ = alpha dS K
-      g.M = S; g.N = dk; g.K = S; g.b_mn = 1; g.alpha = alpha;
-      g.A = prob_view(dprob, S, W.Sp, h, B);
-      g.B = head_view(qkv + d, dk, S, h, B, 3 * d);
-      g.C = head_view(dqkv, dk, S, h, B, 3 * d);
-      batch_all(g, h, B); g.block_n = pick_block_n(dk);
-      ARB_TRY(launch_gemm_tf32(g, st));
-    }
-    {
-      GemmDesc g;   // dK = alpha dS^T Q
-      g.M = S; g.N = dk; g.K = S; g.a_mn = 1; g.b_mn = 1; g.alpha = alpha;
-      g.A = prob_view(dprob, S, W.Sp, h, B);
-      g.B = head_view(qkv, dk, S, h, B, 3 * d);
-      g.C = head_view(dqkv + d, dk, S, h, B, 3 * d);
-      batch_all(g, h, B); g.block_n = pick_block_n(dk);
-      ARB_TRY(launch_gemm_tf32(g, st));
+    if (use_fused_bwd(c, S)) {
+      AttnBwdArgs a;   // dQ, dK, dV from d ctx in one kernel; P is recomputed in TMEM from the saved row statistics
+      a.q = head_view(qkv, dk, S, h, B, 3 * d);
+      a.k = head_view(qkv + d, dk, S, h, B, 3 * d);
+      a.v = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
+      a.d_o = head_view(dctx, dk, S, h, B, d);
+      a.dq = head_view(dqkv, dk, S, h, B, 3 * d);
+      a.dk_ = head_view(dqkv + d, dk, S, h, B, 3 * d);
+      a.dv = head_view(dqkv + 2 * d, dk, S, h, B, 3 * d);
+      a.o_ptr = ctx; a.do_ptr = dctx; a.o_pitch = d;
+      a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum; a.delta = scratch + Z.delta;
+      a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = alpha;
+      ARB_TRY(launch_attn_bwd(a, st));
+    } else {
+      if (W.fused) {   // the fused forward kept no probabilities: recompute P = softmax(mask(alpha Q K^T))
+        GemmDesc g;
+        g.M = S; g.N = S; g.K = dk; g.alpha = alpha;
+        g.A = head_view(qkv, dk, S, h, B, 3 * d);
+        g.B = head_view(qkv + d, dk, S, h, B, 3 * d);
+        g.C = prob_view(prob, S, W.Sp, h, B);
+        batch_all(g, h, B); g.block_n = 64;
+        ARB_TRY(launch_gemm_tf32(g, st));
+        ARB_TRY(softmax_forward(prob, mask, B, h, S, W.Sp, st));
+      }
+      {
+        GemmDesc g;   // dP = dctx V^T
+        g.M = S; g.N = S; g.K = dk;
+        g.A = head_view(dctx, dk, S, h, B, d);
+        g.B = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
+        g.C = prob_view(dprob, S, W.Sp, h, B);
+        batch_all(g, h, B); g.block_n = 64;
+        ARB_TRY(launch_gemm_tf32(g, st));
+      }
+      {
+        GemmDesc g;   // dV = P^T dctx     (P read as an MN-major A operand, dctx as an MN-major B operand)
+        g.M = S; g.N = dk; g.K = S; g.a_mn = 1; g.b_mn = 1;
+        g.A = prob_view(prob, S, W.Sp, h, B);
+        g.B = head_view(dctx, dk, S, h, B, d);
+        g.C = head_view(dqkv + 2 * d, dk, S, h, B, 3 * d);
+        batch_all(g, h, B); g.block_n = pick_block_n(dk);
+        ARB_TRY(launch_gemm_tf32(g, st));
+      }
+      ARB_TRY(softmax_backward(dprob, prob, int64_t(B) * h * S, S, W.Sp, st));   // dprob <- dS (pre-scale)
+      {
+        GemmDesc g;   // dQ = alpha dS K
+        g.M = S; g.N = dk; g.K = S; g.b_mn = 1; g.alpha = alpha;
+        g.A = prob_view(dprob, S, W.Sp, h, B);
+        g.B = head_view(qkv + d, dk, S, h, B, 3 * d);
+        g.C = head_view(dqkv, dk, S, h, B, 3 * d);
+        batch_all(g, h, B); g.block_n = pick_block_n(dk);
+        ARB_TRY(launch_gemm_tf32(g, st));
+      }
+      {
+        GemmDesc g;   // dK = alpha dS^T Q
+        g.M = S; g.N = dk; g.K = S; g.a_mn = 1; g.b_mn = 1; g.alpha = alpha;
+        g.A = prob_view(dprob, S, W.Sp, h, B);
+        g.B = head_view(qkv, dk, S, h, B, 3 * d);
+        g.C = head_view(dqkv + d, dk, S, h, B, 3 * d);
+        batch_all(g, h, B); g.block_n = pick_block_n(dk);
+        ARB_TRY(launch_gemm_tf32(g, st));
+      }
     }
     ARB_TRY(linear_bwd_weight(k, dqkv, 3 * d, 3 * d, xn1, d, d, G + pl.wqkv));
     ARB_TRY(colsum_accumulate(dqkv, k.R, 3 * d, 3 * d, G + pl.bqkv, st));
@@ -349,6 +405,8 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
 }  // namespace arb
 
 using namespace arb;
+
+extern "C" void arb_set_attention_mode(int32_t mode) { g_attn_mode = mode; }
 
 extern "C" int64_t arb_scorer_param_count(const arb_scorer_config* cfg) {
   ParamLayout L;

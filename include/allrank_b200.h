@@ -162,6 +162,11 @@ int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, c
                             float* workspace, int64_t workspace_floats, float* scratch, int64_t scratch_floats,
                             void* stream);
 
+/* 0: unfused attention (materialised logits + generic GEMMs); 1: fused tcgen05 attention forward kernel, unfused
+ * backward; 2 (default): fused forward and backward kernels.  Fused kernels serve slates of <= 256 items (backward:
+ * head width <= 32); other shapes use the unfused path automatically.  Process-wide; exists for A/B tests. */
+void arb_set_attention_mode(int32_t mode);
+
 /* 1 (default): MMA operands are rounded fp32 -> tf32 by the TMA unit (TFLOAT32 tensor maps); 0: the tensor core
  * truncates.  Process-wide; exists for the precision tests. */
 void arb_set_tf32_round_on_load(int32_t enable);
