@@ -43,7 +43,8 @@ __device__ __forceinline__ uint32_t round_tf32_b(float x) {
   return y;
 }
 
-// delta[b,h,q] = sum_e dO[b,q,h,e] * O[b,q,h,e]        (one warp per row of the [B*S, d_model] activations)
+// delta[b,h,q] = sum_e dO[b,q,h,e] * O[b,q,h,e]: one warp per row of the [B*S, d_model] activations, 128-bit loads,
+// segmented shuffle reduction over the dk/4 lanes that share a head (dk in {16, 32}: 4 or 8 lanes per head).
 __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict__ d_o, const float* __restrict__ o,
                                                          long long pitch, int B, int S, int h, int dk,
                                                          float* __restrict__ delta) {
@@ -51,11 +52,17 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)B * S) return;
   const int b = int(row / S), qi = int(row % S);
-  for (int hh = 0; hh < h; ++hh) {
+  const int width = h * dk, lanes_per_head = dk >> 2;
+  for (int c0 = 0; c0 < width; c0 += 128) {
+    const int c = c0 + lane * 4;
     float acc = 0.f;
-    for (int e = lane; e < dk; e += 32) acc += d_o[row * pitch + hh * dk + e] * o[row * pitch + hh * dk + e];
-    acc = warp_sum(acc);
-    if (lane == 0) delta[((long long)b * h + hh) * S + qi] = acc;
+    if (c < width) {
+      const float4 a = *reinterpret_cast<const float4*>(d_o + row * pitch + c);
+      const float4 bq = *reinterpret_cast<const float4*>(o + row * pitch + c);
+      acc = a.x * bq.x + a.y * bq.y + a.z * bq.z + a.w * bq.w;
+    }
+    for (int off = lanes_per_head >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+    if (c < width && (lane % lanes_per_head) == 0) delta[((long long)b * h + c / dk) * S + qi] = acc;
   }
 }
 

@@ -49,8 +49,16 @@ struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGING_BYTES = BLOCK_M * BLOCK_N * 4;
-  static constexpr int stages() { return BLOCK_N <= 64 ? 4 : 3; }
-  static constexpr int total() { return stages() * STAGE_BYTES + STAGING_BYTES + 256 + BLOCK_N * 4 + 1024; }
+  // Two stages: the contraction is short (K = 32..512) and latency is hidden by co-resident CTAs instead
+  // (~80 KB per CTA with an epilogue tile -> 2 per SM; ~50 KB without -> 4 per SM).
+  static constexpr int stages() { return 2; }
+  static constexpr int pipe_bytes() { return stages() * STAGE_BYTES; }
+  // without an aux (residual / mask) tile the output staging aliases the operand ring: it is only written after
+  // the last MMA has consumed the ring
+  static constexpr int total(bool with_aux) {
+    return (with_aux ? pipe_bytes() + STAGING_BYTES : (pipe_bytes() > STAGING_BYTES ? pipe_bytes() : STAGING_BYTES)) +
+           256 + BLOCK_N * 4 + 1024;
+  }
 };
 
 template <int BLOCK_N, int A_MN, int B_MN>
@@ -66,13 +74,16 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
 
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + STAGES * L::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + L::STAGING_BYTES);
+  const bool has_aux = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
+  uint8_t* staging = has_aux ? smem + L::pipe_bytes() : smem;
+  uint8_t* tail = smem + (has_aux ? L::pipe_bytes() + L::STAGING_BYTES
+                                  : (L::pipe_bytes() > L::STAGING_BYTES ? L::pipe_bytes() : L::STAGING_BYTES));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* aux_bar = tmem_full_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 1);
-  float* bias_s = reinterpret_cast<float*>(staging + L::STAGING_BYTES + 256);
+  float* bias_s = reinterpret_cast<float*>(tail + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
@@ -82,7 +93,6 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
   const int kb_begin = split ? int(blockIdx.z) * p.kb_per_split : 0;
   const int kb_end = split ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
   const int nkb = kb_end - kb_begin;
-  const bool has_aux = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
         for (int c = 0; c < N_SLABS; ++c)
           ptx::tma_store_4d(&tmC, staging + c * (BLOCK_M * 128), n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
         ptx::tma_store_commit();
-        ptx::tma_store_wait_all();
+        ptx::tma_store_wait_read();   // smem may be released once the TMA engine has read it
       }
     }
     ptx::tc_fence_before();
@@ -289,10 +299,11 @@ template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
   auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
-  constexpr int smem = SmemLayout<BLOCK_N>::total();
+  const bool with_aux = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
+  const int smem = SmemLayout<BLOCK_N>::total(with_aux);
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BLOCK_N>::total(true)) != cudaSuccess) {
       arb_set_error("gemm_tf32: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }

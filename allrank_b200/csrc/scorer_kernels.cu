@@ -234,15 +234,50 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(float* __restrict__ dp
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
-// out[c] += sum_rows in[row, c]   (bias gradients).  grid.x = row chunks, threads over columns.
+// out[c] += sum_rows in[row, c]   (bias gradients).  A warp reads whole rows with 128-bit loads (4 rows in
+// flight per lane), 8 warps per block stride over the block's rows, then one shared-memory reduction and one
+// atomicAdd per column per block.
+template <int NV>
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ in, long long rows, int width,
                                                      long long ld, int rows_per_block, float* __restrict__ out) {
+  __shared__ float sh[8][128 * NV + 4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
+  RowRegs<NV> acc;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long r = r0 + wid;
+  for (; r + 24 < r1; r += 32) {
+    RowRegs<NV> a0, a1, a2, a3;
+    load_row<NV>(in + r * ld, width, lane, a0);
+    load_row<NV>(in + (r + 8) * ld, width, lane, a1);
+    load_row<NV>(in + (r + 16) * ld, width, lane, a2);
+    load_row<NV>(in + (r + 24) * ld, width, lane, a3);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      acc.v[k].x += (a0.v[k].x + a1.v[k].x) + (a2.v[k].x + a3.v[k].x);
+      acc.v[k].y += (a0.v[k].y + a1.v[k].y) + (a2.v[k].y + a3.v[k].y);
+      acc.v[k].z += (a0.v[k].z + a1.v[k].z) + (a2.v[k].z + a3.v[k].z);
+      acc.v[k].w += (a0.v[k].w + a1.v[k].w) + (a2.v[k].w + a3.v[k].w);
+    }
+  }
+  for (; r < r1; r += 8) {
+    RowRegs<NV> a0;
+    load_row<NV>(in + r * ld, width, lane, a0);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      acc.v[k].x += a0.v[k].x; acc.v[k].y += a0.v[k].y; acc.v[k].z += a0.v[k].z; acc.v[k].w += a0.v[k].w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) *reinterpret_cast<float4*>(&sh[wid][lane * 4 + 128 * k]) = acc.v[k];
+  __syncthreads();
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    float acc = 0.f;
-    for (long long r = r0; r < r1; ++r) acc += in[r * ld + c];
-    atomicAdd(out + c, acc);
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][c];
+    atomicAdd(out + c, t);
   }
 }
 
@@ -480,9 +515,11 @@ int softmax_backward(float* dp, const float* prob, long long rows, int S, int pi
 }
 
 int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st) {
-  const int rpb = 128;
+  if (width % 4 || ld % 4) { arb_set_error("colsum: width and pitch must be multiples of 4"); return ARB_E_UNSUPPORTED; }
+  const int rpb = 256;
+  const unsigned blocks = unsigned((rows + rpb - 1) / rpb);
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 4.0 * width, st);
-  colsum_kernel<<<unsigned((rows + rpb - 1) / rpb), 256, 0, st>>>(in, rows, width, ld, rpb, out);
+  ARB_DISPATCH_NV(width, (colsum_kernel<NV><<<blocks, 256, 0, st>>>(in, rows, width, ld, rpb, out)));
   return check_launch();
 }
 
