@@ -1,0 +1,102 @@
+"""world_size-2 gloo test of the data-parallel host logic (allrank_b200/ddp.py) on CPU tensors:
+rank replicas start identical after the parameter broadcast, and the single flat-bucket all-reduce reproduces
+the single-process gradient of the concatenated batch for a mean-over-batch loss (average=True) and for a
+sum-reduced loss (average=False).   The kernels themselves need a GPU; here the "model" is a flat parameter
+vector with a hand-written listwise gradient so that only the collective logic is under test."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class FlatToy:
+    """Minimal stand-in with the two attributes FlatDDP uses (flat_parameters / flat_gradients)."""
+
+    def __init__(self, n, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.flat_parameters = torch.randn(n, generator=g)
+        self.flat_gradients = torch.zeros(n)
+
+    def loss_and_grad(self, x, y, reduction):
+        # listNet-like: softmax cross entropy of scores x @ w against softmax(labels), per slate
+        w = self.flat_parameters.clone().requires_grad_(True)
+        scores = x @ w
+        per_slate = -(torch.softmax(y, 1) * torch.log_softmax(scores, 1)).sum(1)
+        loss = per_slate.mean() if reduction == "mean" else per_slate.sum()
+        loss.backward()
+        self.flat_gradients.copy_(w.grad)
+        return loss.item()
+
+
+def _worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from allrank_b200.ddp import FlatDDP
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(123)
+    x_all = torch.randn(8, 6, 5, generator=g)          # 8 slates x 6 items x 5 features
+    y_all = torch.randint(0, 5, (8, 6), generator=g).float()
+    shard = slice(rank * 4, rank * 4 + 4)
+    results = {}
+    for reduction, average in (("mean", True), ("sum", False)):
+        model = FlatToy(5, seed=100 + rank)             # ranks start DIFFERENT on purpose
+        ddp = FlatDDP(model, average=average)
+        ddp.sync_parameters()
+        params_after_sync = model.flat_parameters.clone()
+        model.loss_and_grad(x_all[shard], y_all[shard], reduction)
+        scale = ddp.reduce_gradients()
+        assert scale == 1.0
+        results[reduction] = (params_after_sync, model.flat_gradients.clone())
+        # folded averaging: pure sum reduce, scale handed to the optimiser
+        model.loss_and_grad(x_all[shard], y_all[shard], reduction)
+        scale = ddp.reduce_gradients(fold_average_into_optimizer=True)
+        results[reduction + "_folded"] = (scale, model.flat_gradients.clone())
+    if rank == 0:
+        ref = FlatToy(5, seed=100)
+        single = {}
+        for reduction in ("mean", "sum"):
+            ref.loss_and_grad(x_all, y_all, reduction)
+            single[reduction] = ref.flat_gradients.clone()
+        out_q.put((results, single, ref.flat_parameters.clone()))
+    else:
+        out_q.put(({k: v[0] if not isinstance(v[0], float) else None for k, v in results.items()}, None, None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_matches_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rank0 = next(g for g in got if g[1] is not None)
+    other = next(g for g in got if g[1] is None)
+    results, single, ref_params = rank0
+    # broadcast: both ranks hold rank 0's parameters
+    assert torch.equal(results["mean"][0], ref_params)
+    assert torch.equal(other[0]["mean"], ref_params)
+    # mean-over-batch loss: averaged shard gradients == gradient of the full batch
+    assert torch.allclose(results["mean"][1], single["mean"], rtol=1e-5, atol=1e-7)
+    # sum-reduced loss (lambdaLoss default): summed shard gradients == gradient of the full batch
+    assert torch.allclose(results["sum"][1], single["sum"], rtol=1e-5, atol=1e-7)
+    # folded averaging returns the optimiser scale instead of touching the buffer
+    scale, summed = results["mean_folded"]
+    assert scale == 0.5
+    assert torch.allclose(summed * scale, single["mean"], rtol=1e-5, atol=1e-7)
+    scale, summed = results["sum_folded"]
+    assert scale == 1.0
