@@ -55,10 +55,10 @@ struct SmemLayout {
   static constexpr int pipe_bytes() { return stages() * STAGE_BYTES; }
   // without an aux (residual / mask) tile the output staging aliases the operand ring: it is only written after
   // the last MMA has consumed the ring
-  static constexpr int total(bool with_aux) {
-    return (with_aux ? pipe_bytes() + STAGING_BYTES : (pipe_bytes() > STAGING_BYTES ? pipe_bytes() : STAGING_BYTES)) +
-           256 + BLOCK_N * 4 + 1024;
-  }
+  // The output staging tile (and the residual / mask tile, fetched only after the last MMA) aliases the operand
+  // ring: both are touched only once every MMA of the CTA has completed.
+  static constexpr int body_bytes() { return pipe_bytes() > STAGING_BYTES ? pipe_bytes() : STAGING_BYTES; }
+  static constexpr int total() { return body_bytes() + 256 + BLOCK_N * 4 + 1024; }
 };
 
 template <int BLOCK_N, int A_MN, int B_MN>
@@ -75,9 +75,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const bool has_aux = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
-  uint8_t* staging = has_aux ? smem + L::pipe_bytes() : smem;
-  uint8_t* tail = smem + (has_aux ? L::pipe_bytes() + L::STAGING_BYTES
-                                  : (L::pipe_bytes() > L::STAGING_BYTES ? L::pipe_bytes() : L::STAGING_BYTES));
+  uint8_t* staging = smem;
+  uint8_t* tail = smem + L::body_bytes();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -113,11 +112,6 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if (has_aux) {
-        ptx::mbar_expect_tx(aux_bar, L::STAGING_BYTES);
-        for (int c = 0; c < N_SLABS; ++c)
-          ptx::tma_load_4d(staging + c * (BLOCK_M * 128), &tmAux, aux_bar, n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
-      }
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES, round = i / STAGES;
         if (round > 0) ptx::mbar_wait(&empty_bar[s], (round - 1) & 1);
@@ -137,6 +131,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
         } else {
           ptx::tma_load_4d(b_s, &tmB, &full_bar[s], k0, n0, b2 * p.b_b2, b3 * p.b_b3);
         }
+      }
+      if (has_aux) {
+        // the residual / ReLU-mask tile goes into the staging area, i.e. over the operand ring: wait until the
+        // tensor core has finished reading it
+        if (nkb > 0) ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::mbar_expect_tx(aux_bar, L::STAGING_BYTES);
+        for (int c = 0; c < N_SLABS; ++c)
+          ptx::tma_load_4d(staging + c * (BLOCK_M * 128), &tmAux, aux_bar, n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
       }
     }
   } else if (warp == 1) {
@@ -299,11 +301,10 @@ template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
   auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
-  const bool with_aux = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
-  const int smem = SmemLayout<BLOCK_N>::total(with_aux);
+  constexpr int smem = SmemLayout<BLOCK_N>::total();
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<BLOCK_N>::total(true)) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       arb_set_error("gemm_tf32: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }

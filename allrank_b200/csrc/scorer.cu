@@ -131,7 +131,7 @@ struct Ctx {
 static TRef rows_view(const float* p, int64_t inner, int64_t rows, int64_t pitch) {
   TRef t; t.ptr = p; t.dim[0] = inner; t.dim[1] = rows; t.stride[0] = 1; t.stride[1] = pitch; return t;
 }
-static int pick_block_n(int n) { return n <= 32 ? 32 : 64; }
+static int pick_block_n(int n) { return n <= 32 ? 32 : (n < 128 ? 64 : 128); }
 
 // Y[R,out] = epi( X[R,in] W[out,in]^T + bias )
 static int linear_fwd(const Ctx& k, const float* X, int64_t x_pitch, int in, const float* Wt, const float* bias, int out,

@@ -291,19 +291,20 @@ def run_b200(args, w):
 
     # ---- (3) per-launch device timing of every kernel class (roofline), a few extra steps
     prof = {}
+    lib = _lib.lib()
+    lib.arb_prof_enable.argtypes = [ctypes.c_int32]
+    lib.arb_prof_collect.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     if rank == 0:
-        lib = _lib.lib()
-        lib.arb_prof_enable.argtypes = [ctypes.c_int32]
-        lib.arb_prof_collect.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
-                                         ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
         lib.arb_prof_enable(1)
-        psteps = 3
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pe0.record()
-        for _ in range(psteps):
-            step(x_dev, y_dev)
-        pe1.record()
-        torch.cuda.synchronize()
+    psteps = 3
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(psteps):          # every rank runs these steps (they contain the gradient all-reduce)
+        step(x_dev, y_dev)
+    pe1.record()
+    torch.cuda.synchronize()
+    if rank == 0:
         names = ["gemm_tf32", "scorer_simt", "loss", "metrics", "adam"]
         for cls, nm in enumerate(names):
             ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
