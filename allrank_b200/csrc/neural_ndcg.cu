@@ -30,7 +30,8 @@ namespace arb {
 
 struct NeuralCfg {
   float pad, tau, tol;
-  int powered, k, max_iter;
+  int powered, k, max_iter;      // powered: 0 = identity gains, 1 = 2^x-1 gains and ideal DCG,
+                                 //          2 = identity gains but 2^x-1 ideal DCG (neuralNDCG_transposed, :126-128)
 };
 
 constexpr int NN_THREADS = 256;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(NN_THREADS) neural_ndcg_kernel(
       uint32_t o = ~ikeys[j];
       float lab = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
       if (lab == -CUDART_INF_F) lab = 0.0f;
-      const float gain = cfg.powered ? pow2_minus_1(lab) : lab;
+      const float gain = cfg.powered != 0 ? pow2_minus_1(lab) : lab;
       acc += double(gain * discounts[j]);
     }
     red[32] = float(acc);
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(NN_THREADS) neural_ndcg_kernel(
     const int p = pos[a];
     const float lab = yt[p];
     s[a] = yp[p];
-    g[a] = cfg.powered ? pow2_minus_1(lab) : lab;
+    g[a] = cfg.powered == 1 ? pow2_minus_1(lab) : lab;
     coef[a] = (p < n) ? float(n + 1 - 2 * (p + 1)) : 0.0f;           // loss_utils.py:54-56
     alpha[a] = (p < kk) ? -discounts[p] / (idcg + NN_EPS) : 0.0f;    // neuralNDCG.py:53-61
     u[a] = 1.0f;

@@ -11,7 +11,7 @@ from . import losses as _losses
 from . import metrics as _metrics
 from . import model as _model
 
-LOSS_NAMES = ("listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG")
+LOSS_NAMES = ("listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "neuralNDCG_transposed")
 METRIC_NAMES = ("ndcg", "dcg", "mrr")
 
 

@@ -141,32 +141,65 @@ def lambdaLoss(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_
     return _run(y_pred, y_true, launch)
 
 
+def _neural_ndcg_launch(scores_2d, labels_2d, pad, temperature, powered, kk, max_iter, tol):
+    """Deterministic NeuralSort + Sinkhorn + soft DCG on [N,S] rows (N = slates, or samples x slates)."""
+    S = scores_2d.shape[-1]
+    dev = scores_2d.device
+    disc = discount_table(S, dev)
+    ws_bytes = int(_lib.lib().arb_neural_ndcg_workspace_bytes(scores_2d.shape[0], S, int(max_iter)))
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+
+    def launch(s, t, B, S_, loss, grad, scratch):
+        rc = _lib.lib().arb_neural_ndcg(_lib.ptr(s), _lib.ptr(t), B, S_, _lib.ptr(disc), float(pad), float(temperature),
+                                        int(powered), kk, int(max_iter), float(tol), _lib.ptr(loss),
+                                        _lib.ptr(grad), _lib.ptr(scratch), _lib.ptr(ws), ws_bytes,
+                                        _lib.stream_ptr(s.device))
+        _lib.check(rc, "arb_neural_ndcg")
+
+    return _run(scores_2d, labels_2d, launch)
+
+
+def _gumbel_perturbed(y_pred, n_samples, beta, log_scores, eps=1e-10):
+    """stochastic_neural_sort's score perturbation (loss_utils.py:96-104): O(S) host-side tensor algebra, kept in
+    PyTorch so autograd carries the gradient back to y_pred; the O(S^2) part stays in the fused kernel."""
+    s_positive = y_pred + torch.abs(y_pred.min())
+    u = torch.rand([n_samples, y_pred.shape[0], y_pred.shape[1]], device=y_pred.device)
+    samples = beta * (-torch.log(-torch.log(u + eps) + eps))          # sample_gumbel, loss_utils.py:70-81
+    if log_scores:
+        s_positive = torch.log(s_positive + eps)
+    return (s_positive.unsqueeze(0) + samples).reshape(n_samples * y_pred.shape[0], y_pred.shape[1])
+
+
 def neuralNDCG(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE, temperature=1., powered_relevancies=True, k=None,
-               stochastic=False, n_samples=32, beta=0.1, log_scores=True, max_iter=50, tol=1e-6):
+               stochastic=False, n_samples=32, beta=0.1, log_scores=True, max_iter=50, tol=1e-6, _gain_mode=None):
     """NeuralNDCG loss -- neuralNDCG.py:10-70.
 
     `max_iter` / `tol` are the Sinkhorn parameters the reference hard-codes to 50 / 1e-6 (:41-42); they are
     exposed here (defaults unchanged) because BASELINE.json also quotes a 30-iteration configuration.
-    The stochastic (Gumbel) variant is a SURVEY.md 8(f) "next" row and is not built yet.
+    stochastic=True draws n_samples Gumbel perturbations per slate (loss_utils.py:84-112) and averages over
+    samples x slates-with-idcg>0 exactly like neuralNDCG.py:69 (statistical parity: the RNG stream differs).
     """
-    if stochastic:
-        raise NotImplementedError("stochastic NeuralSort is not implemented in allrank_b200 yet (no CPU fallback)")
     kk = 0 if k is None else int(k)
-    S = y_pred.shape[-1]
-    dev = y_pred.device
-    disc = discount_table(S, dev)
-    ws_bytes = int(_lib.lib().arb_neural_ndcg_workspace_bytes(y_pred.shape[0], S, int(max_iter)))
-    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
-
-    def launch(s, t, B, S_, loss, grad, scratch):
-        rc = _lib.lib().arb_neural_ndcg(_lib.ptr(s), _lib.ptr(t), B, S_, _lib.ptr(disc),
-                                        float(padded_value_indicator), float(temperature),
-                                        1 if powered_relevancies else 0, kk, int(max_iter), float(tol),
-                                        _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(scratch), _lib.ptr(ws), ws_bytes,
-                                        _lib.stream_ptr(s.device))
-        _lib.check(rc, "arb_neural_ndcg")
-
-    return _run(y_pred, y_true, launch)
+    if stochastic:
+        scores = _gumbel_perturbed(y_pred, int(n_samples), float(beta), bool(log_scores))
+        labels = y_true.repeat(int(n_samples), 1)
+    else:
+        scores, labels = y_pred, y_true
+    mode = _gain_mode if _gain_mode is not None else (1 if powered_relevancies else 0)
+    return _neural_ndcg_launch(scores, labels, padded_value_indicator, temperature, mode, kk, max_iter, tol)
 
 
-__all__ = ["listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "DEFAULT_EPS", "PADDED_Y_VALUE"]
+def neuralNDCG_transposed(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE, temperature=1.,
+                          powered_relevancies=True, k=None, stochastic=False, n_samples=32, beta=0.1, log_scores=True,
+                          max_iter=50, tol=1e-6):
+    """NeuralNDCG Transposed -- neuralNDCG.py:73-136.  It evaluates sum_i g_i (P^T disc)_i, which is the same
+    bilinear form sum_{j,i} disc_j P[j,i] g_i as neuralNDCG (:48-55) on the same Sinkhorn-scaled matrix, with the
+    same mean over slates with idcg != 0, so both names map onto one kernel; the transposed signature exposes
+    max_iter / tol (:75).  Quirk kept: with powered_relevancies=False the reference still normalises by the
+    2^x-1 ideal DCG (:126-128)."""
+    return neuralNDCG(y_pred, y_true, padded_value_indicator, temperature, powered_relevancies, k, stochastic,
+                      n_samples, beta, log_scores, max_iter, tol, _gain_mode=1 if powered_relevancies else 2)
+
+
+__all__ = ["listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "neuralNDCG_transposed", "DEFAULT_EPS",
+           "PADDED_Y_VALUE"]

@@ -249,12 +249,37 @@ def neuralNDCG(y_pred, y_true, padded_value_indicator=PAD, temperature=1.0, powe
     return -1.0 * (val.sum() / (~dead).sum())
 
 
+def neuralNDCG_transposed(y_pred, y_true, padded_value_indicator=PAD, temperature=1.0, powered_relevancies=True,
+                          k=None, stochastic=False, n_samples=32, beta=0.1, log_scores=True, max_iter=50, tol=1e-6):
+    """neuralNDCG.py:73-136: expected discounts P^T disc (truncated at k), times gains, over (idcg + eps)."""
+    if stochastic:
+        raise NotImplementedError("oracle restates the deterministic variant only")
+    if k is None:
+        k = y_true.shape[1]
+    mask = y_true == padded_value_indicator
+    P = deterministic_neural_sort(y_pred.unsqueeze(-1), tau=temperature, mask=mask)
+    P = sinkhorn_scaling(P, mask, tol=tol, max_iter=max_iter)
+    disc = (torch.tensor(1) / torch.log2(torch.arange(y_true.shape[-1], dtype=torch.float) + 2.0)).to(y_pred.device)
+    disc = disc.clone()
+    disc[k:] = 0.0
+    expected = torch.matmul(P.permute(0, 2, 1), disc[None, :, None]).squeeze(-1)
+    gains = torch.pow(2.0, y_true) - 1 if powered_relevancies else y_true
+    idcg = _dcg(y_true, y_true, ats=[k]).squeeze(1)
+    val = (gains * expected).sum(dim=1) / (idcg + EPS)
+    dead = idcg == 0.0
+    val = val.masked_fill(dead, 0.0)
+    if bool(dead.all()):
+        return torch.tensor(0.0)
+    return -1.0 * (val.sum() / (~dead).sum())
+
+
 LOSSES = {
     "listNet": listNet,
     "listMLE": listMLE,
     "approxNDCGLoss": approxNDCGLoss,
     "lambdaLoss": lambdaLoss,
     "neuralNDCG": neuralNDCG,
+    "neuralNDCG_transposed": neuralNDCG_transposed,
 }
 
 LN2 = math.log(2.0)

@@ -44,6 +44,9 @@ LOSS_CASES = [
     ("neuralNDCG", {}),
     ("neuralNDCG", {"temperature": 0.1, "k": 10}),
     ("neuralNDCG", {"powered_relevancies": False, "temperature": 3.0}),
+    ("neuralNDCG_transposed", {"temperature": 0.5, "k": 5}),
+    ("neuralNDCG_transposed", {"max_iter": 20, "tol": 1e-4}),
+    ("neuralNDCG_transposed", {"powered_relevancies": False}),
 ]
 SHAPES = [(5, 7), (4, 33), (3, 120), (3, 240)]
 
@@ -73,7 +76,7 @@ def gen_losses():
     for ci, (name, kw) in enumerate(LOSS_CASES):
         fn = getattr(ref_losses, name)
         for (b, s) in SHAPES:
-            if name == "neuralNDCG" and s > 120:
+            if name.startswith("neuralNDCG") and s > 120:
                 continue
             key = f"c{ci}_s{s}"
             yp, y = case_inputs(b, s, seed=100 * ci + s)
@@ -82,7 +85,7 @@ def gen_losses():
             blob[key + "_true"] = y.numpy()
             blob[key + "_loss32"] = v32.numpy()
             blob[key + "_grad32"] = g32.numpy()
-            if name != "neuralNDCG":   # reference neuralNDCG builds fp32 helpers internally; no fp64 run
+            if not name.startswith("neuralNDCG"):   # reference neuralNDCG builds fp32 helpers internally; no fp64 run
                 v64, g64 = run_loss(fn, yp, y, kw, torch.float64)
                 blob[key + "_loss64"] = v64.numpy()
                 blob[key + "_grad64"] = g64.numpy()

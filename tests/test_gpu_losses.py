@@ -76,7 +76,7 @@ def test_golden_losses(L, golden):
         assert abs(val - ref) <= tol, (key, name, kw, val, ref)
         scale = max(np.abs(gref).max(), 1e-12)
         gnoise = np.abs(g[key + "_grad64"] - gref).max() if key + "_grad64" in g.files else 0.0
-        gtol = (1e-5 if name != "neuralNDCG" else 2e-4) * scale + 2 * gnoise
+        gtol = (1e-5 if not name.startswith("neuralNDCG") else 2e-4) * scale + 2 * gnoise
         err = np.abs(grad - gref).max()
         worst[name] = max(worst.get(name, 0.0), err / scale)
         assert err <= gtol, (key, name, kw, err, scale)
@@ -204,3 +204,29 @@ def test_all_padded_or_no_relevant_slates(L):
     # neuralNDCG with every slate dead returns 0 (neuralNDCG.py:66-67)
     z = L.neuralNDCG(p, dev([[0.0, 0.0, 0.0, -1.0], [0.0, 0.0, -1.0, -1.0]]))
     assert z.item() == 0.0
+
+
+def test_stochastic_neuralndcg_statistics(L):
+    """Gumbel-perturbed NeuralSort (loss_utils.py:84-112): the RNG stream cannot match the reference, so parity is
+    statistical -- with beta -> 0 it must reproduce the deterministic loss of log-transformed scores, it must be
+    finite with a finite gradient, and its mean over many samples must sit close to the small-beta value."""
+    from allrank_b200.synth import make_slates, make_scores
+    _, y, _ = make_slates(6, 40, n_features=1, seed=41, mean_len=30, std_len=6)
+    yp = make_scores(6, 40, seed=42)
+    p = dev(yp).clone().requires_grad_(True)
+    t = dev(y)
+    torch.manual_seed(0)
+    v = L.neuralNDCG(p, t, stochastic=True, n_samples=64, beta=0.1, temperature=1.0)
+    v.backward()
+    assert torch.isfinite(v) and torch.isfinite(p.grad).all() and p.grad.abs().max() > 0
+    # beta = 0: every sample is the deterministic loss of log(scores + |min|)
+    det_scores = torch.log(p.detach() + p.detach().min().abs() + 1e-10)
+    ref = L.neuralNDCG(det_scores, t, temperature=1.0)
+    zero = L.neuralNDCG(p.detach(), t, stochastic=True, n_samples=3, beta=0.0, temperature=1.0)
+    assert zero.item() == pytest.approx(ref.item(), rel=1e-5)
+    small = L.neuralNDCG(p.detach(), t, stochastic=True, n_samples=256, beta=0.01, temperature=1.0)
+    assert abs(small.item() - ref.item()) < 0.02
+    # the transposed name is the same bilinear form
+    a = L.neuralNDCG(p.detach(), t, temperature=0.7, k=7)
+    b = L.neuralNDCG_transposed(p.detach(), t, temperature=0.7, k=7)
+    assert a.item() == b.item()
