@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
                                                                   const uint8_t* __restrict__ mask,
                                                                   float* __restrict__ stat_max,
                                                                   float* __restrict__ stat_sum, int S, int n_heads,
-                                                                  float scale_log2e) {
+                                                                  float scale_log2e, DropSite drop) {
   using L = AttFwdSmem<DK>;
   constexpr int NKB = L::NKB;
   extern __shared__ uint8_t smem_dyn[];
@@ -174,8 +174,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
       for (int j = 0; j < 32; ++j) {
         // exp((s - max)/sqrt(dk)) as exp2; padded keys contribute exactly 0.  An all-padded slate gives
         // (-inf) - (-inf) = NaN like the reference (quirk Q2).
-        const float e = (bits & (1u << j)) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs)) : 0.0f;
-        sum += e;
+        float e = (bits & (1u << j)) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs)) : 0.0f;
+        sum += e;                       // softmax normalises BEFORE dropout (transformer.py:153-155)
+        if (drop.thresh != 0) {
+          const unsigned long long idx =
+              ((unsigned long long)(b * n_heads + head) * S + qidx) * (unsigned long long)S + (32 * c + j);
+          e = drop_keep(idx, drop.seed, drop.thresh) ? e * drop.scale : 0.0f;
+        }
         v[j] = round_tf32(e);
       }
       ptx::tmem_st_32x32(tmem_S + lane_addr + 32 * c, v);
@@ -245,7 +250,7 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   {
     ProfScope ps(ARB_PROF_GEMM, 4.0 * double(a.S) * a.S * a.dk * a.h * a.B, st);
     kern<<<grid, ATT_THREADS, L::total(), st>>>(tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
-                                               a.scale * 1.4426950408889634f);
+                                               a.scale * 1.4426950408889634f, a.drop);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

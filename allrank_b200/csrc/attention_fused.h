@@ -14,6 +14,7 @@ struct AttnFwdArgs {
   float* stat_sum;            // [B,h,S] sum_j exp((s_j - max)/sqrt(dk)) over real keys
   int B, h, S, dk;
   float scale;                // 1/sqrt(dk)
+  DropSite drop{0u, 0u, 1.0f};   // dropout on the probabilities (transformer.py:154-155); index ((b*h+head)*S+q)*S+key
 };
 
 bool attn_fused_supported(int S, int dk);
@@ -35,6 +36,7 @@ struct AttnBwdArgs {
   float* delta;               // [B,h,S] scratch
   int B, h, S, dk;
   float scale;
+  DropSite drop{0u, 0u, 1.0f};
 };
 
 bool attn_fused_bwd_supported(int S, int dk);

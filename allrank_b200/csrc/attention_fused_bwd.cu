@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const __grid_constant__ CUtensorMap tmDOm, const __grid_constant__ CUtensorMap tmDQ,
     const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
     const uint8_t* __restrict__ mask, const float* __restrict__ stat_max, const float* __restrict__ stat_sum,
-    const float* __restrict__ delta, int S, int n_heads, float scale) {
+    const float* __restrict__ delta, int S, int n_heads, float scale, DropSite drop) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   auto tile = [&](int t) { return smem + t * TILE_BYTES; };
@@ -234,8 +234,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           for (int j = 0; j < 32; ++j) {
             const float2 st = qstats[col0 + j];
             const float p = key_ok ? ex2_approx_b(fmaf(__uint_as_float(sv[j]), c_log2e, st.x)) : 0.0f;
-            const float ds = p * (__uint_as_float(dv[j]) - st.y);
-            sv[j] = round_tf32_b(p);
+            float p_used = p, dp = __uint_as_float(dv[j]);
+            if (drop.thresh != 0) {      // regenerate the forward's dropout mask on the probabilities
+              const unsigned long long idx =
+                  ((unsigned long long)(b * n_heads + head) * S + (128 * qc + col0 + j)) * (unsigned long long)S + key;
+              const float m = drop_keep(idx, drop.seed, drop.thresh) ? drop.scale : 0.0f;
+              p_used = p * m;
+              dp *= m;
+            }
+            const float ds = p * (dp - st.y);
+            sv[j] = round_tf32_b(p_used);
             dv[j] = round_tf32_b(ds);
           }
           ptx::tmem_st_32x32(T_ST + lane_addr + col0, sv);
@@ -342,7 +350,7 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   {
     ProfScope ps(ARB_PROF_GEMM, 10.0 * double(a.S) * a.S * a.dk * a.h * a.B, st);
     kern<<<grid, BWD_THREADS, BwdSmem::total(), st>>>(tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
-                                                      a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale);
+                                                      a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale, a.drop);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

@@ -42,6 +42,7 @@ struct GemmParams {
   const float* bias;
   float* atomic_out;
   long long atomic_ld;
+  DropSite drop;
 };
 
 template <int BLOCK_N>
@@ -201,6 +202,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
           float x = __uint_as_float(v[j]) * p.alpha;
           if (p.flags & EPI_BIAS) x += bias_s[32 * c + j];
           if (p.flags & EPI_RELU) x = fmaxf(x, 0.0f);
+          if (p.flags & EPI_DROPOUT) {
+            const unsigned long long idx = (unsigned long long)(m0 + row) * (unsigned long long)p.N + (n0 + 32 * c + j);
+            x = drop_keep(idx, p.drop.seed, p.drop.thresh) ? x * p.drop.scale : 0.0f;
+          }
           o[e] = x;
         }
         if (has_aux) {
@@ -346,6 +351,8 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
   p.M = d.M; p.N = d.N; p.K = d.K; p.nb2 = d.nb2;
   p.a_b2 = d.a_b2; p.a_b3 = d.a_b3; p.b_b2 = d.b_b2; p.b_b3 = d.b_b3; p.c_b2 = d.c_b2; p.c_b3 = d.c_b3;
   p.flags = d.flags; p.alpha = d.alpha; p.bias = d.bias; p.atomic_out = d.atomic_out; p.atomic_ld = d.atomic_ld;
+  p.drop = d.drop;
+  if ((d.flags & EPI_DROPOUT) && d.drop.thresh == 0) p.flags &= ~EPI_DROPOUT;
   p.kb_per_split = (total_kb + splits - 1) / splits;
   const int eff_splits = split ? (total_kb + p.kb_per_split - 1) / std::max(1, p.kb_per_split) : 1;
   dim3 grid((d.N + d.block_n - 1) / d.block_n, (d.M + BLOCK_M - 1) / BLOCK_M, split ? std::max(1, eff_splits) : d.nb2 * d.nb3);

@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "dropout.cuh"
+
 namespace arb {
 
 // A strided view of up to 4 dimensions, dim[0] contiguous (stride[0] == 1), strides in elements.
@@ -18,6 +20,7 @@ enum : int {
   EPI_ADD_AUX = 4,    // + Aux[m,n]          (residual; Aux may alias C)
   EPI_MASK_AUX = 8,   // . * (Aux[m,n] > 0)  (ReLU backward)
   EPI_ATOMIC = 16,    // red.add into atomic_out instead of storing C (split-K weight gradients)
+  EPI_DROPOUT = 32,   // inverted dropout on (alpha*acc + bias [relu]) before the aux tile is added
 };
 
 struct GemmDesc {
@@ -34,6 +37,7 @@ struct GemmDesc {
   const float* bias = nullptr;  // [N]
   float* atomic_out = nullptr;  // row-major [M, atomic_ld]
   int64_t atomic_ld = 0;
+  DropSite drop{0u, 0u, 1.0f};  // EPI_DROPOUT: element index = m * N + n (unbatched problems only)
 };
 
 int launch_gemm_tf32(const GemmDesc& d, cudaStream_t stream);   // 0 or ARB_E_*

@@ -135,9 +135,12 @@ static int pick_block_n(int n) { return n <= 32 ? 32 : (n < 128 ? 64 : 128); }
 
 // Y[R,out] = epi( X[R,in] W[out,in]^T + bias )
 static int linear_fwd(const Ctx& k, const float* X, int64_t x_pitch, int in, const float* Wt, const float* bias, int out,
-                      float* Y, int64_t y_pitch, int flags, const float* aux, int64_t aux_pitch) {
+                      float* Y, int64_t y_pitch, int flags, const float* aux, int64_t aux_pitch,
+                      DropSite drop = DropSite{0u, 0u, 1.0f}) {
   GemmDesc g;
   g.M = int(k.R); g.N = out; g.K = in;
+  g.drop = drop;
+  if (drop.thresh != 0) flags |= EPI_DROPOUT;
   g.A = rows_view(X, in, k.R, x_pitch);
   g.B = rows_view(Wt, in, out, in);
   g.C = rows_view(Y, out, k.R, y_pitch);
@@ -148,8 +151,9 @@ static int linear_fwd(const Ctx& k, const float* X, int64_t x_pitch, int in, con
 }
 // dX[R,in] = epi( dY[R,out] W[out,in] )      (W read as an MN-major B operand)
 static int linear_bwd_input(const Ctx& k, const float* dY, int64_t dy_pitch, int out, const float* Wt, int in, float* dX,
-                            int64_t dx_pitch, int flags, const float* aux, int64_t aux_pitch) {
+                            int64_t dx_pitch, int flags, const float* aux, int64_t aux_pitch, float alpha = 1.0f) {
   GemmDesc g;
+  g.alpha = alpha;
   g.M = int(k.R); g.N = in; g.K = out; g.b_mn = 1;
   g.A = rows_view(dY, out, k.R, dy_pitch);
   g.B = rows_view(Wt, in, out, in);          // dim0 = in (N, contiguous), dim1 = out (K)
@@ -196,7 +200,7 @@ static void batch_all(GemmDesc& g, int h, int B) {
 #define ARB_TRY(expr) do { int rc__ = (expr); if (rc__ != ARB_OK) return rc__; } while (0)
 
 static int forward_impl(const arb_scorer_config& c, const float* P, const float* x, const uint8_t* mask, int B, int S,
-                        float* scores, float* ws, int64_t ws_floats, int training, cudaStream_t st) {
+                        float* scores, float* ws, int64_t ws_floats, int training, uint64_t seed, cudaStream_t st) {
   ParamLayout L;
   ARB_TRY(make_param_layout(c, L));
   WsLayout W;
@@ -206,8 +210,15 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   const int d = c.d_model, F = c.n_features, f = c.d_ff, h = c.n_heads;
   const int dk = c.n_layers > 0 ? d / h : 0;
 
+  // dropout follows the module's train()/eval() mode (the host zeroes these in eval); `training` only selects
+  // whether activations are kept for a backward pass
+  const float p_drop = c.dropout, p_fc = c.fc_dropout;
+  if (p_drop > 0.0f && c.n_layers > 0 && !use_fused_bwd(c, S)) {
+    arb_set_error("scorer: dropout > 0 needs the fused attention kernels (slate_length <= 256, head width <= 32)");
+    return ARB_E_UNSUPPORTED;
+  }
   float* xcur = ws + W.x0;
-  ARB_TRY(linear_fwd(k, x, F, F, P + L.fc_w, P + L.fc_b, d, xcur, d, 0, nullptr, 0));
+  ARB_TRY(linear_fwd(k, x, F, F, P + L.fc_w, P + L.fc_b, d, xcur, d, 0, nullptr, 0, make_drop_site(seed, 0, SITE_FC, p_fc)));
   for (int l = 0; l < c.n_layers; ++l) {
     const auto& pl = L.layer[l];
     const auto& wl = W.layer[l];
@@ -224,6 +235,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
       a.o = head_view(ctx, dk, S, h, B, d);
       a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum;
       a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = 1.0f / sqrtf(float(dk));
+      a.drop = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
       ARB_TRY(launch_attn_fwd(a, st));
     } else {
       {
@@ -246,11 +258,14 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
         ARB_TRY(launch_gemm_tf32(g, st));
       }
     }
-    ARB_TRY(linear_fwd(k, ctx, d, d, P + pl.wo, P + pl.bo, d, xmid, d, EPI_ADD_AUX, xcur, d));
+    ARB_TRY(linear_fwd(k, ctx, d, d, P + pl.wo, P + pl.bo, d, xmid, d, EPI_ADD_AUX, xcur, d,
+                       make_drop_site(seed, l, SITE_ATTN_OUT, p_drop)));
     // ---- feed-forward sublayer: x + W2 relu(W1 LN(x))   (transformer.py:134, :227)
     ARB_TRY(ln_forward(xmid, P + pl.ln2_a, P + pl.ln2_b, c.ln_eps, k.R, d, xn2, ws + wl.mean2, ws + wl.std2, st));
-    ARB_TRY(linear_fwd(k, xn2, d, d, P + pl.w1, P + pl.b1, f, hdn, f, EPI_RELU, nullptr, 0));
-    ARB_TRY(linear_fwd(k, hdn, f, f, P + pl.w2, P + pl.b2, d, xout, d, EPI_ADD_AUX, xmid, d));
+    ARB_TRY(linear_fwd(k, xn2, d, d, P + pl.w1, P + pl.b1, f, hdn, f, EPI_RELU, nullptr, 0,
+                       make_drop_site(seed, l, SITE_FFN_HID, p_drop)));
+    ARB_TRY(linear_fwd(k, hdn, f, f, P + pl.w2, P + pl.b2, d, xout, d, EPI_ADD_AUX, xmid, d,
+                       make_drop_site(seed, l, SITE_FFN_OUT, p_drop)));
     xcur = xout;
   }
   const int has_norm = c.n_layers > 0;
@@ -259,13 +274,14 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   return ARB_OK;
 }
 
-struct ScratchLayout { int64_t dxa, dxb, dxn, dqkv, dctx, dprob, prob, delta, total; };
+struct ScratchLayout { int64_t dxa, dxb, dxn, dxm, dqkv, dctx, dprob, prob, delta, total; };
 static void make_scratch_layout(const arb_scorer_config& c, int B, int S, ScratchLayout& Z) {
   const int64_t R = int64_t(B) * S, d = c.d_model;
   const int Sp = int(align_up(S, 4));
   int64_t o = 0;
   auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
   Z.dxa = take(R * d); Z.dxb = take(R * d); Z.dxn = take(R * d);
+  Z.dxm = (c.dropout > 0.0f || c.fc_dropout > 0.0f) ? take(R * d) : 0;
   if (c.n_layers > 0) {
     Z.dqkv = take(R * 3 * d); Z.dctx = take(R * d);
     const bool fb = use_fused_bwd(c, S);
@@ -280,7 +296,7 @@ static void make_scratch_layout(const arb_scorer_config& c, int B, int S, Scratc
 
 static int backward_impl(const arb_scorer_config& c, const float* P, const float* x, const uint8_t* mask, int B, int S,
                          const float* scores, const float* dscores, float* G, float* ws, int64_t ws_floats,
-                         float* scratch, int64_t scratch_floats, cudaStream_t st) {
+                         float* scratch, int64_t scratch_floats, uint64_t seed, cudaStream_t st) {
   ParamLayout L;
   ARB_TRY(make_param_layout(c, L));
   WsLayout W;
@@ -299,13 +315,24 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   float* dqkv = scratch + Z.dqkv;
   float* dctx = scratch + Z.dctx;
   float* dprob = scratch + Z.dprob;
+  float* dxm = scratch + Z.dxm;      // dx seen through the dropout of the sublayer below (masked copy)
+  const float p_drop = c.dropout, p_fc = c.fc_dropout;
+  const bool drop_on = p_drop > 0.0f;
+  if (drop_on && c.n_layers > 0 && !use_fused_bwd(c, S)) {
+    arb_set_error("scorer: dropout > 0 needs the fused attention kernels (slate_length <= 256, head width <= 32)");
+    return ARB_E_UNSUPPORTED;
+  }
+  // site whose mask the gradient of the residual stream must pass through right below the head / final norm
+  const DropSite top_site = c.n_layers > 0 ? make_drop_site(seed, c.n_layers - 1, SITE_FFN_OUT, p_drop)
+                                           : make_drop_site(seed, 0, SITE_FC, p_fc);
 
   const int has_norm = c.n_layers > 0;
   const float* xlast = c.n_layers > 0 ? ws + W.layer[c.n_layers - 1].xout : ws + W.x0;
   ARB_TRY(head_backward(dscores, scores, xlast, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr,
                         ws + W.meanf, ws + W.stdf, c.ln_eps, P + L.head_w, P + L.head_b, has_norm, c.out_act, k.R, d, dx,
                         has_norm ? G + L.lnf_a : nullptr, has_norm ? G + L.lnf_b : nullptr, G + L.head_w, G + L.head_b,
-                        st));
+                        st, dxm, top_site));
+  const float* dy = top_site.thresh ? dxm : dx;   // gradient w.r.t. the output of the linear below the dropout
   for (int l = c.n_layers - 1; l >= 0; --l) {
     const auto& pl = L.layer[l];
     const auto& wl = W.layer[l];
@@ -314,19 +341,24 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     float* prob = W.fused ? scratch + Z.prob : ws + wl.prob;
     float* xmid = ws + wl.xmid; float* xn2 = ws + wl.xn2; float* hdn = ws + wl.hdn;
     // ---- feed-forward sublayer backward:  xout = xmid + W2 relu(W1 xn2 + b1) + b2
-    ARB_TRY(linear_bwd_weight(k, dx, d, d, hdn, f, f, G + pl.w2));
-    ARB_TRY(colsum_accumulate(dx, k.R, d, d, G + pl.b2, st));
-    ARB_TRY(linear_bwd_input(k, dx, d, d, P + pl.w2, f, hdn, f, EPI_MASK_AUX, hdn, f));   // hdn <- d hdn (in place)
+    ARB_TRY(linear_bwd_weight(k, dy, d, d, hdn, f, f, G + pl.w2));
+    ARB_TRY(colsum_accumulate(dy, k.R, d, d, G + pl.b2, st));
+    // hdn <- d hdn in place; hdn > 0 <=> ReLU active AND kept by the hidden dropout, so the mask tile also carries
+    // the dropout mask and only the 1/(1-p) scale is needed
+    ARB_TRY(linear_bwd_input(k, dy, d, d, P + pl.w2, f, hdn, f, EPI_MASK_AUX, hdn, f,
+                             drop_on ? 1.0f / (1.0f - p_drop) : 1.0f));
     ARB_TRY(linear_bwd_weight(k, hdn, f, f, xn2, d, d, G + pl.w1));
     ARB_TRY(colsum_accumulate(hdn, k.R, f, f, G + pl.b1, st));
     ARB_TRY(linear_bwd_input(k, hdn, f, f, P + pl.w1, d, dxn, d, 0, nullptr, 0));
+    const DropSite site_ao = make_drop_site(seed, l, SITE_ATTN_OUT, p_drop);
     ARB_TRY(ln_backward(dxn, xmid, P + pl.ln2_a, ws + wl.mean2, ws + wl.std2, c.ln_eps, dx, k.R, d, dx_alt,
-                        G + pl.ln2_a, G + pl.ln2_b, st));
-    // dx_alt = d loss / d xmid
+                        G + pl.ln2_a, G + pl.ln2_b, st, dxm, site_ao));
+    // dx_alt = d loss / d xmid ; dy = the same through the dropout on the attention sublayer output
+    dy = site_ao.thresh ? dxm : dx_alt;
     // ---- attention sublayer backward:  xmid = xin + Wo ctx + bo
-    ARB_TRY(linear_bwd_weight(k, dx_alt, d, d, ctx, d, d, G + pl.wo));
-    ARB_TRY(colsum_accumulate(dx_alt, k.R, d, d, G + pl.bo, st));
-    ARB_TRY(linear_bwd_input(k, dx_alt, d, d, P + pl.wo, d, dctx, d, 0, nullptr, 0));
+    ARB_TRY(linear_bwd_weight(k, dy, d, d, ctx, d, d, G + pl.wo));
+    ARB_TRY(colsum_accumulate(dy, k.R, d, d, G + pl.bo, st));
+    ARB_TRY(linear_bwd_input(k, dy, d, d, P + pl.wo, d, dctx, d, 0, nullptr, 0));
     if (use_fused_bwd(c, S)) {
       AttnBwdArgs a;   // dQ, dK, dV from d ctx in one kernel; P is recomputed in TMEM from the saved row statistics
       a.q = head_view(qkv, dk, S, h, B, 3 * d);
@@ -339,6 +371,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
       a.o_ptr = ctx; a.do_ptr = dctx; a.o_pitch = d;
       a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum; a.delta = scratch + Z.delta;
       a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = alpha;
+      a.drop = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
       ARB_TRY(launch_attn_bwd(a, st));
     } else {
       if (W.fused) {   // the fused forward kept no probabilities: recompute P = softmax(mask(alpha Q K^T))
@@ -392,13 +425,16 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(linear_bwd_weight(k, dqkv, 3 * d, 3 * d, xn1, d, d, G + pl.wqkv));
     ARB_TRY(colsum_accumulate(dqkv, k.R, 3 * d, 3 * d, G + pl.bqkv, st));
     ARB_TRY(linear_bwd_input(k, dqkv, 3 * d, 3 * d, P + pl.wqkv, d, dxn, d, 0, nullptr, 0));
+    const DropSite site_below = l > 0 ? make_drop_site(seed, l - 1, SITE_FFN_OUT, p_drop)
+                                      : make_drop_site(seed, 0, SITE_FC, p_fc);
     ARB_TRY(ln_backward(dxn, xin, P + pl.ln1_a, ws + wl.mean1, ws + wl.std1, c.ln_eps, dx_alt, k.R, d, dx,
-                        G + pl.ln1_a, G + pl.ln1_b, st));
-    // dx = d loss / d xin
+                        G + pl.ln1_a, G + pl.ln1_b, st, dxm, site_below));
+    // dx = d loss / d xin ; dy = the same through the dropout that produced xin's last summand
+    dy = site_below.thresh ? dxm : dx;
   }
   // ---- input FC backward (x is data: no input gradient)
-  ARB_TRY(linear_bwd_weight(k, dx, d, d, x, F, F, G + L.fc_w));
-  ARB_TRY(colsum_accumulate(dx, k.R, d, d, G + L.fc_b, st));
+  ARB_TRY(linear_bwd_weight(k, dy, d, d, x, F, F, G + L.fc_w));
+  ARB_TRY(colsum_accumulate(dy, k.R, d, d, G + L.fc_b, st));
   return ARB_OK;
 }
 
@@ -429,22 +465,22 @@ extern "C" int64_t arb_scorer_backward_scratch_floats(const arb_scorer_config* c
 }
 extern "C" int32_t arb_scorer_forward(const arb_scorer_config* cfg, const float* params, const float* x,
                                       const uint8_t* mask, int32_t B, int32_t S, float* scores, float* workspace,
-                                      int64_t workspace_floats, int32_t training, void* stream) {
+                                      int64_t workspace_floats, int32_t training, uint64_t seed, void* stream) {
   if (!cfg || !params || !x || !mask || !scores || !workspace || B <= 0 || S <= 0) {
     arb_set_error("arb_scorer_forward: null pointer or bad shape");
     return ARB_E_INVALID_ARG;
   }
-  return forward_impl(*cfg, params, x, mask, B, S, scores, workspace, workspace_floats, training,
+  return forward_impl(*cfg, params, x, mask, B, S, scores, workspace, workspace_floats, training, seed,
                       static_cast<cudaStream_t>(stream));
 }
 extern "C" int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, const float* x,
                                        const uint8_t* mask, int32_t B, int32_t S, const float* scores,
                                        const float* d_scores, float* grads, float* workspace, int64_t workspace_floats,
-                                       float* scratch, int64_t scratch_floats, void* stream) {
+                                       float* scratch, int64_t scratch_floats, uint64_t seed, void* stream) {
   if (!cfg || !params || !x || !mask || !scores || !d_scores || !grads || !workspace || !scratch || B <= 0 || S <= 0) {
     arb_set_error("arb_scorer_backward: null pointer or bad shape");
     return ARB_E_INVALID_ARG;
   }
   return backward_impl(*cfg, params, x, mask, B, S, scores, d_scores, grads, workspace, workspace_floats, scratch,
-                       scratch_floats, static_cast<cudaStream_t>(stream));
+                       scratch_floats, seed, static_cast<cudaStream_t>(stream));
 }

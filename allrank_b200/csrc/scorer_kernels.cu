@@ -9,6 +9,7 @@
 
 #include "block_utils.cuh"
 #include "common.h"
+#include "dropout.cuh"
 #include "scorer_kernels.h"
 
 namespace arb {
@@ -36,6 +37,20 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int width, int 
   for (int k = 0; k < NV; ++k) {
     const int c = lane * 4 + 128 * k;
     if (c < width) *reinterpret_cast<float4*>(p + c) = r.v[k];
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void apply_drop(RowRegs<NV>& r, long long row, int width, int lane, const DropSite& site) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + 128 * k;
+    float* v = &r.v[k].x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned long long idx = (unsigned long long)row * (unsigned long long)width + (c + e);
+      v[e] = drop_keep(idx, site.seed, site.thresh) ? v[e] * site.scale : 0.0f;
+    }
   }
 }
 
@@ -93,7 +108,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
                                                                     const float* __restrict__ dres, long long rows,
                                                                     int width, int rows_per_warp,
                                                                     float* __restrict__ dx, float* __restrict__ grad_a,
-                                                                    float* __restrict__ grad_b) {
+                                                                    float* __restrict__ grad_b,
+                                                                    float* __restrict__ dx_masked, DropSite site) {
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   RowRegs<NV> ga, acc_a, acc_b;
@@ -150,6 +166,10 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
       }
     }
     store_row<NV>(dx + row * width, width, lane, g);
+    if (dx_masked) {   // the same gradient through the dropout of the sublayer below (mask regenerated)
+      apply_drop<NV>(g, row, width, lane, site);
+      store_row<NV>(dx_masked + row * width, width, lane, g);
+    }
   }
   // block-level reduction of the gain/bias gradients
 #pragma unroll
@@ -359,7 +379,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
     const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean_i,
     const float* __restrict__ std_i, float eps, const float* __restrict__ w, const float* __restrict__ wb,
     int has_norm, int act, long long rows, int width, int rows_per_warp, float* __restrict__ dx,
-    float* __restrict__ grad_a, float* __restrict__ grad_b, float* __restrict__ grad_w, float* __restrict__ grad_wb) {
+    float* __restrict__ grad_a, float* __restrict__ grad_b, float* __restrict__ grad_w, float* __restrict__ grad_wb,
+    float* __restrict__ dx_masked, DropSite site) {
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   __shared__ float shb[ROWS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -391,6 +412,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
         for (int e = 0; e < 4; ++e) { gv[e] = dz * wv[e]; aw[e] += dz * xv[e]; }
       }
       store_row<NV>(dx + row * width, width, lane, g);
+      if (dx_masked) { apply_drop<NV>(g, row, width, lane, site); store_row<NV>(dx_masked + row * width, width, lane, g); }
       continue;
     }
     const float mean = mean_i[row], sd = std_i[row];
@@ -435,6 +457,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
       for (int e = 0; e < 4; ++e) gv[e] = r * (gv[e] - m1) - coef * xv[e];
     }
     store_row<NV>(dx + row * width, width, lane, g);
+    if (dx_masked) { apply_drop<NV>(g, row, width, lane, site); store_row<NV>(dx_masked + row * width, width, lane, g); }
   }
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
@@ -492,11 +515,12 @@ int ln_forward(const float* x, const float* a, const float* b, float eps, long l
 
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
-                cudaStream_t st) {
+                cudaStream_t st, float* dx_masked, DropSite site) {
+  if (site.thresh == 0) dx_masked = nullptr;
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((dres ? 16.0 : 12.0) * width + 8), st);
-  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b)));
+  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site)));
   return check_launch();
 }
 
@@ -536,11 +560,12 @@ int head_forward(const float* x, const float* a, const float* b, float eps, cons
 int head_backward(const float* dscore, const float* score, const float* x, const float* a, const float* b,
                   const float* mean, const float* sd, float eps, const float* w, const float* wb, int has_norm,
                   int act, long long rows, int width, float* dx, float* grad_a, float* grad_b, float* grad_w,
-                  float* grad_wb, cudaStream_t st) {
+                  float* grad_wb, cudaStream_t st, float* dx_masked, DropSite site) {
+  if (site.thresh == 0) dx_masked = nullptr;
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 16), st);
-  ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb)));
+  ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site)));
   return check_launch();
 }
 

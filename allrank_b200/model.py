@@ -18,8 +18,12 @@ TF32 GEMMs + fp32 SIMT kernels.  The nn.Parameters are views of ONE flat fp32 bu
 one flat gradient buffer -- which is what makes the single-bucket NCCL all-reduce (allrank_b200/ddp.py) and
 flat optimisers possible.  There is no eager fallback: CPU tensors raise.
 
-Not built yet (raise NotImplementedError rather than fall back): dropout > 0 in training mode, positional
-encodings, multi-layer / activated / input-normed FC blocks, d_output > 1.
+Dropout (transformer.dropout on attention probabilities, sublayer outputs and the FFN hidden layer; fc_model.dropout
+on the input FC) is fused into the kernels with counter-based masks that backward regenerates; like nn.Dropout it is
+active in train() mode only.  The mask stream differs from torch's Philox stream: parity under dropout is statistical.
+
+Not built yet (raise NotImplementedError rather than fall back): positional encodings, multi-layer / activated /
+input-normed FC blocks, d_output > 1.
 """
 import copy
 import ctypes
@@ -35,15 +39,16 @@ _ACTS = {None: 0, "Tanh": 1, "Sigmoid": 2, "ReLU": 3}
 class ScorerConfig(ctypes.Structure):
     _fields_ = [("n_features", ctypes.c_int32), ("d_model", ctypes.c_int32), ("n_layers", ctypes.c_int32),
                 ("n_heads", ctypes.c_int32), ("d_ff", ctypes.c_int32), ("out_act", ctypes.c_int32),
-                ("ln_eps", ctypes.c_float)]
+                ("ln_eps", ctypes.c_float), ("dropout", ctypes.c_float), ("fc_dropout", ctypes.c_float)]
 
 
 c_p, c_i, c_i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
 _lib.register("arb_scorer_param_count", c_i64, [c_p])
 _lib.register("arb_scorer_workspace_floats", c_i64, [c_p, c_i, c_i, c_i])
 _lib.register("arb_scorer_backward_scratch_floats", c_i64, [c_p, c_i, c_i])
-_lib.register("arb_scorer_forward", c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i64, c_i, c_p])
-_lib.register("arb_scorer_backward", c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p])
+_lib.register("arb_scorer_forward", c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i64, c_i, ctypes.c_uint64, c_p])
+_lib.register("arb_scorer_backward", c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64,
+                                           ctypes.c_uint64, c_p])
 
 
 # ------------------------------------------------------------------------------------------------ module tree
@@ -112,18 +117,20 @@ def _clone_linear(proto):
 class _ScorerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, x, mask, model):
-        training = ctx.needs_input_grad[0]
-        scores, ws = model._launch_forward(x, mask, training)
-        if training:
+        keep = ctx.needs_input_grad[0]
+        seed = model._draw_seed()
+        scores, ws = model._launch_forward(x, mask, keep, seed)
+        if keep:
             ctx.model = model
             ctx.ws = ws
+            ctx.seed = seed
             ctx.save_for_backward(x, mask, scores)
         return scores
 
     @staticmethod
     def backward(ctx, d_scores):
         x, mask, scores = ctx.saved_tensors
-        ctx.model._launch_backward(x, mask, scores, d_scores.contiguous().float(), ctx.ws)
+        ctx.model._launch_backward(x, mask, scores, d_scores.contiguous().float(), ctx.ws, ctx.seed)
         ctx.ws = None
         return None, None, None, None
 
@@ -131,12 +138,13 @@ class _ScorerFn(torch.autograd.Function):
 class LTRModel(nn.Module):
     """B200 scorer with the reference LTRModel's surface (model.py:47-92)."""
 
-    def __init__(self, n_features, d_model, n_layers, n_heads, d_ff, dropout, output_activation):
+    def __init__(self, n_features, d_model, n_layers, n_heads, d_ff, dropout, output_activation, fc_dropout=0.0):
         super().__init__()
         if output_activation not in _ACTS:
             raise NotImplementedError(f"output activation {output_activation!r}: supported {sorted(map(str, _ACTS))}")
         self.n_features, self.d_model, self.n_layers = int(n_features), int(d_model), int(n_layers)
         self.n_heads, self.d_ff, self.dropout_p = int(n_heads), int(d_ff), float(dropout or 0.0)
+        self.fc_dropout_p = float(fc_dropout or 0.0)
         self.output_activation = output_activation
         if n_layers > 0:
             assert d_model % n_heads == 0   # transformer.py:170
@@ -156,7 +164,7 @@ class LTRModel(nn.Module):
                 nn.init.xavier_uniform_(p)
         self._Fp = (self.n_features + 3) // 4 * 4
         self._cfg = ScorerConfig(self._Fp, self.d_model, self.n_layers, max(self.n_heads, 1), max(self.d_ff, 4),
-                                 _ACTS[output_activation], 1e-6)
+                                 _ACTS[output_activation], 1e-6, self.dropout_p, self.fc_dropout_p)
         self._flat = None
         self._flat_grad = None
         self._views = None
@@ -242,7 +250,14 @@ class LTRModel(nn.Module):
             x = torch.nn.functional.pad(x, (0, self._Fp - self.n_features))
         return x.contiguous(), mask.detach().to(torch.uint8).contiguous()
 
-    def _launch_forward(self, x, mask, training):
+    def _draw_seed(self):
+        """Per-call dropout seed from torch's global CPU generator (so torch.manual_seed makes runs repeatable)."""
+        if self.training and (self.dropout_p > 0.0 or self.fc_dropout_p > 0.0):
+            return int(torch.randint(0, 2 ** 62, (1,)).item())
+        return 0
+
+    def _launch_forward(self, x, mask, keep_for_backward, seed=0):
+        training = keep_for_backward
         B, S = x.shape[0], x.shape[1]
         dev = x.device
         cfg = ctypes.byref(self._cfg)
@@ -250,26 +265,32 @@ class LTRModel(nn.Module):
         ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
         scores = torch.empty((B, S), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            # dropout is applied iff the module is in train() mode, like nn.Dropout; `training` only selects
+            # whether activations are kept for backward
+            self._cfg.dropout = self.dropout_p if self.training else 0.0
+            self._cfg.fc_dropout = self.fc_dropout_p if self.training else 0.0
             rc = _lib.lib().arb_scorer_forward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask), B, S,
                                                _lib.ptr(scores), _lib.ptr(ws), n_ws, 1 if training else 0,
-                                               _lib.stream_ptr(dev))
+                                               ctypes.c_uint64(seed), _lib.stream_ptr(dev))
         _lib.check(rc, "arb_scorer_forward")
         return scores, (ws if training else None)
 
-    def _launch_backward(self, x, mask, scores, d_scores, ws):
+    def _launch_backward(self, x, mask, scores, d_scores, ws, seed=0):
         B, S = x.shape[0], x.shape[1]
         dev = x.device
         cfg = ctypes.byref(self._cfg)
         fresh = any(p.grad is None or p.grad.data_ptr() != gv.data_ptr() for p, _, gv in self._views)
         if fresh:                      # after optimizer.zero_grad(set_to_none=True): start from zero
             self._flat_grad.zero_()
+        self._cfg.dropout = self.dropout_p if seed else 0.0          # same mask configuration as the forward call
+        self._cfg.fc_dropout = self.fc_dropout_p if seed else 0.0
         n_sc = int(_lib.lib().arb_scorer_backward_scratch_floats(cfg, B, S))
         scratch = torch.empty(n_sc, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = _lib.lib().arb_scorer_backward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask), B, S,
                                                 _lib.ptr(scores), _lib.ptr(d_scores), _lib.ptr(self._flat_grad),
                                                 _lib.ptr(ws), ws.numel(), _lib.ptr(scratch), n_sc,
-                                                _lib.stream_ptr(dev))
+                                                ctypes.c_uint64(seed), _lib.stream_ptr(dev))
         _lib.check(rc, "arb_scorer_backward")
         if fresh:
             for p, _, gv in self._views:
@@ -281,15 +302,12 @@ class LTRModel(nn.Module):
         raise NotImplementedError("the fused scorer does not expose the encoder output; use forward()/score()")
 
     def forward(self, x, mask, indices=None):
-        if self.training and self.dropout_p > 0.0:
-            raise NotImplementedError("dropout > 0 in training mode is not implemented in allrank_b200 yet "
-                                      "(no eager fallback); use dropout 0.0 or eval()")
         xin, m = self._prep_inputs(x, mask)
         self._ensure_packed(xin.device)
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             return _ScorerFn.apply(self._anchor, xin, m, self)
-        scores, _ = self._launch_forward(xin, m, False)
+        scores, _ = self._launch_forward(xin, m, False, self._draw_seed())
         return scores
 
     def score(self, x, mask, indices=None):
@@ -325,5 +343,5 @@ def make_model(fc_model, transformer, post_model, n_features):
         dropout = float(_get(transformer, "dropout", 0.0) or 0.0)
     else:
         n_layers, heads, d_ff, dropout = 0, 1, 4, 0.0
-    dropout = max(dropout, float(_get(fc_model, "dropout", 0.0) or 0.0))
-    return LTRModel(n_features, d_model, n_layers, heads, d_ff, dropout, _get(post_model, "output_activation", None))
+    return LTRModel(n_features, d_model, n_layers, heads, d_ff, dropout, _get(post_model, "output_activation", None),
+                    fc_dropout=float(_get(fc_model, "dropout", 0.0) or 0.0))

@@ -124,8 +124,9 @@ int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int32_t B, int
  * Called from allrank/training/train_utils.py:20 (`model(xb, mask, indices)`) and :34 (`model.score`).
  *
  * Every matrix product runs on the tcgen05 tensor cores in TF32 with fp32 accumulation (csrc/gemm_tf32.cu);
- * LayerNorm / softmax / head are fp32 SIMT kernels (csrc/scorer_kernels.cu).  Dropout must be 0 (eval, or
- * configs with dropout 0.0): a fused Philox dropout is a "next" item.
+ * LayerNorm / softmax / head are fp32 SIMT kernels (csrc/scorer_kernels.cu).  Dropout masks are a counter-based
+ * hash of (seed, layer, site, element index) fused into the producing kernels and regenerated in backward
+ * (csrc/dropout.cuh); `seed` must be the same in the forward and the backward call of a step.
  *
  * Parameters live in ONE flat fp32 buffer (the host layer makes the nn.Parameters views of it), laid out as
  *   fc_w[d,F] fc_b[d] | per layer: wq wk wv [3d,d] bq bk bv [3d] wo[d,d] bo[d] w1[dff,d] b1[dff] w2[d,dff] b2[d]
@@ -145,6 +146,9 @@ typedef struct arb_scorer_config {
   int32_t d_ff;         /* PositionwiseFeedForward hidden width                                           */
   int32_t out_act;      /* ARB_ACT_*: post_model.output_activation (model.py:105-107)                     */
   float ln_eps;         /* 1e-6 (transformer.py:63)                                                       */
+  float dropout;        /* transformer.dropout: on attention probabilities, both sublayer outputs and the FFN
+                           hidden layer (transformer.py:105,155,227); applied only when training != 0          */
+  float fc_dropout;     /* fc_model.dropout on the input FC output (model.py:43)                          */
 } arb_scorer_config;
 
 int64_t arb_scorer_param_count(const arb_scorer_config* cfg);
@@ -153,14 +157,14 @@ int64_t arb_scorer_workspace_floats(const arb_scorer_config* cfg, int32_t B, int
 /* x [B,S,F] fp32, mask [B,S] uint8 (1 = padded, train_utils.py:19) -> scores [B,S] fp32 */
 int32_t arb_scorer_forward(const arb_scorer_config* cfg, const float* params, const float* x, const uint8_t* mask,
                            int32_t B, int32_t S, float* scores, float* workspace, int64_t workspace_floats,
-                           int32_t training, void* stream);
+                           int32_t training, uint64_t seed, void* stream);
 /* d_scores [B,S] -> grads += d loss / d params.  `workspace` is the one the training forward filled;
  * `scratch`: arb_scorer_backward_scratch_floats(cfg,B,S) floats. */
 int64_t arb_scorer_backward_scratch_floats(const arb_scorer_config* cfg, int32_t B, int32_t S);
 int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, const float* x, const uint8_t* mask,
                             int32_t B, int32_t S, const float* scores, const float* d_scores, float* grads,
                             float* workspace, int64_t workspace_floats, float* scratch, int64_t scratch_floats,
-                            void* stream);
+                            uint64_t seed, void* stream);
 
 /* 0: unfused attention (materialised logits + generic GEMMs); 1: fused tcgen05 attention forward kernel, unfused
  * backward; 2 (default): fused forward and backward kernels.  Fused kernels serve slates of <= 256 items (backward:

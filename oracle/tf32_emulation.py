@@ -61,15 +61,23 @@ def row_norm(x, a, b, eps=1e-6):
     return a * (x - mu) / (sd + eps) + b
 
 
-def scorer_forward(sd, x, mask, n_layers, heads, out_act=None, mode="trunc"):
-    """Functional forward from a reference-keyed state_dict (tensors may require grad)."""
+def scorer_forward(sd, x, mask, n_layers, heads, out_act=None, mode="trunc", drop=None):
+    """Functional forward from a reference-keyed state_dict (tensors may require grad).
+    `drop`: optional {(layer, site): already-scaled mask tensor} with sites fc / attn_p / attn_out / ffn_hid /
+    ffn_out (shapes [R,d], [B,h,S,S], [R,d], [R,d_ff], [R,d]) -- the dropout sites of transformer.py:105,155,227
+    and model.py:43."""
     B, S, F = x.shape
     R = B * S
+    drop = drop or {}
+
+    def dr(t, layer, site):
+        m = drop.get((layer, site))
+        return t if m is None else t * m
 
     def lin(inp, w, b):   # inp [R, in]
         return mm(inp, w.t(), mode) + b
 
-    h = lin(x.reshape(R, F), sd["input_layer.layers.0.weight"], sd["input_layer.layers.0.bias"])
+    h = dr(lin(x.reshape(R, F), sd["input_layer.layers.0.weight"], sd["input_layer.layers.0.bias"]), 0, "fc")
     d = h.shape[-1]
     dk = d // heads if n_layers else 0
     for l in range(n_layers):
@@ -79,12 +87,12 @@ def scorer_forward(sd, x, mask, n_layers, heads, out_act=None, mode="trunc"):
                    .view(B, S, heads, dk).transpose(1, 2) for i in range(3))
         logits = mm(q, k.transpose(-1, -2), mode) * (1.0 / math.sqrt(dk))
         logits = logits.masked_fill(mask[:, None, None, :], float("-inf"))
-        prob = torch.softmax(logits, dim=-1)
+        prob = dr(torch.softmax(logits, dim=-1), l, "attn_p")
         ctx = mm(prob, v, mode).transpose(1, 2).reshape(R, d)
-        h = h + lin(ctx, sd[p + "self_attn.linears.3.weight"], sd[p + "self_attn.linears.3.bias"])
+        h = h + dr(lin(ctx, sd[p + "self_attn.linears.3.weight"], sd[p + "self_attn.linears.3.bias"]), l, "attn_out")
         xn = row_norm(h, sd[p + "sublayer.1.norm.a_2"], sd[p + "sublayer.1.norm.b_2"])
-        hid = torch.relu(lin(xn, sd[p + "feed_forward.w_1.weight"], sd[p + "feed_forward.w_1.bias"]))
-        h = h + lin(hid, sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"])
+        hid = dr(torch.relu(lin(xn, sd[p + "feed_forward.w_1.weight"], sd[p + "feed_forward.w_1.bias"])), l, "ffn_hid")
+        h = h + dr(lin(hid, sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"]), l, "ffn_out")
     if n_layers:
         h = row_norm(h, sd["encoder.norm.a_2"], sd["encoder.norm.b_2"])
     z = (h * sd["output_layer.w_1.weight"].reshape(1, -1)).sum(-1) + sd["output_layer.w_1.bias"]   # fp32 head (SIMT)

@@ -72,11 +72,13 @@ def test_golden_losses(L, golden):
         ref, gref = float(g[key + "_loss32"]), g[key + "_grad32"]
         # the reference's own fp32 rounding noise, measured against its fp64 evaluation where available
         noise = abs(float(g[key + "_loss64"]) - ref) if key + "_loss64" in g.files else 0.0
-        tol = REL * abs(ref) + 2 * noise + 1e-7
+        # a non-default Sinkhorn tolerance makes the early-exit point matter: the reference tests the whole batch,
+        # the kernel each slate, so values agree to a fraction of `tol` only
+        tol = (REL + 0.5 * kw.get("tol", 0.0)) * abs(ref) + 2 * noise + 1e-7
         assert abs(val - ref) <= tol, (key, name, kw, val, ref)
         scale = max(np.abs(gref).max(), 1e-12)
         gnoise = np.abs(g[key + "_grad64"] - gref).max() if key + "_grad64" in g.files else 0.0
-        gtol = (1e-5 if not name.startswith("neuralNDCG") else 2e-4) * scale + 2 * gnoise
+        gtol = (1e-5 if not name.startswith("neuralNDCG") else 2e-4 + 20 * kw.get("tol", 0.0)) * scale + 2 * gnoise
         err = np.abs(grad - gref).max()
         worst[name] = max(worst.get(name, 0.0), err / scale)
         assert err <= gtol, (key, name, kw, err, scale)
