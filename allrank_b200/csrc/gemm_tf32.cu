@@ -249,6 +249,270 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent variant
+// Same maths and epilogues as gemm_tf32_kernel, restructured as a persistent, fully decoupled pipeline: one CTA per
+// SM walks a static round-robin list of output tiles; the TMA producer keeps a 4-stage operand ring (128 KB) full
+// ACROSS tile boundaries, the MMA issuer alternates between two TMEM accumulators, and the epilogue warps drain one
+// accumulator while the next tile's loads and MMAs are already in flight.  This keeps ~128 KB of loads in flight
+// per SM at all times, which is what an HBM-bound GEMM with K = 128..512 needs (the non-persistent kernel has no
+// loads in flight during its epilogue).
+template <int BLOCK_N>
+struct PersistLayout {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BLOCK_N <= 64 ? 6 : 4;
+  static constexpr int STAGING_BYTES = BLOCK_M * BLOCK_N * 4;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int total() { return RING_BYTES + STAGING_BYTES + 512 + BLOCK_N * 4 + 1024; }
+};
+
+constexpr int EPI_THREADS = 256;
+constexpr int PERSIST_THREADS = 64 + EPI_THREADS;
+
+template <int BLOCK_N, int A_MN, int B_MN>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA,
+                                                                        const __grid_constant__ CUtensorMap tmB,
+                                                                        const __grid_constant__ CUtensorMap tmC,
+                                                                        const __grid_constant__ CUtensorMap tmAux,
+                                                                        const GemmParams p, int n_tiles_n,
+                                                                        int n_tiles_m, int n_z) {
+  using L = PersistLayout<BLOCK_N>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  constexpr int N_SLABS = BLOCK_N / 32;
+
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + L::RING_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + L::STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;        // [2] accumulator complete
+  uint64_t* acc_empty = acc_full + 2;             // [2] accumulator drained by the epilogue (128 arrivals)
+  uint64_t* aux_full = acc_empty + 2;             // aux tile landed in staging
+  uint64_t* stage_free = aux_full + 1;            // staging free again (store has read it), 1 arrival
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
+  float* bias_s = reinterpret_cast<float*>(staging + L::STAGING_BYTES + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool split = (p.flags & EPI_ATOMIC) != 0;
+  const bool has_aux = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
+  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int n_tiles = n_tiles_n * n_tiles_m * n_z;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    if (!split) ptx::prefetch_tmap(&tmC);
+    if (has_aux) ptx::prefetch_tmap(&tmAux);
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&acc_full[a], 1); ptx::mbar_init(&acc_empty[a], EPI_THREADS); }
+    ptx::mbar_init(aux_full, 1);
+    ptx::mbar_init(stage_free, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int t, int& n0, int& m0, int& z) {
+    const int nt = t % n_tiles_n;
+    const int rest = t / n_tiles_n;
+    n0 = nt * BLOCK_N;
+    m0 = (rest % n_tiles_m) * BLOCK_M;
+    z = rest / n_tiles_m;
+  };
+  auto k_range = [&](int z, int& kb0, int& nkb) {
+    if (split) {
+      kb0 = z * p.kb_per_split;
+      nkb = min(total_kb, kb0 + p.kb_per_split) - kb0;
+      if (nkb < 0) nkb = 0;
+    } else {
+      kb0 = 0;
+      nkb = total_kb;
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;          // running k-block counter across tiles (ring position)
+      int local = 0;            // tiles processed by this CTA
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+        int n0, m0, z, kb0, nkb;
+        decode(t, n0, m0, z);
+        k_range(z, kb0, nkb);
+        const int b2 = split ? 0 : z % p.nb2, b3 = split ? 0 : z / p.nb2;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t round = it / STAGES;
+          if (round > 0) ptx::mbar_wait(&empty_bar[s], (round - 1) & 1);
+          uint8_t* a_s = smem + s * L::STAGE_BYTES;
+          uint8_t* b_s = a_s + A_STAGE_BYTES;
+          const int k0 = (kb0 + i) * BLOCK_K;
+          ptx::mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          if (A_MN) {
+            for (int c = 0; c < BLOCK_M / 32; ++c)
+              ptx::tma_load_4d(a_s + c * 4096, &tmA, &full_bar[s], m0 + 32 * c, k0, b2 * p.a_b2, b3 * p.a_b3);
+          } else {
+            ptx::tma_load_4d(a_s, &tmA, &full_bar[s], k0, m0, b2 * p.a_b2, b3 * p.a_b3);
+          }
+          if (B_MN) {
+            for (int c = 0; c < N_SLABS; ++c)
+              ptx::tma_load_4d(b_s + c * 4096, &tmB, &full_bar[s], n0 + 32 * c, k0, b2 * p.b_b2, b3 * p.b_b3);
+          } else {
+            ptx::tma_load_4d(b_s, &tmB, &full_bar[s], k0, n0, b2 * p.b_b2, b3 * p.b_b3);
+          }
+        }
+        if (has_aux) {
+          // the residual / mask tile goes into the staging area, which is reused tile after tile: wait until the
+          // previous tile's TMA store has read it (issued AFTER this tile's operand loads so the ring never stalls
+          // behind the epilogue)
+          if (local > 0) ptx::mbar_wait(stage_free, (local - 1) & 1);
+          ptx::mbar_expect_tx(aux_full, L::STAGING_BYTES);
+          for (int c = 0; c < N_SLABS; ++c)
+            ptx::tma_load_4d(staging + c * (BLOCK_M * 128), &tmAux, aux_full, n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_tf32(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      uint32_t it = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+        int n0, m0, z, kb0, nkb;
+        decode(t, n0, m0, z);
+        k_range(z, kb0, nkb);
+        const int acc = local & 1;
+        const uint32_t use = local >> 1;      // how many times this accumulator has been used before
+        if (use > 0) ptx::mbar_wait(&acc_empty[acc], (use - 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t round = it / STAGES;
+          ptx::mbar_wait(&full_bar[s], round & 1);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = A_MN ? ptx::smem_desc_sw128<1>(a_addr + k * 1024, 4096, 512)
+                                     : ptx::smem_desc_sw128<2>(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? ptx::smem_desc_sw128<1>(b_addr + k * 1024, 4096, 512)
+                                     : ptx::smem_desc_sw128<2>(b_addr + k * 32, 16, 1024);
+            ptx::mma_tf32_ss(d_tmem, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[s]);
+        }
+        ptx::mma_commit(&acc_full[acc]);     // (with nkb == 0 this still arrives: nothing outstanding)
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9: two warps per TMEM lane quadrant, alternating 32-column slabs) ====
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const int et = threadIdx.x - 64;
+    const int slab_par = (warp - 2) >> 2;
+    int local = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
+      int n0, m0, z, kb0, nkb;
+      decode(t, n0, m0, z);
+      k_range(z, kb0, nkb);
+      const int b2 = split ? 0 : z % p.nb2, b3 = split ? 0 : z / p.nb2;
+      const int acc = local & 1;
+      const uint32_t use = local >> 1;
+      if (p.flags & EPI_BIAS) {
+        for (int j = et; j < BLOCK_N; j += EPI_THREADS) bias_s[j] = (n0 + j < p.N) ? p.bias[n0 + j] : 0.0f;
+      }
+      // staging must be free before we write it: without an aux tile the producer does not wait on stage_free,
+      // so the epilogue (the only other user) does
+      if (!split && !has_aux && local > 0) ptx::mbar_wait(stage_free, (local - 1) & 1);
+      ptx::named_bar_sync(1, EPI_THREADS);
+      ptx::mbar_wait(&acc_full[acc], use & 1);
+      ptx::tc_fence_after();
+      if (has_aux) ptx::mbar_wait(aux_full, local & 1);
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+#pragma unroll 1
+      for (int c = (N_SLABS > 1 ? slab_par : 0); c < (N_SLABS > 1 || slab_par == 0 ? N_SLABS : 0); c += (N_SLABS > 1 ? 2 : 1)) {
+        uint32_t v[32];
+        if (nkb > 0) {
+          ptx::tmem_ld_32x32(d_tmem + (uint32_t(32 * q) << 16) + uint32_t(32 * c), v);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
+#pragma unroll
+        for (int piece = 0; piece < 8; ++piece) {
+          float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = piece * 4 + e;
+            float x = __uint_as_float(v[j]) * p.alpha;
+            if (p.flags & EPI_BIAS) x += bias_s[32 * c + j];
+            if (p.flags & EPI_RELU) x = fmaxf(x, 0.0f);
+            if (p.flags & EPI_DROPOUT) {
+              const unsigned long long idx = (unsigned long long)(m0 + row) * (unsigned long long)p.N + (n0 + 32 * c + j);
+              x = drop_keep(idx, p.drop.seed, p.drop.thresh) ? x * p.drop.scale : 0.0f;
+            }
+            o[e] = x;
+          }
+          if (has_aux) {
+            const float4 a = *dst;
+            if (p.flags & EPI_ADD_AUX) { o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w; }
+            if (p.flags & EPI_MASK_AUX) {
+              o[0] = a.x > 0.f ? o[0] : 0.f; o[1] = a.y > 0.f ? o[1] : 0.f;
+              o[2] = a.z > 0.f ? o[2] : 0.f; o[3] = a.w > 0.f ? o[3] : 0.f;
+            }
+          }
+          if (split) {
+            const int gm = m0 + row, gn = n0 + 32 * c + piece * 4;
+            if (gm < p.M && gn < p.N) {
+              float* dstg = p.atomic_out + (long long)gm * p.atomic_ld + gn;
+              if (gn + 3 < p.N && (p.atomic_ld & 3) == 0) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstg), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                             "f"(o[3]) : "memory");
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (gn + e < p.N) atomicAdd(dstg + e, o[e]);
+              }
+            }
+          } else {
+            *dst = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      // this accumulator may be overwritten by the MMA warp from now on
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&acc_empty[acc]);
+      if (!split) {
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(1, EPI_THREADS);
+        if (et == 0) {
+          for (int c = 0; c < N_SLABS; ++c)
+            ptx::tma_store_4d(&tmC, staging + c * (BLOCK_M * 128), n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
+          ptx::tma_store_commit();
+          ptx::tma_store_wait_read();
+          ptx::mbar_arrive(stage_free);     // staging can take the next aux tile / the next output tile
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -302,9 +566,45 @@ int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32, int as_tf32)
   return ARB_OK;
 }
 
+// Measured on B200 (cfg2, B=1024): the one-CTA-per-tile kernel with 3 co-resident CTAs per SM is faster (5.7 ms of
+// GEMM time per step) than the persistent pipeline (6.6 ms with 8 epilogue warps): the persistent epilogue is the
+// bottleneck.  Kept opt-in for the next round (profiles/README.md).
+static int g_persistent = 0;
+void set_gemm_persistent(int on) { g_persistent = on; }
+
+template <int BLOCK_N, int A_MN, int B_MN>
+static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
+                               const CUtensorMap& tX, const GemmParams& p, dim3 tiles, cudaStream_t st) {
+  auto kern = gemm_tf32_persistent<BLOCK_N, A_MN, B_MN>;
+  constexpr int smem = PersistLayout<BLOCK_N>::total();
+  static bool configured = false;
+  static int n_sm = 148;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      arb_set_error("gemm_tf32 (persistent): cannot raise the dynamic shared memory limit");
+      return ARB_E_CUDA;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const long long n_tiles = (long long)tiles.x * tiles.y * tiles.z;
+  const int grid = int(std::min<long long>(n_tiles, n_sm));
+  {
+    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * double(d.nb2) * double(d.nb3), st);
+    kern<<<grid, PERSIST_THREADS, smem, st>>>(tA, tB, tC, tX, p, int(tiles.x), int(tiles.y), int(tiles.z));
+  }
+  arb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { arb_set_error(cudaGetErrorString(e)); return ARB_E_CUDA; }
+  return ARB_OK;
+}
+
 template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
+  if (g_persistent) return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
   auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
   constexpr int smem = SmemLayout<BLOCK_N>::total();
   static bool configured = false;
@@ -374,6 +674,7 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
 //   b_mn = 0: B is [N,K] row-major (an nn.Linear weight);  b_mn = 1: B is [K,N] row-major.
 //   batch > 1: operands are `batch` consecutive matrices (stride = rows*cols), unless the stride argument is 0.
 extern "C" void arb_set_tf32_round_on_load(int32_t enable) { arb::set_tf32_round_on_load(enable); }
+extern "C" void arb_set_gemm_persistent(int32_t on) { arb::set_gemm_persistent(on); }
 
 extern "C" int32_t arb_gemm_tf32(const float* A, const float* B, float* C, const float* aux, const float* bias,
                                  int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t batch,

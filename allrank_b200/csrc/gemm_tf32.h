@@ -49,5 +49,6 @@ struct TmapBox { uint32_t b[4]; };
 int make_tmap_4d(void* out_CUtensorMap, const TRef& t, TmapBox box, int atom32, int as_tf32);
 
 void set_tf32_round_on_load(int enable);
+void set_gemm_persistent(int on);
 
 }  // namespace arb

@@ -171,6 +171,10 @@ int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, c
  * head width <= 32); other shapes use the unfused path automatically.  Process-wide; exists for A/B tests. */
 void arb_set_attention_mode(int32_t mode);
 
+/* 1: persistent, decoupled-pipeline GEMM kernel (one CTA per SM walking all tiles); 0 (default): one CTA per tile.
+ * Process-wide; exists for A/B measurements. */
+void arb_set_gemm_persistent(int32_t on);
+
 /* 1 (default): MMA operands are rounded fp32 -> tf32 by the TMA unit (TFLOAT32 tensor maps); 0: the tensor core
  * truncates.  Process-wide; exists for the precision tests. */
 void arb_set_tf32_round_on_load(int32_t enable);
