@@ -49,7 +49,7 @@ struct AttFwdSmem {
   static constexpr int total() { return Q_BYTES + K_BYTES + V_BYTES + O_BYTES + 256 + 1024; }
 };
 
-template <int DK>
+template <int DK, bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                   const __grid_constant__ CUtensorMap tmK,
                                                                   const __grid_constant__ CUtensorMap tmV,
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
         // (-inf) - (-inf) = NaN like the reference (quirk Q2).
         float e = (bits & (1u << j)) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs)) : 0.0f;
         sum += e;                       // softmax normalises BEFORE dropout (transformer.py:153-155)
-        if (drop.thresh != 0) {
+        if constexpr (DROP) {
           const unsigned long long idx =
               ((unsigned long long)(b * n_heads + head) * S + qidx) * (unsigned long long)S + (32 * c + j);
           e = drop_keep(idx, drop.seed, drop.thresh) ? e * drop.scale : 0.0f;
@@ -237,14 +237,15 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   if ((rc = make_tmap_4d(&tK, a.k, TmapBox{{32, 256, 1, 1}}, 0, 1))) return rc;
   if ((rc = make_tmap_4d(&tV, a.v, TmapBox{{32, 256, 1, 1}}, 1, 1))) return rc;
   if ((rc = make_tmap_4d(&tO, a.o, TmapBox{{32, 128, 1, 1}}, 0, 0))) return rc;
-  auto kern = attn_fwd_kernel<DK>;
-  static bool configured = false;
-  if (!configured) {
+  const bool drop = a.drop.thresh != 0;
+  auto kern = drop ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
+  static bool configured[2] = {false, false};
+  if (!configured[drop ? 1 : 0]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total()) != cudaSuccess) {
       arb_set_error("attn_fwd: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    configured = true;
+    configured[drop ? 1 : 0] = true;
   }
   dim3 grid((a.S + 127) / 128, a.h, a.B);
   {

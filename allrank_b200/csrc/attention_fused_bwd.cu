@@ -83,7 +83,7 @@ struct BwdSmem {
   static constexpr int total() { return BARS_OFF + 256 + 1024; }
 };
 
-template <int DK>
+template <int DK, bool DROP>
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const __grid_constant__ CUtensorMap tmQk, const __grid_constant__ CUtensorMap tmQm,
     const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmKm,
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
             const float2 st = qstats[col0 + j];
             const float p = key_ok ? ex2_approx_b(fmaf(__uint_as_float(sv[j]), c_log2e, st.x)) : 0.0f;
             float p_used = p, dp = __uint_as_float(dv[j]);
-            if (drop.thresh != 0) {      // regenerate the forward's dropout mask on the probabilities
+            if constexpr (DROP) {        // regenerate the forward's dropout mask on the probabilities
               const unsigned long long idx =
                   ((unsigned long long)(b * n_heads + head) * S + (128 * qc + col0 + j)) * (unsigned long long)S + key;
               const float m = drop_keep(idx, drop.seed, drop.thresh) ? drop.scale : 0.0f;
@@ -337,14 +337,15 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
                                                                 a.delta);
   }
   arb_count_launch();
-  auto kern = attn_bwd_kernel<DK>;
-  static bool configured = false;
-  if (!configured) {
+  const bool drop = a.drop.thresh != 0;
+  auto kern = drop ? attn_bwd_kernel<DK, true> : attn_bwd_kernel<DK, false>;
+  static bool configured[2] = {false, false};
+  if (!configured[drop ? 1 : 0]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::total()) != cudaSuccess) {
       arb_set_error("attn_bwd: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    configured = true;
+    configured[drop ? 1 : 0] = true;
   }
   dim3 grid(a.h, a.B);
   {

@@ -62,7 +62,7 @@ struct SmemLayout {
   static constexpr int total() { return body_bytes() + 256 + BLOCK_N * 4 + 1024; }
 };
 
-template <int BLOCK_N, int A_MN, int B_MN>
+template <int BLOCK_N, int A_MN, int B_MN, bool DROP>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const __grid_constant__ CUtensorMap tmC,
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
           float x = __uint_as_float(v[j]) * p.alpha;
           if (p.flags & EPI_BIAS) x += bias_s[32 * c + j];
           if (p.flags & EPI_RELU) x = fmaxf(x, 0.0f);
-          if (p.flags & EPI_DROPOUT) {
+          if constexpr (DROP) {
             const unsigned long long idx = (unsigned long long)(m0 + row) * (unsigned long long)p.N + (n0 + 32 * c + j);
             x = drop_keep(idx, p.drop.seed, p.drop.thresh) ? x * p.drop.scale : 0.0f;
           }
@@ -605,15 +605,19 @@ template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
   if (g_persistent) return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
-  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
+  // dropout epilogue is a separate instantiation (forward linears only) so the common path carries no mask code
+  constexpr bool CAN_DROP = (A_MN == 0 && B_MN == 0);
+  const bool drop = (p.flags & EPI_DROPOUT) != 0;
+  if (drop && !CAN_DROP) { arb_set_error("gemm_tf32: dropout epilogue needs K-major operands"); return ARB_E_UNSUPPORTED; }
+  auto kern = drop ? gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, CAN_DROP> : gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false>;
   constexpr int smem = SmemLayout<BLOCK_N>::total();
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[2] = {false, false};
+  if (!configured[drop ? 1 : 0]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       arb_set_error("gemm_tf32: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    configured = true;
+    configured[drop ? 1 : 0] = true;
   }
   {
     ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * double(d.nb2) * double(d.nb3), st);

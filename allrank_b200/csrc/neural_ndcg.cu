@@ -316,6 +316,352 @@ __global__ void __launch_bounds__(NN_THREADS) neural_ndcg_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ register-tiled variant
+// Slates with at most 128 items (BASELINE config 4: S = 120): the whole n x n matrix M0 and its adjoint live in the
+// REGISTERS of a 1024-thread CTA -- warp w owns rows {w, w+32, w+64, w+96}, lane l owns columns {l, l+32, l+64,
+// l+96}, 4 x 4 elements per thread.  A Sinkhorn iteration is then 16 FMAs per thread plus one warp-shuffle row
+// reduction and one shared-memory column reduction; nothing of size n^2 is read from shared memory inside the
+// 2 x 50 iteration loops (the generic kernel above re-reads the matrix from shared memory ~300 times per slate).
+constexpr int RG_THREADS = 1024;
+constexpr int RG_N = 128;
+
+__host__ __device__ inline size_t rg_smem_bytes(int T) {
+  return (size_t(12) * RG_N + RG_N /*ikeys*/ + 64 + 8 + 2 * 32 * RG_N /*part,part2*/ + 2 * size_t(T) * RG_N) * 4 + 64;
+}
+
+__global__ void __launch_bounds__(RG_THREADS, 1) neural_ndcg_reg_kernel(
+    const float* __restrict__ y_pred, const float* __restrict__ y_true, int B, int S,
+    const float* __restrict__ discounts, NeuralCfg cfg, float* __restrict__ val, float* __restrict__ cnt,
+    float* __restrict__ grad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, l = tid & 31, w = tid >> 5;
+  const bool need_grad = grad != nullptr;
+  const int T = cfg.max_iter;
+
+  float* f = reinterpret_cast<float*>(smem_raw);
+  int* pos = reinterpret_cast<int*>(f);  f += RG_N;
+  float* s = f;       f += RG_N;
+  float* g = f;       f += RG_N;
+  float* coef = f;    f += RG_N;
+  float* alpha = f;   f += RG_N;
+  float* rowtot = f;  f += RG_N;
+  float* u = f;       f += RG_N;
+  float* v = f;       f += RG_N;
+  float* xa = f;      f += RG_N;
+  float* xb = f;      f += RG_N;
+  float* ubar = f;    f += RG_N;
+  float* vbar = f;    f += RG_N;
+  uint32_t* ikeys = reinterpret_cast<uint32_t*>(f);  f += RG_N;
+  float* red = f;     f += 64;
+  int* ishare = reinterpret_cast<int*>(f);  f += 8;
+  float* part = f;    f += 32 * RG_N;
+  float* part2 = f;   f += 32 * RG_N;
+  float* hist_u = f;  f += size_t(T) * RG_N;
+  float* hist_v = f;
+
+  const float* yp = y_pred + size_t(b) * S;
+  const float* yt = y_true + size_t(b) * S;
+
+  const int np2 = next_pow2(S);
+  for (int i = tid; i < np2; i += RG_THREADS) {
+    if (i < S) {
+      const float lab = yt[i];
+      ikeys[i] = ~float_to_ordered(lab == cfg.pad ? -CUDART_INF_F : lab);
+    } else {
+      ikeys[i] = ~0u;
+    }
+  }
+  if (tid == 0) {
+    int n = 0;
+    for (int i = 0; i < S; ++i)
+      if (yt[i] != cfg.pad) pos[n++] = i;
+    ishare[0] = n;
+  }
+  __syncthreads();
+  const int n = ishare[0];
+  bitonic_sort(ikeys, np2);
+  const int kk = (cfg.k <= 0 || cfg.k > S) ? S : cfg.k;
+  if (tid == 0) {
+    double acc = 0.0;
+    for (int j = 0; j < kk; ++j) {
+      uint32_t o = ~ikeys[j];
+      float lab = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+      if (lab == -CUDART_INF_F) lab = 0.0f;
+      const float gain = cfg.powered != 0 ? pow2_minus_1(lab) : lab;
+      acc += double(gain * discounts[j]);
+    }
+    red[32] = float(acc);
+  }
+  __syncthreads();
+  const float idcg = red[32];
+  if (idcg == 0.0f || n == 0) {
+    if (tid == 0) { val[b] = 0.0f; cnt[b] = 0.0f; }
+    if (need_grad) for (int i = tid; i < S; i += RG_THREADS) grad[size_t(b) * S + i] = 0.0f;
+    return;
+  }
+  for (int a = tid; a < RG_N; a += RG_THREADS) {
+    if (a < n) {
+      const int p = pos[a];
+      const float lab = yt[p];
+      s[a] = yp[p];
+      g[a] = cfg.powered == 1 ? pow2_minus_1(lab) : lab;
+      coef[a] = (p < n) ? float(n + 1 - 2 * (p + 1)) : 0.0f;
+      alpha[a] = (p < kk) ? -discounts[p] / (idcg + NN_EPS) : 0.0f;
+    } else {
+      s[a] = 0.f; g[a] = 0.f; coef[a] = 0.f; alpha[a] = 0.f;
+    }
+    u[a] = 1.0f; v[a] = 1.0f; ubar[a] = 0.f; vbar[a] = 0.f; xa[a] = 0.f; xb[a] = 0.f;
+  }
+  __syncthreads();
+  for (int a = tid; a < RG_N; a += RG_THREADS) {
+    float acc = 0.f;
+    if (a < n) {
+      const float sa = s[a];
+      for (int c = 0; c < n; ++c) acc += fabsf(sa - s[c]);
+    }
+    rowtot[a] = acc;
+  }
+  __syncthreads();
+
+  // ---- M0 in registers: m0[k][c] = element (row w+32k, column l+32c)
+  float m0[4][4], mb[4][4];
+  bool rok[4], cok[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { rok[k] = (w + 32 * k) < n; cok[k] = (l + 32 * k) < n; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float cj = coef[w + 32 * k];
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = l + 32 * c;
+      const float lg = (cj * s[i] - rowtot[i]) / cfg.tau;
+      m0[k][c] = (rok[k] && cok[c]) ? lg : -CUDART_INF_F;
+      mx = fmaxf(mx, m0[k][c]);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float e = (rok[k] && cok[c]) ? expf(m0[k][c] - mx) : 0.0f;
+      m0[k][c] = e;
+      z += e;
+    }
+    z = warp_sum(z);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) m0[k][c] = rok[k] ? m0[k][c] / z : 0.0f;
+  }
+
+  // column reduction helper: per-thread partials over its 4 rows -> sums over all rows, result in dst[0..127]
+  auto col_reduce = [&](const float (&cp)[4], float* scratch, float* dst) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) scratch[w * RG_N + l + 32 * c] = cp[c];
+    __syncthreads();
+    if (tid < RG_N) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int ww = 0; ww < 32; ++ww) t += scratch[ww * RG_N + tid];
+      dst[tid] = t;
+    }
+    __syncthreads();
+  };
+
+  // ---- Sinkhorn iterations on the scale vectors
+  int iters = 0;
+  for (int t = 0; t < T; ++t) {
+    float cp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float uk = u[w + 32 * k];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) cp[c] += uk * m0[k][c];
+    }
+    col_reduce(cp, part, xa);                      // xa[i] = sum_j u_j M0[j,i]
+    float dev = 0.f;
+    if (tid < RG_N) {
+      const float cs = (tid < n) ? v[tid] * xa[tid] : 1.0f;
+      xa[tid] = cs;
+      dev = fabsf(cs - 1.0f);
+      dev = warp_max(dev);
+      if (l == 0) red[w] = dev;
+    }
+    __syncthreads();
+    dev = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    if (t > 0 && dev < cfg.tol) break;
+    if (tid < n) {
+      const float cs = xa[tid];
+      const bool clamped = cs < NN_EPS;
+      const float vn = v[tid] / (clamped ? NN_EPS : cs);
+      v[tid] = vn;
+      if (need_grad) hist_v[size_t(t) * RG_N + tid] = clamped ? -vn : vn;
+    }
+    __syncthreads();
+    float vc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) vc[c] = v[l + 32 * c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float rp = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rp += m0[k][c] * vc[c];
+      rp = warp_sum(rp);
+      const int j = w + 32 * k;
+      if (l == 0 && j < n) {
+        const float rs = u[j] * rp;
+        const bool clamped = rs < NN_EPS;
+        const float un = u[j] / (clamped ? NN_EPS : rs);
+        u[j] = un;
+        if (need_grad) hist_u[size_t(t) * RG_N + j] = clamped ? -un : un;
+      }
+    }
+    __syncthreads();
+    iters = t + 1;
+  }
+  __syncthreads();
+
+  // ---- soft DCG and the adjoints of u, v, M0 at the end of the iterations
+  float lossb = 0.f;
+  {
+    float vg[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) vg[c] = v[l + 32 * c] * g[l + 32 * c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc += m0[k][c] * vg[c];
+      acc = warp_sum(acc);
+      const int j = w + 32 * k;
+      if (l == 0 && j < n) {
+        lossb += alpha[j] * u[j] * acc;
+        ubar[j] = alpha[j] * acc;
+      }
+    }
+  }
+  lossb = block_sum(lossb, red);
+  if (tid == 0) { val[b] = lossb; cnt[b] = 1.0f; }
+  if (!need_grad) return;
+  {
+    float cp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = w + 32 * k;
+      const float au = alpha[j] * u[j];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        cp[c] += au * m0[k][c];
+        mb[k][c] = au * (v[l + 32 * c] * g[l + 32 * c]);
+      }
+    }
+    col_reduce(cp, part, xb);
+    if (tid < RG_N) vbar[tid] = g[tid] * xb[tid];
+    __syncthreads();
+  }
+
+  // ---- reverse sweep
+  for (int t = iters - 1; t >= 0; --t) {
+    const float* ut = hist_u + size_t(t) * RG_N;
+    const float* vt = hist_v + size_t(t) * RG_N;
+    if (tid < RG_N) {
+      float x = 0.f;
+      if (tid < n) {
+        const float uj = ut[tid];
+        if (uj < 0.f) { x = 0.f; ubar[tid] = ubar[tid] / NN_EPS; }
+        else          { x = -ubar[tid] * uj * uj; ubar[tid] = 0.f; }
+      }
+      xa[tid] = x;
+    }
+    __syncthreads();
+    {
+      float cp[4] = {0.f, 0.f, 0.f, 0.f};
+      float vtc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vtc[c] = cok[c] ? fabsf(vt[l + 32 * c]) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float bj = xa[w + 32 * k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          cp[c] += bj * m0[k][c];
+          mb[k][c] += bj * vtc[c];
+        }
+      }
+      col_reduce(cp, part, xb);                    // xb[i] = (M0^T bbar)_i
+    }
+    if (tid < RG_N) {
+      float x = 0.f;
+      if (tid < n) {
+        const float vb = vbar[tid] + xb[tid];
+        const float vi = vt[tid];
+        if (vi < 0.f) { x = 0.f; vbar[tid] = vb / NN_EPS; }
+        else          { x = -vb * vi * vi; vbar[tid] = 0.f; }
+      }
+      xb[tid] = x;                                  // abar
+    }
+    __syncthreads();
+    {
+      const float* up = (t > 0) ? hist_u + size_t(t - 1) * RG_N : nullptr;
+      float ab[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ab[c] = xb[l + 32 * c];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = w + 32 * k;
+        const float uj = (j < n) ? (up ? fabsf(up[j]) : 1.0f) : 0.0f;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          acc += m0[k][c] * ab[c];
+          mb[k][c] += uj * ab[c];
+        }
+        acc = warp_sum(acc);
+        if (l == 0 && j < n) ubar[j] += acc;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- row softmax backward, then logits -> scores
+  {
+    float cpd[4] = {0.f, 0.f, 0.f, 0.f}, cpr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dot += m0[k][c] * mb[k][c];
+      dot = warp_sum(dot);
+      const float cj = coef[w + 32 * k];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float lb = m0[k][c] * (mb[k][c] - dot);
+        cpd[c] += lb * cj;
+        cpr[c] += lb;
+      }
+    }
+    col_reduce(cpd, part, xa);
+    col_reduce(cpr, part2, xb);
+  }
+  const float inv_tau = 1.0f / cfg.tau;
+  if (tid < RG_N) {
+    xa[tid] = xa[tid] * inv_tau;       // direct_i
+    xb[tid] = -xb[tid] * inv_tau;      // rbar_i
+  }
+  for (int i = tid; i < S; i += RG_THREADS) grad[size_t(b) * S + i] = 0.0f;
+  __syncthreads();
+  if (tid < n) {
+    const float sm = s[tid], rm = xb[tid];
+    float acc = xa[tid];
+    for (int i = 0; i < n; ++i) {
+      const float d = sm - s[i];
+      const float sg = (d > 0.f) ? 1.0f : (d < 0.f ? -1.0f : 0.0f);
+      acc += (rm + xb[i]) * sg;
+    }
+    grad[size_t(b) * S + pos[tid]] = acc;
+  }
+}
+
 }  // namespace arb
 
 using namespace arb;
@@ -326,6 +672,7 @@ extern "C" size_t arb_neural_ndcg_workspace_bytes(int32_t B, int32_t S, int32_t 
   if (B <= 0 || S <= 0) return 0;
   const size_t small = nn_small_floats(S) * 4;
   const size_t big = nn_big_floats(S, max_iter, true) * 4;
+  if (S <= RG_N && rg_smem_bytes(max_iter) <= nn_smem_budget()) return 0;
   if (small + big <= nn_smem_budget()) return 0;
   return size_t(B) * big;
 }
@@ -340,6 +687,26 @@ extern "C" int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int
     return ARB_E_INVALID_ARG;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (S <= RG_N && rg_smem_bytes(max_iter) <= nn_smem_budget()) {
+    // register-tiled kernel: the whole matrix and its adjoint stay in the registers of a 1024-thread CTA
+    const size_t smem_rg = rg_smem_bytes(max_iter);
+    if (smem_rg > 48 * 1024 &&
+        cudaFuncSetAttribute((const void*)neural_ndcg_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(smem_rg)) != cudaSuccess) {
+      arb_set_error("arb_neural_ndcg: cannot raise the shared-memory limit");
+      return ARB_E_CUDA;
+    }
+    NeuralCfg cfg_rg{pad_value, temperature, tol, powered_relevancies, k, max_iter};
+    {
+      ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
+      neural_ndcg_reg_kernel<<<B, RG_THREADS, smem_rg, st>>>(y_pred, y_true, B, S, discounts, cfg_rg, scratch,
+                                                          scratch + B, grad);
+    }
+    arb_count_launch();
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) { arb_set_error(cudaGetErrorString(e2)); return ARB_E_CUDA; }
+    return arb_finalize_mean_over_count(scratch, scratch + B, B, loss, grad, size_t(B) * S, st);
+  }
   const size_t small = nn_small_floats(S) * 4;
   if (small > nn_smem_budget()) { arb_set_error("arb_neural_ndcg: slate too long"); return ARB_E_UNSUPPORTED; }
   const size_t big_all = nn_big_floats(S, max_iter, grad != nullptr) * 4;
