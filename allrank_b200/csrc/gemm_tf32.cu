@@ -45,14 +45,15 @@ struct GemmParams {
   DropSite drop;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool LONG_K = false>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGING_BYTES = BLOCK_M * BLOCK_N * 4;
   // Two stages: the contraction is short (K = 32..512) and latency is hidden by co-resident CTAs instead
   // (~80 KB per CTA with an epilogue tile -> 2 per SM; ~50 KB without -> 4 per SM).
-  static constexpr int stages() { return 2; }
+  // weight-gradient GEMMs (both operands MN-major, K = all rows of the batch) run a long K loop per CTA: 4 stages
+  static constexpr int stages() { return LONG_K ? 4 : 2; }
   static constexpr int pipe_bytes() { return stages() * STAGE_BYTES; }
   // without an aux (residual / mask) tile the output staging aliases the operand ring: it is only written after
   // the last MMA has consumed the ring
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tmC,
                                                                  const __grid_constant__ CUtensorMap tmAux,
                                                                  const GemmParams p) {
-  using L = SmemLayout<BLOCK_N>;
+  using L = SmemLayout<BLOCK_N, (A_MN == 1 && B_MN == 1)>;
   constexpr int STAGES = L::stages();
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr int N_SLABS = BLOCK_N / 32;
@@ -610,7 +611,7 @@ static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap&
   const bool drop = (p.flags & EPI_DROPOUT) != 0;
   if (drop && !CAN_DROP) { arb_set_error("gemm_tf32: dropout epilogue needs K-major operands"); return ARB_E_UNSUPPORTED; }
   auto kern = drop ? gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, CAN_DROP> : gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false>;
-  constexpr int smem = SmemLayout<BLOCK_N>::total();
+  constexpr int smem = SmemLayout<BLOCK_N, (A_MN == 1 && B_MN == 1)>::total();
   static bool configured[2] = {false, false};
   if (!configured[drop ? 1 : 0]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
