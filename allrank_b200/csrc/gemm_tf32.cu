@@ -45,7 +45,7 @@ struct GemmParams {
   DropSite drop;
 };
 
-template <int BLOCK_N, bool LONG_K = false>
+template <int BLOCK_N, int NST = 2>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -53,7 +53,7 @@ struct SmemLayout {
   // Two stages: the contraction is short (K = 32..512) and latency is hidden by co-resident CTAs instead
   // (~80 KB per CTA with an epilogue tile -> 2 per SM; ~50 KB without -> 4 per SM).
   // weight-gradient GEMMs (both operands MN-major, K = all rows of the batch) run a long K loop per CTA: 4 stages
-  static constexpr int stages() { return LONG_K ? 4 : 2; }
+  static constexpr int stages() { return NST; }
   static constexpr int pipe_bytes() { return stages() * STAGE_BYTES; }
   // without an aux (residual / mask) tile the output staging aliases the operand ring: it is only written after
   // the last MMA has consumed the ring
@@ -63,13 +63,13 @@ struct SmemLayout {
   static constexpr int total() { return body_bytes() + 256 + BLOCK_N * 4 + 1024; }
 };
 
-template <int BLOCK_N, int A_MN, int B_MN, bool DROP>
+template <int BLOCK_N, int A_MN, int B_MN, bool DROP, int NST>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const __grid_constant__ CUtensorMap tmC,
                                                                  const __grid_constant__ CUtensorMap tmAux,
                                                                  const GemmParams p) {
-  using L = SmemLayout<BLOCK_N, (A_MN == 1 && B_MN == 1)>;
+  using L = SmemLayout<BLOCK_N, NST>;
   constexpr int STAGES = L::stages();
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr int N_SLABS = BLOCK_N / 32;
@@ -606,19 +606,32 @@ template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
   if (g_persistent) return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
-  // dropout epilogue is a separate instantiation (forward linears only) so the common path carries no mask code
+  // dropout epilogue is a separate instantiation (forward linears only) so the common path carries no mask code;
+  // ring depth: 4 stages for the long split-K loops of the weight gradients (1 CTA/SM), 3 for K >= 256
+  // (2 CTAs/SM), 2 for the short contractions (3-4 CTAs/SM)
   constexpr bool CAN_DROP = (A_MN == 0 && B_MN == 0);
+  constexpr bool WGRAD = (A_MN == 1 && B_MN == 1);
   const bool drop = (p.flags & EPI_DROPOUT) != 0;
   if (drop && !CAN_DROP) { arb_set_error("gemm_tf32: dropout epilogue needs K-major operands"); return ARB_E_UNSUPPORTED; }
-  auto kern = drop ? gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, CAN_DROP> : gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false>;
-  constexpr int smem = SmemLayout<BLOCK_N, (A_MN == 1 && B_MN == 1)>::total();
-  static bool configured[2] = {false, false};
-  if (!configured[drop ? 1 : 0]) {
+  const bool deep = !WGRAD && d.K >= 256;
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmParams);
+  int smem, slot;
+  if (WGRAD) {
+    kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false, 4>; smem = SmemLayout<BLOCK_N, 4>::total(); slot = 0;
+  } else if (drop) {
+    if (deep) { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, CAN_DROP, 3>; smem = SmemLayout<BLOCK_N, 3>::total(); slot = 1; }
+    else      { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, CAN_DROP, 2>; smem = SmemLayout<BLOCK_N, 2>::total(); slot = 2; }
+  } else {
+    if (deep) { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false, 3>; smem = SmemLayout<BLOCK_N, 3>::total(); slot = 3; }
+    else      { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false, 2>; smem = SmemLayout<BLOCK_N, 2>::total(); slot = 4; }
+  }
+  static bool configured[5] = {false, false, false, false, false};
+  if (!configured[slot]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       arb_set_error("gemm_tf32: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    configured[drop ? 1 : 0] = true;
+    configured[slot] = true;
   }
   {
     ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * double(d.nb2) * double(d.nb3), st);
