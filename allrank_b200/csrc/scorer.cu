@@ -174,7 +174,8 @@ static int linear_bwd_weight(const Ctx& k, const float* dY, int64_t dy_pitch, in
   g.block_n = pick_block_n(in);
   const int tiles = ((out + 127) / 128) * ((in + g.block_n - 1) / g.block_n);
   const int kb = int((k.R + 31) / 32);
-  g.split_k = std::max(1, std::min(kb / 8 + 1, (148 * 2 + tiles - 1) / tiles));   // 4-stage ring: 1 CTA per SM, 2 waves
+  // 4-stage ring => 1 CTA per SM: one wave of ~148 CTAs (fewer splits = fewer L2 reductions of the dW tile)
+  g.split_k = std::max(1, std::min(kb / 8 + 1, std::max(1, 148 / tiles)));
   return launch_gemm_tf32(g, k.st);
 }
 
