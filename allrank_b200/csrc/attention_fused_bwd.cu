@@ -99,11 +99,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
   float2* qstats = reinterpret_cast<float2*>(smem + BwdSmem::STATS_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS_OFF);
   uint64_t* kv_bar = bars;          // K/V tiles of this key tile landed        (one phase per key tile)
-  uint64_t* q_bar = bars + 1;       // Q/dO tiles of this iteration landed        (one phase per iteration)
+  uint64_t* q_bar = bars + 1;       // K-major Q/dO tiles of this iteration landed (one phase per iteration)
   uint64_t* s_bar = bars + 2;       // S^T and dP^T complete                      (per iteration)
   uint64_t* p_bar = bars + 3;       // P^T / dS^T written by the 256 compute threads (per iteration)
   uint64_t* mma_bar = bars + 4;     // trailing MMAs (dV, dK, dQ) complete        (per iteration)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* qm_bar = bars + 5;      // MN-major Q/dO tiles of this iteration landed (one phase per iteration)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x, b = blockIdx.y;
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     ptx::mbar_init(s_bar, 1);
     ptx::mbar_init(p_bar, 256);
     ptx::mbar_init(mma_bar, 1);
+    ptx::mbar_init(qm_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -134,18 +136,23 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       int it = 0;
       for (int jt = 0; jt < n_kt; ++jt) {
         for (int qc = 0; qc < n_kt; ++qc, ++it) {
-          if (it > 0) ptx::mbar_wait(mma_bar, (it - 1) & 1);   // previous iteration's MMAs have consumed the tiles
+          // The K-major Q/dO tiles are read only by the S^T / dP^T MMAs, so they can be refilled as soon as the
+          // previous iteration's S^T / dP^T have completed -- i.e. while its compute phase and trailing MMAs run.
+          if (it > 0) ptx::mbar_wait(s_bar, (it - 1) & 1);
+          ptx::mbar_expect_tx(q_bar, 2 * TILE_BYTES);
+          ptx::tma_load_4d(tile(BwdSmem::Q_KM), &tmQk, q_bar, 0, 128 * qc, head, b);
+          ptx::tma_load_4d(tile(BwdSmem::DO_KM), &tmDOk, q_bar, 0, 128 * qc, head, b);
+          // everything else is still in use by the trailing MMAs (dV, dK, dQ) of the previous iteration
+          if (it > 0) ptx::mbar_wait(mma_bar, (it - 1) & 1);
           if (qc == 0) {
             ptx::mbar_expect_tx(kv_bar, 3 * TILE_BYTES);
             ptx::tma_load_4d(tile(BwdSmem::K_KM), &tmKk, kv_bar, 0, 128 * jt, head, b);
             ptx::tma_load_4d(tile(BwdSmem::K_MN), &tmKm, kv_bar, 0, 128 * jt, head, b);
             ptx::tma_load_4d(tile(BwdSmem::V_KM), &tmVk, kv_bar, 0, 128 * jt, head, b);
           }
-          ptx::mbar_expect_tx(q_bar, 4 * TILE_BYTES);
-          ptx::tma_load_4d(tile(BwdSmem::Q_KM), &tmQk, q_bar, 0, 128 * qc, head, b);
-          ptx::tma_load_4d(tile(BwdSmem::Q_MN), &tmQm, q_bar, 0, 128 * qc, head, b);
-          ptx::tma_load_4d(tile(BwdSmem::DO_KM), &tmDOk, q_bar, 0, 128 * qc, head, b);
-          ptx::tma_load_4d(tile(BwdSmem::DO_MN), &tmDOm, q_bar, 0, 128 * qc, head, b);
+          ptx::mbar_expect_tx(qm_bar, 2 * TILE_BYTES);
+          ptx::tma_load_4d(tile(BwdSmem::Q_MN), &tmQm, qm_bar, 0, 128 * qc, head, b);
+          ptx::tma_load_4d(tile(BwdSmem::DO_MN), &tmDOm, qm_bar, 0, 128 * qc, head, b);
         }
       }
     }
@@ -178,6 +185,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           }
           ptx::mma_commit(s_bar);
           ptx::mbar_wait(p_bar, it & 1);
+          ptx::mbar_wait(qm_bar, it & 1);
           ptx::tc_fence_after();
           for (int i = 0; i < 16; ++i) {     // contraction over the 128 queries of this chunk
             ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, ptx::smem_desc_sw128<1>(dom + i * 1024, TILE_BYTES, 512), id_ts,
