@@ -34,6 +34,8 @@ struct AttnBwdArgs {
   const float* stat_max;      // [B,h,S] from the fused forward
   const float* stat_sum;      // [B,h,S]
   float* delta;               // [B,h,S] scratch
+  float* dbias_qkv = nullptr; // optional [3*d_model]: += column sums of dQ | dK | dV (bias gradient of the QKV linear)
+  int d_model = 0;
   int B, h, S, dk;
   float scale;
   DropSite drop{0u, 0u, 1.0f};

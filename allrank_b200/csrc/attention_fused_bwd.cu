@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const __grid_constant__ CUtensorMap tmDOm, const __grid_constant__ CUtensorMap tmDQ,
     const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
     const uint8_t* __restrict__ mask, const float* __restrict__ stat_max, const float* __restrict__ stat_sum,
-    const float* __restrict__ delta, int S, int n_heads, float scale, DropSite drop) {
+    const float* __restrict__ delta, int S, int n_heads, float scale, DropSite drop, float* __restrict__ dbias_qkv,
+    int d_model) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   auto tile = [&](int t) { return smem + t * TILE_BYTES; };
@@ -301,6 +302,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           }
           ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(1, 256);
+          if (dbias_qkv != nullptr && ct < 96) {
+            // bias gradient of the QKV projection: column sums of the staged dV / dK / dQ tiles (rows past S are 0)
+            const int which = ct >> 5, cc = ct & 31;
+            const bool live = (which < 2) ? last_qc : last_jt;
+            if (live && cc < DK) {
+              const uint8_t* tl = stage + which * TILE_BYTES;
+              float t = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 128; ++r)
+                t += *reinterpret_cast<const float*>(tl + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
+              const int off = (which == 0 ? 2 * d_model : (which == 1 ? d_model : 0)) + head * DK + cc;
+              atomicAdd(dbias_qkv + off, t);
+            }
+          }
           if (ct == 0) {
             if (last_qc) {
               ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * jt, head, b);
@@ -359,7 +374,8 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   {
     ProfScope ps(ARB_PROF_GEMM, 10.0 * double(a.S) * a.S * a.dk * a.h * a.B, st);
     kern<<<grid, BWD_THREADS, BwdSmem::total(), st>>>(tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
-                                                      a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale, a.drop);
+                                                      a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale, a.drop, a.dbias_qkv,
+                                                      a.d_model);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

@@ -43,6 +43,7 @@ struct GemmParams {
   float* atomic_out;
   long long atomic_ld;
   DropSite drop;
+  float* colsum_out;
 };
 
 template <int BLOCK_N, int NST = 2>
@@ -244,8 +245,19 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
         for (int c = 0; c < N_SLABS; ++c)
           ptx::tma_store_4d(&tmC, staging + c * (BLOCK_M * 128), n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
         ptx::tma_store_commit();
-        ptx::tma_store_wait_read();   // smem may be released once the TMA engine has read it
       }
+      if ((p.flags & EPI_COLSUM) && et < BLOCK_N && n0 + et < p.N) {
+        // bias gradient fused into the epilogue: thread = output column, walks the 128 staged rows (conflict-free
+        // under the 128B swizzle).  Rows past M hold exact zeros (zero-filled operands / mask tile).
+        const uint8_t* slab = staging + (et >> 5) * (BLOCK_M * 128);
+        const int cc = et & 31;
+        float t = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < BLOCK_M; ++r)
+          t += *reinterpret_cast<const float*>(slab + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
+        atomicAdd(p.colsum_out + n0 + et, t);
+      }
+      if (et == 0) ptx::tma_store_wait_read();   // smem may be released once the TMA engine has read it
     }
     ptx::tc_fence_before();
   }
@@ -611,7 +623,7 @@ static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const C
 template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
-  if (g_persistent) return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
+  if (g_persistent && !(p.flags & EPI_COLSUM)) return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
   // dropout epilogue is a separate instantiation (forward linears only) so the common path carries no mask code;
   // ring depth: 4 stages for the long split-K loops of the weight gradients (1 CTA/SM), 3 for K >= 256
   // (2 CTAs/SM), 2 for the short contractions (3-4 CTAs/SM)
@@ -676,6 +688,8 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
   p.a_b2 = d.a_b2; p.a_b3 = d.a_b3; p.b_b2 = d.b_b2; p.b_b3 = d.b_b3; p.c_b2 = d.c_b2; p.c_b3 = d.c_b3;
   p.flags = d.flags; p.alpha = d.alpha; p.bias = d.bias; p.atomic_out = d.atomic_out; p.atomic_ld = d.atomic_ld;
   p.drop = d.drop;
+  p.colsum_out = d.colsum_out;
+  if ((d.flags & EPI_COLSUM) && (!d.colsum_out || split)) { arb_set_error("gemm_tf32: EPI_COLSUM needs colsum_out and a non-split launch"); return ARB_E_INVALID_ARG; }
   if ((d.flags & EPI_DROPOUT) && d.drop.thresh == 0) p.flags &= ~EPI_DROPOUT;
   p.kb_per_split = (total_kb + splits - 1) / splits;
   const int eff_splits = split ? (total_kb + p.kb_per_split - 1) / std::max(1, p.kb_per_split) : 1;

@@ -21,6 +21,7 @@ enum : int {
   EPI_MASK_AUX = 8,   // . * (Aux[m,n] > 0)  (ReLU backward)
   EPI_ATOMIC = 16,    // red.add into atomic_out instead of storing C (split-K weight gradients)
   EPI_DROPOUT = 32,   // inverted dropout on (alpha*acc + bias [relu]) before the aux tile is added
+  EPI_COLSUM = 64,    // colsum_out[n] += sum_m C[m,n]  (bias gradient of the layer that produced C's input)
 };
 
 struct GemmDesc {
@@ -38,6 +39,7 @@ struct GemmDesc {
   float* atomic_out = nullptr;  // row-major [M, atomic_ld]
   int64_t atomic_ld = 0;
   DropSite drop{0u, 0u, 1.0f};  // EPI_DROPOUT: element index = m * N + n (unbatched problems only)
+  float* colsum_out = nullptr;  // EPI_COLSUM: [N], accumulated with atomics
 };
 
 int launch_gemm_tf32(const GemmDesc& d, cudaStream_t stream);   // 0 or ARB_E_*

@@ -151,9 +151,11 @@ static int linear_fwd(const Ctx& k, const float* X, int64_t x_pitch, int in, con
 }
 // dX[R,in] = epi( dY[R,out] W[out,in] )      (W read as an MN-major B operand)
 static int linear_bwd_input(const Ctx& k, const float* dY, int64_t dy_pitch, int out, const float* Wt, int in, float* dX,
-                            int64_t dx_pitch, int flags, const float* aux, int64_t aux_pitch, float alpha = 1.0f) {
+                            int64_t dx_pitch, int flags, const float* aux, int64_t aux_pitch, float alpha = 1.0f,
+                            float* colsum_out = nullptr) {
   GemmDesc g;
   g.alpha = alpha;
+  g.colsum_out = colsum_out;
   g.M = int(k.R); g.N = in; g.K = out; g.b_mn = 1;
   g.A = rows_view(dY, out, k.R, dy_pitch);
   g.B = rows_view(Wt, in, out, in);          // dim0 = in (N, contiguous), dim1 = out (K)
@@ -332,7 +334,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   ARB_TRY(head_backward(dscores, scores, xlast, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr,
                         ws + W.meanf, ws + W.stdf, c.ln_eps, P + L.head_w, P + L.head_b, has_norm, c.out_act, k.R, d, dx,
                         has_norm ? G + L.lnf_a : nullptr, has_norm ? G + L.lnf_b : nullptr, G + L.head_w, G + L.head_b,
-                        st, dxm, top_site));
+                        st, dxm, top_site, c.n_layers > 0 ? G + L.layer[c.n_layers - 1].b2 : G + L.fc_b));
   const float* dy = top_site.thresh ? dxm : dx;   // gradient w.r.t. the output of the linear below the dropout
   for (int l = c.n_layers - 1; l >= 0; --l) {
     const auto& pl = L.layer[l];
@@ -342,23 +344,20 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     float* prob = W.fused ? scratch + Z.prob : ws + wl.prob;
     float* xmid = ws + wl.xmid; float* xn2 = ws + wl.xn2; float* hdn = ws + wl.hdn;
     // ---- feed-forward sublayer backward:  xout = xmid + W2 relu(W1 xn2 + b1) + b2
-    ARB_TRY(linear_bwd_weight(k, dy, d, d, hdn, f, f, G + pl.w2));
-    ARB_TRY(colsum_accumulate(dy, k.R, d, d, G + pl.b2, st));
+    ARB_TRY(linear_bwd_weight(k, dy, d, d, hdn, f, f, G + pl.w2));   // (b2 gradient: fused into the kernel that emitted dy)
     // hdn <- d hdn in place; hdn > 0 <=> ReLU active AND kept by the hidden dropout, so the mask tile also carries
     // the dropout mask and only the 1/(1-p) scale is needed
-    ARB_TRY(linear_bwd_input(k, dy, d, d, P + pl.w2, f, hdn, f, EPI_MASK_AUX, hdn, f,
-                             drop_on ? 1.0f / (1.0f - p_drop) : 1.0f));
+    ARB_TRY(linear_bwd_input(k, dy, d, d, P + pl.w2, f, hdn, f, EPI_MASK_AUX | EPI_COLSUM, hdn, f,
+                             drop_on ? 1.0f / (1.0f - p_drop) : 1.0f, G + pl.b1));   // b1 gradient in the epilogue
     ARB_TRY(linear_bwd_weight(k, hdn, f, f, xn2, d, d, G + pl.w1));
-    ARB_TRY(colsum_accumulate(hdn, k.R, f, f, G + pl.b1, st));
     ARB_TRY(linear_bwd_input(k, hdn, f, f, P + pl.w1, d, dxn, d, 0, nullptr, 0));
     const DropSite site_ao = make_drop_site(seed, l, SITE_ATTN_OUT, p_drop);
     ARB_TRY(ln_backward(dxn, xmid, P + pl.ln2_a, ws + wl.mean2, ws + wl.std2, c.ln_eps, dx, k.R, d, dx_alt,
-                        G + pl.ln2_a, G + pl.ln2_b, st, dxm, site_ao));
+                        G + pl.ln2_a, G + pl.ln2_b, st, dxm, site_ao, G + pl.bo));
     // dx_alt = d loss / d xmid ; dy = the same through the dropout on the attention sublayer output
     dy = site_ao.thresh ? dxm : dx_alt;
     // ---- attention sublayer backward:  xmid = xin + Wo ctx + bo
-    ARB_TRY(linear_bwd_weight(k, dy, d, d, ctx, d, d, G + pl.wo));
-    ARB_TRY(colsum_accumulate(dy, k.R, d, d, G + pl.bo, st));
+    ARB_TRY(linear_bwd_weight(k, dy, d, d, ctx, d, d, G + pl.wo));   // (bo gradient: fused into the LayerNorm backward above)
     ARB_TRY(linear_bwd_input(k, dy, d, d, P + pl.wo, d, dctx, d, 0, nullptr, 0));
     if (use_fused_bwd(c, S)) {
       AttnBwdArgs a;   // dQ, dK, dV from d ctx in one kernel; P is recomputed in TMEM from the saved row statistics
@@ -373,6 +372,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
       a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum; a.delta = scratch + Z.delta;
       a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = alpha;
       a.drop = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
+      a.dbias_qkv = G + pl.bqkv; a.d_model = d;          // bias gradient of the QKV projection, fused
       ARB_TRY(launch_attn_bwd(a, st));
     } else {
       if (W.fused) {   // the fused forward kept no probabilities: recompute P = softmax(mask(alpha Q K^T))
@@ -424,18 +424,17 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
       }
     }
     ARB_TRY(linear_bwd_weight(k, dqkv, 3 * d, 3 * d, xn1, d, d, G + pl.wqkv));
-    ARB_TRY(colsum_accumulate(dqkv, k.R, 3 * d, 3 * d, G + pl.bqkv, st));
+    if (!use_fused_bwd(c, S)) ARB_TRY(colsum_accumulate(dqkv, k.R, 3 * d, 3 * d, G + pl.bqkv, st));
     ARB_TRY(linear_bwd_input(k, dqkv, 3 * d, 3 * d, P + pl.wqkv, d, dxn, d, 0, nullptr, 0));
     const DropSite site_below = l > 0 ? make_drop_site(seed, l - 1, SITE_FFN_OUT, p_drop)
                                       : make_drop_site(seed, 0, SITE_FC, p_fc);
     ARB_TRY(ln_backward(dxn, xin, P + pl.ln1_a, ws + wl.mean1, ws + wl.std1, c.ln_eps, dx_alt, k.R, d, dx,
-                        G + pl.ln1_a, G + pl.ln1_b, st, dxm, site_below));
+                        G + pl.ln1_a, G + pl.ln1_b, st, dxm, site_below, l > 0 ? G + L.layer[l - 1].b2 : G + L.fc_b));
     // dx = d loss / d xin ; dy = the same through the dropout that produced xin's last summand
     dy = site_below.thresh ? dxm : dx;
   }
   // ---- input FC backward (x is data: no input gradient)
-  ARB_TRY(linear_bwd_weight(k, dy, d, d, x, F, F, G + L.fc_w));
-  ARB_TRY(colsum_accumulate(dy, k.R, d, d, G + L.fc_b, st));
+  ARB_TRY(linear_bwd_weight(k, dy, d, d, x, F, F, G + L.fc_w));   // (fc_b gradient: fused into the kernel that emitted dy)
   return ARB_OK;
 }
 

@@ -109,13 +109,14 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
                                                                     int width, int rows_per_warp,
                                                                     float* __restrict__ dx, float* __restrict__ grad_a,
                                                                     float* __restrict__ grad_b,
-                                                                    float* __restrict__ dx_masked, DropSite site) {
+                                                                    float* __restrict__ dx_masked, DropSite site,
+                                                                    float* __restrict__ colsum_out) {
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  RowRegs<NV> ga, acc_a, acc_b;
+  RowRegs<NV> ga, acc_a, acc_b, acc_c;
   load_row<NV>(a, width, lane, ga);
 #pragma unroll
-  for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = acc_c.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
   for (int it = 0; it < rows_per_warp; ++it) {
     const long long row = first + it;
@@ -170,15 +171,22 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
       apply_drop<NV>(g, row, width, lane, site);
       store_row<NV>(dx_masked + row * width, width, lane, g);
     }
+    if (colsum_out) {  // bias gradient of the linear below = column sums of what that linear receives
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        acc_c.v[k].x += g.v[k].x; acc_c.v[k].y += g.v[k].y; acc_c.v[k].z += g.v[k].z; acc_c.v[k].w += g.v[k].w;
+      }
+    }
   }
   // block-level reduction of the gain/bias gradients
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    const RowRegs<NV>& src = pass == 0 ? acc_a : acc_b;
+  for (int pass = 0; pass < 3; ++pass) {
+    if (pass == 2 && !colsum_out) continue;
+    const RowRegs<NV>& src = pass == 0 ? acc_a : (pass == 1 ? acc_b : acc_c);
 #pragma unroll
     for (int k = 0; k < NV; ++k) *reinterpret_cast<float4*>(&sh[wid][lane * 4 + 128 * k]) = src.v[k];
     __syncthreads();
-    float* dst = pass == 0 ? grad_a : grad_b;
+    float* dst = pass == 0 ? grad_a : (pass == 1 ? grad_b : colsum_out);
     for (int c = threadIdx.x; c < width; c += blockDim.x) {
       float t = 0.f;
 #pragma unroll
@@ -380,15 +388,15 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
     const float* __restrict__ std_i, float eps, const float* __restrict__ w, const float* __restrict__ wb,
     int has_norm, int act, long long rows, int width, int rows_per_warp, float* __restrict__ dx,
     float* __restrict__ grad_a, float* __restrict__ grad_b, float* __restrict__ grad_w, float* __restrict__ grad_wb,
-    float* __restrict__ dx_masked, DropSite site) {
+    float* __restrict__ dx_masked, DropSite site, float* __restrict__ colsum_out) {
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   __shared__ float shb[ROWS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  RowRegs<NV> ga, gb, gw, acc_a, acc_b, acc_w;
+  RowRegs<NV> ga, gb, gw, acc_a, acc_b, acc_w, acc_c;
   load_row<NV>(w, width, lane, gw);
   if (has_norm) { load_row<NV>(a, width, lane, ga); load_row<NV>(b, width, lane, gb); }
 #pragma unroll
-  for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = acc_w.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = acc_w.v[k] = acc_c.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   float acc_wb = 0.f;
   const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
   for (int it = 0; it < rows_per_warp; ++it) {
@@ -413,6 +421,12 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
       }
       store_row<NV>(dx + row * width, width, lane, g);
       if (dx_masked) { apply_drop<NV>(g, row, width, lane, site); store_row<NV>(dx_masked + row * width, width, lane, g); }
+      if (colsum_out) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          acc_c.v[k].x += g.v[k].x; acc_c.v[k].y += g.v[k].y; acc_c.v[k].z += g.v[k].z; acc_c.v[k].w += g.v[k].w;
+        }
+      }
       continue;
     }
     const float mean = mean_i[row], sd = std_i[row];
@@ -458,15 +472,22 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
     }
     store_row<NV>(dx + row * width, width, lane, g);
     if (dx_masked) { apply_drop<NV>(g, row, width, lane, site); store_row<NV>(dx_masked + row * width, width, lane, g); }
+    if (colsum_out) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        acc_c.v[k].x += g.v[k].x; acc_c.v[k].y += g.v[k].y; acc_c.v[k].z += g.v[k].z; acc_c.v[k].w += g.v[k].w;
+      }
+    }
   }
 #pragma unroll
-  for (int pass = 0; pass < 3; ++pass) {
+  for (int pass = 0; pass < 4; ++pass) {
     if (!has_norm && pass < 2) continue;
-    const RowRegs<NV>& src = pass == 0 ? acc_a : (pass == 1 ? acc_b : acc_w);
+    if (pass == 3 && !colsum_out) continue;
+    const RowRegs<NV>& src = pass == 0 ? acc_a : (pass == 1 ? acc_b : (pass == 2 ? acc_w : acc_c));
 #pragma unroll
     for (int k = 0; k < NV; ++k) *reinterpret_cast<float4*>(&sh[wid][lane * 4 + 128 * k]) = src.v[k];
     __syncthreads();
-    float* dst = pass == 0 ? grad_a : (pass == 1 ? grad_b : grad_w);
+    float* dst = pass == 0 ? grad_a : (pass == 1 ? grad_b : (pass == 2 ? grad_w : colsum_out));
     for (int c = threadIdx.x; c < width; c += blockDim.x) {
       float t = 0.f;
 #pragma unroll
@@ -515,12 +536,12 @@ int ln_forward(const float* x, const float* a, const float* b, float eps, long l
 
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
-                cudaStream_t st, float* dx_masked, DropSite site) {
+                cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out) {
   if (site.thresh == 0) dx_masked = nullptr;
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((dres ? 16.0 : 12.0) * width + 8), st);
-  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site)));
+  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out)));
   return check_launch();
 }
 
@@ -560,12 +581,12 @@ int head_forward(const float* x, const float* a, const float* b, float eps, cons
 int head_backward(const float* dscore, const float* score, const float* x, const float* a, const float* b,
                   const float* mean, const float* sd, float eps, const float* w, const float* wb, int has_norm,
                   int act, long long rows, int width, float* dx, float* grad_a, float* grad_b, float* grad_w,
-                  float* grad_wb, cudaStream_t st, float* dx_masked, DropSite site) {
+                  float* grad_wb, cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out) {
   if (site.thresh == 0) dx_masked = nullptr;
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 16), st);
-  ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site)));
+  ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out)));
   return check_launch();
 }
 

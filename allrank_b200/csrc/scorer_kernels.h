@@ -12,7 +12,8 @@ int ln_forward(const float* x, const float* a, const float* b, float eps, long l
 // dx = (dres ? dres : 0) + LayerNormBackward(dy); grad_a / grad_b are accumulated (atomicAdd)
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
-                cudaStream_t st, float* dx_masked = nullptr, DropSite site = DropSite{0u, 0u, 1.0f});
+                cudaStream_t st, float* dx_masked = nullptr, DropSite site = DropSite{0u, 0u, 1.0f},
+                float* colsum_out = nullptr);   // colsum_out[c] += column sums of the emitted (masked) gradient
 int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pitch, cudaStream_t st);
 int softmax_backward(float* dp, const float* prob, long long rows, int S, int pitch, cudaStream_t st);
 int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st);
@@ -23,6 +24,6 @@ int head_backward(const float* dscore, const float* score, const float* x, const
                   const float* mean, const float* sd, float eps, const float* w, const float* wb, int has_norm,
                   int act, long long rows, int width, float* dx, float* grad_a, float* grad_b, float* grad_w,
                   float* grad_wb, cudaStream_t st, float* dx_masked = nullptr,
-                  DropSite site = DropSite{0u, 0u, 1.0f});
+                  DropSite site = DropSite{0u, 0u, 1.0f}, float* colsum_out = nullptr);
 
 }  // namespace arb
