@@ -664,6 +664,160 @@ __global__ void __launch_bounds__(256) lambda_loss_kernel(const float* __restric
   if (threadIdx.x == 0) { val[b] = lossb; cnt[b] = npairs; }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// "Next-row" losses of allrank.models.losses that reuse the machinery above.
+// ------------------------------------------------------------------------------------------------
+// rankNet / rankNet_weightByGTDiff / rankNet_weightByGTDiff_pow     reference: losses/rankNet.py:9-79
+//   BCEWithLogits(target = 1, weight = w) over every ordered pair (i,j) of real items with t_i > t_j:
+//   term = w * softplus(-(s_i - s_j)),  loss = mean over all selected pairs of the batch.
+//   weight_mode 0: 1   1: |t_i - t_j|   2: |t_i^2 - t_j^2|
+__device__ __forceinline__ float softplus_neg(float x) {   // log(1 + exp(-x)), stable
+  return fmaxf(-x, 0.0f) + log1pf(expf(-fabsf(x)));
+}
+__global__ void __launch_bounds__(256) ranknet_kernel(const float* __restrict__ y_pred,
+                                                      const float* __restrict__ y_true, int B, int S, float pad,
+                                                      int weight_mode, float* __restrict__ val,
+                                                      float* __restrict__ cnt, float* __restrict__ grad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s = reinterpret_cast<float*>(smem_raw);
+  float* t = s + S;
+  float* red = t + S;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const float lab = y_true[size_t(b) * S + i];
+    t[i] = (lab == pad) ? -CUDART_INF_F : lab;
+    s[i] = y_pred[size_t(b) * S + i];
+  }
+  __syncthreads();
+  float lossb = 0.f, npairs = 0.f;
+  for (int r = threadIdx.x; r < S; r += blockDim.x) {
+    float g = 0.f;
+    const float tr = t[r], sr = s[r];
+    if (tr != -CUDART_INF_F) {
+      for (int c = 0; c < S; ++c) {
+        const float tc = t[c];
+        if (tc == -CUDART_INF_F || tc == tr) continue;
+        const float w = weight_mode == 0 ? 1.0f : (weight_mode == 1 ? fabsf(tr - tc) : fabsf(tr * tr - tc * tc));
+        if (tr > tc) {            // pair (r, c): x = s_r - s_c
+          const float x = sr - s[c];
+          lossb += w * softplus_neg(x);
+          npairs += 1.0f;
+          g -= w * (1.0f / (1.0f + expf(x)));      // d/ds_r = -w sigmoid(-x)
+        } else {                  // pair (c, r): x = s_c - s_r, d/ds_r = +w sigmoid(-x)
+          const float x = s[c] - sr;
+          g += w * (1.0f / (1.0f + expf(x)));
+        }
+      }
+    }
+    if (grad) grad[size_t(b) * S + r] = g;
+  }
+  lossb = block_sum(lossb, red);
+  npairs = block_sum(npairs, red);
+  if (threadIdx.x == 0) { val[b] = lossb; cnt[b] = npairs; }
+}
+
+// binary_listNet (losses/binary_listNet.py:8-33), pointwise_rmse (pointwise.py:6-32), bce (bce.py:8-32):
+// O(S) per slate, one warp per slate, mode selects the formula.
+//   mode 0 binary_listNet: -sum_i (y_i / max(sum y,1 if 0)) log(softmax(s)_i + eps)           mean over batch
+//   mode 1 pointwise_rmse: sqrt( sum_valid (y_i - L s_i)^2 / n_valid )                          mean over batch
+//   mode 2 bce           : sum_valid -(y log p + (1-y) log(1-p)) (logs clamped at -100),  / #slates with a valid item
+constexpr int PW_MAX_PER_LANE = 40;
+__global__ void __launch_bounds__(128) pointwise_warp_kernel(const float* __restrict__ y_pred,
+                                                             const float* __restrict__ y_true, int B, int S,
+                                                             float pad, int mode, float param, float eps, float inv_B,
+                                                             float* __restrict__ val, float* __restrict__ cnt,
+                                                             float* __restrict__ grad) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* yp = y_pred + size_t(b) * S;
+  const float* yt = y_true + size_t(b) * S;
+  float s[PW_MAX_PER_LANE], t[PW_MAX_PER_LANE];
+  bool ok[PW_MAX_PER_LANE];
+  float nvalid = 0.f, tsum = 0.f, ms = -CUDART_INF_F;
+#pragma unroll
+  for (int r = 0; r < PW_MAX_PER_LANE; ++r) {
+    const int i = lane + 32 * r;
+    ok[r] = false; s[r] = 0.f; t[r] = 0.f;
+    if (i < S) {
+      const float lab = yt[i];
+      ok[r] = lab != pad;
+      s[r] = yp[i];
+      t[r] = ok[r] ? lab : 0.f;
+    }
+    if (ok[r]) { nvalid += 1.f; tsum += t[r]; ms = fmaxf(ms, s[r]); }
+  }
+  nvalid = warp_sum(nvalid);
+  tsum = warp_sum(tsum);
+  float lossb = 0.f;
+  if (mode == 0) {
+    ms = warp_max(ms);
+    const float norm = (tsum == 0.0f) ? 1.0f : tsum;
+    float zs = 0.f;
+#pragma unroll
+    for (int r = 0; r < PW_MAX_PER_LANE; ++r) { s[r] = ok[r] ? expf(s[r] - ms) : 0.f; zs += s[r]; }
+    zs = warp_sum(zs);
+    float R = 0.f;
+#pragma unroll
+    for (int r = 0; r < PW_MAX_PER_LANE; ++r) {
+      const float p = s[r] / zs, q = t[r] / norm;
+      if (lane + 32 * r < S) lossb -= q * logf(p + eps);   // padded items: q = 0 and p = 0 -> 0 * log(eps) = -0
+      const float rr = q * p / (p + eps);
+      R += rr;
+      s[r] = p; t[r] = rr;
+    }
+    lossb = warp_sum(lossb);
+    R = warp_sum(R);
+    if (lane == 0) { val[b] = lossb * inv_B; cnt[b] = 1.f; }
+    if (grad) {
+#pragma unroll
+      for (int r = 0; r < PW_MAX_PER_LANE; ++r) {
+        const int i = lane + 32 * r;
+        if (i < S) grad[size_t(b) * S + i] = -(t[r] - s[r] * R) * inv_B;
+      }
+    }
+  } else if (mode == 1) {
+    float sq = 0.f;
+#pragma unroll
+    for (int r = 0; r < PW_MAX_PER_LANE; ++r) {
+      const float e = ok[r] ? t[r] - param * s[r] : 0.f;
+      t[r] = e;
+      sq += e * e;
+    }
+    sq = warp_sum(sq);
+    const float rmse = sqrtf(sq / nvalid);
+    if (lane == 0) { val[b] = rmse * inv_B; cnt[b] = 1.f; }
+    if (grad) {
+#pragma unroll
+      for (int r = 0; r < PW_MAX_PER_LANE; ++r) {
+        const int i = lane + 32 * r;
+        if (i < S) grad[size_t(b) * S + i] = ok[r] ? (-param * t[r] / (nvalid * rmse)) * inv_B : 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < PW_MAX_PER_LANE; ++r) {
+      if (ok[r]) {
+        const float p = s[r], y = t[r];
+        lossb -= y * fmaxf(logf(p), -100.0f) + (1.0f - y) * fmaxf(logf(1.0f - p), -100.0f);
+        t[r] = (p - y) / fmaxf(p * (1.0f - p), 1e-12f);       // BCELoss backward
+      } else {
+        t[r] = 0.f;
+      }
+    }
+    lossb = warp_sum(lossb);
+    if (lane == 0) { val[b] = lossb; cnt[b] = nvalid > 0.f ? 1.f : 0.f; }
+    if (grad) {
+#pragma unroll
+      for (int r = 0; r < PW_MAX_PER_LANE; ++r) {
+        const int i = lane + 32 * r;
+        if (i < S) grad[size_t(b) * S + i] = t[r];
+      }
+    }
+  }
+}
+
 }  // namespace arb
 
 // ================================================================================================
@@ -826,4 +980,40 @@ extern "C" int32_t arb_lambda_loss(const float* y_pred, const float* y_true, int
   arb_count_launch();
   ARB_LAUNCH_OK();
   return finalize(scratch, scratch + B, B, reduction == ARB_REDUCTION_MEAN ? 1 : 0, loss, grad, size_t(B) * S, st);
+}
+
+extern "C" int32_t arb_ranknet(const float* y_pred, const float* y_true, int32_t B, int32_t S, float pad_value,
+                               int32_t weight_mode, float* loss, float* grad, float* scratch, void* stream) {
+  ARB_CHECK_ARGS(y_pred && y_true && loss && scratch && B > 0 && S > 0, "arb_ranknet: null pointer or bad shape");
+  ARB_CHECK_ARGS(weight_mode >= 0 && weight_mode <= 2, "arb_ranknet: weight_mode must be 0, 1 or 2");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = size_t(S) * 8 + 256;
+  int rc = set_smem((const void*)ranknet_kernel, smem);
+  if (rc) { arb_set_error("arb_ranknet: slate too long"); return rc; }
+  {
+    ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
+    ranknet_kernel<<<B, 256, smem, st>>>(y_pred, y_true, B, S, pad_value, weight_mode, scratch, scratch + B, grad);
+  }
+  arb_count_launch();
+  ARB_LAUNCH_OK();
+  return finalize(scratch, scratch + B, B, 1, loss, grad, size_t(B) * S, st);   // mean over selected pairs
+}
+
+extern "C" int32_t arb_pointwise_loss(const float* y_pred, const float* y_true, int32_t B, int32_t S, float pad_value,
+                                      int32_t mode, float param, float eps, float* loss, float* grad, float* scratch,
+                                      void* stream) {
+  ARB_CHECK_ARGS(y_pred && y_true && loss && scratch && B > 0 && S > 0, "arb_pointwise_loss: null pointer or bad shape");
+  ARB_CHECK_ARGS(mode >= 0 && mode <= 2, "arb_pointwise_loss: mode must be 0 (binary_listNet), 1 (rmse) or 2 (bce)");
+  if (S > 32 * PW_MAX_PER_LANE) { arb_set_error("arb_pointwise_loss: slate_length above 1280 is not supported"); return ARB_E_UNSUPPORTED; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int wpb = 4;
+  {
+    ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
+    pointwise_warp_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(y_pred, y_true, B, S, pad_value, mode, param, eps,
+                                                                   1.0f / float(B), scratch, scratch + B, grad);
+  }
+  arb_count_launch();
+  ARB_LAUNCH_OK();
+  // binary_listNet / rmse: mean over the batch is already folded in; bce: divide by the number of non-empty slates
+  return finalize(scratch, scratch + B, B, mode == 2 ? 1 : 0, loss, grad, size_t(B) * S, st);
 }

@@ -11,7 +11,8 @@ from . import losses as _losses
 from . import metrics as _metrics
 from . import model as _model
 
-LOSS_NAMES = ("listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "neuralNDCG_transposed")
+LOSS_NAMES = ("listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "neuralNDCG_transposed", "rankNet",
+              "rankNet_weightByGTDiff", "rankNet_weightByGTDiff_pow", "binary_listNet", "pointwise_rmse", "bce")
 METRIC_NAMES = ("ndcg", "dcg", "mrr")
 
 

@@ -201,5 +201,54 @@ def neuralNDCG_transposed(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE,
                       n_samples, beta, log_scores, max_iter, tol, _gain_mode=1 if powered_relevancies else 2)
 
 
-__all__ = ["listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "neuralNDCG_transposed", "DEFAULT_EPS",
+def rankNet(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE, weight_by_diff=False, weight_by_diff_powed=False):
+    """RankNet -- rankNet.py:31-79 (BCE-with-logits over every ordered pair with t_i > t_j, mean over pairs)."""
+    mode = 1 if weight_by_diff else (2 if weight_by_diff_powed else 0)
+
+    def launch(s, t, B, S, loss, grad, scratch):
+        rc = _lib.lib().arb_ranknet(_lib.ptr(s), _lib.ptr(t), B, S, float(padded_value_indicator), mode, _lib.ptr(loss),
+                                    _lib.ptr(grad), _lib.ptr(scratch), _lib.stream_ptr(s.device))
+        _lib.check(rc, "arb_ranknet")
+
+    return _run(y_pred, y_true, launch)
+
+
+def rankNet_weightByGTDiff(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE):
+    """rankNet.py:9-17"""
+    return rankNet(y_pred, y_true, padded_value_indicator, weight_by_diff=True)
+
+
+def rankNet_weightByGTDiff_pow(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE):
+    """rankNet.py:20-28"""
+    return rankNet(y_pred, y_true, padded_value_indicator, weight_by_diff=False, weight_by_diff_powed=True)
+
+
+def _pointwise(y_pred, y_true, pad, mode, param, eps):
+    def launch(s, t, B, S, loss, grad, scratch):
+        rc = _lib.lib().arb_pointwise_loss(_lib.ptr(s), _lib.ptr(t), B, S, float(pad), mode, float(param), float(eps),
+                                           _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(scratch), _lib.stream_ptr(s.device))
+        _lib.check(rc, "arb_pointwise_loss")
+
+    return _run(y_pred, y_true, launch)
+
+
+def binary_listNet(y_pred, y_true, eps=DEFAULT_EPS, padded_value_indicator=PADDED_Y_VALUE):
+    """ListNet for binary labels (labels normalised by their sum) -- binary_listNet.py:8-33."""
+    return _pointwise(y_pred, y_true, padded_value_indicator, 0, 0.0, eps)
+
+
+def pointwise_rmse(y_pred, y_true, no_of_levels, padded_value_indicator=PADDED_Y_VALUE):
+    """Pointwise RMSE between labels and no_of_levels * scores -- pointwise.py:6-32."""
+    return _pointwise(y_pred, y_true, padded_value_indicator, 1, float(no_of_levels), 0.0)
+
+
+def bce(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE):
+    """Binary cross-entropy on probabilities, padded items ignored, summed per slate and divided by the number of
+    non-empty slates -- bce.py:8-32.  (With padded targets the reference itself only runs on torch < 2:
+    nn.BCELoss now rejects the -1 targets before they are masked; the intended semantics are implemented.)"""
+    return _pointwise(y_pred, y_true, padded_value_indicator, 2, 0.0, 0.0)
+
+
+__all__ = ["listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "neuralNDCG_transposed", "rankNet",
+           "rankNet_weightByGTDiff", "rankNet_weightByGTDiff_pow", "binary_listNet", "pointwise_rmse", "bce", "DEFAULT_EPS",
            "PADDED_Y_VALUE"]

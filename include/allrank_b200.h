@@ -105,6 +105,18 @@ int32_t arb_lambda_loss(const float* y_pred, const float* y_true, int32_t B, int
                         float pad_value, int32_t scheme, int32_t k, float sigma, float mu, int32_t reduction,
                         int32_t log_base, float* loss, float* grad, float* scratch, void* stream);
 
+/* --- SURVEY.md 8(f) rank-1 "next" losses, built on the same machinery ---
+ * rankNet / rankNet_weightByGTDiff / rankNet_weightByGTDiff_pow            .../losses/rankNet.py:9-79
+ * weight_mode 0: unweighted, 1: |t_i - t_j|, 2: |t_i^2 - t_j^2|; mean over all selected pairs of the batch. */
+int32_t arb_ranknet(const float* y_pred, const float* y_true, int32_t B, int32_t S, float pad_value,
+                    int32_t weight_mode, float* loss, float* grad, float* scratch, void* stream);
+/* mode 0: binary_listNet(eps)            .../losses/binary_listNet.py:8-33
+ * mode 1: pointwise_rmse(no_of_levels = param)   .../losses/pointwise.py:6-32
+ * mode 2: bce (y_pred are probabilities)          .../losses/bce.py:8-32 */
+int32_t arb_pointwise_loss(const float* y_pred, const float* y_true, int32_t B, int32_t S, float pad_value,
+                           int32_t mode, float param, float eps, float* loss, float* grad, float* scratch,
+                           void* stream);
+
 /* neuralNDCG(y_pred, y_true, pad, temperature, powered_relevancies, k, stochastic=False)
  *                            .../losses/neuralNDCG.py:10-70 + loss_utils.py:8-67 (NeuralSort, Sinkhorn)
  * max_iter / tol are the Sinkhorn parameters the reference hard-codes to 50 / 1e-6 (neuralNDCG.py:41-42).

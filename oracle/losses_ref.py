@@ -273,6 +273,60 @@ def neuralNDCG_transposed(y_pred, y_true, padded_value_indicator=PAD, temperatur
     return -1.0 * (val.sum() / (~dead).sum())
 
 
+# --------------------------------------------------------------------------- SURVEY 8(f) rank-1 "next" losses
+def rankNet(y_pred, y_true, padded_value_indicator=PAD, weight_by_diff=False, weight_by_diff_powed=False):
+    # rankNet.py:31-79: BCE-with-logits (target 1) over ordered pairs of real items with t_i > t_j, mean over pairs
+    is_pad = y_true == padded_value_indicator
+    t = y_true.masked_fill(is_pad, float("-inf"))
+    gap_t = t[:, :, None] - t[:, None, :]
+    gap_s = y_pred[:, :, None] - y_pred[:, None, :]
+    chosen = (gap_t > 0) & ~torch.isinf(gap_t)
+    weight = None
+    if weight_by_diff:
+        weight = torch.abs(gap_t)[chosen]
+    elif weight_by_diff_powed:
+        weight = torch.abs(t[:, :, None] ** 2 - t[:, None, :] ** 2)[chosen]
+    x = gap_s[chosen]
+    return torch.nn.functional.binary_cross_entropy_with_logits(x, torch.ones_like(x), weight=weight)
+
+
+def rankNet_weightByGTDiff(y_pred, y_true, padded_value_indicator=PAD):       # rankNet.py:9-17
+    return rankNet(y_pred, y_true, padded_value_indicator, weight_by_diff=True)
+
+
+def rankNet_weightByGTDiff_pow(y_pred, y_true, padded_value_indicator=PAD):   # rankNet.py:20-28
+    return rankNet(y_pred, y_true, padded_value_indicator, weight_by_diff_powed=True)
+
+
+def binary_listNet(y_pred, y_true, eps=EPS, padded_value_indicator=PAD):
+    # binary_listNet.py:17-33: labels normalised by their sum (1 if the sum is 0), softmax of the scores
+    is_pad = y_true == padded_value_indicator
+    s = y_pred.masked_fill(is_pad, float("-inf"))
+    t = y_true.masked_fill(is_pad, 0.0)
+    norm = t.sum(dim=-1, keepdim=True)
+    norm = torch.where(norm == 0.0, torch.ones_like(norm), norm)
+    return torch.mean(-torch.sum((t / norm) * torch.log(torch.softmax(s, dim=1) + eps), dim=1))
+
+
+def pointwise_rmse(y_pred, y_true, no_of_levels, padded_value_indicator=PAD):
+    # pointwise.py:16-32
+    is_pad = y_true == padded_value_indicator
+    err = (y_true.masked_fill(is_pad, 0.0) - no_of_levels * y_pred.masked_fill(is_pad, 0.0)) ** 2
+    return torch.mean(torch.sqrt(err.sum(dim=1) / (~is_pad).float().sum(dim=1)))
+
+
+def bce(y_pred, y_true, padded_value_indicator=PAD):
+    # bce.py:17-32 (intended semantics: padded items contribute 0; torch >= 2 rejects -1 targets in nn.BCELoss, so the
+    # per-element loss is restated with the same -100 log clamp)
+    is_pad = y_true == padded_value_indicator
+    t = y_true.masked_fill(is_pad, 0.0)
+    p = y_pred
+    per = -(t * torch.log(p).clamp(min=-100.0) + (1 - t) * torch.log(1 - p).clamp(min=-100.0))
+    per = per.masked_fill(is_pad, 0.0)
+    non_empty = ((~is_pad).sum(dim=-1) > 0).float().sum()
+    return per.sum() / non_empty
+
+
 LOSSES = {
     "listNet": listNet,
     "listMLE": listMLE,
@@ -280,6 +334,12 @@ LOSSES = {
     "lambdaLoss": lambdaLoss,
     "neuralNDCG": neuralNDCG,
     "neuralNDCG_transposed": neuralNDCG_transposed,
+    "rankNet": rankNet,
+    "rankNet_weightByGTDiff": rankNet_weightByGTDiff,
+    "rankNet_weightByGTDiff_pow": rankNet_weightByGTDiff_pow,
+    "binary_listNet": binary_listNet,
+    "pointwise_rmse": pointwise_rmse,
+    "bce": bce,
 }
 
 LN2 = math.log(2.0)

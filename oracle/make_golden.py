@@ -47,6 +47,11 @@ LOSS_CASES = [
     ("neuralNDCG_transposed", {"temperature": 0.5, "k": 5}),
     ("neuralNDCG_transposed", {"max_iter": 20, "tol": 1e-4}),
     ("neuralNDCG_transposed", {"powered_relevancies": False}),
+    ("rankNet", {}),
+    ("rankNet_weightByGTDiff", {}),
+    ("rankNet_weightByGTDiff_pow", {}),
+    ("binary_listNet", {}),
+    ("pointwise_rmse", {"no_of_levels": 4}),
 ]
 SHAPES = [(5, 7), (4, 33), (3, 120), (3, 240)]
 
@@ -94,6 +99,28 @@ def gen_losses():
     blob["keys"] = np.array(names)
     np.savez_compressed(os.path.join(OUT, "losses.npz"), **blob)
     print("losses:", len(names), "cases")
+
+
+def gen_bce():
+    """bce needs probabilities and (on torch >= 2) targets in [0,1]: unpadded slates, binary labels."""
+    blob = {}
+    keys = []
+    for (b, s) in SHAPES:
+        yp, y = case_inputs(b, s, seed=700 + s)
+        yt = (y > 0).float()
+        prob = torch.sigmoid(yp)
+        p = prob.clone().requires_grad_(True)
+        val = ref_losses.bce(p, yt)
+        val.backward()
+        key = f"s{s}"
+        blob[key + "_pred"] = prob.numpy()
+        blob[key + "_true"] = yt.numpy()
+        blob[key + "_loss32"] = val.detach().numpy()
+        blob[key + "_grad32"] = p.grad.numpy()
+        keys.append(key)
+    blob["keys"] = np.array(keys)
+    np.savez_compressed(os.path.join(OUT, "bce.npz"), **blob)
+    print("bce:", len(keys), "cases")
 
 
 def gen_listmle():
@@ -204,6 +231,7 @@ if __name__ == "__main__":
     torch.set_num_threads(4)
     gen_losses()
     gen_listmle()
+    gen_bce()
     gen_metrics()
     gen_scorer()
     gen_init()

@@ -232,3 +232,36 @@ def test_stochastic_neuralndcg_statistics(L):
     a = L.neuralNDCG(p.detach(), t, temperature=0.7, k=7)
     b = L.neuralNDCG_transposed(p.detach(), t, temperature=0.7, k=7)
     assert a.item() == b.item()
+
+
+def test_golden_bce_and_padding(L, golden):
+    g = golden("bce")
+    for key in g["keys"]:
+        key = str(key)
+        val, grad = run(L.bce, g[key + "_pred"], g[key + "_true"])
+        ref, gref = float(g[key + "_loss32"]), g[key + "_grad32"]
+        assert abs(val - ref) <= REL * abs(ref), key
+        assert np.abs(grad - gref).max() <= 1e-5 * np.abs(gref).max(), key
+        # appended padded items (label -1) are ignored -- the intended semantics of bce.py:24-25
+        b, s = g[key + "_pred"].shape
+        yp2 = np.concatenate([g[key + "_pred"], np.full((b, 3), 0.5, dtype=np.float32)], axis=1)
+        yt2 = np.concatenate([g[key + "_true"], np.full((b, 3), -1.0, dtype=np.float32)], axis=1)
+        val2, grad2 = run(L.bce, yp2, yt2)
+        assert val2 == pytest.approx(val, rel=1e-6)
+        assert (grad2[:, s:] == 0).all()
+
+
+@pytest.mark.parametrize("name,kw", [("rankNet", {}), ("rankNet_weightByGTDiff", {}), ("binary_listNet", {}),
+                                     ("pointwise_rmse", {"no_of_levels": 4})])
+def test_next_row_losses_against_oracle_at_bench_shape(L, name, kw):
+    from oracle import losses_ref
+    from allrank_b200.synth import make_slates, make_scores
+    B, S = 32, 240
+    _, y, _ = make_slates(B, S, n_features=1, seed=51)
+    yp = make_scores(B, S, seed=52)
+    p = yp.clone().double().requires_grad_(True)
+    ref = losses_ref.LOSSES[name](p, y.double(), **kw)
+    ref.backward()
+    val, grad = run(getattr(L, name), yp, y, **kw)
+    assert abs(val - ref.item()) <= 1e-5 * abs(ref.item())
+    assert np.abs(grad - p.grad.numpy()).max() <= 2e-5 * np.abs(p.grad.numpy()).max()

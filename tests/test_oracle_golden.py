@@ -89,3 +89,14 @@ def test_scorer_matches_reference(golden, name):
     for k, p in model.named_parameters():
         ref = g["g:" + k]
         assert np.abs(p.grad.numpy() - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-6), k
+
+
+def test_bce_matches_reference(golden):
+    g = golden("bce")
+    for key in g["keys"]:
+        key = str(key)
+        yp = torch.tensor(g[key + "_pred"]).requires_grad_(True)
+        val = losses_ref.bce(yp, torch.tensor(g[key + "_true"]))
+        val.backward()
+        assert np.allclose(val.item(), g[key + "_loss32"], rtol=2e-6), key
+        assert np.allclose(yp.grad.numpy(), g[key + "_grad32"], rtol=1e-5, atol=1e-7), key
