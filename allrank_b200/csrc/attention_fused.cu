@@ -249,7 +249,8 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   }
   dim3 grid((a.S + 127) / 128, a.h, a.B);
   {
-    ProfScope ps(ARB_PROF_GEMM, 4.0 * double(a.S) * a.S * a.dk * a.h * a.B, st);
+    ProfScope ps(ARB_PROF_GEMM, 4.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
+                 4.0 * double(a.B) * a.h * a.S * (4.0 * a.dk + 2.0));
     kern<<<grid, ATT_THREADS, L::total(), st>>>(tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
                                                a.scale * 1.4426950408889634f, a.drop);
   }

@@ -21,18 +21,18 @@ extern "C" int64_t arb_launch_count(void) { return g_launches.load(std::memory_o
 #include <mutex>
 #include <vector>
 namespace {
-struct ProfRec { int cls; double work; cudaEvent_t e0, e1; };
+struct ProfRec { int cls; double work; double bytes; cudaEvent_t e0, e1; };
 std::vector<ProfRec> g_recs;
 std::mutex g_prof_mu;
 bool g_prof_on = false;
 constexpr size_t kMaxRecs = 1 << 16;
 }  // namespace
 
-ProfScope::ProfScope(int cls, double work, cudaStream_t s) : idx(-1), st(s) {
+ProfScope::ProfScope(int cls, double work, cudaStream_t s, double bytes) : idx(-1), st(s) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (g_recs.size() >= kMaxRecs) return;
-  ProfRec r{cls, work, nullptr, nullptr};
+  ProfRec r{cls, work, bytes, nullptr, nullptr};
   if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
   cudaEventRecord(r.e0, st);
   g_recs.push_back(r);
@@ -51,17 +51,21 @@ extern "C" void arb_prof_enable(int32_t on) {
   g_prof_on = on != 0;
 }
 // Sums device time (ms), work units and launch count of one kernel class since arb_prof_enable(1).
+static double g_last_bytes[ARB_PROF_CLASSES] = {0};
+extern "C" double arb_prof_last_bytes(int32_t cls) { return (cls >= 0 && cls < ARB_PROF_CLASSES) ? g_last_bytes[cls] : 0.0; }
+
 extern "C" int32_t arb_prof_collect(int32_t cls, double* total_ms, double* total_work, int64_t* launches) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  double ms = 0, work = 0;
+  double ms = 0, work = 0, bytes = 0;
   long long n = 0;
   for (auto& r : g_recs) {
     if (r.cls != cls) continue;
     if (cudaEventSynchronize(r.e1) != cudaSuccess) { arb_set_error("arb_prof_collect: event sync failed"); return ARB_E_CUDA; }
     float t = 0;
     cudaEventElapsedTime(&t, r.e0, r.e1);
-    ms += t; work += r.work; ++n;
+    ms += t; work += r.work; bytes += r.bytes; ++n;
   }
+  if (cls >= 0 && cls < ARB_PROF_CLASSES) g_last_bytes[cls] = bytes;
   if (total_ms) *total_ms = ms;
   if (total_work) *total_work = work;
   if (launches) *launches = n;

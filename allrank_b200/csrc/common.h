@@ -18,7 +18,7 @@ int arb_finalize_mean_over_count(const float* val, const float* cnt, int B, floa
 enum { ARB_PROF_GEMM = 0, ARB_PROF_SCORER_SIMT = 1, ARB_PROF_LOSS = 2, ARB_PROF_METRICS = 3, ARB_PROF_OPTIM = 4,
        ARB_PROF_CLASSES = 5 };
 struct ProfScope {
-  ProfScope(int cls, double work, cudaStream_t st);
+  ProfScope(int cls, double work, cudaStream_t st, double bytes = 0.0);
   ~ProfScope();
   int idx;
   cudaStream_t st;

@@ -17,6 +17,7 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   return h;
 }
 __host__ __device__ __forceinline__ bool drop_keep(unsigned long long idx, uint32_t seed, uint32_t thresh) {
+  if (thresh == 0) return true;   // disabled site (may still carry a scale)
   uint32_t h = mix32(uint32_t(idx) ^ seed);
   h = mix32(h + uint32_t(idx >> 32) * 0x9e3779b1u + 0x7f4a7c15u);
   return h >= thresh;

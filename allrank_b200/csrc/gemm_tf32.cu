@@ -652,7 +652,10 @@ static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap&
     configured[slot] = true;
   }
   {
-    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * double(d.nb2) * double(d.nb3), st);
+    const double nb = double(d.nb2) * double(d.nb3);
+    const double has_x = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) ? 1.0 : 0.0;
+    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
+                 4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N));
     kern<<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tX, p);
   }
   arb_count_launch();

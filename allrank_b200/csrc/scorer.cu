@@ -35,7 +35,7 @@ struct ParamLayout {
   int64_t fc_w, fc_b;
   struct Layer { int64_t wqkv, bqkv, wo, bo, w1, b1, w2, b2, ln1_a, ln1_b, ln2_a, ln2_b; };
   Layer layer[64];
-  int64_t lnf_a, lnf_b, head_w, head_b, total;
+  int64_t lnf_a, lnf_b, head_w, head_b, pe, total;
 };
 
 static int make_param_layout(const arb_scorer_config& c, ParamLayout& L) {
@@ -74,6 +74,14 @@ static int make_param_layout(const arb_scorer_config& c, ParamLayout& L) {
   if (c.n_layers > 0) { L.lnf_a = o; o += d; L.lnf_b = o; o += d; } else { L.lnf_a = L.lnf_b = -1; }
   L.head_w = o; o += d;
   L.head_b = o; o += 1;
+  L.pe = -1;
+  if (c.pe_mode != 0) {
+    if (c.n_layers == 0 || c.pe_rows < 2 || c.pe_mode < 0 || c.pe_mode > 2) {
+      arb_set_error("scorer: positional encoding needs a transformer and a table of >= 2 rows");
+      return ARB_E_UNSUPPORTED;
+    }
+    if (c.pe_mode == 2) { o = align_up(o, 4); L.pe = o; o += int64_t(c.pe_rows) * d; }
+  }
   L.total = o;
   return ARB_OK;
 }
@@ -202,7 +210,8 @@ static void batch_all(GemmDesc& g, int h, int B) {
 
 #define ARB_TRY(expr) do { int rc__ = (expr); if (rc__ != ARB_OK) return rc__; } while (0)
 
-static int forward_impl(const arb_scorer_config& c, const float* P, const float* x, const uint8_t* mask, int B, int S,
+static int forward_impl(const arb_scorer_config& c, const float* P, const float* x, const uint8_t* mask,
+                        const int64_t* indices, const float* pe_table, int B, int S,
                         float* scores, float* ws, int64_t ws_floats, int training, uint64_t seed, cudaStream_t st) {
   ParamLayout L;
   ARB_TRY(make_param_layout(c, L));
@@ -222,6 +231,11 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   }
   float* xcur = ws + W.x0;
   ARB_TRY(linear_fwd(k, x, F, F, P + L.fc_w, P + L.fc_b, d, xcur, d, 0, nullptr, 0, make_drop_site(seed, 0, SITE_FC, p_fc)));
+  if (c.pe_mode != 0) {   // x = sqrt(d) x + pe[indices]   (transformer.py:51-52, positional.py)
+    const float* table = c.pe_mode == 2 ? P + L.pe : pe_table;
+    if (!indices || !table) { arb_set_error("scorer: positional encoding needs indices and a table"); return ARB_E_INVALID_ARG; }
+    ARB_TRY(pos_forward(xcur, reinterpret_cast<const long long*>(indices), mask, table, c.pe_rows, sqrtf(float(d)), k.R, d, st));
+  }
   for (int l = 0; l < c.n_layers; ++l) {
     const auto& pl = L.layer[l];
     const auto& wl = W.layer[l];
@@ -284,7 +298,7 @@ static void make_scratch_layout(const arb_scorer_config& c, int B, int S, Scratc
   int64_t o = 0;
   auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
   Z.dxa = take(R * d); Z.dxb = take(R * d); Z.dxn = take(R * d);
-  Z.dxm = (c.dropout > 0.0f || c.fc_dropout > 0.0f) ? take(R * d) : 0;
+  Z.dxm = (c.dropout > 0.0f || c.fc_dropout > 0.0f || c.pe_mode != 0) ? take(R * d) : 0;
   if (c.n_layers > 0) {
     Z.dqkv = take(R * 3 * d); Z.dctx = take(R * d);
     const bool fb = use_fused_bwd(c, S);
@@ -297,7 +311,8 @@ static void make_scratch_layout(const arb_scorer_config& c, int B, int S, Scratc
   Z.total = o;
 }
 
-static int backward_impl(const arb_scorer_config& c, const float* P, const float* x, const uint8_t* mask, int B, int S,
+static int backward_impl(const arb_scorer_config& c, const float* P, const float* x, const uint8_t* mask,
+                         const int64_t* indices, int B, int S,
                          const float* scores, const float* dscores, float* G, float* ws, int64_t ws_floats,
                          float* scratch, int64_t scratch_floats, uint64_t seed, cudaStream_t st) {
   ParamLayout L;
@@ -426,12 +441,19 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(linear_bwd_weight(k, dqkv, 3 * d, 3 * d, xn1, d, d, G + pl.wqkv));
     if (!use_fused_bwd(c, S)) ARB_TRY(colsum_accumulate(dqkv, k.R, 3 * d, 3 * d, G + pl.bqkv, st));
     ARB_TRY(linear_bwd_input(k, dqkv, 3 * d, 3 * d, P + pl.wqkv, d, dxn, d, 0, nullptr, 0));
-    const DropSite site_below = l > 0 ? make_drop_site(seed, l - 1, SITE_FFN_OUT, p_drop)
-                                      : make_drop_site(seed, 0, SITE_FC, p_fc);
+    DropSite site_below = l > 0 ? make_drop_site(seed, l - 1, SITE_FFN_OUT, p_drop)
+                                : make_drop_site(seed, 0, SITE_FC, p_fc);
+    // with a positional encoding the encoder input is sqrt(d) * fc_out + pe: the gradient that reaches the FC
+    // (through its dropout mask, if any) carries the extra sqrt(d)
+    if (l == 0 && c.pe_mode != 0) site_below.scale *= sqrtf(float(d));
     ARB_TRY(ln_backward(dxn, xin, P + pl.ln1_a, ws + wl.mean1, ws + wl.std1, c.ln_eps, dx_alt, k.R, d, dx,
                         G + pl.ln1_a, G + pl.ln1_b, st, dxm, site_below, l > 0 ? G + L.layer[l - 1].b2 : G + L.fc_b));
     // dx = d loss / d xin ; dy = the same through the dropout that produced xin's last summand
-    dy = site_below.thresh ? dxm : dx;
+    dy = (site_below.thresh || site_below.scale != 1.0f) ? dxm : dx;
+  }
+  if (c.pe_mode == 2) {   // learned table: d pe[idx] += d x0
+    if (!indices) { arb_set_error("scorer: positional encoding needs indices"); return ARB_E_INVALID_ARG; }
+    ARB_TRY(pos_backward(dx, reinterpret_cast<const long long*>(indices), mask, G + L.pe, c.pe_rows, k.R, d, st));
   }
   // ---- input FC backward (x is data: no input gradient)
   ARB_TRY(linear_bwd_weight(k, dy, d, d, x, F, F, G + L.fc_w));   // (fc_b gradient: fused into the kernel that emitted dy)
@@ -464,23 +486,25 @@ extern "C" int64_t arb_scorer_backward_scratch_floats(const arb_scorer_config* c
   return Z.total;
 }
 extern "C" int32_t arb_scorer_forward(const arb_scorer_config* cfg, const float* params, const float* x,
-                                      const uint8_t* mask, int32_t B, int32_t S, float* scores, float* workspace,
-                                      int64_t workspace_floats, int32_t training, uint64_t seed, void* stream) {
+                                      const uint8_t* mask, const int64_t* indices, const float* pe_table, int32_t B,
+                                      int32_t S, float* scores, float* workspace, int64_t workspace_floats,
+                                      int32_t training, uint64_t seed, void* stream) {
   if (!cfg || !params || !x || !mask || !scores || !workspace || B <= 0 || S <= 0) {
     arb_set_error("arb_scorer_forward: null pointer or bad shape");
     return ARB_E_INVALID_ARG;
   }
-  return forward_impl(*cfg, params, x, mask, B, S, scores, workspace, workspace_floats, training, seed,
+  return forward_impl(*cfg, params, x, mask, indices, pe_table, B, S, scores, workspace, workspace_floats, training, seed,
                       static_cast<cudaStream_t>(stream));
 }
 extern "C" int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, const float* x,
-                                       const uint8_t* mask, int32_t B, int32_t S, const float* scores,
+                                       const uint8_t* mask, const int64_t* indices, int32_t B, int32_t S,
+                                       const float* scores,
                                        const float* d_scores, float* grads, float* workspace, int64_t workspace_floats,
                                        float* scratch, int64_t scratch_floats, uint64_t seed, void* stream) {
   if (!cfg || !params || !x || !mask || !scores || !d_scores || !grads || !workspace || !scratch || B <= 0 || S <= 0) {
     arb_set_error("arb_scorer_backward: null pointer or bad shape");
     return ARB_E_INVALID_ARG;
   }
-  return backward_impl(*cfg, params, x, mask, B, S, scores, d_scores, grads, workspace, workspace_floats, scratch,
+  return backward_impl(*cfg, params, x, mask, indices, B, S, scores, d_scores, grads, workspace, workspace_floats, scratch,
                        scratch_floats, seed, static_cast<cudaStream_t>(stream));
 }

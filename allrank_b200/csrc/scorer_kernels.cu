@@ -506,6 +506,40 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------ positional encoding
+// x = sqrt(d) * x + pe[idx],  idx = padded ? last row : min(index, last row)     (allrank/models/positional.py:39-50,66-77)
+__global__ void __launch_bounds__(256) pos_fwd_kernel(float* __restrict__ x, const long long* __restrict__ indices,
+                                                      const uint8_t* __restrict__ mask, const float* __restrict__ pe,
+                                                      int pe_rows, float scale, long long rows, int width) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int pad = pe_rows - 1;
+  long long idx = mask[row] ? pad : indices[row];
+  if (idx > pad) idx = pad;
+  if (idx < 0) idx += pe_rows;                     // python-style negative index (only reachable for unmasked -1)
+  for (int c = lane * 4; c < width; c += 128) {
+    float4 v = *reinterpret_cast<float4*>(x + row * width + c);
+    const float4 p = *reinterpret_cast<const float4*>(pe + idx * width + c);
+    v.x = scale * v.x + p.x; v.y = scale * v.y + p.y; v.z = scale * v.z + p.z; v.w = scale * v.w + p.w;
+    *reinterpret_cast<float4*>(x + row * width + c) = v;
+  }
+}
+// learned table: dpe[idx] += dx   (the padding row receives no gradient: nn.Embedding(padding_idx=-1), positional.py:64)
+__global__ void __launch_bounds__(256) pos_bwd_kernel(const float* __restrict__ dx, const long long* __restrict__ indices,
+                                                      const uint8_t* __restrict__ mask, float* __restrict__ dpe,
+                                                      int pe_rows, long long rows, int width) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int pad = pe_rows - 1;
+  long long idx = mask[row] ? pad : indices[row];
+  if (idx > pad) idx = pad;
+  if (idx < 0) idx += pe_rows;
+  if (idx == pad) return;
+  for (int c = lane; c < width; c += 32) atomicAdd(dpe + idx * width + c, dx[row * width + c]);
+}
+
 // ------------------------------------------------------------------------------------------------ host launchers
 static int nv_for(int width) { return (width + 127) / 128; }
 
@@ -537,11 +571,26 @@ int ln_forward(const float* x, const float* a, const float* b, float eps, long l
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
                 cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out) {
-  if (site.thresh == 0) dx_masked = nullptr;
+  if (site.thresh == 0 && site.scale == 1.0f) dx_masked = nullptr;   // thresh 0 with a scale = pure rescale (positional encoding)
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((dres ? 16.0 : 12.0) * width + 8), st);
   ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out)));
+  return check_launch();
+}
+
+int pos_forward(float* x, const long long* indices, const uint8_t* mask, const float* pe, int pe_rows, float scale,
+                long long rows, int width, cudaStream_t st) {
+  if (width % 4) { arb_set_error("positional encoding: width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 12.0 * width, st);
+  pos_fwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(x, indices, mask, pe, pe_rows, scale, rows, width);
+  return check_launch();
+}
+
+int pos_backward(const float* dx, const long long* indices, const uint8_t* mask, float* dpe, int pe_rows, long long rows,
+                 int width, cudaStream_t st) {
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 8.0 * width, st);
+  pos_bwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(dx, indices, mask, dpe, pe_rows, rows, width);
   return check_launch();
 }
 

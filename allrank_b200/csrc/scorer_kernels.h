@@ -14,6 +14,10 @@ int ln_backward(const float* dy, const float* x, const float* a, const float* me
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
                 cudaStream_t st, float* dx_masked = nullptr, DropSite site = DropSite{0u, 0u, 1.0f},
                 float* colsum_out = nullptr);   // colsum_out[c] += column sums of the emitted (masked) gradient
+int pos_forward(float* x, const long long* indices, const uint8_t* mask, const float* pe, int pe_rows, float scale,
+                long long rows, int width, cudaStream_t st);
+int pos_backward(const float* dx, const long long* indices, const uint8_t* mask, float* dpe, int pe_rows, long long rows,
+                 int width, cudaStream_t st);
 int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pitch, cudaStream_t st);
 int softmax_backward(float* dp, const float* prob, long long rows, int S, int pitch, cudaStream_t st);
 int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st);

@@ -22,8 +22,12 @@ Dropout (transformer.dropout on attention probabilities, sublayer outputs and th
 on the input FC) is fused into the kernels with counter-based masks that backward regenerates; like nn.Dropout it is
 active in train() mode only.  The mask stream differs from torch's Philox stream: parity under dropout is statistical.
 
-Not built yet (raise NotImplementedError rather than fall back): positional encodings, multi-layer / activated /
-input-normed FC blocks, d_output > 1.
+Positional encodings (allrank/models/positional.py: fixed sinusoidal buffer or learned embedding indexed by `indices`,
+padding row for padded items) are applied by a SIMT kernel after the input FC; the learned table is part of the flat
+parameter buffer.
+
+Not built yet (raise NotImplementedError rather than fall back): multi-layer / activated / input-normed FC blocks,
+d_output > 1.
 """
 import copy
 import ctypes
@@ -39,15 +43,17 @@ _ACTS = {None: 0, "Tanh": 1, "Sigmoid": 2, "ReLU": 3}
 class ScorerConfig(ctypes.Structure):
     _fields_ = [("n_features", ctypes.c_int32), ("d_model", ctypes.c_int32), ("n_layers", ctypes.c_int32),
                 ("n_heads", ctypes.c_int32), ("d_ff", ctypes.c_int32), ("out_act", ctypes.c_int32),
-                ("ln_eps", ctypes.c_float), ("dropout", ctypes.c_float), ("fc_dropout", ctypes.c_float)]
+                ("ln_eps", ctypes.c_float), ("dropout", ctypes.c_float), ("fc_dropout", ctypes.c_float),
+                ("pe_mode", ctypes.c_int32), ("pe_rows", ctypes.c_int32)]
 
 
 c_p, c_i, c_i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
 _lib.register("arb_scorer_param_count", c_i64, [c_p])
 _lib.register("arb_scorer_workspace_floats", c_i64, [c_p, c_i, c_i, c_i])
 _lib.register("arb_scorer_backward_scratch_floats", c_i64, [c_p, c_i, c_i])
-_lib.register("arb_scorer_forward", c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i64, c_i, ctypes.c_uint64, c_p])
-_lib.register("arb_scorer_backward", c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64,
+_lib.register("arb_scorer_forward", c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_i64, c_i, ctypes.c_uint64,
+                                          c_p])
+_lib.register("arb_scorer_backward", c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64,
                                            ctypes.c_uint64, c_p])
 
 
@@ -88,11 +94,35 @@ class _EncoderLayer(nn.Module):
         self.sublayer = nn.ModuleList([_Sublayer(width), _Sublayer(width)])
 
 
+class _FixedPE(nn.Module):
+    """Sinusoidal table + one zero padding row, a buffer named `pe` (positional.py:15-37)."""
+
+    def __init__(self, width, max_len):
+        super().__init__()
+        import math
+        pe = torch.zeros(max_len, width)
+        position = torch.arange(0.0, max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0.0, width, 2) * -(math.log(10000.0) / width))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        pe = torch.cat((pe, torch.zeros([1, width])))
+        self.register_buffer("pe", pe)
+
+
+class _LearnedPE(nn.Module):
+    """nn.Embedding(max_len + 1, d, padding_idx=-1) named `pe` (positional.py:53-64)."""
+
+    def __init__(self, width, max_len):
+        super().__init__()
+        self.pe = nn.Embedding(max_len + 1, width, padding_idx=-1)
+
+
 class _Encoder(nn.Module):
-    def __init__(self, n_layers, width, attn_proto, w1, w2):
+    def __init__(self, n_layers, width, attn_proto, w1, w2, position=None):
         super().__init__()
         self.layers = nn.ModuleList([_EncoderLayer(width, attn_proto, w1, w2) for _ in range(n_layers)])
         self.norm = _Norm(width)
+        self.position = position
 
 
 class _InputFC(nn.Module):
@@ -116,29 +146,31 @@ def _clone_linear(proto):
 # ------------------------------------------------------------------------------------------------ autograd glue
 class _ScorerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, anchor, x, mask, model):
+    def forward(ctx, anchor, x, mask, model, indices):
         keep = ctx.needs_input_grad[0]
         seed = model._draw_seed()
-        scores, ws = model._launch_forward(x, mask, keep, seed)
+        scores, ws = model._launch_forward(x, mask, keep, seed, indices)
         if keep:
             ctx.model = model
             ctx.ws = ws
             ctx.seed = seed
+            ctx.indices = indices
             ctx.save_for_backward(x, mask, scores)
         return scores
 
     @staticmethod
     def backward(ctx, d_scores):
         x, mask, scores = ctx.saved_tensors
-        ctx.model._launch_backward(x, mask, scores, d_scores.contiguous().float(), ctx.ws, ctx.seed)
+        ctx.model._launch_backward(x, mask, scores, d_scores.contiguous().float(), ctx.ws, ctx.seed, ctx.indices)
         ctx.ws = None
-        return None, None, None, None
+        return None, None, None, None, None
 
 
 class LTRModel(nn.Module):
     """B200 scorer with the reference LTRModel's surface (model.py:47-92)."""
 
-    def __init__(self, n_features, d_model, n_layers, n_heads, d_ff, dropout, output_activation, fc_dropout=0.0):
+    def __init__(self, n_features, d_model, n_layers, n_heads, d_ff, dropout, output_activation, fc_dropout=0.0,
+                 positional=None):
         super().__init__()
         if output_activation not in _ACTS:
             raise NotImplementedError(f"output activation {output_activation!r}: supported {sorted(map(str, _ACTS))}")
@@ -155,7 +187,16 @@ class LTRModel(nn.Module):
             attn_proto = nn.Linear(d_model, d_model)
             w1 = nn.Linear(d_model, d_ff)
             w2 = nn.Linear(d_ff, d_model)
-            self.encoder = _Encoder(n_layers, d_model, attn_proto, w1, w2)
+            position = None
+            if positional is not None:                      # positional.py:80-94
+                strategy, max_len = positional
+                if strategy == "fixed":
+                    position = _FixedPE(d_model, max_len)
+                elif strategy == "learned":
+                    position = _LearnedPE(d_model, max_len)
+                else:
+                    raise ValueError("Invalid positional encoding type: {}".format(strategy))
+            self.encoder = _Encoder(n_layers, d_model, attn_proto, w1, w2, position)
         else:
             self.encoder = None
         self.output_layer = _Head(nn.Linear(d_model, 1))
@@ -164,7 +205,11 @@ class LTRModel(nn.Module):
                 nn.init.xavier_uniform_(p)
         self._Fp = (self.n_features + 3) // 4 * 4
         self._cfg = ScorerConfig(self._Fp, self.d_model, self.n_layers, max(self.n_heads, 1), max(self.d_ff, 4),
-                                 _ACTS[output_activation], 1e-6, self.dropout_p, self.fc_dropout_p)
+                                 _ACTS[output_activation], 1e-6, self.dropout_p, self.fc_dropout_p, 0, 0)
+        pos = self.encoder.position if self.encoder is not None else None
+        if pos is not None:
+            self._cfg.pe_mode = 1 if isinstance(pos, _FixedPE) else 2
+            self._cfg.pe_rows = (pos.pe if isinstance(pos, _FixedPE) else pos.pe.weight).shape[0]
         self._flat = None
         self._flat_grad = None
         self._views = None
@@ -187,6 +232,8 @@ class LTRModel(nn.Module):
                         (lyr.sublayer[1].norm.a_2, None), (lyr.sublayer[1].norm.b_2, None)]
             out += [(self.encoder.norm.a_2, None), (self.encoder.norm.b_2, None)]
         out += [(self.output_layer.w_1.weight, None), (self.output_layer.w_1.bias, None)]
+        if self.encoder is not None and isinstance(self.encoder.position, _LearnedPE):
+            out += [(self.encoder.position.pe.weight, "align4")]
         return out
 
     def _view_of(self, flat, offset, p, flat_shape):
@@ -206,6 +253,9 @@ class LTRModel(nn.Module):
         grad = torch.zeros(total, dtype=torch.float32, device=device)
         views, off = [], 0
         for p, shape in self._ordered():
+            if shape == "align4":          # the learned positional table starts on a 16-byte boundary
+                off = (off + 3) // 4 * 4
+                shape = None
             v, n = self._view_of(flat, off, p, shape)
             gv, _ = self._view_of(grad, off, p, shape)
             with torch.no_grad():
@@ -239,6 +289,17 @@ class LTRModel(nn.Module):
         return self._flat_grad
 
     # ---- launches -----------------------------------------------------------------------------------
+    def _prep_indices(self, indices, device):
+        if self._cfg.pe_mode == 0:
+            return None
+        if indices is None:
+            raise ValueError("this model has a positional encoding: `indices` is required")
+        return indices.detach().to(device=device, dtype=torch.int64).contiguous()
+
+    def _pe_table(self):
+        pos = self.encoder.position if self.encoder is not None else None
+        return pos.pe.float().contiguous() if isinstance(pos, _FixedPE) else None
+
     def _prep_inputs(self, x, mask):
         _lib.require_cuda(x, mask)
         if x.dim() != 3 or x.shape[-1] != self.n_features:
@@ -256,7 +317,7 @@ class LTRModel(nn.Module):
             return int(torch.randint(0, 2 ** 62, (1,)).item())
         return 0
 
-    def _launch_forward(self, x, mask, keep_for_backward, seed=0):
+    def _launch_forward(self, x, mask, keep_for_backward, seed=0, indices=None):
         training = keep_for_backward
         B, S = x.shape[0], x.shape[1]
         dev = x.device
@@ -269,13 +330,15 @@ class LTRModel(nn.Module):
             # whether activations are kept for backward
             self._cfg.dropout = self.dropout_p if self.training else 0.0
             self._cfg.fc_dropout = self.fc_dropout_p if self.training else 0.0
-            rc = _lib.lib().arb_scorer_forward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask), B, S,
+            table = self._pe_table()
+            rc = _lib.lib().arb_scorer_forward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask),
+                                               _lib.ptr(indices), _lib.ptr(table), B, S,
                                                _lib.ptr(scores), _lib.ptr(ws), n_ws, 1 if training else 0,
                                                ctypes.c_uint64(seed), _lib.stream_ptr(dev))
         _lib.check(rc, "arb_scorer_forward")
         return scores, (ws if training else None)
 
-    def _launch_backward(self, x, mask, scores, d_scores, ws, seed=0):
+    def _launch_backward(self, x, mask, scores, d_scores, ws, seed=0, indices=None):
         B, S = x.shape[0], x.shape[1]
         dev = x.device
         cfg = ctypes.byref(self._cfg)
@@ -287,7 +350,8 @@ class LTRModel(nn.Module):
         n_sc = int(_lib.lib().arb_scorer_backward_scratch_floats(cfg, B, S))
         scratch = torch.empty(n_sc, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            rc = _lib.lib().arb_scorer_backward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask), B, S,
+            rc = _lib.lib().arb_scorer_backward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask),
+                                                _lib.ptr(indices), B, S,
                                                 _lib.ptr(scores), _lib.ptr(d_scores), _lib.ptr(self._flat_grad),
                                                 _lib.ptr(ws), ws.numel(), _lib.ptr(scratch), n_sc,
                                                 ctypes.c_uint64(seed), _lib.stream_ptr(dev))
@@ -303,11 +367,12 @@ class LTRModel(nn.Module):
 
     def forward(self, x, mask, indices=None):
         xin, m = self._prep_inputs(x, mask)
+        idx = self._prep_indices(indices, xin.device)
         self._ensure_packed(xin.device)
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
-            return _ScorerFn.apply(self._anchor, xin, m, self)
-        scores, _ = self._launch_forward(xin, m, False, self._draw_seed())
+            return _ScorerFn.apply(self._anchor, xin, m, self, idx)
+        scores, _ = self._launch_forward(xin, m, False, self._draw_seed(), idx)
         return scores
 
     def score(self, x, mask, indices=None):
@@ -337,11 +402,11 @@ def make_model(fc_model, transformer, post_model, n_features):
         raise NotImplementedError("d_output > 1 (ordinal loss) is a SURVEY 8(f) next item")
     d_model = int(sizes[0])
     if transformer:
-        if _get(transformer, "positional_encoding", None) is not None:
-            raise NotImplementedError("positional encodings are a SURVEY 8(f) next item")
+        pe_cfg = _get(transformer, "positional_encoding", None)
+        positional = None if pe_cfg is None else (_get(pe_cfg, "strategy"), int(_get(pe_cfg, "max_indices")))
         n_layers, heads, d_ff = int(_get(transformer, "N")), int(_get(transformer, "h")), int(_get(transformer, "d_ff"))
         dropout = float(_get(transformer, "dropout", 0.0) or 0.0)
     else:
-        n_layers, heads, d_ff, dropout = 0, 1, 4, 0.0
+        n_layers, heads, d_ff, dropout, positional = 0, 1, 4, 0.0, None
     return LTRModel(n_features, d_model, n_layers, heads, d_ff, dropout, _get(post_model, "output_activation", None),
-                    fc_dropout=float(_get(fc_model, "dropout", 0.0) or 0.0))
+                    fc_dropout=float(_get(fc_model, "dropout", 0.0) or 0.0), positional=positional)

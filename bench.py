@@ -311,6 +311,10 @@ def run_b200(args, w):
             lib.arb_prof_collect(cls, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n))
             prof[nm] = {"ms_per_step": ms.value / psteps, "work_per_step": work.value / psteps,
                         "launches_per_step": n.value / psteps}
+            if cls == 0:
+                lib.arb_prof_last_bytes.restype = ctypes.c_double
+                lib.arb_prof_last_bytes.argtypes = [ctypes.c_int32]
+                prof[nm]["algorithmic_bytes_per_step"] = lib.arb_prof_last_bytes(0) / psteps
         prof["step_ms_profiled"] = pe0.elapsed_time(pe1) / psteps
         lib.arb_prof_enable(0)
     if world > 1:
@@ -349,6 +353,15 @@ def run_b200(args, w):
             "share_of_step": gemm["ms_per_step"] / prof["step_ms_profiled"] if prof.get("step_ms_profiled") else None,
             "model_flops_per_step": flops_per_slate_step(w) * B,
             "whole_step_tflops": flops_per_slate_step(w) * B * world / (ms_total / args.steps * 1e-3) / 1e12,
+            # the same kernels against the HBM roofline: with K = 128..512 the linears move 4(MK+NK+MN) bytes for
+            # 2MNK flops (arithmetic intensity 32..100 flop/B, below the ~110 flop/B tf32 ridge), so HBM is the
+            # binding roof; ncu (profiles/) shows 51-64 % of DRAM peak on the individual launches
+            "hbm_view": {"achieved_gbs": gemm.get("algorithmic_bytes_per_step", 0.0) / (gemm["ms_per_step"] * 1e-3) / 1e9
+                         if gemm["ms_per_step"] > 0 else 0.0,
+                         "peak_gbs": peaks["hbm_gbs"],
+                         "frac": (gemm.get("algorithmic_bytes_per_step", 0.0) / (gemm["ms_per_step"] * 1e-3) / 1e9) /
+                                 peaks["hbm_gbs"] if gemm["ms_per_step"] > 0 else None,
+                         "algorithmic_bytes_per_step": gemm.get("algorithmic_bytes_per_step", 0.0)},
         },
         "kernel_classes": prof,
         "final_loss": final_loss,

@@ -142,7 +142,8 @@ int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int32_t B, int
  *
  * Parameters live in ONE flat fp32 buffer (the host layer makes the nn.Parameters views of it), laid out as
  *   fc_w[d,F] fc_b[d] | per layer: wq wk wv [3d,d] bq bk bv [3d] wo[d,d] bo[d] w1[dff,d] b1[dff] w2[d,dff] b2[d]
- *   ln1_a ln1_b ln2_a ln2_b [d each] | lnf_a lnf_b [d] head_w[d] head_b[1]
+ *   ln1_a ln1_b ln2_a ln2_b [d each] | lnf_a lnf_b [d] head_w[d] head_b[1] (pad to 4) | pe[pe_rows,d] if pe_mode == 2
+ * (a fixed sinusoidal table, pe_mode == 1, is a buffer, not a parameter: it is passed separately as `pe_table`)
  * arb_scorer_param_count() gives the total; gradients use the same layout and are ACCUMULATED into `grads`.
  */
 #define ARB_ACT_NONE 0
@@ -161,20 +162,25 @@ typedef struct arb_scorer_config {
   float dropout;        /* transformer.dropout: on attention probabilities, both sublayer outputs and the FFN
                            hidden layer (transformer.py:105,155,227); applied only when training != 0          */
   float fc_dropout;     /* fc_model.dropout on the input FC output (model.py:43)                          */
+  int32_t pe_mode;      /* positional encoding (allrank/models/positional.py): 0 none, 1 fixed table, 2 learned     */
+  int32_t pe_rows;      /* rows of the table = max_indices + 1; the last row is the padding row              */
 } arb_scorer_config;
 
 int64_t arb_scorer_param_count(const arb_scorer_config* cfg);
 /* floats of activation workspace for a [B,S] batch; `training` != 0 keeps what backward needs */
 int64_t arb_scorer_workspace_floats(const arb_scorer_config* cfg, int32_t B, int32_t S, int32_t training);
-/* x [B,S,F] fp32, mask [B,S] uint8 (1 = padded, train_utils.py:19) -> scores [B,S] fp32 */
+/* x [B,S,F] fp32, mask [B,S] uint8 (1 = padded, train_utils.py:19) -> scores [B,S] fp32.
+ * indices [B,S] int64 (original item ranks, -1 = padded; positional.py:45-50) and pe_table are only read when
+ * cfg->pe_mode != 0 (pe_table: the fixed table for mode 1; ignored for mode 2, whose table lives in params). */
 int32_t arb_scorer_forward(const arb_scorer_config* cfg, const float* params, const float* x, const uint8_t* mask,
+                           const int64_t* indices, const float* pe_table,
                            int32_t B, int32_t S, float* scores, float* workspace, int64_t workspace_floats,
                            int32_t training, uint64_t seed, void* stream);
 /* d_scores [B,S] -> grads += d loss / d params.  `workspace` is the one the training forward filled;
  * `scratch`: arb_scorer_backward_scratch_floats(cfg,B,S) floats. */
 int64_t arb_scorer_backward_scratch_floats(const arb_scorer_config* cfg, int32_t B, int32_t S);
 int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, const float* x, const uint8_t* mask,
-                            int32_t B, int32_t S, const float* scores, const float* d_scores, float* grads,
+                            const int64_t* indices, int32_t B, int32_t S, const float* scores, const float* d_scores, float* grads,
                             float* workspace, int64_t workspace_floats, float* scratch, int64_t scratch_floats,
                             uint64_t seed, void* stream);
 
@@ -209,6 +215,8 @@ int32_t arb_adam_step(float* params, const float* grads, float* exp_avg, float* 
  * (0 = tcgen05 GEMM [work = flops], 1 = scorer SIMT, 2 = losses, 3 = metrics, 4 = optimiser [work = bytes]). */
 void arb_prof_enable(int32_t on);
 int32_t arb_prof_collect(int32_t cls, double* total_ms, double* total_work, int64_t* launches);
+/* algorithmic HBM bytes (operands + outputs, each counted once) summed by the last arb_prof_collect(cls, ...) */
+double arb_prof_last_bytes(int32_t cls);
 
 #ifdef __cplusplus
 }

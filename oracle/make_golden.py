@@ -22,7 +22,7 @@ import torch  # noqa: E402
 from allrank.models import losses as ref_losses  # noqa: E402
 from allrank.models import metrics as ref_metrics  # noqa: E402
 from allrank.models.model import make_model as ref_make_model  # noqa: E402
-from allrank.config import TransformerConfig  # noqa: E402
+from allrank.config import TransformerConfig, PositionalEncoding  # noqa: E402
 from allrank_b200.synth import make_slates, make_scores  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -215,6 +215,35 @@ def gen_scorer():
         print("scorer", name, "scores", tuple(scores.shape))
 
 
+def gen_scorer_pe():
+    """Scorer with positional encodings (allrank/models/positional.py): fixed and learned, max_indices < slate length
+    so that the index clipping to the padding row is exercised."""
+    for strategy in ("fixed", "learned"):
+        torch.manual_seed(9)
+        F, d, N, h, dff, B, S, max_idx = 20, 32, 2, 2, 64, 3, 20, 15
+        model = ref_make_model(
+            fc_model={"sizes": [d], "input_norm": False, "activation": None, "dropout": 0.0},
+            transformer=TransformerConfig(N=N, d_ff=dff, h=h, dropout=0.0,
+                                          positional_encoding=PositionalEncoding(strategy=strategy, max_indices=max_idx)),
+            post_model={"d_output": 1, "output_activation": None}, n_features=F)
+        model.eval()
+        x, y, idx = make_slates(B, S, n_features=F, seed=33, mean_len=0.7 * S, std_len=0.2 * S)
+        g = torch.Generator().manual_seed(12)
+        idx = torch.where(idx >= 0, torch.stack([torch.randperm(S, generator=g) for _ in range(B)]), idx)
+        mask = y == -1
+        scores = model(x, mask, idx)
+        w = torch.randn(scores.shape, generator=g)
+        (scores * w).sum().backward()
+        blob = {"x": x.numpy(), "y": y.numpy(), "idx": idx.numpy(), "scores": scores.detach().numpy(), "w": w.numpy(),
+                "meta": np.array([F, d, N, h, dff, B, S, max_idx])}
+        for k_, v in model.state_dict().items():
+            blob["p:" + k_] = v.numpy()
+        for k_, p in model.named_parameters():
+            blob["g:" + k_] = p.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, f"scorer_pe_{strategy}.npz"), **blob)
+        print("scorer pe", strategy, [k_ for k_ in model.state_dict() if "position" in k_])
+
+
 def gen_init():
     """Seeded initialisation of the reference's make_model (model.py:131-151): pins construction order."""
     torch.manual_seed(123)
@@ -234,4 +263,5 @@ if __name__ == "__main__":
     gen_bce()
     gen_metrics()
     gen_scorer()
+    gen_scorer_pe()
     gen_init()

@@ -99,15 +99,44 @@ class Block(nn.Module):
         return self.sublayer[1](x, self.feed_forward)
 
 
-class Stack(nn.Module):
-    """transformer.py:28-56 (positional encoding is None in every shipped config; not restated)."""
+class Position(nn.Module):
+    """allrank/models/positional.py:15-77: x = sqrt(d) x + table[idx]; padded items and indices beyond the table use
+    the last (padding) row.  strategy "fixed": sinusoidal buffer `pe`; "learned": nn.Embedding `pe`."""
 
-    def __init__(self, n_layers, width, heads, hidden, dropout):
+    def __init__(self, width, max_len, strategy):
+        super().__init__()
+        self.strategy = strategy
+        if strategy == "fixed":
+            table = torch.zeros(max_len, width)
+            pos = torch.arange(0.0, max_len).unsqueeze(1)
+            freq = torch.exp(torch.arange(0.0, width, 2) * -(math.log(10000.0) / width))
+            table[:, 0::2] = torch.sin(pos * freq)
+            table[:, 1::2] = torch.cos(pos * freq)
+            self.register_buffer("pe", torch.cat((table, torch.zeros([1, width]))))
+        else:
+            self.pe = nn.Embedding(max_len + 1, width, padding_idx=-1)
+
+    def forward(self, x, mask, indices):
+        table = self.pe if self.strategy == "fixed" else self.pe.weight
+        last = table.shape[0] - 1
+        idx = indices.masked_fill(mask, last)
+        idx = torch.where(idx > last, torch.full_like(idx, last), idx)
+        looked_up = table[idx] if self.strategy == "fixed" else self.pe(idx)
+        return math.sqrt(table.shape[1]) * x + looked_up
+
+
+class Stack(nn.Module):
+    """transformer.py:28-56"""
+
+    def __init__(self, n_layers, width, heads, hidden, dropout, position=None):
         super().__init__()
         self.layers = nn.ModuleList([Block(width, heads, hidden, dropout) for _ in range(n_layers)])
         self.norm = RowNorm(width)
+        self.position = position
 
     def forward(self, x, mask, indices):
+        if self.position is not None:
+            x = self.position(x, mask, indices)
         for blk in self.layers:
             x = blk(x, mask)
         return self.norm(x)
@@ -169,13 +198,14 @@ class RefLTRModel(nn.Module):
 
 
 def make_ref_model(n_features, fc_sizes, n_layers, heads, d_ff, dropout=0.0, d_output=1,
-                   output_activation=None, fc_activation=None, seed=None):
+                   output_activation=None, fc_activation=None, seed=None, positional=None):
     """model.py:131-151: build + xavier_uniform_ on every parameter with dim > 1."""
     if seed is not None:
         torch.manual_seed(seed)
     fc = InputFC(fc_sizes, n_features, activation=fc_activation)
     width = fc.output_size
-    enc = Stack(n_layers, width, heads, d_ff, dropout)
+    position = Position(width, positional[1], positional[0]) if positional else None
+    enc = Stack(n_layers, width, heads, d_ff, dropout, position)
     model = RefLTRModel(fc, enc, Head(width, d_output, output_activation))
     for p in model.parameters():
         if p.dim() > 1:

@@ -252,3 +252,34 @@ def test_fused_attention_matches_unfused_path(shape):
         print(shape, "mode", mode, "vs unfused: score diff", ds, "grad rel diff", dg)
         assert ds <= 2e-3 * max(1.0, out[0][0].abs().max().item())
         assert dg <= 1.5e-2, (mode, dg)
+
+
+@pytest.mark.parametrize("strategy", ["fixed", "learned"])
+def test_positional_encodings_match_reference(golden, strategy):
+    """allrank/models/positional.py through the CUDA scorer: state_dict keys, scores, every gradient (incl. the learned
+    table) against the reference's golden vectors; indices beyond max_indices and padded items use the padding row."""
+    from allrank_b200.model import make_model
+    g = golden("scorer_pe_" + strategy)
+    F, d, N, h, dff, B, S, max_idx = [int(v) for v in g["meta"]]
+    model = make_model(fc_model={"sizes": [d], "input_norm": False, "activation": None, "dropout": 0.0},
+                       transformer={"N": N, "d_ff": dff, "h": h, "dropout": 0.0,
+                                    "positional_encoding": {"strategy": strategy, "max_indices": max_idx}},
+                       post_model={"d_output": 1, "output_activation": None}, n_features=F)
+    sd = {k[2:]: torch.tensor(g[k]) for k in g.files if k.startswith("p:")}
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    x, y, idx = torch.tensor(g["x"]).cuda(), torch.tensor(g["y"]).cuda(), torch.tensor(g["idx"]).cuda()
+    scores = model(x, y == -1, idx)
+    err = np.abs(scores.detach().cpu().numpy() - g["scores"]).max()
+    assert err <= SCORE_TOL * max(1.0, np.abs(g["scores"]).max()), err
+    (scores * torch.tensor(g["w"]).cuda()).sum().backward()
+    floor = 1e-2 * max(np.abs(g["g:" + k]).max() for k, _ in model.named_parameters())
+    bad = []
+    for k, p in model.named_parameters():
+        fro, mx = grad_errors(p.grad.cpu().numpy(), g["g:" + k], floor)
+        if fro > GRAD_TOL or mx > GRAD_TOL_MAX:
+            bad.append((k, fro, mx))
+    assert not bad, bad
+    with torch.no_grad():
+        assert torch.equal(model.eval()(x, y == -1, idx), scores.detach())

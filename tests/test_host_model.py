@@ -75,5 +75,28 @@ def test_param_count_matches_reference_models():
     import allrank_b200.model  # noqa: F401  (registers signatures)
     # parameter counts the survey measured for the two BASELINE shapes
     for (F, d, N, h, dff, expect) in [(136, 128, 2, 4, 512, 414465), (136, 256, 4, 8, 1024, 3194881)]:
-        cfg = ScorerConfig(F, d, N, h, dff, 0, 1e-6, 0.0, 0.0)
+        cfg = ScorerConfig(F, d, N, h, dff, 0, 1e-6, 0.0, 0.0, 0, 0)
         assert _lib.lib().arb_scorer_param_count(ctypes.byref(cfg)) == expect
+
+
+@pytest.mark.parametrize("strategy", ["fixed", "learned"])
+def test_positional_encoding_state_dict_surface(golden, strategy):
+    from allrank_b200.model import make_model
+    g = golden("scorer_pe_" + strategy)
+    F, d, N, h, dff, B, S, max_idx = [int(v) for v in g["meta"]]
+    model = make_model(fc_model={"sizes": [d], "input_norm": False, "activation": None, "dropout": 0.0},
+                       transformer={"N": N, "d_ff": dff, "h": h, "dropout": 0.0,
+                                    "positional_encoding": {"strategy": strategy, "max_indices": max_idx}},
+                       post_model={"d_output": 1, "output_activation": None}, n_features=F)
+    ref = {k[2:]: g[k] for k in g.files if k.startswith("p:")}
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == ref[k].shape, k
+    if strategy == "fixed":
+        assert np.array_equal(sd["encoder.position.pe"].numpy(), ref["encoder.position.pe"])
+    with pytest.raises(ValueError):
+        make_model(fc_model={"sizes": [d], "input_norm": False, "activation": None, "dropout": 0.0},
+                   transformer={"N": 1, "d_ff": 8, "h": 1, "dropout": 0.0,
+                                "positional_encoding": {"strategy": "rotary", "max_indices": 4}},
+                   post_model={"d_output": 1, "output_activation": None}, n_features=F)

@@ -100,3 +100,20 @@ def test_bce_matches_reference(golden):
         val.backward()
         assert np.allclose(val.item(), g[key + "_loss32"], rtol=2e-6), key
         assert np.allclose(yp.grad.numpy(), g[key + "_grad32"], rtol=1e-5, atol=1e-7), key
+
+
+@pytest.mark.parametrize("strategy", ["fixed", "learned"])
+def test_scorer_with_positional_encoding_matches_reference(golden, strategy):
+    g = golden("scorer_pe_" + strategy)
+    F, d, N, h, dff, B, S, max_idx = [int(v) for v in g["meta"]]
+    model = scorer_ref.make_ref_model(F, [d], N, h, dff, positional=(strategy, max_idx)).eval()
+    sd = {k[2:]: torch.tensor(g[k]) for k in g.files if k.startswith("p:")}
+    assert set(sd) == set(model.state_dict())
+    model.load_state_dict(sd)
+    x, y, idx = torch.tensor(g["x"]), torch.tensor(g["y"]), torch.tensor(g["idx"])
+    scores = model(x, y == -1, idx)
+    assert np.allclose(scores.detach().numpy(), g["scores"], rtol=1e-5, atol=2e-6)
+    (scores * torch.tensor(g["w"])).sum().backward()
+    for k, p in model.named_parameters():
+        ref = g["g:" + k]
+        assert np.abs(p.grad.numpy() - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-6), k
