@@ -228,6 +228,195 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ two-pass variant
+// Same result, organised so that TWO CTAs fit on an SM (the kernel above needs S(<=256)+O columns = a 512-column TMEM
+// allocation, i.e. one CTA per SM, and is latency-bound at 7 % tensor pipe).  Here the score tile is produced in
+// 128-key chunks into a 128-column TMEM window, twice: pass A only takes the row maximum, pass B recomputes the chunk
+// (K = dk, a handful of MMAs), exponentiates against the final maximum, writes P in place and accumulates O += P V.
+// TMEM: S chunk [0,128) + O [128,128+DK) -> 256 columns; shared memory 96 KB -> two co-resident CTAs overlap each
+// other's load / MMA / softmax phases.  Head width <= 32.
+template <int DK, bool DROP>
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                   const __grid_constant__ CUtensorMap tmK,
+                                                                   const __grid_constant__ CUtensorMap tmV,
+                                                                   const __grid_constant__ CUtensorMap tmO,
+                                                                   const uint8_t* __restrict__ mask,
+                                                                   float* __restrict__ stat_max,
+                                                                   float* __restrict__ stat_sum, int S, int n_heads,
+                                                                   float scale_log2e, DropSite drop) {
+  static_assert(DK <= 32, "two-pass forward kernel: head width <= 32");
+  using L = AttFwdSmem<DK>;
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + L::Q_BYTES;
+  uint8_t* v_s = k_s + L::K_BYTES;
+  uint8_t* o_s = v_s + L::V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_s + L::O_BYTES);
+  uint64_t* load_bar = bars;
+  uint64_t* s_bar = bars + 1;       // a score chunk is complete            (one phase per step)
+  uint64_t* t_bar = bars + 2;       // the 128 softmax threads are done with the chunk (one phase per step)
+  uint64_t* o_bar = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* mask_bits = tmem_slot + 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int S16 = (S + 15) & ~15, S8 = (S + 7) & ~7;
+  const int nkc = (S16 + 127) / 128;          // key chunks
+  const int nsteps = 2 * nkc;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmO);
+    ptx::mbar_init(load_bar, 1);
+    ptx::mbar_init(s_bar, 1);
+    ptx::mbar_init(t_bar, 128);
+    ptx::mbar_init(o_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
+  if (warp >= 2) {
+    const int et = threadIdx.x - 64;
+    if (et < 8) {
+      uint32_t w = 0;
+      for (int j = 0; j < 32; ++j) {
+        const int key = 32 * et + j;
+        if (key < S && mask[size_t(b) * S + key] == 0) w |= (1u << j);
+      }
+      mask_bits[et] = w;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(load_bar, L::Q_BYTES + L::K_BYTES + L::V_BYTES);
+      ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, m0, head, b);
+      ptx::tma_load_4d(k_s, &tmK, load_bar, 0, 0, head, b);
+      ptx::tma_load_4d(v_s, &tmV, load_bar, 0, 0, head, b);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      ptx::mbar_wait(load_bar, 0);
+      ptx::tc_fence_after();
+      constexpr int KSTEPS = (DK + 7) / 8;
+      const uint32_t qa = ptx::smem_u32(q_s), ka = ptx::smem_u32(k_s), va = ptx::smem_u32(v_s);
+      const uint32_t idesc_o = ptx::idesc_tf32(128, DK < 16 ? 16 : DK, 0, 1);
+      auto issue_pv = [&](int kc) {
+        const int keys = min(128, S8 - 128 * kc);
+        for (int i = 0; i < keys / 8; ++i)
+          ptx::mma_tf32_ts(tmem_O, tmem_S + 8 * i, ptx::smem_desc_sw128<1>(va + kc * 16384 + i * 1024, 256 * 128, 512),
+                           idesc_o, (kc > 0 || i > 0) ? 1u : 0u);
+      };
+      for (int st = 0; st < nsteps; ++st) {
+        const int kc = st % nkc;
+        if (st > 0) {
+          ptx::mbar_wait(t_bar, (st - 1) & 1);
+          ptx::tc_fence_after();
+          if (st - 1 >= nkc) issue_pv((st - 1) % nkc);      // P of the previous pass-B chunk is in the S window
+        }
+        const int nc = min(128, S16 - 128 * kc);
+        const uint32_t idesc_s = ptx::idesc_tf32(128, nc, 0, 0);
+        for (int k = 0; k < KSTEPS; ++k)
+          ptx::mma_tf32_ss(tmem_S, ptx::smem_desc_sw128<2>(qa + k * 32, 16, 1024),
+                           ptx::smem_desc_sw128<2>(ka + kc * 16384 + k * 32, 16, 1024), idesc_s, k > 0);
+        ptx::mma_commit(s_bar);
+      }
+      ptx::mbar_wait(t_bar, (nsteps - 1) & 1);
+      ptx::tc_fence_after();
+      issue_pv(nkc - 1);
+      ptx::mma_commit(o_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const int qidx = m0 + row;
+    const uint32_t lane_addr = uint32_t(32 * q) << 16;
+    float mx = -CUDART_INF_F, sum = 0.f, mxs = 0.f;
+    for (int st = 0; st < nsteps; ++st) {
+      const int kc = st % nkc;
+      const bool pass_b = st >= nkc;
+      if (st == nkc) mxs = mx * scale_log2e;
+      ptx::mbar_wait(s_bar, st & 1);
+      ptx::tc_fence_after();
+      const int keys = min(128, S8 - 128 * kc);
+      const int nch = (keys + 31) / 32;
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
+        ptx::tmem_ld_wait();
+        const uint32_t bits = mask_bits[4 * kc + c];
+        if (!pass_b) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (bits & (1u << j)) mx = fmaxf(mx, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e = (bits & (1u << j)) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs)) : 0.0f;
+            sum += e;
+            if constexpr (DROP) {
+              const unsigned long long idx =
+                  ((unsigned long long)(b * n_heads + head) * S + qidx) * (unsigned long long)S + (128 * kc + 32 * c + j);
+              e = drop_keep(idx, drop.seed, drop.thresh) ? e * drop.scale : 0.0f;
+            }
+            v[j] = round_tf32(e);
+          }
+          ptx::tmem_st_32x32(tmem_S + lane_addr + 32 * c, v);
+        }
+      }
+      if (pass_b) ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(t_bar);
+    }
+    if (qidx < S) {
+      const size_t so = (size_t(b) * n_heads + head) * S + qidx;
+      stat_max[so] = mx;
+      stat_sum[so] = sum;
+    }
+    const float inv = 1.0f / sum;
+    ptx::mbar_wait(o_bar, 0);
+    ptx::tc_fence_after();
+    {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_O + lane_addr, v);
+      ptx::tmem_ld_wait();
+      uint8_t* slab_row = o_s + row * 128;
+#pragma unroll
+      for (int piece = 0; piece < 8; ++piece) {
+        float4 o;
+        o.x = __uint_as_float(v[piece * 4 + 0]) * inv;
+        o.y = __uint_as_float(v[piece * 4 + 1]) * inv;
+        o.z = __uint_as_float(v[piece * 4 + 2]) * inv;
+        o.w = __uint_as_float(v[piece * 4 + 3]) * inv;
+        *reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4)) = o;
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::named_bar_sync(1, 128);
+    if (threadIdx.x == 64) {
+      ptx::tma_store_4d(&tmO, o_s, 0, m0, head, b);
+      ptx::tma_store_commit();
+      ptx::tma_store_wait_read();
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<256>(tmem_base);
+  }
+}
+
+static int g_attn_fwd_two_pass = 1;
+void set_attn_fwd_two_pass(int on) { g_attn_fwd_two_pass = on; }
+
 template <int DK>
 static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   using L = AttFwdSmem<DK>;
@@ -238,14 +427,22 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   if ((rc = make_tmap_4d(&tV, a.v, TmapBox{{32, 256, 1, 1}}, 1, 1))) return rc;
   if ((rc = make_tmap_4d(&tO, a.o, TmapBox{{32, 128, 1, 1}}, 0, 0))) return rc;
   const bool drop = a.drop.thresh != 0;
-  auto kern = drop ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
-  static bool configured[2] = {false, false};
-  if (!configured[drop ? 1 : 0]) {
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const uint8_t*, float*, float*, int, int, float,
+               DropSite);
+  if constexpr (DK <= 32) {
+    if (g_attn_fwd_two_pass) kern = drop ? attn_fwd2_kernel<DK, true> : attn_fwd2_kernel<DK, false>;
+    else kern = drop ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
+  } else {
+    kern = drop ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
+  }
+  static bool configured[4] = {false, false, false, false};
+  const int slot = (drop ? 1 : 0) + ((DK <= 32 && g_attn_fwd_two_pass) ? 2 : 0);
+  if (!configured[slot]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total()) != cudaSuccess) {
       arb_set_error("attn_fwd: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    configured[drop ? 1 : 0] = true;
+    configured[slot] = true;
   }
   dim3 grid((a.S + 127) / 128, a.h, a.B);
   {

@@ -465,6 +465,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
 using namespace arb;
 
 extern "C" void arb_set_attention_mode(int32_t mode) { g_attn_mode = mode; }
+extern "C" void arb_set_attention_fwd_two_pass(int32_t on) { set_attn_fwd_two_pass(on); }
 
 extern "C" int64_t arb_scorer_param_count(const arb_scorer_config* cfg) {
   ParamLayout L;

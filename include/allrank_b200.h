@@ -189,6 +189,10 @@ int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, c
  * head width <= 32); other shapes use the unfused path automatically.  Process-wide; exists for A/B tests. */
 void arb_set_attention_mode(int32_t mode);
 
+/* 1 (default): the fused attention forward runs as the two-pass / two-CTAs-per-SM kernel (head width <= 32);
+ * 0: the single-pass kernel that keeps the whole S x S tile in TMEM (one CTA per SM). For A/B measurements. */
+void arb_set_attention_fwd_two_pass(int32_t on);
+
 /* 1: persistent, decoupled-pipeline GEMM kernel (one CTA per SM walking all tiles); 0 (default): one CTA per tile.
  * Process-wide; exists for A/B measurements. */
 void arb_set_gemm_persistent(int32_t on);
