@@ -387,7 +387,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=1024, help="slates per step per GPU")
+    ap.add_argument("--batch", type=int, default=4096,
+                    help="slates per step per GPU (saturating batch; 64 = allRank's default batch_size, see profiles/)")
     ap.add_argument("--ref-batch", type=int, default=64, help="slates per CPU step (reference default batch_size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
