@@ -15,7 +15,6 @@
 namespace arb {
 
 constexpr int ROWS_PER_BLOCK = 8;   // 8 warps
-constexpr int MAX_VEC = 8;          // width <= 32 * 4 * MAX_VEC/4 ... each lane holds up to 4*MAX_VEC/4 floats
 
 // Each lane owns columns lane*4 + 128*k .. +3 (float4), k < NV; width must be a multiple of 4 and <= 128*NV.
 template <int NV>

@@ -465,9 +465,8 @@ __global__ void __launch_bounds__(256) listmle_kernel(const float* __restrict__ 
       float g = 0.f;
       if (valid) {
         g = e[i] * cc[i] - 1.0f;
-        if (i == amax) g += shift - 0.0f;
-        // the -max shift removes sum_k(e_k C_k) - n_valid ... from the arg-max; analytically that equals
-        // -sum_i tail_i/(tail_i+eps) + n_valid = shift, already added above.
+        // the max-shift z = raw - max routes -sum_k dL/dz_k = sum_i eps/(tail_i+eps) to the arg-max item
+        if (i == amax) g += shift;
       }
       grad[size_t(b) * S + src[i]] = g * inv_B;
     }
@@ -563,7 +562,7 @@ struct LambdaCfg {
 __device__ __forceinline__ float lambda_weight(const LambdaCfg& cfg, int i, int j, const float* G,
                                                const float* invD, const float* toe, const float* t) {
   switch (cfg.scheme) {
-    case ARB_SCHEME_NDCGLOSS1: return G[i] * invD[i];   // (G / D)[:, :, None]   (G/D, not G*1/D: see below)
+    case ARB_SCHEME_NDCGLOSS1: return G[i] * invD[i];   // (G / D)[:, :, None]; the kernel divides by log2 directly
     case ARB_SCHEME_NDCGLOSS2: return toe[abs(i - j)] * fabsf(G[i] - G[j]);
     case ARB_SCHEME_LAMBDARANK: return fabsf(invD[i] - invD[j]) * fabsf(G[i] - G[j]);
     case ARB_SCHEME_NDCGLOSS2PP:
