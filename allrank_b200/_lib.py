@@ -26,6 +26,7 @@ _SIGS = {
     "arb_lambda_loss": (c_i, [c_p, c_p, c_i, c_i, c_f, c_f, c_i, c_i, c_f, c_f, c_i, c_i, c_p, c_p, c_p, c_p]),
     "arb_ranknet": (c_i, [c_p, c_p, c_i, c_i, c_f, c_i, c_p, c_p, c_p, c_p]),
     "arb_pointwise_loss": (c_i, [c_p, c_p, c_i, c_i, c_f, c_i, c_f, c_f, c_p, c_p, c_p, c_p]),
+    "arb_ordinal": (c_i, [c_p, c_p, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p]),
     "arb_neural_ndcg_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "arb_neural_ndcg": (c_i, [c_p, c_p, c_i, c_i, c_p, c_f, c_f, c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_sz, c_p]),
 }

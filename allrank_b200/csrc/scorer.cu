@@ -31,6 +31,8 @@ static bool use_fused_bwd(const arb_scorer_config& c, int S) {
   return g_attn_mode >= 2 && use_fused(c, S) && attn_fused_bwd_supported(S, c.d_model / c.n_heads);
 }
 
+static inline int n_outputs(const arb_scorer_config& c) { return c.d_output > 1 ? c.d_output : 1; }
+
 struct ParamLayout {
   int64_t fc_w, fc_b;
   struct Layer { int64_t wqkv, bqkv, wo, bo, w1, b1, w2, b2, ln1_a, ln1_b, ln2_a, ln2_b; };
@@ -72,8 +74,10 @@ static int make_param_layout(const arb_scorer_config& c, ParamLayout& L) {
     y.ln2_b = o; o += d;
   }
   if (c.n_layers > 0) { L.lnf_a = o; o += d; L.lnf_b = o; o += d; } else { L.lnf_a = L.lnf_b = -1; }
-  L.head_w = o; o += d;
-  L.head_b = o; o += 1;
+  if (c.d_output < 0 || c.d_output > 64) { arb_set_error("scorer: d_output must be in [1,64]"); return ARB_E_UNSUPPORTED; }
+  const int64_t n_out = n_outputs(c);
+  L.head_w = o; o += n_out * d;      // nn.Linear(d, d_output).weight, row-major [d_output, d]
+  L.head_b = o; o += n_out;
   L.pe = -1;
   if (c.pe_mode != 0) {
     if (c.n_layers == 0 || c.pe_rows < 2 || c.pe_mode < 0 || c.pe_mode > 2) {
@@ -90,7 +94,7 @@ struct WsLayout {
   int64_t x0;
   struct Layer { int64_t xn1, mean1, std1, qkv, prob, smax, ssum, ctx, xmid, xn2, mean2, std2, hdn, xout; };
   Layer layer[64];
-  int64_t meanf, stdf, total;
+  int64_t meanf, stdf, xf, total;   // xf: final-norm output, kept only for the multi-output head
   int Sp;
   bool fused;
 };
@@ -125,6 +129,7 @@ static void make_ws_layout(const arb_scorer_config& c, int B, int S, int trainin
   }
   W.meanf = take(R);
   W.stdf = take(R);
+  W.xf = (n_outputs(c) > 1 && c.n_layers > 0) ? take(R * d) : 0;
   W.total = o;
 }
 
@@ -286,6 +291,14 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     xcur = xout;
   }
   const int has_norm = c.n_layers > 0;
+  if (n_outputs(c) > 1) {   // d_output > 1: final norm as its own kernel, then one dot product per output (model.py:116)
+    const float* xf = xcur;
+    if (has_norm) {
+      ARB_TRY(ln_forward(xcur, P + L.lnf_a, P + L.lnf_b, c.ln_eps, k.R, d, ws + W.xf, ws + W.meanf, ws + W.stdf, st));
+      xf = ws + W.xf;
+    }
+    return head_multi_forward(xf, P + L.head_w, P + L.head_b, c.out_act, k.R, d, n_outputs(c), scores, st);
+  }
   ARB_TRY(head_forward(xcur, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr, c.ln_eps, P + L.head_w,
                        P + L.head_b, has_norm, c.out_act, k.R, d, scores, ws + W.meanf, ws + W.stdf, st));
   return ARB_OK;
@@ -346,10 +359,23 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
 
   const int has_norm = c.n_layers > 0;
   const float* xlast = c.n_layers > 0 ? ws + W.layer[c.n_layers - 1].xout : ws + W.x0;
-  ARB_TRY(head_backward(dscores, scores, xlast, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr,
-                        ws + W.meanf, ws + W.stdf, c.ln_eps, P + L.head_w, P + L.head_b, has_norm, c.out_act, k.R, d, dx,
-                        has_norm ? G + L.lnf_a : nullptr, has_norm ? G + L.lnf_b : nullptr, G + L.head_w, G + L.head_b,
-                        st, dxm, top_site, c.n_layers > 0 ? G + L.layer[c.n_layers - 1].b2 : G + L.fc_b));
+  float* top_bias_grad = c.n_layers > 0 ? G + L.layer[c.n_layers - 1].b2 : G + L.fc_b;
+  if (n_outputs(c) > 1) {
+    if (has_norm) {   // d xf into dxn, then the final norm's backward emits dx (+ its masked copy and the b2 gradient)
+      ARB_TRY(head_multi_backward(dscores, scores, ws + W.xf, P + L.head_w, c.out_act, k.R, d, n_outputs(c), dxn,
+                                  G + L.head_w, G + L.head_b, st));
+      ARB_TRY(ln_backward(dxn, xlast, P + L.lnf_a, ws + W.meanf, ws + W.stdf, c.ln_eps, nullptr, k.R, d, dx,
+                          G + L.lnf_a, G + L.lnf_b, st, dxm, top_site, top_bias_grad));
+    } else {
+      ARB_TRY(head_multi_backward(dscores, scores, xlast, P + L.head_w, c.out_act, k.R, d, n_outputs(c), dx,
+                                  G + L.head_w, G + L.head_b, st, dxm, top_site, top_bias_grad));
+    }
+  } else {
+    ARB_TRY(head_backward(dscores, scores, xlast, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr,
+                          ws + W.meanf, ws + W.stdf, c.ln_eps, P + L.head_w, P + L.head_b, has_norm, c.out_act, k.R, d,
+                          dx, has_norm ? G + L.lnf_a : nullptr, has_norm ? G + L.lnf_b : nullptr, G + L.head_w,
+                          G + L.head_b, st, dxm, top_site, top_bias_grad));
+  }
   const float* dy = top_site.thresh ? dxm : dx;   // gradient w.r.t. the output of the linear below the dropout
   for (int l = c.n_layers - 1; l >= 0; --l) {
     const auto& pl = L.layer[l];

@@ -505,6 +505,110 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------ multi-output head
+// post_model.d_output = n > 1 (model.py:104-117; the ordinal loss reads n probabilities per item):
+//   score[row, j] = act( w_j . xf[row] + b_j ),   xf = the final LayerNorm's output (or the FC output), kept in HBM.
+// n is small (the number of relevance levels), so the kernels loop over it; the weight rows stay in L1.
+template <int NV>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_multi_fwd_kernel(const float* __restrict__ xf,
+                                                                            const float* __restrict__ w,
+                                                                            const float* __restrict__ wb, int act,
+                                                                            long long rows, int width, int n,
+                                                                            float* __restrict__ score) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  RowRegs<NV> r, gw;
+  load_row<NV>(xf + row * width, width, lane, r);
+  for (int j = 0; j < n; ++j) {
+    load_row<NV>(w + (long long)j * width, width, lane, gw);
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) dot += r.v[k].x * gw.v[k].x + r.v[k].y * gw.v[k].y + r.v[k].z * gw.v[k].z + r.v[k].w * gw.v[k].w;
+    dot = warp_sum(dot);
+    if (lane == 0) score[row * n + j] = act_fwd(dot + wb[j], act);
+  }
+}
+
+// d xf[row] = sum_j dz_j w_j;  grad_w[j] += sum_rows dz_j xf[row];  grad_wb[j] += sum_rows dz_j;  dz = dscore * act'.
+// dx_masked / colsum_out: the FC-only model has no final norm, so this kernel also emits the gradient seen through
+// the FC dropout and the FC bias gradient (what head_bwd_kernel does for n = 1).
+template <int NV>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_multi_bwd_kernel(
+    const float* __restrict__ dscore, const float* __restrict__ score, const float* __restrict__ xf,
+    const float* __restrict__ w, int act, long long rows, int width, int n, int rows_per_warp,
+    float* __restrict__ dxf, float* __restrict__ grad_w, float* __restrict__ grad_wb, float* __restrict__ dx_masked,
+    DropSite site, float* __restrict__ colsum_out) {
+  __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
+  __shared__ float shb[ROWS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
+  RowRegs<NV> acc, gw;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = 0; it < rows_per_warp; ++it) {
+    const long long row = first + it;
+    if (row >= rows) break;
+    RowRegs<NV> g;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) g.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < n; ++j) {
+      const float out = score[row * n + j];
+      const float dz = dscore[row * n + j] * act_bwd(out, out, act);   // relu: out > 0 <=> z > 0
+      load_row<NV>(w + (long long)j * width, width, lane, gw);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        g.v[k].x += dz * gw.v[k].x; g.v[k].y += dz * gw.v[k].y; g.v[k].z += dz * gw.v[k].z; g.v[k].w += dz * gw.v[k].w;
+      }
+    }
+    store_row<NV>(dxf + row * width, width, lane, g);
+    if (dx_masked) { apply_drop<NV>(g, row, width, lane, site); store_row<NV>(dx_masked + row * width, width, lane, g); }
+    if (colsum_out) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        acc.v[k].x += g.v[k].x; acc.v[k].y += g.v[k].y; acc.v[k].z += g.v[k].z; acc.v[k].w += g.v[k].w;
+      }
+    }
+  }
+  // block-level column reductions: pass -1 = colsum_out, pass j = grad_w row j
+  for (int j = colsum_out ? -1 : 0; j < n; ++j) {
+    float acc_b = 0.f;
+    if (j >= 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) acc.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int it = 0; it < rows_per_warp; ++it) {
+        const long long row = first + it;
+        if (row >= rows) break;
+        const float out = score[row * n + j];
+        const float dz = dscore[row * n + j] * act_bwd(out, out, act);
+        load_row<NV>(xf + row * width, width, lane, gw);
+        acc_b += dz;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          acc.v[k].x += dz * gw.v[k].x; acc.v[k].y += dz * gw.v[k].y; acc.v[k].z += dz * gw.v[k].z; acc.v[k].w += dz * gw.v[k].w;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) *reinterpret_cast<float4*>(&sh[wid][lane * 4 + 128 * k]) = acc.v[k];
+    if (lane == 0) shb[wid] = acc_b;
+    __syncthreads();
+    float* dst = j < 0 ? colsum_out : grad_w + (long long)j * width;
+    for (int c = threadIdx.x; c < width; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < ROWS_PER_BLOCK; ++ww) t += sh[ww][c];
+      atomicAdd(dst + c, t);
+    }
+    if (j >= 0 && threadIdx.x == 0) {
+      float t = 0.f;
+      for (int ww = 0; ww < ROWS_PER_BLOCK; ++ww) t += shb[ww];
+      atomicAdd(grad_wb + j, t);
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ positional encoding
 // x = sqrt(d) * x + pe[idx],  idx = padded ? last row : min(index, last row)     (allrank/models/positional.py:39-50,66-77)
 __global__ void __launch_bounds__(256) pos_fwd_kernel(float* __restrict__ x, const long long* __restrict__ indices,
@@ -635,6 +739,26 @@ int head_backward(const float* dscore, const float* score, const float* x, const
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 16), st);
   ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out)));
+  return check_launch();
+}
+
+int head_multi_forward(const float* xf, const float* w, const float* wb, int act, long long rows, int width, int n,
+                       float* score, cudaStream_t st) {
+  if (width % 4) { arb_set_error("model width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
+  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (4.0 * width + 4.0 * n), st);
+  ARB_DISPATCH_NV(width, (head_multi_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(xf, w, wb, act, rows, width, n, score)));
+  return check_launch();
+}
+
+int head_multi_backward(const float* dscore, const float* score, const float* xf, const float* w, int act,
+                        long long rows, int width, int n, float* dxf, float* grad_w, float* grad_wb, cudaStream_t st,
+                        float* dx_masked, DropSite site, float* colsum_out) {
+  if (site.thresh == 0) dx_masked = nullptr;
+  const int rpw = 8;
+  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 8.0 * n), st);
+  ARB_DISPATCH_NV(width, (head_multi_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, xf, w, act, rows, width, n, rpw, dxf, grad_w, grad_wb, dx_masked, site, colsum_out)));
   return check_launch();
 }
 

@@ -29,5 +29,12 @@ int head_backward(const float* dscore, const float* score, const float* x, const
                   int act, long long rows, int width, float* dx, float* grad_a, float* grad_b, float* grad_w,
                   float* grad_wb, cudaStream_t st, float* dx_masked = nullptr,
                   DropSite site = DropSite{0u, 0u, 1.0f}, float* colsum_out = nullptr);
+// d_output = n > 1: scores [rows, n] from the (already normalised) rows xf; see scorer_kernels.cu
+int head_multi_forward(const float* xf, const float* w, const float* wb, int act, long long rows, int width, int n,
+                       float* score, cudaStream_t st);
+int head_multi_backward(const float* dscore, const float* score, const float* xf, const float* w, int act,
+                        long long rows, int width, int n, float* dxf, float* grad_w, float* grad_wb, cudaStream_t st,
+                        float* dx_masked = nullptr, DropSite site = DropSite{0u, 0u, 1.0f},
+                        float* colsum_out = nullptr);
 
 }  // namespace arb

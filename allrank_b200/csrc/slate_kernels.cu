@@ -817,6 +817,39 @@ __global__ void __launch_bounds__(128) pointwise_warp_kernel(const float* __rest
   }
 }
 
+// ordinal (losses/ordinal.py:8-50): y_pred [B,S,n] probabilities, target level j of an item with label t is
+// 1[t >= j+1] (with_ordinals :8-22).  BCE per (item, level) with PyTorch's BCELoss conventions (logs clamped at
+// -100, backward divides by max(p(1-p), 1e-12)); padded items contribute nothing.  One warp per slate; the n
+// levels of an item are contiguous, so lanes stride over the flattened [S*n] row for coalesced loads.
+//   val[b] = sum of the BCE terms, cnt[b] = number of valid items  -> finalize mode 1 (sum / total valid items)
+__global__ void __launch_bounds__(128) ordinal_warp_kernel(const float* __restrict__ y_pred,
+                                                           const float* __restrict__ y_true, int B, int S, int n,
+                                                           float pad, float* __restrict__ val,
+                                                           float* __restrict__ cnt, float* __restrict__ grad) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float* yp = y_pred + size_t(b) * S * n;
+  const float* yt = y_true + size_t(b) * S;
+  float lossb = 0.f, nvalid = 0.f;
+  for (int e = lane; e < S * n; e += 32) {
+    const int i = e / n, j = e - i * n;
+    const float lab = yt[i];
+    float g = 0.f;
+    if (lab != pad) {
+      const float p = yp[e];
+      const float y = (lab >= float(j + 1)) ? 1.0f : 0.0f;
+      lossb -= y * fmaxf(logf(p), -100.0f) + (1.0f - y) * fmaxf(logf(1.0f - p), -100.0f);
+      g = (p - y) / fmaxf(p * (1.0f - p), 1e-12f);
+      if (j == 0) nvalid += 1.0f;
+    }
+    if (grad) grad[size_t(b) * S * n + e] = g;
+  }
+  lossb = warp_sum(lossb);
+  nvalid = warp_sum(nvalid);
+  if (lane == 0) { val[b] = lossb; cnt[b] = nvalid; }
+}
+
 }  // namespace arb
 
 // ================================================================================================
@@ -1015,4 +1048,19 @@ extern "C" int32_t arb_pointwise_loss(const float* y_pred, const float* y_true, 
   ARB_LAUNCH_OK();
   // binary_listNet / rmse: mean over the batch is already folded in; bce: divide by the number of non-empty slates
   return finalize(scratch, scratch + B, B, mode == 2 ? 1 : 0, loss, grad, size_t(B) * S, st);
+}
+
+extern "C" int32_t arb_ordinal(const float* y_pred, const float* y_true, int32_t B, int32_t S, int32_t n,
+                               float pad_value, float* loss, float* grad, float* scratch, void* stream) {
+  ARB_CHECK_ARGS(y_pred && y_true && loss && scratch && B > 0 && S > 0 && n > 0, "arb_ordinal: null pointer or bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int wpb = 4;
+  {
+    ProfScope ps(ARB_PROF_LOSS, double(B) * S * ((grad ? 8.0 : 4.0) * n + 4.0) + 4.0, st);
+    ordinal_warp_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(y_pred, y_true, B, S, n, pad_value, scratch,
+                                                                 scratch + B, grad);
+  }
+  arb_count_launch();
+  ARB_LAUNCH_OK();
+  return finalize(scratch, scratch + B, B, 1, loss, grad, size_t(B) * S * n, st);   // / total number of valid items
 }

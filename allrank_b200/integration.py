@@ -12,7 +12,8 @@ from . import metrics as _metrics
 from . import model as _model
 
 LOSS_NAMES = ("listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "neuralNDCG_transposed", "rankNet",
-              "rankNet_weightByGTDiff", "rankNet_weightByGTDiff_pow", "binary_listNet", "pointwise_rmse", "bce")
+              "rankNet_weightByGTDiff", "rankNet_weightByGTDiff_pow", "binary_listNet", "pointwise_rmse", "bce",
+              "ordinal", "with_ordinals")
 METRIC_NAMES = ("ndcg", "dcg", "mrr")
 
 

@@ -249,6 +249,41 @@ def bce(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE):
     return _pointwise(y_pred, y_true, padded_value_indicator, 2, 0.0, 0.0)
 
 
+def with_ordinals(y, n, padded_value_indicator=PADDED_Y_VALUE):
+    """Labels [B,S] -> ordinal targets [B,S,n]: level j is 1 where y >= j+1, padded items keep the padding value --
+    ordinal.py:8-22.  (Target preparation only; the loss kernel derives the targets on the fly.)"""
+    _lib.require_cuda(y)
+    levels = torch.arange(1, n + 1, dtype=torch.float32, device=y.device)
+    spread = y.unsqueeze(2).repeat(1, 1, n)
+    out = (spread >= levels).float()
+    out[spread == padded_value_indicator] = padded_value_indicator
+    return out
+
+
+def ordinal(y_pred, y_true, n, padded_value_indicator=PADDED_Y_VALUE):
+    """Ordinal loss -- ordinal.py:25-50: y_pred [B,S,n] are per-level probabilities (a d_output = n model with a
+    Sigmoid head), BCE against with_ordinals(y_true, n), summed over levels and valid items and divided by the
+    number of valid items.  (On torch >= 2 the reference itself rejects padded slates: nn.BCELoss checks the -1
+    targets before they are masked; the intended semantics are implemented.)"""
+    _lib.require_cuda(y_pred, y_true)
+    n = int(n)
+    if y_pred.dim() != 3 or y_pred.shape[:2] != y_true.shape or y_pred.shape[2] != n:
+        raise ValueError("ordinal: y_pred must be [batch_size, slate_length, n] and y_true [batch_size, slate_length]")
+    if y_pred.shape[0] == 0:
+        raise ValueError("empty batch")
+    labels = y_true.detach().float().contiguous()
+    B, S = labels.shape
+    scratch = torch.empty(2 * B, dtype=torch.float32, device=labels.device)
+
+    def launch(probs, loss, grad):
+        rc = _lib.lib().arb_ordinal(_lib.ptr(probs), _lib.ptr(labels), B, S, n, float(padded_value_indicator),
+                                    _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(scratch), _lib.stream_ptr(probs.device))
+        _lib.check(rc, "arb_ordinal")
+
+    return _FusedLoss.apply(y_pred, launch)
+
+
 __all__ = ["listNet", "listMLE", "approxNDCGLoss", "lambdaLoss", "neuralNDCG", "neuralNDCG_transposed", "rankNet",
-           "rankNet_weightByGTDiff", "rankNet_weightByGTDiff_pow", "binary_listNet", "pointwise_rmse", "bce", "DEFAULT_EPS",
+           "rankNet_weightByGTDiff", "rankNet_weightByGTDiff_pow", "binary_listNet", "pointwise_rmse", "bce", "ordinal",
+           "with_ordinals", "DEFAULT_EPS",
            "PADDED_Y_VALUE"]

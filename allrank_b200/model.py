@@ -3,7 +3,7 @@
 Same call surface as the reference (/root/reference/allrank/models/model.py):
 
     model = make_model(fc_model=..., transformer=..., post_model=..., n_features=...)      # model.py:131
-    scores = model(x, mask, indices)            # [B,S]   (model.py:72-80,  train_utils.py:20)
+    scores = model(x, mask, indices)            # [B,S] ([B,S,d_output] when d_output > 1; model.py:72-80)
     scores = model.score(x, mask, indices)      # [B,S]   (model.py:82-92,  train_utils.py:34)
     model.parameters() / .state_dict() / .load_state_dict() / .train() / .eval() / .to(device)
 
@@ -26,8 +26,7 @@ Positional encodings (allrank/models/positional.py: fixed sinusoidal buffer or l
 padding row for padded items) are applied by a SIMT kernel after the input FC; the learned table is part of the flat
 parameter buffer.
 
-Not built yet (raise NotImplementedError rather than fall back): multi-layer / activated / input-normed FC blocks,
-d_output > 1.
+Not built yet (raise NotImplementedError rather than fall back): multi-layer / activated / input-normed FC blocks.
 """
 import copy
 import ctypes
@@ -44,7 +43,7 @@ class ScorerConfig(ctypes.Structure):
     _fields_ = [("n_features", ctypes.c_int32), ("d_model", ctypes.c_int32), ("n_layers", ctypes.c_int32),
                 ("n_heads", ctypes.c_int32), ("d_ff", ctypes.c_int32), ("out_act", ctypes.c_int32),
                 ("ln_eps", ctypes.c_float), ("dropout", ctypes.c_float), ("fc_dropout", ctypes.c_float),
-                ("pe_mode", ctypes.c_int32), ("pe_rows", ctypes.c_int32)]
+                ("pe_mode", ctypes.c_int32), ("pe_rows", ctypes.c_int32), ("d_output", ctypes.c_int32)]
 
 
 c_p, c_i, c_i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
@@ -136,7 +135,7 @@ class _Head(nn.Module):
     def __init__(self, lin):
         super().__init__()
         self.w_1 = lin
-        self.d_output = 1
+        self.d_output = lin.out_features
 
 
 def _clone_linear(proto):
@@ -170,8 +169,11 @@ class LTRModel(nn.Module):
     """B200 scorer with the reference LTRModel's surface (model.py:47-92)."""
 
     def __init__(self, n_features, d_model, n_layers, n_heads, d_ff, dropout, output_activation, fc_dropout=0.0,
-                 positional=None):
+                 positional=None, d_output=1):
         super().__init__()
+        self.d_output = int(d_output)
+        if not 1 <= self.d_output <= 64:
+            raise NotImplementedError("d_output must be in [1, 64]")
         if output_activation not in _ACTS:
             raise NotImplementedError(f"output activation {output_activation!r}: supported {sorted(map(str, _ACTS))}")
         self.n_features, self.d_model, self.n_layers = int(n_features), int(d_model), int(n_layers)
@@ -199,13 +201,13 @@ class LTRModel(nn.Module):
             self.encoder = _Encoder(n_layers, d_model, attn_proto, w1, w2, position)
         else:
             self.encoder = None
-        self.output_layer = _Head(nn.Linear(d_model, 1))
+        self.output_layer = _Head(nn.Linear(d_model, self.d_output))
         for p in self.parameters():
             if p.dim() > 1:
                 nn.init.xavier_uniform_(p)
         self._Fp = (self.n_features + 3) // 4 * 4
         self._cfg = ScorerConfig(self._Fp, self.d_model, self.n_layers, max(self.n_heads, 1), max(self.d_ff, 4),
-                                 _ACTS[output_activation], 1e-6, self.dropout_p, self.fc_dropout_p, 0, 0)
+                                 _ACTS[output_activation], 1e-6, self.dropout_p, self.fc_dropout_p, 0, 0, self.d_output)
         pos = self.encoder.position if self.encoder is not None else None
         if pos is not None:
             self._cfg.pe_mode = 1 if isinstance(pos, _FixedPE) else 2
@@ -324,7 +326,8 @@ class LTRModel(nn.Module):
         cfg = ctypes.byref(self._cfg)
         n_ws = int(_lib.lib().arb_scorer_workspace_floats(cfg, B, S, 1 if training else 0))
         ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
-        scores = torch.empty((B, S), dtype=torch.float32, device=dev)
+        shape = (B, S) if self.d_output == 1 else (B, S, self.d_output)   # squeeze(dim=2) is a no-op for n > 1 (model.py:117)
+        scores = torch.empty(shape, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             # dropout is applied iff the module is in train() mode, like nn.Dropout; `training` only selects
             # whether activations are kept for backward
@@ -376,7 +379,8 @@ class LTRModel(nn.Module):
         return scores
 
     def score(self, x, mask, indices=None):
-        return self.forward(x, mask, indices)
+        out = self.forward(x, mask, indices)
+        return out.sum(-1) if self.d_output > 1 else out       # model.py:119-128
 
 
 def _get(cfg, name, default=None):
@@ -398,8 +402,6 @@ def make_model(fc_model, transformer, post_model, n_features):
         raise NotImplementedError("allrank_b200 fuses a single input Linear; multi-layer FC blocks are a next item")
     if _get(fc_model, "input_norm", False) or _get(fc_model, "activation", None) is not None:
         raise NotImplementedError("input_norm / FC activation are not built into the fused scorer yet")
-    if int(_get(post_model, "d_output", 1)) != 1:
-        raise NotImplementedError("d_output > 1 (ordinal loss) is a SURVEY 8(f) next item")
     d_model = int(sizes[0])
     if transformer:
         pe_cfg = _get(transformer, "positional_encoding", None)
@@ -409,4 +411,5 @@ def make_model(fc_model, transformer, post_model, n_features):
     else:
         n_layers, heads, d_ff, dropout, positional = 0, 1, 4, 0.0, None
     return LTRModel(n_features, d_model, n_layers, heads, d_ff, dropout, _get(post_model, "output_activation", None),
-                    fc_dropout=float(_get(fc_model, "dropout", 0.0) or 0.0), positional=positional)
+                    fc_dropout=float(_get(fc_model, "dropout", 0.0) or 0.0), positional=positional,
+                    d_output=int(_get(post_model, "d_output", 1)))

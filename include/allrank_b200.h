@@ -117,6 +117,12 @@ int32_t arb_pointwise_loss(const float* y_pred, const float* y_true, int32_t B, 
                            int32_t mode, float param, float eps, float* loss, float* grad, float* scratch,
                            void* stream);
 
+/* ordinal(y_pred, y_true, n, pad)                                          .../losses/ordinal.py:8-50
+ * y_pred [B,S,n] are probabilities (the scorer's d_output = n, Sigmoid head); target level j of an item with
+ * label t is 1[t >= j+1] (with_ordinals, :8-22).  loss = sum of the n*valid BCE terms / number of valid items. */
+int32_t arb_ordinal(const float* y_pred, const float* y_true, int32_t B, int32_t S, int32_t n, float pad_value,
+                    float* loss, float* grad, float* scratch, void* stream);
+
 /* neuralNDCG(y_pred, y_true, pad, temperature, powered_relevancies, k, stochastic=False)
  *                            .../losses/neuralNDCG.py:10-70 + loss_utils.py:8-67 (NeuralSort, Sinkhorn)
  * max_iter / tol are the Sinkhorn parameters the reference hard-codes to 50 / 1e-6 (neuralNDCG.py:41-42).
@@ -164,6 +170,8 @@ typedef struct arb_scorer_config {
   float fc_dropout;     /* fc_model.dropout on the input FC output (model.py:43)                          */
   int32_t pe_mode;      /* positional encoding (allrank/models/positional.py): 0 none, 1 fixed table, 2 learned     */
   int32_t pe_rows;      /* rows of the table = max_indices + 1; the last row is the padding row              */
+  int32_t d_output;     /* post_model.d_output (model.py:104,108): outputs per item; 0 or 1 = one score per item.
+                           > 1 (ordinal loss): scores are [B,S,d_output], head weight [d_output,d_model]           */
 } arb_scorer_config;
 
 int64_t arb_scorer_param_count(const arb_scorer_config* cfg);

@@ -327,6 +327,26 @@ def bce(y_pred, y_true, padded_value_indicator=PAD):
     return per.sum() / non_empty
 
 
+def with_ordinals(y, n, padded_value_indicator=PAD):
+    # ordinal.py:8-22: level j (1-based) is 1 where y >= j; padded items keep the padding value
+    levels = torch.arange(1, n + 1, dtype=torch.float32)
+    spread = y.unsqueeze(2).repeat(1, 1, n)
+    out = (spread >= levels).float()
+    return torch.where(spread == padded_value_indicator, torch.full_like(out, float(padded_value_indicator)), out)
+
+
+def ordinal(y_pred, y_true, n, padded_value_indicator=PAD):
+    # ordinal.py:25-50 (intended semantics, as for bce above: padded items contribute 0): BCE of the [B,S,n] level
+    # probabilities against with_ordinals(y_true), summed, divided by the number of valid items
+    t = with_ordinals(y_true, n, padded_value_indicator)
+    is_pad = t == padded_value_indicator
+    t = t.masked_fill(is_pad, 0.0)
+    per = -(t * torch.log(y_pred).clamp(min=-100.0) + (1 - t) * torch.log(1 - y_pred).clamp(min=-100.0))
+    per = per.masked_fill(is_pad, 0.0)
+    n_valid_items = ((~is_pad).sum(dim=2) > 0).float().sum()
+    return per.sum() / n_valid_items
+
+
 LOSSES = {
     "listNet": listNet,
     "listMLE": listMLE,
@@ -337,6 +357,7 @@ LOSSES = {
     "rankNet": rankNet,
     "rankNet_weightByGTDiff": rankNet_weightByGTDiff,
     "rankNet_weightByGTDiff_pow": rankNet_weightByGTDiff_pow,
+    "ordinal": ordinal,
     "binary_listNet": binary_listNet,
     "pointwise_rmse": pointwise_rmse,
     "bce": bce,

@@ -244,6 +244,64 @@ def gen_scorer_pe():
         print("scorer pe", strategy, [k_ for k_ in model.state_dict() if "position" in k_])
 
 
+def gen_ordinal():
+    """ordinal (ordinal.py:25-50) on per-level probabilities [B,S,n]; unpadded slates only -- on torch >= 2 the
+    reference's nn.BCELoss rejects the -1 targets of padded items (its own padded test fails here)."""
+    blob = {}
+    keys = []
+    for n in (2, 4):
+        for (b, s) in SHAPES:
+            _, y = case_inputs(b, s, seed=1100 + s + n)
+            g = torch.Generator().manual_seed(s + n)
+            y = torch.where(y < 0, torch.randint(0, 5, y.shape, generator=g).float(), y)   # fill the padding
+            prob = torch.sigmoid(torch.randn(b, s, n, generator=g) * 2.0)
+            p = prob.clone().requires_grad_(True)
+            val = ref_losses.ordinal(p, y, n)
+            val.backward()
+            key = f"n{n}_s{s}"
+            blob[key + "_pred"] = prob.numpy()
+            blob[key + "_true"] = y.numpy()
+            blob[key + "_targets"] = ref_losses.with_ordinals(y, n).numpy()
+            blob[key + "_loss32"] = val.detach().numpy()
+            blob[key + "_grad32"] = p.grad.numpy()
+            keys.append(key)
+    blob["keys"] = np.array(keys)
+    np.savez_compressed(os.path.join(OUT, "ordinal.npz"), **blob)
+    print("ordinal:", len(keys), "cases")
+
+
+def gen_scorer_multi():
+    """d_output > 1 heads (model.py:104-128; the ordinal configuration: Sigmoid over n levels), with and without
+    the transformer; stores forward(), score() and parameter gradients."""
+    cases = {"dout4": (20, 32, 1, 2, 64, 3, 20, 4, "Sigmoid"), "dout3_fc": (20, 32, 0, 0, 0, 3, 20, 3, None)}
+    for name, (F, d, N, h, dff, B, S, n_out, act) in cases.items():
+        torch.manual_seed(13)
+        tr = TransformerConfig(N=N, d_ff=dff, h=h, positional_encoding=None, dropout=0.0) if N else None
+        model = ref_make_model(
+            fc_model={"sizes": [d], "input_norm": False, "activation": None, "dropout": 0.0},
+            transformer=tr, post_model={"d_output": n_out, "output_activation": act}, n_features=F)
+        g = torch.Generator().manual_seed(14)
+        with torch.no_grad():
+            for _, p in model.named_parameters():
+                if p.dim() == 1:
+                    p.add_(0.1 * torch.randn(p.shape, generator=g))
+        model.eval()
+        x, y, idx = make_slates(B, S, n_features=F, seed=35, mean_len=0.6 * S, std_len=0.3 * S)
+        mask = y == -1
+        out = model(x, mask, idx)
+        w = torch.randn(out.shape, generator=g)
+        (out * w).sum().backward()
+        blob = {"x": x.numpy(), "y": y.numpy(), "scores": out.detach().numpy(), "w": w.numpy(),
+                "score_sum": model.score(x, mask, idx).detach().numpy(),
+                "meta": np.array([F, d, N, h, dff, B, S, n_out]), "act": np.array(str(act))}
+        for k_, v in model.state_dict().items():
+            blob["p:" + k_] = v.numpy()
+        for k_, p in model.named_parameters():
+            blob["g:" + k_] = p.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, f"scorer_{name}.npz"), **blob)
+        print("scorer", name, "out", tuple(out.shape))
+
+
 def gen_init():
     """Seeded initialisation of the reference's make_model (model.py:131-151): pins construction order."""
     torch.manual_seed(123)
@@ -258,10 +316,7 @@ def gen_init():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    gen_losses()
-    gen_listmle()
-    gen_bce()
-    gen_metrics()
-    gen_scorer()
-    gen_scorer_pe()
-    gen_init()
+    gens = {"losses": gen_losses, "listmle": gen_listmle, "bce": gen_bce, "ordinal": gen_ordinal, "metrics": gen_metrics,
+            "scorer": gen_scorer, "scorer_pe": gen_scorer_pe, "scorer_multi": gen_scorer_multi, "init": gen_init}
+    for name in (sys.argv[1:] or list(gens)):      # optionally: only the named generators
+        gens[name]()

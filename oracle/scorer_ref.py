@@ -188,7 +188,8 @@ class RefLTRModel(nn.Module):
         self.output_layer = output_layer
 
     def prepare_for_output(self, x, mask, indices):
-        return self.encoder(self.input_layer(x), mask, indices)
+        h = self.input_layer(x)
+        return h if self.encoder is None else self.encoder(h, mask, indices)   # model.py:59: no encoder -> identity
 
     def forward(self, x, mask, indices):
         return self.output_layer(self.prepare_for_output(x, mask, indices))
@@ -205,7 +206,7 @@ def make_ref_model(n_features, fc_sizes, n_layers, heads, d_ff, dropout=0.0, d_o
     fc = InputFC(fc_sizes, n_features, activation=fc_activation)
     width = fc.output_size
     position = Position(width, positional[1], positional[0]) if positional else None
-    enc = Stack(n_layers, width, heads, d_ff, dropout, position)
+    enc = Stack(n_layers, width, heads, d_ff, dropout, position) if n_layers > 0 else None   # transformer=None
     model = RefLTRModel(fc, enc, Head(width, d_output, output_activation))
     for p in model.parameters():
         if p.dim() > 1:

@@ -30,6 +30,22 @@ LOSS_KNOWN = [
 ]
 
 
+def _xe(true, pred):
+    return -true * math.log(pred) - (1 - true) * math.log(1 - pred)
+
+
+# (y_pred [S][n], y_true [S], n, expected)      reference: tests/losses/test_loss_ordinal.py:26-57
+# (the padded case is the one the reference itself cannot run on torch >= 2; its closed form still pins the semantics)
+ORDINAL_KNOWN = [
+    ([[0.8, 0.6]], [1.0], 2, _xe(1, 0.8) + _xe(0, 0.6)),
+    ([[0.8, 0.7], [0.4, 0.3], [0.2, 0.1]], [2.0, 1.0, 0.0], 2,
+     (_xe(1, 0.8) + _xe(1, 0.7) + _xe(1, 0.4) + _xe(0, 0.3) + _xe(0, 0.2) + _xe(0, 0.1)) / 3.0),
+    ([[0.8, 0.6], [0.2, 0.1]], [1.0, PAD], 2, _xe(1, 0.8) + _xe(0, 0.6)),
+]
+# tests/losses/test_loss_ordinal.py:20-24: with_ordinals([2,1,0], n=2)
+WITH_ORDINALS_KNOWN = ([2.0, 1.0, 0.0], 2, [[1.0, 1.0], [1.0, 0.0], [0.0, 0.0]])
+
+
 def _softmax(v):
     m = max(v)
     e = [math.exp(a - m) for a in v]

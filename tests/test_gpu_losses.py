@@ -263,3 +263,72 @@ def test_next_row_losses_against_oracle_at_bench_shape(L, name, kw):
     val, grad = run(getattr(L, name), yp, y, **kw)
     assert abs(val - ref.item()) <= 1e-5 * abs(ref.item())
     assert np.abs(grad - p.grad.numpy()).max() <= 2e-5 * np.abs(p.grad.numpy()).max()
+
+
+@pytest.mark.parametrize("yp,yt,n,expected", cases.ORDINAL_KNOWN)
+def test_ordinal_known_answers(L, yp, yt, n, expected):
+    val, grad = run(L.ordinal, [yp], [yt], n=n)
+    assert math.isfinite(val) and np.isfinite(grad).all()
+    assert val == pytest.approx(expected, rel=1e-5)
+
+
+def test_with_ordinals_known_answer(L):
+    y, n, expected = cases.WITH_ORDINALS_KNOWN
+    assert L.with_ordinals(dev([y]), n).tolist() == [expected]
+    assert L.with_ordinals(dev([[1.0, cases.PAD]]), 2).tolist() == [[[1.0, 0.0], [cases.PAD, cases.PAD]]]
+
+
+def test_golden_ordinal_and_padding(L, golden):
+    g = golden("ordinal")
+    for key in g["keys"]:
+        key = str(key)
+        n = int(key.split("_")[0][1:])
+        val, grad = run(L.ordinal, g[key + "_pred"], g[key + "_true"], n=n)
+        ref, gref = float(g[key + "_loss32"]), g[key + "_grad32"]
+        assert abs(val - ref) <= REL * abs(ref), key
+        assert np.abs(grad - gref).max() <= 1e-5 * np.abs(gref).max(), key
+        # appended padded items (label -1) change nothing: they add no BCE terms and no valid items (ordinal.py:40-48)
+        b, s, _ = g[key + "_pred"].shape
+        yp2 = np.concatenate([g[key + "_pred"], np.full((b, 3, n), 0.5, dtype=np.float32)], axis=1)
+        yt2 = np.concatenate([g[key + "_true"], np.full((b, 3), -1.0, dtype=np.float32)], axis=1)
+        val2, grad2 = run(L.ordinal, yp2, yt2, n=n)
+        assert val2 == pytest.approx(val, rel=1e-6)
+        assert (grad2[:, s:] == 0).all()
+        assert np.array_equal(grad2[:, :s], grad)
+
+
+def test_ordinal_against_oracle_at_bench_shape(L):
+    from oracle import losses_ref
+    from allrank_b200.synth import make_slates
+    B, S, n = 64, 240, 4
+    _, y, _ = make_slates(B, S, n_features=1, seed=61)
+    prob = torch.sigmoid(2.0 * torch.randn(B, S, n, generator=torch.Generator().manual_seed(62)))
+    p = prob.clone().double().requires_grad_(True)
+    ref = losses_ref.ordinal(p, y.double(), n)
+    ref.backward()
+    val, grad = run(L.ordinal, prob, y, n=n)
+    assert abs(val - ref.item()) <= 1e-5 * abs(ref.item())
+    assert np.abs(grad - p.grad.numpy()).max() <= 2e-5 * np.abs(p.grad.numpy()).max()
+    assert (grad[(y == -1).numpy()] == 0).all()
+
+
+def test_ordinal_saturated_probabilities_follow_bceloss(L):
+    """p = 0 / p = 1: nn.BCELoss (what ordinal.py:42 calls) clamps the logs at -100 and its backward divides by
+    max(p(1-p), 1e-12); the kernel follows both conventions."""
+    y = torch.tensor([[3.0, 0.0, 1.0]])
+    prob = torch.tensor([[[0.0, 1.0, 0.3], [0.0, 1.0, 0.5], [1.0, 0.0, 0.25]]])
+    p = prob.clone().requires_grad_(True)
+    targets = (y.unsqueeze(2) >= torch.arange(1.0, 4.0)).float()
+    ref = torch.nn.functional.binary_cross_entropy(p, targets, reduction="sum") / 3.0
+    ref.backward()
+    val, grad = run(L.ordinal, prob, y, n=3)
+    assert val == pytest.approx(ref.item(), rel=1e-6)
+    assert np.allclose(grad, p.grad.numpy(), rtol=1e-5)
+
+
+def test_ordinal_rejects_bad_shapes(L):
+    with pytest.raises(ValueError):
+        L.ordinal(dev(np.zeros((2, 5), dtype=np.float32)), dev(np.zeros((2, 5), dtype=np.float32)), n=2)
+    with pytest.raises(ValueError):
+        L.ordinal(dev(np.zeros((2, 5, 3), dtype=np.float32)), dev(np.zeros((2, 5), dtype=np.float32)), n=2)
+

@@ -283,3 +283,76 @@ def test_positional_encodings_match_reference(golden, strategy):
     assert not bad, bad
     with torch.no_grad():
         assert torch.equal(model.eval()(x, y == -1, idx), scores.detach())
+
+
+@pytest.mark.parametrize("name", ["dout4", "dout3_fc"])
+def test_multi_output_head_matches_reference(golden, name):
+    """d_output > 1 (model.py:104-128): forward() is [B,S,n], score() sums the n outputs; golden vectors from the
+    reference, with and without a transformer."""
+    from allrank_b200.model import make_model
+    g = golden("scorer_" + name)
+    F, d, N, h, dff, B, S, n_out = [int(v) for v in g["meta"]]
+    act = None if str(g["act"]) == "None" else str(g["act"])
+    tr = {"N": N, "d_ff": dff, "h": h, "positional_encoding": None, "dropout": 0.0} if N else None
+    model = make_model(fc_model={"sizes": [d], "input_norm": False, "activation": None, "dropout": 0.0}, transformer=tr,
+                       post_model={"d_output": n_out, "output_activation": act}, n_features=F)
+    sd = {k[2:]: torch.tensor(g[k]) for k in g.files if k.startswith("p:")}
+    assert set(sd) == set(model.state_dict())
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    x, y = torch.tensor(g["x"]).cuda(), torch.tensor(g["y"]).cuda()
+    mask = y == -1
+    out = model(x, mask, None)
+    assert tuple(out.shape) == (B, S, n_out)
+    ref = g["scores"]
+    assert np.abs(out.detach().cpu().numpy() - ref).max() <= SCORE_TOL * max(1.0, np.abs(ref).max())
+    (out * torch.tensor(g["w"]).cuda()).sum().backward()
+    floor = 1e-2 * max(np.abs(g["g:" + k]).max() for k, _ in model.named_parameters())
+    bad = []
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        fro, mx = grad_errors(p.grad.cpu().numpy(), g["g:" + k], floor)
+        if fro > GRAD_TOL or mx > GRAD_TOL_MAX:
+            bad.append((k, fro, mx))
+    assert not bad, bad
+    with torch.no_grad():
+        summed = model.eval().score(x, mask, None)
+    assert tuple(summed.shape) == (B, S)
+    assert np.abs(summed.cpu().numpy() - g["score_sum"]).max() <= SCORE_TOL * n_out * max(1.0, np.abs(ref).max())
+
+
+def test_ordinal_training_matches_reference_trajectory():
+    """The paper's ordinal configuration (d_output = n, Sigmoid head, ordinal loss) trained for a few Adam steps:
+    same loss curve as the eager oracle; metrics read model.score()."""
+    from oracle.scorer_ref import make_ref_model
+    from oracle import losses_ref
+    from allrank_b200.model import make_model
+    from allrank_b200 import losses, metrics
+    from allrank_b200.synth import make_slates
+    torch.manual_seed(29)
+    n = 4
+    ref = make_ref_model(136, [64], 1, 2, 128, d_output=n, output_activation="Sigmoid").train()
+    mine = make_model(fc_model={"sizes": [64], "input_norm": False, "activation": None, "dropout": 0.0},
+                      transformer={"N": 1, "d_ff": 128, "h": 2, "positional_encoding": None, "dropout": 0.0},
+                      post_model={"d_output": n, "output_activation": "Sigmoid"}, n_features=136).cuda().train()
+    mine.load_state_dict(ref.state_dict())
+    x, y, idx = make_slates(32, 60, seed=6, mean_len=40, std_len=15)
+    mask = y == -1
+    xc, yc, mc = x.cuda(), y.cuda(), mask.cuda()
+    o_ref = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    o_mine = torch.optim.Adam(mine.parameters(), lr=1e-3)
+    curve_ref, curve_mine = [], []
+    for _ in range(8):
+        lr_ = losses_ref.ordinal(ref(x, mask, idx), y, n)
+        lr_.backward(); o_ref.step(); o_ref.zero_grad()
+        lm = losses.ordinal(mine(xc, mc, None), yc, n)
+        lm.backward(); o_mine.step(); o_mine.zero_grad()
+        curve_ref.append(lr_.item()); curve_mine.append(lm.item())
+    assert curve_mine[-1] < curve_mine[0]
+    assert np.allclose(curve_ref, curve_mine, rtol=2e-3, atol=2e-3), (curve_ref, curve_mine)
+    with torch.no_grad():
+        s_ref = ref.eval().score(x, mask, idx)
+        s_mine = mine.eval().score(xc, mc, None)
+    assert (s_ref - s_mine.cpu()).abs().max() <= SCORE_TOL * n
+    assert torch.isfinite(metrics.ndcg(s_mine, yc, ats=[5])).all()
+

@@ -44,14 +44,25 @@ def test_reference_state_dict_loads(golden):
     assert not missing.missing_keys and not missing.unexpected_keys
 
 
+def test_multi_output_head_has_the_reference_state_dict_layout(golden):
+    """post_model.d_output = n > 1 (the ordinal configuration): same keys and shapes as the reference's module tree."""
+    from allrank_b200.model import make_model
+    g = golden("scorer_dout4")
+    F, d, N, h, dff, B, S, n_out = [int(v) for v in g["meta"]]
+    model = make_model(fc_model={"sizes": [d], "input_norm": False, "activation": None, "dropout": 0.0},
+                       transformer={"N": N, "d_ff": dff, "h": h, "positional_encoding": None, "dropout": 0.0},
+                       post_model={"d_output": n_out, "output_activation": "Sigmoid"}, n_features=F)
+    sd = {k[2:]: torch.tensor(g[k]) for k in g.files if k.startswith("p:")}
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    assert tuple(model.output_layer.w_1.weight.shape) == (n_out, d) and model.output_layer.d_output == n_out
+    model.load_state_dict(sd, strict=True)
+
+
 def test_unsupported_configs_raise_not_fallback():
     from allrank_b200.model import make_model
     with pytest.raises(NotImplementedError):
         make_model(fc_model={"sizes": [32, 32], "input_norm": False, "activation": None, "dropout": 0.0},
                    transformer=None, post_model={"d_output": 1, "output_activation": None}, n_features=20)
-    with pytest.raises(NotImplementedError):
-        make_model(fc_model={"sizes": [32], "input_norm": False, "activation": None, "dropout": 0.0},
-                   transformer=None, post_model={"d_output": 3, "output_activation": None}, n_features=20)
     m = make()
     with pytest.raises(Exception):   # CPU tensors: no eager fallback
         m(torch.zeros(1, 4, 20), torch.zeros(1, 4, dtype=torch.bool), None)
@@ -66,7 +77,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in include/allrank_b200.h but not exported"
     lib.arb_abi_version.restype = ctypes.c_int32
-    assert lib.arb_abi_version() == 1
+    assert lib.arb_abi_version() == 2
 
 
 def test_param_count_matches_reference_models():

@@ -67,9 +67,11 @@ def test_metrics_match_reference_bit_exact(golden):
 
 
 def build_from_golden(g):
-    F, d, N, h, dff, B, S = [int(v) for v in g["meta"]]
+    meta = [int(v) for v in g["meta"]]
+    F, d, N, h, dff = meta[:5]
+    n_out = meta[7] if len(meta) > 7 else 1
     act = str(g["act"])
-    model = scorer_ref.make_ref_model(F, [d], N, h, dff, output_activation=None if act == "None" else act)
+    model = scorer_ref.make_ref_model(F, [d], N, h, dff, d_output=n_out, output_activation=None if act == "None" else act)
     sd = {k[2:]: torch.tensor(g[k]) for k in g.files if k.startswith("p:")}
     assert set(sd) == set(model.state_dict()), "state_dict keys must equal the reference's"
     model.load_state_dict(sd)
@@ -89,6 +91,36 @@ def test_scorer_matches_reference(golden, name):
     for k, p in model.named_parameters():
         ref = g["g:" + k]
         assert np.abs(p.grad.numpy() - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-6), k
+
+
+@pytest.mark.parametrize("name", ["dout4", "dout3_fc"])
+def test_multi_output_scorer_matches_reference(golden, name):
+    g = golden("scorer_" + name)
+    model = build_from_golden(g)
+    x, y = torch.tensor(g["x"]), torch.tensor(g["y"])
+    mask = y == -1
+    out = model(x, mask, None)
+    assert out.shape == g["scores"].shape and out.dim() == 3
+    assert np.allclose(out.detach().numpy(), g["scores"], rtol=1e-5, atol=2e-6)
+    assert np.allclose(model.score(x, mask, None).detach().numpy(), g["score_sum"], rtol=1e-5, atol=4e-6)
+    (out * torch.tensor(g["w"])).sum().backward()
+    for k, p in model.named_parameters():
+        ref = g["g:" + k]
+        assert np.abs(p.grad.numpy() - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-6), k
+
+
+def test_ordinal_matches_reference(golden):
+    g = golden("ordinal")
+    for key in g["keys"]:
+        key = str(key)
+        n = int(key.split("_")[0][1:])
+        yp = torch.tensor(g[key + "_pred"]).requires_grad_(True)
+        yt = torch.tensor(g[key + "_true"])
+        assert np.array_equal(losses_ref.with_ordinals(yt, n).numpy(), g[key + "_targets"]), key
+        val = losses_ref.ordinal(yp, yt, n)
+        val.backward()
+        assert np.allclose(val.item(), g[key + "_loss32"], rtol=2e-6), key
+        assert np.allclose(yp.grad.numpy(), g[key + "_grad32"], rtol=1e-5, atol=1e-7), key
 
 
 def test_bce_matches_reference(golden):

@@ -15,6 +15,20 @@ def test_loss_known_answers(name, kw, yp, yt, expected):
     assert val == pytest.approx(expected)
 
 
+@pytest.mark.parametrize("yp,yt,n,expected", cases.ORDINAL_KNOWN)
+def test_ordinal_known_answers(yp, yt, n, expected):
+    val = losses_ref.ordinal(torch.tensor([yp]), torch.tensor([yt]), n).item()
+    assert math.isfinite(val)
+    assert val == pytest.approx(expected)
+
+
+def test_with_ordinals_known_answer():
+    y, n, expected = cases.WITH_ORDINALS_KNOWN
+    assert losses_ref.with_ordinals(torch.tensor([y]), n).tolist() == [expected]
+    padded = losses_ref.with_ordinals(torch.tensor([[1.0, cases.PAD]]), 2).tolist()
+    assert padded == [[[1.0, 0.0], [cases.PAD, cases.PAD]]]
+
+
 @pytest.mark.parametrize("yp,yt,eps", cases.LISTNET_KNOWN)
 def test_listnet_closed_form(yp, yt, eps):
     val = losses_ref.listNet(torch.tensor([yp]), torch.tensor([yt]), eps).item()
