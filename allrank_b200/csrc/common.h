@@ -16,7 +16,7 @@ int arb_finalize_mean_over_count(const float* val, const float* cnt, int B, floa
 // Optional per-launch device timing (bench.py roofline): when enabled, every launch made inside a ProfScope is
 // bracketed by CUDA events on its own stream; arb_prof_collect sums durations and work units per kernel class.
 enum { ARB_PROF_GEMM = 0, ARB_PROF_SCORER_SIMT = 1, ARB_PROF_LOSS = 2, ARB_PROF_METRICS = 3, ARB_PROF_OPTIM = 4,
-       ARB_PROF_CLASSES = 5 };
+       ARB_PROF_SLATES = 5, ARB_PROF_CLASSES = 6 };
 struct ProfScope {
   ProfScope(int cls, double work, cudaStream_t st, double bytes = 0.0);
   ~ProfScope();

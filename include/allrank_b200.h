@@ -223,8 +223,29 @@ int32_t arb_adam_step(float* params, const float* grads, float* exp_avg, float* 
                       float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                       void* stream);
 
+/* ---------------------------------------------------------------- slate movers
+ * arb_assemble_slates: the per-slate FixLength transform + ToTensor + DataLoader collation of
+ * allrank/data/dataset_loading.py:32-93,:230-247 for a batch of queries, from a corpus resident in HBM:
+ *   docs_x [N,F] fp32 and docs_y [N] fp32 grouped by query, offsets [n_queries+1] int64 (CSR), queries [B] int64
+ *   (a query number outside [0, n_queries) produces an all-padding slate).
+ * Query shorter than S: rows in order, then zero rows with y = -1 and index = -1 (bit-identical to the reference).
+ * Otherwise: S items sampled uniformly without replacement in random order; a sample without any relevant item is
+ * redrawn while the query has one (the query's only relevant item, if its labels sum to 1, replaces the last
+ * sampled item instead) -- :55-74.  The sample stream is a counter hash of (seed, slate, attempt, item).
+ * max_query_len: longest query of the corpus (sizes the shared-memory sort; arb_assemble_slates_smem_bytes).
+ * Outputs: x_out [B,S,F], y_out [B,S] fp32, idx_out [B,S] int64 (positions inside the query, -1 = padded). */
+size_t arb_assemble_slates_smem_bytes(int32_t max_query_len, int32_t S);
+int32_t arb_assemble_slates(const float* docs_x, const float* docs_y, const int64_t* offsets, int64_t n_queries,
+                            const int64_t* queries, int32_t B, int32_t S, int32_t F, int32_t max_query_len,
+                            uint64_t seed, float* x_out, float* y_out, int64_t* idx_out, void* stream);
+/* inference_utils.__rank_slates (allrank/inference/inference_utils.py:37-60): x_out[b,r,:] = x[b,order[b,r],:],
+ * y_out[b,r] = y[b,order[b,r]], with `order` the descending score ranking (arb_rank_metrics' out_order). */
+int32_t arb_gather_slates(const float* x, const float* y, const int32_t* order, int32_t B, int32_t S, int32_t F,
+                          float* x_out, float* y_out, void* stream);
+
 /* Per-launch device timing for bench.py's roofline: enable, run steps, collect per kernel class
- * (0 = tcgen05 GEMM [work = flops], 1 = scorer SIMT, 2 = losses, 3 = metrics, 4 = optimiser [work = bytes]). */
+ * (0 = tcgen05 GEMM [work = flops], 1 = scorer SIMT, 2 = losses, 3 = metrics, 4 = optimiser, 5 = slate assembly /
+ * gather [work = bytes]). */
 void arb_prof_enable(int32_t on);
 int32_t arb_prof_collect(int32_t cls, double* total_ms, double* total_work, int64_t* launches);
 /* algorithmic HBM bytes (operands + outputs, each counted once) summed by the last arb_prof_collect(cls, ...) */

@@ -302,6 +302,53 @@ def gen_scorer_multi():
         print("scorer", name, "out", tuple(out.shape))
 
 
+def write_corpus(path, lengths, n_features, seed):
+    """A small libsvm corpus (label qid:N f:v ...), query ids deliberately not sorted, a few all-zero-label queries
+    and one query with a single relevant item."""
+    rng = np.random.RandomState(seed)
+    qids = rng.permutation(len(lengths)) + 3
+    with open(path, "w") as f:
+        for qi, n in enumerate(lengths):
+            labels = rng.choice(5, size=n, p=[0.6, 0.2, 0.1, 0.06, 0.04])
+            if qi % 5 == 1:
+                labels[:] = 0
+            if qi % 5 == 2:
+                labels[:] = 0
+                labels[rng.randint(n)] = 1
+            for d in range(n):
+                feats = rng.randn(n_features).round(4)
+                feats[rng.rand(n_features) < 0.2] = 0.0          # sparse entries are simply absent in libsvm
+                cols = " ".join(f"{j + 1}:{v}" for j, v in enumerate(feats) if v != 0.0)
+                f.write(f"{labels[d]} qid:{qids[qi]} {cols}\n")
+
+
+def gen_slates():
+    """LibSVMDataset + FixLength on a small corpus (dataset_loading.py:32-165): padded slates, and sampled slates under
+    np.random.seed so that the oracle (same numpy calls) can be pinned exactly."""
+    from allrank.data.dataset_loading import LibSVMDataset, FixLength
+    path = os.path.join(OUT, "slates_corpus.txt")
+    lengths = [3, 17, 25, 8, 40, 12, 31, 20, 5, 64, 1, 22]
+    write_corpus(path, lengths, n_features=12, seed=77)
+    ds = LibSVMDataset.from_svm_file(path)
+    blob = {"lengths": np.array([len(v) for v in ds.y_by_qid]), "shape": np.array(ds.shape)}
+    S = 20
+    fix = FixLength(S)
+    for qi in range(len(ds)):
+        np.random.seed(1000 + qi)
+        x, y, idx = fix((ds.X_by_qid[qi], ds.y_by_qid[qi]))
+        blob[f"q{qi}_x"], blob[f"q{qi}_y"], blob[f"q{qi}_idx"] = x.astype(np.float32), y.astype(np.float32), idx
+    blob["slate_length"] = np.array(S)
+    # the validation transform pads everything to the longest query (:185-192)
+    longest = int(ds.longest_query_length)
+    fix = FixLength(longest)
+    for qi in range(len(ds)):
+        if len(ds.y_by_qid[qi]) < longest:
+            x, y, idx = fix((ds.X_by_qid[qi], ds.y_by_qid[qi]))
+            blob[f"v{qi}_x"], blob[f"v{qi}_y"], blob[f"v{qi}_idx"] = x.astype(np.float32), y.astype(np.float32), idx
+    np.savez_compressed(os.path.join(OUT, "slates.npz"), **blob)
+    print("slates:", len(ds), "queries, longest", longest)
+
+
 def gen_init():
     """Seeded initialisation of the reference's make_model (model.py:131-151): pins construction order."""
     torch.manual_seed(123)
@@ -317,6 +364,6 @@ def gen_init():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     gens = {"losses": gen_losses, "listmle": gen_listmle, "bce": gen_bce, "ordinal": gen_ordinal, "metrics": gen_metrics,
-            "scorer": gen_scorer, "scorer_pe": gen_scorer_pe, "scorer_multi": gen_scorer_multi, "init": gen_init}
+            "scorer": gen_scorer, "scorer_pe": gen_scorer_pe, "scorer_multi": gen_scorer_multi, "slates": gen_slates, "init": gen_init}
     for name in (sys.argv[1:] or list(gens)):      # optionally: only the named generators
         gens[name]()
