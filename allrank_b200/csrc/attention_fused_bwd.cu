@@ -16,7 +16,13 @@
 // chunks accumulate in TMEM across key tiles.  TMEM columns: S^T [0,128) dP^T [128,256) dV [256..) dK [320..)
 // dQ0 [384..) dQ1 [448..).
 //   warp 0: TMA producer   warp 1: TMEM alloc + MMA issue   warps 2-9: 256 compute/epilogue threads
-//   (warp w owns TMEM lanes 32*(w%4).., query-column half (w-2)/4).
+//   (warp w owns TMEM lanes 32*(w%4).., and 32 of the 64 query columns of each half: sub = (w-2)/4).
+//
+// Each 128-query chunk is processed as two 64-column HALVES (a, b) that are software-pipelined against each other:
+// while the 256 compute threads turn half b's S^T / dP^T into P^T / dS^T, the tensor core runs half a's dV / dK
+// products and already produces half a's S^T / dP^T of the NEXT iteration in the columns that just became free; the
+// dQ product (which contracts over all 128 keys and needs both halves staged) trails half b.  The compute threads
+// therefore never sit behind an MMA round trip except in the pipeline prologue.
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -99,13 +105,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
   uint8_t* stage = smem + BwdSmem::STAGE_OFF;
   float2* qstats = reinterpret_cast<float2*>(smem + BwdSmem::STATS_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS_OFF);
-  uint64_t* kv_bar = bars;          // K/V tiles of this key tile landed        (one phase per key tile)
+  uint64_t* kv_bar = bars;          // K-major K/V tiles of this key tile landed (one phase per key tile)
   uint64_t* q_bar = bars + 1;       // K-major Q/dO tiles of this iteration landed (one phase per iteration)
-  uint64_t* s_bar = bars + 2;       // S^T and dP^T complete                      (per iteration)
-  uint64_t* p_bar = bars + 3;       // P^T / dS^T written by the 256 compute threads (per iteration)
-  uint64_t* mma_bar = bars + 4;     // trailing MMAs (dV, dK, dQ) complete        (per iteration)
-  uint64_t* qm_bar = bars + 5;      // MN-major Q/dO tiles of this iteration landed (one phase per iteration)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* s_bar = bars + 2;       // [2] S^T and dP^T of half a / b complete    (per iteration)
+  uint64_t* p_bar = bars + 4;       // [2] P^T / dS^T of half a / b written by the 256 compute threads (per iteration)
+  uint64_t* mma_bar = bars + 6;     // all trailing MMAs (dV, dK, dQ) of the iteration complete
+  uint64_t* qm_bar = bars + 7;      // MN-major Q/dO tiles of this iteration landed (one phase per iteration)
+  uint64_t* km_bar = bars + 8;      // MN-major K tile of this key tile landed   (one phase per key tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x, b = blockIdx.y;
@@ -118,9 +125,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     ptx::mbar_init(kv_bar, 1);
     ptx::mbar_init(q_bar, 1);
     ptx::mbar_init(s_bar, 1);
+    ptx::mbar_init(s_bar + 1, 1);
     ptx::mbar_init(p_bar, 256);
+    ptx::mbar_init(p_bar + 1, 256);
     ptx::mbar_init(mma_bar, 1);
     ptx::mbar_init(qm_bar, 1);
+    ptx::mbar_init(km_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -137,23 +147,26 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       int it = 0;
       for (int jt = 0; jt < n_kt; ++jt) {
         for (int qc = 0; qc < n_kt; ++qc, ++it) {
-          // The K-major Q/dO tiles are read only by the S^T / dP^T MMAs, so they can be refilled as soon as the
-          // previous iteration's S^T / dP^T have completed -- i.e. while its compute phase and trailing MMAs run.
-          if (it > 0) ptx::mbar_wait(s_bar, (it - 1) & 1);
+          // The K-major tiles are read only by the S^T / dP^T MMAs, so they can be refilled as soon as the previous
+          // iteration's second half of S^T / dP^T has completed -- i.e. while its compute phases and trailing MMAs run.
+          if (it > 0) ptx::mbar_wait(s_bar + 1, (it - 1) & 1);
           ptx::mbar_expect_tx(q_bar, 2 * TILE_BYTES);
           ptx::tma_load_4d(tile(BwdSmem::Q_KM), &tmQk, q_bar, 0, 128 * qc, head, b);
           ptx::tma_load_4d(tile(BwdSmem::DO_KM), &tmDOk, q_bar, 0, 128 * qc, head, b);
-          // everything else is still in use by the trailing MMAs (dV, dK, dQ) of the previous iteration
-          if (it > 0) ptx::mbar_wait(mma_bar, (it - 1) & 1);
           if (qc == 0) {
-            ptx::mbar_expect_tx(kv_bar, 3 * TILE_BYTES);
+            ptx::mbar_expect_tx(kv_bar, 2 * TILE_BYTES);
             ptx::tma_load_4d(tile(BwdSmem::K_KM), &tmKk, kv_bar, 0, 128 * jt, head, b);
-            ptx::tma_load_4d(tile(BwdSmem::K_MN), &tmKm, kv_bar, 0, 128 * jt, head, b);
             ptx::tma_load_4d(tile(BwdSmem::V_KM), &tmVk, kv_bar, 0, 128 * jt, head, b);
           }
+          // the MN-major tiles are still in use by the trailing MMAs (dV, dK, dQ) of the previous iteration
+          if (it > 0) ptx::mbar_wait(mma_bar, (it - 1) & 1);
           ptx::mbar_expect_tx(qm_bar, 2 * TILE_BYTES);
           ptx::tma_load_4d(tile(BwdSmem::Q_MN), &tmQm, qm_bar, 0, 128 * qc, head, b);
           ptx::tma_load_4d(tile(BwdSmem::DO_MN), &tmDOm, qm_bar, 0, 128 * qc, head, b);
+          if (qc == 0) {
+            ptx::mbar_expect_tx(km_bar, TILE_BYTES);
+            ptx::tma_load_4d(tile(BwdSmem::K_MN), &tmKm, km_bar, 0, 128 * jt, head, b);
+          }
         }
       }
     }
@@ -162,7 +175,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     if (lane == 0) {
       constexpr int KSTEPS = (DK + 7) / 8;                 // contraction steps over the head width
       constexpr int DKN = DK < 16 ? 16 : DK;               // UMMA N of the dk-wide outputs
-      const uint32_t id_st = ptx::idesc_tf32(128, 128, 0, 0);
       const uint32_t id_ts = ptx::idesc_tf32(128, DKN, 0, 1);     // A from TMEM, B MN-major
       const uint32_t id_dq = ptx::idesc_tf32(128, DKN, 1, 1);     // A MN-major (staged dS^T), B MN-major
       const uint32_t kk = ptx::smem_u32(tile(BwdSmem::K_KM)), km = ptx::smem_u32(tile(BwdSmem::K_MN));
@@ -170,38 +182,54 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       const uint32_t qk = ptx::smem_u32(tile(BwdSmem::Q_KM)), qm = ptx::smem_u32(tile(BwdSmem::Q_MN));
       const uint32_t dok = ptx::smem_u32(tile(BwdSmem::DO_KM)), dom = ptx::smem_u32(tile(BwdSmem::DO_MN));
       const uint32_t sg = ptx::smem_u32(stage);
+      const uint32_t id_sh = ptx::idesc_tf32(128, 64, 0, 0);      // one 64-query half of S^T / dP^T
+      const int n_it = n_kt * n_kt;
+      // S^T / dP^T of half `hf` of iteration `t` (queries 64*hf.. of the chunk: rows 64*hf.. of the K-major Q / dO tiles)
+      auto issue_scores = [&](int t, int hf) {
+        if (hf == 0) {
+          if (t % n_kt == 0) ptx::mbar_wait(kv_bar, (t / n_kt) & 1);
+          ptx::mbar_wait(q_bar, t & 1);
+          ptx::tc_fence_after();
+        }
+        for (int k = 0; k < KSTEPS; ++k) {
+          ptx::mma_tf32_ss(T_ST + 64 * hf, ptx::smem_desc_sw128<2>(kk + k * 32, 16, 1024),
+                           ptx::smem_desc_sw128<2>(qk + hf * 8192 + k * 32, 16, 1024), id_sh, k > 0);
+        }
+        for (int k = 0; k < KSTEPS; ++k) {
+          ptx::mma_tf32_ss(T_DPT + 64 * hf, ptx::smem_desc_sw128<2>(vk + k * 32, 16, 1024),
+                           ptx::smem_desc_sw128<2>(dok + hf * 8192 + k * 32, 16, 1024), id_sh, k > 0);
+        }
+        ptx::mma_commit(s_bar + hf);
+      };
+      issue_scores(0, 0);
+      issue_scores(0, 1);
       int it = 0;
       for (int jt = 0; jt < n_kt; ++jt) {
         for (int qc = 0; qc < n_kt; ++qc, ++it) {
-          if (qc == 0) ptx::mbar_wait(kv_bar, jt & 1);
-          ptx::mbar_wait(q_bar, it & 1);
-          ptx::tc_fence_after();
-          for (int k = 0; k < KSTEPS; ++k) {
-            ptx::mma_tf32_ss(T_ST, ptx::smem_desc_sw128<2>(kk + k * 32, 16, 1024),
-                             ptx::smem_desc_sw128<2>(qk + k * 32, 16, 1024), id_st, k > 0);
+          for (int hf = 0; hf < 2; ++hf) {
+            ptx::mbar_wait(p_bar + hf, it & 1);
+            if (hf == 0) ptx::mbar_wait(qm_bar, it & 1);
+            ptx::tc_fence_after();
+            for (int i = 8 * hf; i < 8 * hf + 8; ++i) {     // contraction over the 64 queries of this half
+              ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, ptx::smem_desc_sw128<1>(dom + i * 1024, TILE_BYTES, 512), id_ts,
+                               (qc > 0 || i > 0) ? 1u : 0u);
+            }
+            for (int i = 8 * hf; i < 8 * hf + 8; ++i) {
+              ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, ptx::smem_desc_sw128<1>(qm + i * 1024, TILE_BYTES, 512), id_ts,
+                               (qc > 0 || i > 0) ? 1u : 0u);
+            }
+            if (hf == 1) {
+              if (qc == 0) ptx::mbar_wait(km_bar, jt & 1);
+              for (int i = 0; i < 16; ++i) {     // dQ: contraction over the 128 keys of this tile, both halves staged
+                ptx::mma_tf32_ss(T_DQ0 + 64 * qc, ptx::smem_desc_sw128<1>(sg + i * 1024, TILE_BYTES, 512),
+                                 ptx::smem_desc_sw128<1>(km + i * 1024, TILE_BYTES, 512), id_dq,
+                                 (jt > 0 || i > 0) ? 1u : 0u);
+              }
+              ptx::mma_commit(mma_bar);
+            }
+            // the columns of this half are free again: produce the next iteration's scores behind the products above
+            if (it + 1 < n_it) issue_scores(it + 1, hf);
           }
-          for (int k = 0; k < KSTEPS; ++k) {
-            ptx::mma_tf32_ss(T_DPT, ptx::smem_desc_sw128<2>(vk + k * 32, 16, 1024),
-                             ptx::smem_desc_sw128<2>(dok + k * 32, 16, 1024), id_st, k > 0);
-          }
-          ptx::mma_commit(s_bar);
-          ptx::mbar_wait(p_bar, it & 1);
-          ptx::mbar_wait(qm_bar, it & 1);
-          ptx::tc_fence_after();
-          for (int i = 0; i < 16; ++i) {     // contraction over the 128 queries of this chunk
-            ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, ptx::smem_desc_sw128<1>(dom + i * 1024, TILE_BYTES, 512), id_ts,
-                             (qc > 0 || i > 0) ? 1u : 0u);
-          }
-          for (int i = 0; i < 16; ++i) {
-            ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, ptx::smem_desc_sw128<1>(qm + i * 1024, TILE_BYTES, 512), id_ts,
-                             (qc > 0 || i > 0) ? 1u : 0u);
-          }
-          for (int i = 0; i < 16; ++i) {     // contraction over the 128 keys of this tile
-            ptx::mma_tf32_ss(T_DQ0 + 64 * qc, ptx::smem_desc_sw128<1>(sg + i * 1024, TILE_BYTES, 512),
-                             ptx::smem_desc_sw128<1>(km + i * 1024, TILE_BYTES, 512), id_dq,
-                             (jt > 0 || i > 0) ? 1u : 0u);
-          }
-          ptx::mma_commit(mma_bar);
         }
       }
     }
@@ -210,8 +238,66 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const int ct = threadIdx.x - 64;            // 0..255
     const int quad = warp & 3;
     const int row = 32 * quad + lane;           // key row inside the tile == TMEM lane
-    const int half = (warp - 2) >> 2;           // which 64 query columns of the chunk this warp handles
+    const int sub = (warp - 2) >> 2;            // which 32 of the 64 query columns of a half this warp handles
     const uint32_t lane_addr = uint32_t(32 * quad) << 16;
+
+    // Outputs of iteration `e_it` that became final with it: dV / dK of its key tile after the last query chunk, dQ of
+    // its query chunk after the last key tile.  TMEM -> swizzled staging -> TMA store (+ the QKV bias column sums).
+    auto epilogue = [&](int e_it) {
+      const int e_jt = e_it / n_kt, e_qc = e_it % n_kt;
+      const bool last_qc = (e_qc == n_kt - 1), last_jt = (e_jt == n_kt - 1);
+      if (!(last_qc || last_jt)) return;
+      // up to 3 output tiles; the warps with sub == 0 read the TMEM lanes (DK <= 32 columns per tile)
+      for (int which = 0; which < 3; ++which) {
+        const bool do_it = (which < 2) ? last_qc : last_jt;
+        if (!do_it) continue;
+        const uint32_t src = which == 0 ? T_DV : (which == 1 ? T_DK : T_DQ0 + 64 * e_qc);
+        const float mul = which == 0 ? 1.0f : scale;
+        if (sub == 0) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(src + lane_addr, v);
+          ptx::tmem_ld_wait();
+          uint8_t* orow = stage + which * TILE_BYTES + row * 128;
+#pragma unroll
+          for (int piece = 0; piece < 8; ++piece) {
+            float4 o;
+            o.x = __uint_as_float(v[piece * 4 + 0]) * mul;
+            o.y = __uint_as_float(v[piece * 4 + 1]) * mul;
+            o.z = __uint_as_float(v[piece * 4 + 2]) * mul;
+            o.w = __uint_as_float(v[piece * 4 + 3]) * mul;
+            *reinterpret_cast<float4*>(orow + ((piece ^ (row & 7)) << 4)) = o;
+          }
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::named_bar_sync(1, 256);
+      if (dbias_qkv != nullptr && ct < 96) {
+        // bias gradient of the QKV projection: column sums of the staged dV / dK / dQ tiles (rows past S are 0)
+        const int which = ct >> 5, cc = ct & 31;
+        const bool live = (which < 2) ? last_qc : last_jt;
+        if (live && cc < DK) {
+          const uint8_t* tl = stage + which * TILE_BYTES;
+          float t = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 128; ++r)
+            t += *reinterpret_cast<const float*>(tl + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
+          const int off = (which == 0 ? 2 * d_model : (which == 1 ? d_model : 0)) + head * DK + cc;
+          atomicAdd(dbias_qkv + off, t);
+        }
+      }
+      if (ct == 0) {
+        if (last_qc) {
+          ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * e_jt, head, b);
+          ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES, 0, 128 * e_jt, head, b);
+        }
+        if (last_jt) ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES, 0, 128 * e_qc, head, b);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_read();      // the staging slabs are rewritten right after this
+      }
+      ptx::named_bar_sync(1, 256);       // column sums read + TMA reads finished before anyone overwrites the slabs
+    };
+
     int it = 0;
     for (int jt = 0; jt < n_kt; ++jt) {
       const int key = 128 * jt + row;
@@ -230,11 +316,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           qstats[ct] = st;
         }
         ptx::named_bar_sync(1, 256);
-        ptx::mbar_wait(s_bar, it & 1);
-        ptx::tc_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int col0 = 64 * half + 32 * cc;           // first query column of this 32-wide piece
+        for (int hf = 0; hf < 2; ++hf) {
+          ptx::mbar_wait(s_bar + hf, it & 1);
+          ptx::tc_fence_after();
+          const int col0 = 64 * hf + 32 * sub;            // first query column of this warp's 32-wide piece
           uint32_t sv[32], dv[32];
           ptx::tmem_ld_32x32(T_ST + lane_addr + col0, sv);
           ptx::tmem_ld_32x32(T_DPT + lane_addr + col0, dv);
@@ -257,6 +343,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           }
           ptx::tmem_st_32x32(T_ST + lane_addr + col0, sv);
           ptx::tmem_st_32x32(T_DPT + lane_addr + col0, dv);
+          if (hf == 0 && it > 0) {
+            // The staging slabs still feed the previous iteration's dQ product (and hold its output tiles): wait for
+            // its trailing MMAs -- they ran behind this half's arithmetic -- and flush what became final.
+            ptx::mbar_wait(mma_bar, (it - 1) & 1);
+            ptx::tc_fence_after();
+            epilogue(it - 1);
+          }
           // dS^T also goes to shared memory as the MN-major A operand of dQ: slab = 32-query group, row = key
           uint8_t* srow = stage + (col0 >> 5) * TILE_BYTES + row * 128;
 #pragma unroll
@@ -265,70 +358,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
             *reinterpret_cast<uint4*>(srow + phys) =
                 make_uint4(dv[piece * 4], dv[piece * 4 + 1], dv[piece * 4 + 2], dv[piece * 4 + 3]);
           }
-        }
-        ptx::tmem_st_wait();
-        ptx::fence_proxy_async_smem();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(p_bar);
-
-        const bool last_qc = (qc == n_kt - 1);
-        const bool last_jt = (jt == n_kt - 1);
-        if (last_qc || last_jt) {
-          // ---- epilogue(s): accumulators that are now final
-          ptx::mbar_wait(mma_bar, it & 1);
-          ptx::tc_fence_after();
-          // up to 3 output tiles: dV_jt, dK_jt (when last_qc) and dQ_qc (when last_jt); warps of column-half 0
-          // read TMEM lanes, half 1 idles (DK <= 32 columns per tile)
-          for (int which = 0; which < 3; ++which) {
-            const bool do_it = (which < 2) ? last_qc : last_jt;
-            if (!do_it) continue;
-            const uint32_t src = which == 0 ? T_DV : (which == 1 ? T_DK : T_DQ0 + 64 * qc);
-            const float mul = which == 0 ? 1.0f : scale;
-            if (half == 0) {
-              uint32_t v[32];
-              ptx::tmem_ld_32x32(src + lane_addr, v);
-              ptx::tmem_ld_wait();
-              uint8_t* orow = stage + which * TILE_BYTES + row * 128;
-#pragma unroll
-              for (int piece = 0; piece < 8; ++piece) {
-                float4 o;
-                o.x = __uint_as_float(v[piece * 4 + 0]) * mul;
-                o.y = __uint_as_float(v[piece * 4 + 1]) * mul;
-                o.z = __uint_as_float(v[piece * 4 + 2]) * mul;
-                o.w = __uint_as_float(v[piece * 4 + 3]) * mul;
-                *reinterpret_cast<float4*>(orow + ((piece ^ (row & 7)) << 4)) = o;
-              }
-            }
-          }
+          ptx::tmem_st_wait();
           ptx::fence_proxy_async_smem();
-          ptx::named_bar_sync(1, 256);
-          if (dbias_qkv != nullptr && ct < 96) {
-            // bias gradient of the QKV projection: column sums of the staged dV / dK / dQ tiles (rows past S are 0)
-            const int which = ct >> 5, cc = ct & 31;
-            const bool live = (which < 2) ? last_qc : last_jt;
-            if (live && cc < DK) {
-              const uint8_t* tl = stage + which * TILE_BYTES;
-              float t = 0.f;
-#pragma unroll 8
-              for (int r = 0; r < 128; ++r)
-                t += *reinterpret_cast<const float*>(tl + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
-              const int off = (which == 0 ? 2 * d_model : (which == 1 ? d_model : 0)) + head * DK + cc;
-              atomicAdd(dbias_qkv + off, t);
-            }
-          }
-          if (ct == 0) {
-            if (last_qc) {
-              ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * jt, head, b);
-              ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES, 0, 128 * jt, head, b);
-            }
-            if (last_jt) ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES, 0, 128 * qc, head, b);
-            ptx::tma_store_commit();
-            ptx::tma_store_wait_read();      // staging is reused by the next iteration
-          }
           ptx::tc_fence_before();
+          ptx::mbar_arrive(p_bar + hf);
         }
       }
     }
+    ptx::mbar_wait(mma_bar, (it - 1) & 1);
+    ptx::tc_fence_after();
+    epilogue(it - 1);
+    ptx::tc_fence_before();
     if (ct == 0) ptx::tma_store_wait_all();
   }
   __syncthreads();
