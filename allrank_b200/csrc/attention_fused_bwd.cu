@@ -15,11 +15,12 @@
 // over 128-key tiles (outer) and 128-query chunks (inner); dV/dK accumulate in TMEM across query chunks, the two dQ
 // chunks accumulate in TMEM across key tiles.  TMEM columns: S^T [0,128) dP^T [128,256) dV [256..) dK [320..)
 // dQ0 [384..) dQ1 [448..).
-//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issue   warps 2-9: 256 compute/epilogue threads
-//   (warp w owns TMEM lanes 32*(w%4).., and 32 of the 64 query columns of each half: sub = (w-2)/4).
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issue   warps 2-17: 512 compute/epilogue threads
+//   (warp w owns TMEM lanes 32*(w%4).., and 16 of the 64 query columns of each half: sub = (w-2)/4; four warps per
+//   scheduler hide the TMEM / shared-memory / MUFU latencies of the element-wise work).
 //
 // Each 128-query chunk is processed as two 64-column HALVES (a, b) that are software-pipelined against each other:
-// while the 256 compute threads turn half b's S^T / dP^T into P^T / dS^T, the tensor core runs half a's dV / dK
+// while the 512 compute threads turn half b's S^T / dP^T into P^T / dS^T, the tensor core runs half a's dV / dK
 // products and already produces half a's S^T / dP^T of the NEXT iteration in the columns that just became free; the
 // dQ product (which contracts over all 128 keys and needs both halves staged) trails half b.  The compute threads
 // therefore never sit behind an MMA round trip except in the pipeline prologue.
@@ -35,7 +36,8 @@
 
 namespace arb {
 
-constexpr int BWD_THREADS = 320;
+constexpr int BWD_COMPUTE = 512;              // 16 compute warps: four per TMEM lane quadrant
+constexpr int BWD_THREADS = 64 + BWD_COMPUTE;
 constexpr int TILE_BYTES = 128 * 128;     // one [128 rows][128 B] operand tile
 
 __device__ __forceinline__ float ex2_approx_b(float x) {
@@ -84,8 +86,8 @@ struct BwdSmem {
   static constexpr int N_TILES = 7;
   static constexpr int STAGE_OFF = N_TILES * TILE_BYTES;          // dS^T staging: 4 slabs x [128 key rows][128 B]
   static constexpr int STAGE_BYTES = 4 * TILE_BYTES;
-  static constexpr int STATS_OFF = STAGE_OFF + STAGE_BYTES;       // float2 {nm_q, delta_q} x 128
-  static constexpr int BARS_OFF = STATS_OFF + 128 * 8;
+  static constexpr int STATS_OFF = STAGE_OFF + STAGE_BYTES;       // float2 {nm_q, delta_q} x 128, double-buffered
+  static constexpr int BARS_OFF = STATS_OFF + 2 * 128 * 8;
   static constexpr int total() { return BARS_OFF + 256 + 1024; }
 };
 
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
   uint64_t* kv_bar = bars;          // K-major K/V tiles of this key tile landed (one phase per key tile)
   uint64_t* q_bar = bars + 1;       // K-major Q/dO tiles of this iteration landed (one phase per iteration)
   uint64_t* s_bar = bars + 2;       // [2] S^T and dP^T of half a / b complete    (per iteration)
-  uint64_t* p_bar = bars + 4;       // [2] P^T / dS^T of half a / b written by the 256 compute threads (per iteration)
+  uint64_t* p_bar = bars + 4;       // [2] P^T / dS^T of half a / b written by the 512 compute threads (per iteration)
   uint64_t* mma_bar = bars + 6;     // all trailing MMAs (dV, dK, dQ) of the iteration complete
   uint64_t* qm_bar = bars + 7;      // MN-major Q/dO tiles of this iteration landed (one phase per iteration)
   uint64_t* km_bar = bars + 8;      // MN-major K tile of this key tile landed   (one phase per key tile)
@@ -126,8 +128,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     ptx::mbar_init(q_bar, 1);
     ptx::mbar_init(s_bar, 1);
     ptx::mbar_init(s_bar + 1, 1);
-    ptx::mbar_init(p_bar, 256);
-    ptx::mbar_init(p_bar + 1, 256);
+    ptx::mbar_init(p_bar, BWD_COMPUTE);
+    ptx::mbar_init(p_bar + 1, BWD_COMPUTE);
     ptx::mbar_init(mma_bar, 1);
     ptx::mbar_init(qm_bar, 1);
     ptx::mbar_init(km_bar, 1);
@@ -184,20 +186,25 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       const uint32_t sg = ptx::smem_u32(stage);
       const uint32_t id_sh = ptx::idesc_tf32(128, 64, 0, 0);      // one 64-query half of S^T / dP^T
       const int n_it = n_kt * n_kt;
-      // S^T / dP^T of half `hf` of iteration `t` (queries 64*hf.. of the chunk: rows 64*hf.. of the K-major Q / dO tiles)
+      // Descriptors are built once; the k-steps of a family differ only by the start-address field (units of 16 B):
+      // +2 per 32-byte k-step of a K-major tile, +64 per 1024-byte k-step of an MN-major tile, +512 for rows 64..127.
+      const uint64_t d_kk = ptx::smem_desc_sw128<2>(kk, 16, 1024), d_vk = ptx::smem_desc_sw128<2>(vk, 16, 1024);
+      const uint64_t d_qk = ptx::smem_desc_sw128<2>(qk, 16, 1024), d_dok = ptx::smem_desc_sw128<2>(dok, 16, 1024);
+      const uint64_t d_dom = ptx::smem_desc_sw128<1>(dom, TILE_BYTES, 512), d_qm = ptx::smem_desc_sw128<1>(qm, TILE_BYTES, 512);
+      const uint64_t d_sg = ptx::smem_desc_sw128<1>(sg, TILE_BYTES, 512), d_km = ptx::smem_desc_sw128<1>(km, TILE_BYTES, 512);
+      // S^T / dP^T of half `hf` of iteration `t` (queries 64*hf.. of the chunk: rows 64*hf.. of the K-major Q / dO
+      // tiles); the two independent accumulators are interleaved so that consecutive MMAs never depend on each other
       auto issue_scores = [&](int t, int hf) {
         if (hf == 0) {
           if (t % n_kt == 0) ptx::mbar_wait(kv_bar, (t / n_kt) & 1);
           ptx::mbar_wait(q_bar, t & 1);
           ptx::tc_fence_after();
         }
+        const uint64_t hoff = uint64_t(hf) * 512;
+#pragma unroll
         for (int k = 0; k < KSTEPS; ++k) {
-          ptx::mma_tf32_ss(T_ST + 64 * hf, ptx::smem_desc_sw128<2>(kk + k * 32, 16, 1024),
-                           ptx::smem_desc_sw128<2>(qk + hf * 8192 + k * 32, 16, 1024), id_sh, k > 0);
-        }
-        for (int k = 0; k < KSTEPS; ++k) {
-          ptx::mma_tf32_ss(T_DPT + 64 * hf, ptx::smem_desc_sw128<2>(vk + k * 32, 16, 1024),
-                           ptx::smem_desc_sw128<2>(dok + hf * 8192 + k * 32, 16, 1024), id_sh, k > 0);
+          ptx::mma_tf32_ss(T_ST + 64 * hf, d_kk + 2 * k, d_qk + hoff + 2 * k, id_sh, k > 0);
+          ptx::mma_tf32_ss(T_DPT + 64 * hf, d_vk + 2 * k, d_dok + hoff + 2 * k, id_sh, k > 0);
         }
         ptx::mma_commit(s_bar + hf);
       };
@@ -206,40 +213,55 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       int it = 0;
       for (int jt = 0; jt < n_kt; ++jt) {
         for (int qc = 0; qc < n_kt; ++qc, ++it) {
-          for (int hf = 0; hf < 2; ++hf) {
-            ptx::mbar_wait(p_bar + hf, it & 1);
-            if (hf == 0) ptx::mbar_wait(qm_bar, it & 1);
-            ptx::tc_fence_after();
-            for (int i = 8 * hf; i < 8 * hf + 8; ++i) {     // contraction over the 64 queries of this half
-              ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, ptx::smem_desc_sw128<1>(dom + i * 1024, TILE_BYTES, 512), id_ts,
-                               (qc > 0 || i > 0) ? 1u : 0u);
-            }
-            for (int i = 8 * hf; i < 8 * hf + 8; ++i) {
-              ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, ptx::smem_desc_sw128<1>(qm + i * 1024, TILE_BYTES, 512), id_ts,
-                               (qc > 0 || i > 0) ? 1u : 0u);
-            }
-            if (hf == 1) {
-              if (qc == 0) ptx::mbar_wait(km_bar, jt & 1);
-              for (int i = 0; i < 16; ++i) {     // dQ: contraction over the 128 keys of this tile, both halves staged
-                ptx::mma_tf32_ss(T_DQ0 + 64 * qc, ptx::smem_desc_sw128<1>(sg + i * 1024, TILE_BYTES, 512),
-                                 ptx::smem_desc_sw128<1>(km + i * 1024, TILE_BYTES, 512), id_dq,
-                                 (jt > 0 || i > 0) ? 1u : 0u);
-              }
-              ptx::mma_commit(mma_bar);
-            }
-            // the columns of this half are free again: produce the next iteration's scores behind the products above
-            if (it + 1 < n_it) issue_scores(it + 1, hf);
+          const uint32_t acc_kv = qc > 0 ? 1u : 0u, acc_q = jt > 0 ? 1u : 0u;
+          // ---- half a: dV / dK over its 64 queries, then the next iteration's half-a scores into the freed columns
+          ptx::mbar_wait(p_bar, it & 1);
+          ptx::mbar_wait(qm_bar, it & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, d_dom + 64 * i, id_ts, i > 0 ? 1u : acc_kv);
+            ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, d_qm + 64 * i, id_ts, i > 0 ? 1u : acc_kv);
           }
+          if (it + 1 < n_it) issue_scores(it + 1, 0);
+          // ---- half b: dV / dK, the next half-b scores, and dQ (contracts over all 128 keys: both halves staged)
+          ptx::mbar_wait(p_bar + 1, it & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int i = 8; i < 16; ++i) {
+            ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, d_dom + 64 * i, id_ts, 1u);
+            ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, d_qm + 64 * i, id_ts, 1u);
+          }
+          if (it + 1 < n_it) issue_scores(it + 1, 1);
+          if (qc == 0) ptx::mbar_wait(km_bar, jt & 1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            ptx::mma_tf32_ss(T_DQ0 + 64 * qc, d_sg + 64 * i, d_km + 64 * i, id_dq, i > 0 ? 1u : acc_q);
+          ptx::mma_commit(mma_bar);
         }
       }
     }
   } else {
-    // ===================== compute + epilogue (256 threads) =====================
-    const int ct = threadIdx.x - 64;            // 0..255
+    // ===================== compute + epilogue (512 threads) =====================
+    const int ct = threadIdx.x - 64;            // 0..511
     const int quad = warp & 3;
     const int row = 32 * quad + lane;           // key row inside the tile == TMEM lane
-    const int sub = (warp - 2) >> 2;            // which 32 of the 64 query columns of a half this warp handles
+    const int sub = (warp - 2) >> 2;            // which 16 of the 64 query columns of a half this warp handles
     const uint32_t lane_addr = uint32_t(32 * quad) << 16;
+    const int n_it = n_kt * n_kt;
+
+    // per-query statistics of iteration t's chunk -> smem buffer t&1 (nm = -max*c - log2(sum); -inf for rows past S)
+    auto load_stats = [&](int t, int slot) {
+      const int qi = 128 * (t % n_kt) + slot;
+      float2 st = make_float2(-CUDART_INF_F, 0.f);
+      if (qi < S) {
+        const size_t so = (size_t(b) * n_heads + head) * S + qi;
+        st.x = -(stat_max[so] * c_log2e) - log2f(stat_sum[so]);
+        st.y = delta[so];
+      }
+      qstats[(t & 1) * 128 + slot] = st;
+    };
+    if (ct < 128) load_stats(0, ct);
 
     // Outputs of iteration `e_it` that became final with it: dV / dK of its key tile after the last query chunk, dQ of
     // its query chunk after the last key tile.  TMEM -> swizzled staging -> TMA store (+ the QKV bias column sums).
@@ -247,45 +269,27 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       const int e_jt = e_it / n_kt, e_qc = e_it % n_kt;
       const bool last_qc = (e_qc == n_kt - 1), last_jt = (e_jt == n_kt - 1);
       if (!(last_qc || last_jt)) return;
-      // up to 3 output tiles; the warps with sub == 0 read the TMEM lanes (DK <= 32 columns per tile)
-      for (int which = 0; which < 3; ++which) {
-        const bool do_it = (which < 2) ? last_qc : last_jt;
-        if (!do_it) continue;
-        const uint32_t src = which == 0 ? T_DV : (which == 1 ? T_DK : T_DQ0 + 64 * e_qc);
-        const float mul = which == 0 ? 1.0f : scale;
-        if (sub == 0) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(src + lane_addr, v);
-          ptx::tmem_ld_wait();
-          uint8_t* orow = stage + which * TILE_BYTES + row * 128;
+      // up to 3 output tiles of DK <= 32 columns, one per warp group: sub 0 -> dV, sub 1 -> dK, sub 2 -> dQ
+      if (sub < 3 && ((sub < 2) ? last_qc : last_jt)) {
+        const uint32_t src = sub == 0 ? T_DV : (sub == 1 ? T_DK : T_DQ0 + 64 * e_qc);
+        const float mul = sub == 0 ? 1.0f : scale;
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(src + lane_addr, v);
+        ptx::tmem_ld_wait();
+        uint8_t* orow = stage + sub * TILE_BYTES + row * 128;
 #pragma unroll
-          for (int piece = 0; piece < 8; ++piece) {
-            float4 o;
-            o.x = __uint_as_float(v[piece * 4 + 0]) * mul;
-            o.y = __uint_as_float(v[piece * 4 + 1]) * mul;
-            o.z = __uint_as_float(v[piece * 4 + 2]) * mul;
-            o.w = __uint_as_float(v[piece * 4 + 3]) * mul;
-            *reinterpret_cast<float4*>(orow + ((piece ^ (row & 7)) << 4)) = o;
-          }
+        for (int piece = 0; piece < 8; ++piece) {
+          float4 o;
+          o.x = __uint_as_float(v[piece * 4 + 0]) * mul;
+          o.y = __uint_as_float(v[piece * 4 + 1]) * mul;
+          o.z = __uint_as_float(v[piece * 4 + 2]) * mul;
+          o.w = __uint_as_float(v[piece * 4 + 3]) * mul;
+          *reinterpret_cast<float4*>(orow + ((piece ^ (row & 7)) << 4)) = o;
         }
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
-      ptx::named_bar_sync(1, 256);
-      if (dbias_qkv != nullptr && ct < 96) {
-        // bias gradient of the QKV projection: column sums of the staged dV / dK / dQ tiles (rows past S are 0)
-        const int which = ct >> 5, cc = ct & 31;
-        const bool live = (which < 2) ? last_qc : last_jt;
-        if (live && cc < DK) {
-          const uint8_t* tl = stage + which * TILE_BYTES;
-          float t = 0.f;
-#pragma unroll 8
-          for (int r = 0; r < 128; ++r)
-            t += *reinterpret_cast<const float*>(tl + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
-          const int off = (which == 0 ? 2 * d_model : (which == 1 ? d_model : 0)) + head * DK + cc;
-          atomicAdd(dbias_qkv + off, t);
-        }
-      }
+      ptx::named_bar_sync(1, BWD_COMPUTE);
       if (ct == 0) {
         if (last_qc) {
           ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * e_jt, head, b);
@@ -293,9 +297,27 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         }
         if (last_jt) ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES, 0, 128 * e_qc, head, b);
         ptx::tma_store_commit();
-        ptx::tma_store_wait_read();      // the staging slabs are rewritten right after this
       }
-      ptx::named_bar_sync(1, 256);       // column sums read + TMA reads finished before anyone overwrites the slabs
+      if (dbias_qkv != nullptr && ct < 384) {
+        // bias gradient of the QKV projection: column sums of the staged dV / dK / dQ tiles (rows past S are 0);
+        // 96 columns x 4 row segments, the 4 partial sums sit in adjacent lanes
+        const int col = ct >> 2, seg = ct & 3;
+        const int which = col >> 5, cc = col & 31;
+        const bool live = ((which < 2) ? last_qc : last_jt) && cc < DK;
+        float t = 0.f;
+        if (live) {
+          const uint8_t* tl = stage + which * TILE_BYTES;
+#pragma unroll 8
+          for (int r = 32 * seg; r < 32 * seg + 32; ++r)
+            t += *reinterpret_cast<const float*>(tl + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
+        }
+        t += __shfl_xor_sync(FULL, t, 1);
+        t += __shfl_xor_sync(FULL, t, 2);
+        if (live && seg == 0)
+          atomicAdd(dbias_qkv + (which == 0 ? 2 * d_model : (which == 1 ? d_model : 0)) + head * DK + cc, t);
+      }
+      if (ct == 0) ptx::tma_store_wait_read();      // the staging slabs are rewritten right after this
+      ptx::named_bar_sync(1, BWD_COMPUTE);  // column sums read + TMA reads finished before anyone overwrites the slabs
     };
 
     int it = 0;
@@ -303,31 +325,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       const int key = 128 * jt + row;
       const bool key_ok = key < S && mask[size_t(b) * S + key] == 0;
       for (int qc = 0; qc < n_kt; ++qc, ++it) {
-        // per-query statistics of this chunk -> smem (nm = -max*c - log2(sum); -inf for query rows past S)
-        if (it > 0) ptx::named_bar_sync(1, 256);          // everyone finished reading the previous chunk's stats
-        if (ct < 128) {
-          const int qi = 128 * qc + ct;
-          float2 st = make_float2(-CUDART_INF_F, 0.f);
-          if (qi < S) {
-            const size_t so = (size_t(b) * n_heads + head) * S + qi;
-            st.x = -(stat_max[so] * c_log2e) - log2f(stat_sum[so]);
-            st.y = delta[so];
-          }
-          qstats[ct] = st;
-        }
-        ptx::named_bar_sync(1, 256);
+        ptx::named_bar_sync(1, BWD_COMPUTE);     // this chunk's statistics are in place; iteration it-1 is fully read
+        if (it + 1 < n_it && ct >= 128 && ct < 256) load_stats(it + 1, ct - 128);   // prefetch behind the arithmetic
+        const float2* qs = qstats + (it & 1) * 128;
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {
           ptx::mbar_wait(s_bar + hf, it & 1);
           ptx::tc_fence_after();
-          const int col0 = 64 * hf + 32 * sub;            // first query column of this warp's 32-wide piece
-          uint32_t sv[32], dv[32];
-          ptx::tmem_ld_32x32(T_ST + lane_addr + col0, sv);
-          ptx::tmem_ld_32x32(T_DPT + lane_addr + col0, dv);
+          const int col0 = 64 * hf + 16 * sub;            // first query column of this warp's 16-wide piece
+          uint32_t sv[16], dv[16];
+          ptx::tmem_ld_32x16(T_ST + lane_addr + col0, sv);
+          ptx::tmem_ld_32x16(T_DPT + lane_addr + col0, dv);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 st = qstats[col0 + j];
+          for (int j = 0; j < 16; ++j) {
+            const float2 st = qs[col0 + j];
             const float p = key_ok ? ex2_approx_b(fmaf(__uint_as_float(sv[j]), c_log2e, st.x)) : 0.0f;
             float p_used = p, dp = __uint_as_float(dv[j]);
             if constexpr (DROP) {        // regenerate the forward's dropout mask on the probabilities
@@ -341,8 +353,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
             sv[j] = round_tf32_b(p_used);
             dv[j] = round_tf32_b(ds);
           }
-          ptx::tmem_st_32x32(T_ST + lane_addr + col0, sv);
-          ptx::tmem_st_32x32(T_DPT + lane_addr + col0, dv);
+          ptx::tmem_st_32x16(T_ST + lane_addr + col0, sv);
+          ptx::tmem_st_32x16(T_DPT + lane_addr + col0, dv);
           if (hf == 0 && it > 0) {
             // The staging slabs still feed the previous iteration's dQ product (and hold its output tiles): wait for
             // its trailing MMAs -- they ran behind this half's arithmetic -- and flush what became final.
@@ -352,11 +364,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           }
           // dS^T also goes to shared memory as the MN-major A operand of dQ: slab = 32-query group, row = key
           uint8_t* srow = stage + (col0 >> 5) * TILE_BYTES + row * 128;
+          const int p0 = (col0 & 31) >> 2;                // first 16-byte piece of these 16 columns in the slab row
 #pragma unroll
-          for (int piece = 0; piece < 8; ++piece) {
+          for (int k = 0; k < 4; ++k) {
+            const int piece = p0 + k;
             const int phys = (((piece >> 1) ^ (row & 3)) << 5) + ((piece & 1) << 4);
-            *reinterpret_cast<uint4*>(srow + phys) =
-                make_uint4(dv[piece * 4], dv[piece * 4 + 1], dv[piece * 4 + 2], dv[piece * 4 + 3]);
+            *reinterpret_cast<uint4*>(srow + phys) = make_uint4(dv[k * 4], dv[k * 4 + 1], dv[k * 4 + 2], dv[k * 4 + 3]);
           }
           ptx::tmem_st_wait();
           ptx::fence_proxy_async_smem();
