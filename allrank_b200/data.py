@@ -10,7 +10,7 @@ follows the same rules with a counter-hash stream instead of numpy's.
 Same call surface as the reference module:
 
     train_ds, val_ds = load_libsvm_dataset(input_path, slate_length, validation_ds_role)    # :206-217
-    n_features = train_ds.shape[-1]                                                         # main.py:62
+    n_features = train_ds.shape[-1]                                                         # main.py:63
     train_dl, val_dl = create_data_loaders(train_ds, val_ds, num_workers, batch_size)       # :230-247
     for xb, yb, indices in train_dl: ...                                                    # train_utils.py:93-96
 
