@@ -205,3 +205,57 @@ def test_rank_slates_and_epoch_metrics_with_a_model(store):
     pos_scores = torch.arange(ry.shape[1], 0, -1, dtype=torch.float32).expand_as(ry).cuda()
     again = metrics.ndcg(pos_scores, ry.cuda(), ats=ats).mean(dim=0).cpu().numpy()
     assert np.allclose(again, ref_ndcg, rtol=1e-6)
+
+
+def test_config1_training_loop_matches_the_oracle(store):
+    """BASELINE configs[0] in miniature (FC-only scorer + listNet + Adam + StepLR, the reference's CPU-runnable case,
+    SURVEY 8c "end-to-end anchor"): the device pipeline (SlateStore loader -> fused scorer -> fused listNet -> Adam ->
+    one-pass epoch metrics) follows the eager oracle (FixLength padding -> nn.Module -> listNet -> ndcg) step by step."""
+    from oracle import losses_ref, metrics_ref
+    from oracle.scorer_ref import make_ref_model
+    from allrank_b200 import losses, training
+    from allrank_b200.data import DeviceSlateLoader
+    from allrank_b200.model import make_model
+    F, S = store.n_features, store.longest_query_length        # every query padded (validation-style): no sampling
+    torch.manual_seed(42)
+    ref = make_ref_model(F, [64], 0, 0, 0).train()
+    mine = make_model(fc_model={"sizes": [64], "input_norm": False, "activation": None, "dropout": 0.0},
+                      transformer=None, post_model={"d_output": 1, "output_activation": None}, n_features=F)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.cuda().train()
+    groups = host_groups(store)
+    padded = [slates_ref.fix_length(xs, ys, S) if len(ys) < S else (xs, ys, np.arange(S)) for xs, ys in groups]
+    X = torch.tensor(np.stack([p[0] for p in padded]), dtype=torch.float32)
+    Y = torch.tensor(np.stack([p[1] for p in padded]), dtype=torch.float32)
+    I = torch.tensor(np.stack([p[2] for p in padded]), dtype=torch.long)
+    bs = 4
+    dl = DeviceSlateLoader(store, batch_size=bs, slate_length=S, shuffle=False)
+    # the longest query is "sampled" (a permutation) on both sides: take the device loader's order for it
+    for bi, (xb, yb, ib) in enumerate(dl):
+        for r in range(xb.shape[0]):
+            q = bi * bs + r
+            if len(groups[q][1]) == S:
+                X[q], Y[q], I[q] = xb[r].cpu(), yb[r].cpu(), ib[r].cpu()
+            else:
+                assert torch.equal(xb[r].cpu(), X[q]) and torch.equal(yb[r].cpu(), Y[q]) and torch.equal(ib[r].cpu(), I[q])
+    o_ref = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    o_mine = torch.optim.Adam(mine.parameters(), lr=1e-3)
+    s_ref = torch.optim.lr_scheduler.StepLR(o_ref, step_size=3, gamma=0.5)
+    s_mine = torch.optim.lr_scheduler.StepLR(o_mine, step_size=3, gamma=0.5)
+    for epoch in range(4):
+        mine.train(); ref.train()
+        for bi in range(0, len(groups), bs):
+            xb, yb, ib = X[bi:bi + bs], Y[bi:bi + bs], I[bi:bi + bs]
+            l_ref = losses_ref.listNet(ref(xb, yb == -1, ib), yb)
+            l_ref.backward(); o_ref.step(); o_ref.zero_grad()
+            l_mine = losses.listNet(mine(xb.cuda(), (yb == -1).cuda(), ib.cuda()), yb.cuda())
+            l_mine.backward(); o_mine.step(); o_mine.zero_grad()
+            assert l_mine.item() == pytest.approx(l_ref.item(), rel=2e-3, abs=2e-3), (epoch, bi)
+        s_ref.step(); s_mine.step()
+    mine.eval(); ref.eval()
+    with torch.no_grad():
+        ref_ndcg = torch.mean(torch.cat([metrics_ref.ndcg(ref.score(X[b:b + bs], Y[b:b + bs] == -1, I[b:b + bs]),
+                                                          Y[b:b + bs], ats=[5]) for b in range(0, len(groups), bs)]), dim=0)
+        batches = [(X[b:b + bs].cuda(), Y[b:b + bs].cuda(), I[b:b + bs].cuda()) for b in range(0, len(groups), bs)]
+        got = training.compute_metrics({"ndcg": [5]}, mine, batches, torch.device("cuda"))
+    assert got["ndcg_5"] == pytest.approx(ref_ndcg.item(), abs=2e-2)     # small slates: one TF32-induced swap moves it
