@@ -27,6 +27,8 @@
 namespace arb {
 
 constexpr int ATT_THREADS = 192;
+constexpr int ATT2_SOFTMAX = 256;              // two-pass kernel: 8 softmax warps, two per TMEM lane quadrant
+constexpr int ATT2_THREADS = 64 + ATT2_SOFTMAX;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -235,9 +237,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
 // 128-key chunks into a 128-column TMEM window, twice: pass A only takes the row maximum, pass B recomputes the chunk
 // (K = dk, a handful of MMAs), exponentiates against the final maximum, writes P in place and accumulates O += P V.
 // TMEM: S chunk [0,128) + O [128,128+DK) -> 256 columns; shared memory 96 KB -> two co-resident CTAs overlap each
-// other's load / MMA / softmax phases.  Head width <= 32.
+// other's load / MMA / softmax phases.  Head width <= 32.  Eight softmax warps per CTA: a warp may only touch the 32
+// TMEM lanes of its quadrant, so two warps share each quadrant and split every 32-key chunk 16 / 16; the two partial
+// row maxima (after pass A) and row sums (after pass B) are combined through shared memory.
 template <int DK, bool DROP>
-__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ,
+__global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                    const __grid_constant__ CUtensorMap tmK,
                                                                    const __grid_constant__ CUtensorMap tmV,
                                                                    const __grid_constant__ CUtensorMap tmO,
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd2_kernel(const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(o_s + L::O_BYTES);
   uint64_t* load_bar = bars;
   uint64_t* s_bar = bars + 1;       // a score chunk is complete            (one phase per step)
-  uint64_t* t_bar = bars + 2;       // the 128 softmax threads are done with the chunk (one phase per step)
+  uint64_t* t_bar = bars + 2;       // the 256 softmax threads are done with the chunk (one phase per step)
   uint64_t* o_bar = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   uint32_t* mask_bits = tmem_slot + 2;
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd2_kernel(const __grid_
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmO);
     ptx::mbar_init(load_bar, 1);
     ptx::mbar_init(s_bar, 1);
-    ptx::mbar_init(t_bar, 128);
+    ptx::mbar_init(t_bar, ATT2_SOFTMAX);
     ptx::mbar_init(o_bar, 1);
     ptx::fence_barrier_init();
   }
@@ -334,48 +338,60 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd2_kernel(const __grid_
       ptx::mma_commit(o_bar);
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                     // TMEM lane quadrant
+    const int sub = (warp - 2) >> 2;            // which 16 keys of every 32-key chunk this warp handles
     const int row = 32 * q + lane;
     const int qidx = m0 + row;
     const uint32_t lane_addr = uint32_t(32 * q) << 16;
+    float* xch_max = reinterpret_cast<float*>(o_s);     // [2][128] partial maxima (the O staging is idle until the end)
+    float* xch_sum = reinterpret_cast<float*>(k_s);     // [2][128] partial sums   (K is dead after the last score chunk)
     float mx = -CUDART_INF_F, sum = 0.f, mxs = 0.f;
     for (int st = 0; st < nsteps; ++st) {
       const int kc = st % nkc;
       const bool pass_b = st >= nkc;
-      if (st == nkc) mxs = mx * scale_log2e;
+      if (st == nkc) {                          // pass A done: combine the two partial row maxima
+        xch_max[sub * 128 + row] = mx;
+        ptx::named_bar_sync(1, ATT2_SOFTMAX);
+        mx = fmaxf(xch_max[row], xch_max[128 + row]);
+        mxs = mx * scale_log2e;
+      }
       ptx::mbar_wait(s_bar, st & 1);
       ptx::tc_fence_after();
       const int keys = min(128, S8 - 128 * kc);
       const int nch = (keys + 31) / 32;
       for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_S + lane_addr + 32 * c, v);
+        uint32_t v[16];
+        const int col = 32 * c + 16 * sub;
+        ptx::tmem_ld_32x16(tmem_S + lane_addr + col, v);
         ptx::tmem_ld_wait();
-        const uint32_t bits = mask_bits[4 * kc + c];
+        const uint32_t bits = mask_bits[4 * kc + c] >> (16 * sub);
         if (!pass_b) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < 16; ++j)
             if (bits & (1u << j)) mx = fmaxf(mx, __uint_as_float(v[j]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 16; ++j) {
             float e = (bits & (1u << j)) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs)) : 0.0f;
             sum += e;
             if constexpr (DROP) {
               const unsigned long long idx =
-                  ((unsigned long long)(b * n_heads + head) * S + qidx) * (unsigned long long)S + (128 * kc + 32 * c + j);
+                  ((unsigned long long)(b * n_heads + head) * S + qidx) * (unsigned long long)S + (128 * kc + col + j);
               e = drop_keep(idx, drop.seed, drop.thresh) ? e * drop.scale : 0.0f;
             }
             v[j] = round_tf32(e);
           }
-          ptx::tmem_st_32x32(tmem_S + lane_addr + 32 * c, v);
+          ptx::tmem_st_32x16(tmem_S + lane_addr + col, v);
         }
       }
       if (pass_b) ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(t_bar);
     }
-    if (qidx < S) {
+    xch_sum[sub * 128 + row] = sum;             // every score MMA has completed: the K tile is free
+    ptx::named_bar_sync(1, ATT2_SOFTMAX);
+    sum = xch_sum[row] + xch_sum[128 + row];
+    if (sub == 0 && qidx < S) {
       const size_t so = (size_t(b) * n_heads + head) * S + qidx;
       stat_max[so] = mx;
       stat_sum[so] = sum;
@@ -384,22 +400,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd2_kernel(const __grid_
     ptx::mbar_wait(o_bar, 0);
     ptx::tc_fence_after();
     {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32(tmem_O + lane_addr, v);
+      uint32_t v[16];                           // this warp's 16 of the (up to) 32 output columns
+      ptx::tmem_ld_32x16(tmem_O + lane_addr + 16 * sub, v);
       ptx::tmem_ld_wait();
       uint8_t* slab_row = o_s + row * 128;
 #pragma unroll
-      for (int piece = 0; piece < 8; ++piece) {
+      for (int k = 0; k < 4; ++k) {
+        const int piece = 4 * sub + k;
         float4 o;
-        o.x = __uint_as_float(v[piece * 4 + 0]) * inv;
-        o.y = __uint_as_float(v[piece * 4 + 1]) * inv;
-        o.z = __uint_as_float(v[piece * 4 + 2]) * inv;
-        o.w = __uint_as_float(v[piece * 4 + 3]) * inv;
+        o.x = __uint_as_float(v[k * 4 + 0]) * inv;
+        o.y = __uint_as_float(v[k * 4 + 1]) * inv;
+        o.z = __uint_as_float(v[k * 4 + 2]) * inv;
+        o.w = __uint_as_float(v[k * 4 + 3]) * inv;
         *reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4)) = o;
       }
     }
     ptx::fence_proxy_async_smem();
-    ptx::named_bar_sync(1, 128);
+    ptx::named_bar_sync(1, ATT2_SOFTMAX);
     if (threadIdx.x == 64) {
       ptx::tma_store_4d(&tmO, o_s, 0, m0, head, b);
       ptx::tma_store_commit();
@@ -448,7 +465,8 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   {
     ProfScope ps(ARB_PROF_GEMM, 4.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
                  4.0 * double(a.B) * a.h * a.S * (4.0 * a.dk + 2.0));
-    kern<<<grid, ATT_THREADS, L::total(), st>>>(tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
+    const int threads = (DK <= 32 && g_attn_fwd_two_pass) ? ATT2_THREADS : ATT_THREADS;
+    kern<<<grid, threads, L::total(), st>>>(tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
                                                a.scale * 1.4426950408889634f, a.drop);
   }
   arb_count_launch();
