@@ -38,6 +38,42 @@ def main():
             metrics.ranking(s, y)
         torch.cuda.synchronize()
         print("ok", (F, d, N, h, dff, B, S, p), float(loss))
+    next_rows()
+
+
+def next_rows():
+    """The SURVEY 8(f) kernels: remaining losses, multi-output head + ordinal, positional encodings, slate movers."""
+    import numpy as np
+    from allrank_b200 import data, inference
+    x, y, idx = make_slates(3, 50, 20, seed=2, mean_len=30, std_len=12)
+    x, y, idx = x.cuda(), y.cuda(), idx.cuda()
+    for n_out, act, pe in [(4, "Sigmoid", None), (3, None, {"strategy": "learned", "max_indices": 40}),
+                           (1, None, {"strategy": "fixed", "max_indices": 40})]:
+        for tr in ({"N": 1, "d_ff": 64, "h": 2, "positional_encoding": pe, "dropout": 0.1}, None):
+            model = make_model(fc_model={"sizes": [32], "input_norm": False, "activation": None, "dropout": 0.1},
+                               transformer=tr, post_model={"d_output": n_out, "output_activation": act},
+                               n_features=20).cuda().train()
+            out = model(x, y == -1, idx)
+            if n_out > 1 and act == "Sigmoid":
+                losses.ordinal(out, y, n=n_out).backward()
+            else:
+                out.sum().backward()
+            with torch.no_grad():
+                model.eval().score(x, y == -1, idx)
+    s = torch.randn(y.shape, device="cuda", requires_grad=True)
+    for fn, kw in [(losses.rankNet, {}), (losses.rankNet_weightByGTDiff_pow, {}), (losses.binary_listNet, {}),
+                   (losses.pointwise_rmse, {"no_of_levels": 4}), (losses.neuralNDCG_transposed, {})]:
+        fn(s, y, **kw).backward()
+    losses.bce(torch.sigmoid(s), (y > 0).float()).backward()
+    rng = np.random.RandomState(0)
+    lens = [3, 40, 17, 64, 1]
+    store = data.SlateStore(rng.randn(sum(lens), 20).astype(np.float32), rng.randint(0, 3, sum(lens)).astype(np.float32),
+                            np.repeat(np.arange(len(lens)), lens), device="cuda")
+    for S in (8, 17, 64, 100):
+        xb, yb, ib = store.assemble(torch.tensor([0, 1, 2, 3, 4, 3]), S, seed=S)
+        inference.reorder_slates(xb, yb, metrics.ranking(torch.randn(yb.shape, device="cuda"), yb))
+    torch.cuda.synchronize()
+    print("ok next rows")
 
 
 if __name__ == "__main__":
