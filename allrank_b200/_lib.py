@@ -52,6 +52,9 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        # A/B switches for measurements (include/allrank_b200.h); the defaults are the measured-fastest settings
+        if os.environ.get("ARB_GEMM_PERSISTENT") in ("0", "1", "2"):
+            handle.arb_set_gemm_persistent(int(os.environ["ARB_GEMM_PERSISTENT"]))
     return _lib
 
 

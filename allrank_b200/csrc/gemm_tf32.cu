@@ -585,10 +585,12 @@ int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32, int as_tf32)
   return ARB_OK;
 }
 
-// Measured on B200 (cfg2, B=1024): the one-CTA-per-tile kernel with 3 co-resident CTAs per SM is faster (5.7 ms of
-// GEMM time per step) than the persistent pipeline (6.6 ms with 8 epilogue warps): the persistent epilogue is the
-// bottleneck.  Kept opt-in for the next round (profiles/README.md).
-static int g_persistent = 0;
+// Measured per launch on B200 (cfg2, B=4096, profiles/r1_gemm_persistent_vs_tiled.csv): the persistent pipeline wins
+// where the contraction is long (K >= 256: W2 forward 520 -> 477 us, dX = dH W1 458 -> 426 us, dX = dQKV Wqkv
+// 411 -> 332 us), loses on the short-K, write-heavy linears (QKV 601 -> 748 us, W1 786 -> 995 us: its epilogue is the
+// critical path, while three co-resident one-tile CTAs overlap three epilogues) and ties on the split-K weight
+// gradients.  Mode 2 (default) therefore picks it only for non-split contractions with K >= 256.
+static int g_persistent = 2;   // 0: never, 1: wherever supported, 2: auto
 void set_gemm_persistent(int on) { g_persistent = on; }
 
 template <int BLOCK_N, int A_MN, int B_MN>
@@ -611,7 +613,10 @@ static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const C
   const long long n_tiles = (long long)tiles.x * tiles.y * tiles.z;
   const int grid = int(std::min<long long>(n_tiles, n_sm));
   {
-    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * double(d.nb2) * double(d.nb3), st);
+    const double nb = double(d.nb2) * double(d.nb3);
+    const double has_x = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) ? 1.0 : 0.0;
+    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
+                 4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N));
     kern<<<grid, PERSIST_THREADS, smem, st>>>(tA, tB, tC, tX, p, int(tiles.x), int(tiles.y), int(tiles.z));
   }
   arb_count_launch();
@@ -623,7 +628,9 @@ static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const C
 template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
-  if (g_persistent && !(p.flags & EPI_COLSUM)) return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
+  const bool long_k = !(A_MN == 1 && B_MN == 1) && !(p.flags & EPI_ATOMIC) && d.K >= 256 && d.nb2 == 1 && d.nb3 == 1;
+  if ((g_persistent == 1 || (g_persistent == 2 && long_k)) && !(p.flags & EPI_COLSUM))
+    return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
   // dropout epilogue is a separate instantiation (forward linears only) so the common path carries no mask code;
   // ring depth: 4 stages for the long split-K loops of the weight gradients (1 CTA/SM), 3 for K >= 256
   // (2 CTAs/SM), 2 for the short contractions (3-4 CTAs/SM)

@@ -201,8 +201,9 @@ void arb_set_attention_mode(int32_t mode);
  * 0: the single-pass kernel that keeps the whole S x S tile in TMEM (one CTA per SM). For A/B measurements. */
 void arb_set_attention_fwd_two_pass(int32_t on);
 
-/* 1: persistent, decoupled-pipeline GEMM kernel (one CTA per SM walking all tiles); 0 (default): one CTA per tile.
- * Process-wide; exists for A/B measurements. */
+/* GEMM kernel choice.  0: one CTA per output tile everywhere; 1: the persistent, decoupled-pipeline kernel (one CTA per
+ * SM walking all tiles) wherever it is supported; 2 (default): persistent only for non-split contractions with
+ * K >= 256, where it measured faster.  Process-wide; exists for A/B measurements. */
 void arb_set_gemm_persistent(int32_t on);
 
 /* 1 (default): MMA operands are rounded fp32 -> tf32 by the TMA unit (TFLOAT32 tensor maps); 0: the tensor core

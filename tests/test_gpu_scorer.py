@@ -356,3 +356,34 @@ def test_ordinal_training_matches_reference_trajectory():
     assert (s_ref - s_mine.cpu()).abs().max() <= SCORE_TOL * n
     assert torch.isfinite(metrics.ndcg(s_mine, yc, ats=[5])).all()
 
+
+
+def test_gemm_kernel_choice_does_not_change_results(golden):
+    """arb_set_gemm_persistent: 0 = one CTA per tile, 1 = the persistent pipeline wherever supported, 2 = auto (default:
+    persistent for K >= 256).  Same tiles, same k order: scores and gradients agree to rounding in all three modes,
+    with dropout off and on (the mask is a pure function of the element index)."""
+    from allrank_b200 import _lib
+    g = golden("scorer_cfg2")
+    x, y = torch.tensor(g["x"]).cuda(), torch.tensor(g["y"]).cuda()
+    w = torch.tensor(g["w"]).cuda()
+    mask = y == -1
+    results = {}
+    try:
+        for mode in (0, 1, 2):
+            _lib.lib().arb_set_gemm_persistent(mode)
+            for p_drop in (0.0, 0.2):
+                model = build(g).train()
+                model.dropout_p = p_drop
+                torch.manual_seed(77)
+                scores = model(x, mask, None)
+                (scores * w).sum().backward()
+                results[(mode, p_drop)] = (scores.detach().clone(), [p.grad.clone() for p in model.parameters()])
+    finally:
+        _lib.lib().arb_set_gemm_persistent(2)
+    for p_drop in (0.0, 0.2):
+        base_s, base_g = results[(0, p_drop)]
+        for mode in (1, 2):
+            s, gr = results[(mode, p_drop)]
+            assert torch.allclose(s, base_s, rtol=1e-5, atol=1e-6), (mode, p_drop)
+            for a, b in zip(gr, base_g):
+                assert (a - b).abs().max() <= 1e-4 * max(b.abs().max().item(), 1e-6), (mode, p_drop)
