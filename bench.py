@@ -344,7 +344,10 @@ def run_b200(args, w):
             "bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05.mma kind::tf32)",
             "achieved": achieved_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / tf32_peak if tf32_peak else None,
-            "traffic": None,
+            "traffic": measured_traffic(args, B),
+            "traffic_note": "DRAM read+write bytes of the class's launches in one step (ncu dram__bytes_{read,write}.sum, "
+                            "profiles/r1_dram_traffic_b4096.json: 66.8 GB vs 67.7 GB algorithmic at batch 4096); null when "
+                            "this run's workload/batch has no committed capture",
             "peak_source": f"{peaks['source']}: MEASURED_PEAKS bf16_tflops_sustained={peaks['bf16_tflops_sustained']} / 2 "
                            "(kind::tf32 issues at half the bf16 rate)",
             "frac_of_bf16_peak": achieved_tflops / peaks["bf16_tflops_sustained"],
@@ -378,6 +381,19 @@ def run_b200(args, w):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measured_traffic(args, batch):
+    """DRAM bytes per step of the tcgen05 class from the committed ncu capture of this exact workload / batch."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dram_traffic_b4096.json")
+    try:
+        with open(path) as f:
+            cap = json.load(f)
+    except (OSError, ValueError):
+        return None
+    if args.workload == "cfg2" and int(batch) == int(cap.get("batch", -1)):
+        return cap.get("tcgen05_dram_bytes_per_step")
+    return None
 
 
 def main():
