@@ -8,10 +8,30 @@ on the device; the returned dict has the reference's keys ("ndcg_5", ...) and nu
 """
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import metrics as metrics_module
 
 PADDED_Y_VALUE = -1
+
+
+def reduce_epoch_sums(totals, count, group=None):
+    """Data-parallel evaluation (one process per GPU, each scoring its own shard of the loader): sum the per-metric
+    running sums and the slate count over all ranks in ONE small all-reduce, so that every rank
+    returns the mean over the whole loader.  No-op without an initialised process group / with a single rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return totals, count
+    names = list(totals)
+    ref = totals[names[0]]
+    flat = torch.cat([totals[n].reshape(-1).double() for n in names] +
+                     [torch.tensor([float(count)], dtype=torch.float64, device=ref.device)])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    out, at = {}, 0
+    for n in names:
+        k = totals[n].numel()
+        out[n] = flat[at:at + k].reshape(totals[n].shape)
+        at += k
+    return out, int(round(flat[at].item()))
 
 
 def metric_on_batch(metric, model, xb, yb, indices):
@@ -28,7 +48,8 @@ def metric_on_epoch(metric, model, dl, dev):
         part = vals.double().sum(dim=0)
         total = part if total is None else total + part
         count += vals.shape[0]
-    return (total / count).float().cpu().numpy()
+    sums, count = reduce_epoch_sums({"m": total}, count)
+    return (sums["m"] / count).float().cpu().numpy()
 
 
 def compute_metrics(metrics, model, dl, dev):
@@ -45,6 +66,7 @@ def compute_metrics(metrics, model, dl, dev):
             part = vals.double().sum(dim=0)
             totals[name] = part if totals[name] is None else totals[name] + part
         count += yb.shape[0]
+    totals, count = reduce_epoch_sums(totals, count)
     out = {}
     for name, ats in names:
         values = (totals[name] / count).float().cpu().numpy()
@@ -52,4 +74,4 @@ def compute_metrics(metrics, model, dl, dev):
     return out
 
 
-__all__ = ["metric_on_batch", "metric_on_epoch", "compute_metrics"]
+__all__ = ["metric_on_batch", "metric_on_epoch", "compute_metrics", "reduce_epoch_sums"]

@@ -100,3 +100,40 @@ def test_flat_bucket_allreduce_matches_single_process():
     assert torch.allclose(summed * scale, single["mean"], rtol=1e-5, atol=1e-7)
     scale, summed = results["sum_folded"]
     assert scale == 1.0
+
+
+def _metric_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from allrank_b200.training import reduce_epoch_sums
+    g = torch.Generator().manual_seed(5)
+    rows = torch.rand(10, 3, generator=g).double()          # per-slate metric rows of the WHOLE loader
+    mine = rows[:7] if rank == 0 else rows[7:]                # uneven shards: 7 + 3 slates
+    totals, count = reduce_epoch_sums({"ndcg": mine.sum(0), "mrr": 2 * mine.sum(0)}, mine.shape[0])
+    out_q.put((rank, totals["ndcg"] / count, totals["mrr"] / count, count, rows.mean(0)))
+    dist.destroy_process_group()
+
+
+def test_epoch_metric_sums_reduce_to_the_whole_loader_mean():
+    """Each rank scores its shard; one all-reduce of (sums, count) gives every rank the mean over all slates --
+    what train_utils.metric_on_epoch's torch.mean(torch.cat(...)) returns in a single process (train_utils.py:37-43)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_metric_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ndcg, mrr, count, expect in got:
+        assert count == 10
+        assert torch.allclose(ndcg, expect) and torch.allclose(mrr, 2 * expect)
+
+
+def test_epoch_metric_reduce_is_a_no_op_without_a_process_group():
+    from allrank_b200.training import reduce_epoch_sums
+    t = {"ndcg": torch.tensor([1.0, 2.0])}
+    out, n = reduce_epoch_sums(t, 4)
+    assert out is t and n == 4
