@@ -111,3 +111,19 @@ def test_positional_encoding_state_dict_surface(golden, strategy):
                    transformer={"N": 1, "d_ff": 8, "h": 1, "dropout": 0.0,
                                 "positional_encoding": {"strategy": "rotary", "max_indices": 4}},
                    post_model={"d_output": 1, "output_activation": None}, n_features=F)
+
+
+def test_slate_movers_have_no_cpu_fallback():
+    """The callers either side of the path are CUDA-only like the path itself: CPU use raises, nothing falls back."""
+    import numpy as np
+    from allrank_b200 import _lib, data, inference, losses
+    with pytest.raises(_lib.ArbError):
+        data.SlateStore(np.zeros((3, 4), dtype=np.float32), np.zeros(3, dtype=np.float32), np.zeros(3), device="cpu")
+    with pytest.raises(Exception):
+        inference.reorder_slates(torch.zeros(1, 2, 4), torch.zeros(1, 2), torch.zeros(1, 2, dtype=torch.int32))
+    with pytest.raises(Exception):
+        losses.ordinal(torch.full((1, 2, 3), 0.5), torch.zeros(1, 2), n=3)
+    with pytest.raises(Exception):
+        losses.with_ordinals(torch.zeros(1, 2), 3)
+    with pytest.raises(ValueError):
+        data.DeviceSlateLoader(object(), batch_size=0, slate_length=4)
