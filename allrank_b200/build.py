@@ -31,7 +31,7 @@ def _fingerprint():
     files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [inc, os.path.abspath(__file__)]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())      # (not the absolute path: the tree moves between boxes)
             h.update(fh.read())
     return h.hexdigest()
 
