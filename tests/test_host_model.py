@@ -127,3 +127,22 @@ def test_slate_movers_have_no_cpu_fallback():
         losses.with_ordinals(torch.zeros(1, 2), 3)
     with pytest.raises(ValueError):
         data.DeviceSlateLoader(object(), batch_size=0, slate_length=4)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/allrank_b200.h is the drop-in boundary: it must compile as C99 (and C++) on its own and link against
+    the library -- no torch types, no C++-isms."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.c"
+    src.write_text('#include "allrank_b200.h"\n'
+                   'int main(void) { arb_scorer_config c; (void)c; return arb_abi_version() == 2 ? 0 : 1; }\n')
+    inc = os.path.join(root, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o",
+                    str(tmp_path / "t.o")], check=True)
+    if shutil.which("g++") is not None:
+        subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-x", "c++", "-c", str(src), "-o",
+                        str(tmp_path / "t2.o")], check=True)
