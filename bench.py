@@ -364,7 +364,8 @@ def run_b200(args, w):
                          "peak_gbs": peaks["hbm_gbs"],
                          "frac": (gemm.get("algorithmic_bytes_per_step", 0.0) / (gemm["ms_per_step"] * 1e-3) / 1e9) /
                                  peaks["hbm_gbs"] if gemm["ms_per_step"] > 0 else None,
-                         "algorithmic_bytes_per_step": gemm.get("algorithmic_bytes_per_step", 0.0)},
+                         "algorithmic_bytes_per_step": gemm.get("algorithmic_bytes_per_step", 0.0),
+                         "asymmetric": asymmetric_hbm_view(args, B, gemm["ms_per_step"])},
         },
         "kernel_classes": prof,
         "final_loss": final_loss,
@@ -383,17 +384,39 @@ def run_b200(args, w):
         dist.destroy_process_group()
 
 
-def measured_traffic(args, batch):
-    """DRAM bytes per step of the tcgen05 class from the committed ncu capture of this exact workload / batch."""
+def _traffic_capture(args, batch):
+    """The committed ncu capture of this exact workload / batch (profiles/r1_dram_traffic_b4096.json), else None."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dram_traffic_b4096.json")
     try:
         with open(path) as f:
             cap = json.load(f)
-    except (OSError, ValueError):
-        return None
-    if args.workload == "cfg2" and int(batch) == int(cap.get("batch", -1)):
-        return cap.get("tcgen05_dram_bytes_per_step")
+        if args.workload == "cfg2" and int(batch) == int(cap.get("batch", -1)):
+            return cap
+    except (OSError, ValueError, TypeError):
+        pass
     return None
+
+
+def measured_traffic(args, batch):
+    """DRAM bytes per step of the tcgen05 class from the committed ncu capture."""
+    cap = _traffic_capture(args, batch)
+    return cap.get("tcgen05_dram_bytes_per_step") if cap else None
+
+
+def asymmetric_hbm_view(args, batch, kernel_ms):
+    """HBM reads and writes do not cost the same on this part (profiles/README.md): the class's measured read / write
+    bytes against t = read/6.9 TB/s + write/3.25 TB/s, as a fraction of the class's measured time.  None without a
+    capture of this workload."""
+    try:
+        cap = _traffic_capture(args, batch)
+        if not cap or kernel_ms <= 0:
+            return None
+        rd, wr = float(cap["tcgen05_dram_read_bytes_per_step"]), float(cap["tcgen05_dram_write_bytes_per_step"])
+        bound_ms = (rd / (float(cap["read_gbs_model"]) * 1e9) + wr / (float(cap["write_gbs_model"]) * 1e9)) * 1e3
+        return {"read_bytes_per_step": rd, "write_bytes_per_step": wr, "bound_ms": bound_ms, "frac": bound_ms / kernel_ms,
+                "model": cap.get("model")}
+    except Exception:       # reporting extra only: never lose the bench line over it
+        return None
 
 
 def main():
