@@ -1,4 +1,4 @@
-"""In-tree build of the C-ABI CUDA library (sm_100a only) and of the oracle's native pieces.
+"""In-tree build of the C-ABI CUDA library (sm_100a only).  (The oracle is pure Python / PyTorch: nothing to compile.)
 
     python -m allrank_b200.build            # or __graft_entry__.build()
 
