@@ -113,9 +113,12 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_mma(const float* __restri
     // ---- exponentials, row sums, O = P V with the contraction index relabelled: A-fragment column t <-> key 2t,
     //      column t+4 <-> key 2t+1 of the 8-key group, so the accumulator registers ARE the A fragment
     float s0 = 0.f, s1 = 0.f;
-    float o[ND][4];
+    float o[ND][4], o2[ND][4];      // two accumulator sets (even / odd key groups): 8 independent MMA chains, not 4
 #pragma unroll
-    for (int nd = 0; nd < ND; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+    for (int nd = 0; nd < ND; ++nd) {
+      o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+      o2[nd][0] = o2[nd][1] = o2[nd][2] = o2[nd][3] = 0.f;
+    }
 #pragma unroll
     for (int kb = 0; kb < NT; ++kb) {
       const float e0 = ex2(acc[kb][0] - m0), e1 = ex2(acc[kb][1] - m0);
@@ -126,7 +129,14 @@ __global__ void __launch_bounds__(WARPS * 32) attn_fwd_mma(const float* __restri
       const uint32_t* v0 = Vs + (8 * kb + 2 * t) * PITCH + g;      // key 2t   -> k = t
       const uint32_t* v1 = v0 + PITCH;                             // key 2t+1 -> k = t+4
 #pragma unroll
-      for (int nd = 0; nd < ND; ++nd) mma(o[nd], a0, a1, a2, a3, v0[8 * nd], v1[8 * nd]);
+      for (int nd = 0; nd < ND; ++nd) {
+        if (kb & 1) mma(o2[nd], a0, a1, a2, a3, v0[8 * nd], v1[8 * nd]);
+        else mma(o[nd], a0, a1, a2, a3, v0[8 * nd], v1[8 * nd]);
+      }
+    }
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) {
+      o[nd][0] += o2[nd][0]; o[nd][1] += o2[nd][1]; o[nd][2] += o2[nd][2]; o[nd][3] += o2[nd][3];
     }
     s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
