@@ -14,7 +14,7 @@ void arb_set_error(const char* msg) {
 void arb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" const char* arb_last_error(void) { return g_err; }
-extern "C" int32_t arb_abi_version(void) { return 2; }
+extern "C" int32_t arb_abi_version(void) { return 3; }
 extern "C" int64_t arb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------- per-launch timing

@@ -34,7 +34,10 @@ static bool use_fused_bwd(const arb_scorer_config& c, int S) {
 static inline int n_outputs(const arb_scorer_config& c) { return c.d_output > 1 ? c.d_output : 1; }
 
 struct ParamLayout {
-  int64_t fc_w, fc_b;
+  int n_fc;                                  // FC layers (>= 1)
+  int fc_size[ARB_MAX_FC_LAYERS];            // output width of FC layer i; fc_size[n_fc-1] = d_model
+  int64_t fc_w[ARB_MAX_FC_LAYERS], fc_b[ARB_MAX_FC_LAYERS];
+  int64_t in_a, in_b;                        // nn.LayerNorm(F) of fc_model.input_norm (-1: none)
   struct Layer { int64_t wqkv, bqkv, wo, bo, w1, b1, w2, b2, ln1_a, ln1_b, ln2_a, ln2_b; };
   Layer layer[64];
   int64_t lnf_a, lnf_b, head_w, head_b, pe, total;
@@ -55,9 +58,26 @@ static int make_param_layout(const arb_scorer_config& c, ParamLayout& L) {
   }
   if (c.d_model > 1024) { arb_set_error("scorer: d_model above 1024 is not supported"); return ARB_E_UNSUPPORTED; }
   const int64_t d = c.d_model, F = c.n_features, f = c.d_ff;
+  L.n_fc = c.n_fc_layers > 0 ? c.n_fc_layers : 1;
+  if (L.n_fc > ARB_MAX_FC_LAYERS) { arb_set_error("scorer: at most 8 FC layers"); return ARB_E_UNSUPPORTED; }
+  for (int i = 0; i < L.n_fc; ++i) {
+    L.fc_size[i] = c.n_fc_layers > 0 ? c.fc_sizes[i] : c.d_model;
+    if (L.fc_size[i] <= 0 || L.fc_size[i] % 4 || L.fc_size[i] > 8192) {
+      arb_set_error("scorer: FC layer widths must be positive multiples of 4, at most 8192");
+      return ARB_E_UNSUPPORTED;
+    }
+  }
+  if (L.fc_size[L.n_fc - 1] != c.d_model) { arb_set_error("scorer: the last FC width must equal d_model"); return ARB_E_INVALID_ARG; }
+  if (c.fc_act < ARB_ACT_NONE || c.fc_act > ARB_ACT_RELU) { arb_set_error("scorer: unknown FC activation"); return ARB_E_UNSUPPORTED; }
+  if (c.fc_input_norm && F > 1024) { arb_set_error("scorer: input_norm supports up to 1024 features"); return ARB_E_UNSUPPORTED; }
   int64_t o = 0;
-  L.fc_w = o; o += d * F;
-  L.fc_b = o; o += d;
+  for (int i = 0; i < L.n_fc; ++i) {
+    const int64_t in = i == 0 ? F : L.fc_size[i - 1];
+    L.fc_w[i] = o; o += int64_t(L.fc_size[i]) * in;
+    L.fc_b[i] = o; o += L.fc_size[i];
+  }
+  L.in_a = L.in_b = -1;
+  if (c.fc_input_norm) { L.in_a = o; o += F; L.in_b = o; o += F; }
   for (int l = 0; l < c.n_layers; ++l) {
     auto& y = L.layer[l];
     y.wqkv = o; o += 3 * d * d;
@@ -92,6 +112,9 @@ static int make_param_layout(const arb_scorer_config& c, ParamLayout& L) {
 
 struct WsLayout {
   int64_t x0;
+  int64_t fch[ARB_MAX_FC_LAYERS];   // outputs of the FC layers before the last (training: kept for backward)
+  int64_t fc_last;                  // last FC output before the positional encoding overwrites x0 (activated FC + PE)
+  int64_t xnorm, in_mean, in_std;   // input_norm output and row statistics
   struct Layer { int64_t xn1, mean1, std1, qkv, prob, smax, ssum, ctx, xmid, xn2, mean2, std2, hdn, xout; };
   Layer layer[64];
   int64_t meanf, stdf, xf, total;   // xf: final-norm output, kept only for the multi-output head
@@ -99,13 +122,27 @@ struct WsLayout {
   bool fused;
 };
 
-static void make_ws_layout(const arb_scorer_config& c, int B, int S, int training, WsLayout& W) {
+static void make_ws_layout(const arb_scorer_config& c, const ParamLayout& L, int B, int S, int training, WsLayout& W) {
   const int64_t R = int64_t(B) * S, d = c.d_model, f = c.d_ff, h = c.n_heads;
   W.Sp = int(align_up(S, 4));
   W.fused = use_fused(c, S);
   int64_t o = 0;
   auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
   W.x0 = take(R * d);
+  {
+    int64_t ping[2] = {0, 0};
+    if (!training && L.n_fc > 1) {   // eval: two buffers of the widest hidden layer, used alternately
+      int64_t widest = 0;
+      for (int i = 0; i + 1 < L.n_fc; ++i) widest = std::max<int64_t>(widest, L.fc_size[i]);
+      ping[0] = take(R * widest);
+      ping[1] = L.n_fc > 2 ? take(R * widest) : ping[0];
+    }
+    for (int i = 0; i < ARB_MAX_FC_LAYERS; ++i)
+      W.fch[i] = (i + 1 < L.n_fc) ? (training ? take(R * L.fc_size[i]) : ping[i & 1]) : 0;
+  }
+  W.fc_last = (training && c.fc_act != ARB_ACT_NONE && c.pe_mode != 0) ? take(R * d) : 0;
+  W.xnorm = W.in_mean = W.in_std = 0;
+  if (c.fc_input_norm) { W.xnorm = take(R * c.n_features); W.in_mean = take(R); W.in_std = take(R); }
   WsLayout::Layer shared{};
   for (int l = 0; l < c.n_layers; ++l) {
     auto& y = W.layer[l];
@@ -221,7 +258,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   ParamLayout L;
   ARB_TRY(make_param_layout(c, L));
   WsLayout W;
-  make_ws_layout(c, B, S, training, W);
+  make_ws_layout(c, L, B, S, training, W);
   if (ws_floats < W.total) { arb_set_error("arb_scorer_forward: workspace too small"); return ARB_E_WORKSPACE; }
   Ctx k{c, B, S, int64_t(B) * S, st};
   const int d = c.d_model, F = c.n_features, f = c.d_ff, h = c.n_heads;
@@ -230,12 +267,34 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   // dropout follows the module's train()/eval() mode (the host zeroes these in eval); `training` only selects
   // whether activations are kept for a backward pass
   const float p_drop = c.dropout, p_fc = c.fc_dropout;
-  if (p_drop > 0.0f && c.n_layers > 0 && !use_fused_bwd(c, S)) {
-    arb_set_error("scorer: dropout > 0 needs the fused attention kernels (slate_length <= 256, head width <= 32)");
-    return ARB_E_UNSUPPORTED;
-  }
   float* xcur = ws + W.x0;
-  ARB_TRY(linear_fwd(k, x, F, F, P + L.fc_w, P + L.fc_b, d, xcur, d, 0, nullptr, 0, make_drop_site(seed, 0, SITE_FC, p_fc)));
+  {   // FCModel (model.py:35-44): [nn.LayerNorm(F)] then dropout(act(Linear)) per layer
+    const float* hin = x;
+    int in = F;
+    if (c.fc_input_norm) {
+      ARB_TRY(ln_forward(x, P + L.in_a, P + L.in_b, 1e-5f, k.R, F, ws + W.xnorm, ws + W.in_mean, ws + W.in_std, st, 1));
+      hin = ws + W.xnorm;
+    }
+    for (int i = 0; i < L.n_fc; ++i) {
+      const int out = L.fc_size[i];
+      const bool last = i + 1 == L.n_fc;
+      float* hout = last ? (W.fc_last ? ws + W.fc_last : xcur) : ws + W.fch[i];
+      const DropSite site = make_drop_site(seed, i, SITE_FC, p_fc);
+      if (c.fc_act == ARB_ACT_NONE || c.fc_act == ARB_ACT_RELU) {
+        ARB_TRY(linear_fwd(k, hin, in, in, P + L.fc_w[i], P + L.fc_b[i], out, hout, out,
+                           c.fc_act == ARB_ACT_RELU ? EPI_RELU : 0, nullptr, 0, site));
+      } else {
+        ARB_TRY(linear_fwd(k, hin, in, in, P + L.fc_w[i], P + L.fc_b[i], out, hout, out, 0, nullptr, 0));
+        ARB_TRY(act_forward(hout, k.R, out, c.fc_act, site, st));
+      }
+      hin = hout; in = out;
+    }
+    if (W.fc_last) {   // keep the activated FC output for backward: the positional encoding rewrites x0 in place
+      if (cudaMemcpyAsync(xcur, ws + W.fc_last, size_t(k.R) * d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        arb_set_error("scorer: device copy failed"); return ARB_E_CUDA;
+      }
+    }
+  }
   if (c.pe_mode != 0) {   // x = sqrt(d) x + pe[indices]   (transformer.py:51-52, positional.py)
     const float* table = c.pe_mode == 2 ? P + L.pe : pe_table;
     if (!indices || !table) { arb_set_error("scorer: positional encoding needs indices and a table"); return ARB_E_INVALID_ARG; }
@@ -269,7 +328,9 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
         batch_all(g, h, B); g.block_n = 64;
         ARB_TRY(launch_gemm_tf32(g, st));
       }
-      ARB_TRY(softmax_forward(prob, mask, B, h, S, W.Sp, st));   // key mask + softmax (transformer.py:150-153)
+      // key mask + softmax + dropout on the probabilities (transformer.py:150-155); with dropout the buffer holds the
+      // dropped probabilities (what P V needs) and the backward recomputes the undropped ones
+      ARB_TRY(softmax_forward(prob, mask, B, h, S, W.Sp, st, make_drop_site(seed, l, SITE_ATTN_P, p_drop)));
       {
         GemmDesc g;   // ctx = P V, written straight into the concatenated-heads layout (transformer.py:156, :201-202)
         g.M = S; g.N = dk; g.K = S; g.b_mn = 1;
@@ -304,8 +365,8 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   return ARB_OK;
 }
 
-struct ScratchLayout { int64_t dxa, dxb, dxn, dxm, dqkv, dctx, dprob, prob, delta, total; };
-static void make_scratch_layout(const arb_scorer_config& c, int B, int S, ScratchLayout& Z) {
+struct ScratchLayout { int64_t dxa, dxb, dxn, dxm, dqkv, dctx, dprob, prob, delta, dfa, dfb, total; };
+static void make_scratch_layout(const arb_scorer_config& c, const ParamLayout& L, int B, int S, ScratchLayout& Z) {
   const int64_t R = int64_t(B) * S, d = c.d_model;
   const int Sp = int(align_up(S, 4));
   int64_t o = 0;
@@ -321,6 +382,12 @@ static void make_scratch_layout(const arb_scorer_config& c, int B, int S, Scratc
   } else {
     Z.dqkv = Z.dctx = Z.dprob = Z.prob = Z.delta = 0;
   }
+  // FC-block backward: two gradient buffers of the widest tensor it differentiates through
+  int64_t widest = c.fc_input_norm ? c.n_features : 0;
+  for (int i = 0; i + 1 < L.n_fc; ++i) widest = std::max<int64_t>(widest, L.fc_size[i]);
+  if (c.fc_act != ARB_ACT_NONE) widest = std::max<int64_t>(widest, d);
+  Z.dfa = widest ? take(R * widest) : 0;
+  Z.dfb = widest ? take(R * widest) : 0;
   Z.total = o;
 }
 
@@ -331,9 +398,9 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   ParamLayout L;
   ARB_TRY(make_param_layout(c, L));
   WsLayout W;
-  make_ws_layout(c, B, S, 1, W);
+  make_ws_layout(c, L, B, S, 1, W);
   ScratchLayout Z;
-  make_scratch_layout(c, B, S, Z);
+  make_scratch_layout(c, L, B, S, Z);
   if (ws_floats < W.total) { arb_set_error("arb_scorer_backward: workspace too small"); return ARB_E_WORKSPACE; }
   if (scratch_floats < Z.total) { arb_set_error("arb_scorer_backward: scratch too small"); return ARB_E_WORKSPACE; }
   Ctx k{c, B, S, int64_t(B) * S, st};
@@ -349,17 +416,19 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   float* dxm = scratch + Z.dxm;      // dx seen through the dropout of the sublayer below (masked copy)
   const float p_drop = c.dropout, p_fc = c.fc_dropout;
   const bool drop_on = p_drop > 0.0f;
-  if (drop_on && c.n_layers > 0 && !use_fused_bwd(c, S)) {
-    arb_set_error("scorer: dropout > 0 needs the fused attention kernels (slate_length <= 256, head width <= 32)");
-    return ARB_E_UNSUPPORTED;
-  }
   // site whose mask the gradient of the residual stream must pass through right below the head / final norm
+  // The last FC layer's dropout mask (and its bias gradient) is folded into the kernel that emits the gradient of the
+  // FC output -- unless the FC block has an activation: then act_backward below does both.
+  const bool fc_act = c.fc_act != ARB_ACT_NONE;
+  const DropSite none_site{0u, 0u, 1.0f};
+  const DropSite fc_site = make_drop_site(seed, L.n_fc - 1, SITE_FC, p_fc);
+  float* const fc_bias_grad = fc_act ? nullptr : G + L.fc_b[L.n_fc - 1];
   const DropSite top_site = c.n_layers > 0 ? make_drop_site(seed, c.n_layers - 1, SITE_FFN_OUT, p_drop)
-                                           : make_drop_site(seed, 0, SITE_FC, p_fc);
+                                           : (fc_act ? none_site : fc_site);
 
   const int has_norm = c.n_layers > 0;
   const float* xlast = c.n_layers > 0 ? ws + W.layer[c.n_layers - 1].xout : ws + W.x0;
-  float* top_bias_grad = c.n_layers > 0 ? G + L.layer[c.n_layers - 1].b2 : G + L.fc_b;
+  float* top_bias_grad = c.n_layers > 0 ? G + L.layer[c.n_layers - 1].b2 : fc_bias_grad;
   if (n_outputs(c) > 1) {
     if (has_norm) {   // d xf into dxn, then the final norm's backward emits dx (+ its masked copy and the b2 gradient)
       ARB_TRY(head_multi_backward(dscores, scores, ws + W.xf, P + L.head_w, c.out_act, k.R, d, n_outputs(c), dxn,
@@ -416,7 +485,10 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
       a.dbias_qkv = G + pl.bqkv; a.d_model = d;          // bias gradient of the QKV projection, fused
       ARB_TRY(launch_attn_bwd(a, st));
     } else {
-      if (W.fused) {   // the fused forward kept no probabilities: recompute P = softmax(mask(alpha Q K^T))
+      const DropSite site_p = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
+      if (W.fused || site_p.thresh) {
+        // no undropped probabilities were kept (the fused forward keeps none; under dropout the unfused forward kept
+        // the dropped ones): recompute P = softmax(mask(alpha Q K^T))
         GemmDesc g;
         g.M = S; g.N = S; g.K = dk; g.alpha = alpha;
         g.A = head_view(qkv, dk, S, h, B, 3 * d);
@@ -427,7 +499,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
         ARB_TRY(softmax_forward(prob, mask, B, h, S, W.Sp, st));
       }
       {
-        GemmDesc g;   // dP = dctx V^T
+        GemmDesc g;   // dP~ = dctx V^T   (gradient w.r.t. the dropped probabilities)
         g.M = S; g.N = S; g.K = dk;
         g.A = head_view(dctx, dk, S, h, B, d);
         g.B = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
@@ -435,8 +507,10 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
         batch_all(g, h, B); g.block_n = 64;
         ARB_TRY(launch_gemm_tf32(g, st));
       }
+      // dprob <- dS (pre-scale); under dropout the mask is regenerated and prob <- dropped probabilities
+      ARB_TRY(softmax_backward(dprob, prob, int64_t(B) * h * S, S, W.Sp, st, site_p));
       {
-        GemmDesc g;   // dV = P^T dctx     (P read as an MN-major A operand, dctx as an MN-major B operand)
+        GemmDesc g;   // dV = P~^T dctx     (P~ read as an MN-major A operand, dctx as an MN-major B operand)
         g.M = S; g.N = dk; g.K = S; g.a_mn = 1; g.b_mn = 1;
         g.A = prob_view(prob, S, W.Sp, h, B);
         g.B = head_view(dctx, dk, S, h, B, d);
@@ -444,7 +518,6 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
         batch_all(g, h, B); g.block_n = pick_block_n(dk);
         ARB_TRY(launch_gemm_tf32(g, st));
       }
-      ARB_TRY(softmax_backward(dprob, prob, int64_t(B) * h * S, S, W.Sp, st));   // dprob <- dS (pre-scale)
       {
         GemmDesc g;   // dQ = alpha dS K
         g.M = S; g.N = dk; g.K = S; g.b_mn = 1; g.alpha = alpha;
@@ -467,13 +540,12 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(linear_bwd_weight(k, dqkv, 3 * d, 3 * d, xn1, d, d, G + pl.wqkv));
     if (!use_fused_bwd(c, S)) ARB_TRY(colsum_accumulate(dqkv, k.R, 3 * d, 3 * d, G + pl.bqkv, st));
     ARB_TRY(linear_bwd_input(k, dqkv, 3 * d, 3 * d, P + pl.wqkv, d, dxn, d, 0, nullptr, 0));
-    DropSite site_below = l > 0 ? make_drop_site(seed, l - 1, SITE_FFN_OUT, p_drop)
-                                : make_drop_site(seed, 0, SITE_FC, p_fc);
+    DropSite site_below = l > 0 ? make_drop_site(seed, l - 1, SITE_FFN_OUT, p_drop) : (fc_act ? none_site : fc_site);
     // with a positional encoding the encoder input is sqrt(d) * fc_out + pe: the gradient that reaches the FC
     // (through its dropout mask, if any) carries the extra sqrt(d)
-    if (l == 0 && c.pe_mode != 0) site_below.scale *= sqrtf(float(d));
+    if (l == 0 && c.pe_mode != 0 && !fc_act) site_below.scale *= sqrtf(float(d));
     ARB_TRY(ln_backward(dxn, xin, P + pl.ln1_a, ws + wl.mean1, ws + wl.std1, c.ln_eps, dx_alt, k.R, d, dx,
-                        G + pl.ln1_a, G + pl.ln1_b, st, dxm, site_below, l > 0 ? G + L.layer[l - 1].b2 : G + L.fc_b));
+                        G + pl.ln1_a, G + pl.ln1_b, st, dxm, site_below, l > 0 ? G + L.layer[l - 1].b2 : fc_bias_grad));
     // dx = d loss / d xin ; dy = the same through the dropout that produced xin's last summand
     dy = (site_below.thresh || site_below.scale != 1.0f) ? dxm : dx;
   }
@@ -481,8 +553,39 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     if (!indices) { arb_set_error("scorer: positional encoding needs indices"); return ARB_E_INVALID_ARG; }
     ARB_TRY(pos_backward(dx, reinterpret_cast<const long long*>(indices), mask, G + L.pe, c.pe_rows, k.R, d, st));
   }
-  // ---- input FC backward (x is data: no input gradient)
-  ARB_TRY(linear_bwd_weight(k, dy, d, d, x, F, F, G + L.fc_w));   // (fc_b gradient: fused into the kernel that emitted dy)
+  // ---- FC-block backward (model.py:35-44), last layer first.  dz = gradient w.r.t. the linear's output.
+  const float* dz = dy;            // identity activation: mask + bias gradient were fused into the kernel that emitted dy
+  float* dfa = scratch + Z.dfa;
+  float* dfb = scratch + Z.dfb;
+  if (fc_act) {
+    const float* h_last = W.fc_last ? ws + W.fc_last : ws + W.x0;
+    ARB_TRY(act_backward(dx, h_last, dfa, k.R, d, c.fc_act, fc_site, c.pe_mode != 0 ? sqrtf(float(d)) : 1.0f,
+                         G + L.fc_b[L.n_fc - 1], st));
+    dz = dfa; std::swap(dfa, dfb);
+  }
+  for (int i = L.n_fc - 1; i >= 0; --i) {
+    const int out = L.fc_size[i];
+    const int in = i > 0 ? L.fc_size[i - 1] : F;
+    const float* hin = i > 0 ? ws + W.fch[i - 1] : (c.fc_input_norm ? ws + W.xnorm : x);
+    ARB_TRY(linear_bwd_weight(k, dz, out, out, hin, in, in, G + L.fc_w[i]));
+    if (i > 0) {
+      const DropSite site = make_drop_site(seed, i - 1, SITE_FC, p_fc);
+      if (c.fc_act == ARB_ACT_RELU) {        // h > 0 <=> ReLU active and kept by the dropout: mask tile + 1/(1-p)
+        ARB_TRY(linear_bwd_input(k, dz, out, out, P + L.fc_w[i], in, dfa, in, EPI_MASK_AUX | EPI_COLSUM, hin, in,
+                                 site.scale, G + L.fc_b[i - 1]));
+      } else if (c.fc_act == ARB_ACT_NONE && site.thresh == 0) {
+        ARB_TRY(linear_bwd_input(k, dz, out, out, P + L.fc_w[i], in, dfa, in, EPI_COLSUM, nullptr, 0, 1.0f, G + L.fc_b[i - 1]));
+      } else {
+        ARB_TRY(linear_bwd_input(k, dz, out, out, P + L.fc_w[i], in, dfa, in, 0, nullptr, 0));
+        ARB_TRY(act_backward(dfa, hin, dfa, k.R, in, c.fc_act, site, 1.0f, G + L.fc_b[i - 1], st));
+      }
+      dz = dfa; std::swap(dfa, dfb);
+    } else if (c.fc_input_norm) {            // x is data: only the LayerNorm's weight / bias gradients are needed
+      ARB_TRY(linear_bwd_input(k, dz, out, out, P + L.fc_w[0], in, dfa, in, 0, nullptr, 0));
+      ARB_TRY(ln_backward(dfa, x, P + L.in_a, ws + W.in_mean, ws + W.in_std, 0.0f, nullptr, k.R, F, dfb,
+                          G + L.in_a, G + L.in_b, st, nullptr, none_site, nullptr, 1));
+    }
+  }
   return ARB_OK;
 }
 
@@ -502,14 +605,14 @@ extern "C" int64_t arb_scorer_workspace_floats(const arb_scorer_config* cfg, int
   ParamLayout L;
   if (!cfg || B <= 0 || S <= 0 || make_param_layout(*cfg, L) != ARB_OK) return -1;
   WsLayout W;
-  make_ws_layout(*cfg, B, S, training, W);
+  make_ws_layout(*cfg, L, B, S, training, W);
   return W.total;
 }
 extern "C" int64_t arb_scorer_backward_scratch_floats(const arb_scorer_config* cfg, int32_t B, int32_t S) {
   ParamLayout L;
   if (!cfg || B <= 0 || S <= 0 || make_param_layout(*cfg, L) != ARB_OK) return -1;
   ScratchLayout Z;
-  make_scratch_layout(*cfg, B, S, Z);
+  make_scratch_layout(*cfg, L, B, S, Z);
   return Z.total;
 }
 extern "C" int32_t arb_scorer_forward(const arb_scorer_config* cfg, const float* params, const float* x,

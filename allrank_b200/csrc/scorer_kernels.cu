@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
                                                                     const float* __restrict__ b, float eps,
                                                                     long long rows, int width,
                                                                     float* __restrict__ y, float* __restrict__ mean_o,
-                                                                    float* __restrict__ std_o) {
+                                                                    float* __restrict__ std_o, int torch_mode) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -82,8 +82,11 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
       ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
     }
   }
-  const float sd = sqrtf(warp_sum(ss) / float(width - 1));
-  const float denom = sd + eps;
+  // torch_mode: nn.LayerNorm (biased variance, eps inside the root; FCModel's input_norm, model.py:27) -- the saved
+  // "std" is then sqrt(var + eps) and the backward is called with eps = 0
+  const float ssum = warp_sum(ss);
+  const float sd = torch_mode ? sqrtf(ssum / float(width) + eps) : sqrtf(ssum / float(width - 1));
+  const float denom = torch_mode ? sd : sd + eps;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     r.v[k].x = ga.v[k].x * (r.v[k].x - mean) / denom + gb.v[k].x;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
                                                                     float* __restrict__ dx, float* __restrict__ grad_a,
                                                                     float* __restrict__ grad_b,
                                                                     float* __restrict__ dx_masked, DropSite site,
-                                                                    float* __restrict__ colsum_out) {
+                                                                    float* __restrict__ colsum_out, int torch_mode) {
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   RowRegs<NV> ga, acc_a, acc_b, acc_c;
@@ -150,7 +153,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     const float m1 = s1 / float(width);
-    const float coef = (sd > 0.f) ? r * r * s2 / (float(width - 1) * sd) : 0.f;
+    const float coef = torch_mode ? r * r * r * s2 / float(width)
+                                  : ((sd > 0.f) ? r * r * s2 / (float(width - 1) * sd) : 0.f);
     RowRegs<NV> res;
     if (dres) load_row<NV>(dres + row * width, width, lane, res);
 #pragma unroll
@@ -199,8 +203,12 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
 // ------------------------------------------------------------------------------------------------ softmax fwd
 // In place on the attention logits [B, h, S, pitch]: key-masked row softmax (padded keys -> probability 0).
 // A slate whose keys are all padded yields NaN rows, as the reference does (quirk Q2).
+// DROP: inverted dropout applied AFTER the normalisation (transformer.py:153-155); element index
+// ((b*h+head)*S + q)*S + key -- the same counter the fused attention kernels use, so a fused forward and this
+// unfused path regenerate identical masks.
+template <bool DROP>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(float* __restrict__ sc, const uint8_t* __restrict__ mask,
-                                                          int B, int h, int S, int pitch) {
+                                                          int B, int h, int S, int pitch, DropSite site) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long total = (long long)B * h * S;
@@ -231,18 +239,29 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(float* __restrict__ sc
 #pragma unroll
   for (int k = 0; k < MAXE; ++k) {
     const int j = lane + 32 * k;
-    if (j < S) p[j] = v[k] / z;
+    if (j < S) {
+      float e = v[k] / z;
+      if (DROP) {
+        const unsigned long long idx = (unsigned long long)row * (unsigned long long)S + j;
+        e = drop_keep(idx, site.seed, site.thresh) ? e * site.scale : 0.0f;
+      }
+      p[j] = e;
+    }
   }
 }
 
-// In place on dP: dS = P * (dP - sum_j P_j dP_j)
-__global__ void __launch_bounds__(256) softmax_bwd_kernel(float* __restrict__ dp, const float* __restrict__ prob,
-                                                          long long rows, int S, int pitch) {
+// In place on dP: dS = P * (dP - sum_j P_j dP_j).
+// DROP: `dp` holds the gradient w.r.t. the DROPPED probabilities P~ = m P / (1-p); the mask m is regenerated,
+// dP = m dP~ / (1-p), and `prob` (the undropped P, recomputed by the caller) is overwritten with P~ for the
+// dV = P~^T dO product that follows.
+template <bool DROP>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(float* __restrict__ dp, float* __restrict__ prob,
+                                                          long long rows, int S, int pitch, DropSite site) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   float* g = dp + row * pitch;
-  const float* p = prob + row * pitch;
+  float* p = prob + row * pitch;
   constexpr int MAXE = 48;
   float pv[MAXE], gv[MAXE];
   float t = 0.f;
@@ -250,7 +269,16 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(float* __restrict__ dp
   for (int k = 0; k < MAXE; ++k) {
     const int j = lane + 32 * k;
     pv[k] = gv[k] = 0.f;
-    if (j < S) { pv[k] = p[j]; gv[k] = g[j]; t += pv[k] * gv[k]; }
+    if (j < S) {
+      pv[k] = p[j]; gv[k] = g[j];
+      if (DROP) {
+        const unsigned long long idx = (unsigned long long)row * (unsigned long long)S + j;
+        const bool keep = drop_keep(idx, site.seed, site.thresh);
+        gv[k] = keep ? gv[k] * site.scale : 0.0f;
+        p[j] = keep ? pv[k] * site.scale : 0.0f;
+      }
+      t += pv[k] * gv[k];
+    }
   }
   t = warp_sum(t);
 #pragma unroll
@@ -621,6 +649,7 @@ __global__ void __launch_bounds__(256) pos_fwd_kernel(float* __restrict__ x, con
   long long idx = mask[row] ? pad : indices[row];
   if (idx > pad) idx = pad;
   if (idx < 0) idx += pe_rows;                     // python-style negative index (only reachable for unmasked -1)
+  if (idx < 0) idx = pad;                          // below -pe_rows: the padding row (the reference would raise)
   for (int c = lane * 4; c < width; c += 128) {
     float4 v = *reinterpret_cast<float4*>(x + row * width + c);
     const float4 p = *reinterpret_cast<const float4*>(pe + idx * width + c);
@@ -639,8 +668,66 @@ __global__ void __launch_bounds__(256) pos_bwd_kernel(const float* __restrict__ 
   long long idx = mask[row] ? pad : indices[row];
   if (idx > pad) idx = pad;
   if (idx < 0) idx += pe_rows;
-  if (idx == pad) return;
+  if (idx < 0 || idx == pad) return;
   for (int c = lane; c < width; c += 32) atomicAdd(dpe + idx * width + c, dx[row * width + c]);
+}
+
+// ------------------------------------------------------------------------------------------------ FC-block activations
+// FCModel applies dropout(activation(linear(x))) per layer (model.py:41-43).  ReLU / identity run inside the GEMM
+// epilogue; the kernels below serve the other activations and the backward of every activation under dropout.
+// Element index of the dropout counter = row * width + column (the same as the GEMM epilogue's).
+__global__ void __launch_bounds__(256) act_fwd_kernel(float* __restrict__ h, long long n4, int act, DropSite site) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(h)[i];
+    float* e = &v.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y = act_fwd(e[j], act);
+      e[j] = drop_keep((unsigned long long)i * 4 + j, site.seed, site.thresh) ? y * site.scale : 0.0f;
+    }
+    reinterpret_cast<float4*>(h)[i] = v;
+  }
+}
+
+// dz = mul * dh * m/(1-p) * act'(y)  with y = act(z) recovered from the stored h = m y/(1-p); colsum_out += column sums
+// of dz (the bias gradient of the linear that produced z).  dz may alias dh.
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* dh, const float* __restrict__ h, float* dz,
+                                                      long long rows, int width, int act, DropSite site, float mul,
+                                                      int tx_n, int rows_per_block, float* __restrict__ colsum_out) {
+  extern __shared__ float sh_cols[];
+  for (int c = threadIdx.x; c < width; c += blockDim.x) sh_cols[c] = 0.f;
+  __syncthreads();
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n, ty_n = blockDim.x / tx_n;
+  const int groups = width / 4;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  const float inv_scale = 1.0f / site.scale;
+  for (int g = tx; g < groups; g += tx_n) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long r = r0 + ty; r < r1; r += ty_n) {
+      const long long at = r * width + g * 4;
+      const float4 hv = *reinterpret_cast<const float4*>(h + at);
+      float4 gv = *reinterpret_cast<const float4*>(dh + at);
+      const float* he = &hv.x;
+      float* ge = &gv.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool keep = drop_keep((unsigned long long)at + j, site.seed, site.thresh);
+        const float y = he[j] * inv_scale;
+        ge[j] = keep ? ge[j] * mul * site.scale * act_bwd(y, y, act) : 0.0f;   // ReLU: y > 0 <=> z > 0
+      }
+      *reinterpret_cast<float4*>(dz + at) = gv;
+      acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+    }
+    if (colsum_out) {
+      atomicAdd(&sh_cols[g * 4 + 0], acc.x); atomicAdd(&sh_cols[g * 4 + 1], acc.y);
+      atomicAdd(&sh_cols[g * 4 + 2], acc.z); atomicAdd(&sh_cols[g * 4 + 3], acc.w);
+    }
+  }
+  if (colsum_out) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < width; c += blockDim.x) atomicAdd(colsum_out + c, sh_cols[c]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host launchers
@@ -663,22 +750,22 @@ static int check_launch() {
 }
 
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
-               float* mean, float* sd, cudaStream_t st) {
+               float* mean, float* sd, cudaStream_t st, int torch_mode) {
   if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 8), st);
-  ARB_DISPATCH_NV(width, (ln_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, rows, width, y, mean, sd)));
+  ARB_DISPATCH_NV(width, (ln_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, rows, width, y, mean, sd, torch_mode)));
   return check_launch();
 }
 
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
-                cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out) {
+                cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out, int torch_mode) {
   if (site.thresh == 0 && site.scale == 1.0f) dx_masked = nullptr;   // thresh 0 with a scale = pure rescale (positional encoding)
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((dres ? 16.0 : 12.0) * width + 8), st);
-  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out)));
+  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode)));
   return check_launch();
 }
 
@@ -697,17 +784,41 @@ int pos_backward(const float* dx, const long long* indices, const uint8_t* mask,
   return check_launch();
 }
 
-int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pitch, cudaStream_t st) {
-  if (S > 32 * 48) { arb_set_error("attention softmax supports slate_length <= 1536"); return ARB_E_UNSUPPORTED; }
-  const long long rows = (long long)B * h * S;
-  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 8.0 * S, st);
-  softmax_fwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(sc, mask, B, h, S, pitch);
+int act_forward(float* h, long long rows, int width, int act, DropSite site, cudaStream_t st) {
+  if (width % 4) { arb_set_error("activation: width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
+  const long long n4 = rows * width / 4;
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 8.0 * width, st);
+  const unsigned blocks = unsigned(std::min<long long>((n4 + 255) / 256, 148 * 16));
+  act_fwd_kernel<<<blocks, 256, 0, st>>>(h, n4, act, site);
   return check_launch();
 }
 
-int softmax_backward(float* dp, const float* prob, long long rows, int S, int pitch, cudaStream_t st) {
-  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 12.0 * S, st);
-  softmax_bwd_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(dp, prob, rows, S, pitch);
+int act_backward(const float* dh, const float* h, float* dz, long long rows, int width, int act, DropSite site, float mul,
+                 float* colsum_out, cudaStream_t st) {
+  if (width % 4 || width > 8192) { arb_set_error("activation: width must be a multiple of 4 and <= 8192"); return ARB_E_UNSUPPORTED; }
+  int tx_n = 1;
+  while (tx_n < width / 4 && tx_n < 256) tx_n *= 2;
+  const int rpb = 64 * (256 / tx_n);
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 12.0 * width, st);
+  act_bwd_kernel<<<unsigned((rows + rpb - 1) / rpb), 256, size_t(width) * 4, st>>>(dh, h, dz, rows, width, act, site, mul,
+                                                                                  tx_n, rpb, colsum_out);
+  return check_launch();
+}
+
+int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pitch, cudaStream_t st, DropSite site) {
+  if (S > 32 * 48) { arb_set_error("attention softmax supports slate_length <= 1536"); return ARB_E_UNSUPPORTED; }
+  const long long rows = (long long)B * h * S;
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 8.0 * S, st);
+  if (site.thresh) softmax_fwd_kernel<true><<<unsigned((rows + 7) / 8), 256, 0, st>>>(sc, mask, B, h, S, pitch, site);
+  else softmax_fwd_kernel<false><<<unsigned((rows + 7) / 8), 256, 0, st>>>(sc, mask, B, h, S, pitch, site);
+  return check_launch();
+}
+
+int softmax_backward(float* dp, float* prob, long long rows, int S, int pitch, cudaStream_t st, DropSite site) {
+  if (S > 32 * 48) { arb_set_error("attention softmax supports slate_length <= 1536"); return ARB_E_UNSUPPORTED; }
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (site.thresh ? 16.0 : 12.0) * S, st);
+  if (site.thresh) softmax_bwd_kernel<true><<<unsigned((rows + 7) / 8), 256, 0, st>>>(dp, prob, rows, S, pitch, site);
+  else softmax_bwd_kernel<false><<<unsigned((rows + 7) / 8), 256, 0, st>>>(dp, prob, rows, S, pitch, site);
   return check_launch();
 }
 

@@ -7,19 +7,32 @@
 
 namespace arb {
 
+// torch_mode = 0: the reference's custom LayerNorm (unbiased std, eps added to the std, transformer.py:73-81);
+// torch_mode = 1: nn.LayerNorm (biased variance, eps under the root; FCModel.input_norm, model.py:27) -- `sd` then
+// receives sqrt(var + eps) and ln_backward must be called with eps = 0 and torch_mode = 1
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
-               float* mean, float* sd, cudaStream_t st);
+               float* mean, float* sd, cudaStream_t st, int torch_mode = 0);
 // dx = (dres ? dres : 0) + LayerNormBackward(dy); grad_a / grad_b are accumulated (atomicAdd)
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
                 cudaStream_t st, float* dx_masked = nullptr, DropSite site = DropSite{0u, 0u, 1.0f},
-                float* colsum_out = nullptr);   // colsum_out[c] += column sums of the emitted (masked) gradient
+                float* colsum_out = nullptr,    // colsum_out[c] += column sums of the emitted (masked) gradient
+                int torch_mode = 0);
 int pos_forward(float* x, const long long* indices, const uint8_t* mask, const float* pe, int pe_rows, float scale,
                 long long rows, int width, cudaStream_t st);
 int pos_backward(const float* dx, const long long* indices, const uint8_t* mask, float* dpe, int pe_rows, long long rows,
                  int width, cudaStream_t st);
-int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pitch, cudaStream_t st);
-int softmax_backward(float* dp, const float* prob, long long rows, int S, int pitch, cudaStream_t st);
+// site.thresh != 0: inverted dropout on the probabilities (index ((b*h+head)*S+q)*S+key, as in the fused kernels);
+// the backward then expects `prob` = the UNDROPPED probabilities and overwrites it with the dropped ones
+// FC-block activations (model.py:41-43): h <- dropout(act(h)) in place; backward: dz = mul * dh * mask/(1-p) * act'
+// from the stored output h, colsum_out[c] += column sums of dz.  act: ARB_ACT_*
+int act_forward(float* h, long long rows, int width, int act, DropSite site, cudaStream_t st);
+int act_backward(const float* dh, const float* h, float* dz, long long rows, int width, int act, DropSite site, float mul,
+                 float* colsum_out, cudaStream_t st);
+int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pitch, cudaStream_t st,
+                    DropSite site = DropSite{0u, 0u, 1.0f});
+int softmax_backward(float* dp, float* prob, long long rows, int S, int pitch, cudaStream_t st,
+                     DropSite site = DropSite{0u, 0u, 1.0f});
 int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st);
 int head_forward(const float* x, const float* a, const float* b, float eps, const float* w, const float* wb,
                  int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,

@@ -146,8 +146,8 @@ int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int32_t B, int
  * hash of (seed, layer, site, element index) fused into the producing kernels and regenerated in backward
  * (csrc/dropout.cuh); `seed` must be the same in the forward and the backward call of a step.
  *
- * Parameters live in ONE flat fp32 buffer (the host layer makes the nn.Parameters views of it), laid out as
- *   fc_w[d,F] fc_b[d] | per layer: wq wk wv [3d,d] bq bk bv [3d] wo[d,d] bo[d] w1[dff,d] b1[dff] w2[d,dff] b2[d]
+ *  Parameters live in ONE flat fp32 buffer (the host layer makes the nn.Parameters views of it), laid out as
+ *   per FC layer i: fc_w[s_i, s_{i-1}] fc_b[s_i] (s_{-1} = F) | in_norm_w[F] in_norm_b[F] if fc_input_norm | per layer: wq wk wv [3d,d] bq bk bv [3d] wo[d,d] bo[d] w1[dff,d] b1[dff] w2[d,dff] b2[d]
  *   ln1_a ln1_b ln2_a ln2_b [d each] | lnf_a lnf_b [d] head_w[d] head_b[1] (pad to 4) | pe[pe_rows,d] if pe_mode == 2
  * (a fixed sinusoidal table, pe_mode == 1, is a buffer, not a parameter: it is passed separately as `pe_table`)
  * arb_scorer_param_count() gives the total; gradients use the same layout and are ACCUMULATED into `grads`.
@@ -172,7 +172,14 @@ typedef struct arb_scorer_config {
   int32_t pe_rows;      /* rows of the table = max_indices + 1; the last row is the padding row              */
   int32_t d_output;     /* post_model.d_output (model.py:104,108): outputs per item; 0 or 1 = one score per item.
                            > 1 (ordinal loss): scores are [B,S,d_output], head weight [d_output,d_model]           */
+  /* --- ABI v3: the general FCModel input block (model.py:16-44): [nn.LayerNorm(F)] -> n x dropout(act(Linear)) */
+  int32_t n_fc_layers;  /* len(fc_model.sizes), 1..ARB_MAX_FC_LAYERS; 0 = one layer of width d_model (v2 behaviour)  */
+  int32_t fc_sizes[8];  /* fc_model.sizes (multiples of 4, <= 8192); fc_sizes[n_fc_layers-1] must equal d_model       */
+  int32_t fc_act;       /* ARB_ACT_*: fc_model.activation applied after every FC linear, before its dropout          */
+  int32_t fc_input_norm;/* fc_model.input_norm: nn.LayerNorm(n_features) (eps 1e-5, biased variance) on x first;
+                           needs n_features % 4 == 0 (no feature padding)                                             */
 } arb_scorer_config;
+#define ARB_MAX_FC_LAYERS 8
 
 int64_t arb_scorer_param_count(const arb_scorer_config* cfg);
 /* floats of activation workspace for a [B,S] batch; `training` != 0 keeps what backward needs */
