@@ -8,7 +8,7 @@ Same call surface as the reference (/root/reference/allrank/models/model.py):
     model.parameters() / .state_dict() / .load_state_dict() / .train() / .eval() / .to(device)
 
 and the same state_dict keys and shapes as the reference's module tree (so a reference `model.pkl` loads):
-`input_layer.layers.0.{weight,bias}`, `encoder.layers.{l}.self_attn.linears.{0..3}.{weight,bias}`,
+`input_layer.layers.{i}.{weight,bias}` (+ `input_layer.input_norm.{weight,bias}`), `encoder.layers.{l}.self_attn.linears.{0..3}.{weight,bias}`,
 `encoder.layers.{l}.feed_forward.w_{1,2}.{weight,bias}`, `encoder.layers.{l}.sublayer.{0,1}.norm.{a_2,b_2}`,
 `encoder.norm.{a_2,b_2}`, `output_layer.w_1.{weight,bias}`; same initialisation order (nn.Linear defaults,
 clones share the prototype's bias, xavier_uniform_ on every parameter with dim > 1: model.py:148-150).
@@ -26,7 +26,10 @@ Positional encodings (allrank/models/positional.py: fixed sinusoidal buffer or l
 padding row for padded items) are applied by a SIMT kernel after the input FC; the learned table is part of the flat
 parameter buffer.
 
-Not built yet (raise NotImplementedError rather than fall back): multi-layer / activated / input-normed FC blocks.
+The input block is the reference's general FCModel (model.py:16-44): optional nn.LayerNorm on the features, then any
+number of Linear layers each followed by the activation (None / ReLU / Tanh / Sigmoid) and dropout.  With
+`transformer=None` the model is that MLP plus the output head (the `*_mlp.json` configurations of the paper).
+Not supported (raise NotImplementedError rather than fall back): `fc_model=None`, other activation classes.
 """
 import copy
 import ctypes
@@ -43,7 +46,9 @@ class ScorerConfig(ctypes.Structure):
     _fields_ = [("n_features", ctypes.c_int32), ("d_model", ctypes.c_int32), ("n_layers", ctypes.c_int32),
                 ("n_heads", ctypes.c_int32), ("d_ff", ctypes.c_int32), ("out_act", ctypes.c_int32),
                 ("ln_eps", ctypes.c_float), ("dropout", ctypes.c_float), ("fc_dropout", ctypes.c_float),
-                ("pe_mode", ctypes.c_int32), ("pe_rows", ctypes.c_int32), ("d_output", ctypes.c_int32)]
+                ("pe_mode", ctypes.c_int32), ("pe_rows", ctypes.c_int32), ("d_output", ctypes.c_int32),
+                ("n_fc_layers", ctypes.c_int32), ("fc_sizes", ctypes.c_int32 * 8), ("fc_act", ctypes.c_int32),
+                ("fc_input_norm", ctypes.c_int32)]
 
 
 c_p, c_i, c_i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
@@ -125,10 +130,13 @@ class _Encoder(nn.Module):
 
 
 class _InputFC(nn.Module):
-    def __init__(self, lin):
+    """Parameter holder with FCModel's attribute order (model.py:27-33): input_norm, then layers."""
+
+    def __init__(self, linears, n_features, input_norm):
         super().__init__()
-        self.layers = nn.ModuleList([lin])
-        self.output_size = lin.out_features
+        self.input_norm = nn.LayerNorm(n_features) if input_norm else nn.Identity()
+        self.layers = nn.ModuleList(linears)
+        self.output_size = linears[-1].out_features
 
 
 class _Head(nn.Module):
@@ -169,8 +177,17 @@ class LTRModel(nn.Module):
     """B200 scorer with the reference LTRModel's surface (model.py:47-92)."""
 
     def __init__(self, n_features, d_model, n_layers, n_heads, d_ff, dropout, output_activation, fc_dropout=0.0,
-                 positional=None, d_output=1):
+                 positional=None, d_output=1, fc_sizes=None, fc_activation=None, input_norm=False):
         super().__init__()
+        fc_sizes = [int(d_model)] if fc_sizes is None else [int(v) for v in fc_sizes]
+        d_model = fc_sizes[-1]
+        if not 1 <= len(fc_sizes) <= 8:
+            raise NotImplementedError("fc_model.sizes must list 1 to 8 layers")
+        if fc_activation not in _ACTS:
+            raise NotImplementedError(f"fc_model.activation {fc_activation!r}: supported {sorted(map(str, _ACTS))}")
+        if input_norm and n_features % 4:
+            raise NotImplementedError("fc_model.input_norm needs n_features % 4 == 0 (no feature padding under the norm)")
+        self.fc_sizes, self.fc_activation, self.input_norm_on = fc_sizes, fc_activation, bool(input_norm)
         self.d_output = int(d_output)
         if not 1 <= self.d_output <= 64:
             raise NotImplementedError("d_output must be in [1, 64]")
@@ -183,8 +200,8 @@ class LTRModel(nn.Module):
         if n_layers > 0:
             assert d_model % n_heads == 0   # transformer.py:170
         # --- build in the reference's construction order so that a seeded init reproduces (model.py:139-150)
-        fc = nn.Linear(n_features, d_model)
-        self.input_layer = _InputFC(fc)
+        dims = [int(n_features)] + fc_sizes
+        self.input_layer = _InputFC([nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:])], int(n_features), input_norm)
         if n_layers > 0:
             attn_proto = nn.Linear(d_model, d_model)
             w1 = nn.Linear(d_model, d_ff)
@@ -207,7 +224,9 @@ class LTRModel(nn.Module):
                 nn.init.xavier_uniform_(p)
         self._Fp = (self.n_features + 3) // 4 * 4
         self._cfg = ScorerConfig(self._Fp, self.d_model, self.n_layers, max(self.n_heads, 1), max(self.d_ff, 4),
-                                 _ACTS[output_activation], 1e-6, self.dropout_p, self.fc_dropout_p, 0, 0, self.d_output)
+                                 _ACTS[output_activation], 1e-6, self.dropout_p, self.fc_dropout_p, 0, 0, self.d_output,
+                                 len(fc_sizes), (ctypes.c_int32 * 8)(*fc_sizes), _ACTS[fc_activation],
+                                 1 if input_norm else 0)
         pos = self.encoder.position if self.encoder is not None else None
         if pos is not None:
             self._cfg.pe_mode = 1 if isinstance(pos, _FixedPE) else 2
@@ -220,8 +239,12 @@ class LTRModel(nn.Module):
     # ---- flat parameter storage -------------------------------------------------------------------
     def _ordered(self):
         """(parameter, flat shape) in the C ABI's layout order (include/allrank_b200.h)."""
-        d, Fp = self.d_model, self._Fp
-        out = [(self.input_layer.layers[0].weight, (d, Fp)), (self.input_layer.layers[0].bias, (d,))]
+        Fp = self._Fp
+        out = []
+        for i, lin in enumerate(self.input_layer.layers):   # layer 0's weight rows are padded to Fp features
+            out += [(lin.weight, (lin.out_features, Fp) if i == 0 else None), (lin.bias, None)]
+        if self.input_norm_on:
+            out += [(self.input_layer.input_norm.weight, None), (self.input_layer.input_norm.bias, None)]
         if self.encoder is not None:
             for lyr in self.encoder.layers:
                 lin = lyr.self_attn.linears
@@ -298,9 +321,19 @@ class LTRModel(nn.Module):
             raise ValueError("this model has a positional encoding: `indices` is required")
         return indices.detach().to(device=device, dtype=torch.int64).contiguous()
 
-    def _pe_table(self):
+    def _pe_table(self, device):
+        """The fixed sinusoidal table on the device of the batch (a model that was never moved with .to(device) keeps
+        the buffer on the host; the parameters are moved lazily by _ensure_packed, so the table must follow)."""
         pos = self.encoder.position if self.encoder is not None else None
-        return pos.pe.float().contiguous() if isinstance(pos, _FixedPE) else None
+        if not isinstance(pos, _FixedPE):
+            return None
+        if pos.pe.device == device and pos.pe.dtype == torch.float32 and pos.pe.is_contiguous():
+            return pos.pe
+        cached = getattr(self, "_pe_dev", None)
+        if cached is None or cached[0].device != device or cached[1] != pos.pe._version:
+            cached = (pos.pe.detach().to(device=device, dtype=torch.float32).contiguous(), pos.pe._version)
+            self._pe_dev = cached
+        return cached[0]
 
     def _prep_inputs(self, x, mask):
         _lib.require_cuda(x, mask)
@@ -333,7 +366,7 @@ class LTRModel(nn.Module):
             # whether activations are kept for backward
             self._cfg.dropout = self.dropout_p if self.training else 0.0
             self._cfg.fc_dropout = self.fc_dropout_p if self.training else 0.0
-            table = self._pe_table()
+            table = self._pe_table(dev)
             rc = _lib.lib().arb_scorer_forward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask),
                                                _lib.ptr(indices), _lib.ptr(table), B, S,
                                                _lib.ptr(scores), _lib.ptr(ws), n_ws, 1 if training else 0,
@@ -397,12 +430,8 @@ def make_model(fc_model, transformer, post_model, n_features):
     positional_encoding} or None, `post_model` dict {d_output, output_activation}."""
     if not fc_model:
         raise NotImplementedError("allrank_b200 needs an input FC block (fc_model.sizes = [d_model])")
-    sizes = list(_get(fc_model, "sizes"))
-    if len(sizes) != 1:
-        raise NotImplementedError("allrank_b200 fuses a single input Linear; multi-layer FC blocks are a next item")
-    if _get(fc_model, "input_norm", False) or _get(fc_model, "activation", None) is not None:
-        raise NotImplementedError("input_norm / FC activation are not built into the fused scorer yet")
-    d_model = int(sizes[0])
+    sizes = [int(v) for v in _get(fc_model, "sizes")]     # (the reference mutates the caller's list, model.py:25; we do not)
+    d_model = sizes[-1]
     if transformer:
         pe_cfg = _get(transformer, "positional_encoding", None)
         positional = None if pe_cfg is None else (_get(pe_cfg, "strategy"), int(_get(pe_cfg, "max_indices")))
@@ -412,4 +441,5 @@ def make_model(fc_model, transformer, post_model, n_features):
         n_layers, heads, d_ff, dropout, positional = 0, 1, 4, 0.0, None
     return LTRModel(n_features, d_model, n_layers, heads, d_ff, dropout, _get(post_model, "output_activation", None),
                     fc_dropout=float(_get(fc_model, "dropout", 0.0) or 0.0), positional=positional,
-                    d_output=int(_get(post_model, "d_output", 1)))
+                    d_output=int(_get(post_model, "d_output", 1)), fc_sizes=sizes,
+                    fc_activation=_get(fc_model, "activation", None), input_norm=bool(_get(fc_model, "input_norm", False)))

@@ -302,6 +302,82 @@ def gen_scorer_multi():
         print("scorer", name, "out", tuple(out.shape))
 
 
+SHIPPED_CONFIGS = [
+    "reproducibility/configs/contextaware_web30k/ndcgloss2pp.json",
+    "reproducibility/configs/contextaware_web30k/ndcgloss2pp_mlp.json",
+    "reproducibility/configs/contextaware_web30k/ordinal.json",
+    "reproducibility/configs/contextaware_web30k/ordinal_mlp.json",
+    "reproducibility/configs/neuralndcg_web30k/approxndcg.json",
+    "reproducibility/configs/neuralndcg_web30k/lambdarank_atmax.json",
+    "reproducibility/configs/neuralndcg_web30k/neuralndcg_atmax.json",
+    "scripts/local_config.json",
+]
+GRAD_SAMPLES = 1024
+
+
+def grad_sample_index(numel):
+    """Deterministic positions at which the golden file keeps a parameter gradient (all of it when small)."""
+    if numel <= GRAD_SAMPLES:
+        return torch.arange(numel)
+    return torch.linspace(0, numel - 1, GRAD_SAMPLES).long()
+
+
+def perturb_vectors(model, seed):
+    """Shift every 1-D parameter (biases, norm gains) so that parity exercises them; the tests repeat this."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for _, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+
+
+def gen_scorer_shipped():
+    """Every model configuration the reference ships (reproducibility/configs/*/*.json, scripts/local_config.json),
+    built by the reference's make_model from the JSON's `model` section at MSLR shape (136 features, the config's
+    slate length), eval mode.  Weights are NOT stored: a seeded init reproduces the reference's bit for bit
+    (tests/test_host_model.py), so the file keeps the seed, the inputs, the scores and sampled parameter gradients."""
+    import json
+    F, B = 136, 2
+    blob = {}
+    names = []
+    x, y, idx = make_slates(B, 240, n_features=F, seed=41, mean_len=150, std_len=60)
+    mask = y == -1
+    blob["x"], blob["y"] = x.numpy(), y.numpy()
+    for rel in SHIPPED_CONFIGS:
+        cfg = json.load(open(os.path.join("/root/reference", rel)))
+        m = cfg["model"]
+        name = os.path.splitext(os.path.basename(rel))[0]
+        assert cfg["data"]["slate_length"] == 240
+        torch.manual_seed(77)
+        tr = m["transformer"]
+        tcfg = None
+        if tr:
+            pe = tr.get("positional_encoding")
+            tcfg = TransformerConfig(N=tr["N"], d_ff=tr["d_ff"], h=tr["h"], dropout=tr["dropout"],
+                                     positional_encoding=PositionalEncoding(**pe) if pe else None)
+        model = ref_make_model(fc_model=dict(m["fc_model"], sizes=list(m["fc_model"]["sizes"])), transformer=tcfg,
+                               post_model=dict(m["post_model"]), n_features=F)
+        perturb_vectors(model, 78)
+        model.eval()
+        for k_, v in model.state_dict().items():       # checksum of every tensor: pins the seeded initialisation
+            blob[name + ":c:" + k_] = np.array([v.double().sum().item(), v.double().abs().sum().item()])
+        out = model(x, mask, idx)
+        w = torch.randn(out.shape, generator=torch.Generator().manual_seed(79))
+        (out * w).sum().backward()
+        blob[name + ":model"] = np.array(json.dumps(m))
+        blob[name + ":loss"] = np.array(json.dumps(cfg["loss"]))
+        blob[name + ":scores"] = out.detach().numpy()
+        blob[name + ":w"] = w.numpy()
+        for k_, p in model.named_parameters():
+            gi = grad_sample_index(p.numel())
+            blob[name + ":g:" + k_] = p.grad.flatten()[gi].numpy()
+            blob[name + ":n:" + k_] = np.array(p.grad.norm().item())
+        names.append(name)
+        print("shipped", name, tuple(out.shape), sum(p.numel() for p in model.parameters()), "params")
+    blob["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "scorer_shipped_configs.npz"), **blob)
+
+
 def write_corpus(path, lengths, n_features, seed):
     """A small libsvm corpus (label qid:N f:v ...), query ids deliberately not sorted, a few all-zero-label queries
     and one query with a single relevant item."""
@@ -364,6 +440,6 @@ def gen_init():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     gens = {"losses": gen_losses, "listmle": gen_listmle, "bce": gen_bce, "ordinal": gen_ordinal, "metrics": gen_metrics,
-            "scorer": gen_scorer, "scorer_pe": gen_scorer_pe, "scorer_multi": gen_scorer_multi, "slates": gen_slates, "init": gen_init}
+            "scorer": gen_scorer, "scorer_pe": gen_scorer_pe, "scorer_multi": gen_scorer_multi, "scorer_shipped": gen_scorer_shipped, "slates": gen_slates, "init": gen_init}
     for name in (sys.argv[1:] or list(gens)):      # optionally: only the named generators
         gens[name]()

@@ -199,11 +199,11 @@ class RefLTRModel(nn.Module):
 
 
 def make_ref_model(n_features, fc_sizes, n_layers, heads, d_ff, dropout=0.0, d_output=1,
-                   output_activation=None, fc_activation=None, seed=None, positional=None):
+                   output_activation=None, fc_activation=None, seed=None, positional=None, input_norm=False):
     """model.py:131-151: build + xavier_uniform_ on every parameter with dim > 1."""
     if seed is not None:
         torch.manual_seed(seed)
-    fc = InputFC(fc_sizes, n_features, activation=fc_activation)
+    fc = InputFC(fc_sizes, n_features, input_norm=input_norm, activation=fc_activation)
     width = fc.output_size
     position = Position(width, positional[1], positional[0]) if positional else None
     enc = Stack(n_layers, width, heads, d_ff, dropout, position) if n_layers > 0 else None   # transformer=None

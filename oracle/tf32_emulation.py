@@ -61,11 +61,20 @@ def row_norm(x, a, b, eps=1e-6):
     return a * (x - mu) / (sd + eps) + b
 
 
-def scorer_forward(sd, x, mask, n_layers, heads, out_act=None, mode="trunc", drop=None):
+def _activation(t, name):
+    if name is None:
+        return t
+    return {"ReLU": torch.relu, "Tanh": torch.tanh, "Sigmoid": torch.sigmoid}[name](t)
+
+
+def scorer_forward(sd, x, mask, n_layers, heads, out_act=None, mode="trunc", drop=None, fc_act=None):
     """Functional forward from a reference-keyed state_dict (tensors may require grad).
     `drop`: optional {(layer, site): already-scaled mask tensor} with sites fc / attn_p / attn_out / ffn_hid /
-    ffn_out (shapes [R,d], [B,h,S,S], [R,d], [R,d_ff], [R,d]) -- the dropout sites of transformer.py:105,155,227
-    and model.py:43."""
+    ffn_out (shapes [R,width], [B,h,S,S], [R,d], [R,d_ff], [R,d]) -- the dropout sites of transformer.py:105,155,227
+    and model.py:43 (site "fc" is keyed by the FC layer index).
+    General FCModel (model.py:35-44): `input_layer.input_norm.*` if present in `sd`, then every
+    `input_layer.layers.{i}` followed by `fc_act` and dropout; `output_layer.w_1.weight` with n > 1 rows gives
+    [B,S,n] outputs (model.py:111-117)."""
     B, S, F = x.shape
     R = B * S
     drop = drop or {}
@@ -77,7 +86,13 @@ def scorer_forward(sd, x, mask, n_layers, heads, out_act=None, mode="trunc", dro
     def lin(inp, w, b):   # inp [R, in]
         return mm(inp, w.t(), mode) + b
 
-    h = dr(lin(x.reshape(R, F), sd["input_layer.layers.0.weight"], sd["input_layer.layers.0.bias"]), 0, "fc")
+    h = x.reshape(R, F)
+    if "input_layer.input_norm.weight" in sd:    # nn.LayerNorm(F): biased variance, eps = 1e-5 under the root
+        h = torch.nn.functional.layer_norm(h, (F,), sd["input_layer.input_norm.weight"], sd["input_layer.input_norm.bias"])
+    i = 0
+    while f"input_layer.layers.{i}.weight" in sd:
+        h = dr(_activation(lin(h, sd[f"input_layer.layers.{i}.weight"], sd[f"input_layer.layers.{i}.bias"]), fc_act), i, "fc")
+        i += 1
     d = h.shape[-1]
     dk = d // heads if n_layers else 0
     for l in range(n_layers):
@@ -95,10 +110,8 @@ def scorer_forward(sd, x, mask, n_layers, heads, out_act=None, mode="trunc", dro
         h = h + dr(lin(hid, sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"]), l, "ffn_out")
     if n_layers:
         h = row_norm(h, sd["encoder.norm.a_2"], sd["encoder.norm.b_2"])
-    z = (h * sd["output_layer.w_1.weight"].reshape(1, -1)).sum(-1) + sd["output_layer.w_1.bias"]   # fp32 head (SIMT)
-    z = z.view(B, S)
-    if out_act == "Tanh":
-        z = torch.tanh(z)
-    elif out_act == "Sigmoid":
-        z = torch.sigmoid(z)
-    return z
+    hw = sd["output_layer.w_1.weight"]
+    n_out = hw.shape[0]
+    z = (h[:, None, :] * hw[None, :, :]).sum(-1) + sd["output_layer.w_1.bias"]   # fp32 head (SIMT), [R, n_out]
+    z = z.view(B, S) if n_out == 1 else z.view(B, S, n_out)
+    return _activation(z, out_act)

@@ -61,36 +61,7 @@ def test_fc_dropout_keep_rate_and_scale():
     assert torch.allclose(out[kept], ref[kept] / (1 - p), rtol=1e-5, atol=1e-6)
 
 
-M32 = np.uint64(0xFFFFFFFF)
-
-
-def _mix32(h):
-    h = h ^ (h >> np.uint64(16)); h = (h * np.uint64(0x85ebca6b)) & M32
-    h = h ^ (h >> np.uint64(13)); h = (h * np.uint64(0xc2b2ae35)) & M32
-    return h ^ (h >> np.uint64(16))
-
-
-def _site(call_seed, layer, site, p):
-    """Host restatement of make_drop_site / drop_keep (csrc/dropout.cuh)."""
-    m64 = (1 << 64) - 1
-    z = (call_seed + 0x9e3779b97f4a7c15 * (layer * 8 + site + 1)) & m64
-    z = ((z ^ (z >> 30)) * 0xbf58476d1ce4e5b9) & m64
-    z = ((z ^ (z >> 27)) * 0x94d049bb133111eb) & m64
-    z ^= z >> 31
-    seed = (z & 0xFFFFFFFF) ^ (z >> 32)
-    thresh = max(1, min(int(p * 4294967296.0), 0xFFFFFFFF))
-    return np.uint64(seed), np.uint64(thresh), 1.0 / (1.0 - p)
-
-
-def _mask(shape, call_seed, layer, site, p):
-    if p <= 0:
-        return None
-    seed, thresh, scale = _site(call_seed, layer, site, p)
-    idx = np.arange(int(np.prod(shape)), dtype=np.uint64)
-    h = _mix32((idx & M32) ^ seed)
-    h = _mix32((h + (idx >> np.uint64(32)) * np.uint64(0x9e3779b1) + np.uint64(0x7f4a7c15)) & M32)
-    keep = (h >= thresh).astype(np.float32) * scale
-    return torch.tensor(keep.reshape(shape))
+from tests.dropout_masks import mask_tensor as _mask  # noqa: E402
 
 
 @pytest.mark.parametrize("p,p_fc", [(0.3, 0.0), (0.15, 0.2)])

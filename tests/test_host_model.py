@@ -60,9 +60,18 @@ def test_multi_output_head_has_the_reference_state_dict_layout(golden):
 
 def test_unsupported_configs_raise_not_fallback():
     from allrank_b200.model import make_model
+    post = {"d_output": 1, "output_activation": None}
+    with pytest.raises(NotImplementedError):      # no input FC block at all
+        make_model(fc_model=None, transformer=None, post_model=post, n_features=20)
+    with pytest.raises(NotImplementedError):      # an activation class the kernels do not implement
+        make_model(fc_model={"sizes": [32, 32], "input_norm": False, "activation": "GELU", "dropout": 0.0},
+                   transformer=None, post_model=post, n_features=20)
+    with pytest.raises(NotImplementedError):      # input_norm over a feature count that needs padding
+        make_model(fc_model={"sizes": [32], "input_norm": True, "activation": None, "dropout": 0.0},
+                   transformer=None, post_model=post, n_features=21)
     with pytest.raises(NotImplementedError):
-        make_model(fc_model={"sizes": [32, 32], "input_norm": False, "activation": None, "dropout": 0.0},
-                   transformer=None, post_model={"d_output": 1, "output_activation": None}, n_features=20)
+        make_model(fc_model={"sizes": [8] * 9, "input_norm": False, "activation": None, "dropout": 0.0},
+                   transformer=None, post_model=post, n_features=20)
     m = make()
     with pytest.raises(Exception):   # CPU tensors: no eager fallback
         m(torch.zeros(1, 4, 20), torch.zeros(1, 4, dtype=torch.bool), None)
