@@ -452,14 +452,15 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   } else {
     kern = drop ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
   }
-  static bool configured[4] = {false, false, false, false};
+  static bool configured[ARB_MAX_DEVICES][4] = {};
   const int slot = (drop ? 1 : 0) + ((DK <= 32 && g_attn_fwd_two_pass) ? 2 : 0);
-  if (!configured[slot]) {
+  const int dev = arb_device_slot();
+  if (!configured[dev][slot]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total()) != cudaSuccess) {
       arb_set_error("attn_fwd: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    configured[slot] = true;
+    configured[dev][slot] = true;
   }
   dim3 grid((a.S + 127) / 128, a.h, a.B);
   {

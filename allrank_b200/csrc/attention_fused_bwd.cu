@@ -415,13 +415,14 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   arb_count_launch();
   const bool drop = a.drop.thresh != 0;
   auto kern = drop ? attn_bwd_kernel<DK, true> : attn_bwd_kernel<DK, false>;
-  static bool configured[2] = {false, false};
-  if (!configured[drop ? 1 : 0]) {
+  static bool configured[ARB_MAX_DEVICES][2] = {};
+  const int dev = arb_device_slot();
+  if (!configured[dev][drop ? 1 : 0]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::total()) != cudaSuccess) {
       arb_set_error("attn_bwd: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    configured[drop ? 1 : 0] = true;
+    configured[dev][drop ? 1 : 0] = true;
   }
   dim3 grid(a.h, a.B);
   {

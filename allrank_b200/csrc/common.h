@@ -7,6 +7,13 @@
 #include "../../include/allrank_b200.h"
 
 void arb_set_error(const char* msg);
+// cudaFuncSetAttribute is per DEVICE: "already configured" flags are kept per device ordinal, not per process
+constexpr int ARB_MAX_DEVICES = 64;
+inline int arb_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < ARB_MAX_DEVICES) ? dev : 0;
+}
 void arb_count_launch(int n = 1);
 
 // loss = sum(val)/sum(cnt), grad *= 1/sum(cnt); an all-zero count gives loss 0 and zero grad (slate_kernels.cu)

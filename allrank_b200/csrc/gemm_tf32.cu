@@ -598,18 +598,21 @@ static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const C
                                const CUtensorMap& tX, const GemmParams& p, dim3 tiles, cudaStream_t st) {
   auto kern = gemm_tf32_persistent<BLOCK_N, A_MN, B_MN>;
   constexpr int smem = PersistLayout<BLOCK_N>::total();
-  static bool configured = false;
-  static int n_sm = 148;
-  if (!configured) {
+  static bool configured[ARB_MAX_DEVICES] = {};
+  static int n_sm_of[ARB_MAX_DEVICES] = {};
+  const int dev_slot = arb_device_slot();
+  if (!configured[dev_slot]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       arb_set_error("gemm_tf32 (persistent): cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    int dev = 0;
+    int dev = 0, n = 148;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    n_sm_of[dev_slot] = n;
+    configured[dev_slot] = true;
   }
+  const int n_sm = n_sm_of[dev_slot];
   const long long n_tiles = (long long)tiles.x * tiles.y * tiles.z;
   const int grid = int(std::min<long long>(n_tiles, n_sm));
   {
@@ -650,13 +653,14 @@ static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap&
     if (deep) { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false, 3>; smem = SmemLayout<BLOCK_N, 3>::total(); slot = 3; }
     else      { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false, 2>; smem = SmemLayout<BLOCK_N, 2>::total(); slot = 4; }
   }
-  static bool configured[5] = {false, false, false, false, false};
-  if (!configured[slot]) {
+  static bool configured[ARB_MAX_DEVICES][5] = {};
+  const int dev_slot = arb_device_slot();
+  if (!configured[dev_slot][slot]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
       arb_set_error("gemm_tf32: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    configured[slot] = true;
+    configured[dev_slot][slot] = true;
   }
   {
     const double nb = double(d.nb2) * double(d.nb3);

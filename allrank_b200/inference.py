@@ -60,16 +60,26 @@ def rank_dataloader(dataloader, model):
     return torch.cat(ranked_x), torch.cat(ranked_y)
 
 
-def rank_slates(datasets, model, config):
-    """inference_utils.rank_slates (:12-30): role -> (X, y) ranked by the model.  `datasets` maps a role to a
-    SlateStore (allrank_b200.data) or to a ready loader yielding (xb, yb, indices); batch size from config.data."""
+def _as_loader(ds, config):
+    """What inference_utils.__create_data_loader (:33-34) does for the reference's LibSVMDataset -- any map-style
+    torch Dataset of (x[S,F], y[S], indices[S]) samples is batched with config.data.batch_size, unshuffled; a
+    SlateStore becomes a device loader; anything already yielding batches (a DataLoader, a DeviceSlateLoader, a list
+    of batches) is used as it is."""
+    from torch.utils.data import DataLoader, Dataset
     from .data import DeviceSlateLoader, SlateStore
-    out = {}
-    for role, ds in datasets.items():
-        if isinstance(ds, SlateStore):
-            ds = DeviceSlateLoader(ds, config.data.batch_size, shuffle=False)
-        out[role] = rank_dataloader(ds, model)
-    return out
+    if isinstance(ds, SlateStore):
+        return DeviceSlateLoader(ds, config.data.batch_size, shuffle=False)
+    if isinstance(ds, Dataset):
+        return DataLoader(ds, batch_size=config.data.batch_size, num_workers=getattr(config.data, "num_workers", 0),
+                          shuffle=False)
+    return ds
+
+
+def rank_slates(datasets, model, config):
+    """inference_utils.rank_slates (:12-30): role -> (X, y) ranked by the model.  `datasets` maps a role to the
+    reference's LibSVMDataset (or any map-style Dataset), a SlateStore (allrank_b200.data) or a ready loader yielding
+    (xb, yb, indices); batch size from config.data."""
+    return {role: rank_dataloader(_as_loader(ds, config), model) for role, ds in datasets.items()}
 
 
 __all__ = ["rank_slates", "rank_dataloader", "rank_batch", "reorder_slates"]

@@ -31,6 +31,15 @@ _MODULES = {"losses": "allrank.models.losses", "metrics": "allrank.models.metric
             "inference_utils": "allrank.inference.inference_utils", "dataset_loading": "allrank.data.dataset_loading"}
 
 
+def single_process_model(model):
+    """Stands in for allrank.models.model_utils.CustomDataParallel when allrank/main.py:76-78 runs on a box with
+    several visible GPUs.  The B200 path scales as ONE PROCESS PER GPU (torchrun + allrank_b200.ddp.FlatDDP, a single
+    NCCL all-reduce of the flat gradient); single-process nn.DataParallel would replicate a model whose parameters
+    are views of one flat device buffer, which cannot work.  The model is returned unwrapped and trains on the device
+    allRank selects (cuda:0 of the visible devices): launch one process per GPU with CUDA_VISIBLE_DEVICES / torchrun."""
+    return model
+
+
 def _rebind(saved, mod_key, name, fn):
     import importlib
     target = importlib.import_module(_MODULES[mod_key])
@@ -59,6 +68,9 @@ def patch_allrank(patch_model=True, patch_eval=True, patch_data=False):
             import allrank.main as ref_main
             saved["main.make_model"] = ref_main.make_model
             ref_main.make_model = _model.make_model
+            # main.py:76-78 wraps the model in CustomDataParallel when device_count() > 1: neutralised (see above)
+            saved["main.CustomDataParallel"] = ref_main.CustomDataParallel
+            ref_main.CustomDataParallel = single_process_model
         except Exception:
             pass
     if patch_eval:

@@ -397,6 +397,13 @@ class LTRModel(nn.Module):
                 if p.requires_grad:
                     p.grad = gv
 
+    def _replicate_for_data_parallel(self):
+        raise RuntimeError(
+            "allrank_b200.LTRModel cannot be replicated by nn.DataParallel (its parameters are views of one flat "
+            "device buffer): run one process per GPU (torchrun) with allrank_b200.ddp.FlatDDP, or restrict "
+            "CUDA_VISIBLE_DEVICES to one device; allrank_b200.integration.patch_allrank() neutralises the "
+            "CustomDataParallel wrap of allrank/main.py:76-78")
+
     # ---- public surface (model.py:62-92) ---------------------------------------------------------------
     def prepare_for_output(self, x, mask, indices):
         raise NotImplementedError("the fused scorer does not expose the encoder output; use forward()/score()")

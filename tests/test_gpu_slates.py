@@ -207,6 +207,44 @@ def test_rank_slates_and_epoch_metrics_with_a_model(store):
     assert np.allclose(again, ref_ndcg, rtol=1e-6)
 
 
+def test_rank_slates_accepts_a_map_style_dataset_like_the_reference(store):
+    """What rank_and_click.py:86 passes after patch_allrank(): the reference's LibSVMDataset objects -- map-style
+    Datasets of UN-batched (x[S,F], y[S], indices[S]) samples, which inference_utils.__create_data_loader (:33-34)
+    batches with config.data.batch_size."""
+    from allrank_b200 import inference
+    from allrank_b200.data import DeviceSlateLoader
+    from allrank_b200.model import make_model
+    torch.manual_seed(2)
+    model = make_model(fc_model={"sizes": [32], "input_norm": False, "activation": None, "dropout": 0.0},
+                       transformer=None, post_model={"d_output": 1, "output_activation": None},
+                       n_features=store.n_features).cuda().eval()
+    S = store.longest_query_length
+    batches = list(DeviceSlateLoader(store, batch_size=4, slate_length=S, shuffle=False))
+
+    class PlainDataset(torch.utils.data.Dataset):      # same sample protocol as LibSVMDataset.__getitem__
+        def __init__(self):
+            self.x = torch.cat([b[0] for b in batches]).cpu()
+            self.y = torch.cat([b[1] for b in batches]).cpu()
+            self.i = torch.cat([b[2] for b in batches]).cpu()
+
+        def __len__(self):
+            return self.x.shape[0]
+
+        def __getitem__(self, k):
+            return self.x[k], self.y[k], self.i[k]
+
+    class Cfg:
+        class data:
+            batch_size = 3
+            num_workers = 0
+    ds = PlainDataset()
+    ranked = inference.rank_slates({"vali": ds}, model, Cfg)["vali"]
+    direct = inference.rank_dataloader(batches, model)
+    assert tuple(ranked[0].shape) == (len(ds), S, store.n_features)
+    valid = direct[1] != -1
+    assert torch.equal(ranked[1][valid], direct[1][valid]) and torch.equal(ranked[0][valid], direct[0][valid])
+
+
 def test_config1_training_loop_matches_the_oracle(store):
     """BASELINE configs[0] in miniature (FC-only scorer + listNet + Adam + StepLR, the reference's CPU-runnable case,
     SURVEY 8c "end-to-end anchor"): the device pipeline (SlateStore loader -> fused scorer -> fused listNet -> Adam ->
