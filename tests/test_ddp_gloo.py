@@ -137,3 +137,56 @@ def test_epoch_metric_reduce_is_a_no_op_without_a_process_group():
     t = {"ndcg": torch.tensor([1.0, 2.0])}
     out, n = reduce_epoch_sums(t, 4)
     assert out is t and n == 4
+
+
+def _weighted_worker(rank, world, port, out_q):
+    """neuralNDCG-style mean over a DATA-DEPENDENT subset of slates (those with a relevant item), uneven shards."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from allrank_b200.ddp import FlatDDP, loss_weight
+    g = torch.Generator().manual_seed(77)
+    x_all = torch.randn(9, 6, 5, generator=g)
+    y_all = torch.randint(0, 3, (9, 6), generator=g).float()
+    y_all[1] = 0.0                                   # slates without any relevant item: excluded from the mean
+    y_all[2, :3] = 0.0; y_all[2, 3:] = -1.0          # ... also when the rest is padding
+    y_all[7] = 0.0
+    shard = slice(0, 5) if rank == 0 else slice(5, 9)            # 5 + 4 slates, 3 + 3 of them counted
+
+    def grad_of(model, x, y):
+        w = model.flat_parameters.clone().requires_grad_(True)
+        keep = ((y > 0) & (y != -1)).any(1)
+        per_slate = -(torch.softmax(y, 1) * torch.log_softmax(x @ w, 1)).sum(1)
+        loss = per_slate[keep].sum() / keep.sum()                # mean over the counted slates only
+        loss.backward()
+        model.flat_gradients.copy_(w.grad)
+
+    model = FlatToy(5, seed=100 + rank)
+    ddp = FlatDDP(model)
+    ddp.sync_parameters()
+    grad_of(model, x_all[shard], y_all[shard])
+    w = loss_weight("neuralNDCG", y_all[shard])
+    ddp.reduce_gradients(local_weight=w)
+    reduced = model.flat_gradients.clone()
+    ref = FlatToy(5, seed=100)
+    grad_of(ref, x_all, y_all)
+    out_q.put((rank, float(w), reduced, ref.flat_gradients.clone(), float(loss_weight("listNet", y_all[shard]))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_numerator_and_count_reduction_for_means_over_a_data_dependent_subset():
+    """neuralNDCG needs the GLOBAL count of idcg != 0 slates (neuralNDCG.py:62-69): all-reduce the
+    numerator and the count, not the per-rank means."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_weighted_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, w, reduced, single, wb in got:
+        assert w == 3.0 and wb == (5.0 if rank == 0 else 4.0)
+        assert torch.allclose(reduced, single, rtol=1e-5, atol=1e-7)
