@@ -465,7 +465,8 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   dim3 grid((a.S + 127) / 128, a.h, a.B);
   {
     ProfScope ps(ARB_PROF_GEMM, 4.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
-                 4.0 * double(a.B) * a.h * a.S * (4.0 * a.dk + 2.0));
+                 4.0 * double(a.B) * a.h * a.S * (4.0 * a.dk + 2.0),
+                 (DK <= 32 && g_attn_fwd_two_pass) ? "attn_fwd2_kernel" : "attn_fwd_kernel");
     const int threads = (DK <= 32 && g_attn_fwd_two_pass) ? ATT2_THREADS : ATT_THREADS;
     kern<<<grid, threads, L::total(), st>>>(tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
                                                a.scale * 1.4426950408889634f, a.drop);

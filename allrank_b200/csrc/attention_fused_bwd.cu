@@ -407,7 +407,7 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   if ((rc = make_tmap_4d(&tDK, a.dk_, box, 0, 0))) return rc;
   if ((rc = make_tmap_4d(&tDV, a.dv, box, 0, 0))) return rc;
   {
-    ProfScope ps(ARB_PROF_SCORER_SIMT, double(a.B) * a.S * (8.0 * a.h * a.dk + 4.0 * a.h), st);
+    ProfScope ps(ARB_PROF_SCORER_SIMT, double(a.B) * a.S * (8.0 * a.h * a.dk + 4.0 * a.h), st, 0.0, "attn_delta_kernel");
     const long long rows = (long long)a.B * a.S;
     attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(a.do_ptr, a.o_ptr, a.o_pitch, a.B, a.S, a.h, a.dk,
                                                                 a.delta);
@@ -427,7 +427,7 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   dim3 grid(a.h, a.B);
   {
     ProfScope ps(ARB_PROF_GEMM, 10.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
-                 4.0 * double(a.B) * a.h * a.S * (7.0 * a.dk + 3.0));
+                 4.0 * double(a.B) * a.h * a.S * (7.0 * a.dk + 3.0), "attn_bwd_kernel");
     kern<<<grid, BWD_THREADS, BwdSmem::total(), st>>>(tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
                                                       a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale, a.drop, a.dbias_qkv,
                                                       a.d_model);

@@ -21,18 +21,19 @@ extern "C" int64_t arb_launch_count(void) { return g_launches.load(std::memory_o
 #include <mutex>
 #include <vector>
 namespace {
-struct ProfRec { int cls; double work; double bytes; cudaEvent_t e0, e1; };
+struct ProfRec { int cls; double work; double bytes; cudaEvent_t e0, e1; char name[56]; };
 std::vector<ProfRec> g_recs;
 std::mutex g_prof_mu;
 bool g_prof_on = false;
 constexpr size_t kMaxRecs = 1 << 16;
 }  // namespace
 
-ProfScope::ProfScope(int cls, double work, cudaStream_t s, double bytes) : idx(-1), st(s) {
+ProfScope::ProfScope(int cls, double work, cudaStream_t s, double bytes, const char* name) : idx(-1), st(s) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   if (g_recs.size() >= kMaxRecs) return;
-  ProfRec r{cls, work, bytes, nullptr, nullptr};
+  ProfRec r{cls, work, bytes, nullptr, nullptr, {0}};
+  std::strncpy(r.name, name ? name : "?", sizeof(r.name) - 1);
   if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
   cudaEventRecord(r.e0, st);
   g_recs.push_back(r);
@@ -70,4 +71,38 @@ extern "C" int32_t arb_prof_collect(int32_t cls, double* total_ms, double* total
   if (total_work) *total_work = work;
   if (launches) *launches = n;
   return ARB_OK;
+}
+
+// Per-kernel table since arb_prof_enable(1): one line per distinct launch name,
+//   name<TAB>class<TAB>launches<TAB>total_ms<TAB>total_work<TAB>total_bytes
+// (work = flops for class 0, algorithmic bytes otherwise; bytes = algorithmic HBM bytes where the launcher states
+// them).  Returns the number of bytes written (truncated to cap - 1), or ARB_E_CUDA.
+#include <cstdio>
+#include <map>
+#include <string>
+extern "C" int64_t arb_prof_report(char* buf, int64_t cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  struct Agg { int cls; long long n; double ms, work, bytes; };
+  std::map<std::string, Agg> table;
+  std::vector<std::string> order;
+  for (auto& r : g_recs) {
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) { arb_set_error("arb_prof_report: event sync failed"); return ARB_E_CUDA; }
+    float t = 0;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    auto it = table.find(r.name);
+    if (it == table.end()) { it = table.emplace(r.name, Agg{r.cls, 0, 0, 0, 0}).first; order.push_back(r.name); }
+    it->second.n += 1; it->second.ms += t; it->second.work += r.work; it->second.bytes += r.bytes;
+  }
+  std::string out;
+  char line[256];
+  for (auto& k : order) {
+    const Agg& a = table[k];
+    std::snprintf(line, sizeof line, "%s\t%d\t%lld\t%.6f\t%.6e\t%.6e\n", k.c_str(), a.cls, a.n, a.ms, a.work, a.bytes);
+    out += line;
+  }
+  if (!buf || cap <= 0) return int64_t(out.size());
+  const int64_t n = std::min<int64_t>(cap - 1, int64_t(out.size()));
+  std::memcpy(buf, out.data(), size_t(n));
+  buf[n] = 0;
+  return n;
 }

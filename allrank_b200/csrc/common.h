@@ -25,7 +25,9 @@ int arb_finalize_mean_over_count(const float* val, const float* cnt, int B, floa
 enum { ARB_PROF_GEMM = 0, ARB_PROF_SCORER_SIMT = 1, ARB_PROF_LOSS = 2, ARB_PROF_METRICS = 3, ARB_PROF_OPTIM = 4,
        ARB_PROF_SLATES = 5, ARB_PROF_CLASSES = 6 };
 struct ProfScope {
-  ProfScope(int cls, double work, cudaStream_t st, double bytes = 0.0);
+  // `name` defaults to the launching host function; GEMM launches pass a shape-derived name so that the per-kernel
+  // table of bench.py tells the QKV projection from the first FFN linear (arb_prof_report)
+  ProfScope(int cls, double work, cudaStream_t st, double bytes = 0.0, const char* name = __builtin_FUNCTION());
   ~ProfScope();
   int idx;
   cudaStream_t st;

@@ -590,6 +590,14 @@ int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32, int as_tf32)
 // 411 -> 332 us), loses on the short-K, write-heavy linears (QKV 601 -> 748 us, W1 786 -> 995 us: its epilogue is the
 // critical path, while three co-resident one-tile CTAs overlap three epilogues) and ties on the split-K weight
 // gradients.  Mode 2 (default) therefore picks it only for non-split contractions with K >= 256.
+// launch name for the per-kernel profile table: shape, operand layouts and what the epilogue does
+static void gemm_prof_name(char (&out)[56], const GemmDesc& d, const char* variant) {
+  const char* kind = (d.flags & EPI_ATOMIC) ? "wgrad" : (d.nb2 * d.nb3 > 1 ? "batched" : (d.b_mn ? "dgrad" : "fwd"));
+  std::snprintf(out, sizeof out, "gemm_%s[%s M%d N%d K%d%s%s%s]", variant, kind, d.M, d.N, d.K,
+                (d.flags & EPI_RELU) ? " relu" : "", (d.flags & EPI_ADD_AUX) ? " +res" : "",
+                (d.flags & EPI_MASK_AUX) ? " mask" : "");
+}
+
 static int g_persistent = 2;   // 0: never, 1: wherever supported, 2: auto
 void set_gemm_persistent(int on) { g_persistent = on; }
 
@@ -618,8 +626,10 @@ static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const C
   {
     const double nb = double(d.nb2) * double(d.nb3);
     const double has_x = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) ? 1.0 : 0.0;
+    char pname[56];
+    gemm_prof_name(pname, d, "persist");
     ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
-                 4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N));
+                 4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N), pname);
     kern<<<grid, PERSIST_THREADS, smem, st>>>(tA, tB, tC, tX, p, int(tiles.x), int(tiles.y), int(tiles.z));
   }
   arb_count_launch();
@@ -665,8 +675,10 @@ static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap&
   {
     const double nb = double(d.nb2) * double(d.nb3);
     const double has_x = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) ? 1.0 : 0.0;
+    char pname[56];
+    gemm_prof_name(pname, d, "tile");
     ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
-                 4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N));
+                 4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N), pname);
     kern<<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tX, p);
   }
   arb_count_launch();

@@ -9,7 +9,7 @@
 Prints ONE JSON line (rank 0).  Contract: see the task statement; fields are documented in DESIGN.md section 6.
 Workloads (BASELINE.json configs):
     cfg2  Transformer(N=2,h=4,d=128,d_ff=512) + approxNDCGLoss, S=240, F=136      <- the metric's configuration
-    cfg3  Transformer(N=4,h=8,d=256,d_ff=1024) + lambdaLoss(ndcgLoss2PP), S=240   (TF32 here; bf16 not built yet)
+    cfg3  Transformer(N=4,h=8,d=256,d_ff=1024) + lambdaLoss(ndcgLoss2PP), S=240
     cfg4  Transformer(N=2,h=4,d=128,d_ff=512) + neuralNDCG, S=120
     cfg5  Transformer(N=4,h=8,d=256,d_ff=1024) + listMLE, S=240
 """
@@ -113,27 +113,56 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def reference_available():
+    return os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "allrank", "main.py"))
+
+
 def cpu_reference_steps(w, batch, steps, warmup, threads):
-    """The reference's eager PyTorch path on the host cores: oracle port of make_model + loss + torch Adam
-    (train_utils.loss_batch semantics, allrank/training/train_utils.py:18-29)."""
-    from oracle import losses_ref
-    from oracle.scorer_ref import make_ref_model
+    """The reference's own eager PyTorch path on the host cores, one step = train_utils.loss_batch
+    (allrank/training/train_utils.py:18-29: forward, loss, backward, Adam step, loss.item()).
+    kind "reference": the UNMODIFIED package installed in baseline/_ref (oracle/install_reference.py) -- its make_model,
+    its loss function, its loss_batch; kind "port": the oracle restatement (only when baseline/_ref is absent).
+    Must run in a process where CUDA is hidden: the reference hard-wires cuda:0 whenever a GPU is visible
+    (allrank/models/model_utils.py:13-18)."""
     from allrank_b200.synth import make_slates
     torch.manual_seed(42)
-    model = make_ref_model(F, [w["d"]], w["N"], w["h"], w["dff"]).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
-    loss_fn = losses_ref.LOSSES[w["loss"]]
     x, y, idx = make_slates(batch, w["S"], F, seed=1234)
+    if reference_available():
+        from oracle.install_reference import import_path
+        sys.path[:0] = import_path()
+        import allrank.models.losses as ref_losses
+        from allrank.config import TransformerConfig
+        from allrank.models.model import make_model as ref_make_model
+        from allrank.training.train_utils import loss_batch
+        from functools import partial
+        model = ref_make_model(fc_model={"sizes": [w["d"]], "input_norm": False, "activation": None, "dropout": 0.0},
+                               transformer=TransformerConfig(N=w["N"], d_ff=w["dff"], h=w["h"],
+                                                             positional_encoding=None, dropout=0.0),
+                               post_model={"d_output": 1, "output_activation": None}, n_features=F).train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        loss_fn = partial(getattr(ref_losses, w["loss"]), **w["loss_args"])
+        kind = "reference"
 
-    def one_step():
-        t0 = time.perf_counter()
-        mask = y == PAD
-        loss = loss_fn(model(x, mask, idx), y, **w["loss_args"])
-        loss.backward()
-        opt.step()
-        opt.zero_grad()
-        _ = loss.item()
-        return time.perf_counter() - t0
+        def one_step():
+            t0 = time.perf_counter()
+            loss_batch(model, loss_fn, x, y, idx, None, opt)
+            return time.perf_counter() - t0
+    else:
+        from oracle import losses_ref
+        from oracle.scorer_ref import make_ref_model
+        model = make_ref_model(F, [w["d"]], w["N"], w["h"], w["dff"]).train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        loss_fn = losses_ref.LOSSES[w["loss"]]
+        kind = "port"
+
+        def one_step():
+            t0 = time.perf_counter()
+            loss = loss_fn(model(x, y == PAD, idx), y, **w["loss_args"])
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            _ = loss.item()
+            return time.perf_counter() - t0
 
     # "all the host threads it can use": intra-op thread counts above the box's real core budget make eager
     # PyTorch slower, so pick the fastest of a few candidates (one untimed + one timed step each) -- the
@@ -148,7 +177,7 @@ def cpu_reference_steps(w, batch, steps, warmup, threads):
     torch.set_num_threads(best)
     times = [one_step() for _ in range(warmup + steps)][warmup:]
     total = sum(times)
-    return batch * steps / total, 1e3 * total / steps, best
+    return batch * steps / total, 1e3 * total / steps, best, kind
 
 
 def run_reference(args, w):
@@ -157,35 +186,88 @@ def run_reference(args, w):
         return
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     batch = args.ref_batch
-    sps, ms, used = cpu_reference_steps(w, batch, args.steps, args.warmup, threads)
-    sample = (f"{batch} slates/step x {args.steps} steps (S={w['S']}, F={F}), eager PyTorch fp32, {used} intra-op threads "
-              f"(fastest of 8..{threads} on a {threads}-thread host)")
+    sps, ms, used, kind = cpu_reference_steps(w, batch, args.steps, args.warmup, threads)
+    what = "the unmodified allRank package (baseline/_ref): make_model + loss + train_utils.loss_batch" \
+        if kind == "reference" else "oracle port of the reference (baseline/_ref absent)"
+    sample = (f"{batch} slates/step x {args.steps} steps (S={w['S']}, F={F}), {what}, eager PyTorch fp32 on the host, "
+              f"{used} intra-op threads (fastest of 8..{threads} on a {threads}-thread host)")
     out = {
         "impl": "reference", "metric": "slates/sec", "value": sps, "unit": "slates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, w, batch),
-        "cpu_baseline": {"value": sps, "unit": "slates/s", "cores": used, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": sps, "unit": "slates/s", "cores": used, "kind": kind, "sample": sample},
         "e2e": {"value": sps, "unit": "slates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
 
 
+def cpu_baseline_subprocess(args, w, steps=3, warmup=1):
+    """The CPU leg of the default run: the reference arm in a child process with CUDA hidden, bounded to a few steps."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONDONTWRITEBYTECODE="1")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps",
+           str(steps), "--warmup", str(warmup), "--ref-batch", str(args.ref_batch), "--allow-short-warmup"]
+    t0 = time.time()
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"value": None, "unit": "slates/s", "cores": 0, "kind": "unavailable", "sample": r.stderr[-300:]}
+    cb = json.loads(lines[-1])["cpu_baseline"]
+    cb["sample"] += f"; {steps} timed steps after {warmup} warm-up, {time.time() - t0:.1f}s of CPU work"
+    return cb
+
+
 def workload_config(args, w, batch):
+    # bytes one step touches: ~20 MB of activations per slate for cfg2 (profiles/README.md), inputs batch*S*F*4
+    act_mb = batch * w["S"] * (w["N"] * (10 * w["d"] + 2 * w["dff"]) + w["d"]) * 4 * 2 / 1e6
     return {"workload": f"{args.workload}: Transformer(N={w['N']},h={w['h']},d_model={w['d']},d_ff={w['dff']}) + "
                         f"{w['loss']}, slate_len={w['S']}, {F} features, full training step (fwd+loss+bwd+Adam)",
             "batch_per_gpu": batch, "slate_len": w["S"], "n_features": F, "loss": w["loss"],
-            "optimizer": "Adam(lr=1e-3)", "l2": "inputs (x alone is batch*S*F*4 bytes) and activations exceed the "
-                                                "126 MB L2; no explicit flush"}
+            "optimizer": "Adam(lr=1e-3)",
+            "l2": f"no explicit flush: one step streams ~{act_mb:.0f} MB of activations (+ {batch * w['S'] * F * 4 / 1e6:.0f} MB "
+                  "of inputs) through the 126 MB L2, so every kernel's inputs come from HBM"
+                  + ("" if act_mb > 252 else " -- EXCEPT at this small batch, where parts stay L2-resident between kernels")}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def kernel_table(lib, psteps, peaks, dtype):
+    """Per-kernel roofline from the library's per-launch CUDA-event timings (arb_prof_report): for each distinct
+    kernel (GEMMs are named by shape) the algorithmic FLOPs and HBM bytes of its launches in one step, its device time,
+    and the fraction of the roof that binds it -- the larger of flops / tensor peak and bytes / HBM copy peak, both
+    from MEASURED_PEAKS.json."""
+    lib.arb_prof_report.restype = ctypes.c_int64
+    lib.arb_prof_report.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+    need = int(lib.arb_prof_report(None, 0))
+    buf = ctypes.create_string_buffer(need + 64)
+    lib.arb_prof_report(buf, need + 64)
+    tensor_peak = peaks["bf16_tflops_sustained"] * (1.0 if dtype == "bf16" else 0.5)      # TFLOP/s
+    rows = []
+    for line in buf.value.decode().splitlines():
+        name, cls, n, ms, work, nbytes = line.split("\t")
+        cls, n, ms, work, nbytes = int(cls), int(n), float(ms), float(work), float(nbytes)
+        if ms <= 0:
+            continue
+        flops = work if cls == 0 else 0.0
+        nbytes = nbytes if cls == 0 else work          # non-GEMM classes state their algorithmic bytes as `work`
+        t_tensor = flops / (tensor_peak * 1e12) * 1e3
+        t_hbm = nbytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+        bound = "tensor" if t_tensor >= t_hbm else "hbm"
+        rows.append({"kernel": name, "launches_per_step": n / psteps, "us_per_step": round(1e3 * ms / psteps, 2),
+                     "flops_per_step": flops / psteps, "bytes_per_step": nbytes / psteps,
+                     "tflops": round(flops / (ms * 1e-3) / 1e12, 2), "gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
+                     "bound": bound, "frac": round(max(t_tensor, t_hbm) / ms, 4)})
+    rows.sort(key=lambda r: -r["us_per_step"])
+    return rows, tensor_peak
+
+
 def run_b200(args, w):
     rank, local_rank, world = dist_env()
     import torch.distributed as dist
     from allrank_b200 import _lib, losses
-    from allrank_b200.ddp import FlatDDP
+    from allrank_b200.ddp import FlatDDP, loss_weight
     from allrank_b200.model import make_model
     from allrank_b200.optim import FlatAdam
     from allrank_b200.synth import make_slates
@@ -196,28 +278,50 @@ def run_b200(args, w):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, S = args.batch, w["S"]
+    if args.scaling == "strong":                 # fixed GLOBAL batch (512), split over the ranks
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be divisible by the number of GPUs")
+        B = args.global_batch // world
+    else:
+        B = args.batch
+    S = w["S"]
     torch.manual_seed(42)
     model = make_model(fc_model={"sizes": [w["d"]], "input_norm": False, "activation": None, "dropout": 0.0},
                        transformer={"N": w["N"], "d_ff": w["dff"], "h": w["h"], "positional_encoding": None,
                                     "dropout": 0.0},
                        post_model={"d_output": 1, "output_activation": None}, n_features=F).to(dev).train()
     loss_fn = getattr(losses, w["loss"])
-    x_host, y_host, _ = make_slates(B, S, F, seed=1234 + rank)
-    x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
+    # two different pinned host batches, alternated by the end-to-end loop
+    hosts = []
+    for k in range(2):
+        xh, yh, _ = make_slates(B, S, F, seed=1234 + rank + 1000 * k)
+        hosts.append((xh.pin_memory(), yh.pin_memory()))
+    x_host, y_host = hosts[0]
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
-    opt = FlatAdam(model, lr=1e-3)
+    model._ensure_packed(dev)
+    if args.optimizer == "torch":                # the optimiser allrank/main.py:82 instantiates from its config
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    else:
+        opt = FlatAdam(model, lr=1e-3)
     ddp = FlatDDP(model) if world > 1 else None
-    average = w["loss"] != "lambdaLoss"      # lambdaLoss(reduction="sum") gradients are summed across ranks
+    mode = "sum" if w["loss"] == "lambdaLoss" else ("weighted" if w["loss"].startswith("neuralNDCG") else "mean")
     if ddp:
-        ddp.average = average
+        ddp.average = mode != "sum"              # lambdaLoss(reduction="sum") gradients are summed across ranks
 
     def step(x, y):
         mask = y == PAD                                    # train_utils.py:19
         loss = loss_fn(model(x, mask, None), y, **w["loss_args"])
         loss.backward()
-        scale = ddp.reduce_gradients(fold_average_into_optimizer=True) if ddp else 1.0
-        opt.step(grad_scale=scale)
+        scale = 1.0
+        if ddp:
+            if mode == "weighted":               # neuralNDCG: all-reduce numerator and count (neuralNDCG.py:62-69)
+                ddp.reduce_gradients(local_weight=loss_weight(w["loss"], y))
+            else:
+                scale = ddp.reduce_gradients(fold_average_into_optimizer=args.optimizer == "flat")
+        if args.optimizer == "flat":
+            opt.step(grad_scale=scale)
+        else:
+            opt.step()
         opt.zero_grad()
         return loss
 
@@ -233,8 +337,7 @@ def run_b200(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    if world > 1:                     # pack + broadcast rank-0 weights before the first step
-        model._ensure_packed(dev)
+    if world > 1:                     # broadcast rank-0 weights before the first step
         ddp.sync_parameters()
     for _ in range(args.warmup):
         step(x_dev, y_dev)
@@ -261,23 +364,24 @@ def run_b200(args, w):
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
 
-    def prefetch():
+    def prefetch(k):
+        xh, yh = hosts[k & 1]
         with torch.cuda.stream(copy_stream):
-            xb = x_host.to(dev, non_blocking=True)
-            yb = y_host.to(dev, non_blocking=True)
+            xb = xh.to(dev, non_blocking=True)
+            yb = yh.to(dev, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return xb, yb, ev
 
     def e2e_loop(n):
-        nxt = prefetch()
+        nxt = prefetch(0)
         for i in range(n):
             xb, yb, ev = nxt
             main_stream.wait_event(ev)
             xb.record_stream(main_stream)
             yb.record_stream(main_stream)
             if i + 1 < n:
-                nxt = prefetch()
+                nxt = prefetch(i + 1)
             _ = step(xb, yb).item()
 
     e2e_loop(2)
@@ -289,12 +393,24 @@ def run_b200(args, w):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
 
-    # ---- (3) per-launch device timing of every kernel class (roofline), a few extra steps
-    prof = {}
+    # ---- (3) the gradient all-reduce alone (N > 1): the flat bucket, CUDA events, max over ranks
+    allreduce_us = None
+    if world > 1:
+        g = model.flat_gradients
+        for _ in range(5):
+            dist.all_reduce(g)
+        barrier()
+        e0.record()
+        for _ in range(20):
+            dist.all_reduce(g)
+        e1.record()
+        barrier()
+        allreduce_us = 1e3 * max_over_ranks(e0.elapsed_time(e1)) / 20
+        g.zero_()
+
+    # ---- (4) per-launch device timing of every kernel (roofline), a few extra steps
     lib = _lib.lib()
     lib.arb_prof_enable.argtypes = [ctypes.c_int32]
-    lib.arb_prof_collect.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
-                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]
     if rank == 0:
         lib.arb_prof_enable(1)
     psteps = 3
@@ -304,18 +420,11 @@ def run_b200(args, w):
         step(x_dev, y_dev)
     pe1.record()
     torch.cuda.synchronize()
+    kernels, tensor_peak, step_ms_profiled = [], 0.0, 0.0
+    peaks = measured_peaks()
     if rank == 0:
-        names = ["gemm_tf32", "scorer_simt", "loss", "metrics", "adam"]
-        for cls, nm in enumerate(names):
-            ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
-            lib.arb_prof_collect(cls, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n))
-            prof[nm] = {"ms_per_step": ms.value / psteps, "work_per_step": work.value / psteps,
-                        "launches_per_step": n.value / psteps}
-            if cls == 0:
-                lib.arb_prof_last_bytes.restype = ctypes.c_double
-                lib.arb_prof_last_bytes.argtypes = [ctypes.c_int32]
-                prof[nm]["algorithmic_bytes_per_step"] = lib.arb_prof_last_bytes(0) / psteps
-        prof["step_ms_profiled"] = pe0.elapsed_time(pe1) / psteps
+        kernels, tensor_peak = kernel_table(lib, psteps, peaks, args.dtype)
+        step_ms_profiled = pe0.elapsed_time(pe1) / psteps
         lib.arb_prof_enable(0)
     if world > 1:
         dist.barrier()
@@ -324,99 +433,75 @@ def run_b200(args, w):
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = measured_peaks()
     slates = B * world * args.steps
     value = slates / (ms_total / 1e3)
     e2e_value = slates / (ms_e2e / 1e3)
-    gemm = prof["gemm_tf32"]
-    achieved_tflops = gemm["work_per_step"] / (gemm["ms_per_step"] * 1e-3) / 1e12 if gemm["ms_per_step"] > 0 else 0.0
-    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    top = kernels[0] if kernels else None
+    kernel_ms = sum(k["us_per_step"] for k in kernels) / 1e3
+    step_flops = flops_per_slate_step(w) * B
     out = {
         "metric": "slates/sec", "value": value, "unit": "slates/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-        "config": workload_config(args, w, B),
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": args.scaling,
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": dict(workload_config(args, w, B), global_batch=B * world,
+                       optimizer=("Adam(lr=1e-3), " + ("allrank_b200.optim.FlatAdam (one launch)" if args.optimizer == "flat"
+                                                       else "torch.optim.Adam over the module's parameters")),
+                       parallelism=f"dp{world}: one process per GPU, one NCCL all-reduce of the flat gradient per step"),
         "e2e": {"value": e2e_value, "unit": "slates/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
+                "note": "two pinned host batches alternate; H2D one step ahead on a copy stream; loss.item() every step"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {
-            "bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05.mma kind::tf32)",
-            "achieved": achieved_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": achieved_tflops / tf32_peak if tf32_peak else None,
-            "traffic": measured_traffic(args, B),
-            "traffic_note": "DRAM read+write bytes of the class's launches in one step (ncu dram__bytes_{read,write}.sum, "
-                            "profiles/r1_dram_traffic_b4096.json: 66.8 GB vs 67.7 GB algorithmic at batch 4096); null when "
-                            "this run's workload/batch has no committed capture",
-            "peak_source": f"{peaks['source']}: MEASURED_PEAKS bf16_tflops_sustained={peaks['bf16_tflops_sustained']} / 2 "
-                           "(kind::tf32 issues at half the bf16 rate)",
-            "frac_of_bf16_peak": achieved_tflops / peaks["bf16_tflops_sustained"],
-            "algorithmic_flops_per_step": gemm["work_per_step"],
-            "kernel_ms_per_step": gemm["ms_per_step"], "launches_per_step": gemm["launches_per_step"],
-            "share_of_step": gemm["ms_per_step"] / prof["step_ms_profiled"] if prof.get("step_ms_profiled") else None,
-            "model_flops_per_step": flops_per_slate_step(w) * B,
-            "whole_step_tflops": flops_per_slate_step(w) * B * world / (ms_total / args.steps * 1e-3) / 1e12,
-            # the same kernels against the HBM roofline: with K = 128..512 the linears move 4(MK+NK+MN) bytes for
-            # 2MNK flops (arithmetic intensity 32..100 flop/B, below the ~110 flop/B tf32 ridge), so HBM is the
-            # binding roof; ncu (profiles/) shows 51-64 % of DRAM peak on the individual launches
-            "hbm_view": {"achieved_gbs": gemm.get("algorithmic_bytes_per_step", 0.0) / (gemm["ms_per_step"] * 1e-3) / 1e9
-                         if gemm["ms_per_step"] > 0 else 0.0,
-                         "peak_gbs": peaks["hbm_gbs"],
-                         "frac": (gemm.get("algorithmic_bytes_per_step", 0.0) / (gemm["ms_per_step"] * 1e-3) / 1e9) /
-                                 peaks["hbm_gbs"] if gemm["ms_per_step"] > 0 else None,
-                         "algorithmic_bytes_per_step": gemm.get("algorithmic_bytes_per_step", 0.0),
-                         "asymmetric": asymmetric_hbm_view(args, B, gemm["ms_per_step"])},
-        },
-        "kernel_classes": prof,
         "final_loss": final_loss,
     }
+    if allreduce_us is not None:
+        out["allreduce"] = {"us": allreduce_us, "bytes": int(model.flat_gradients.numel() * 4),
+                            "note": "flat gradient bucket alone, NCCL, CUDA events, max over ranks; issued after the "
+                                    "backward on the compute stream"}
+    if top:
+        unit = "TFLOP/s" if top["bound"] == "tensor" else "GB/s"
+        out["roofline"] = {
+            "bound": top["bound"], "kernel": top["kernel"],
+            "achieved": top["tflops"] if top["bound"] == "tensor" else top["gbs"],
+            "peak": tensor_peak if top["bound"] == "tensor" else peaks["hbm_gbs"], "unit": unit, "frac": top["frac"],
+            "traffic": measured_traffic(args, B, top["kernel"]),
+            "us_per_step": top["us_per_step"], "launches_per_step": top["launches_per_step"],
+            "share_of_step": round(top["us_per_step"] / 1e3 / step_ms_profiled, 4) if step_ms_profiled else None,
+            "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json): tensor = bf16_tflops_sustained "
+                           f"{peaks['bf16_tflops_sustained']}" + (" / 2 (kind::tf32 issues at half the bf16 rate)"
+                                                                  if args.dtype != "bf16" else "") +
+                           f", HBM = copy {peaks['hbm_gbs']} GB/s",
+            "definition": "dominant kernel = largest device time per step; achieved = algorithmic flops (or bytes) of its "
+                          "launches / their CUDA-event time, measured live; frac against the roof that binds that kernel",
+            "whole_step": {"model_tflops": round(step_flops * world / (ms_total / args.steps * 1e-3) / 1e12, 2),
+                           "frac_of_tensor_peak": round(step_flops / (ms_total / args.steps * 1e-3) / 1e12 / tensor_peak, 4),
+                           "algorithmic_gbs": round(sum(k["bytes_per_step"] for k in kernels) /
+                                                    (kernel_ms * 1e-3) / 1e9, 1) if kernel_ms else None,
+                           "kernel_ms_per_step": round(kernel_ms, 3), "step_ms_profiled": round(step_ms_profiled, 3)},
+            "kernels": kernels,
+        }
     if world == 1 and not args.no_cpu_baseline:
-        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        cb, csteps = args.ref_batch, 3
-        t0 = time.time()
-        sps, ms, used = cpu_reference_steps(w, cb, csteps, 1, threads)
-        out["cpu_baseline"] = {"value": sps, "unit": "slates/s", "cores": used, "kind": "port",
-                               "sample": f"{cb} slates/step x {csteps} steps after 1 warm-up (same shapes), eager "
-                                         f"PyTorch fp32, {used} intra-op threads (fastest of 8..{threads}), "
-                                         f"{time.time() - t0:.1f}s of CPU work"}
+        out["cpu_baseline"] = cpu_baseline_subprocess(args, w)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def _traffic_capture(args, batch):
-    """The committed ncu capture of this exact workload / batch (profiles/r1_dram_traffic_b4096.json), else None."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dram_traffic_b4096.json")
+def measured_traffic(args, batch, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture of
+    this exact workload / batch (profiles/r2_dram_traffic.json: {workload: {batch: {kernel: bytes}}}), else null."""
+    path = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
     try:
         with open(path) as f:
             cap = json.load(f)
-        if args.workload == "cfg2" and int(batch) == int(cap.get("batch", -1)):
-            return cap
-    except (OSError, ValueError, TypeError):
+        per_kernel = cap[args.workload][str(int(batch))]
+        for name, val in per_kernel.items():
+            if kernel.startswith(name):
+                return val
+    except (OSError, ValueError, TypeError, KeyError):
         pass
     return None
-
-
-def measured_traffic(args, batch):
-    """DRAM bytes per step of the tcgen05 class from the committed ncu capture."""
-    cap = _traffic_capture(args, batch)
-    return cap.get("tcgen05_dram_bytes_per_step") if cap else None
-
-
-def asymmetric_hbm_view(args, batch, kernel_ms):
-    """HBM reads and writes do not cost the same on this part (profiles/README.md): the class's measured read / write
-    bytes against t = read/6.9 TB/s + write/3.25 TB/s, as a fraction of the class's measured time.  None without a
-    capture of this workload."""
-    try:
-        cap = _traffic_capture(args, batch)
-        if not cap or kernel_ms <= 0:
-            return None
-        rd, wr = float(cap["tcgen05_dram_read_bytes_per_step"]), float(cap["tcgen05_dram_write_bytes_per_step"])
-        bound_ms = (rd / (float(cap["read_gbs_model"]) * 1e9) + wr / (float(cap["write_gbs_model"]) * 1e9)) * 1e3
-        return {"read_bytes_per_step": rd, "write_bytes_per_step": wr, "bound_ms": bound_ms, "frac": bound_ms / kernel_ms,
-                "model": cap.get("model")}
-    except Exception:       # reporting extra only: never lose the bench line over it
-        return None
 
 
 def main():
@@ -426,15 +511,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="tf32", choices=["tf32"],
+                    help="arithmetic of the tensor-core products (fp32 everywhere else)")
     ap.add_argument("--batch", type=int, default=4096,
                     help="slates per step per GPU (saturating batch; 64 = allRank's default batch_size, see profiles/)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch slates per GPU; strong: --global-batch slates split over the GPUs")
+    ap.add_argument("--global-batch", type=int, default=512, help="global batch of --scaling strong (SURVEY.md 8e)")
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
+                    help="flat: allrank_b200.optim.FlatAdam; torch: torch.optim.Adam (what allrank/main.py:82 builds)")
     ap.add_argument("--ref-batch", type=int, default=64, help="slates per CPU step (reference default batch_size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allow-short-warmup", action="store_true", help="(internal: the bounded CPU leg)")
     args = ap.parse_args()
-    if args.warmup < 3:
+    if args.warmup < 3 and not args.allow_short_warmup:
         args.warmup = 3
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""      # the reference hard-wires cuda:0 when it sees a GPU
         run_reference(args, w)
     else:
         run_b200(args, w)

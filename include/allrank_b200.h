@@ -258,6 +258,11 @@ void arb_prof_enable(int32_t on);
 int32_t arb_prof_collect(int32_t cls, double* total_ms, double* total_work, int64_t* launches);
 /* algorithmic HBM bytes (operands + outputs, each counted once) summed by the last arb_prof_collect(cls, ...) */
 double arb_prof_last_bytes(int32_t cls);
+/* Per-kernel table since arb_prof_enable(1), one text line per distinct launch name:
+ *   name \t class \t launches \t total_ms \t total_work \t total_algorithmic_bytes
+ * (GEMM launches are named by shape and operand layout, the other kernels by their launcher).  Writes at most
+ * cap - 1 bytes + NUL into buf and returns the count; buf == NULL returns the size needed. */
+int64_t arb_prof_report(char* buf, int64_t cap);
 
 #ifdef __cplusplus
 }
