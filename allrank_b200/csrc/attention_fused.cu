@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
                                                                   const uint8_t* __restrict__ mask,
                                                                   float* __restrict__ stat_max,
                                                                   float* __restrict__ stat_sum, int S, int n_heads,
-                                                                  float scale_log2e, DropSite drop) {
+                                                                  float scale_log2e, DropSite drop,
+                                                                  const int* __restrict__ extent) {
+  (void)extent;   // the single-pass kernel always covers the whole slate
   using L = AttFwdSmem<DK>;
   constexpr int NKB = L::NKB;
   extern __shared__ uint8_t smem_dyn[];
@@ -248,7 +250,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
                                                                    const uint8_t* __restrict__ mask,
                                                                    float* __restrict__ stat_max,
                                                                    float* __restrict__ stat_sum, int S, int n_heads,
-                                                                   float scale_log2e, DropSite drop) {
+                                                                   float scale_log2e, DropSite drop,
+                                                                   const int* __restrict__ extent) {
   static_assert(DK <= 32, "two-pass forward kernel: head width <= 32");
   using L = AttFwdSmem<DK>;
   extern __shared__ uint8_t smem_dyn[];
@@ -267,7 +270,11 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
-  const int S16 = (S + 15) & ~15, S8 = (S + 7) & ~7;
+  // keys at or beyond the slate's extent are all masked (probability exactly 0): the score / P V products, the softmax
+  // loop and the K / V loads stop there.  At least one key column group is always processed, so an all-padded slate
+  // still produces the reference's NaN rows.
+  const int kext = extent ? max(1, min(S, extent[b])) : S;
+  const int S16 = (kext + 15) & ~15, S8 = (kext + 7) & ~7;
   const int nkc = (S16 + 127) / 128;          // key chunks
   const int nsteps = 2 * nkc;
 
@@ -300,10 +307,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(load_bar, L::Q_BYTES + L::K_BYTES + L::V_BYTES);
+      // K and V arrive as 128-key boxes: only the chunks that hold keys below the extent are fetched
+      ptx::mbar_expect_tx(load_bar, L::Q_BYTES + nkc * 2 * (128 * 128));
       ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, m0, head, b);
-      ptx::tma_load_4d(k_s, &tmK, load_bar, 0, 0, head, b);
-      ptx::tma_load_4d(v_s, &tmV, load_bar, 0, 0, head, b);
+      for (int kc = 0; kc < nkc; ++kc) {
+        ptx::tma_load_4d(k_s + kc * 16384, &tmK, load_bar, 0, 128 * kc, head, b);
+        ptx::tma_load_4d(v_s + kc * 16384, &tmV, load_bar, 0, 128 * kc, head, b);
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -440,12 +450,13 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   alignas(64) CUtensorMap tQ, tK, tV, tO;
   int rc;
   if ((rc = make_tmap_4d(&tQ, a.q, TmapBox{{32, 128, 1, 1}}, 0, 1))) return rc;
-  if ((rc = make_tmap_4d(&tK, a.k, TmapBox{{32, 256, 1, 1}}, 0, 1))) return rc;
-  if ((rc = make_tmap_4d(&tV, a.v, TmapBox{{32, 256, 1, 1}}, 1, 1))) return rc;
+  const uint32_t kv_rows = (DK <= 32 && g_attn_fwd_two_pass) ? 128u : 256u;   // two-pass kernel: one box per key chunk
+  if ((rc = make_tmap_4d(&tK, a.k, TmapBox{{32, kv_rows, 1, 1}}, 0, 1))) return rc;
+  if ((rc = make_tmap_4d(&tV, a.v, TmapBox{{32, kv_rows, 1, 1}}, 1, 1))) return rc;
   if ((rc = make_tmap_4d(&tO, a.o, TmapBox{{32, 128, 1, 1}}, 0, 0))) return rc;
   const bool drop = a.drop.thresh != 0;
   void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const uint8_t*, float*, float*, int, int, float,
-               DropSite);
+               DropSite, const int*);
   if constexpr (DK <= 32) {
     if (g_attn_fwd_two_pass) kern = drop ? attn_fwd2_kernel<DK, true> : attn_fwd2_kernel<DK, false>;
     else kern = drop ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
@@ -469,7 +480,7 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
                  (DK <= 32 && g_attn_fwd_two_pass) ? "attn_fwd2_kernel" : "attn_fwd_kernel");
     const int threads = (DK <= 32 && g_attn_fwd_two_pass) ? ATT2_THREADS : ATT_THREADS;
     kern<<<grid, threads, L::total(), st>>>(tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
-                                               a.scale * 1.4426950408889634f, a.drop);
+                                               a.scale * 1.4426950408889634f, a.drop, a.extent);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

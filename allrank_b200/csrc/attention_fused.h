@@ -15,6 +15,8 @@ struct AttnFwdArgs {
   int B, h, S, dk;
   float scale;                // 1/sqrt(dk)
   DropSite drop{0u, 0u, 1.0f};   // dropout on the probabilities (transformer.py:154-155); index ((b*h+head)*S+q)*S+key
+  const int* extent = nullptr;   // optional [B]: every key >= extent[b] is masked (slate_extents); work beyond it is
+                                 // skipped -- those keys have probability exactly 0, so the result is unchanged
 };
 
 bool attn_fused_supported(int S, int dk);
@@ -40,6 +42,10 @@ struct AttnBwdArgs {
   int B, h, S, dk;
   float scale;
   DropSite drop{0u, 0u, 1.0f};
+  const int* extent = nullptr;   // optional [B]: rows >= extent[b] are masked keys whose d ctx rows are exactly zero
+                                 // (slate_extents over the mask and the incoming score gradient): their tiles are
+                                 // skipped and their dQ / dK / dV rows written as zeros -- exactly what the dense
+                                 // computation produces
 };
 
 bool attn_fused_bwd_supported(int S, int dk);

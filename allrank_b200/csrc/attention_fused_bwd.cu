@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
     const uint8_t* __restrict__ mask, const float* __restrict__ stat_max, const float* __restrict__ stat_sum,
     const float* __restrict__ delta, int S, int n_heads, float scale, DropSite drop, float* __restrict__ dbias_qkv,
-    int d_model) {
+    int d_model, const int* __restrict__ extent) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   auto tile = [&](int t) { return smem + t * TILE_BYTES; };
@@ -118,7 +118,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x, b = blockIdx.y;
-  const int n_kt = (S + 127) / 128;     // key tiles == query chunks
+  // Rows at or beyond the slate's extent are masked keys (probability exactly 0) whose d ctx rows are exactly zero:
+  // neither their key tiles nor their query chunks contribute anything, and their dQ / dK / dV rows are zero.  Only
+  // the tiles below the extent are processed; the rest is written as zeros up front.
+  const int n_full = (S + 127) / 128;
+  const int ext = extent ? max(1, min(S, extent[b])) : S;
+  const int n_kt = (ext + 127) / 128;   // active key tiles == active query chunks
   const float c_log2e = scale * 1.4426950408889634f;
 
   if (warp == 0 && lane == 0) {
@@ -261,6 +266,22 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       }
       qstats[(t & 1) * 128 + slot] = st;
     };
+    if (n_kt < n_full) {
+      // zero rows of the skipped tiles: one zero slab, TMA-stored over every skipped dQ / dK / dV tile (TMA clips at S)
+      for (int i = ct; i < TILE_BYTES / 16; i += BWD_COMPUTE) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0u, 0u, 0u, 0u);
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(1, BWD_COMPUTE);
+      if (ct == 0) {
+        for (int jt = n_kt; jt < n_full; ++jt) {
+          ptx::tma_store_4d(&tmDQ, stage, 0, 128 * jt, head, b);
+          ptx::tma_store_4d(&tmDK, stage, 0, 128 * jt, head, b);
+          ptx::tma_store_4d(&tmDV, stage, 0, 128 * jt, head, b);
+        }
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_read();
+      }
+      ptx::named_bar_sync(1, BWD_COMPUTE);
+    }
     if (ct < 128) load_stats(0, ct);
 
     // Outputs of iteration `e_it` that became final with it: dV / dK of its key tile after the last query chunk, dQ of
@@ -430,7 +451,7 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
                  4.0 * double(a.B) * a.h * a.S * (7.0 * a.dk + 3.0), "attn_bwd_kernel");
     kern<<<grid, BWD_THREADS, BwdSmem::total(), st>>>(tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
                                                       a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale, a.drop, a.dbias_qkv,
-                                                      a.d_model);
+                                                      a.d_model, a.extent);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

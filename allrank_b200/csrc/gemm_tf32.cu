@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&acc_full[a], 1); ptx::mbar_init(&acc_empty[a], EPI_THREADS); }
     ptx::mbar_init(aux_full, 1);
-    ptx::mbar_init(stage_free, 1);
+    ptx::mbar_init(stage_free, N_SLABS >= 2 ? 2 : 1);   // one arrival per epilogue group that stores
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -432,11 +432,19 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9: two warps per TMEM lane quadrant, alternating 32-column slabs) ====
+    // ===================== epilogue (warps 2..9) =====================
+    // Two GROUPS of four warps (one warp per TMEM lane quadrant each), group g owning the 32-column slabs g, g+2 of
+    // the tile.  A group turns one slab TMEM -> registers -> swizzled staging and its leader immediately issues that
+    // slab's TMA store; the staging slab is reclaimed lazily (cp.async.bulk.wait_group.read) right before the group
+    // writes it again one tile later.  Stores, staging writes and the other group's work therefore overlap, and no
+    // barrier spans more than the 128 threads of a group.
     const int q = warp & 3;
     const int row = 32 * q + lane;
-    const int et = threadIdx.x - 64;
-    const int slab_par = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;                    // 0 or 1
+    const int gt = threadIdx.x - 64 - 128 * grp;        // 0..127 inside the group
+    const bool leader = gt == 0;
+    constexpr int SLABS_PER_GROUP = N_SLABS >= 2 ? N_SLABS / 2 : 1;
+    const bool active = N_SLABS >= 2 || grp == 0;       // a 32-wide tile has a single slab: group 1 only drains barriers
     int local = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
       int n0, m0, z, kb0, nkb;
@@ -445,85 +453,111 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
       const int b2 = split ? 0 : z % p.nb2, b3 = split ? 0 : z / p.nb2;
       const int acc = local & 1;
       const uint32_t use = local >> 1;
-      if (p.flags & EPI_BIAS) {
-        for (int j = et; j < BLOCK_N; j += EPI_THREADS) bias_s[j] = (n0 + j < p.N) ? p.bias[n0 + j] : 0.0f;
+      if (active && (p.flags & EPI_BIAS)) {             // this group's columns only (ordered by the group barriers)
+        for (int j = gt; j < 32 * SLABS_PER_GROUP; j += 128) {
+          const int col = 32 * (grp + 2 * (j >> 5)) + (j & 31);
+          bias_s[col] = (n0 + col < p.N) ? p.bias[n0 + col] : 0.0f;
+        }
       }
-      // staging must be free before we write it: without an aux tile the producer does not wait on stage_free,
-      // so the epilogue (the only other user) does
-      if (!split && !has_aux && local > 0) ptx::mbar_wait(stage_free, (local - 1) & 1);
-      ptx::named_bar_sync(1, EPI_THREADS);
       ptx::mbar_wait(&acc_full[acc], use & 1);
       ptx::tc_fence_after();
       if (has_aux) ptx::mbar_wait(aux_full, local & 1);
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+      if (active) {
 #pragma unroll 1
-      for (int c = (N_SLABS > 1 ? slab_par : 0); c < (N_SLABS > 1 || slab_par == 0 ? N_SLABS : 0); c += (N_SLABS > 1 ? 2 : 1)) {
-        uint32_t v[32];
-        if (nkb > 0) {
-          ptx::tmem_ld_32x32(d_tmem + (uint32_t(32 * q) << 16) + uint32_t(32 * c), v);
-          ptx::tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
-        }
-        uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
-#pragma unroll
-        for (int piece = 0; piece < 8; ++piece) {
-          float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = piece * 4 + e;
-            float x = __uint_as_float(v[j]) * p.alpha;
-            if (p.flags & EPI_BIAS) x += bias_s[32 * c + j];
-            if (p.flags & EPI_RELU) x = fmaxf(x, 0.0f);
-            if (p.flags & EPI_DROPOUT) {
-              const unsigned long long idx = (unsigned long long)(m0 + row) * (unsigned long long)p.N + (n0 + 32 * c + j);
-              x = drop_keep(idx, p.drop.seed, p.drop.thresh) ? x * p.drop.scale : 0.0f;
-            }
-            o[e] = x;
+        for (int ci = 0; ci < SLABS_PER_GROUP; ++ci) {
+          const int c = N_SLABS >= 2 ? grp + 2 * ci : 0;
+          // reclaim the slab: every store this leader committed except the most recent (SLABS_PER_GROUP - 1) ones has
+          // been read out of shared memory -- in particular the one that used slab c a tile ago.  With an aux tile
+          // the leader already drained its stores before the producer refilled the staging area.
+          if (!split && !has_aux && leader && local > 0) {
+            if constexpr (SLABS_PER_GROUP == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else ptx::tma_store_wait_read();
           }
-          if (has_aux) {
-            const float4 a = *dst;
-            if (p.flags & EPI_ADD_AUX) { o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w; }
-            if (p.flags & EPI_MASK_AUX) {
-              o[0] = a.x > 0.f ? o[0] : 0.f; o[1] = a.y > 0.f ? o[1] : 0.f;
-              o[2] = a.z > 0.f ? o[2] : 0.f; o[3] = a.w > 0.f ? o[3] : 0.f;
-            }
-          }
-          if (split) {
-            const int gm = m0 + row, gn = n0 + 32 * c + piece * 4;
-            if (gm < p.M && gn < p.N) {
-              float* dstg = p.atomic_out + (long long)gm * p.atomic_ld + gn;
-              if (gn + 3 < p.N && (p.atomic_ld & 3) == 0) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstg), "f"(o[0]), "f"(o[1]), "f"(o[2]),
-                             "f"(o[3]) : "memory");
-              } else {
+          ptx::named_bar_sync(1 + grp, 128);
+          uint32_t v[32];
+          if (nkb > 0) {
+            ptx::tmem_ld_32x32(d_tmem + (uint32_t(32 * q) << 16) + uint32_t(32 * c), v);
+            ptx::tmem_ld_wait();
+          } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (gn + e < p.N) atomicAdd(dstg + e, o[e]);
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
+#pragma unroll
+          for (int piece = 0; piece < 8; ++piece) {
+            float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = piece * 4 + e;
+              float x = __uint_as_float(v[j]) * p.alpha;
+              if (p.flags & EPI_BIAS) x += bias_s[32 * c + j];
+              if (p.flags & EPI_RELU) x = fmaxf(x, 0.0f);
+              if (p.flags & EPI_DROPOUT) {
+                const unsigned long long idx = (unsigned long long)(m0 + row) * (unsigned long long)p.N + (n0 + 32 * c + j);
+                x = drop_keep(idx, p.drop.seed, p.drop.thresh) ? x * p.drop.scale : 0.0f;
+              }
+              o[e] = x;
+            }
+            if (has_aux) {
+              const float4 a = *dst;
+              if (p.flags & EPI_ADD_AUX) { o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w; }
+              if (p.flags & EPI_MASK_AUX) {
+                o[0] = a.x > 0.f ? o[0] : 0.f; o[1] = a.y > 0.f ? o[1] : 0.f;
+                o[2] = a.z > 0.f ? o[2] : 0.f; o[3] = a.w > 0.f ? o[3] : 0.f;
               }
             }
-          } else {
-            *dst = make_float4(o[0], o[1], o[2], o[3]);
+            if (split) {
+              const int gm = m0 + row, gn = n0 + 32 * c + piece * 4;
+              if (gm < p.M && gn < p.N) {
+                float* dstg = p.atomic_out + (long long)gm * p.atomic_ld + gn;
+                if (gn + 3 < p.N && (p.atomic_ld & 3) == 0) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstg), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                               "f"(o[3]) : "memory");
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (gn + e < p.N) atomicAdd(dstg + e, o[e]);
+                }
+              }
+            } else {
+              *dst = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          if (!split) {
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(1 + grp, 128);
+            if (leader) {
+              ptx::tma_store_4d(&tmC, staging + c * (BLOCK_M * 128), n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
+              ptx::tma_store_commit();
+            }
+            if (p.flags & EPI_COLSUM) {
+              // bias gradient fused into the epilogue: 4 threads per output column, 32 staged rows each (conflict-free
+              // under the 128B swizzle), combined by shuffles.  Rows past M hold exact zeros.  The slab is not
+              // rewritten before this group's next barrier.
+              const int cc = gt >> 2, seg = gt & 3;
+              const uint8_t* slab = staging + c * (BLOCK_M * 128);
+              float tsum = 0.f;
+#pragma unroll 8
+              for (int r = 32 * seg; r < 32 * seg + 32; ++r)
+                tsum += *reinterpret_cast<const float*>(slab + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
+              tsum += __shfl_xor_sync(0xffffffffu, tsum, 1);
+              tsum += __shfl_xor_sync(0xffffffffu, tsum, 2);
+              if (seg == 0 && n0 + 32 * c + cc < p.N) atomicAdd(p.colsum_out + n0 + 32 * c + cc, tsum);
+            }
           }
         }
       }
       // this accumulator may be overwritten by the MMA warp from now on
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_empty[acc]);
-      if (!split) {
-        ptx::fence_proxy_async_smem();
-        ptx::named_bar_sync(1, EPI_THREADS);
-        if (et == 0) {
-          for (int c = 0; c < N_SLABS; ++c)
-            ptx::tma_store_4d(&tmC, staging + c * (BLOCK_M * 128), n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
-          ptx::tma_store_commit();
-          ptx::tma_store_wait_read();
-          ptx::mbar_arrive(stage_free);     // staging can take the next aux tile / the next output tile
-        }
+      if (!split && has_aux && active && leader) {     // the producer refills the staging area with the next aux tile
+        ptx::tma_store_wait_read();
+        ptx::mbar_arrive(stage_free);
       }
     }
+    if (!split && active && leader) ptx::tma_store_wait_read();
   }
   __syncthreads();
   if (warp == 1) {
@@ -642,7 +676,7 @@ template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
   const bool long_k = !(A_MN == 1 && B_MN == 1) && !(p.flags & EPI_ATOMIC) && d.K >= 256 && d.nb2 == 1 && d.nb3 == 1;
-  if ((g_persistent == 1 || (g_persistent == 2 && long_k)) && !(p.flags & EPI_COLSUM))
+  if (g_persistent == 1 || (g_persistent == 2 && long_k && !(p.flags & EPI_COLSUM)))
     return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
   // dropout epilogue is a separate instantiation (forward linears only) so the common path carries no mask code;
   // ring depth: 4 stages for the long split-K loops of the weight gradients (1 CTA/SM), 3 for K >= 256

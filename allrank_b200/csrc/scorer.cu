@@ -24,6 +24,9 @@ static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 // 0: unfused attention (materialised [B,h,S,S] logits, generic GEMMs)   1: fused forward kernel, unfused backward
 // 2 (default): fused forward and fused backward kernels
 static int g_attn_mode = 2;
+// 1 (default): the fused attention kernels skip the tiles that lie entirely in a slate's padding (exact: masked keys
+// have probability 0 and padded rows a zero gradient); 0: dense tiles, for A/B measurements
+static int g_skip_padding = 1;
 static bool use_fused(const arb_scorer_config& c, int S) {
   return g_attn_mode >= 1 && c.n_layers > 0 && attn_fused_supported(S, c.d_model / c.n_heads);
 }
@@ -117,6 +120,7 @@ struct WsLayout {
   int64_t xnorm, in_mean, in_std;   // input_norm output and row statistics
   struct Layer { int64_t xn1, mean1, std1, qkv, prob, smax, ssum, ctx, xmid, xn2, mean2, std2, hdn, xout; };
   Layer layer[64];
+  int64_t kext;                     // [B] ints: key extent of every slate (keys at or beyond it are all masked)
   int64_t meanf, stdf, xf, total;   // xf: final-norm output, kept only for the multi-output head
   int Sp;
   bool fused;
@@ -164,6 +168,7 @@ static void make_ws_layout(const arb_scorer_config& c, const ParamLayout& L, int
       y = shared;
     }
   }
+  W.kext = take(B);
   W.meanf = take(R);
   W.stdf = take(R);
   W.xf = (n_outputs(c) > 1 && c.n_layers > 0) ? take(R * d) : 0;
@@ -300,6 +305,9 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     if (!indices || !table) { arb_set_error("scorer: positional encoding needs indices and a table"); return ARB_E_INVALID_ARG; }
     ARB_TRY(pos_forward(xcur, reinterpret_cast<const long long*>(indices), mask, table, c.pe_rows, sqrtf(float(d)), k.R, d, st));
   }
+  int* kext = reinterpret_cast<int*>(ws + W.kext);
+  if (c.n_layers > 0 && W.fused && g_skip_padding)
+    ARB_TRY(slate_extents(mask, nullptr, 0, B, S, kext, st));   // once per call, shared by every layer
   for (int l = 0; l < c.n_layers; ++l) {
     const auto& pl = L.layer[l];
     const auto& wl = W.layer[l];
@@ -317,6 +325,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
       a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum;
       a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = 1.0f / sqrtf(float(dk));
       a.drop = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
+      a.extent = g_skip_padding ? kext : nullptr;
       ARB_TRY(launch_attn_fwd(a, st));
     } else {
       {
@@ -365,7 +374,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   return ARB_OK;
 }
 
-struct ScratchLayout { int64_t dxa, dxb, dxn, dxm, dqkv, dctx, dprob, prob, delta, dfa, dfb, total; };
+struct ScratchLayout { int64_t dxa, dxb, dxn, dxm, dqkv, dctx, dprob, prob, delta, dfa, dfb, ext, total; };
 static void make_scratch_layout(const arb_scorer_config& c, const ParamLayout& L, int B, int S, ScratchLayout& Z) {
   const int64_t R = int64_t(B) * S, d = c.d_model;
   const int Sp = int(align_up(S, 4));
@@ -388,6 +397,7 @@ static void make_scratch_layout(const arb_scorer_config& c, const ParamLayout& L
   if (c.fc_act != ARB_ACT_NONE) widest = std::max<int64_t>(widest, d);
   Z.dfa = widest ? take(R * widest) : 0;
   Z.dfb = widest ? take(R * widest) : 0;
+  Z.ext = take(B);      // [B] ints: gradient extent of every slate
   Z.total = o;
 }
 
@@ -426,6 +436,11 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   const DropSite top_site = c.n_layers > 0 ? make_drop_site(seed, c.n_layers - 1, SITE_FFN_OUT, p_drop)
                                            : (fc_act ? none_site : fc_site);
 
+  // rows at or beyond this extent are masked keys with a zero score gradient: their gradients stay exactly zero in
+  // every layer, which lets the fused attention backward skip their tiles
+  int* gext = reinterpret_cast<int*>(scratch + Z.ext);
+  const bool skip = g_skip_padding && c.n_layers > 0 && use_fused_bwd(c, S);
+  if (skip) ARB_TRY(slate_extents(mask, dscores, n_outputs(c), B, S, gext, st));
   const int has_norm = c.n_layers > 0;
   const float* xlast = c.n_layers > 0 ? ws + W.layer[c.n_layers - 1].xout : ws + W.x0;
   float* top_bias_grad = c.n_layers > 0 ? G + L.layer[c.n_layers - 1].b2 : fc_bias_grad;
@@ -483,6 +498,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
       a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = alpha;
       a.drop = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
       a.dbias_qkv = G + pl.bqkv; a.d_model = d;          // bias gradient of the QKV projection, fused
+      a.extent = skip ? gext : nullptr;
       ARB_TRY(launch_attn_bwd(a, st));
     } else {
       const DropSite site_p = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
@@ -594,6 +610,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
 using namespace arb;
 
 extern "C" void arb_set_attention_mode(int32_t mode) { g_attn_mode = mode; }
+extern "C" void arb_set_attention_skip_padding(int32_t on) { g_skip_padding = on; }
 extern "C" void arb_set_attention_fwd_two_pass(int32_t on) { set_attn_fwd_two_pass(on); }
 
 extern "C" int64_t arb_scorer_param_count(const arb_scorer_config* cfg) {

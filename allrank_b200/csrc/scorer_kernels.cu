@@ -288,6 +288,25 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(float* __restrict__ dp
   }
 }
 
+// ------------------------------------------------------------------------------------------------ slate extents
+__global__ void __launch_bounds__(256) slate_extent_kernel(const uint8_t* __restrict__ mask,
+                                                           const float* __restrict__ dscores, int n_out, int B, int S,
+                                                           int* __restrict__ extent) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int last = -1;
+  for (int r = lane; r < S; r += 32) {
+    bool live = mask[(long long)b * S + r] == 0;
+    if (!live && dscores) {
+      for (int j = 0; j < n_out; ++j) live |= dscores[((long long)b * S + r) * n_out + j] != 0.0f;
+    }
+    if (live) last = r;
+  }
+  last = warp_max_int(last);
+  if (lane == 0) extent[b] = last + 1;
+}
+
 // ------------------------------------------------------------------------------------------------ column sums
 // out[c] += sum_rows in[row, c]   (bias gradients).  A warp reads whole rows with 128-bit loads (4 rows in
 // flight per lane), 8 warps per block stride over the block's rows, then one shared-memory reduction and one
@@ -819,6 +838,12 @@ int softmax_backward(float* dp, float* prob, long long rows, int S, int pitch, c
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (site.thresh ? 16.0 : 12.0) * S, st);
   if (site.thresh) softmax_bwd_kernel<true><<<unsigned((rows + 7) / 8), 256, 0, st>>>(dp, prob, rows, S, pitch, site);
   else softmax_bwd_kernel<false><<<unsigned((rows + 7) / 8), 256, 0, st>>>(dp, prob, rows, S, pitch, site);
+  return check_launch();
+}
+
+int slate_extents(const uint8_t* mask, const float* dscores, int n_out, int B, int S, int* extent, cudaStream_t st) {
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(B) * S * (dscores ? 1.0 + 4.0 * n_out : 1.0), st);
+  slate_extent_kernel<<<unsigned((B + 7) / 8), 256, 0, st>>>(mask, dscores, n_out, B, S, extent);
   return check_launch();
 }
 

@@ -33,6 +33,10 @@ int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pit
                     DropSite site = DropSite{0u, 0u, 1.0f});
 int softmax_backward(float* dp, float* prob, long long rows, int S, int pitch, cudaStream_t st,
                      DropSite site = DropSite{0u, 0u, 1.0f});
+// extent[b] = 1 + the last item r of slate b that is a real key (mask == 0) or -- when `dscores` is given -- carries a
+// non-zero score gradient (any of its n_out outputs); 0 for a slate without such an item.  Rows at or beyond the extent
+// are padding whose activations gradients are exactly zero in every layer, and keys no query attends to.
+int slate_extents(const uint8_t* mask, const float* dscores, int n_out, int B, int S, int* extent, cudaStream_t st);
 int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st);
 int head_forward(const float* x, const float* a, const float* b, float eps, const float* w, const float* wb,
                  int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,

@@ -204,6 +204,11 @@ int32_t arb_scorer_backward(const arb_scorer_config* cfg, const float* params, c
  * head width <= 32); other shapes use the unfused path automatically.  Process-wide; exists for A/B tests. */
 void arb_set_attention_mode(int32_t mode);
 
+/* 1 (default): the fused attention kernels skip the 128-item tiles that lie entirely inside a slate's padding -- keys
+ * beyond the last real item have probability exactly 0 and rows beyond the last item that is real or carries a score
+ * gradient have exactly zero activation gradients, so results are unchanged; 0: dense tiles.  For A/B measurements. */
+void arb_set_attention_skip_padding(int32_t on);
+
 /* 1 (default): the fused attention forward runs as the two-pass / two-CTAs-per-SM kernel (head width <= 32);
  * 0: the single-pass kernel that keeps the whole S x S tile in TMEM (one CTA per SM). For A/B measurements. */
 void arb_set_attention_fwd_two_pass(int32_t on);

@@ -387,3 +387,41 @@ def test_gemm_kernel_choice_does_not_change_results(golden):
             assert torch.allclose(s, base_s, rtol=1e-5, atol=1e-6), (mode, p_drop)
             for a, b in zip(gr, base_g):
                 assert (a - b).abs().max() <= 1e-4 * max(b.abs().max().item(), 1e-6), (mode, p_drop)
+
+
+def test_skipping_padding_tiles_is_bit_identical_to_dense_tiles():
+    """The fused attention kernels stop at a slate's extent (arb_set_attention_skip_padding): keys beyond the last real
+    item have probability exactly 0 and rows beyond the last item that is real or carries a score gradient have exactly
+    zero gradients, so scores and every parameter gradient equal the dense computation BIT FOR BIT -- short slates
+    (one key tile), slates that straddle the tile boundary, full slates, and a score gradient on a padded item."""
+    from allrank_b200 import _lib
+    from allrank_b200.model import make_model
+    from allrank_b200.synth import make_slates
+    lib = _lib.lib()
+    for p in (0.0, 0.2):
+        torch.manual_seed(3)
+        model = make_model(fc_model={"sizes": [128], "input_norm": False, "activation": None, "dropout": 0.0},
+                           transformer={"N": 2, "d_ff": 256, "h": 4, "positional_encoding": None, "dropout": p},
+                           post_model={"d_output": 1, "output_activation": None}, n_features=136).cuda().train()
+        x, y, _ = make_slates(24, 240, 136, seed=19, mean_len=120, std_len=60)
+        lens = (y != -1).sum(1)
+        assert (lens <= 128).any() and (lens > 128).any()
+        y[0] = torch.where(torch.arange(240) < 240, torch.ones(240), y[0])     # one full slate
+        x[0] = torch.randn(240, 136, generator=torch.Generator().manual_seed(1))
+        x, y = x.cuda(), y.cuda()
+        w = torch.randn(24, 240, generator=torch.Generator().manual_seed(2)).cuda()
+        w = torch.where(y == -1, torch.zeros_like(w), w)
+        w[3, 200] = 0.7          # a score gradient on a PADDED item: its row must not be skipped
+        out = {}
+        for skip in (1, 0):
+            lib.arb_set_attention_skip_padding(skip)
+            try:
+                model.zero_grad(set_to_none=True)
+                torch.manual_seed(9)
+                s = model(x, y == -1, None)
+                (s * w).sum().backward()
+                out[skip] = (s.detach().clone(), model.flat_gradients.clone())
+            finally:
+                lib.arb_set_attention_skip_padding(1)
+        assert torch.equal(out[1][0], out[0][0]), p
+        assert torch.equal(out[1][1], out[0][1]), p
