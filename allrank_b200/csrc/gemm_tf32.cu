@@ -29,6 +29,11 @@ namespace arb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                    // 32 fp32 = one 128-byte swizzle row
 constexpr int UMMA_K = 8;                      // kind::tf32: 8 elements (32 bytes) per instruction
+// bf16 operands (kind::f16) keep the BYTE geometry: a k-block is still one 128-byte swizzle row (64 bf16), an
+// instruction still consumes 32 bytes of K (16 bf16), so ring stages, K-major descriptors and k-step advances are
+// shared; only MN-major tiles differ (plain SWIZZLE_128B slabs of 64 MN-elements x 64 k-rows instead of tf32's
+// 32-byte-atom slabs of 32 x 32).
+constexpr int BLOCK_K_BF16 = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
 constexpr int GEMM_THREADS = 192;
 
@@ -64,7 +69,7 @@ struct SmemLayout {
   static constexpr int total() { return body_bytes() + 256 + BLOCK_N * 4 + 1024; }
 };
 
-template <int BLOCK_N, int A_MN, int B_MN, bool DROP, int NST>
+template <int BLOCK_N, int A_MN, int B_MN, bool DROP, int NST, bool IN16 = false, bool OUT16 = false>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const __grid_constant__ CUtensorMap tmC,
@@ -73,7 +78,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
   using L = SmemLayout<BLOCK_N, NST>;
   constexpr int STAGES = L::stages();
   constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-  constexpr int N_SLABS = BLOCK_N / 32;
+  constexpr int N_SLABS = BLOCK_N / 32;                       // 32-column accumulator chunks
+  constexpr int OUT_COLS = OUT16 ? 64 : 32;                   // output columns per 128-byte staging slab row
+  constexpr int OUT_SLABS = (BLOCK_N + OUT_COLS - 1) / OUT_COLS;
+  static_assert(!OUT16 || BLOCK_N >= 64, "bf16 outputs need at least one full 128-byte slab row");
 
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -91,7 +99,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
   const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
   const bool split = (p.flags & EPI_ATOMIC) != 0;
   const int b2 = split ? 0 : int(blockIdx.z) % p.nb2, b3 = split ? 0 : int(blockIdx.z) / p.nb2;
-  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  constexpr int KELEMS = IN16 ? BLOCK_K_BF16 : BLOCK_K;       // elements of K per k-block (128 bytes either way)
+  constexpr int MN_SLAB = IN16 ? 64 : 32;                     // MN-elements per MN-major slab (128 bytes)
+  constexpr int MN_SLAB_BYTES = MN_SLAB * KELEMS * (IN16 ? 2 : 4);   // 8192 (bf16) / 4096 (tf32)
+  const int total_kb = (p.K + KELEMS - 1) / KELEMS;
   const int kb_begin = split ? int(blockIdx.z) * p.kb_per_split : 0;
   const int kb_end = split ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
   const int nkb = kb_end - kb_begin;
@@ -120,34 +131,36 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
         if (round > 0) ptx::mbar_wait(&empty_bar[s], (round - 1) & 1);
         uint8_t* a_s = smem + s * L::STAGE_BYTES;
         uint8_t* b_s = a_s + A_STAGE_BYTES;
-        const int k0 = (kb_begin + i) * BLOCK_K;
+        const int k0 = (kb_begin + i) * KELEMS;
         ptx::mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
         if (A_MN) {
-          for (int c = 0; c < BLOCK_M / 32; ++c)
-            ptx::tma_load_4d(a_s + c * 4096, &tmA, &full_bar[s], m0 + 32 * c, k0, b2 * p.a_b2, b3 * p.a_b3);
+          for (int c = 0; c < BLOCK_M / MN_SLAB; ++c)
+            ptx::tma_load_4d(a_s + c * MN_SLAB_BYTES, &tmA, &full_bar[s], m0 + MN_SLAB * c, k0, b2 * p.a_b2, b3 * p.a_b3);
         } else {
           ptx::tma_load_4d(a_s, &tmA, &full_bar[s], k0, m0, b2 * p.a_b2, b3 * p.a_b3);
         }
         if (B_MN) {
-          for (int c = 0; c < N_SLABS; ++c)
-            ptx::tma_load_4d(b_s + c * 4096, &tmB, &full_bar[s], n0 + 32 * c, k0, b2 * p.b_b2, b3 * p.b_b3);
+          for (int c = 0; c < BLOCK_N / MN_SLAB; ++c)
+            ptx::tma_load_4d(b_s + c * MN_SLAB_BYTES, &tmB, &full_bar[s], n0 + MN_SLAB * c, k0, b2 * p.b_b2, b3 * p.b_b3);
         } else {
           ptx::tma_load_4d(b_s, &tmB, &full_bar[s], k0, n0, b2 * p.b_b2, b3 * p.b_b3);
         }
       }
       if (has_aux) {
         // the residual / ReLU-mask tile goes into the staging area, i.e. over the operand ring: wait until the
-        // tensor core has finished reading it
+        // tensor core has finished reading it.  It has the output's element type: 128-byte slab rows hold 32 fp32 or
+        // 64 bf16 columns.
         if (nkb > 0) ptx::mbar_wait(tmem_full_bar, 0);
-        ptx::mbar_expect_tx(aux_bar, L::STAGING_BYTES);
-        for (int c = 0; c < N_SLABS; ++c)
-          ptx::tma_load_4d(staging + c * (BLOCK_M * 128), &tmAux, aux_bar, n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
+        ptx::mbar_expect_tx(aux_bar, OUT16 ? L::STAGING_BYTES / 2 : L::STAGING_BYTES);
+        for (int c = 0; c < OUT_SLABS; ++c)
+          ptx::tma_load_4d(staging + c * (BLOCK_M * 128), &tmAux, aux_bar, n0 + OUT_COLS * c, m0, b2 * p.c_b2, b3 * p.c_b3);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_tf32(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      constexpr uint32_t idesc = IN16 ? ptx::idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN)
+                                      : ptx::idesc_tf32(BLOCK_M, BLOCK_N, A_MN, B_MN);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES, round = i / STAGES;
         ptx::mbar_wait(&full_bar[s], round & 1);
@@ -155,15 +168,22 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
         const uint32_t a_addr = ptx::smem_u32(smem + s * L::STAGE_BYTES);
         const uint32_t b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {      // 4 instructions per k-block for both element types
           // K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); advance 32 B per K step inside the swizzle row
-          // MN-major: 32-wide slabs of [32 k-rows x 128 B] 4096 B apart (LBO); swizzle atom = 4 k-rows (512 B, SBO);
-          //           8 k-rows (1024 B) per K step
-          const uint64_t da = A_MN ? ptx::smem_desc_sw128<1>(a_addr + k * 1024, 4096, 512)
-                                   : ptx::smem_desc_sw128<2>(a_addr + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? ptx::smem_desc_sw128<1>(b_addr + k * 1024, 4096, 512)
-                                   : ptx::smem_desc_sw128<2>(b_addr + k * 32, 16, 1024);
-          ptx::mma_tf32_ss(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          // MN-major tf32: 32-wide slabs of [32 k-rows x 128 B] 4096 B apart (LBO); swizzle atom = 4 k-rows (512 B,
+          //           SBO); 8 k-rows (1024 B) per K step
+          // MN-major bf16: 64-wide slabs of [64 k-rows x 128 B] 8192 B apart (LBO); 8-k-row groups 1024 B apart (SBO);
+          //           16 k-rows (2048 B) per K step; plain SWIZZLE_128B
+          uint64_t da, db;
+          if constexpr (IN16) {
+            da = A_MN ? ptx::smem_desc_sw128<2>(a_addr + k * 2048, 8192, 1024) : ptx::smem_desc_sw128<2>(a_addr + k * 32, 16, 1024);
+            db = B_MN ? ptx::smem_desc_sw128<2>(b_addr + k * 2048, 8192, 1024) : ptx::smem_desc_sw128<2>(b_addr + k * 32, 16, 1024);
+            ptx::mma_bf16_ss(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          } else {
+            da = A_MN ? ptx::smem_desc_sw128<1>(a_addr + k * 1024, 4096, 512) : ptx::smem_desc_sw128<2>(a_addr + k * 32, 16, 1024);
+            db = B_MN ? ptx::smem_desc_sw128<1>(b_addr + k * 1024, 4096, 512) : ptx::smem_desc_sw128<2>(b_addr + k * 32, 16, 1024);
+            ptx::mma_tf32_ss(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
         }
         ptx::mma_commit(&empty_bar[s]);     // frees the stage when these MMAs have read it
       }
@@ -192,6 +212,44 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if constexpr (OUT16) {
+        // bf16 output: a 128-byte staging row holds 64 columns; this 32-column chunk fills 16-byte pieces
+        // 4*(c&1) .. +3 of slab c/2.  The aux (ReLU-mask) tile has the same layout and type.
+        uint8_t* slab_row = staging + (c >> 1) * (BLOCK_M * 128) + row * 128;
+#pragma unroll
+        for (int piece = 0; piece < 4; ++piece) {
+          uint4* dst = reinterpret_cast<uint4*>(slab_row + ((((c & 1) * 4 + piece) ^ (row & 7)) << 4));
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = piece * 8 + e;
+            float x = __uint_as_float(v[j]) * p.alpha;
+            if (p.flags & EPI_BIAS) x += bias_s[32 * c + j];
+            if (p.flags & EPI_RELU) x = fmaxf(x, 0.0f);
+            if constexpr (DROP) {
+              const unsigned long long idx = (unsigned long long)(m0 + row) * (unsigned long long)p.N + (n0 + 32 * c + j);
+              x = drop_keep(idx, p.drop.seed, p.drop.thresh) ? x * p.drop.scale : 0.0f;
+            }
+            o[e] = x;
+          }
+          if (has_aux) {                       // bf16 aux: bit 15 clear and non-zero <=> value > 0
+            const uint4 a = *dst;
+            const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t h = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+              const float av = __uint_as_float(h << 16);
+              if (p.flags & EPI_ADD_AUX) o[e] += av;
+              if (p.flags & EPI_MASK_AUX) o[e] = av > 0.f ? o[e] : 0.f;
+            }
+          }
+          uint4 pk;
+          pk.x = ptx::pack_bf16(o[0], o[1]); pk.y = ptx::pack_bf16(o[2], o[3]);
+          pk.z = ptx::pack_bf16(o[4], o[5]); pk.w = ptx::pack_bf16(o[6], o[7]);
+          *dst = pk;
+        }
+        continue;
       }
       uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
 #pragma unroll
@@ -242,19 +300,30 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(1, 128);
       if (et == 0) {
-        for (int c = 0; c < N_SLABS; ++c)
-          ptx::tma_store_4d(&tmC, staging + c * (BLOCK_M * 128), n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
+        for (int c = 0; c < OUT_SLABS; ++c)
+          ptx::tma_store_4d(&tmC, staging + c * (BLOCK_M * 128), n0 + OUT_COLS * c, m0, b2 * p.c_b2, b3 * p.c_b3);
         ptx::tma_store_commit();
       }
       if ((p.flags & EPI_COLSUM) && et < BLOCK_N && n0 + et < p.N) {
         // bias gradient fused into the epilogue: thread = output column, walks the 128 staged rows (conflict-free
-        // under the 128B swizzle).  Rows past M hold exact zeros (zero-filled operands / mask tile).
-        const uint8_t* slab = staging + (et >> 5) * (BLOCK_M * 128);
-        const int cc = et & 31;
+        // under the 128B swizzle).  Rows past M hold exact zeros (zero-filled operands / mask tile).  A bf16 output
+        // is summed as staged (bf16-rounded terms, fp32 sum).
         float t = 0.f;
+        if constexpr (OUT16) {
+          const uint8_t* slab = staging + (et >> 6) * (BLOCK_M * 128);
+          const int cc = et & 63;
 #pragma unroll 8
-        for (int r = 0; r < BLOCK_M; ++r)
-          t += *reinterpret_cast<const float*>(slab + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
+          for (int r = 0; r < BLOCK_M; ++r) {
+            const uint16_t hv = *reinterpret_cast<const uint16_t*>(slab + r * 128 + ((((cc >> 3) ^ (r & 7)) << 4) | ((cc & 7) << 1)));
+            t += __uint_as_float(uint32_t(hv) << 16);
+          }
+        } else {
+          const uint8_t* slab = staging + (et >> 5) * (BLOCK_M * 128);
+          const int cc = et & 31;
+#pragma unroll 8
+          for (int r = 0; r < BLOCK_M; ++r)
+            t += *reinterpret_cast<const float*>(slab + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
+        }
         atomicAdd(p.colsum_out + n0 + et, t);
       }
       if (et == 0) ptx::tma_store_wait_read();   // smem may be released once the TMA engine has read it
@@ -591,20 +660,25 @@ void set_tf32_round_on_load(int enable) { g_round_on_load = enable; }
 int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32, int as_tf32) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { arb_set_error("cuTensorMapEncodeTiled is not available from this driver"); return ARB_E_CUDA; }
+  const int64_t esz = t.bf16 ? 2 : 4;
+  const int64_t per16 = 16 / esz;                 // elements per 16 bytes
   cuuint64_t gdim[4], gstride[3];
   cuuint32_t bx[4], estr[4] = {1, 1, 1, 1};
   for (int i = 0; i < 4; ++i) { gdim[i] = cuuint64_t(t.dim[i] > 0 ? t.dim[i] : 1); bx[i] = box.b[i]; }
   for (int i = 1; i < 4; ++i) {
     // a broadcast / unused dimension (extent 1) still needs a legal (multiple of 16 B) stride
     int64_t s = t.stride[i];
-    if (gdim[i] == 1 && (s <= 0 || (s * 4) % 16 != 0)) s = int64_t(gdim[0]) * 4 >= 16 ? ((int64_t(gdim[0]) + 3) / 4) * 4 : 4;
-    gstride[i - 1] = cuuint64_t(s) * 4;
+    if (gdim[i] == 1 && (s <= 0 || (s * esz) % 16 != 0))
+      s = int64_t(gdim[0]) * esz >= 16 ? ((int64_t(gdim[0]) + per16 - 1) / per16) * per16 : per16;
+    gstride[i - 1] = cuuint64_t(s) * esz;
     if (gstride[i - 1] % 16 != 0) { arb_set_error("tensor map: strides must be multiples of 16 bytes"); return ARB_E_INVALID_ARG; }
   }
   if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) { arb_set_error("tensor map: base must be 16-byte aligned"); return ARB_E_INVALID_ARG; }
-  for (int i = 0; i < 4; ++i) if (bx[i] > gdim[i] && i > 0) bx[i] = bx[i];   // boxes may exceed the extent (OOB fill)
-  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out),
-                   (as_tf32 && g_round_on_load) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(t.ptr),
+  if (t.bf16 && atom32) { arb_set_error("tensor map: the 32-byte-atom swizzle is a tf32 layout"); return ARB_E_INVALID_ARG; }
+  const CUtensorMapDataType dt = t.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                        : ((as_tf32 && g_round_on_load) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                                                                        : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), dt, 4, const_cast<void*>(t.ptr),
                    gdim, gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -619,16 +693,11 @@ int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32, int as_tf32)
   return ARB_OK;
 }
 
-// Measured per launch on B200 (cfg2, B=4096, profiles/r1_gemm_persistent_vs_tiled.csv): the persistent pipeline wins
-// where the contraction is long (K >= 256: W2 forward 520 -> 477 us, dX = dH W1 458 -> 426 us, dX = dQKV Wqkv
-// 411 -> 332 us), loses on the short-K, write-heavy linears (QKV 601 -> 748 us, W1 786 -> 995 us: its epilogue is the
-// critical path, while three co-resident one-tile CTAs overlap three epilogues) and ties on the split-K weight
-// gradients.  Mode 2 (default) therefore picks it only for non-split contractions with K >= 256.
 // launch name for the per-kernel profile table: shape, operand layouts and what the epilogue does
 static void gemm_prof_name(char (&out)[56], const GemmDesc& d, const char* variant) {
   const char* kind = (d.flags & EPI_ATOMIC) ? "wgrad" : (d.nb2 * d.nb3 > 1 ? "batched" : (d.b_mn ? "dgrad" : "fwd"));
-  std::snprintf(out, sizeof out, "gemm_%s[%s M%d N%d K%d%s%s%s]", variant, kind, d.M, d.N, d.K,
-                (d.flags & EPI_RELU) ? " relu" : "", (d.flags & EPI_ADD_AUX) ? " +res" : "",
+  std::snprintf(out, sizeof out, "gemm_%s%s[%s M%d N%d K%d%s%s%s]", variant, d.A.bf16 ? (d.C.bf16 ? "_bf16o" : "_bf16") : "",
+                kind, d.M, d.N, d.K, (d.flags & EPI_RELU) ? " relu" : "", (d.flags & EPI_ADD_AUX) ? " +res" : "",
                 (d.flags & EPI_MASK_AUX) ? " mask" : "");
 }
 
@@ -672,9 +741,59 @@ static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const C
   return ARB_OK;
 }
 
+// bf16 operands (kind::f16): the one-tile-per-CTA kernel; 4-stage ring for the split-K weight gradients, else 3 stages
+// (a k-block is 64 elements, so K = 256 is four blocks); fp32 or bf16 output.
+template <int BLOCK_N, int A_MN, int B_MN>
+static int launch_bf16_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
+                         const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
+  constexpr bool WGRAD = (A_MN == 1 && B_MN == 1);
+  const bool drop = (p.flags & EPI_DROPOUT) != 0;
+  if (drop && (A_MN || B_MN)) { arb_set_error("gemm_bf16: dropout epilogue needs K-major operands"); return ARB_E_UNSUPPORTED; }
+  void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmParams) = nullptr;
+  int smem = 0, slot = 0;
+  if constexpr (WGRAD) {
+    kern = gemm_tf32_kernel<BLOCK_N, 1, 1, false, 4, true, false>; smem = SmemLayout<BLOCK_N, 4>::total(); slot = 0;
+  } else if constexpr (BLOCK_N >= 64) {
+    constexpr bool CAN_DROP = (A_MN == 0 && B_MN == 0);
+    if (d.C.bf16) {
+      if (drop) { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, CAN_DROP, 3, true, true>; slot = 1; }
+      else      { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false, 3, true, true>; slot = 2; }
+    } else {
+      if (drop) { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, CAN_DROP, 3, true, false>; slot = 3; }
+      else      { kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, false, 3, true, false>; slot = 4; }
+    }
+    smem = SmemLayout<BLOCK_N, 3>::total();
+  }
+  if (!kern) { arb_set_error("gemm_bf16: block_n must be 64 or 128"); return ARB_E_UNSUPPORTED; }
+  static bool configured[ARB_MAX_DEVICES][5] = {};
+  const int dev_slot = arb_device_slot();
+  if (!configured[dev_slot][slot]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      arb_set_error("gemm_bf16: cannot raise the dynamic shared memory limit");
+      return ARB_E_CUDA;
+    }
+    configured[dev_slot][slot] = true;
+  }
+  {
+    const double nb = double(d.nb2) * double(d.nb3);
+    const double has_x = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) ? 1.0 : 0.0;
+    const double osz = d.C.bf16 ? 2.0 : 4.0;
+    char pname[56];
+    gemm_prof_name(pname, d, "tile");
+    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
+                 nb * (2.0 * (double(d.M) * d.K + double(d.N) * d.K) + osz * (1.0 + has_x) * double(d.M) * d.N), pname);
+    kern<<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tX, p);
+  }
+  arb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { arb_set_error(cudaGetErrorString(e)); return ARB_E_CUDA; }
+  return ARB_OK;
+}
+
 template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
+  if (d.A.bf16) return launch_bf16_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
   const bool long_k = !(A_MN == 1 && B_MN == 1) && !(p.flags & EPI_ATOMIC) && d.K >= 256 && d.nb2 == 1 && d.nb3 == 1;
   if (g_persistent == 1 || (g_persistent == 2 && long_k && !(p.flags & EPI_COLSUM)))
     return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
@@ -727,21 +846,28 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
   const bool split = (d.flags & EPI_ATOMIC) != 0;
   if (split && (d.nb2 != 1 || d.nb3 != 1 || !d.atomic_out)) { arb_set_error("gemm_tf32: split-K needs an unbatched problem and atomic_out"); return ARB_E_INVALID_ARG; }
   if (!split && d.split_k != 1) { arb_set_error("gemm_tf32: split_k > 1 needs EPI_ATOMIC"); return ARB_E_INVALID_ARG; }
+  const bool in16 = d.A.bf16 != 0, out16 = d.C.bf16 != 0;
+  if ((d.B.bf16 != 0) != in16) { arb_set_error("gemm: A and B must have the same element type"); return ARB_E_INVALID_ARG; }
+  if (out16 && (!in16 || split || d.block_n < 64)) { arb_set_error("gemm: a bf16 output needs bf16 operands, no split-K and block_n >= 64"); return ARB_E_INVALID_ARG; }
+  if ((d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) && (d.Aux.bf16 != 0) != out16) { arb_set_error("gemm: the aux tile must have the output's element type"); return ARB_E_INVALID_ARG; }
+  if (in16 && (d.nb2 != 1 || d.nb3 != 1)) { arb_set_error("gemm: bf16 operands serve the unbatched linears only"); return ARB_E_UNSUPPORTED; }
+  const uint32_t kel = in16 ? 64u : 32u;          // K elements per 128-byte row
+  const uint32_t ocol = out16 ? 64u : 32u;        // output columns per 128-byte staging row
   alignas(64) CUtensorMap tA, tB, tC, tX;
   int rc;
-  if ((rc = make_tmap_4d(&tA, d.A, d.a_mn ? TmapBox{{32, 32, 1, 1}} : TmapBox{{32, 128, 1, 1}}, d.a_mn, 1))) return rc;
-  if ((rc = make_tmap_4d(&tB, d.B, d.b_mn ? TmapBox{{32, 32, 1, 1}} : TmapBox{{32, uint32_t(d.block_n), 1, 1}}, d.b_mn, 1))) return rc;
+  if ((rc = make_tmap_4d(&tA, d.A, d.a_mn ? TmapBox{{kel, kel, 1, 1}} : TmapBox{{kel, 128, 1, 1}}, d.a_mn && !in16, 1))) return rc;
+  if ((rc = make_tmap_4d(&tB, d.B, d.b_mn ? TmapBox{{kel, kel, 1, 1}} : TmapBox{{kel, uint32_t(d.block_n), 1, 1}}, d.b_mn && !in16, 1))) return rc;
   if (!split) {
-    if ((rc = make_tmap_4d(&tC, d.C, TmapBox{{32, 128, 1, 1}}, 0, 0))) return rc;
+    if ((rc = make_tmap_4d(&tC, d.C, TmapBox{{ocol, 128, 1, 1}}, 0, 0))) return rc;
   } else {
     tC = tA;
   }
   if (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) {
-    if ((rc = make_tmap_4d(&tX, d.Aux, TmapBox{{32, 128, 1, 1}}, 0, 0))) return rc;
+    if ((rc = make_tmap_4d(&tX, d.Aux, TmapBox{{ocol, 128, 1, 1}}, 0, 0))) return rc;
   } else {
     tX = tA;
   }
-  const int total_kb = (d.K + BLOCK_K - 1) / BLOCK_K;
+  const int total_kb = (d.K + int(kel) - 1) / int(kel);
   const int splits = split ? std::max(1, std::min(d.split_k, total_kb)) : 1;
   GemmParams p;
   p.M = d.M; p.N = d.N; p.K = d.K; p.nb2 = d.nb2;
@@ -793,5 +919,27 @@ extern "C" int32_t arb_gemm_tf32(const float* A, const float* B, float* C, const
   d.C = mat(C, N, M, batch, c_bstride);
   if (aux) d.Aux = mat(aux, N, M, batch, c_bstride);
   if (flags & EPI_ATOMIC) { d.atomic_out = C; d.atomic_ld = N; }
+  return launch_gemm_tf32(d, static_cast<cudaStream_t>(stream));
+}
+
+// The same building block with bf16 operands (tcgen05 kind::f16, fp32 accumulation): A, B are bfloat16 matrices in the
+// layouts described above; C (and aux, if given) is bfloat16 when out_bf16 != 0, else fp32.  With EPI_ATOMIC
+// (split-K) C must be fp32 and is accumulated into.
+extern "C" int32_t arb_gemm_bf16(const void* A, const void* B, void* C, const void* aux, const float* bias, int32_t M,
+                                 int32_t N, int32_t K, int32_t a_mn, int32_t b_mn, int32_t block_n, int32_t flags,
+                                 float alpha, int32_t split_k, int32_t out_bf16, float* colsum_out, void* stream) {
+  using namespace arb;
+  if (!A || !B || !C) { arb_set_error("arb_gemm_bf16: null pointer"); return ARB_E_INVALID_ARG; }
+  GemmDesc d;
+  d.M = M; d.N = N; d.K = K; d.a_mn = a_mn; d.b_mn = b_mn; d.block_n = block_n; d.flags = flags; d.alpha = alpha;
+  d.bias = bias; d.split_k = split_k; d.colsum_out = colsum_out;
+  auto mat = [](const void* p, int64_t inner, int64_t rows, int is16) {
+    TRef t; t.ptr = p; t.dim[0] = inner; t.dim[1] = rows; t.stride[0] = 1; t.stride[1] = inner; t.bf16 = is16; return t;
+  };
+  d.A = a_mn ? mat(A, M, K, 1) : mat(A, K, M, 1);
+  d.B = b_mn ? mat(B, N, K, 1) : mat(B, K, N, 1);
+  d.C = mat(C, N, M, out_bf16 != 0);
+  if (aux) d.Aux = mat(aux, N, M, out_bf16 != 0);
+  if (flags & EPI_ATOMIC) { d.atomic_out = static_cast<float*>(C); d.atomic_ld = N; }
   return launch_gemm_tf32(d, static_cast<cudaStream_t>(stream));
 }

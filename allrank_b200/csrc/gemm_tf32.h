@@ -8,10 +8,12 @@
 namespace arb {
 
 // A strided view of up to 4 dimensions, dim[0] contiguous (stride[0] == 1), strides in elements.
+// bf16 = 1: the elements are bfloat16 (2 bytes) -- the bf16 mode of the scorer (BASELINE config 3); else fp32.
 struct TRef {
-  const float* ptr = nullptr;
+  const void* ptr = nullptr;
   int64_t dim[4] = {1, 1, 1, 1};
   int64_t stride[4] = {1, 0, 0, 0};
+  int bf16 = 0;
 };
 
 enum : int {
@@ -40,11 +42,14 @@ struct GemmDesc {
   int64_t atomic_ld = 0;
   DropSite drop{0u, 0u, 1.0f};  // EPI_DROPOUT: element index = m * N + n (unbatched problems only)
   float* colsum_out = nullptr;  // EPI_COLSUM: [N], accumulated with atomics
+  // Element types come from the views: A and B must agree (both fp32 -> kind::tf32, both bf16 -> kind::f16, fp32
+  // accumulation either way); C may be fp32 or bf16; an Aux tile has C's type (fp32 residual into an fp32 stream,
+  // bf16 ReLU-mask tile into a bf16 gradient).  bf16 outputs need block_n >= 64.
 };
 
 int launch_gemm_tf32(const GemmDesc& d, cudaStream_t stream);   // 0 or ARB_E_*
 
-// 4-D tiled tensor map with 128-byte swizzle over fp32 data; box[0] must be 32 (=128 bytes).
+// 4-D tiled tensor map with 128-byte swizzle; box[0] must span 128 bytes (32 fp32 / 64 bf16 elements).
 struct TmapBox { uint32_t b[4]; };
 // atom32 = 0: SWIZZLE_128B (16-byte chunks); 1: SWIZZLE_128B_ATOM_32B (MN-major tf32 operands)
 // as_tf32 = 1: MMA operand (TFLOAT32 map, rounded on load when enabled); 0: plain fp32 (stores, epilogue tiles)

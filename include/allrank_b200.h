@@ -228,6 +228,13 @@ int32_t arb_gemm_tf32(const float* A, const float* B, float* C, const float* aux
                       int64_t b_bstride, int64_t c_bstride, int32_t block_n, int32_t flags, float alpha,
                       int32_t split_k, void* stream);
 
+/* The same building block with bf16 operands (tcgen05 kind::f16, fp32 accumulation) -- the matrix products of the
+ * scorer's bf16 mode (BASELINE config 3).  A and B are bfloat16; C (and aux) bfloat16 when out_bf16 != 0, else fp32;
+ * flags as for arb_gemm_tf32 (the ARB_GEMM_* values below); colsum_out: optional [N] bias-gradient accumulator. */
+int32_t arb_gemm_bf16(const void* A, const void* B, void* C, const void* aux, const float* bias, int32_t M, int32_t N,
+                      int32_t K, int32_t a_mn, int32_t b_mn, int32_t block_n, int32_t flags, float alpha,
+                      int32_t split_k, int32_t out_bf16, float* colsum_out, void* stream);
+
 /* ---------------------------------------------------------------- optimiser + profiling helpers
  * Flat Adam over the scorer's flat parameter/gradient buffers: torch.optim.Adam semantics (the optimiser the
  * reference instantiates from its config, allrank/main.py:82), one launch.  grads are multiplied by grad_scale
