@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
 // other's load / MMA / softmax phases.  Head width <= 32.  Eight softmax warps per CTA: a warp may only touch the 32
 // TMEM lanes of its quadrant, so two warps share each quadrant and split every 32-key chunk 16 / 16; the two partial
 // row maxima (after pass A) and row sums (after pass B) are combined through shared memory.
-template <int DK, bool DROP>
+template <int DK, bool DROP, bool OUT16 = false>
 __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                    const __grid_constant__ CUtensorMap tmK,
                                                                    const __grid_constant__ CUtensorMap tmV,
@@ -413,16 +413,31 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
       uint32_t v[16];                           // this warp's 16 of the (up to) 32 output columns
       ptx::tmem_ld_32x16(tmem_O + lane_addr + 16 * sub, v);
       ptx::tmem_ld_wait();
-      uint8_t* slab_row = o_s + row * 128;
+      if constexpr (OUT16) {
+        // bf16 mode: the context only feeds the output projection -- stage it as dense bfloat16 rows (32 columns =
+        // 64 bytes, unswizzled tensor map); this warp's 16 columns are bytes [32 sub, 32 sub + 32)
+        uint4* dst = reinterpret_cast<uint4*>(o_s + row * 64 + sub * 32);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int piece = 4 * sub + k;
-        float4 o;
-        o.x = __uint_as_float(v[k * 4 + 0]) * inv;
-        o.y = __uint_as_float(v[k * 4 + 1]) * inv;
-        o.z = __uint_as_float(v[k * 4 + 2]) * inv;
-        o.w = __uint_as_float(v[k * 4 + 3]) * inv;
-        *reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4)) = o;
+        for (int k = 0; k < 2; ++k) {
+          uint4 pk;
+          pk.x = ptx::pack_bf16(__uint_as_float(v[8 * k + 0]) * inv, __uint_as_float(v[8 * k + 1]) * inv);
+          pk.y = ptx::pack_bf16(__uint_as_float(v[8 * k + 2]) * inv, __uint_as_float(v[8 * k + 3]) * inv);
+          pk.z = ptx::pack_bf16(__uint_as_float(v[8 * k + 4]) * inv, __uint_as_float(v[8 * k + 5]) * inv);
+          pk.w = ptx::pack_bf16(__uint_as_float(v[8 * k + 6]) * inv, __uint_as_float(v[8 * k + 7]) * inv);
+          dst[k] = pk;
+        }
+      } else {
+        uint8_t* slab_row = o_s + row * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int piece = 4 * sub + k;
+          float4 o;
+          o.x = __uint_as_float(v[k * 4 + 0]) * inv;
+          o.y = __uint_as_float(v[k * 4 + 1]) * inv;
+          o.z = __uint_as_float(v[k * 4 + 2]) * inv;
+          o.w = __uint_as_float(v[k * 4 + 3]) * inv;
+          *reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4)) = o;
+        }
       }
     }
     ptx::fence_proxy_async_smem();
@@ -453,18 +468,24 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   const uint32_t kv_rows = (DK <= 32 && g_attn_fwd_two_pass) ? 128u : 256u;   // two-pass kernel: one box per key chunk
   if ((rc = make_tmap_4d(&tK, a.k, TmapBox{{32, kv_rows, 1, 1}}, 0, 1))) return rc;
   if ((rc = make_tmap_4d(&tV, a.v, TmapBox{{32, kv_rows, 1, 1}}, 1, 1))) return rc;
-  if ((rc = make_tmap_4d(&tO, a.o, TmapBox{{32, 128, 1, 1}}, 0, 0))) return rc;
+  const bool out16 = a.o.bf16 != 0;
+  if (out16 && !(DK <= 32 && g_attn_fwd_two_pass)) { arb_set_error("attn_fwd: a bf16 context needs the two-pass kernel (head width <= 32)"); return ARB_E_UNSUPPORTED; }
+  if ((rc = make_tmap_4d(&tO, a.o, TmapBox{{32, 128, 1, 1}}, out16 ? 2 : 0, 0))) return rc;
   const bool drop = a.drop.thresh != 0;
   void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const uint8_t*, float*, float*, int, int, float,
                DropSite, const int*);
   if constexpr (DK <= 32) {
-    if (g_attn_fwd_two_pass) kern = drop ? attn_fwd2_kernel<DK, true> : attn_fwd2_kernel<DK, false>;
-    else kern = drop ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
+    if (g_attn_fwd_two_pass) {
+      if (out16) kern = drop ? attn_fwd2_kernel<DK, true, true> : attn_fwd2_kernel<DK, false, true>;
+      else kern = drop ? attn_fwd2_kernel<DK, true> : attn_fwd2_kernel<DK, false>;
+    } else {
+      kern = drop ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
+    }
   } else {
     kern = drop ? attn_fwd_kernel<DK, true> : attn_fwd_kernel<DK, false>;
   }
-  static bool configured[ARB_MAX_DEVICES][4] = {};
-  const int slot = (drop ? 1 : 0) + ((DK <= 32 && g_attn_fwd_two_pass) ? 2 : 0);
+  static bool configured[ARB_MAX_DEVICES][8] = {};
+  const int slot = (drop ? 1 : 0) + ((DK <= 32 && g_attn_fwd_two_pass) ? 2 : 0) + (out16 ? 4 : 0);
   const int dev = arb_device_slot();
   if (!configured[dev][slot]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total()) != cudaSuccess) {
@@ -476,7 +497,7 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   dim3 grid((a.S + 127) / 128, a.h, a.B);
   {
     ProfScope ps(ARB_PROF_GEMM, 4.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
-                 4.0 * double(a.B) * a.h * a.S * (4.0 * a.dk + 2.0),
+                 4.0 * double(a.B) * a.h * a.S * ((out16 ? 3.5 : 4.0) * a.dk + 2.0),
                  (DK <= 32 && g_attn_fwd_two_pass) ? "attn_fwd2_kernel" : "attn_fwd_kernel");
     const int threads = (DK <= 32 && g_attn_fwd_two_pass) ? ATT2_THREADS : ATT_THREADS;
     kern<<<grid, threads, L::total(), st>>>(tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,

@@ -30,7 +30,8 @@ namespace arb {
 struct AttnBwdArgs {
   TRef q, k, v, d_o;          // per-head views (dk, S, h, B): saved Q/K/V and the incoming d ctx
   TRef dq, dk_, dv;           // per-head views of the outputs (into the packed d qkv buffer)
-  const float* o_ptr;         // ctx [B*S, d_model] (for delta = rowsum(dO * O))
+  const void* o_ptr;          // ctx [B*S, d_model] (for delta = rowsum(dO * O)); bfloat16 when o_bf16
+  int o_bf16 = 0;
   const float* do_ptr;        // d ctx [B*S, d_model]
   int64_t o_pitch;
   const uint8_t* mask;        // [B,S]

@@ -55,7 +55,7 @@ __device__ __forceinline__ uint32_t round_tf32_b(float x) {
 // segmented shuffle reduction over the dk/4 lanes that share a head (dk in {16, 32}: 4 or 8 lanes per head).
 __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict__ d_o, const float* __restrict__ o,
                                                          long long pitch, int B, int S, int h, int dk,
-                                                         float* __restrict__ delta) {
+                                                         float* __restrict__ delta, int o_bf16) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)B * S) return;
@@ -66,7 +66,14 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict
     float acc = 0.f;
     if (c < width) {
       const float4 a = *reinterpret_cast<const float4*>(d_o + row * pitch + c);
-      const float4 bq = *reinterpret_cast<const float4*>(o + row * pitch + c);
+      float4 bq;
+      if (o_bf16) {       // bf16 mode: the saved context is bfloat16
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(o) + row * pitch + c);
+        bq = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                         __uint_as_float(u.y & 0xffff0000u));
+      } else {
+        bq = *reinterpret_cast<const float4*>(o + row * pitch + c);
+      }
       acc = a.x * bq.x + a.y * bq.y + a.z * bq.z + a.w * bq.w;
     }
     for (int off = lanes_per_head >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
@@ -91,7 +98,7 @@ struct BwdSmem {
   static constexpr int total() { return BARS_OFF + 256 + 1024; }
 };
 
-template <int DK, bool DROP>
+template <int DK, bool DROP, bool OUT16 = false>
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const __grid_constant__ CUtensorMap tmQk, const __grid_constant__ CUtensorMap tmQm,
     const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmKm,
@@ -297,15 +304,30 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         uint32_t v[32];
         ptx::tmem_ld_32x32(src + lane_addr, v);
         ptx::tmem_ld_wait();
-        uint8_t* orow = stage + sub * TILE_BYTES + row * 128;
+        if constexpr (OUT16) {
+          // bf16 mode: dQ / dK / dV only feed the QKV weight- and input-gradient products: dense bfloat16 rows of
+          // 32 columns (64 bytes), unswizzled tensor maps
+          uint4* orow = reinterpret_cast<uint4*>(stage + sub * TILE_BYTES + row * 64);
 #pragma unroll
-        for (int piece = 0; piece < 8; ++piece) {
-          float4 o;
-          o.x = __uint_as_float(v[piece * 4 + 0]) * mul;
-          o.y = __uint_as_float(v[piece * 4 + 1]) * mul;
-          o.z = __uint_as_float(v[piece * 4 + 2]) * mul;
-          o.w = __uint_as_float(v[piece * 4 + 3]) * mul;
-          *reinterpret_cast<float4*>(orow + ((piece ^ (row & 7)) << 4)) = o;
+          for (int k = 0; k < 4; ++k) {
+            uint4 pk;
+            pk.x = ptx::pack_bf16(__uint_as_float(v[8 * k + 0]) * mul, __uint_as_float(v[8 * k + 1]) * mul);
+            pk.y = ptx::pack_bf16(__uint_as_float(v[8 * k + 2]) * mul, __uint_as_float(v[8 * k + 3]) * mul);
+            pk.z = ptx::pack_bf16(__uint_as_float(v[8 * k + 4]) * mul, __uint_as_float(v[8 * k + 5]) * mul);
+            pk.w = ptx::pack_bf16(__uint_as_float(v[8 * k + 6]) * mul, __uint_as_float(v[8 * k + 7]) * mul);
+            orow[k] = pk;
+          }
+        } else {
+          uint8_t* orow = stage + sub * TILE_BYTES + row * 128;
+#pragma unroll
+          for (int piece = 0; piece < 8; ++piece) {
+            float4 o;
+            o.x = __uint_as_float(v[piece * 4 + 0]) * mul;
+            o.y = __uint_as_float(v[piece * 4 + 1]) * mul;
+            o.z = __uint_as_float(v[piece * 4 + 2]) * mul;
+            o.w = __uint_as_float(v[piece * 4 + 3]) * mul;
+            *reinterpret_cast<float4*>(orow + ((piece ^ (row & 7)) << 4)) = o;
+          }
         }
       }
       ptx::fence_proxy_async_smem();
@@ -329,8 +351,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         if (live) {
           const uint8_t* tl = stage + which * TILE_BYTES;
 #pragma unroll 8
-          for (int r = 32 * seg; r < 32 * seg + 32; ++r)
-            t += *reinterpret_cast<const float*>(tl + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
+          for (int r = 32 * seg; r < 32 * seg + 32; ++r) {
+            if constexpr (OUT16) t += __uint_as_float(uint32_t(*reinterpret_cast<const uint16_t*>(tl + r * 64 + cc * 2)) << 16);
+            else t += *reinterpret_cast<const float*>(tl + r * 128 + ((((cc >> 2) ^ (r & 7)) << 4) | ((cc & 3) << 2)));
+          }
         }
         t += __shfl_xor_sync(FULL, t, 1);
         t += __shfl_xor_sync(FULL, t, 2);
@@ -424,26 +448,30 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   if ((rc = make_tmap_4d(&tVk, a.v, box, 0, 1))) return rc;
   if ((rc = make_tmap_4d(&tDOk, a.d_o, box, 0, 1))) return rc;
   if ((rc = make_tmap_4d(&tDOm, a.d_o, box, 1, 1))) return rc;
-  if ((rc = make_tmap_4d(&tDQ, a.dq, box, 0, 0))) return rc;
-  if ((rc = make_tmap_4d(&tDK, a.dk_, box, 0, 0))) return rc;
-  if ((rc = make_tmap_4d(&tDV, a.dv, box, 0, 0))) return rc;
+  const bool out16 = a.dq.bf16 != 0;
+  if ((a.dk_.bf16 != 0) != out16 || (a.dv.bf16 != 0) != out16) { arb_set_error("attn_bwd: dQ, dK, dV must share an element type"); return ARB_E_INVALID_ARG; }
+  if ((rc = make_tmap_4d(&tDQ, a.dq, box, out16 ? 2 : 0, 0))) return rc;
+  if ((rc = make_tmap_4d(&tDK, a.dk_, box, out16 ? 2 : 0, 0))) return rc;
+  if ((rc = make_tmap_4d(&tDV, a.dv, box, out16 ? 2 : 0, 0))) return rc;
   {
     ProfScope ps(ARB_PROF_SCORER_SIMT, double(a.B) * a.S * (8.0 * a.h * a.dk + 4.0 * a.h), st, 0.0, "attn_delta_kernel");
     const long long rows = (long long)a.B * a.S;
-    attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(a.do_ptr, a.o_ptr, a.o_pitch, a.B, a.S, a.h, a.dk,
-                                                                a.delta);
+    attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(a.do_ptr, static_cast<const float*>(a.o_ptr), a.o_pitch, a.B, a.S, a.h, a.dk,
+                                                                a.delta, a.o_bf16);
   }
   arb_count_launch();
   const bool drop = a.drop.thresh != 0;
-  auto kern = drop ? attn_bwd_kernel<DK, true> : attn_bwd_kernel<DK, false>;
-  static bool configured[ARB_MAX_DEVICES][2] = {};
+  auto kern = out16 ? (drop ? attn_bwd_kernel<DK, true, true> : attn_bwd_kernel<DK, false, true>)
+                    : (drop ? attn_bwd_kernel<DK, true> : attn_bwd_kernel<DK, false>);
+  static bool configured[ARB_MAX_DEVICES][4] = {};
   const int dev = arb_device_slot();
-  if (!configured[dev][drop ? 1 : 0]) {
+  const int cslot = (drop ? 1 : 0) + (out16 ? 2 : 0);
+  if (!configured[dev][cslot]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::total()) != cudaSuccess) {
       arb_set_error("attn_bwd: cannot raise the dynamic shared memory limit");
       return ARB_E_CUDA;
     }
-    configured[dev][drop ? 1 : 0] = true;
+    configured[dev][cslot] = true;
   }
   dim3 grid(a.h, a.B);
   {

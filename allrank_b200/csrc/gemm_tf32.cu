@@ -674,13 +674,14 @@ int make_tmap_4d(void* out, const TRef& t, TmapBox box, int atom32, int as_tf32)
     if (gstride[i - 1] % 16 != 0) { arb_set_error("tensor map: strides must be multiples of 16 bytes"); return ARB_E_INVALID_ARG; }
   }
   if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) { arb_set_error("tensor map: base must be 16-byte aligned"); return ARB_E_INVALID_ARG; }
-  if (t.bf16 && atom32) { arb_set_error("tensor map: the 32-byte-atom swizzle is a tf32 layout"); return ARB_E_INVALID_ARG; }
+  if (t.bf16 && atom32 == 1) { arb_set_error("tensor map: the 32-byte-atom swizzle is a tf32 layout"); return ARB_E_INVALID_ARG; }
   const CUtensorMapDataType dt = t.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                         : ((as_tf32 && g_round_on_load) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
                                                                         : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), dt, 4, const_cast<void*>(t.ptr),
                    gdim, gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   atom32 == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                               : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[256];

@@ -51,7 +51,8 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t stream);   // 0 or ARB_E_*
 
 // 4-D tiled tensor map with 128-byte swizzle; box[0] must span 128 bytes (32 fp32 / 64 bf16 elements).
 struct TmapBox { uint32_t b[4]; };
-// atom32 = 0: SWIZZLE_128B (16-byte chunks); 1: SWIZZLE_128B_ATOM_32B (MN-major tf32 operands)
+// atom32 = 0: SWIZZLE_128B (16-byte chunks); 1: SWIZZLE_128B_ATOM_32B (MN-major tf32 operands); 2: no swizzle (dense
+// rows narrower than 128 bytes: the bf16 outputs of the attention kernels)
 // as_tf32 = 1: MMA operand (TFLOAT32 map, rounded on load when enabled); 0: plain fp32 (stores, epilogue tiles)
 int make_tmap_4d(void* out_CUtensorMap, const TRef& t, TmapBox box, int atom32, int as_tf32);
 

@@ -60,6 +60,10 @@ static int make_param_layout(const arb_scorer_config& c, ParamLayout& L) {
     if (c.d_model / c.n_heads > 128) { arb_set_error("scorer: head width above 128 is not supported"); return ARB_E_UNSUPPORTED; }
   }
   if (c.d_model > 1024) { arb_set_error("scorer: d_model above 1024 is not supported"); return ARB_E_UNSUPPORTED; }
+  if (c.bf16 && c.n_layers > 0 && (c.d_model % 8 || c.d_ff % 8 || c.d_model < 64 || c.d_ff < 64)) {
+    arb_set_error("scorer: bf16 mode needs d_model and d_ff to be multiples of 8, at least 64");
+    return ARB_E_UNSUPPORTED;
+  }
   const int64_t d = c.d_model, F = c.n_features, f = c.d_ff;
   L.n_fc = c.n_fc_layers > 0 ? c.n_fc_layers : 1;
   if (L.n_fc > ARB_MAX_FC_LAYERS) { arb_set_error("scorer: at most 8 FC layers"); return ARB_E_UNSUPPORTED; }
@@ -121,6 +125,7 @@ struct WsLayout {
   struct Layer { int64_t xn1, mean1, std1, qkv, prob, smax, ssum, ctx, xmid, xn2, mean2, std2, hdn, xout; };
   Layer layer[64];
   int64_t kext;                     // [B] ints: key extent of every slate (keys at or beyond it are all masked)
+  int64_t wb16;                     // bf16 mode: bfloat16 shadow of the whole parameter buffer (same element offsets)
   int64_t meanf, stdf, xf, total;   // xf: final-norm output, kept only for the multi-output head
   int Sp;
   bool fused;
@@ -147,20 +152,23 @@ static void make_ws_layout(const arb_scorer_config& c, const ParamLayout& L, int
   W.fc_last = (training && c.fc_act != ARB_ACT_NONE && c.pe_mode != 0) ? take(R * d) : 0;
   W.xnorm = W.in_mean = W.in_std = 0;
   if (c.fc_input_norm) { W.xnorm = take(R * c.n_features); W.in_mean = take(R); W.in_std = take(R); }
+  // bf16 mode: tensors that only feed products (LayerNorm outputs, context, FFN hidden) are bfloat16: half the floats
+  const int64_t op = (c.bf16 && c.n_layers > 0) ? 2 : 1;
+  W.wb16 = op == 2 ? take((L.total + 1) / 2) : 0;
   WsLayout::Layer shared{};
   for (int l = 0; l < c.n_layers; ++l) {
     auto& y = W.layer[l];
     if (training || l == 0) {
-      y.xn1 = take(R * d); y.mean1 = take(R); y.std1 = take(R);
+      y.xn1 = take(R * d / op); y.mean1 = take(R); y.std1 = take(R);
       y.qkv = take(R * 3 * d);
       y.prob = W.fused ? 0 : take(int64_t(B) * h * S * W.Sp);
       y.smax = take(int64_t(B) * h * S);
       y.ssum = take(int64_t(B) * h * S);
-      y.ctx = take(R * d);
-      y.xn2 = training ? take(R * d) : y.xn1;
+      y.ctx = take(R * d / op);
+      y.xn2 = training ? take(R * d / op) : y.xn1;
       y.mean2 = training ? take(R) : y.mean1;
       y.std2 = training ? take(R) : y.std1;
-      y.hdn = take(R * f);
+      y.hdn = take(R * f / op);
       y.xmid = training ? take(R * d) : W.x0;    // eval: the residual stream is updated in place
       y.xout = training ? take(R * d) : W.x0;
       shared = y;
@@ -183,14 +191,23 @@ struct Ctx {
 };
 
 // ---- GEMM helpers ------------------------------------------------------------------------------
-static TRef rows_view(const float* p, int64_t inner, int64_t rows, int64_t pitch) {
-  TRef t; t.ptr = p; t.dim[0] = inner; t.dim[1] = rows; t.stride[0] = 1; t.stride[1] = pitch; return t;
+// A pointer with its element type: fp32 (implicitly, from any float*) or bfloat16 (b16(...)) -- bf16 mode.
+struct V {
+  const void* p;
+  int bf16;
+  V(const float* q = nullptr) : p(q), bf16(0) {}
+  V(const void* q, int is16) : p(q), bf16(is16) {}
+};
+static inline V b16(const void* q) { return V(q, 1); }
+
+static TRef rows_view(V v, int64_t inner, int64_t rows, int64_t pitch) {
+  TRef t; t.ptr = v.p; t.bf16 = v.bf16; t.dim[0] = inner; t.dim[1] = rows; t.stride[0] = 1; t.stride[1] = pitch; return t;
 }
 static int pick_block_n(int n) { return n <= 32 ? 32 : (n < 128 ? 64 : 128); }
 
 // Y[R,out] = epi( X[R,in] W[out,in]^T + bias )
-static int linear_fwd(const Ctx& k, const float* X, int64_t x_pitch, int in, const float* Wt, const float* bias, int out,
-                      float* Y, int64_t y_pitch, int flags, const float* aux, int64_t aux_pitch,
+static int linear_fwd(const Ctx& k, V X, int64_t x_pitch, int in, V Wt, const float* bias, int out,
+                      V Y, int64_t y_pitch, int flags, V aux, int64_t aux_pitch,
                       DropSite drop = DropSite{0u, 0u, 1.0f}) {
   GemmDesc g;
   g.M = int(k.R); g.N = out; g.K = in;
@@ -199,14 +216,15 @@ static int linear_fwd(const Ctx& k, const float* X, int64_t x_pitch, int in, con
   g.A = rows_view(X, in, k.R, x_pitch);
   g.B = rows_view(Wt, in, out, in);
   g.C = rows_view(Y, out, k.R, y_pitch);
-  if (aux) g.Aux = rows_view(aux, out, k.R, aux_pitch);
+  if (aux.p) g.Aux = rows_view(aux, out, k.R, aux_pitch);
   g.bias = bias; g.flags = flags | (bias ? EPI_BIAS : 0);
   g.block_n = pick_block_n(out);
+  if (Y.bf16 && g.block_n < 64) g.block_n = 64;
   return launch_gemm_tf32(g, k.st);
 }
 // dX[R,in] = epi( dY[R,out] W[out,in] )      (W read as an MN-major B operand)
-static int linear_bwd_input(const Ctx& k, const float* dY, int64_t dy_pitch, int out, const float* Wt, int in, float* dX,
-                            int64_t dx_pitch, int flags, const float* aux, int64_t aux_pitch, float alpha = 1.0f,
+static int linear_bwd_input(const Ctx& k, V dY, int64_t dy_pitch, int out, V Wt, int in, V dX,
+                            int64_t dx_pitch, int flags, V aux, int64_t aux_pitch, float alpha = 1.0f,
                             float* colsum_out = nullptr) {
   GemmDesc g;
   g.alpha = alpha;
@@ -215,13 +233,14 @@ static int linear_bwd_input(const Ctx& k, const float* dY, int64_t dy_pitch, int
   g.A = rows_view(dY, out, k.R, dy_pitch);
   g.B = rows_view(Wt, in, out, in);          // dim0 = in (N, contiguous), dim1 = out (K)
   g.C = rows_view(dX, in, k.R, dx_pitch);
-  if (aux) g.Aux = rows_view(aux, in, k.R, aux_pitch);
+  if (aux.p) g.Aux = rows_view(aux, in, k.R, aux_pitch);
   g.flags = flags;
   g.block_n = pick_block_n(in);
+  if (dX.bf16 && g.block_n < 64) g.block_n = 64;
   return launch_gemm_tf32(g, k.st);
 }
 // dW[out,in] += dY[R,out]^T X[R,in]          (both operands MN-major, reduction over all rows, split-K)
-static int linear_bwd_weight(const Ctx& k, const float* dY, int64_t dy_pitch, int out, const float* X, int64_t x_pitch,
+static int linear_bwd_weight(const Ctx& k, V dY, int64_t dy_pitch, int out, V X, int64_t x_pitch,
                              int in, float* dW) {
   GemmDesc g;
   g.M = out; g.N = in; g.K = int(k.R); g.a_mn = 1; g.b_mn = 1;
@@ -230,15 +249,16 @@ static int linear_bwd_weight(const Ctx& k, const float* dY, int64_t dy_pitch, in
   g.flags = EPI_ATOMIC; g.atomic_out = dW; g.atomic_ld = in;
   g.block_n = pick_block_n(in);
   const int tiles = ((out + 127) / 128) * ((in + g.block_n - 1) / g.block_n);
-  const int kb = int((k.R + 31) / 32);
+  const int kel = dY.bf16 ? 64 : 32;          // rows of the batch per k-block
+  const int kb = int((k.R + kel - 1) / kel);
   // 4-stage ring => 1 CTA per SM: one wave of ~148 CTAs (fewer splits = fewer L2 reductions of the dW tile)
   g.split_k = std::max(1, std::min(kb / 8 + 1, std::max(1, 148 / tiles)));
   return launch_gemm_tf32(g, k.st);
 }
 
 // per-head strided view of a [R, pitch] activation: dims (dk, S, h, B)
-static TRef head_view(const float* p, int dk, int S, int h, int B, int64_t pitch) {
-  TRef t; t.ptr = p;
+static TRef head_view(V v, int dk, int S, int h, int B, int64_t pitch) {
+  TRef t; t.ptr = v.p; t.bf16 = v.bf16;
   t.dim[0] = dk; t.dim[1] = S; t.dim[2] = h; t.dim[3] = B;
   t.stride[0] = 1; t.stride[1] = pitch; t.stride[2] = dk; t.stride[3] = int64_t(S) * pitch;
   return t;
@@ -272,6 +292,18 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   // dropout follows the module's train()/eval() mode (the host zeroes these in eval); `training` only selects
   // whether activations are kept for a backward pass
   const float p_drop = c.dropout, p_fc = c.fc_dropout;
+  // bf16 mode (cfg.bf16): encoder linears as bfloat16 products; see include/allrank_b200.h
+  const bool bf = c.bf16 && c.n_layers > 0;
+  uint16_t* Pb = bf ? reinterpret_cast<uint16_t*>(ws + W.wb16) : nullptr;
+  if (bf) {
+    if (!use_fused_bwd(c, S)) {
+      arb_set_error("scorer: bf16 mode needs the fused attention kernels (slate_length <= 256, head width 16 or 32)");
+      return ARB_E_UNSUPPORTED;
+    }
+    ARB_TRY(convert_to_bf16(P, Pb, L.total, st));      // refresh the GEMM-operand shadow of the master weights
+  }
+  auto wt = [&](int64_t off) { return bf ? b16(Pb + off) : V(P + off); };
+  auto act = [&](float* q) { return bf ? b16(q) : V(q); };   // a product-only activation buffer of this mode
   float* xcur = ws + W.x0;
   {   // FCModel (model.py:35-44): [nn.LayerNorm(F)] then dropout(act(Linear)) per layer
     const float* hin = x;
@@ -314,14 +346,15 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     float* xn1 = ws + wl.xn1; float* qkv = ws + wl.qkv; float* prob = ws + wl.prob; float* ctx = ws + wl.ctx;
     float* xmid = ws + wl.xmid; float* xn2 = ws + wl.xn2; float* hdn = ws + wl.hdn; float* xout = ws + wl.xout;
     // ---- self-attention sublayer: x + O(attn(LN(x)))   (transformer.py:133, :105-106)
-    ARB_TRY(ln_forward(xcur, P + pl.ln1_a, P + pl.ln1_b, c.ln_eps, k.R, d, xn1, ws + wl.mean1, ws + wl.std1, st));
-    ARB_TRY(linear_fwd(k, xn1, d, d, P + pl.wqkv, P + pl.bqkv, 3 * d, qkv, 3 * d, 0, nullptr, 0));
+    ARB_TRY(ln_forward(xcur, P + pl.ln1_a, P + pl.ln1_b, c.ln_eps, k.R, d, xn1, ws + wl.mean1, ws + wl.std1, st, 0,
+                       bf ? xn1 : nullptr));
+    ARB_TRY(linear_fwd(k, act(xn1), d, d, wt(pl.wqkv), P + pl.bqkv, 3 * d, qkv, 3 * d, 0, nullptr, 0));
     if (W.fused) {
       AttnFwdArgs a;   // QK^T, key mask, softmax, PV in one kernel; the S x S tile never leaves TMEM
       a.q = head_view(qkv, dk, S, h, B, 3 * d);
       a.k = head_view(qkv + d, dk, S, h, B, 3 * d);
       a.v = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
-      a.o = head_view(ctx, dk, S, h, B, d);
+      a.o = head_view(act(ctx), dk, S, h, B, d);
       a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum;
       a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = 1.0f / sqrtf(float(dk));
       a.drop = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
@@ -350,13 +383,14 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
         ARB_TRY(launch_gemm_tf32(g, st));
       }
     }
-    ARB_TRY(linear_fwd(k, ctx, d, d, P + pl.wo, P + pl.bo, d, xmid, d, EPI_ADD_AUX, xcur, d,
+    ARB_TRY(linear_fwd(k, act(ctx), d, d, wt(pl.wo), P + pl.bo, d, xmid, d, EPI_ADD_AUX, xcur, d,
                        make_drop_site(seed, l, SITE_ATTN_OUT, p_drop)));
     // ---- feed-forward sublayer: x + W2 relu(W1 LN(x))   (transformer.py:134, :227)
-    ARB_TRY(ln_forward(xmid, P + pl.ln2_a, P + pl.ln2_b, c.ln_eps, k.R, d, xn2, ws + wl.mean2, ws + wl.std2, st));
-    ARB_TRY(linear_fwd(k, xn2, d, d, P + pl.w1, P + pl.b1, f, hdn, f, EPI_RELU, nullptr, 0,
+    ARB_TRY(ln_forward(xmid, P + pl.ln2_a, P + pl.ln2_b, c.ln_eps, k.R, d, xn2, ws + wl.mean2, ws + wl.std2, st, 0,
+                       bf ? xn2 : nullptr));
+    ARB_TRY(linear_fwd(k, act(xn2), d, d, wt(pl.w1), P + pl.b1, f, act(hdn), f, EPI_RELU, nullptr, 0,
                        make_drop_site(seed, l, SITE_FFN_HID, p_drop)));
-    ARB_TRY(linear_fwd(k, hdn, f, f, P + pl.w2, P + pl.b2, d, xout, d, EPI_ADD_AUX, xmid, d,
+    ARB_TRY(linear_fwd(k, act(hdn), f, f, wt(pl.w2), P + pl.b2, d, xout, d, EPI_ADD_AUX, xmid, d,
                        make_drop_site(seed, l, SITE_FFN_OUT, p_drop)));
     xcur = xout;
   }
@@ -374,7 +408,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   return ARB_OK;
 }
 
-struct ScratchLayout { int64_t dxa, dxb, dxn, dxm, dqkv, dctx, dprob, prob, delta, dfa, dfb, ext, total; };
+struct ScratchLayout { int64_t dxa, dxb, dxn, dxm, dqkv, dctx, dprob, prob, delta, dfa, dfb, ext, dy16, total; };
 static void make_scratch_layout(const arb_scorer_config& c, const ParamLayout& L, int B, int S, ScratchLayout& Z) {
   const int64_t R = int64_t(B) * S, d = c.d_model;
   const int Sp = int(align_up(S, 4));
@@ -398,6 +432,7 @@ static void make_scratch_layout(const arb_scorer_config& c, const ParamLayout& L
   Z.dfa = widest ? take(R * widest) : 0;
   Z.dfb = widest ? take(R * widest) : 0;
   Z.ext = take(B);      // [B] ints: gradient extent of every slate
+  Z.dy16 = (c.bf16 && c.n_layers > 0) ? take(R * d / 2) : 0;   // bf16 copy of the residual-stream gradient
   Z.total = o;
 }
 
@@ -426,6 +461,18 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   float* dxm = scratch + Z.dxm;      // dx seen through the dropout of the sublayer below (masked copy)
   const float p_drop = c.dropout, p_fc = c.fc_dropout;
   const bool drop_on = p_drop > 0.0f;
+  // bf16 mode: products read bfloat16 operands -- the weights' shadow (written by the forward call into the
+  // workspace), the saved bf16 activations, and bf16 copies of the gradients (dy16: the residual-stream gradient as
+  // the sublayer below receives it; dxn / dqkv: gradients that only feed products are bfloat16 outright)
+  const bool bf = c.bf16 && c.n_layers > 0;
+  if (bf && !use_fused_bwd(c, S)) {
+    arb_set_error("scorer: bf16 mode needs the fused attention kernels (slate_length <= 256, head width 16 or 32)");
+    return ARB_E_UNSUPPORTED;
+  }
+  const uint16_t* Pb = bf ? reinterpret_cast<const uint16_t*>(ws + W.wb16) : nullptr;
+  void* dy16 = bf ? static_cast<void*>(scratch + Z.dy16) : nullptr;
+  auto wt = [&](int64_t off) { return bf ? b16(Pb + off) : V(P + off); };
+  auto act = [&](const float* q) { return bf ? b16(q) : V(q); };
   // site whose mask the gradient of the residual stream must pass through right below the head / final norm
   // The last FC layer's dropout mask (and its bias gradient) is folded into the kernel that emits the gradient of the
   // FC output -- unless the FC block has an activation: then act_backward below does both.
@@ -449,7 +496,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
       ARB_TRY(head_multi_backward(dscores, scores, ws + W.xf, P + L.head_w, c.out_act, k.R, d, n_outputs(c), dxn,
                                   G + L.head_w, G + L.head_b, st));
       ARB_TRY(ln_backward(dxn, xlast, P + L.lnf_a, ws + W.meanf, ws + W.stdf, c.ln_eps, nullptr, k.R, d, dx,
-                          G + L.lnf_a, G + L.lnf_b, st, dxm, top_site, top_bias_grad));
+                          G + L.lnf_a, G + L.lnf_b, st, dxm, top_site, top_bias_grad, 0, nullptr, dy16));
     } else {
       ARB_TRY(head_multi_backward(dscores, scores, xlast, P + L.head_w, c.out_act, k.R, d, n_outputs(c), dx,
                                   G + L.head_w, G + L.head_b, st, dxm, top_site, top_bias_grad));
@@ -458,7 +505,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(head_backward(dscores, scores, xlast, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr,
                           ws + W.meanf, ws + W.stdf, c.ln_eps, P + L.head_w, P + L.head_b, has_norm, c.out_act, k.R, d,
                           dx, has_norm ? G + L.lnf_a : nullptr, has_norm ? G + L.lnf_b : nullptr, G + L.head_w,
-                          G + L.head_b, st, dxm, top_site, top_bias_grad));
+                          G + L.head_b, st, dxm, top_site, top_bias_grad, dy16));
   }
   const float* dy = top_site.thresh ? dxm : dx;   // gradient w.r.t. the output of the linear below the dropout
   for (int l = c.n_layers - 1; l >= 0; --l) {
@@ -469,31 +516,40 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     float* prob = W.fused ? scratch + Z.prob : ws + wl.prob;
     float* xmid = ws + wl.xmid; float* xn2 = ws + wl.xn2; float* hdn = ws + wl.hdn;
     // ---- feed-forward sublayer backward:  xout = xmid + W2 relu(W1 xn2 + b1) + b2
-    ARB_TRY(linear_bwd_weight(k, dy, d, d, hdn, f, f, G + pl.w2));   // (b2 gradient: fused into the kernel that emitted dy)
+    const V dyv = bf ? b16(dy16) : V(dy);      // what the sublayer's products read as the incoming gradient
+    ARB_TRY(linear_bwd_weight(k, dyv, d, d, act(hdn), f, f, G + pl.w2));   // (b2 gradient: fused into the kernel that emitted dy)
     // hdn <- d hdn in place; hdn > 0 <=> ReLU active AND kept by the hidden dropout, so the mask tile also carries
     // the dropout mask and only the 1/(1-p) scale is needed
-    ARB_TRY(linear_bwd_input(k, dy, d, d, P + pl.w2, f, hdn, f, EPI_MASK_AUX | EPI_COLSUM, hdn, f,
+    ARB_TRY(linear_bwd_input(k, dyv, d, d, wt(pl.w2), f, act(hdn), f, EPI_MASK_AUX | EPI_COLSUM, act(hdn), f,
                              drop_on ? 1.0f / (1.0f - p_drop) : 1.0f, G + pl.b1));   // b1 gradient in the epilogue
-    ARB_TRY(linear_bwd_weight(k, hdn, f, f, xn2, d, d, G + pl.w1));
-    ARB_TRY(linear_bwd_input(k, hdn, f, f, P + pl.w1, d, dxn, d, 0, nullptr, 0));
+    ARB_TRY(linear_bwd_weight(k, act(hdn), f, f, act(xn2), d, d, G + pl.w1));
+    ARB_TRY(linear_bwd_input(k, act(hdn), f, f, wt(pl.w1), d, act(dxn), d, 0, nullptr, 0));
     const DropSite site_ao = make_drop_site(seed, l, SITE_ATTN_OUT, p_drop);
     ARB_TRY(ln_backward(dxn, xmid, P + pl.ln2_a, ws + wl.mean2, ws + wl.std2, c.ln_eps, dx, k.R, d, dx_alt,
-                        G + pl.ln2_a, G + pl.ln2_b, st, dxm, site_ao, G + pl.bo));
+                        G + pl.ln2_a, G + pl.ln2_b, st, dxm, site_ao, G + pl.bo, 0, bf ? dxn : nullptr, dy16));
     // dx_alt = d loss / d xmid ; dy = the same through the dropout on the attention sublayer output
     dy = site_ao.thresh ? dxm : dx_alt;
     // ---- attention sublayer backward:  xmid = xin + Wo ctx + bo
-    ARB_TRY(linear_bwd_weight(k, dy, d, d, ctx, d, d, G + pl.wo));   // (bo gradient: fused into the LayerNorm backward above)
-    ARB_TRY(linear_bwd_input(k, dy, d, d, P + pl.wo, d, dctx, d, 0, nullptr, 0));
+    const V dyo = bf ? b16(dy16) : V(dy);
+    ARB_TRY(linear_bwd_weight(k, dyo, d, d, act(ctx), d, d, G + pl.wo));   // (bo gradient: fused into the LayerNorm backward above)
+    ARB_TRY(linear_bwd_input(k, dyo, d, d, wt(pl.wo), d, dctx, d, 0, nullptr, 0));
     if (use_fused_bwd(c, S)) {
       AttnBwdArgs a;   // dQ, dK, dV from d ctx in one kernel; P is recomputed in TMEM from the saved row statistics
       a.q = head_view(qkv, dk, S, h, B, 3 * d);
       a.k = head_view(qkv + d, dk, S, h, B, 3 * d);
       a.v = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
       a.d_o = head_view(dctx, dk, S, h, B, d);
-      a.dq = head_view(dqkv, dk, S, h, B, 3 * d);
-      a.dk_ = head_view(dqkv + d, dk, S, h, B, 3 * d);
-      a.dv = head_view(dqkv + 2 * d, dk, S, h, B, 3 * d);
-      a.o_ptr = ctx; a.do_ptr = dctx; a.o_pitch = d;
+      if (bf) {   // dQ | dK | dV as one packed bfloat16 [R, 3d] buffer
+        uint16_t* g16 = reinterpret_cast<uint16_t*>(dqkv);
+        a.dq = head_view(b16(g16), dk, S, h, B, 3 * d);
+        a.dk_ = head_view(b16(g16 + d), dk, S, h, B, 3 * d);
+        a.dv = head_view(b16(g16 + 2 * d), dk, S, h, B, 3 * d);
+      } else {
+        a.dq = head_view(dqkv, dk, S, h, B, 3 * d);
+        a.dk_ = head_view(dqkv + d, dk, S, h, B, 3 * d);
+        a.dv = head_view(dqkv + 2 * d, dk, S, h, B, 3 * d);
+      }
+      a.o_ptr = ctx; a.o_bf16 = bf ? 1 : 0; a.do_ptr = dctx; a.o_pitch = d;
       a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum; a.delta = scratch + Z.delta;
       a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = alpha;
       a.drop = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
@@ -553,15 +609,16 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
         ARB_TRY(launch_gemm_tf32(g, st));
       }
     }
-    ARB_TRY(linear_bwd_weight(k, dqkv, 3 * d, 3 * d, xn1, d, d, G + pl.wqkv));
+    ARB_TRY(linear_bwd_weight(k, act(dqkv), 3 * d, 3 * d, act(xn1), d, d, G + pl.wqkv));
     if (!use_fused_bwd(c, S)) ARB_TRY(colsum_accumulate(dqkv, k.R, 3 * d, 3 * d, G + pl.bqkv, st));
-    ARB_TRY(linear_bwd_input(k, dqkv, 3 * d, 3 * d, P + pl.wqkv, d, dxn, d, 0, nullptr, 0));
+    ARB_TRY(linear_bwd_input(k, act(dqkv), 3 * d, 3 * d, wt(pl.wqkv), d, act(dxn), d, 0, nullptr, 0));
     DropSite site_below = l > 0 ? make_drop_site(seed, l - 1, SITE_FFN_OUT, p_drop) : (fc_act ? none_site : fc_site);
     // with a positional encoding the encoder input is sqrt(d) * fc_out + pe: the gradient that reaches the FC
     // (through its dropout mask, if any) carries the extra sqrt(d)
     if (l == 0 && c.pe_mode != 0 && !fc_act) site_below.scale *= sqrtf(float(d));
     ARB_TRY(ln_backward(dxn, xin, P + pl.ln1_a, ws + wl.mean1, ws + wl.std1, c.ln_eps, dx_alt, k.R, d, dx,
-                        G + pl.ln1_a, G + pl.ln1_b, st, dxm, site_below, l > 0 ? G + L.layer[l - 1].b2 : fc_bias_grad));
+                        G + pl.ln1_a, G + pl.ln1_b, st, dxm, site_below, l > 0 ? G + L.layer[l - 1].b2 : fc_bias_grad,
+                        0, bf ? dxn : nullptr, l > 0 ? dy16 : nullptr));   // (the FC block below layer 0 stays TF32)
     // dx = d loss / d xin ; dy = the same through the dropout that produced xin's last summand
     dy = (site_below.thresh || site_below.scale != 1.0f) ? dxm : dx;
   }

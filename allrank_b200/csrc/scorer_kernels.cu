@@ -39,6 +39,37 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int width, int 
   }
 }
 
+// bf16 rows (the scorer's bf16 mode keeps GEMM operands -- LayerNorm outputs, hidden activations, the gradients that
+// feed weight / input-gradient products -- as bfloat16): a lane's 4 elements are 8 bytes.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <int NV>
+__device__ __forceinline__ void load_row_bf16(const uint16_t* __restrict__ p, int width, int lane, RowRegs<NV>& r) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + 128 * k;
+    if (c < width) {
+      const uint2 u = *reinterpret_cast<const uint2*>(p + c);
+      r.v[k] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                           __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    } else {
+      r.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+template <int NV>
+__device__ __forceinline__ void store_row_bf16(uint16_t* __restrict__ p, int width, int lane, const RowRegs<NV>& r) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + 128 * k;
+    if (c < width)
+      *reinterpret_cast<uint2*>(p + c) = make_uint2(pack_bf16x2(r.v[k].x, r.v[k].y), pack_bf16x2(r.v[k].z, r.v[k].w));
+  }
+}
+
 template <int NV>
 __device__ __forceinline__ void apply_drop(RowRegs<NV>& r, long long row, int width, int lane, const DropSite& site) {
 #pragma unroll
@@ -61,7 +92,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
                                                                     const float* __restrict__ b, float eps,
                                                                     long long rows, int width,
                                                                     float* __restrict__ y, float* __restrict__ mean_o,
-                                                                    float* __restrict__ std_o, int torch_mode) {
+                                                                    float* __restrict__ std_o, int torch_mode,
+                                                                    uint16_t* __restrict__ y16) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -94,7 +126,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
     r.v[k].z = ga.v[k].z * (r.v[k].z - mean) / denom + gb.v[k].z;
     r.v[k].w = ga.v[k].w * (r.v[k].w - mean) / denom + gb.v[k].w;
   }
-  store_row<NV>(y + row * width, width, lane, r);
+  if (y16) store_row_bf16<NV>(y16 + row * width, width, lane, r);      // bf16 mode: the GEMM operand copy only
+  else store_row<NV>(y + row * width, width, lane, r);
   if (lane == 0) { mean_o[row] = mean; std_o[row] = sd; }
 }
 
@@ -112,7 +145,9 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
                                                                     float* __restrict__ dx, float* __restrict__ grad_a,
                                                                     float* __restrict__ grad_b,
                                                                     float* __restrict__ dx_masked, DropSite site,
-                                                                    float* __restrict__ colsum_out, int torch_mode) {
+                                                                    float* __restrict__ colsum_out, int torch_mode,
+                                                                    const uint16_t* __restrict__ dy16_in,
+                                                                    uint16_t* __restrict__ dy16_out) {
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   RowRegs<NV> ga, acc_a, acc_b, acc_c;
@@ -124,7 +159,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
     const long long row = first + it;
     if (row >= rows) break;
     RowRegs<NV> g, xr;
-    load_row<NV>(dy + row * width, width, lane, g);
+    if (dy16_in) load_row_bf16<NV>(dy16_in + row * width, width, lane, g);
+    else load_row<NV>(dy + row * width, width, lane, g);
     load_row<NV>(x + row * width, width, lane, xr);
     const float mean = mean_i[row], sd = std_i[row];
     const float r = 1.0f / (sd + eps);
@@ -174,6 +210,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
       apply_drop<NV>(g, row, width, lane, site);
       store_row<NV>(dx_masked + row * width, width, lane, g);
     }
+    // bf16 mode: the copy the weight / input-gradient GEMMs of the sublayer below read (after its dropout mask)
+    if (dy16_out) store_row_bf16<NV>(dy16_out + row * width, width, lane, g);
     if (colsum_out) {  // bias gradient of the linear below = column sums of what that linear receives
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
@@ -285,6 +323,20 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(float* __restrict__ dp
   for (int k = 0; k < MAXE; ++k) {
     const int j = lane + 32 * k;
     if (j < S) g[j] = pv[k] * (gv[k] - t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 -> bf16
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n) {
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {          // the (up to three) trailing elements
+    const float* s1 = reinterpret_cast<const float*>(src);
+    uint16_t* d1 = reinterpret_cast<uint16_t*>(dst);
+    for (long long i = 4 * n4; i < n; ++i) d1[i] = uint16_t(pack_bf16x2(s1[i], 0.f) & 0xffffu);
   }
 }
 
@@ -434,7 +486,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
     const float* __restrict__ std_i, float eps, const float* __restrict__ w, const float* __restrict__ wb,
     int has_norm, int act, long long rows, int width, int rows_per_warp, float* __restrict__ dx,
     float* __restrict__ grad_a, float* __restrict__ grad_b, float* __restrict__ grad_w, float* __restrict__ grad_wb,
-    float* __restrict__ dx_masked, DropSite site, float* __restrict__ colsum_out) {
+    float* __restrict__ dx_masked, DropSite site, float* __restrict__ colsum_out, uint16_t* __restrict__ dy16_out) {
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   __shared__ float shb[ROWS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -467,6 +519,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
       }
       store_row<NV>(dx + row * width, width, lane, g);
       if (dx_masked) { apply_drop<NV>(g, row, width, lane, site); store_row<NV>(dx_masked + row * width, width, lane, g); }
+      if (dy16_out) store_row_bf16<NV>(dy16_out + row * width, width, lane, g);
       if (colsum_out) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
@@ -518,6 +571,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
     }
     store_row<NV>(dx + row * width, width, lane, g);
     if (dx_masked) { apply_drop<NV>(g, row, width, lane, site); store_row<NV>(dx_masked + row * width, width, lane, g); }
+    if (dy16_out) store_row_bf16<NV>(dy16_out + row * width, width, lane, g);
     if (colsum_out) {
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
@@ -769,22 +823,26 @@ static int check_launch() {
 }
 
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
-               float* mean, float* sd, cudaStream_t st, int torch_mode) {
+               float* mean, float* sd, cudaStream_t st, int torch_mode, void* y16) {
   if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
-  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 8), st);
-  ARB_DISPATCH_NV(width, (ln_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, rows, width, y, mean, sd, torch_mode)));
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((y16 ? 6.0 : 8.0) * width + 8), st);
+  ARB_DISPATCH_NV(width, (ln_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16))));
   return check_launch();
 }
 
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
-                cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out, int torch_mode) {
-  if (site.thresh == 0 && site.scale == 1.0f) dx_masked = nullptr;   // thresh 0 with a scale = pure rescale (positional encoding)
+                cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out, int torch_mode,
+                const void* dy16_in, void* dy16_out) {
+  if (site.thresh == 0 && site.scale == 1.0f) dx_masked = nullptr;
+  if (dy16_out && dx_masked == nullptr && (site.thresh != 0 || site.scale != 1.0f)) {
+    arb_set_error("ln_backward: a masked bf16 copy needs the masked fp32 buffer too"); return ARB_E_INVALID_ARG;
+  }   // thresh 0 with a scale = pure rescale (positional encoding)
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((dres ? 16.0 : 12.0) * width + 8), st);
-  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode)));
+  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode, static_cast<const uint16_t*>(dy16_in), static_cast<uint16_t*>(dy16_out))));
   return check_launch();
 }
 
@@ -847,6 +905,14 @@ int slate_extents(const uint8_t* mask, const float* dscores, int n_out, int B, i
   return check_launch();
 }
 
+int convert_to_bf16(const float* src, void* dst, long long n, cudaStream_t st) {
+  const long long n4 = (n + 3) / 4;
+  ProfScope ps(ARB_PROF_SCORER_SIMT, 6.0 * double(n), st);
+  to_bf16_kernel<<<unsigned(std::max<long long>(1, std::min<long long>((n4 + 255) / 256, 148 * 8))), 256, 0, st>>>(
+      reinterpret_cast<const float4*>(src), static_cast<uint2*>(dst), n);
+  return check_launch();
+}
+
 int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st) {
   if (width % 4 || ld % 4) { arb_set_error("colsum: width and pitch must be multiples of 4"); return ARB_E_UNSUPPORTED; }
   const int rpb = 256;
@@ -869,12 +935,12 @@ int head_forward(const float* x, const float* a, const float* b, float eps, cons
 int head_backward(const float* dscore, const float* score, const float* x, const float* a, const float* b,
                   const float* mean, const float* sd, float eps, const float* w, const float* wb, int has_norm,
                   int act, long long rows, int width, float* dx, float* grad_a, float* grad_b, float* grad_w,
-                  float* grad_wb, cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out) {
+                  float* grad_wb, cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out, void* dy16_out) {
   if (site.thresh == 0) dx_masked = nullptr;
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 16), st);
-  ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out)));
+  ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out, static_cast<uint16_t*>(dy16_out))));
   return check_launch();
 }
 

@@ -11,13 +11,16 @@ namespace arb {
 // torch_mode = 1: nn.LayerNorm (biased variance, eps under the root; FCModel.input_norm, model.py:27) -- `sd` then
 // receives sqrt(var + eps) and ln_backward must be called with eps = 0 and torch_mode = 1
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
-               float* mean, float* sd, cudaStream_t st, int torch_mode = 0);
+               float* mean, float* sd, cudaStream_t st, int torch_mode = 0,
+               void* y16 = nullptr);   // y16 != nullptr: write the output as bfloat16 there INSTEAD of y (bf16 mode)
 // dx = (dres ? dres : 0) + LayerNormBackward(dy); grad_a / grad_b are accumulated (atomicAdd)
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
                 cudaStream_t st, float* dx_masked = nullptr, DropSite site = DropSite{0u, 0u, 1.0f},
                 float* colsum_out = nullptr,    // colsum_out[c] += column sums of the emitted (masked) gradient
-                int torch_mode = 0);
+                int torch_mode = 0,
+                const void* dy16_in = nullptr,  // bf16 mode: dy is read from this bfloat16 buffer instead
+                void* dy16_out = nullptr);      // bf16 mode: bfloat16 copy of the emitted (masked) gradient
 int pos_forward(float* x, const long long* indices, const uint8_t* mask, const float* pe, int pe_rows, float scale,
                 long long rows, int width, cudaStream_t st);
 int pos_backward(const float* dx, const long long* indices, const uint8_t* mask, float* dpe, int pe_rows, long long rows,
@@ -37,6 +40,8 @@ int softmax_backward(float* dp, float* prob, long long rows, int S, int pitch, c
 // non-zero score gradient (any of its n_out outputs); 0 for a slate without such an item.  Rows at or beyond the extent
 // are padding whose activations gradients are exactly zero in every layer, and keys no query attends to.
 int slate_extents(const uint8_t* mask, const float* dscores, int n_out, int B, int S, int* extent, cudaStream_t st);
+// flat fp32 -> bfloat16 copy (the GEMM-operand shadow of the parameter buffer in bf16 mode); n multiple of 4
+int convert_to_bf16(const float* src, void* dst, long long n, cudaStream_t st);
 int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st);
 int head_forward(const float* x, const float* a, const float* b, float eps, const float* w, const float* wb,
                  int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,
@@ -45,7 +50,7 @@ int head_backward(const float* dscore, const float* score, const float* x, const
                   const float* mean, const float* sd, float eps, const float* w, const float* wb, int has_norm,
                   int act, long long rows, int width, float* dx, float* grad_a, float* grad_b, float* grad_w,
                   float* grad_wb, cudaStream_t st, float* dx_masked = nullptr,
-                  DropSite site = DropSite{0u, 0u, 1.0f}, float* colsum_out = nullptr);
+                  DropSite site = DropSite{0u, 0u, 1.0f}, float* colsum_out = nullptr, void* dy16_out = nullptr);
 // d_output = n > 1: scores [rows, n] from the (already normalised) rows xf; see scorer_kernels.cu
 int head_multi_forward(const float* xf, const float* w, const float* wb, int act, long long rows, int width, int n,
                        float* score, cudaStream_t st);

@@ -48,7 +48,7 @@ class ScorerConfig(ctypes.Structure):
                 ("ln_eps", ctypes.c_float), ("dropout", ctypes.c_float), ("fc_dropout", ctypes.c_float),
                 ("pe_mode", ctypes.c_int32), ("pe_rows", ctypes.c_int32), ("d_output", ctypes.c_int32),
                 ("n_fc_layers", ctypes.c_int32), ("fc_sizes", ctypes.c_int32 * 8), ("fc_act", ctypes.c_int32),
-                ("fc_input_norm", ctypes.c_int32)]
+                ("fc_input_norm", ctypes.c_int32), ("bf16", ctypes.c_int32)]
 
 
 c_p, c_i, c_i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
@@ -177,7 +177,8 @@ class LTRModel(nn.Module):
     """B200 scorer with the reference LTRModel's surface (model.py:47-92)."""
 
     def __init__(self, n_features, d_model, n_layers, n_heads, d_ff, dropout, output_activation, fc_dropout=0.0,
-                 positional=None, d_output=1, fc_sizes=None, fc_activation=None, input_norm=False):
+                 positional=None, d_output=1, fc_sizes=None, fc_activation=None, input_norm=False,
+                 compute_dtype="tf32"):
         super().__init__()
         fc_sizes = [int(d_model)] if fc_sizes is None else [int(v) for v in fc_sizes]
         d_model = fc_sizes[-1]
@@ -226,7 +227,8 @@ class LTRModel(nn.Module):
         self._cfg = ScorerConfig(self._Fp, self.d_model, self.n_layers, max(self.n_heads, 1), max(self.d_ff, 4),
                                  _ACTS[output_activation], 1e-6, self.dropout_p, self.fc_dropout_p, 0, 0, self.d_output,
                                  len(fc_sizes), (ctypes.c_int32 * 8)(*fc_sizes), _ACTS[fc_activation],
-                                 1 if input_norm else 0)
+                                 1 if input_norm else 0, 0)
+        self.compute_dtype = compute_dtype
         pos = self.encoder.position if self.encoder is not None else None
         if pos is not None:
             self._cfg.pe_mode = 1 if isinstance(pos, _FixedPE) else 2
@@ -235,6 +237,25 @@ class LTRModel(nn.Module):
         self._flat_grad = None
         self._views = None
         self._anchor = None
+
+    # ---- arithmetic of the encoder's matrix products ------------------------------------------------
+    @property
+    def compute_dtype(self):
+        """"tf32" (default): tcgen05 kind::tf32 products on fp32 data.  "bf16": every encoder linear is a kind::f16
+        product of bfloat16 operands with fp32 accumulation -- bfloat16 shadow of the fp32 master weights, bfloat16
+        LayerNorm outputs / attention context / FFN hidden layer and product-only gradients; residual stream,
+        normalisation statistics, softmax, attention scores, head, loss and parameter gradients stay fp32
+        (BASELINE config 3; include/allrank_b200.h: arb_scorer_config.bf16)."""
+        return "bf16" if self._cfg.bf16 else "tf32"
+
+    @compute_dtype.setter
+    def compute_dtype(self, value):
+        if value not in ("tf32", "bf16"):
+            raise ValueError("compute_dtype must be 'tf32' or 'bf16'")
+        if value == "bf16" and self.n_layers > 0 and (self.d_model % 8 or self.d_ff % 8 or
+                                                      self.d_model // max(self.n_heads, 1) not in (16, 32)):
+            raise NotImplementedError("bf16 mode needs d_model, d_ff multiples of 8 and a head width of 16 or 32")
+        self._cfg.bf16 = 1 if value == "bf16" else 0
 
     # ---- flat parameter storage -------------------------------------------------------------------
     def _ordered(self):
@@ -431,10 +452,11 @@ def _get(cfg, name, default=None):
     return getattr(cfg, name, default)
 
 
-def make_model(fc_model, transformer, post_model, n_features):
+def make_model(fc_model, transformer, post_model, n_features, compute_dtype="tf32"):
     """Same arguments as allrank.models.model.make_model (model.py:131-151): `fc_model` dict
     {sizes, input_norm, activation, dropout}, `transformer` config object/dict {N, d_ff, h, dropout,
-    positional_encoding} or None, `post_model` dict {d_output, output_activation}."""
+    positional_encoding} or None, `post_model` dict {d_output, output_activation}.
+    Extension (after the reference's parameters): compute_dtype "tf32" | "bf16", see LTRModel.compute_dtype."""
     if not fc_model:
         raise NotImplementedError("allrank_b200 needs an input FC block (fc_model.sizes = [d_model])")
     sizes = [int(v) for v in _get(fc_model, "sizes")]     # (the reference mutates the caller's list, model.py:25; we do not)
@@ -449,4 +471,5 @@ def make_model(fc_model, transformer, post_model, n_features):
     return LTRModel(n_features, d_model, n_layers, heads, d_ff, dropout, _get(post_model, "output_activation", None),
                     fc_dropout=float(_get(fc_model, "dropout", 0.0) or 0.0), positional=positional,
                     d_output=int(_get(post_model, "d_output", 1)), fc_sizes=sizes,
-                    fc_activation=_get(fc_model, "activation", None), input_norm=bool(_get(fc_model, "input_norm", False)))
+                    fc_activation=_get(fc_model, "activation", None), input_norm=bool(_get(fc_model, "input_norm", False)),
+                    compute_dtype=compute_dtype)

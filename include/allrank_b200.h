@@ -178,6 +178,14 @@ typedef struct arb_scorer_config {
   int32_t fc_act;       /* ARB_ACT_*: fc_model.activation applied after every FC linear, before its dropout          */
   int32_t fc_input_norm;/* fc_model.input_norm: nn.LayerNorm(n_features) (eps 1e-5, biased variance) on x first;
                            needs n_features % 4 == 0 (no feature padding)                                             */
+  int32_t bf16;         /* 1: bf16 mode of the encoder (BASELINE config 3): every encoder linear runs as a tcgen05
+                           kind::f16 product of bfloat16 operands with fp32 accumulation -- weights from a bfloat16
+                           shadow of the fp32 master parameters (refreshed by every forward call), activations that only
+                           feed products (LayerNorm outputs, attention context, FFN hidden layer) and the gradients that
+                           only feed products stored as bfloat16; residual stream, LayerNorm statistics, softmax,
+                           attention scores (TF32 products on fp32 Q/K/V), head, loss and parameter gradients stay fp32.
+                           Needs the fused attention kernels (slate_length <= 256, head width 16 or 32) and
+                           d_model, d_ff multiples of 8.  0: TF32 products on fp32 data everywhere.                  */
 } arb_scorer_config;
 #define ARB_MAX_FC_LAYERS 8
 

@@ -26,8 +26,9 @@ def test_patch_and_unpatch_rebinds_the_reference_names():
         for name in integration.METRIC_NAMES:
             ref_params = list(inspect.signature(getattr(ref_metrics, name)).parameters)
             assert list(inspect.signature(getattr(metrics, name)).parameters) == ref_params, name
-        assert (list(inspect.signature(model.make_model).parameters) ==
-                list(inspect.signature(ref_model.make_model).parameters))
+        ref_params = list(inspect.signature(ref_model.make_model).parameters)
+        mine = list(inspect.signature(model.make_model).parameters)
+        assert mine[:len(ref_params)] == ref_params and mine[len(ref_params):] == ["compute_dtype"]   # one extension
         # the callers either side of the path: same parameter names as the reference functions they replace
         import allrank.training.train_utils as ref_tu
         import allrank.inference.inference_utils as ref_iu
