@@ -243,7 +243,7 @@ def kernel_table(lib, psteps, peaks, dtype):
     need = int(lib.arb_prof_report(None, 0))
     buf = ctypes.create_string_buffer(need + 64)
     lib.arb_prof_report(buf, need + 64)
-    tensor_peak = peaks["bf16_tflops_sustained"] * (1.0 if dtype == "bf16" else 0.5)      # TFLOP/s
+    tf32_peak, bf16_peak = peaks["bf16_tflops_sustained"] * 0.5, peaks["bf16_tflops_sustained"]      # TFLOP/s
     rows = []
     for line in buf.value.decode().splitlines():
         name, cls, n, ms, work, nbytes = line.split("\t")
@@ -252,15 +252,16 @@ def kernel_table(lib, psteps, peaks, dtype):
             continue
         flops = work if cls == 0 else 0.0
         nbytes = nbytes if cls == 0 else work          # non-GEMM classes state their algorithmic bytes as `work`
+        tensor_peak = bf16_peak if "_bf16" in name else tf32_peak     # kind::f16 products vs kind::tf32 products
         t_tensor = flops / (tensor_peak * 1e12) * 1e3
         t_hbm = nbytes / (peaks["hbm_gbs"] * 1e9) * 1e3
         bound = "tensor" if t_tensor >= t_hbm else "hbm"
         rows.append({"kernel": name, "launches_per_step": n / psteps, "us_per_step": round(1e3 * ms / psteps, 2),
                      "flops_per_step": flops / psteps, "bytes_per_step": nbytes / psteps,
                      "tflops": round(flops / (ms * 1e-3) / 1e12, 2), "gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
-                     "bound": bound, "frac": round(max(t_tensor, t_hbm) / ms, 4)})
+                     "bound": bound, "frac": round(max(t_tensor, t_hbm) / ms, 4), "tensor_peak": tensor_peak})
     rows.sort(key=lambda r: -r["us_per_step"])
-    return rows, tensor_peak
+    return rows, (bf16_peak if dtype == "bf16" else tf32_peak)
 
 
 def run_b200(args, w):
@@ -289,7 +290,8 @@ def run_b200(args, w):
     model = make_model(fc_model={"sizes": [w["d"]], "input_norm": False, "activation": None, "dropout": 0.0},
                        transformer={"N": w["N"], "d_ff": w["dff"], "h": w["h"], "positional_encoding": None,
                                     "dropout": 0.0},
-                       post_model={"d_output": 1, "output_activation": None}, n_features=F).to(dev).train()
+                       post_model={"d_output": 1, "output_activation": None}, n_features=F,
+                       compute_dtype=args.dtype).to(dev).train()
     loss_fn = getattr(losses, w["loss"])
     # two different pinned host batches, alternated by the end-to-end loop
     hosts = []
@@ -464,13 +466,13 @@ def run_b200(args, w):
         out["roofline"] = {
             "bound": top["bound"], "kernel": top["kernel"],
             "achieved": top["tflops"] if top["bound"] == "tensor" else top["gbs"],
-            "peak": tensor_peak if top["bound"] == "tensor" else peaks["hbm_gbs"], "unit": unit, "frac": top["frac"],
+            "peak": top["tensor_peak"] if top["bound"] == "tensor" else peaks["hbm_gbs"], "unit": unit, "frac": top["frac"],
             "traffic": measured_traffic(args, B, top["kernel"]),
             "us_per_step": top["us_per_step"], "launches_per_step": top["launches_per_step"],
             "share_of_step": round(top["us_per_step"] / 1e3 / step_ms_profiled, 4) if step_ms_profiled else None,
             "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json): tensor = bf16_tflops_sustained "
-                           f"{peaks['bf16_tflops_sustained']}" + (" / 2 (kind::tf32 issues at half the bf16 rate)"
-                                                                  if args.dtype != "bf16" else "") +
+                           f"{peaks['bf16_tflops_sustained']} for kind::f16 (bf16) products, half of it for kind::tf32 "
+                           "products (tf32 issues at half the bf16 rate)" +
                            f", HBM = copy {peaks['hbm_gbs']} GB/s",
             "definition": "dominant kernel = largest device time per step; achieved = algorithmic flops (or bytes) of its "
                           "launches / their CUDA-event time, measured live; frac against the roof that binds that kernel",
@@ -511,8 +513,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", default="tf32", choices=["tf32"],
-                    help="arithmetic of the tensor-core products (fp32 everywhere else)")
+    ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"],
+                    help="arithmetic of the encoder's tensor-core products (LTRModel.compute_dtype); fp32 elsewhere")
     ap.add_argument("--batch", type=int, default=4096,
                     help="slates per step per GPU (saturating batch; 64 = allRank's default batch_size, see profiles/)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
