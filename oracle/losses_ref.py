@@ -192,11 +192,11 @@ def deterministic_neural_sort(s, tau, mask):
     both = mask[:, :, None] & mask[:, None, :]
     s_far = s.masked_fill(mask[:, :, None], -1e8)
     absdiff = torch.abs(s_far - s_far.permute(0, 2, 1)).masked_fill(either, 0.0)
-    ones = torch.ones((n, 1), dtype=torch.float32, device=dev)
+    ones = torch.ones((n, 1), dtype=s.dtype, device=dev)   # (the reference hard-wires fp32 here; fp64 inputs are an oracle extension)
     row_tot = torch.matmul(absdiff, torch.matmul(ones, ones.t()))            # [b,i,j] = sum_k |s_i - s_k|
     n_valid = n - mask.sum(dim=1)                                            # [B]
     ranks = torch.arange(n, device=dev)[None, :]
-    coef = (n_valid[:, None] + 1 - 2 * (ranks + 1)).float()
+    coef = (n_valid[:, None] + 1 - 2 * (ranks + 1)).to(s.dtype)
     coef = torch.where(ranks < n_valid[:, None], coef, torch.zeros_like(coef))  # zero beyond the valid count
     s_zero = s.masked_fill(mask[:, :, None], 0.0)
     lin = torch.matmul(s_zero, coef.unsqueeze(-2))                           # [b,i,j] = s_i * coef_j
@@ -235,7 +235,7 @@ def neuralNDCG(y_pred, y_true, padded_value_indicator=PAD, temperature=1.0, powe
     rel = y_true.masked_fill(mask, 0.0)
     gains = torch.pow(2.0, rel) - 1.0 if powered_relevancies else rel
     soft_sorted = torch.matmul(P, gains.unsqueeze(-1)).squeeze(-1)
-    disc = (torch.tensor(1.0) / torch.log2(torch.arange(y_true.shape[-1], dtype=torch.float) + 2.0)).to(y_pred.device)
+    disc = (torch.tensor(1.0) / torch.log2(torch.arange(y_true.shape[-1], dtype=torch.float) + 2.0)).to(y_pred.device, y_pred.dtype)
     disc_gains = (soft_sorted * disc)[:, :k]
     if powered_relevancies:
         idcg = _dcg(y_true, y_true, ats=[k]).squeeze(1)
@@ -259,7 +259,7 @@ def neuralNDCG_transposed(y_pred, y_true, padded_value_indicator=PAD, temperatur
     mask = y_true == padded_value_indicator
     P = deterministic_neural_sort(y_pred.unsqueeze(-1), tau=temperature, mask=mask)
     P = sinkhorn_scaling(P, mask, tol=tol, max_iter=max_iter)
-    disc = (torch.tensor(1) / torch.log2(torch.arange(y_true.shape[-1], dtype=torch.float) + 2.0)).to(y_pred.device)
+    disc = (torch.tensor(1) / torch.log2(torch.arange(y_true.shape[-1], dtype=torch.float) + 2.0)).to(y_pred.device, y_pred.dtype)
     disc = disc.clone()
     disc[k:] = 0.0
     expected = torch.matmul(P.permute(0, 2, 1), disc[None, :, None]).squeeze(-1)
