@@ -36,9 +36,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 __device__ __forceinline__ uint32_t round_tf32(float x) {
-  uint32_t y;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
-  return y;
+  // round-to-nearest (ties away) to tf32 as "+ half an ulp of the 10-bit mantissa, then let the tensor core ignore the
+  // low 13 bits" -- one integer add instead of cvt.rna.tf32.f32, which ptxas expands to three instructions here.
+  // Same result as cvt.rna for every finite value (probabilities and their gradients are finite).
+  return __float_as_uint(x) + 0x1000u;
 }
 
 template <int DK>
