@@ -851,6 +851,7 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
   if ((d.B.bf16 != 0) != in16) { arb_set_error("gemm: A and B must have the same element type"); return ARB_E_INVALID_ARG; }
   if (out16 && (!in16 || split || d.block_n < 64)) { arb_set_error("gemm: a bf16 output needs bf16 operands, no split-K and block_n >= 64"); return ARB_E_INVALID_ARG; }
   if ((d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) && (d.Aux.bf16 != 0) != out16) { arb_set_error("gemm: the aux tile must have the output's element type"); return ARB_E_INVALID_ARG; }
+  if (in16 && d.block_n < 64) { arb_set_error("gemm: bf16 operands need block_n >= 64 (a 128-byte row holds 64 elements)"); return ARB_E_INVALID_ARG; }
   if (in16 && (d.nb2 != 1 || d.nb3 != 1)) { arb_set_error("gemm: bf16 operands serve the unbatched linears only"); return ARB_E_UNSUPPORTED; }
   const uint32_t kel = in16 ? 64u : 32u;          // K elements per 128-byte row
   const uint32_t ocol = out16 ? 64u : 32u;        // output columns per 128-byte staging row

@@ -85,6 +85,9 @@ static int make_param_layout(const arb_scorer_config& c, ParamLayout& L) {
   }
   L.in_a = L.in_b = -1;
   if (c.fc_input_norm) { L.in_a = o; o += F; L.in_b = o; o += F; }
+  // the encoder's parameters start on a 32-byte boundary (8 elements): their bfloat16 shadow (bf16 mode) is read by TMA,
+  // which needs 16-byte aligned bases; every size inside the encoder section is then a multiple of 8 elements
+  if (c.n_layers > 0) o = align_up(o, 8);
   for (int l = 0; l < c.n_layers; ++l) {
     auto& y = L.layer[l];
     y.wqkv = o; o += 3 * d * d;

@@ -267,6 +267,8 @@ class LTRModel(nn.Module):
         if self.input_norm_on:
             out += [(self.input_layer.input_norm.weight, None), (self.input_layer.input_norm.bias, None)]
         if self.encoder is not None:
+            out += [(None, "align8")]      # the encoder section starts on a 32-byte boundary (include/allrank_b200.h)
+        if self.encoder is not None:
             for lyr in self.encoder.layers:
                 lin = lyr.self_attn.linears
                 out += [(lin[0].weight, None), (lin[1].weight, None), (lin[2].weight, None),
@@ -299,6 +301,9 @@ class LTRModel(nn.Module):
         grad = torch.zeros(total, dtype=torch.float32, device=device)
         views, off = [], 0
         for p, shape in self._ordered():
+            if shape == "align8":          # padding only
+                off = (off + 7) // 8 * 8
+                continue
             if shape == "align4":          # the learned positional table starts on a 16-byte boundary
                 off = (off + 3) // 4 * 4
                 shape = None

@@ -147,7 +147,8 @@ int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int32_t B, int
  * (csrc/dropout.cuh); `seed` must be the same in the forward and the backward call of a step.
  *
  *  Parameters live in ONE flat fp32 buffer (the host layer makes the nn.Parameters views of it), laid out as
- *   per FC layer i: fc_w[s_i, s_{i-1}] fc_b[s_i] (s_{-1} = F) | in_norm_w[F] in_norm_b[F] if fc_input_norm | per layer: wq wk wv [3d,d] bq bk bv [3d] wo[d,d] bo[d] w1[dff,d] b1[dff] w2[d,dff] b2[d]
+ *   per FC layer i: fc_w[s_i, s_{i-1}] fc_b[s_i] (s_{-1} = F) | in_norm_w[F] in_norm_b[F] if fc_input_norm |
+ *   (pad to a multiple of 8 elements) | per layer: wq wk wv [3d,d] bq bk bv [3d] wo[d,d] bo[d] w1[dff,d] b1[dff] w2[d,dff] b2[d]
  *   ln1_a ln1_b ln2_a ln2_b [d each] | lnf_a lnf_b [d] head_w[d] head_b[1] (pad to 4) | pe[pe_rows,d] if pe_mode == 2
  * (a fixed sinusoidal table, pe_mode == 1, is a buffer, not a parameter: it is passed separately as `pe_table`)
  * arb_scorer_param_count() gives the total; gradients use the same layout and are ACCUMULATED into `grads`.

@@ -47,7 +47,7 @@ def test_bf16_gemm_all_majors(gemm, block_n, a_mn, b_mn, M, N, K, out16):
     assert ((C.double() - ref).abs() <= bound).all(), float(((C.double() - ref).abs() / bound).max())
 
 
-@pytest.mark.parametrize("block_n", [32, 64, 128])
+@pytest.mark.parametrize("block_n", [64, 128])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 4096), (256, 136, 983), (512, 256, 2048), (96, 72, 640)])
 def test_bf16_weight_gradient_split_k(gemm, block_n, M, N, K):
     """dW[M,N] += dY[K,M]^T X[K,N]: both operands MN-major, split-K with fp32 red.add (K must keep 16-byte rows)."""
