@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  arb_pdl_wait();
   if (warp >= 2) {
     const int et = threadIdx.x - 64;
     if (et < 8) {
@@ -271,13 +272,6 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
-  // keys at or beyond the slate's extent are all masked (probability exactly 0): the score / P V products, the softmax
-  // loop and the K / V loads stop there.  At least one key column group is always processed, so an all-padded slate
-  // still produces the reference's NaN rows.
-  const int kext = extent ? max(1, min(S, extent[b])) : S;
-  const int S16 = (kext + 15) & ~15, S8 = (kext + 7) & ~7;
-  const int nkc = (S16 + 127) / 128;          // key chunks
-  const int nsteps = 2 * nkc;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmO);
@@ -288,6 +282,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
+  arb_pdl_wait();
   if (warp >= 2) {
     const int et = threadIdx.x - 64;
     if (et < 8) {
@@ -305,6 +300,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
+  // keys at or beyond the slate's extent are all masked (probability exactly 0): the score / P V products, the softmax
+  // loop and the K / V loads stop there.  At least one key column group is always processed, so an all-padded slate
+  // still produces the reference's NaN rows.
+  const int kext = extent ? max(1, min(S, extent[b])) : S;
+  const int S16 = (kext + 15) & ~15, S8 = (kext + 7) & ~7;
+  const int nkc = (S16 + 127) / 128;          // key chunks
+  const int nsteps = 2 * nkc;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -501,8 +503,8 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
                  4.0 * double(a.B) * a.h * a.S * ((out16 ? 3.5 : 4.0) * a.dk + 2.0),
                  (DK <= 32 && g_attn_fwd_two_pass) ? "attn_fwd2_kernel" : "attn_fwd_kernel");
     const int threads = (DK <= 32 && g_attn_fwd_two_pass) ? ATT2_THREADS : ATT_THREADS;
-    kern<<<grid, threads, L::total(), st>>>(tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
-                                               a.scale * 1.4426950408889634f, a.drop, a.extent);
+    arb_launch(kern, grid, dim3(threads), size_t(L::total()), st, tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
+               a.scale * 1.4426950408889634f, a.drop, a.extent);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

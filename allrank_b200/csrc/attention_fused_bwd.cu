@@ -57,6 +57,7 @@ __device__ __forceinline__ uint32_t round_tf32_b(float x) {
 __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict__ d_o, const float* __restrict__ o,
                                                          long long pitch, int B, int S, int h, int dk,
                                                          float* __restrict__ delta, int o_bf16) {
+  arb_pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)B * S) return;
@@ -130,8 +131,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
   // neither their key tiles nor their query chunks contribute anything, and their dQ / dK / dV rows are zero.  Only
   // the tiles below the extent are processed; the rest is written as zeros up front.
   const int n_full = (S + 127) / 128;
-  const int ext = extent ? max(1, min(S, extent[b])) : S;
-  const int n_kt = (ext + 127) / 128;   // active key tiles == active query chunks
   const float c_log2e = scale * 1.4426950408889634f;
 
   if (warp == 0 && lane == 0) {
@@ -149,9 +148,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  arb_pdl_wait();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  const int ext = extent ? max(1, min(S, extent[b])) : S;
+  const int n_kt = (ext + 127) / 128;   // active key tiles == active query chunks
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 320;
   const uint32_t T_DQ0 = tmem_base + 384;   // + 64 * qc
@@ -457,8 +459,8 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   {
     ProfScope ps(ARB_PROF_SCORER_SIMT, double(a.B) * a.S * (8.0 * a.h * a.dk + 4.0 * a.h), st, 0.0, "attn_delta_kernel");
     const long long rows = (long long)a.B * a.S;
-    attn_delta_kernel<<<unsigned((rows + 7) / 8), 256, 0, st>>>(a.do_ptr, static_cast<const float*>(a.o_ptr), a.o_pitch, a.B, a.S, a.h, a.dk,
-                                                                a.delta, a.o_bf16);
+    arb_launch(attn_delta_kernel, dim3(unsigned((rows + 7) / 8)), dim3(256), 0, st, a.do_ptr,
+               static_cast<const float*>(a.o_ptr), (long long)a.o_pitch, a.B, a.S, a.h, a.dk, a.delta, a.o_bf16);
   }
   arb_count_launch();
   const bool drop = a.drop.thresh != 0;
@@ -478,7 +480,7 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   {
     ProfScope ps(ARB_PROF_GEMM, 10.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
                  4.0 * double(a.B) * a.h * a.S * (7.0 * a.dk + 3.0), "attn_bwd_kernel");
-    kern<<<grid, BWD_THREADS, BwdSmem::total(), st>>>(tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
+    arb_launch(kern, grid, dim3(BWD_THREADS), size_t(BwdSmem::total()), st, tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
                                                       a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale, a.drop, a.dbias_qkv,
                                                       a.d_model, a.extent);
   }

@@ -17,6 +17,11 @@ extern "C" const char* arb_last_error(void) { return g_err; }
 extern "C" int32_t arb_abi_version(void) { return 3; }
 extern "C" int64_t arb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// programmatic dependent launch: on by default; arb_set_pdl(0) / ARB_PDL=0 launches every kernel fully serialised
+static std::atomic<int> g_pdl{1};
+bool arb_pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+extern "C" void arb_set_pdl(int32_t on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+
 // ---------------------------------------------------------------- per-launch timing
 #include <mutex>
 #include <vector>

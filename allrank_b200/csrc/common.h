@@ -16,6 +16,32 @@ inline int arb_device_slot() {
 }
 void arb_count_launch(int n = 1);
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The step is a chain of ~50 dependent kernels; at allRank's own batch size (64 slates) every one of them is
+// latency-bound, so the gap between a kernel's last wave and its successor's first instruction matters.  Kernels
+// launched through arb_launch carry cudaLaunchAttributeProgrammaticStreamSerialization (when enabled): the successor
+// may start its prologue (barrier init, TMEM allocation, tensor-map prefetch, smem carve-up) while the predecessor
+// drains, and blocks in arb_pdl_wait() -- griddepcontrol.wait -- until the predecessor has completed and flushed its
+// memory.  Every kernel launched this way executes arb_pdl_wait() on every thread before its first access to global
+// memory; without the launch attribute the instruction is a no-op.
+bool arb_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void arb_pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t arb_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = arb_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 // loss = sum(val)/sum(cnt), grad *= 1/sum(cnt); an all-zero count gives loss 0 and zero grad (slate_kernels.cu)
 int arb_finalize_mean_over_count(const float* val, const float* cnt, int B, float* loss, float* grad, size_t n_grad,
                                  cudaStream_t st);

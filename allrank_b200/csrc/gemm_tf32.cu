@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  arb_pdl_wait();          // everything above overlaps the previous kernel's tail; global memory is touched below
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  arb_pdl_wait();          // everything above overlaps the previous kernel's tail; global memory is touched below
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -734,7 +736,7 @@ static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const C
     gemm_prof_name(pname, d, "persist");
     ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
                  4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N), pname);
-    kern<<<grid, PERSIST_THREADS, smem, st>>>(tA, tB, tC, tX, p, int(tiles.x), int(tiles.y), int(tiles.z));
+    arb_launch(kern, dim3(grid), dim3(PERSIST_THREADS), smem, st, tA, tB, tC, tX, p, int(tiles.x), int(tiles.y), int(tiles.z));
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();
@@ -783,7 +785,7 @@ static int launch_bf16_t(const GemmDesc& d, const CUtensorMap& tA, const CUtenso
     gemm_prof_name(pname, d, "tile");
     ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
                  nb * (2.0 * (double(d.M) * d.K + double(d.N) * d.K) + osz * (1.0 + has_x) * double(d.M) * d.N), pname);
-    kern<<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tX, p);
+    arb_launch(kern, grid, dim3(GEMM_THREADS), smem, st, tA, tB, tC, tX, p);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();
@@ -833,7 +835,7 @@ static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap&
     gemm_prof_name(pname, d, "tile");
     ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
                  4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N), pname);
-    kern<<<grid, GEMM_THREADS, smem, st>>>(tA, tB, tC, tX, p);
+    arb_launch(kern, grid, dim3(GEMM_THREADS), smem, st, tA, tB, tC, tX, p);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
                                                                     float* __restrict__ y, float* __restrict__ mean_o,
                                                                     float* __restrict__ std_o, int torch_mode,
                                                                     uint16_t* __restrict__ y16) {
+  arb_pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
                                                                     float* __restrict__ colsum_out, int torch_mode,
                                                                     const uint16_t* __restrict__ dy16_in,
                                                                     uint16_t* __restrict__ dy16_out) {
+  arb_pdl_wait();
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   RowRegs<NV> ga, acc_a, acc_b, acc_c;
@@ -328,6 +330,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(float* __restrict__ dp
 
 // ------------------------------------------------------------------------------------------------ fp32 -> bf16
 __global__ void __launch_bounds__(256) to_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n) {
+  arb_pdl_wait();
   const long long n4 = n / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = src[i];
@@ -344,6 +347,7 @@ __global__ void __launch_bounds__(256) to_bf16_kernel(const float4* __restrict__
 __global__ void __launch_bounds__(256) slate_extent_kernel(const uint8_t* __restrict__ mask,
                                                            const float* __restrict__ dscores, int n_out, int B, int S,
                                                            int* __restrict__ extent) {
+  arb_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -432,6 +436,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
                                                                       float* __restrict__ score,
                                                                       float* __restrict__ mean_o,
                                                                       float* __restrict__ std_o) {
+  arb_pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -487,6 +492,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
     int has_norm, int act, long long rows, int width, int rows_per_warp, float* __restrict__ dx,
     float* __restrict__ grad_a, float* __restrict__ grad_b, float* __restrict__ grad_w, float* __restrict__ grad_wb,
     float* __restrict__ dx_masked, DropSite site, float* __restrict__ colsum_out, uint16_t* __restrict__ dy16_out) {
+  arb_pdl_wait();
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   __shared__ float shb[ROWS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -827,7 +833,7 @@ int ln_forward(const float* x, const float* a, const float* b, float eps, long l
   if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((y16 ? 6.0 : 8.0) * width + 8), st);
-  ARB_DISPATCH_NV(width, (ln_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16))));
+  ARB_DISPATCH_NV(width, (arb_launch(ln_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16))));
   return check_launch();
 }
 
@@ -842,7 +848,7 @@ int ln_backward(const float* dy, const float* x, const float* a, const float* me
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((dres ? 16.0 : 12.0) * width + 8), st);
-  ARB_DISPATCH_NV(width, (ln_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode, static_cast<const uint16_t*>(dy16_in), static_cast<uint16_t*>(dy16_out))));
+  ARB_DISPATCH_NV(width, (arb_launch(ln_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode, static_cast<const uint16_t*>(dy16_in), static_cast<uint16_t*>(dy16_out))));
   return check_launch();
 }
 
@@ -901,15 +907,15 @@ int softmax_backward(float* dp, float* prob, long long rows, int S, int pitch, c
 
 int slate_extents(const uint8_t* mask, const float* dscores, int n_out, int B, int S, int* extent, cudaStream_t st) {
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(B) * S * (dscores ? 1.0 + 4.0 * n_out : 1.0), st);
-  slate_extent_kernel<<<unsigned((B + 7) / 8), 256, 0, st>>>(mask, dscores, n_out, B, S, extent);
+  arb_launch(slate_extent_kernel, dim3(unsigned((B + 7) / 8)), dim3(256), 0, st, mask, dscores, n_out, B, S, extent);
   return check_launch();
 }
 
 int convert_to_bf16(const float* src, void* dst, long long n, cudaStream_t st) {
   const long long n4 = (n + 3) / 4;
   ProfScope ps(ARB_PROF_SCORER_SIMT, 6.0 * double(n), st);
-  to_bf16_kernel<<<unsigned(std::max<long long>(1, std::min<long long>((n4 + 255) / 256, 148 * 8))), 256, 0, st>>>(
-      reinterpret_cast<const float4*>(src), static_cast<uint2*>(dst), n);
+  arb_launch(to_bf16_kernel, dim3(unsigned(std::max<long long>(1, std::min<long long>((n4 + 255) / 256, 148 * 8)))), dim3(256), 0, st,
+             reinterpret_cast<const float4*>(src), static_cast<uint2*>(dst), n);
   return check_launch();
 }
 
@@ -928,7 +934,7 @@ int head_forward(const float* x, const float* a, const float* b, float eps, cons
   if (width % 4) { arb_set_error("model width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (4.0 * width + 12), st);
-  ARB_DISPATCH_NV(width, (head_fwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd)));
+  ARB_DISPATCH_NV(width, (arb_launch(head_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd)));
   return check_launch();
 }
 
@@ -940,7 +946,7 @@ int head_backward(const float* dscore, const float* score, const float* x, const
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 16), st);
-  ARB_DISPATCH_NV(width, (head_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out, static_cast<uint16_t*>(dy16_out))));
+  ARB_DISPATCH_NV(width, (arb_launch(head_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out, static_cast<uint16_t*>(dy16_out))));
   return check_launch();
 }
 

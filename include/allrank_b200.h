@@ -218,6 +218,11 @@ void arb_set_attention_mode(int32_t mode);
  * gradient have exactly zero activation gradients, so results are unchanged; 0: dense tiles.  For A/B measurements. */
 void arb_set_attention_skip_padding(int32_t on);
 
+/* 1 (default): the kernels of a step are chained with programmatic dependent launch -- a kernel's prologue (barrier
+ * init, TMEM allocation, tensor-map prefetch) overlaps its predecessor's last wave, and it blocks in griddepcontrol.wait
+ * before its first global-memory access; 0: every launch fully serialised.  For A/B measurements. */
+void arb_set_pdl(int32_t on);
+
 /* 1 (default): the fused attention forward runs as the two-pass / two-CTAs-per-SM kernel (head width <= 32);
  * 0: the single-pass kernel that keeps the whole S x S tile in TMEM (one CTA per SM). For A/B measurements. */
 void arb_set_attention_fwd_two_pass(int32_t on);
