@@ -1,16 +1,23 @@
 #!/bin/bash
-# Round-2 GPU call 2: full GPU test suite, then A/B bench lines (padding skip, persistent GEMM everywhere), other workloads.
+# Round-2 GPU call 2: full GPU test suite, then A/B bench lines (padding skip, persistent GEMM everywhere, PDL), other
+# workloads, bf16.
 mkdir -p gpurun_out/r2
-python -m pytest tests -m gpu -q > gpurun_out/r2/pytest_gpu.log 2>&1
-tail -15 gpurun_out/r2/pytest_gpu.log
+python -m pytest tests -m gpu -q -x > gpurun_out/r2/pytest_gpu.log 2>&1
+tail -25 gpurun_out/r2/pytest_gpu.log
+python -m pytest tests -m gpu -q > gpurun_out/r2/pytest_gpu_all.log 2>&1
+tail -40 gpurun_out/r2/pytest_gpu_all.log | cut -c1-220
 B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
-timeout 300 $B > gpurun_out/r2/bench_cfg2_skip.json 2> gpurun_out/r2/bench_cfg2_skip.err
+timeout 300 $B > gpurun_out/r2/bench_cfg2_default.json 2> gpurun_out/r2/bench_cfg2_default.err
+ARB_PDL=0 timeout 300 $B > gpurun_out/r2/bench_cfg2_nopdl.json 2>&1
 ARB_ATTN_SKIP_PADDING=0 timeout 300 $B > gpurun_out/r2/bench_cfg2_dense.json 2>&1
 ARB_GEMM_PERSISTENT=1 timeout 300 $B > gpurun_out/r2/bench_cfg2_persist1.json 2>&1
 ARB_GEMM_PERSISTENT=0 timeout 300 $B > gpurun_out/r2/bench_cfg2_persist0.json 2>&1
 timeout 300 $B --batch 64 > gpurun_out/r2/bench_cfg2_b64.json 2>&1
+ARB_PDL=0 timeout 300 $B --batch 64 > gpurun_out/r2/bench_cfg2_b64_nopdl.json 2>&1
 timeout 300 $B --batch 64 --optimizer torch > gpurun_out/r2/bench_cfg2_b64_torchadam.json 2>&1
-timeout 300 $B --workload cfg3 --batch 1024 > gpurun_out/r2/bench_cfg3.json 2>&1
+timeout 300 $B --workload cfg3 --batch 1024 > gpurun_out/r2/bench_cfg3_tf32.json 2>&1
+timeout 300 $B --workload cfg3 --batch 1024 --dtype bf16 > gpurun_out/r2/bench_cfg3_bf16.json 2>&1
+timeout 300 $B --dtype bf16 > gpurun_out/r2/bench_cfg2_bf16.json 2>&1
 timeout 300 $B --workload cfg4 --batch 4096 > gpurun_out/r2/bench_cfg4.json 2>&1
 timeout 300 $B --workload cfg5 --batch 1024 > gpurun_out/r2/bench_cfg5.json 2>&1
-for f in gpurun_out/r2/bench_*.json; do echo "$f: $(python -c "import json,sys; d=json.loads([l for l in open('$f') if l.startswith('{')][-1]); print(round(d['value']), d['ms_per_step'], d['roofline']['kernel'], d['roofline']['frac'])" 2>&1 | tail -1)"; done
+for f in gpurun_out/r2/bench_*.json; do echo "$f: $(python -c "import json,sys; d=json.loads([l for l in open('$f') if l.startswith('{')][-1]); print(round(d['value']), round(d['ms_per_step'],3), d['roofline']['kernel'], d['roofline']['frac'])" 2>&1 | tail -1)"; done
