@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   const int kext = extent ? max(1, min(S, extent[b])) : S;
   const int S16 = (kext + 15) & ~15, S8 = (kext + 7) & ~7;
   const int nkc = (S16 + 127) / 128;          // key chunks
-  const int nsteps = 2 * nkc;
+  const int nsteps = 1 + nkc;                 // one pass-A step over the whole score row + one pass-B step per chunk
 
   if (warp == 0) {
     if (lane == 0) {
@@ -331,13 +331,22 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
           ptx::mma_tf32_ts(tmem_O, tmem_S + 8 * i, ptx::smem_desc_sw128<1>(va + kc * 16384 + i * 1024, 256 * 128, 512),
                            idesc_o, (kc > 0 || i > 0) ? 1u : 0u);
       };
-      for (int st = 0; st < nsteps; ++st) {
-        const int kc = st % nkc;
-        if (st > 0) {
-          ptx::mbar_wait(t_bar, (st - 1) & 1);
-          ptx::tc_fence_after();
-          if (st - 1 >= nkc) issue_pv((st - 1) % nkc);      // P of the previous pass-B chunk is in the S window
-        }
+      // step 0 (pass A): the WHOLE score row block S = Q K^T, N = S16 <= 256 columns, in one issue -- it may spill over
+      // the O columns, which pass B only starts to use after every softmax thread has taken its row maximum
+      {
+        const uint32_t idesc_a = ptx::idesc_tf32(128, S16, 0, 0);
+        for (int k = 0; k < KSTEPS; ++k)
+          ptx::mma_tf32_ss(tmem_S, ptx::smem_desc_sw128<2>(qa + k * 32, 16, 1024),
+                           ptx::smem_desc_sw128<2>(ka + k * 32, 16, 1024), idesc_a, k > 0);
+        ptx::mma_commit(s_bar);
+      }
+      // steps 1..nkc (pass B): recompute one 128-key chunk into the 128-column window; the previous chunk's P V runs
+      // first (P sits in the window until then)
+      for (int st = 1; st < nsteps; ++st) {
+        const int kc = st - 1;
+        ptx::mbar_wait(t_bar, (st - 1) & 1);
+        ptx::tc_fence_after();
+        if (kc > 0) issue_pv(kc - 1);
         const int nc = min(128, S16 - 128 * kc);
         const uint32_t idesc_s = ptx::idesc_tf32(128, nc, 0, 0);
         for (int k = 0; k < KSTEPS; ++k)
@@ -360,9 +369,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
     float* xch_sum = reinterpret_cast<float*>(k_s);     // [2][128] partial sums   (K is dead after the last score chunk)
     float mx = -CUDART_INF_F, sum = 0.f, mxs = 0.f;
     for (int st = 0; st < nsteps; ++st) {
-      const int kc = st % nkc;
-      const bool pass_b = st >= nkc;
-      if (st == nkc) {                          // pass A done: combine the two partial row maxima
+      const bool pass_b = st > 0;
+      const int kc = pass_b ? st - 1 : 0;
+      if (st == 1) {                            // pass A done: combine the two partial row maxima
         xch_max[sub * 128 + row] = mx;
         ptx::named_bar_sync(1, ATT2_SOFTMAX);
         mx = fmaxf(xch_max[row], xch_max[128 + row]);
@@ -370,7 +379,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
       }
       ptx::mbar_wait(s_bar, st & 1);
       ptx::tc_fence_after();
-      const int keys = min(128, S8 - 128 * kc);
+      // pass A walks every 32-key group of the row block, pass B the groups of its chunk
+      const int keys = pass_b ? min(128, S8 - 128 * kc) : S8;
       const int nch = (keys + 31) / 32;
       for (int c = 0; c < nch; ++c) {
         uint32_t v[16];
