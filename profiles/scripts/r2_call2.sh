@@ -2,10 +2,17 @@
 # Round-2 GPU call 2: full GPU test suite, then A/B bench lines (padding skip, persistent GEMM everywhere, PDL), other
 # workloads, bf16.
 mkdir -p gpurun_out/r2
-python -m pytest tests -m gpu -q -x > gpurun_out/r2/pytest_gpu.log 2>&1
-tail -25 gpurun_out/r2/pytest_gpu.log
-python -m pytest tests -m gpu -q > gpurun_out/r2/pytest_gpu_all.log 2>&1
-tail -40 gpurun_out/r2/pytest_gpu_all.log | cut -c1-220
+# one pytest process per file: a faulting kernel poisons only its own CUDA context
+: > gpurun_out/r2/pytest_gpu.log
+for f in tests/test_gpu_gemm.py tests/test_gpu_gemm_bf16.py tests/test_gpu_scorer.py tests/test_gpu_dropout.py \
+         tests/test_gpu_fc_block.py tests/test_shipped_configs.py tests/test_gpu_bf16.py tests/test_gpu_losses.py \
+         tests/test_gpu_metrics.py tests/test_gpu_optim.py tests/test_gpu_slates.py tests/test_gpu_l3_training.py \
+         tests/test_gpu_ddp.py; do
+  echo "=== $f" >> gpurun_out/r2/pytest_gpu.log
+  timeout 900 python -m pytest $f -m gpu -q -x -s >> gpurun_out/r2/pytest_gpu.log 2>&1
+  echo "=== $f rc=$?" >> gpurun_out/r2/pytest_gpu.log
+done
+grep -E "^=== |passed|failed|error|Error|assert" gpurun_out/r2/pytest_gpu.log | cut -c1-200 | tail -80
 B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
 timeout 300 $B > gpurun_out/r2/bench_cfg2_default.json 2> gpurun_out/r2/bench_cfg2_default.err
 ARB_PDL=0 timeout 300 $B > gpurun_out/r2/bench_cfg2_nopdl.json 2>&1
