@@ -203,6 +203,53 @@ def run_reference(args, w):
     print(json.dumps(out), flush=True)
 
 
+def run_reference_gpu(args, w):
+    """Optional, stricter bar: the UNMODIFIED reference (baseline/_ref) in eager PyTorch on the same
+    B200 -- its make_model, its loss, train_utils.loss_batch, torch.optim.Adam, fp32 (torch's default matmul precision),
+    inputs resident on the device.  One JSON line with impl "reference-gpu"."""
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    if not reference_available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "baseline/_ref is not installed"}), flush=True)
+        return
+    from oracle.install_reference import import_path
+    sys.path[:0] = import_path()
+    import allrank.models.losses as ref_losses
+    from allrank.config import TransformerConfig
+    from allrank.models.model import make_model as ref_make_model
+    from allrank.training.train_utils import loss_batch
+    from allrank_b200.synth import make_slates
+    from functools import partial
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(42)
+    B = args.batch
+    model = ref_make_model(fc_model={"sizes": [w["d"]], "input_norm": False, "activation": None, "dropout": 0.0},
+                           transformer=TransformerConfig(N=w["N"], d_ff=w["dff"], h=w["h"], positional_encoding=None,
+                                                         dropout=0.0),
+                           post_model={"d_output": 1, "output_activation": None}, n_features=F).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    loss_fn = partial(getattr(ref_losses, w["loss"]), **w["loss_args"])
+    x, y, idx = make_slates(B, w["S"], F, seed=1234)
+    x, y, idx = x.to(dev), y.to(dev), idx.to(dev)
+    for _ in range(args.warmup):
+        loss_batch(model, loss_fn, x, y, idx, None, opt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss_batch(model, loss_fn, x, y, idx, None, opt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"impl": "reference-gpu", "metric": "slates/sec", "value": B / ms * 1e3, "unit": "slates/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                      "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": workload_config(args, w, B),
+                      "note": "unmodified allRank (baseline/_ref) in eager PyTorch on cuda:0; loss.item() every step "
+                              "(train_utils.loss_batch)"}), flush=True)
+
+
 def cpu_baseline_subprocess(args, w, steps=3, warmup=1):
     """The CPU leg of the default run: the reference arm in a child process with CUDA hidden, bounded to a few steps."""
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONDONTWRITEBYTECODE="1")
@@ -511,7 +558,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"],
                     help="arithmetic of the encoder's tensor-core products (LTRModel.compute_dtype); fp32 elsewhere")
@@ -532,6 +579,8 @@ def main():
     if args.impl == "reference":
         os.environ["CUDA_VISIBLE_DEVICES"] = ""      # the reference hard-wires cuda:0 when it sees a GPU
         run_reference(args, w)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args, w)
     else:
         run_b200(args, w)
 

@@ -27,4 +27,6 @@ timeout 300 $B --workload cfg3 --batch 1024 --dtype bf16 > gpurun_out/r2/bench_c
 timeout 300 $B --dtype bf16 > gpurun_out/r2/bench_cfg2_bf16.json 2>&1
 timeout 300 $B --workload cfg4 --batch 4096 > gpurun_out/r2/bench_cfg4.json 2>&1
 timeout 300 $B --workload cfg5 --batch 1024 > gpurun_out/r2/bench_cfg5.json 2>&1
+timeout 600 python bench.py --impl reference-gpu --steps 5 --warmup 3 --batch 64 > gpurun_out/r2/refgpu_cfg2_b64.json 2>&1
+timeout 600 python bench.py --impl reference-gpu --steps 3 --warmup 3 --batch 512 > gpurun_out/r2/refgpu_cfg2_b512.json 2>&1
 for f in gpurun_out/r2/bench_*.json; do echo "$f: $(python -c "import json,sys; d=json.loads([l for l in open('$f') if l.startswith('{')][-1]); print(round(d['value']), round(d['ms_per_step'],3), d['roofline']['kernel'], d['roofline']['frac'])" 2>&1 | tail -1)"; done
