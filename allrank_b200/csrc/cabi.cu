@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include "common.h"
+#include "defaults.h"
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
@@ -18,7 +19,7 @@ extern "C" int32_t arb_abi_version(void) { return 3; }
 extern "C" int64_t arb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // programmatic dependent launch: on by default; arb_set_pdl(0) / ARB_PDL=0 launches every kernel fully serialised
-static std::atomic<int> g_pdl{1};
+static std::atomic<int> g_pdl{ARB_DEFAULT_PDL};
 bool arb_pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 extern "C" void arb_set_pdl(int32_t on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include "common.h"
+#include "defaults.h"
 #include "gemm_tf32.h"
 #include "sm100_ptx.cuh"
 
@@ -704,7 +705,7 @@ static void gemm_prof_name(char (&out)[56], const GemmDesc& d, const char* varia
                 (d.flags & EPI_MASK_AUX) ? " mask" : "");
 }
 
-static int g_persistent = 2;   // 0: never, 1: wherever supported, 2: auto
+static int g_persistent = ARB_DEFAULT_GEMM_PERSISTENT;   // 0: never, 1: wherever supported, 2: auto
 void set_gemm_persistent(int on) { g_persistent = on; }
 
 template <int BLOCK_N, int A_MN, int B_MN>

@@ -14,6 +14,7 @@
 
 #include "attention_fused.h"
 #include "common.h"
+#include "defaults.h"
 #include "gemm_tf32.h"
 #include "scorer_kernels.h"
 
@@ -26,7 +27,7 @@ static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 static int g_attn_mode = 2;
 // 1 (default): the fused attention kernels skip the tiles that lie entirely in a slate's padding (exact: masked keys
 // have probability 0 and padded rows a zero gradient); 0: dense tiles, for A/B measurements
-static int g_skip_padding = 1;
+static int g_skip_padding = ARB_DEFAULT_SKIP_PADDING;
 static bool use_fused(const arb_scorer_config& c, int S) {
   return g_attn_mode >= 1 && c.n_layers > 0 && attn_fused_supported(S, c.d_model / c.n_heads);
 }
