@@ -118,9 +118,7 @@ ORACLE_CASES = [
 def test_against_oracle_on_synthetic_slates(L, name, kw, B, S):
     from oracle import losses_ref
     from allrank_b200.synth import make_slates, make_scores
-    if name == "neuralNDCG" and S > 240:
-        pytest.skip("oracle materialises S^2 x 50 iterations; covered at S<=240")
-    if name == "neuralNDCG":
+    if name == "neuralNDCG":       # the oracle materialises [B,S,S] x 50 iterations under autograd: 2 GB at (2, 1251)
         B = min(B, 8)
     _, y, _ = make_slates(B, S, n_features=1, seed=5)
     yp = make_scores(B, S, seed=6)
