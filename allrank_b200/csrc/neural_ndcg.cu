@@ -333,7 +333,7 @@ __host__ __device__ inline size_t rg_smem_bytes(int T) {
 __global__ void __launch_bounds__(RG_THREADS, 1) neural_ndcg_reg_kernel(
     const float* __restrict__ y_pred, const float* __restrict__ y_true, int B, int S,
     const float* __restrict__ discounts, NeuralCfg cfg, float* __restrict__ val, float* __restrict__ cnt,
-    float* __restrict__ grad) {
+    float* __restrict__ grad, float* __restrict__ dump_p0, float* __restrict__ dump_p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, l = tid & 31, w = tid >> 5;
@@ -454,6 +454,16 @@ __global__ void __launch_bounds__(RG_THREADS, 1) neural_ndcg_reg_kernel(
     for (int c = 0; c < 4; ++c) m0[k][c] = rok[k] ? m0[k][c] / z : 0.0f;
   }
 
+  // debug dump (arb_neural_sort_debug): the NeuralSort matrix P_hat[rank j, item i] of the real items, in the slate's
+  // own [S, S] layout (loss_utils.py:34-67); rows / columns of padded items stay as the caller initialised them
+  if (dump_p0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (rok[k] && cok[c]) dump_p0[(size_t(b) * S + (w + 32 * k)) * S + pos[l + 32 * c]] = m0[k][c];
+  }
+
   // column reduction helper: per-thread partials over its 4 rows -> sums over all rows, result in dst[0..127]
   auto col_reduce = [&](const float (&cp)[4], float* scratch, float* dst) {
 #pragma unroll
@@ -520,6 +530,15 @@ __global__ void __launch_bounds__(RG_THREADS, 1) neural_ndcg_reg_kernel(
     iters = t + 1;
   }
   __syncthreads();
+
+  if (dump_p) {   // the Sinkhorn-scaled matrix diag(u) M0 diag(v) (loss_utils.py:8-31)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (rok[k] && cok[c])
+          dump_p[(size_t(b) * S + (w + 32 * k)) * S + pos[l + 32 * c]] = u[w + 32 * k] * m0[k][c] * v[l + 32 * c];
+  }
 
   // ---- soft DCG and the adjoints of u, v, M0 at the end of the iterations
   float lossb = 0.f;
@@ -700,7 +719,7 @@ extern "C" int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int
     {
       ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
       neural_ndcg_reg_kernel<<<B, RG_THREADS, smem_rg, st>>>(y_pred, y_true, B, S, discounts, cfg_rg, scratch,
-                                                          scratch + B, grad);
+                                                          scratch + B, grad, nullptr, nullptr);
     }
     arb_count_launch();
     cudaError_t e2 = cudaGetLastError();
@@ -735,4 +754,36 @@ extern "C" int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int
   if (e != cudaSuccess) { arb_set_error(cudaGetErrorString(e)); return ARB_E_CUDA; }
   // mean over the slates with idcg != 0 (neuralNDCG.py:69); all-dead batch -> 0 (:66-67)
   return arb_finalize_mean_over_count(scratch, scratch + B, B, loss, grad, size_t(B) * S, st);
+}
+
+// Debug / parity hook for SURVEY.md 8(a) rows a17, a18: the matrices the fused neuralNDCG kernel works with, for slates of
+// at most 128 items -- p0_out = deterministic_neural_sort(y_pred, tau, mask) and p_out = sinkhorn_scaling(p0, mask, tol,
+// max_iter) restricted to the real items (entries of padded rows / columns are left untouched: pass zero-filled
+// [B,S,S] buffers).  Slates without a relevant item are skipped by the kernel (left untouched too).
+extern "C" int32_t arb_neural_sort_debug(const float* y_pred, const float* y_true, int32_t B, int32_t S,
+                                         const float* discounts, float pad_value, float temperature, int32_t max_iter,
+                                         float tol, float* p0_out, float* p_out, float* scratch, void* stream) {
+  if (!(y_pred && y_true && discounts && p0_out && p_out && scratch && B > 0 && S > 0 && max_iter >= 0 && temperature > 0.f)) {
+    arb_set_error("arb_neural_sort_debug: null pointer or bad argument");
+    return ARB_E_INVALID_ARG;
+  }
+  if (S > RG_N || rg_smem_bytes(max_iter) > nn_smem_budget()) {
+    arb_set_error("arb_neural_sort_debug: serves slates of at most 128 items");
+    return ARB_E_UNSUPPORTED;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem_rg = rg_smem_bytes(max_iter);
+  if (smem_rg > 48 * 1024 &&
+      cudaFuncSetAttribute((const void*)neural_ndcg_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           int(smem_rg)) != cudaSuccess) {
+    arb_set_error("arb_neural_sort_debug: cannot raise the shared-memory limit");
+    return ARB_E_CUDA;
+  }
+  NeuralCfg cfg{pad_value, temperature, tol, 1, 0, max_iter};
+  neural_ndcg_reg_kernel<<<B, RG_THREADS, smem_rg, st>>>(y_pred, y_true, B, S, discounts, cfg, scratch, scratch + B,
+                                                        nullptr, p0_out, p_out);
+  arb_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { arb_set_error(cudaGetErrorString(e)); return ARB_E_CUDA; }
+  return ARB_OK;
 }

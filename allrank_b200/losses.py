@@ -170,6 +170,30 @@ def _gumbel_perturbed(y_pred, n_samples, beta, log_scores, eps=1e-10):
     return (s_positive.unsqueeze(0) + samples).reshape(n_samples * y_pred.shape[0], y_pred.shape[1])
 
 
+def neural_sort_matrices(y_pred, y_true, temperature=1., max_iter=50, tol=1e-6, padded_value_indicator=PADDED_Y_VALUE):
+    """Parity hook (not part of the reference's surface): the matrices the fused neuralNDCG kernel works with, for
+    slates of at most 128 items -- (deterministic_neural_sort(y_pred, tau, mask), sinkhorn_scaling(., mask, tol,
+    max_iter)) of loss_utils.py:34-67 / :8-31, as [B,S,S] tensors whose padded rows / columns are zero."""
+    import ctypes
+    _lib.require_cuda(y_pred, y_true)
+    s = y_pred.detach().float().contiguous()
+    t = y_true.detach().float().contiguous()
+    B, S = s.shape
+    p0 = torch.zeros(B, S, S, device=s.device)
+    p = torch.zeros(B, S, S, device=s.device)
+    scratch = torch.empty(2 * B, device=s.device)
+    disc = discount_table(S, s.device)
+    fn = _lib.lib().arb_neural_sort_debug
+    fn.restype = ctypes.c_int32
+    c_p, c_i, c_f = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
+    fn.argtypes = [c_p, c_p, c_i, c_i, c_p, c_f, c_f, c_i, c_f, c_p, c_p, c_p, c_p]
+    with torch.cuda.device(s.device):
+        rc = fn(_lib.ptr(s), _lib.ptr(t), B, S, _lib.ptr(disc), float(padded_value_indicator), float(temperature),
+                int(max_iter), float(tol), _lib.ptr(p0), _lib.ptr(p), _lib.ptr(scratch), _lib.stream_ptr(s.device))
+    _lib.check(rc, "arb_neural_sort_debug")
+    return p0, p
+
+
 def neuralNDCG(y_pred, y_true, padded_value_indicator=PADDED_Y_VALUE, temperature=1., powered_relevancies=True, k=None,
                stochastic=False, n_samples=32, beta=0.1, log_scores=True, max_iter=50, tol=1e-6, _gain_mode=None):
     """NeuralNDCG loss -- neuralNDCG.py:10-70.

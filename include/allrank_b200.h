@@ -134,6 +134,15 @@ int32_t arb_neural_ndcg(const float* y_pred, const float* y_true, int32_t B, int
                         float* loss, float* grad, float* scratch, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* Parity hook for deterministic_neural_sort / sinkhorn_scaling (allrank/models/losses/loss_utils.py:34-67, :8-31), which
+ * arb_neural_ndcg fuses: the kernel's own matrices for slates of at most 128 items.  p0_out, p_out: zero-filled
+ * [B,S,S] buffers; entries [b, rank j, item i] of the real items receive NeuralSort's P_hat and its Sinkhorn scaling
+ * (max_iter iterations at most, per-slate tolerance test).  Slates without a relevant item are left untouched.
+ * scratch: >= 2*B floats. */
+int32_t arb_neural_sort_debug(const float* y_pred, const float* y_true, int32_t B, int32_t S, const float* discounts,
+                              float pad_value, float temperature, int32_t max_iter, float tol, float* p0_out,
+                              float* p_out, float* scratch, void* stream);
+
 /* ---------------------------------------------------------------- scorer: LTRModel(x, mask, indices) -> scores
  * Replaces allrank.models.model.LTRModel.forward / .score (allrank/models/model.py:72-92) for the model family
  * make_model builds (model.py:131-151): one input Linear (FCModel, model.py:12-44) -> N pre-norm Transformer

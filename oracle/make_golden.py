@@ -378,6 +378,30 @@ def gen_scorer_shipped():
     np.savez_compressed(os.path.join(OUT, "scorer_shipped_configs.npz"), **blob)
 
 
+def gen_neural_sort():
+    """deterministic_neural_sort and sinkhorn_scaling themselves (loss_utils.py:34-67, :8-31), which no test of the
+    reference pins in the tau = 1, 50-iteration regime of BASELINE config 4: P_hat before and after the scaling."""
+    from allrank.models.losses.loss_utils import deterministic_neural_sort, sinkhorn_scaling
+    blob = {}
+    keys = []
+    for (b, s_len, tau, iters, tol) in [(4, 7, 1.0, 50, 1e-6), (3, 33, 1.0, 50, 1e-6), (3, 120, 1.0, 50, 1e-6),
+                                        (3, 120, 0.1, 50, 1e-6), (3, 64, 3.0, 20, 1e-6), (2, 128, 1.0, 50, 1e-6)]:
+        yp, y = case_inputs(b, s_len, seed=2100 + s_len + int(10 * tau))
+        if s_len >= 33:
+            y[0] = torch.where(y[0] >= 0, torch.ones_like(y[0]), y[0])   # (case_inputs zeroes slate 0: give it relevance)
+        mask = y == -1
+        p0 = deterministic_neural_sort(yp.unsqueeze(-1), tau=tau, mask=mask)
+        p = sinkhorn_scaling(p0, mask, tol=tol, max_iter=iters)
+        key = f"s{s_len}_t{tau}_i{iters}"
+        blob[key + "_pred"], blob[key + "_true"] = yp.numpy(), y.numpy()
+        blob[key + "_p0"], blob[key + "_p"] = p0.numpy(), p.numpy()
+        blob[key + "_args"] = np.array([tau, iters, tol])
+        keys.append(key)
+    blob["keys"] = np.array(keys)
+    np.savez_compressed(os.path.join(OUT, "neural_sort.npz"), **blob)
+    print("neural_sort:", keys)
+
+
 def write_corpus(path, lengths, n_features, seed):
     """A small libsvm corpus (label qid:N f:v ...), query ids deliberately not sorted, a few all-zero-label queries
     and one query with a single relevant item."""
@@ -440,6 +464,6 @@ def gen_init():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     gens = {"losses": gen_losses, "listmle": gen_listmle, "bce": gen_bce, "ordinal": gen_ordinal, "metrics": gen_metrics,
-            "scorer": gen_scorer, "scorer_pe": gen_scorer_pe, "scorer_multi": gen_scorer_multi, "scorer_shipped": gen_scorer_shipped, "slates": gen_slates, "init": gen_init}
+            "scorer": gen_scorer, "scorer_pe": gen_scorer_pe, "scorer_multi": gen_scorer_multi, "scorer_shipped": gen_scorer_shipped, "neural_sort": gen_neural_sort, "slates": gen_slates, "init": gen_init}
     for name in (sys.argv[1:] or list(gens)):      # optionally: only the named generators
         gens[name]()

@@ -330,3 +330,28 @@ def test_ordinal_rejects_bad_shapes(L):
     with pytest.raises(ValueError):
         L.ordinal(dev(np.zeros((2, 5, 3), dtype=np.float32)), dev(np.zeros((2, 5), dtype=np.float32)), n=2)
 
+
+
+def test_neural_sort_and_sinkhorn_matrices_match_the_reference(golden):
+    """SURVEY.md 8(a) rows a17 / a18 pinned directly: the matrices the fused neuralNDCG kernel works with
+    (arb_neural_sort_debug) against loss_utils.deterministic_neural_sort and loss_utils.sinkhorn_scaling of the
+    unmodified reference, on the block of real items (the reference fills the padded block with softmax(1) rows and
+    zeroes it after the scaling; the kernel never forms it)."""
+    from allrank_b200 import losses
+    g = golden("neural_sort")
+    for key in g["keys"]:
+        key = str(key)
+        tau, iters, tol = [float(v) for v in g[key + "_args"]]
+        yp, yt = torch.tensor(g[key + "_pred"]).cuda(), torch.tensor(g[key + "_true"]).cuda()
+        p0, p = losses.neural_sort_matrices(yp, yt, temperature=tau, max_iter=int(iters), tol=tol)
+        real = (yt != -1)
+        block = (real[:, :, None] & real[:, None, :]).cpu().numpy()
+        # rank rows beyond the number of real items belong to the padded block as well
+        n_real = real.sum(1).cpu().numpy()
+        for b in range(block.shape[0]):
+            block[b, n_real[b]:, :] = False
+        r0, r1 = g[key + "_p0"], g[key + "_p"]
+        # the reference's row j of the real block is the j-th RANK; its columns are the items
+        assert np.abs(p0.cpu().numpy() - r0)[block].max() <= 1e-5, key
+        assert np.abs(p.cpu().numpy() - r1)[block].max() <= 2e-5, key
+        assert (p.cpu().numpy()[~block] == 0).all()
