@@ -306,7 +306,8 @@ def kernel_table(lib, psteps, peaks, dtype):
         rows.append({"kernel": name, "launches_per_step": n / psteps, "us_per_step": round(1e3 * ms / psteps, 2),
                      "flops_per_step": flops / psteps, "bytes_per_step": nbytes / psteps,
                      "tflops": round(flops / (ms * 1e-3) / 1e12, 2), "gbs": round(nbytes / (ms * 1e-3) / 1e9, 1),
-                     "bound": bound, "frac": round(max(t_tensor, t_hbm) / ms, 4), "tensor_peak": tensor_peak})
+                     "bound": bound, "frac": round(max(t_tensor, t_hbm) / ms, 4),
+                     "tensor_frac": round(t_tensor / ms, 4), "hbm_frac": round(t_hbm / ms, 4), "tensor_peak": tensor_peak})
     rows.sort(key=lambda r: -r["us_per_step"])
     return rows, (bf16_peak if dtype == "bf16" else tf32_peak)
 

@@ -35,7 +35,7 @@ def operands(M, N, K, a_mn, b_mn, seed):
 
 @pytest.mark.parametrize("block_n", [64, 128])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (240, 96, 136), (300, 200, 40), (64, 64, 512), (256, 1024, 256)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (240, 96, 136), (304, 200, 40), (64, 64, 512), (256, 1024, 256)])   # bf16 rows need 16-byte pitches: multiples of 8
 @pytest.mark.parametrize("out16", [False, True])
 def test_bf16_gemm_all_majors(gemm, block_n, a_mn, b_mn, M, N, K, out16):
     A, B, As, Bs = operands(M, N, K, a_mn, b_mn, M * 7 + N * 3 + K + a_mn * 2 + b_mn)

@@ -68,15 +68,21 @@ def test_shipped_config_eval_matches_the_reference(golden, name):
     assert err <= 5e-3 * max(1.0, ref[valid].abs().max().item()), err
     (out * torch.tensor(g[name + ":w"]).cuda()).sum().backward()
     worst = 0.0
-    for k, p in model.named_parameters():
+    # gradients that are mathematically zero (the key-projection bias: softmax is invariant to a per-query shift of
+    # the scores) are rounding noise on both sides: errors are measured against a floor tied to the largest
+    # per-element gradient of the model, like the other scorer tests
+    params = dict(model.named_parameters())
+    rms_max = max(float(g[name + ":n:" + k]) / np.sqrt(p.numel()) for k, p in params.items())
+    for k, p in params.items():
         gi = grad_sample_index(p.numel())
         got = p.grad.detach().flatten().cpu()[gi].double().numpy()
         want = g[name + ":g:" + k].astype(np.float64)
-        scale = float(g[name + ":n:" + k]) * np.sqrt(len(gi) / p.numel())     # expected norm of the sample
-        rel = np.linalg.norm(got - want) / max(np.linalg.norm(want), 0.05 * scale, 1e-12)
+        floor = 1e-2 * rms_max * np.sqrt(len(gi))
+        rel = np.linalg.norm(got - want) / max(np.linalg.norm(want), floor)
         worst = max(worst, rel)
         assert rel <= 5e-2, (k, rel)
-        n_rel = abs(p.grad.norm().item() - float(g[name + ":n:" + k])) / max(float(g[name + ":n:" + k]), 1e-12)
+        ref_norm = float(g[name + ":n:" + k])
+        n_rel = abs(p.grad.norm().item() - ref_norm) / max(ref_norm, 1e-2 * rms_max * np.sqrt(p.numel()))
         assert n_rel <= 5e-2, (k, n_rel)
     print(name, "eval: score err", err, "worst sampled-gradient rel err", worst)
 
