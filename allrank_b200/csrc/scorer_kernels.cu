@@ -86,6 +86,9 @@ __device__ __forceinline__ void apply_drop(RowRegs<NV>& r, long long row, int wi
 
 // ------------------------------------------------------------------------------------------------ LayerNorm fwd
 // y = a * (x - mean) / (std_unbiased + eps) + b ; saves mean and std per row.
+// A warp owns FWD_RPW consecutive rows and issues all their loads before the first reduction: one row per warp leaves
+// only 512 B in flight per warp at d_model = 128, far too little to cover the HBM latency (Little's law).
+constexpr int FWD_RPW = 4;
 template <int NV>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float* __restrict__ x,
                                                                     const float* __restrict__ a,
@@ -96,40 +99,64 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
                                                                     uint16_t* __restrict__ y16) {
   arb_pdl_wait();
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  RowRegs<NV> r, ga, gb;
-  load_row<NV>(x + row * width, width, lane, r);
-  load_row<NV>(a, width, lane, ga);
-  load_row<NV>(b, width, lane, gb);
-  float s = 0.f;
+  const long long row0 = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * FWD_RPW;
+  if (row0 >= rows) return;
+  RowRegs<NV> r[FWD_RPW], ga, gb;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) s += r.v[k].x + r.v[k].y + r.v[k].z + r.v[k].w;
-  const float mean = warp_sum(s) / float(width);
-  float ss = 0.f;
+  for (int q = 0; q < FWD_RPW; ++q) {
+    if (row0 + q < rows) load_row<NV>(x + (row0 + q) * width, width, lane, r[q]);
+    else {
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c = lane * 4 + 128 * k;
-    if (c < width) {
-      const float d0 = r.v[k].x - mean, d1 = r.v[k].y - mean, d2 = r.v[k].z - mean, d3 = r.v[k].w - mean;
-      ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      for (int k = 0; k < NV; ++k) r[q].v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  // torch_mode: nn.LayerNorm (biased variance, eps inside the root; FCModel's input_norm, model.py:27) -- the saved
-  // "std" is then sqrt(var + eps) and the backward is called with eps = 0
-  const float ssum = warp_sum(ss);
-  const float sd = torch_mode ? sqrtf(ssum / float(width) + eps) : sqrtf(ssum / float(width - 1));
-  const float denom = torch_mode ? sd : sd + eps;
+  load_row<NV>(a, width, lane, ga);
+  load_row<NV>(b, width, lane, gb);
+  float mean[FWD_RPW], sd[FWD_RPW];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    r.v[k].x = ga.v[k].x * (r.v[k].x - mean) / denom + gb.v[k].x;
-    r.v[k].y = ga.v[k].y * (r.v[k].y - mean) / denom + gb.v[k].y;
-    r.v[k].z = ga.v[k].z * (r.v[k].z - mean) / denom + gb.v[k].z;
-    r.v[k].w = ga.v[k].w * (r.v[k].w - mean) / denom + gb.v[k].w;
+  for (int q = 0; q < FWD_RPW; ++q) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s += r[q].v[k].x + r[q].v[k].y + r[q].v[k].z + r[q].v[k].w;
+    mean[q] = s;
   }
-  if (y16) store_row_bf16<NV>(y16 + row * width, width, lane, r);      // bf16 mode: the GEMM operand copy only
-  else store_row<NV>(y + row * width, width, lane, r);
-  if (lane == 0) { mean_o[row] = mean; std_o[row] = sd; }
+#pragma unroll
+  for (int q = 0; q < FWD_RPW; ++q) mean[q] = warp_sum(mean[q]) / float(width);
+#pragma unroll
+  for (int q = 0; q < FWD_RPW; ++q) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane * 4 + 128 * k;
+      if (c < width) {
+        const float d0 = r[q].v[k].x - mean[q], d1 = r[q].v[k].y - mean[q], d2 = r[q].v[k].z - mean[q],
+                    d3 = r[q].v[k].w - mean[q];
+        ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      }
+    }
+    sd[q] = ss;
+  }
+#pragma unroll
+  for (int q = 0; q < FWD_RPW; ++q) sd[q] = warp_sum(sd[q]);
+#pragma unroll
+  for (int q = 0; q < FWD_RPW; ++q) {
+    if (row0 + q >= rows) break;
+    // torch_mode: nn.LayerNorm (biased variance, eps inside the root; FCModel's input_norm, model.py:27) -- the saved
+    // "std" is then sqrt(var + eps) and the backward is called with eps = 0
+    const float sdq = torch_mode ? sqrtf(sd[q] / float(width) + eps) : sqrtf(sd[q] / float(width - 1));
+    const float denom = torch_mode ? sdq : sdq + eps;
+    const float m = mean[q];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) / denom + gb.v[k].x;
+      r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) / denom + gb.v[k].y;
+      r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) / denom + gb.v[k].z;
+      r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) / denom + gb.v[k].w;
+    }
+    if (y16) store_row_bf16<NV>(y16 + (row0 + q) * width, width, lane, r[q]);   // bf16 mode: the GEMM operand copy only
+    else store_row<NV>(y + (row0 + q) * width, width, lane, r[q]);
+    if (lane == 0) { mean_o[row0 + q] = m; std_o[row0 + q] = sdq; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm bwd
@@ -157,14 +184,23 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
 #pragma unroll
   for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = acc_c.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
+  // Software pipeline over the warp's rows: the loads of row it+1 (dy, x, residual gradient, statistics) are issued
+  // before the reductions of row it, so two rows of traffic are in flight per warp.
+  RowRegs<NV> g, xr, res, g_n, xr_n, res_n;
+  float mean = 0.f, sd = 1.f, mean_n = 0.f, sd_n = 1.f;
+  auto fetch = [&](long long row, RowRegs<NV>& gg, RowRegs<NV>& xx, RowRegs<NV>& rr, float& mm, float& ss) {
+    if (dy16_in) load_row_bf16<NV>(dy16_in + row * width, width, lane, gg);
+    else load_row<NV>(dy + row * width, width, lane, gg);
+    load_row<NV>(x + row * width, width, lane, xx);
+    if (dres) load_row<NV>(dres + row * width, width, lane, rr);
+    mm = mean_i[row]; ss = std_i[row];
+  };
+  if (first < rows) fetch(first, g, xr, res, mean, sd);
   for (int it = 0; it < rows_per_warp; ++it) {
     const long long row = first + it;
     if (row >= rows) break;
-    RowRegs<NV> g, xr;
-    if (dy16_in) load_row_bf16<NV>(dy16_in + row * width, width, lane, g);
-    else load_row<NV>(dy + row * width, width, lane, g);
-    load_row<NV>(x + row * width, width, lane, xr);
-    const float mean = mean_i[row], sd = std_i[row];
+    const bool more = it + 1 < rows_per_warp && row + 1 < rows;
+    if (more) fetch(row + 1, g_n, xr_n, res_n, mean_n, sd_n);
     const float r = 1.0f / (sd + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -193,8 +229,6 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
     const float m1 = s1 / float(width);
     const float coef = torch_mode ? r * r * r * s2 / float(width)
                                   : ((sd > 0.f) ? r * r * s2 / (float(width - 1) * sd) : 0.f);
-    RowRegs<NV> res;
-    if (dres) load_row<NV>(dres + row * width, width, lane, res);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       float* gv = &g.v[k].x;
@@ -219,6 +253,11 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float
       for (int k = 0; k < NV; ++k) {
         acc_c.v[k].x += g.v[k].x; acc_c.v[k].y += g.v[k].y; acc_c.v[k].z += g.v[k].z; acc_c.v[k].w += g.v[k].w;
       }
+    }
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) { g.v[k] = g_n.v[k]; xr.v[k] = xr_n.v[k]; res.v[k] = res_n.v[k]; }
+      mean = mean_n; sd = sd_n;
     }
   }
   // block-level reduction of the gain/bias gradients
@@ -438,48 +477,84 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
                                                                       float* __restrict__ std_o) {
   arb_pdl_wait();
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  RowRegs<NV> r, ga, gb, gw;
-  load_row<NV>(x + row * width, width, lane, r);
+  // FWD_RPW rows per warp, all loads issued up front (see ln_fwd_kernel)
+  const long long row0 = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * FWD_RPW;
+  if (row0 >= rows) return;
+  RowRegs<NV> r[FWD_RPW], ga, gb, gw;
+#pragma unroll
+  for (int q = 0; q < FWD_RPW; ++q) {
+    if (row0 + q < rows) load_row<NV>(x + (row0 + q) * width, width, lane, r[q]);
+    else {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) r[q].v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   load_row<NV>(w, width, lane, gw);
-  float mean = 0.f, sd = 0.f;
+  float mean[FWD_RPW], sd[FWD_RPW];
+#pragma unroll
+  for (int q = 0; q < FWD_RPW; ++q) mean[q] = sd[q] = 0.f;
   if (has_norm) {
     load_row<NV>(a, width, lane, ga);
     load_row<NV>(b, width, lane, gb);
-    float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) s += r.v[k].x + r.v[k].y + r.v[k].z + r.v[k].w;
-    mean = warp_sum(s) / float(width);
-    float ss = 0.f;
+    for (int q = 0; q < FWD_RPW; ++q) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) s += r[q].v[k].x + r[q].v[k].y + r[q].v[k].z + r[q].v[k].w;
+      mean[q] = s;
+    }
+#pragma unroll
+    for (int q = 0; q < FWD_RPW; ++q) mean[q] = warp_sum(mean[q]) / float(width);
+#pragma unroll
+    for (int q = 0; q < FWD_RPW; ++q) {
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + 128 * k;
+        if (c < width) {
+          const float d0 = r[q].v[k].x - mean[q], d1 = r[q].v[k].y - mean[q], d2 = r[q].v[k].z - mean[q],
+                      d3 = r[q].v[k].w - mean[q];
+          ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+      }
+      sd[q] = ss;
+    }
+#pragma unroll
+    for (int q = 0; q < FWD_RPW; ++q) sd[q] = sqrtf(warp_sum(sd[q]) / float(width - 1));
+#pragma unroll
+    for (int q = 0; q < FWD_RPW; ++q) {
+      const float denom = sd[q] + eps, m = mean[q];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) / denom + gb.v[k].x;
+        r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) / denom + gb.v[k].y;
+        r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) / denom + gb.v[k].z;
+        r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) / denom + gb.v[k].w;
+      }
+    }
+  }
+  float dot[FWD_RPW];
+#pragma unroll
+  for (int q = 0; q < FWD_RPW; ++q) {
+    float t = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c = lane * 4 + 128 * k;
-      if (c < width) {
-        const float d0 = r.v[k].x - mean, d1 = r.v[k].y - mean, d2 = r.v[k].z - mean, d3 = r.v[k].w - mean;
-        ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-      }
+      if (c < width)
+        t += r[q].v[k].x * gw.v[k].x + r[q].v[k].y * gw.v[k].y + r[q].v[k].z * gw.v[k].z + r[q].v[k].w * gw.v[k].w;
     }
-    sd = sqrtf(warp_sum(ss) / float(width - 1));
-    const float denom = sd + eps;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      r.v[k].x = ga.v[k].x * (r.v[k].x - mean) / denom + gb.v[k].x;
-      r.v[k].y = ga.v[k].y * (r.v[k].y - mean) / denom + gb.v[k].y;
-      r.v[k].z = ga.v[k].z * (r.v[k].z - mean) / denom + gb.v[k].z;
-      r.v[k].w = ga.v[k].w * (r.v[k].w - mean) / denom + gb.v[k].w;
-    }
+    dot[q] = t;
   }
-  float dot = 0.f;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c = lane * 4 + 128 * k;
-    if (c < width) dot += r.v[k].x * gw.v[k].x + r.v[k].y * gw.v[k].y + r.v[k].z * gw.v[k].z + r.v[k].w * gw.v[k].w;
-  }
-  dot = warp_sum(dot);
+  for (int q = 0; q < FWD_RPW; ++q) dot[q] = warp_sum(dot[q]);
   if (lane == 0) {
-    score[row] = act_fwd(dot + wb[0], act);
-    if (has_norm && mean_o) { mean_o[row] = mean; std_o[row] = sd; }
+    const float bias = wb[0];
+#pragma unroll
+    for (int q = 0; q < FWD_RPW; ++q) {
+      if (row0 + q >= rows) break;
+      score[row0 + q] = act_fwd(dot[q] + bias, act);
+      if (has_norm && mean_o) { mean_o[row0 + q] = mean[q]; std_o[row0 + q] = sd[q]; }
+    }
   }
 }
 
@@ -503,15 +578,23 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
   for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = acc_w.v[k] = acc_c.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   float acc_wb = 0.f;
   const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
+  // software pipeline: row it+1's loads are issued before row it's reductions (see ln_bwd_kernel)
+  RowRegs<NV> xr, g, xr_n;
+  float out = 0.f, dsc = 0.f, mean = 0.f, sd = 1.f, out_n = 0.f, dsc_n = 0.f, mean_n = 0.f, sd_n = 1.f;
+  auto fetch = [&](long long row, RowRegs<NV>& xx, float& oo, float& dd, float& mm, float& ss) {
+    load_row<NV>(x + row * width, width, lane, xx);
+    oo = score[row]; dd = dscore[row];
+    if (has_norm) { mm = mean_i[row]; ss = std_i[row]; }
+  };
+  if (first < rows) fetch(first, xr, out, dsc, mean, sd);
   for (int it = 0; it < rows_per_warp; ++it) {
     const long long row = first + it;
     if (row >= rows) break;
-    RowRegs<NV> xr, g;
-    load_row<NV>(x + row * width, width, lane, xr);
-    const float out = score[row];
+    const bool more = it + 1 < rows_per_warp && row + 1 < rows;
+    if (more) fetch(row + 1, xr_n, out_n, dsc_n, mean_n, sd_n);
     float z = 0.f;
     if (act == ARB_ACT_RELU) z = out;   // relu: out > 0 <=> z > 0
-    const float dz = dscore[row] * act_bwd(out, z, act);
+    const float dz = dsc * act_bwd(out, z, act);
     if (lane == 0) acc_wb += dz;
     if (!has_norm) {
 #pragma unroll
@@ -532,9 +615,13 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
           acc_c.v[k].x += g.v[k].x; acc_c.v[k].y += g.v[k].y; acc_c.v[k].z += g.v[k].z; acc_c.v[k].w += g.v[k].w;
         }
       }
+      if (more) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) xr.v[k] = xr_n.v[k];
+        out = out_n; dsc = dsc_n;
+      }
       continue;
     }
-    const float mean = mean_i[row], sd = std_i[row];
     const float r = 1.0f / (sd + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -583,6 +670,11 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
       for (int k = 0; k < NV; ++k) {
         acc_c.v[k].x += g.v[k].x; acc_c.v[k].y += g.v[k].y; acc_c.v[k].z += g.v[k].z; acc_c.v[k].w += g.v[k].w;
       }
+    }
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) xr.v[k] = xr_n.v[k];
+      out = out_n; dsc = dsc_n; mean = mean_n; sd = sd_n;
     }
   }
 #pragma unroll
@@ -831,7 +923,7 @@ static int check_launch() {
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
                float* mean, float* sd, cudaStream_t st, int torch_mode, void* y16) {
   if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
-  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * FWD_RPW - 1) / (ROWS_PER_BLOCK * FWD_RPW));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((y16 ? 6.0 : 8.0) * width + 8), st);
   ARB_DISPATCH_NV(width, (arb_launch(ln_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16))));
   return check_launch();
@@ -932,7 +1024,7 @@ int head_forward(const float* x, const float* a, const float* b, float eps, cons
                  int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,
                  cudaStream_t st) {
   if (width % 4) { arb_set_error("model width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
-  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * FWD_RPW - 1) / (ROWS_PER_BLOCK * FWD_RPW));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (4.0 * width + 12), st);
   ARB_DISPATCH_NV(width, (arb_launch(head_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd)));
   return check_launch();
