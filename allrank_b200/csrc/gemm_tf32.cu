@@ -52,6 +52,50 @@ struct GemmParams {
   float* colsum_out;
 };
 
+// ---- epilogue element transform -----------------------------------------------------------------------------------
+// One thread turns its 32 accumulator values of a 32-column chunk into the staged fp32 output row piece by piece.
+// The flags are COMPILE-TIME here: with run-time flags the unrolled loop carries a test per element and flag (about
+// 20 instructions per element), and the epilogue -- not HBM -- bounds the short-K linears (ncu, round 2: the eight
+// epilogue warps of the persistent kernel issue 37 % of all cycles at 31 % DRAM utilisation).  epi_chunk_dispatch
+// picks the instantiation once per chunk; unusual flag combinations take the generic run-time path.
+template <int F>
+__device__ __forceinline__ void epi_chunk_f32(const uint32_t (&v)[32], uint8_t* slab_row, int row, const float* bias_c,
+                                              float alpha) {
+#pragma unroll
+  for (int piece = 0; piece < 8; ++piece) {
+    float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
+    float4 o = make_float4(__uint_as_float(v[piece * 4 + 0]) * alpha, __uint_as_float(v[piece * 4 + 1]) * alpha,
+                           __uint_as_float(v[piece * 4 + 2]) * alpha, __uint_as_float(v[piece * 4 + 3]) * alpha);
+    if constexpr ((F & EPI_BIAS) != 0) {
+      const float4 bv = *reinterpret_cast<const float4*>(bias_c + 4 * piece);
+      o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+    }
+    if constexpr ((F & EPI_RELU) != 0) {
+      o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
+    }
+    if constexpr ((F & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0) {
+      const float4 a = *dst;
+      if constexpr ((F & EPI_ADD_AUX) != 0) { o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+      if constexpr ((F & EPI_MASK_AUX) != 0) {
+        o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f; o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f;
+      }
+    }
+    *dst = o;
+  }
+}
+// returns false when the flag combination has no specialisation (caller runs the generic loop)
+__device__ __forceinline__ bool epi_chunk_dispatch(int flags, const uint32_t (&v)[32], uint8_t* slab_row, int row,
+                                                   const float* bias_c, float alpha) {
+  switch (flags & (EPI_BIAS | EPI_RELU | EPI_ADD_AUX | EPI_MASK_AUX | EPI_DROPOUT | EPI_ATOMIC)) {
+    case 0: epi_chunk_f32<0>(v, slab_row, row, bias_c, alpha); return true;
+    case EPI_BIAS: epi_chunk_f32<EPI_BIAS>(v, slab_row, row, bias_c, alpha); return true;
+    case EPI_BIAS | EPI_RELU: epi_chunk_f32<EPI_BIAS | EPI_RELU>(v, slab_row, row, bias_c, alpha); return true;
+    case EPI_BIAS | EPI_ADD_AUX: epi_chunk_f32<EPI_BIAS | EPI_ADD_AUX>(v, slab_row, row, bias_c, alpha); return true;
+    case EPI_MASK_AUX: epi_chunk_f32<EPI_MASK_AUX>(v, slab_row, row, bias_c, alpha); return true;
+    default: return false;
+  }
+}
+
 template <int BLOCK_N, int NST = 2>
 struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 4;
@@ -254,6 +298,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
         continue;
       }
       uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
+      if constexpr (!DROP) {
+        if (epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha)) continue;
+      }
 #pragma unroll
       for (int piece = 0; piece < 8; ++piece) {
         float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
@@ -556,6 +603,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
             for (int j = 0; j < 32; ++j) v[j] = 0u;
           }
           uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
+          if (!epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha)) {
 #pragma unroll
           for (int piece = 0; piece < 8; ++piece) {
             float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
@@ -596,6 +644,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
             } else {
               *dst = make_float4(o[0], o[1], o[2], o[3]);
             }
+          }
           }
           if (!split) {
             ptx::fence_proxy_async_smem();

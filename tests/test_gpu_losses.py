@@ -355,6 +355,8 @@ def test_neural_sort_and_sinkhorn_matrices_match_the_reference(golden):
                 block[b] = False
         r0, r1 = g[key + "_p0"], g[key + "_p"]
         # the reference's row j of the real block is the j-th RANK; its columns are the items
-        assert np.abs(p0.cpu().numpy() - r0)[block].max() <= 1e-5, key
-        assert np.abs(p.cpu().numpy() - r1)[block].max() <= 2e-5, key
+        # fp32 logits are O(n * |s|) / tau: at tau = 0.1 their ulp (2.4e-4 at 3000) bounds what exp() can reproduce
+        tol0 = 1e-5 if tau >= 1.0 else 1e-4
+        assert np.abs(p0.cpu().numpy() - r0)[block].max() <= tol0, key
+        assert np.abs(p.cpu().numpy() - r1)[block].max() <= 2 * tol0, key
         assert (p.cpu().numpy()[~block] == 0).all()
