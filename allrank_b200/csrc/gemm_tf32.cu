@@ -847,8 +847,15 @@ template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                     const CUtensorMap& tX, const GemmParams& p, dim3 grid, cudaStream_t st) {
   if (d.A.bf16) return launch_bf16_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
-  const bool long_k = !(A_MN == 1 && B_MN == 1) && !(p.flags & EPI_ATOMIC) && d.K >= 256 && d.nb2 == 1 && d.nb3 == 1;
-  if (g_persistent == 1 || (g_persistent == 2 && long_k && !(p.flags & EPI_COLSUM)))
+  // Mode 2 (default), measured per launch in round 2 after the epilogue was specialised (profiles/r2): the persistent
+  // pipeline wins on every unbatched, non-split shape (short-K wide-N forward linears 0.76-0.86 of the HBM roof against
+  // 0.58-0.62 for one-tile CTAs; K >= 256: 0.93-0.98) EXCEPT short-K products with a residual / mask tile, whose aux
+  // load it can only issue once the previous tile's stores have left the staging area (dgrad N512 K128 mask: 0.70
+  // against 0.85; the K128 +res projection ties).
+  const bool has_aux_tile = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
+  const bool pick = !(A_MN == 1 && B_MN == 1) && !(p.flags & EPI_ATOMIC) && d.nb2 == 1 && d.nb3 == 1 &&
+                    (d.K >= 256 || !has_aux_tile);
+  if (g_persistent == 1 || (g_persistent == 2 && pick))
     return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
   // dropout epilogue is a separate instantiation (forward linears only) so the common path carries no mask code;
   // ring depth: 4 stages for the long split-K loops of the weight gradients (1 CTA/SM), 3 for K >= 256

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
 // dx = [dres +] r (dxh - mean(dxh)) - r^2 (sum_k dxh_k c_k) / ((d-1) std) * c,   dxh = dy * a, c = x - mean,
 // r = 1/(std+eps).   grad_a += sum_rows dy * xhat,  grad_b += sum_rows dy  (block partials -> atomicAdd).
 template <int NV>
-__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_bwd_kernel(const float* __restrict__ dy,
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32, NV == 1 ? 4 : 1) ln_bwd_kernel(const float* __restrict__ dy,
                                                                     const float* __restrict__ x,
                                                                     const float* __restrict__ a,
                                                                     const float* __restrict__ mean_i,
@@ -578,23 +578,15 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
   for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = acc_w.v[k] = acc_c.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   float acc_wb = 0.f;
   const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
-  // software pipeline: row it+1's loads are issued before row it's reductions (see ln_bwd_kernel)
-  RowRegs<NV> xr, g, xr_n;
-  float out = 0.f, dsc = 0.f, mean = 0.f, sd = 1.f, out_n = 0.f, dsc_n = 0.f, mean_n = 0.f, sd_n = 1.f;
-  auto fetch = [&](long long row, RowRegs<NV>& xx, float& oo, float& dd, float& mm, float& ss) {
-    load_row<NV>(x + row * width, width, lane, xx);
-    oo = score[row]; dd = dscore[row];
-    if (has_norm) { mm = mean_i[row]; ss = std_i[row]; }
-  };
-  if (first < rows) fetch(first, xr, out, dsc, mean, sd);
   for (int it = 0; it < rows_per_warp; ++it) {
     const long long row = first + it;
     if (row >= rows) break;
-    const bool more = it + 1 < rows_per_warp && row + 1 < rows;
-    if (more) fetch(row + 1, xr_n, out_n, dsc_n, mean_n, sd_n);
+    RowRegs<NV> xr, g;
+    load_row<NV>(x + row * width, width, lane, xr);
+    const float out = score[row];
     float z = 0.f;
     if (act == ARB_ACT_RELU) z = out;   // relu: out > 0 <=> z > 0
-    const float dz = dsc * act_bwd(out, z, act);
+    const float dz = dscore[row] * act_bwd(out, z, act);
     if (lane == 0) acc_wb += dz;
     if (!has_norm) {
 #pragma unroll
@@ -615,13 +607,9 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
           acc_c.v[k].x += g.v[k].x; acc_c.v[k].y += g.v[k].y; acc_c.v[k].z += g.v[k].z; acc_c.v[k].w += g.v[k].w;
         }
       }
-      if (more) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) xr.v[k] = xr_n.v[k];
-        out = out_n; dsc = dsc_n;
-      }
       continue;
     }
+    const float mean = mean_i[row], sd = std_i[row];
     const float r = 1.0f / (sd + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -670,11 +658,6 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
       for (int k = 0; k < NV; ++k) {
         acc_c.v[k].x += g.v[k].x; acc_c.v[k].y += g.v[k].y; acc_c.v[k].z += g.v[k].z; acc_c.v[k].w += g.v[k].w;
       }
-    }
-    if (more) {
-#pragma unroll
-      for (int k = 0; k < NV; ++k) xr.v[k] = xr_n.v[k];
-      out = out_n; dsc = dsc_n; mean = mean_n; sd = sd_n;
     }
   }
 #pragma unroll
