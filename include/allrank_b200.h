@@ -237,8 +237,10 @@ void arb_set_pdl(int32_t on);
 void arb_set_attention_fwd_two_pass(int32_t on);
 
 /* GEMM kernel choice.  0: one CTA per output tile everywhere; 1: the persistent, decoupled-pipeline kernel (one CTA per
- * SM walking all tiles) wherever it is supported; 2 (default): persistent only for non-split contractions with
- * K >= 256, where it measured faster.  Process-wide; exists for A/B measurements. */
+ * SM walking all tiles) wherever it is supported; 2 (default): persistent for every unbatched, non-split product except
+ * short-K ones with a residual / mask tile (measured per launch, profiles/r2); 3: as 2 plus those, every aux tile in a
+ * shared-memory buffer of its own; 4: as 3 but the own buffer only when K < 256.  Process-wide; exists for A/B
+ * measurements. */
 void arb_set_gemm_persistent(int32_t on);
 
 /* 1 (default): MMA operands are rounded fp32 -> tf32 by the TMA unit (TFLOAT32 tensor maps); 0: the tensor core

@@ -129,3 +129,45 @@ def test_linearity_property(gemm):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
     ref, bound = ref_and_bound(A, B1)
     assert ((outs[0].double() - ref).abs() <= bound).all()
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("K", [128, 512])
+@pytest.mark.parametrize("block_n", [64, 128])
+def test_persistent_modes_are_bit_identical_to_the_tile_kernel(gemm, mode, K, block_n):
+    """Every CTA of the persistent kernel walks several tiles (M x N = 400 x 2 tiles of 128 x 128 on 148 SMs), with
+    and without a residual / ReLU-mask tile (modes 3 / 4: the aux tile in a buffer of its own), ragged last tiles
+    included; same MMA order per tile -> same bits as the one-tile-per-CTA kernel."""
+    from allrank_b200 import _lib
+    _lib.register("arb_set_gemm_persistent", None, [ctypes.c_int32])
+    torch.manual_seed(K + block_n)
+    M, N = 128 * 400 - 40, 256 - 8
+    A = torch.randn(M, K, device="cuda")
+    W = torch.randn(N, K, device="cuda") / K ** 0.5
+    bias = torch.randn(N, device="cuda")
+    X = torch.randn(M, N, device="cuda")
+
+    def run():
+        outs = []
+        C = torch.empty(M, N, device="cuda")
+        gemm(A, W, C, None, bias, M, N, K, 0, 0, 1, 0, 0, 0, block_n, EPI_BIAS | EPI_RELU, 1.0)
+        outs.append(C)
+        Xc = X.clone()
+        gemm(A, W, Xc, Xc, bias, M, N, K, 0, 0, 1, 0, 0, 0, block_n, EPI_BIAS | EPI_ADD_AUX, 1.0)
+        outs.append(Xc)
+        C = torch.empty(M, N, device="cuda")
+        gemm(A, W, C, X, None, M, N, K, 0, 0, 1, 0, 0, 0, block_n, EPI_MASK_AUX, 0.5)
+        outs.append(C)
+        return outs
+
+    try:
+        _lib.lib().arb_set_gemm_persistent(0)
+        want = run()
+        _lib.lib().arb_set_gemm_persistent(mode)
+        got = run()
+    finally:
+        import os
+        _lib.lib().arb_set_gemm_persistent(int(os.environ.get("ARB_GEMM_PERSISTENT", 2)))
+    assert (want[1].double() - (A.double() @ W.double().t() + bias.double() + X.double())).abs().max() < 6e-3
+    for w, g in zip(want, got):
+        assert torch.equal(w, g)
