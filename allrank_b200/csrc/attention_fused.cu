@@ -61,8 +61,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
                                                                   float* __restrict__ stat_max,
                                                                   float* __restrict__ stat_sum, int S, int n_heads,
                                                                   float scale_log2e, DropSite drop,
-                                                                  const int* __restrict__ extent) {
-  (void)extent;   // the single-pass kernel always covers the whole slate
+                                                                  const int* __restrict__ extent,
+                                                                  const int* __restrict__ pack_off) {
+  (void)extent; (void)pack_off;   // the single-pass kernel always covers the whole (dense) slate
   using L = AttFwdSmem<DK>;
   constexpr int NKB = L::NKB;
   extern __shared__ uint8_t smem_dyn[];
@@ -253,7 +254,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
                                                                    float* __restrict__ stat_max,
                                                                    float* __restrict__ stat_sum, int S, int n_heads,
                                                                    float scale_log2e, DropSite drop,
-                                                                   const int* __restrict__ extent) {
+                                                                   const int* __restrict__ extent,
+                                                                   const int* __restrict__ pack_off) {
   static_assert(DK <= 32, "two-pass forward kernel: head width <= 32");
   using L = AttFwdSmem<DK>;
   extern __shared__ uint8_t smem_dyn[];
@@ -272,6 +274,15 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  // Packed rows (pack_off != nullptr): the activations hold only the first round_up(extent, 16) rows of every slate,
+  // slate b starting at row pack_off[b] of one long [rows, h, dk] tensor (TMA coordinates (.., row, head, 0)).  Boxes
+  // that overrun the slate read the next slates' rows (finite; their keys are masked, their query rows never stored);
+  // the output is stored in 16-row boxes that stop at the slate's last packed row.  extent / pack_off were written by
+  // kernels at least two launches upstream, so they may be read before the PDL wait.
+  const bool packed = pack_off != nullptr;
+  const int row_base = packed ? pack_off[b] : 0;
+  const int bc = packed ? 0 : b;
+  if (packed && m0 >= ((extent[b] + 15) & ~15)) return;   // no packed query rows in this tile (or an empty slate)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmO);
@@ -312,10 +323,10 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
     if (lane == 0) {
       // K and V arrive as 128-key boxes: only the chunks that hold keys below the extent are fetched
       ptx::mbar_expect_tx(load_bar, L::Q_BYTES + nkc * 2 * (128 * 128));
-      ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, m0, head, b);
+      ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, row_base + m0, head, bc);
       for (int kc = 0; kc < nkc; ++kc) {
-        ptx::tma_load_4d(k_s + kc * 16384, &tmK, load_bar, 0, 128 * kc, head, b);
-        ptx::tma_load_4d(v_s + kc * 16384, &tmV, load_bar, 0, 128 * kc, head, b);
+        ptx::tma_load_4d(k_s + kc * 16384, &tmK, load_bar, 0, row_base + 128 * kc, head, bc);
+        ptx::tma_load_4d(v_s + kc * 16384, &tmV, load_bar, 0, row_base + 128 * kc, head, bc);
       }
     }
   } else if (warp == 1) {
@@ -456,7 +467,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
     ptx::fence_proxy_async_smem();
     ptx::named_bar_sync(1, ATT2_SOFTMAX);
     if (threadIdx.x == 64) {
-      ptx::tma_store_4d(&tmO, o_s, 0, m0, head, b);
+      if (packed) {       // 16-row boxes up to the slate's last packed row (the staged rows are 128 / 64 bytes wide)
+        const int n16 = (min(128, S16 - m0) + 15) >> 4;
+        for (int i = 0; i < n16; ++i)
+          ptx::tma_store_4d(&tmO, o_s + i * (OUT16 ? 1024 : 2048), 0, row_base + m0 + 16 * i, head, 0);
+      } else {
+        ptx::tma_store_4d(&tmO, o_s, 0, m0, head, b);
+      }
       ptx::tma_store_commit();
       ptx::tma_store_wait_read();
     }
@@ -483,10 +500,12 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   if ((rc = make_tmap_4d(&tV, a.v, TmapBox{{32, kv_rows, 1, 1}}, 1, 1))) return rc;
   const bool out16 = a.o.bf16 != 0;
   if (out16 && !(DK <= 32 && g_attn_fwd_two_pass)) { arb_set_error("attn_fwd: a bf16 context needs the two-pass kernel (head width <= 32)"); return ARB_E_UNSUPPORTED; }
-  if ((rc = make_tmap_4d(&tO, a.o, TmapBox{{32, 128, 1, 1}}, out16 ? 2 : 0, 0))) return rc;
+  const bool packed = a.pack_off != nullptr;
+  if (packed && !(DK <= 32 && g_attn_fwd_two_pass && a.extent)) { arb_set_error("attn_fwd: packed rows need the two-pass kernel and the slate extents"); return ARB_E_UNSUPPORTED; }
+  if ((rc = make_tmap_4d(&tO, a.o, TmapBox{{32, packed ? 16u : 128u, 1, 1}}, out16 ? 2 : 0, 0))) return rc;
   const bool drop = a.drop.thresh != 0;
   void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const uint8_t*, float*, float*, int, int, float,
-               DropSite, const int*);
+               DropSite, const int*, const int*);
   if constexpr (DK <= 32) {
     if (g_attn_fwd_two_pass) {
       if (out16) kern = drop ? attn_fwd2_kernel<DK, true, true> : attn_fwd2_kernel<DK, false, true>;
@@ -510,11 +529,11 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   dim3 grid((a.S + 127) / 128, a.h, a.B);
   {
     ProfScope ps(ARB_PROF_GEMM, 4.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
-                 4.0 * double(a.B) * a.h * a.S * ((out16 ? 3.5 : 4.0) * a.dk + 2.0),
+                 (packed ? arb_row_frac() : 1.0) * 4.0 * double(a.B) * a.h * a.S * ((out16 ? 3.5 : 4.0) * a.dk + 2.0),
                  (DK <= 32 && g_attn_fwd_two_pass) ? "attn_fwd2_kernel" : "attn_fwd_kernel");
     const int threads = (DK <= 32 && g_attn_fwd_two_pass) ? ATT2_THREADS : ATT_THREADS;
     arb_launch(kern, grid, dim3(threads), size_t(L::total()), st, tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
-               a.scale * 1.4426950408889634f, a.drop, a.extent);
+               a.scale * 1.4426950408889634f, a.drop, a.extent, a.pack_off);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

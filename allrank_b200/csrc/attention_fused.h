@@ -17,6 +17,8 @@ struct AttnFwdArgs {
   DropSite drop{0u, 0u, 1.0f};   // dropout on the probabilities (transformer.py:154-155); index ((b*h+head)*S+q)*S+key
   const int* extent = nullptr;   // optional [B]: every key >= extent[b] is masked (slate_extents); work beyond it is
                                  // skipped -- those keys have probability exactly 0, so the result is unchanged
+  const int* pack_off = nullptr; // packed rows (needs extent): q/k/v/o are views (dk, rows, h, 1) of activations that hold
+                                 // only the first round_up(extent[b], 16) rows of every slate, slate b at row pack_off[b]
 };
 
 bool attn_fused_supported(int S, int dk);
@@ -47,6 +49,9 @@ struct AttnBwdArgs {
                                  // (slate_extents over the mask and the incoming score gradient): their tiles are
                                  // skipped and their dQ / dK / dV rows written as zeros -- exactly what the dense
                                  // computation produces
+  const int* pack_off = nullptr; // packed rows (needs extent = the forward's key extents): see AttnFwdArgs
+  const int* rows_dev = nullptr; // packed rows: plan[0] (live packed rows, for the delta kernel)
+  const int* rowmap = nullptr;   // packed rows: item index of every packed row (for the delta kernel)
 };
 
 bool attn_fused_bwd_supported(int S, int dk);

@@ -56,12 +56,17 @@ __device__ __forceinline__ uint32_t round_tf32_b(float x) {
 // segmented shuffle reduction over the dk/4 lanes that share a head (dk in {16, 32}: 4 or 8 lanes per head).
 __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict__ d_o, const float* __restrict__ o,
                                                          long long pitch, int B, int S, int h, int dk,
-                                                         float* __restrict__ delta, int o_bf16) {
+                                                         float* __restrict__ delta, int o_bf16,
+                                                         const int* __restrict__ rows_dev,
+                                                         const int* __restrict__ rowmap) {
   arb_pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= (long long)B * S) return;
-  const int b = int(row / S), qi = int(row % S);
+  if (row >= (long long)B * S || (rows_dev && row >= rows_dev[0])) return;
+  // packed rows: the activations are indexed by the packed row, delta by the item (rows without an item are skipped)
+  const long long item = rowmap ? (long long)rowmap[row] : row;
+  if (item < 0) return;
+  const int b = int(item / S), qi = int(item % S);
   const int width = h * dk, lanes_per_head = dk >> 2;
   for (int c0 = 0; c0 < width; c0 += 128) {
     const int c = c0 + lane * 4;
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
     const uint8_t* __restrict__ mask, const float* __restrict__ stat_max, const float* __restrict__ stat_sum,
     const float* __restrict__ delta, int S, int n_heads, float scale, DropSite drop, float* __restrict__ dbias_qkv,
-    int d_model, const int* __restrict__ extent) {
+    int d_model, const int* __restrict__ extent, const int* __restrict__ pack_off) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   auto tile = [&](int t) { return smem + t * TILE_BYTES; };
@@ -132,6 +137,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
   // the tiles below the extent are processed; the rest is written as zeros up front.
   const int n_full = (S + 127) / 128;
   const float c_log2e = scale * 1.4426950408889634f;
+  // Packed rows (see attn_fwd2_kernel): slate b holds its first ext16 = round_up(extent, 16) rows at row pack_off[b] of
+  // one long tensor.  Tiles that overrun the slate read other slates' rows: as keys they are masked, as queries their
+  // probabilities are forced to zero below (their d ctx rows are NOT zero, unlike the dense layout's padding); outputs
+  // are stored in 16-row boxes that stop at the slate's last packed row, and nothing is zero-filled.
+  const bool packed = pack_off != nullptr;
+  const int row_base = packed ? pack_off[b] : 0;
+  const int bc = packed ? 0 : b;
+  if (packed && extent[b] <= 0) return;       // an empty slate holds no packed rows
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQk); ptx::prefetch_tmap(&tmQm); ptx::prefetch_tmap(&tmKk); ptx::prefetch_tmap(&tmKm);
@@ -154,6 +167,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
   ptx::tc_fence_after();
   const int ext = extent ? max(1, min(S, extent[b])) : S;
   const int n_kt = (ext + 127) / 128;   // active key tiles == active query chunks
+  const int ext16 = (ext + 15) & ~15;
+  const int q_lim = packed ? min(S, ext16) : S;   // queries at or beyond it do not exist in this slate
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 320;
   const uint32_t T_DQ0 = tmem_base + 384;   // + 64 * qc
@@ -168,21 +183,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           // iteration's second half of S^T / dP^T has completed -- i.e. while its compute phases and trailing MMAs run.
           if (it > 0) ptx::mbar_wait(s_bar + 1, (it - 1) & 1);
           ptx::mbar_expect_tx(q_bar, 2 * TILE_BYTES);
-          ptx::tma_load_4d(tile(BwdSmem::Q_KM), &tmQk, q_bar, 0, 128 * qc, head, b);
-          ptx::tma_load_4d(tile(BwdSmem::DO_KM), &tmDOk, q_bar, 0, 128 * qc, head, b);
+          ptx::tma_load_4d(tile(BwdSmem::Q_KM), &tmQk, q_bar, 0, row_base + 128 * qc, head, bc);
+          ptx::tma_load_4d(tile(BwdSmem::DO_KM), &tmDOk, q_bar, 0, row_base + 128 * qc, head, bc);
           if (qc == 0) {
             ptx::mbar_expect_tx(kv_bar, 2 * TILE_BYTES);
-            ptx::tma_load_4d(tile(BwdSmem::K_KM), &tmKk, kv_bar, 0, 128 * jt, head, b);
-            ptx::tma_load_4d(tile(BwdSmem::V_KM), &tmVk, kv_bar, 0, 128 * jt, head, b);
+            ptx::tma_load_4d(tile(BwdSmem::K_KM), &tmKk, kv_bar, 0, row_base + 128 * jt, head, bc);
+            ptx::tma_load_4d(tile(BwdSmem::V_KM), &tmVk, kv_bar, 0, row_base + 128 * jt, head, bc);
           }
           // the MN-major tiles are still in use by the trailing MMAs (dV, dK, dQ) of the previous iteration
           if (it > 0) ptx::mbar_wait(mma_bar, (it - 1) & 1);
           ptx::mbar_expect_tx(qm_bar, 2 * TILE_BYTES);
-          ptx::tma_load_4d(tile(BwdSmem::Q_MN), &tmQm, qm_bar, 0, 128 * qc, head, b);
-          ptx::tma_load_4d(tile(BwdSmem::DO_MN), &tmDOm, qm_bar, 0, 128 * qc, head, b);
+          ptx::tma_load_4d(tile(BwdSmem::Q_MN), &tmQm, qm_bar, 0, row_base + 128 * qc, head, bc);
+          ptx::tma_load_4d(tile(BwdSmem::DO_MN), &tmDOm, qm_bar, 0, row_base + 128 * qc, head, bc);
           if (qc == 0) {
             ptx::mbar_expect_tx(km_bar, TILE_BYTES);
-            ptx::tma_load_4d(tile(BwdSmem::K_MN), &tmKm, km_bar, 0, 128 * jt, head, b);
+            ptx::tma_load_4d(tile(BwdSmem::K_MN), &tmKm, km_bar, 0, row_base + 128 * jt, head, bc);
           }
         }
       }
@@ -269,14 +284,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     auto load_stats = [&](int t, int slot) {
       const int qi = 128 * (t % n_kt) + slot;
       float2 st = make_float2(-CUDART_INF_F, 0.f);
-      if (qi < S) {
+      if (qi < q_lim) {
         const size_t so = (size_t(b) * n_heads + head) * S + qi;
         st.x = -(stat_max[so] * c_log2e) - log2f(stat_sum[so]);
         st.y = delta[so];
       }
       qstats[(t & 1) * 128 + slot] = st;
     };
-    if (n_kt < n_full) {
+    if (n_kt < n_full && !packed) {
       // zero rows of the skipped tiles: one zero slab, TMA-stored over every skipped dQ / dK / dV tile (TMA clips at S)
       for (int i = ct; i < TILE_BYTES / 16; i += BWD_COMPUTE) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0u, 0u, 0u, 0u);
       ptx::fence_proxy_async_smem();
@@ -337,11 +352,27 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       ptx::tc_fence_before();
       ptx::named_bar_sync(1, BWD_COMPUTE);
       if (ct == 0) {
-        if (last_qc) {
-          ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * e_jt, head, b);
-          ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES, 0, 128 * e_jt, head, b);
+        if (packed) {      // 16-row boxes up to the slate's last packed row (staged rows are 128 / 64 bytes wide)
+          constexpr int BOX = OUT16 ? 1024 : 2048;
+          if (last_qc) {
+            const int n16 = (min(128, ext16 - 128 * e_jt) + 15) >> 4;
+            for (int i = 0; i < n16; ++i) {
+              ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES + i * BOX, 0, row_base + 128 * e_jt + 16 * i, head, 0);
+              ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES + i * BOX, 0, row_base + 128 * e_jt + 16 * i, head, 0);
+            }
+          }
+          if (last_jt) {
+            const int n16 = (min(128, ext16 - 128 * e_qc) + 15) >> 4;
+            for (int i = 0; i < n16; ++i)
+              ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES + i * BOX, 0, row_base + 128 * e_qc + 16 * i, head, 0);
+          }
+        } else {
+          if (last_qc) {
+            ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * e_jt, head, b);
+            ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES, 0, 128 * e_jt, head, b);
+          }
+          if (last_jt) ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES, 0, 128 * e_qc, head, b);
         }
-        if (last_jt) ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES, 0, 128 * e_qc, head, b);
         ptx::tma_store_commit();
       }
       if (dbias_qkv != nullptr && ct < 384) {
@@ -453,14 +484,19 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   if ((rc = make_tmap_4d(&tDOm, a.d_o, box, 1, 1))) return rc;
   const bool out16 = a.dq.bf16 != 0;
   if ((a.dk_.bf16 != 0) != out16 || (a.dv.bf16 != 0) != out16) { arb_set_error("attn_bwd: dQ, dK, dV must share an element type"); return ARB_E_INVALID_ARG; }
-  if ((rc = make_tmap_4d(&tDQ, a.dq, box, out16 ? 2 : 0, 0))) return rc;
-  if ((rc = make_tmap_4d(&tDK, a.dk_, box, out16 ? 2 : 0, 0))) return rc;
-  if ((rc = make_tmap_4d(&tDV, a.dv, box, out16 ? 2 : 0, 0))) return rc;
+  const bool packed = a.pack_off != nullptr;
+  if (packed && !(a.extent && a.rows_dev && a.rowmap)) { arb_set_error("attn_bwd: packed rows need the extents, the row count and the row map"); return ARB_E_INVALID_ARG; }
+  const TmapBox obox{{32, packed ? 16u : 128u, 1, 1}};
+  if ((rc = make_tmap_4d(&tDQ, a.dq, obox, out16 ? 2 : 0, 0))) return rc;
+  if ((rc = make_tmap_4d(&tDK, a.dk_, obox, out16 ? 2 : 0, 0))) return rc;
+  if ((rc = make_tmap_4d(&tDV, a.dv, obox, out16 ? 2 : 0, 0))) return rc;
+  const double rf = packed ? arb_row_frac() : 1.0;
   {
-    ProfScope ps(ARB_PROF_SCORER_SIMT, double(a.B) * a.S * (8.0 * a.h * a.dk + 4.0 * a.h), st, 0.0, "attn_delta_kernel");
+    ProfScope ps(ARB_PROF_SCORER_SIMT, rf * double(a.B) * a.S * (8.0 * a.h * a.dk + 4.0 * a.h), st, 0.0, "attn_delta_kernel");
     const long long rows = (long long)a.B * a.S;
     arb_launch(attn_delta_kernel, dim3(unsigned((rows + 7) / 8)), dim3(256), 0, st, a.do_ptr,
-               static_cast<const float*>(a.o_ptr), (long long)a.o_pitch, a.B, a.S, a.h, a.dk, a.delta, a.o_bf16);
+               static_cast<const float*>(a.o_ptr), (long long)a.o_pitch, a.B, a.S, a.h, a.dk, a.delta, a.o_bf16, a.rows_dev,
+               a.rowmap);
   }
   arb_count_launch();
   const bool drop = a.drop.thresh != 0;
@@ -479,10 +515,10 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   dim3 grid(a.h, a.B);
   {
     ProfScope ps(ARB_PROF_GEMM, 10.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
-                 4.0 * double(a.B) * a.h * a.S * (7.0 * a.dk + 3.0), "attn_bwd_kernel");
+                 rf * 4.0 * double(a.B) * a.h * a.S * (7.0 * a.dk + 3.0), "attn_bwd_kernel");
     arb_launch(kern, grid, dim3(BWD_THREADS), size_t(BwdSmem::total()), st, tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
                                                       a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale, a.drop, a.dbias_qkv,
-                                                      a.d_model, a.extent);
+                                                      a.d_model, a.extent, a.pack_off);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

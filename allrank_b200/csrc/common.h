@@ -15,6 +15,11 @@ inline int arb_device_slot() {
   return (dev >= 0 && dev < ARB_MAX_DEVICES) ? dev : 0;
 }
 void arb_count_launch(int n = 1);
+// Accounting only: the fraction of the nominal B * S rows that launches over packed rows actually process (set by the
+// scorer when per-launch profiling is on; 1.0 otherwise).  Never steers a kernel.
+double arb_row_frac();
+void arb_set_row_frac(double f);
+bool arb_prof_enabled();
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
 // The step is a chain of ~50 dependent kernels; at allRank's own batch size (64 slates) every one of them is

@@ -50,6 +50,7 @@ struct GemmParams {
   long long atomic_ld;
   DropSite drop;
   float* colsum_out;
+  const int* rows_dev;   // packed rows: device-resident live row count -- bounds M, or K for the split-K weight gradients
 };
 
 // ---- epilogue element transform -----------------------------------------------------------------------------------
@@ -147,10 +148,17 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
   constexpr int KELEMS = IN16 ? BLOCK_K_BF16 : BLOCK_K;       // elements of K per k-block (128 bytes either way)
   constexpr int MN_SLAB = IN16 ? 64 : 32;                     // MN-elements per MN-major slab (128 bytes)
   constexpr int MN_SLAB_BYTES = MN_SLAB * KELEMS * (IN16 ? 2 : 4);   // 8192 (bf16) / 4096 (tf32)
-  const int total_kb = (p.K + KELEMS - 1) / KELEMS;
-  const int kb_begin = split ? int(blockIdx.z) * p.kb_per_split : 0;
-  const int kb_end = split ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
-  const int nkb = kb_end - kb_begin;
+  // Packed rows: the live row count is on the device (written at least two launches upstream, so it may be read
+  // before the PDL wait).  It bounds M -- CTAs of tiles beyond it leave at once -- or, for the split-K weight gradients,
+  // K, which is then divided evenly over the grid's splits here.
+  const bool dev_rows = p.rows_dev != nullptr;
+  if (dev_rows && !split && m0 >= p.rows_dev[0]) return;
+  const int k_live = (dev_rows && split) ? min(p.K, p.rows_dev[0]) : p.K;
+  const int total_kb = (k_live + KELEMS - 1) / KELEMS;
+  const int kb_per = (dev_rows && split) ? (total_kb + int(gridDim.z) - 1) / int(gridDim.z) : p.kb_per_split;
+  const int kb_begin = split ? int(blockIdx.z) * kb_per : 0;
+  const int kb_end = split ? min(total_kb, kb_begin + kb_per) : total_kb;
+  const int nkb = max(0, kb_end - kb_begin);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -439,7 +447,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split = (p.flags & EPI_ATOMIC) != 0;
   const bool has_aux = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
-  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const bool dev_rows = p.rows_dev != nullptr;     // packed rows: see gemm_tf32_kernel
+  if (dev_rows && !split) n_tiles_m = min(n_tiles_m, (p.rows_dev[0] + BLOCK_M - 1) / BLOCK_M);
+  const int total_kb = (((dev_rows && split) ? min(p.K, p.rows_dev[0]) : p.K) + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per = (dev_rows && split) ? (total_kb + n_z - 1) / n_z : p.kb_per_split;
   const int n_tiles = n_tiles_n * n_tiles_m * n_z;
 
   if (warp == 0 && lane == 0) {
@@ -469,8 +480,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
   };
   auto k_range = [&](int z, int& kb0, int& nkb) {
     if (split) {
-      kb0 = z * p.kb_per_split;
-      nkb = min(total_kb, kb0 + p.kb_per_split) - kb0;
+      kb0 = z * kb_per;
+      nkb = min(total_kb, kb0 + kb_per) - kb0;
       if (nkb < 0) nkb = 0;
     } else {
       kb0 = 0;
@@ -762,6 +773,9 @@ static void gemm_prof_name(char (&out)[56], const GemmDesc& d, const char* varia
                 (d.flags & EPI_MASK_AUX) ? " mask" : "");
 }
 
+// accounting only: a launch over packed rows (rows_dev) processes arb_row_frac() of its nominal M (or K, split-K)
+static double live_m(const GemmDesc& d) { return double(d.M) * ((d.rows_dev && !(d.flags & EPI_ATOMIC)) ? arb_row_frac() : 1.0); }
+static double live_k(const GemmDesc& d) { return double(d.K) * ((d.rows_dev && (d.flags & EPI_ATOMIC)) ? arb_row_frac() : 1.0); }
 static int g_persistent = ARB_DEFAULT_GEMM_PERSISTENT;   // 0: never, 1: wherever supported, 2: auto
 void set_gemm_persistent(int on) { g_persistent = on; }
 
@@ -793,8 +807,9 @@ static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const C
     const double has_x = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) ? 1.0 : 0.0;
     char pname[56];
     gemm_prof_name(pname, d, AUXBUF ? "persistx" : "persist");
-    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
-                 4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N), pname);
+    const double dM = live_m(d), dK = live_k(d);
+    ProfScope ps(ARB_PROF_GEMM, 2.0 * dM * double(d.N) * dK * nb, st,
+                 4.0 * nb * (dM * dK + double(d.N) * dK + (1.0 + has_x) * dM * d.N), pname);
     arb_launch(kern, dim3(grid), dim3(PERSIST_THREADS), smem, st, tA, tB, tC, tX, p, int(tiles.x), int(tiles.y), int(tiles.z));
   }
   arb_count_launch();
@@ -842,8 +857,9 @@ static int launch_bf16_t(const GemmDesc& d, const CUtensorMap& tA, const CUtenso
     const double osz = d.C.bf16 ? 2.0 : 4.0;
     char pname[56];
     gemm_prof_name(pname, d, "tile");
-    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
-                 nb * (2.0 * (double(d.M) * d.K + double(d.N) * d.K) + osz * (1.0 + has_x) * double(d.M) * d.N), pname);
+    const double dM = live_m(d), dK = live_k(d);
+    ProfScope ps(ARB_PROF_GEMM, 2.0 * dM * double(d.N) * dK * nb, st,
+                 nb * (2.0 * (dM * dK + double(d.N) * dK) + osz * (1.0 + has_x) * dM * d.N), pname);
     arb_launch(kern, grid, dim3(GEMM_THREADS), smem, st, tA, tB, tC, tX, p);
   }
   arb_count_launch();
@@ -905,8 +921,9 @@ static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap&
     const double has_x = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) ? 1.0 : 0.0;
     char pname[56];
     gemm_prof_name(pname, d, "tile");
-    ProfScope ps(ARB_PROF_GEMM, 2.0 * double(d.M) * double(d.N) * double(d.K) * nb, st,
-                 4.0 * nb * (double(d.M) * d.K + double(d.N) * d.K + (1.0 + has_x) * double(d.M) * d.N), pname);
+    const double dM = live_m(d), dK = live_k(d);
+    ProfScope ps(ARB_PROF_GEMM, 2.0 * dM * double(d.N) * dK * nb, st,
+                 4.0 * nb * (dM * dK + double(d.N) * dK + (1.0 + has_x) * dM * d.N), pname);
     arb_launch(kern, grid, dim3(GEMM_THREADS), smem, st, tA, tB, tC, tX, p);
   }
   arb_count_launch();
@@ -951,6 +968,8 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
   p.flags = d.flags; p.alpha = d.alpha; p.bias = d.bias; p.atomic_out = d.atomic_out; p.atomic_ld = d.atomic_ld;
   p.drop = d.drop;
   p.colsum_out = d.colsum_out;
+  p.rows_dev = d.rows_dev;
+  if (d.rows_dev && (d.nb2 != 1 || d.nb3 != 1)) { arb_set_error("gemm: a device-side row count serves unbatched launches only"); return ARB_E_INVALID_ARG; }
   if ((d.flags & EPI_COLSUM) && (!d.colsum_out || split)) { arb_set_error("gemm_tf32: EPI_COLSUM needs colsum_out and a non-split launch"); return ARB_E_INVALID_ARG; }
   if ((d.flags & EPI_DROPOUT) && d.drop.thresh == 0) p.flags &= ~EPI_DROPOUT;
   p.kb_per_split = (total_kb + splits - 1) / splits;

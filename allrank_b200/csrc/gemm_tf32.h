@@ -42,6 +42,10 @@ struct GemmDesc {
   int64_t atomic_ld = 0;
   DropSite drop{0u, 0u, 1.0f};  // EPI_DROPOUT: element index = m * N + n (unbatched problems only)
   float* colsum_out = nullptr;  // EPI_COLSUM: [N], accumulated with atomics
+  const int* rows_dev = nullptr;   // packed rows (unbatched launches): device pointer to the live row count, a
+                                   // multiple of 128.  It bounds M (tiles beyond it are not computed) or, with
+                                   // EPI_ATOMIC, K (the weight gradients reduce over the live rows only); the host-side
+                                   // M / K stay the upper bound the tensor maps and the grid are built from.
   // Element types come from the views: A and B must agree (both fp32 -> kind::tf32, both bf16 -> kind::f16, fp32
   // accumulation either way); C may be fp32 or bf16; an Aux tile has C's type (fp32 residual into an fp32 stream,
   // bf16 ReLU-mask tile into a bf16 gradient).  bf16 outputs need block_n >= 64.

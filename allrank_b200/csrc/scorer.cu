@@ -28,6 +28,10 @@ static int g_attn_mode = 2;
 // 1 (default): the fused attention kernels skip the tiles that lie entirely in a slate's padding (exact: masked keys
 // have probability 0 and padded rows a zero gradient); 0: dense tiles, for A/B measurements
 static int g_skip_padding = ARB_DEFAULT_SKIP_PADDING;
+// 1 (default): packed rows -- the encoder runs over the items below every slate's extent only (padding removal; exact
+// for every real item and every parameter gradient; scores of padded items are then 0 instead of what the network
+// computes for an all-zero feature row, which every consumer in allRank masks: DESIGN.md 4.12); 0: dense [B*S] rows
+static int g_pack_rows = ARB_DEFAULT_PACK_ROWS;
 static bool use_fused(const arb_scorer_config& c, int S) {
   return g_attn_mode >= 1 && c.n_layers > 0 && attn_fused_supported(S, c.d_model / c.n_heads);
 }
@@ -36,6 +40,14 @@ static bool use_fused_bwd(const arb_scorer_config& c, int S) {
 }
 
 static inline int n_outputs(const arb_scorer_config& c) { return c.d_output > 1 ? c.d_output : 1; }
+
+// Packed rows need both fused attention kernels (they take per-slate row offsets) and, so far, a call without dropout
+// (its counters index the dense layout), without a positional encoding and with a single output per item.
+static bool pack_eligible(const arb_scorer_config& c, int S) {
+  return c.n_layers > 0 && use_fused_bwd(c, S) && c.dropout == 0.0f && c.fc_dropout == 0.0f && c.pe_mode == 0 &&
+         n_outputs(c) == 1;
+}
+static bool use_pack(const arb_scorer_config& c, int S) { return g_pack_rows && g_skip_padding && pack_eligible(c, S); }
 
 struct ParamLayout {
   int n_fc;                                  // FC layers (>= 1)
@@ -129,6 +141,7 @@ struct WsLayout {
   struct Layer { int64_t xn1, mean1, std1, qkv, prob, smax, ssum, ctx, xmid, xn2, mean2, std2, hdn, xout; };
   Layer layer[64];
   int64_t kext;                     // [B] ints: key extent of every slate (keys at or beyond it are all masked)
+  int64_t xc, poff, plan, rowmap;   // packed rows: features of the packed rows, off [B+1], plan [2], rowmap [B*S] (ints)
   int64_t wb16;                     // bf16 mode: bfloat16 shadow of the whole parameter buffer (same element offsets)
   int64_t meanf, stdf, xf, total;   // xf: final-norm output, kept only for the multi-output head
   int Sp;
@@ -181,6 +194,8 @@ static void make_ws_layout(const arb_scorer_config& c, const ParamLayout& L, int
     }
   }
   W.kext = take(B);
+  W.xc = W.poff = W.plan = W.rowmap = 0;
+  if (pack_eligible(c, S)) { W.xc = take(R * c.n_features); W.poff = take(B + 1); W.plan = take(2); W.rowmap = take(R); }
   W.meanf = take(R);
   W.stdf = take(R);
   W.xf = (n_outputs(c) > 1 && c.n_layers > 0) ? take(R * d) : 0;
@@ -192,6 +207,7 @@ struct Ctx {
   int B, S;
   int64_t R;
   cudaStream_t st;
+  const int* rows_dev = nullptr;   // packed rows: device pointer to the live row count (plan[0]); R is the upper bound
 };
 
 // ---- GEMM helpers ------------------------------------------------------------------------------
@@ -224,6 +240,7 @@ static int linear_fwd(const Ctx& k, V X, int64_t x_pitch, int in, V Wt, const fl
   g.bias = bias; g.flags = flags | (bias ? EPI_BIAS : 0);
   g.block_n = pick_block_n(out);
   if (Y.bf16 && g.block_n < 64) g.block_n = 64;
+  g.rows_dev = k.rows_dev;
   return launch_gemm_tf32(g, k.st);
 }
 // dX[R,in] = epi( dY[R,out] W[out,in] )      (W read as an MN-major B operand)
@@ -241,6 +258,7 @@ static int linear_bwd_input(const Ctx& k, V dY, int64_t dy_pitch, int out, V Wt,
   g.flags = flags;
   g.block_n = pick_block_n(in);
   if (dX.bf16 && g.block_n < 64) g.block_n = 64;
+  g.rows_dev = k.rows_dev;
   return launch_gemm_tf32(g, k.st);
 }
 // dW[out,in] += dY[R,out]^T X[R,in]          (both operands MN-major, reduction over all rows, split-K)
@@ -257,6 +275,7 @@ static int linear_bwd_weight(const Ctx& k, V dY, int64_t dy_pitch, int out, V X,
   const int kb = int((k.R + kel - 1) / kel);
   // 4-stage ring => 1 CTA per SM: one wave of ~148 CTAs (fewer splits = fewer L2 reductions of the dW tile)
   g.split_k = std::max(1, std::min(kb / 8 + 1, std::max(1, 148 / tiles)));
+  g.rows_dev = k.rows_dev;
   return launch_gemm_tf32(g, k.st);
 }
 
@@ -309,11 +328,38 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   auto wt = [&](int64_t off) { return bf ? b16(Pb + off) : V(P + off); };
   auto act = [&](float* q) { return bf ? b16(q) : V(q); };   // a product-only activation buffer of this mode
   float* xcur = ws + W.x0;
+  int* kext = reinterpret_cast<int*>(ws + W.kext);
+  if (c.n_layers > 0 && W.fused && g_skip_padding)
+    ARB_TRY(slate_extents(mask, nullptr, 0, B, S, kext, st));   // once per call, shared by every layer
+  // Packed rows: every kernel below runs over the rows below the slates' extents only (scorer_kernels.cu: pack_plan)
+  const bool pack = use_pack(c, S);
+  const int* plan = nullptr;
+  const int* rowmap = nullptr;
+  const int* poff = nullptr;
+  if (pack) {
+    plan = reinterpret_cast<const int*>(ws + W.plan);
+    rowmap = reinterpret_cast<const int*>(ws + W.rowmap);
+    poff = reinterpret_cast<const int*>(ws + W.poff);
+    ARB_TRY(pack_plan(x, kext, B, S, F, reinterpret_cast<int*>(ws + W.poff), reinterpret_cast<int*>(ws + W.plan),
+                      reinterpret_cast<int*>(ws + W.rowmap), ws + W.xc, st));
+    // items beyond their slate's extent get the score 0
+    if (cudaMemsetAsync(scores, 0, size_t(k.R) * sizeof(float), st) != cudaSuccess) { arb_set_error("scorer: memset failed"); return ARB_E_CUDA; }
+    if (arb_prof_enabled()) {     // per-launch accounting (bench.py) needs the live row count on the host
+      int live = 0;
+      if (cudaStreamSynchronize(st) != cudaSuccess || cudaMemcpy(&live, plan, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        arb_set_error("scorer: reading the packed row count failed"); return ARB_E_CUDA;
+      }
+      arb_set_row_frac(double(live) / double(k.R));
+    }
+    k.rows_dev = plan;
+    x = ws + W.xc;
+  }
   {   // FCModel (model.py:35-44): [nn.LayerNorm(F)] then dropout(act(Linear)) per layer
     const float* hin = x;
     int in = F;
     if (c.fc_input_norm) {
-      ARB_TRY(ln_forward(x, P + L.in_a, P + L.in_b, 1e-5f, k.R, F, ws + W.xnorm, ws + W.in_mean, ws + W.in_std, st, 1));
+      ARB_TRY(ln_forward(x, P + L.in_a, P + L.in_b, 1e-5f, k.R, F, ws + W.xnorm, ws + W.in_mean, ws + W.in_std, st, 1,
+                         nullptr, plan));
       hin = ws + W.xnorm;
     }
     for (int i = 0; i < L.n_fc; ++i) {
@@ -326,7 +372,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
                            c.fc_act == ARB_ACT_RELU ? EPI_RELU : 0, nullptr, 0, site));
       } else {
         ARB_TRY(linear_fwd(k, hin, in, in, P + L.fc_w[i], P + L.fc_b[i], out, hout, out, 0, nullptr, 0));
-        ARB_TRY(act_forward(hout, k.R, out, c.fc_act, site, st));
+        ARB_TRY(act_forward(hout, k.R, out, c.fc_act, site, st, plan));
       }
       hin = hout; in = out;
     }
@@ -341,9 +387,8 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     if (!indices || !table) { arb_set_error("scorer: positional encoding needs indices and a table"); return ARB_E_INVALID_ARG; }
     ARB_TRY(pos_forward(xcur, reinterpret_cast<const long long*>(indices), mask, table, c.pe_rows, sqrtf(float(d)), k.R, d, st));
   }
-  int* kext = reinterpret_cast<int*>(ws + W.kext);
-  if (c.n_layers > 0 && W.fused && g_skip_padding)
-    ARB_TRY(slate_extents(mask, nullptr, 0, B, S, kext, st));   // once per call, shared by every layer
+  // per-head views: dense (dk, S, h, B), or packed (dk, rows, h, 1) with per-slate row offsets inside the kernels
+  auto hview = [&](V v, int64_t pitch) { return pack ? head_view(v, dk, int(k.R), h, 1, pitch) : head_view(v, dk, S, h, B, pitch); };
   for (int l = 0; l < c.n_layers; ++l) {
     const auto& pl = L.layer[l];
     const auto& wl = W.layer[l];
@@ -351,14 +396,18 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     float* xmid = ws + wl.xmid; float* xn2 = ws + wl.xn2; float* hdn = ws + wl.hdn; float* xout = ws + wl.xout;
     // ---- self-attention sublayer: x + O(attn(LN(x)))   (transformer.py:133, :105-106)
     ARB_TRY(ln_forward(xcur, P + pl.ln1_a, P + pl.ln1_b, c.ln_eps, k.R, d, xn1, ws + wl.mean1, ws + wl.std1, st, 0,
-                       bf ? xn1 : nullptr));
+                       bf ? xn1 : nullptr, plan));
     ARB_TRY(linear_fwd(k, act(xn1), d, d, wt(pl.wqkv), P + pl.bqkv, 3 * d, qkv, 3 * d, 0, nullptr, 0));
     if (W.fused) {
+      if (pack)   // the kernel's 128-row boxes overrun the last slates: 256 finite rows behind the packed rows of Q|K|V;
+                  // and the context of the alignment rows (no slate writes them) feeds the output projection: zero
+        ARB_TRY(zero_rows(qkv, 3 * d, 3 * d, 0, 256, ctx, bf ? d / 2 : d, bf ? d / 2 : d, 1, 0, plan, k.R, st));
       AttnFwdArgs a;   // QK^T, key mask, softmax, PV in one kernel; the S x S tile never leaves TMEM
-      a.q = head_view(qkv, dk, S, h, B, 3 * d);
-      a.k = head_view(qkv + d, dk, S, h, B, 3 * d);
-      a.v = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
-      a.o = head_view(act(ctx), dk, S, h, B, d);
+      a.q = hview(qkv, 3 * d);
+      a.k = hview(qkv + d, 3 * d);
+      a.v = hview(qkv + 2 * d, 3 * d);
+      a.o = hview(act(ctx), d);
+      a.pack_off = poff;
       a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum;
       a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = 1.0f / sqrtf(float(dk));
       a.drop = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
@@ -391,7 +440,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
                        make_drop_site(seed, l, SITE_ATTN_OUT, p_drop)));
     // ---- feed-forward sublayer: x + W2 relu(W1 LN(x))   (transformer.py:134, :227)
     ARB_TRY(ln_forward(xmid, P + pl.ln2_a, P + pl.ln2_b, c.ln_eps, k.R, d, xn2, ws + wl.mean2, ws + wl.std2, st, 0,
-                       bf ? xn2 : nullptr));
+                       bf ? xn2 : nullptr, plan));
     ARB_TRY(linear_fwd(k, act(xn2), d, d, wt(pl.w1), P + pl.b1, f, act(hdn), f, EPI_RELU, nullptr, 0,
                        make_drop_site(seed, l, SITE_FFN_HID, p_drop)));
     ARB_TRY(linear_fwd(k, act(hdn), f, f, wt(pl.w2), P + pl.b2, d, xout, d, EPI_ADD_AUX, xmid, d,
@@ -408,7 +457,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     return head_multi_forward(xf, P + L.head_w, P + L.head_b, c.out_act, k.R, d, n_outputs(c), scores, st);
   }
   ARB_TRY(head_forward(xcur, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr, c.ln_eps, P + L.head_w,
-                       P + L.head_b, has_norm, c.out_act, k.R, d, scores, ws + W.meanf, ws + W.stdf, st));
+                       P + L.head_b, has_norm, c.out_act, k.R, d, scores, ws + W.meanf, ws + W.stdf, st, plan, rowmap));
   return ARB_OK;
 }
 
@@ -491,7 +540,15 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   // every layer, which lets the fused attention backward skip their tiles
   int* gext = reinterpret_cast<int*>(scratch + Z.ext);
   const bool skip = g_skip_padding && c.n_layers > 0 && use_fused_bwd(c, S);
-  if (skip) ARB_TRY(slate_extents(mask, dscores, n_outputs(c), B, S, gext, st));
+  // Packed rows: the forward call left the plan in the workspace (row count, row map, slate offsets, packed features,
+  // key extents); the items it dropped have the constant score 0, so their score gradient is not read.
+  const bool pack = use_pack(c, S);
+  const int* plan = pack ? reinterpret_cast<const int*>(ws + W.plan) : nullptr;
+  const int* rowmap = pack ? reinterpret_cast<const int*>(ws + W.rowmap) : nullptr;
+  const int* poff = pack ? reinterpret_cast<const int*>(ws + W.poff) : nullptr;
+  if (pack) { k.rows_dev = plan; x = ws + W.xc; gext = reinterpret_cast<int*>(ws + W.kext); }
+  else if (skip) ARB_TRY(slate_extents(mask, dscores, n_outputs(c), B, S, gext, st));
+  auto hview = [&](V v, int64_t pitch) { return pack ? head_view(v, dk, int(k.R), h, 1, pitch) : head_view(v, dk, S, h, B, pitch); };
   const int has_norm = c.n_layers > 0;
   const float* xlast = c.n_layers > 0 ? ws + W.layer[c.n_layers - 1].xout : ws + W.x0;
   float* top_bias_grad = c.n_layers > 0 ? G + L.layer[c.n_layers - 1].b2 : fc_bias_grad;
@@ -509,7 +566,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(head_backward(dscores, scores, xlast, has_norm ? P + L.lnf_a : nullptr, has_norm ? P + L.lnf_b : nullptr,
                           ws + W.meanf, ws + W.stdf, c.ln_eps, P + L.head_w, P + L.head_b, has_norm, c.out_act, k.R, d,
                           dx, has_norm ? G + L.lnf_a : nullptr, has_norm ? G + L.lnf_b : nullptr, G + L.head_w,
-                          G + L.head_b, st, dxm, top_site, top_bias_grad, dy16));
+                          G + L.head_b, st, dxm, top_site, top_bias_grad, dy16, plan, rowmap));
   }
   const float* dy = top_site.thresh ? dxm : dx;   // gradient w.r.t. the output of the linear below the dropout
   for (int l = c.n_layers - 1; l >= 0; --l) {
@@ -530,7 +587,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(linear_bwd_input(k, act(hdn), f, f, wt(pl.w1), d, act(dxn), d, 0, nullptr, 0));
     const DropSite site_ao = make_drop_site(seed, l, SITE_ATTN_OUT, p_drop);
     ARB_TRY(ln_backward(dxn, xmid, P + pl.ln2_a, ws + wl.mean2, ws + wl.std2, c.ln_eps, dx, k.R, d, dx_alt,
-                        G + pl.ln2_a, G + pl.ln2_b, st, dxm, site_ao, G + pl.bo, 0, bf ? dxn : nullptr, dy16));
+                        G + pl.ln2_a, G + pl.ln2_b, st, dxm, site_ao, G + pl.bo, 0, bf ? dxn : nullptr, dy16, plan));
     // dx_alt = d loss / d xmid ; dy = the same through the dropout on the attention sublayer output
     dy = site_ao.thresh ? dxm : dx_alt;
     // ---- attention sublayer backward:  xmid = xin + Wo ctx + bo
@@ -538,27 +595,31 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(linear_bwd_weight(k, dyo, d, d, act(ctx), d, d, G + pl.wo));   // (bo gradient: fused into the LayerNorm backward above)
     ARB_TRY(linear_bwd_input(k, dyo, d, d, wt(pl.wo), d, dctx, d, 0, nullptr, 0));
     if (use_fused_bwd(c, S)) {
+      if (pack)   // 256 finite rows of d ctx behind the packed rows (the kernel's boxes overrun the last slates), and
+                  // zero dQ | dK | dV in the alignment rows no slate writes (the QKV weight gradient sums over them)
+        ARB_TRY(zero_rows(dctx, d, d, 0, 256, dqkv, bf ? 3 * d / 2 : 3 * d, bf ? 3 * d / 2 : 3 * d, 1, 0, plan, k.R, st));
       AttnBwdArgs a;   // dQ, dK, dV from d ctx in one kernel; P is recomputed in TMEM from the saved row statistics
-      a.q = head_view(qkv, dk, S, h, B, 3 * d);
-      a.k = head_view(qkv + d, dk, S, h, B, 3 * d);
-      a.v = head_view(qkv + 2 * d, dk, S, h, B, 3 * d);
-      a.d_o = head_view(dctx, dk, S, h, B, d);
+      a.q = hview(qkv, 3 * d);
+      a.k = hview(qkv + d, 3 * d);
+      a.v = hview(qkv + 2 * d, 3 * d);
+      a.d_o = hview(dctx, d);
       if (bf) {   // dQ | dK | dV as one packed bfloat16 [R, 3d] buffer
         uint16_t* g16 = reinterpret_cast<uint16_t*>(dqkv);
-        a.dq = head_view(b16(g16), dk, S, h, B, 3 * d);
-        a.dk_ = head_view(b16(g16 + d), dk, S, h, B, 3 * d);
-        a.dv = head_view(b16(g16 + 2 * d), dk, S, h, B, 3 * d);
+        a.dq = hview(b16(g16), 3 * d);
+        a.dk_ = hview(b16(g16 + d), 3 * d);
+        a.dv = hview(b16(g16 + 2 * d), 3 * d);
       } else {
-        a.dq = head_view(dqkv, dk, S, h, B, 3 * d);
-        a.dk_ = head_view(dqkv + d, dk, S, h, B, 3 * d);
-        a.dv = head_view(dqkv + 2 * d, dk, S, h, B, 3 * d);
+        a.dq = hview(dqkv, 3 * d);
+        a.dk_ = hview(dqkv + d, 3 * d);
+        a.dv = hview(dqkv + 2 * d, 3 * d);
       }
+      a.pack_off = poff; a.rows_dev = plan; a.rowmap = rowmap;
       a.o_ptr = ctx; a.o_bf16 = bf ? 1 : 0; a.do_ptr = dctx; a.o_pitch = d;
       a.mask = mask; a.stat_max = ws + wl.smax; a.stat_sum = ws + wl.ssum; a.delta = scratch + Z.delta;
       a.B = B; a.h = h; a.S = S; a.dk = dk; a.scale = alpha;
       a.drop = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
       a.dbias_qkv = G + pl.bqkv; a.d_model = d;          // bias gradient of the QKV projection, fused
-      a.extent = skip ? gext : nullptr;
+      a.extent = (skip || pack) ? gext : nullptr;
       ARB_TRY(launch_attn_bwd(a, st));
     } else {
       const DropSite site_p = make_drop_site(seed, l, SITE_ATTN_P, p_drop);
@@ -622,7 +683,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     if (l == 0 && c.pe_mode != 0 && !fc_act) site_below.scale *= sqrtf(float(d));
     ARB_TRY(ln_backward(dxn, xin, P + pl.ln1_a, ws + wl.mean1, ws + wl.std1, c.ln_eps, dx_alt, k.R, d, dx,
                         G + pl.ln1_a, G + pl.ln1_b, st, dxm, site_below, l > 0 ? G + L.layer[l - 1].b2 : fc_bias_grad,
-                        0, bf ? dxn : nullptr, l > 0 ? dy16 : nullptr));   // (the FC block below layer 0 stays TF32)
+                        0, bf ? dxn : nullptr, l > 0 ? dy16 : nullptr, plan));   // (the FC block below layer 0 stays TF32)
     // dx = d loss / d xin ; dy = the same through the dropout that produced xin's last summand
     dy = (site_below.thresh || site_below.scale != 1.0f) ? dxm : dx;
   }
@@ -637,7 +698,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   if (fc_act) {
     const float* h_last = W.fc_last ? ws + W.fc_last : ws + W.x0;
     ARB_TRY(act_backward(dx, h_last, dfa, k.R, d, c.fc_act, fc_site, c.pe_mode != 0 ? sqrtf(float(d)) : 1.0f,
-                         G + L.fc_b[L.n_fc - 1], st));
+                         G + L.fc_b[L.n_fc - 1], st, plan));
     dz = dfa; std::swap(dfa, dfb);
   }
   for (int i = L.n_fc - 1; i >= 0; --i) {
@@ -654,13 +715,13 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
         ARB_TRY(linear_bwd_input(k, dz, out, out, P + L.fc_w[i], in, dfa, in, EPI_COLSUM, nullptr, 0, 1.0f, G + L.fc_b[i - 1]));
       } else {
         ARB_TRY(linear_bwd_input(k, dz, out, out, P + L.fc_w[i], in, dfa, in, 0, nullptr, 0));
-        ARB_TRY(act_backward(dfa, hin, dfa, k.R, in, c.fc_act, site, 1.0f, G + L.fc_b[i - 1], st));
+        ARB_TRY(act_backward(dfa, hin, dfa, k.R, in, c.fc_act, site, 1.0f, G + L.fc_b[i - 1], st, plan));
       }
       dz = dfa; std::swap(dfa, dfb);
     } else if (c.fc_input_norm) {            // x is data: only the LayerNorm's weight / bias gradients are needed
       ARB_TRY(linear_bwd_input(k, dz, out, out, P + L.fc_w[0], in, dfa, in, 0, nullptr, 0));
       ARB_TRY(ln_backward(dfa, x, P + L.in_a, ws + W.in_mean, ws + W.in_std, 0.0f, nullptr, k.R, F, dfb,
-                          G + L.in_a, G + L.in_b, st, nullptr, none_site, nullptr, 1));
+                          G + L.in_a, G + L.in_b, st, nullptr, none_site, nullptr, 1, nullptr, nullptr, plan));
     }
   }
   return ARB_OK;
@@ -672,6 +733,7 @@ using namespace arb;
 
 extern "C" void arb_set_attention_mode(int32_t mode) { g_attn_mode = mode; }
 extern "C" void arb_set_attention_skip_padding(int32_t on) { g_skip_padding = on; }
+extern "C" void arb_set_pack_rows(int32_t on) { g_pack_rows = on; }
 extern "C" void arb_set_attention_fwd_two_pass(int32_t on) { set_attn_fwd_two_pass(on); }
 
 extern "C" int64_t arb_scorer_param_count(const arb_scorer_config* cfg) {

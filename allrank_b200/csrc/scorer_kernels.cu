@@ -96,8 +96,10 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
                                                                     long long rows, int width,
                                                                     float* __restrict__ y, float* __restrict__ mean_o,
                                                                     float* __restrict__ std_o, int torch_mode,
-                                                                    uint16_t* __restrict__ y16) {
+                                                                    uint16_t* __restrict__ y16,
+                                                                    const int* __restrict__ rows_dev) {
   arb_pdl_wait();
+  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);   // packed rows: the live row count lives on the device
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * FWD_RPW;
   if (row0 >= rows) return;
@@ -175,8 +177,13 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32, NV == 1 ? 4 : 1) ln_bwd_k
                                                                     float* __restrict__ dx_masked, DropSite site,
                                                                     float* __restrict__ colsum_out, int torch_mode,
                                                                     const uint16_t* __restrict__ dy16_in,
-                                                                    uint16_t* __restrict__ dy16_out) {
+                                                                    uint16_t* __restrict__ dy16_out,
+                                                                    const int* __restrict__ rows_dev) {
   arb_pdl_wait();
+  if (rows_dev) {
+    rows = min(rows, (long long)rows_dev[0]);
+    if ((long long)blockIdx.x * ROWS_PER_BLOCK * rows_per_warp >= rows) return;   // whole block beyond the packed rows
+  }
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   RowRegs<NV> ga, acc_a, acc_b, acc_c;
@@ -474,8 +481,11 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
                                                                       int act, long long rows, int width,
                                                                       float* __restrict__ score,
                                                                       float* __restrict__ mean_o,
-                                                                      float* __restrict__ std_o) {
+                                                                      float* __restrict__ std_o,
+                                                                      const int* __restrict__ rows_dev,
+                                                                      const int* __restrict__ rowmap) {
   arb_pdl_wait();
+  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);
   const int lane = threadIdx.x & 31;
   // FWD_RPW rows per warp, all loads issued up front (see ln_fwd_kernel)
   const long long row0 = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * FWD_RPW;
@@ -552,7 +562,9 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
 #pragma unroll
     for (int q = 0; q < FWD_RPW; ++q) {
       if (row0 + q >= rows) break;
-      score[row0 + q] = act_fwd(dot[q] + bias, act);
+      // packed rows: the score goes to the item's place in the [B, S] tensor (alignment rows have none)
+      const long long at = rowmap ? (long long)rowmap[row0 + q] : row0 + q;
+      if (at >= 0) score[at] = act_fwd(dot[q] + bias, act);
       if (has_norm && mean_o) { mean_o[row0 + q] = mean[q]; std_o[row0 + q] = sd[q]; }
     }
   }
@@ -566,8 +578,13 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
     const float* __restrict__ std_i, float eps, const float* __restrict__ w, const float* __restrict__ wb,
     int has_norm, int act, long long rows, int width, int rows_per_warp, float* __restrict__ dx,
     float* __restrict__ grad_a, float* __restrict__ grad_b, float* __restrict__ grad_w, float* __restrict__ grad_wb,
-    float* __restrict__ dx_masked, DropSite site, float* __restrict__ colsum_out, uint16_t* __restrict__ dy16_out) {
+    float* __restrict__ dx_masked, DropSite site, float* __restrict__ colsum_out, uint16_t* __restrict__ dy16_out,
+    const int* __restrict__ rows_dev, const int* __restrict__ rowmap) {
   arb_pdl_wait();
+  if (rows_dev) {
+    rows = min(rows, (long long)rows_dev[0]);
+    if ((long long)blockIdx.x * ROWS_PER_BLOCK * rows_per_warp >= rows) return;
+  }
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
   __shared__ float shb[ROWS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -583,10 +600,12 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
     if (row >= rows) break;
     RowRegs<NV> xr, g;
     load_row<NV>(x + row * width, width, lane, xr);
-    const float out = score[row];
+    // packed rows: score and its gradient sit at the item's place in the [B, S] tensors; alignment rows have neither
+    const long long at = rowmap ? (long long)rowmap[row] : row;
+    const float out = at >= 0 ? score[at] : 0.f;
     float z = 0.f;
     if (act == ARB_ACT_RELU) z = out;   // relu: out > 0 <=> z > 0
-    const float dz = dscore[row] * act_bwd(out, z, act);
+    const float dz = at >= 0 ? dscore[at] * act_bwd(out, z, act) : 0.f;
     if (lane == 0) acc_wb += dz;
     if (!has_norm) {
 #pragma unroll
@@ -830,7 +849,9 @@ __global__ void __launch_bounds__(256) pos_bwd_kernel(const float* __restrict__ 
 // FCModel applies dropout(activation(linear(x))) per layer (model.py:41-43).  ReLU / identity run inside the GEMM
 // epilogue; the kernels below serve the other activations and the backward of every activation under dropout.
 // Element index of the dropout counter = row * width + column (the same as the GEMM epilogue's).
-__global__ void __launch_bounds__(256) act_fwd_kernel(float* __restrict__ h, long long n4, int act, DropSite site) {
+__global__ void __launch_bounds__(256) act_fwd_kernel(float* __restrict__ h, long long n4, int act, DropSite site,
+                                                      const int* __restrict__ rows_dev, int width4) {
+  if (rows_dev) n4 = min(n4, (long long)rows_dev[0] * width4);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<float4*>(h)[i];
     float* e = &v.x;
@@ -847,8 +868,10 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(float* __restrict__ h, lon
 // of dz (the bias gradient of the linear that produced z).  dz may alias dh.
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* dh, const float* __restrict__ h, float* dz,
                                                       long long rows, int width, int act, DropSite site, float mul,
-                                                      int tx_n, int rows_per_block, float* __restrict__ colsum_out) {
+                                                      int tx_n, int rows_per_block, float* __restrict__ colsum_out,
+                                                      const int* __restrict__ rows_dev) {
   extern __shared__ float sh_cols[];
+  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);
   for (int c = threadIdx.x; c < width; c += blockDim.x) sh_cols[c] = 0.f;
   __syncthreads();
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n, ty_n = blockDim.x / tx_n;
@@ -903,27 +926,131 @@ static int check_launch() {
   return ARB_OK;
 }
 
+
+// Accounting only (ProfScope): launches over packed rows process arb_row_frac() of the nominal rows.
+static double live_rows(long long rows, const int* rows_dev) { return double(rows) * (rows_dev ? arb_row_frac() : 1.0); }
+
+// ------------------------------------------------------------------------------------------------ packed rows
+// Padding removal.  A slate of extent e (slate_extents: every item at or beyond e is padding) contributes its first
+// e16 = round_up(e, 16) rows to the packed [rows, width] activation layout, slate after slate; the total is rounded up
+// to a multiple of 128 (the GEMM tile height) with rows that belong to no item.  Every row-wise kernel and GEMM of the
+// encoder then runs over plan[0] rows instead of B * S -- the count lives on the device, so nothing synchronises.
+//   off[b]    first packed row of slate b (off[B] = plan[1])
+//   plan[0]   packed rows, multiple of 128;  plan[1] = rows that belong to slates
+//   rowmap[r] item index b * S + s of packed row r, or -1 (alignment row: zero features, no score)
+__global__ void __launch_bounds__(1024) pack_scan_kernel(const int* __restrict__ ext, int B, int* __restrict__ off,
+                                                         int* __restrict__ plan) {
+  arb_pdl_wait();
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  const int per = (B + 1023) / 1024;
+  const int b0 = min(B, t * per), b1 = min(B, b0 + per);
+  int s = 0;
+  for (int b = b0; b < b1; ++b) s += (ext[b] + 15) & ~15;
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {      // inclusive scan of the 1024 partial sums
+    const int v = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = part[t] - s;                    // exclusive prefix of this thread's chunk
+  for (int b = b0; b < b1; ++b) { off[b] = run; run += (ext[b] + 15) & ~15; }
+  if (t == 1023) {
+    const int total = part[1023];
+    off[B] = total;
+    plan[0] = (total + 127) & ~127;
+    plan[1] = total;
+  }
+}
+
+// one block per slate (+ one for the tail alignment rows): row map and the packed copy of the features
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ x, const int* __restrict__ ext,
+                                                        const int* __restrict__ off, const int* __restrict__ plan,
+                                                        int B, int S, int F, float* __restrict__ xc,
+                                                        int* __restrict__ rowmap) {
+  arb_pdl_wait();
+  const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int r0, n, src0;
+  if (b < B) { r0 = off[b]; n = (ext[b] + 15) & ~15; src0 = b * S; }
+  else { r0 = plan[1]; n = plan[0] - plan[1]; src0 = -1; }
+  for (int s = wid; s < n; s += 8) {
+    const bool real = src0 >= 0 && s < S;
+    float* dst = xc + (long long)(r0 + s) * F;
+    const float* src = x + (long long)(src0 + s) * F;
+    for (int c = lane * 4; c < F; c += 128)
+      *reinterpret_cast<float4*>(dst + c) = real ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane == 0) rowmap[r0 + s] = real ? src0 + s : -1;
+  }
+}
+
+// Rows the fused attention kernels may read beyond the packed rows (their 128-row boxes overrun the last slates) must
+// be finite, and the alignment rows nobody writes must be zero before a product reads them: zero
+//   rows [plan[from_a], end_a) of a  and  rows [plan[from_b], end_b) of b,   end = from == 0 ? +n rows (capped at
+//   cap_rows) : plan[0]         (from: 0 = after the packed rows, 1 = after the slates' rows)
+__global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ a, int a_pitch, int a_width, int a_from, int a_n,
+                                                        float* __restrict__ b, int b_pitch, int b_width, int b_from, int b_n,
+                                                        const int* __restrict__ plan, long long cap_rows) {
+  arb_pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  for (int which = 0; which < 2; ++which) {
+    float* p = which ? b : a;
+    if (!p) continue;
+    const int pitch = which ? b_pitch : a_pitch, width = which ? b_width : a_width, from = which ? b_from : a_from;
+    const long long start = plan[from];
+    const long long end = from == 0 ? min(cap_rows, start + (which ? b_n : a_n)) : (long long)plan[0];
+    const long long row = start + r;
+    if (row >= end) continue;
+    for (int c = lane * 4; c < width; c += 128) *reinterpret_cast<float4*>(p + row * pitch + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+int pack_plan(const float* x, const int* ext, int B, int S, int F, int* off, int* plan, int* rowmap, float* xc, cudaStream_t st) {
+  if (F % 4) { arb_set_error("packed rows: the feature count must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
+  {
+    ProfScope ps(ARB_PROF_SCORER_SIMT, 8.0 * B, st, 0.0, "pack_scan");
+    arb_launch(pack_scan_kernel, dim3(1), dim3(1024), 0, st, ext, B, off, plan);
+    arb_count_launch();
+  }
+  ProfScope ps(ARB_PROF_SCORER_SIMT, double(B) * S * arb_row_frac() * (8.0 * F + 4.0), st, 0.0, "pack_rows");
+  arb_launch(pack_rows_kernel, dim3(unsigned(B + 1)), dim3(256), 0, st, x, ext, static_cast<const int*>(off),
+             static_cast<const int*>(plan), B, S, F, xc, rowmap);
+  return check_launch();
+}
+
+int zero_rows(float* a, int a_pitch, int a_width, int a_from, int a_n, float* b, int b_pitch, int b_width, int b_from,
+              int b_n, const int* plan, long long cap_rows, cudaStream_t st) {
+  if (a_width % 4 || b_width % 4 || a_pitch % 4 || b_pitch % 4) { arb_set_error("zero_rows: widths must be multiples of 4 floats"); return ARB_E_UNSUPPORTED; }
+  const int n = std::max(128, std::max(a_from == 0 ? a_n : 0, b_from == 0 ? b_n : 0));
+  ProfScope ps(ARB_PROF_SCORER_SIMT, 4.0 * n * (a_width + b_width), st, 0.0, "zero_rows");
+  arb_launch(zero_rows_kernel, dim3(unsigned((n + 7) / 8)), dim3(256), 0, st, a, a_pitch, a_width, a_from, a_n, b, b_pitch,
+             b_width, b_from, b_n, plan, cap_rows);
+  return check_launch();
+}
+
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
-               float* mean, float* sd, cudaStream_t st, int torch_mode, void* y16) {
+               float* mean, float* sd, cudaStream_t st, int torch_mode, void* y16, const int* rows_dev) {
   if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * FWD_RPW - 1) / (ROWS_PER_BLOCK * FWD_RPW));
-  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((y16 ? 6.0 : 8.0) * width + 8), st);
-  ARB_DISPATCH_NV(width, (arb_launch(ln_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16))));
+  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * ((y16 ? 6.0 : 8.0) * width + 8), st);
+  ARB_DISPATCH_NV(width, (arb_launch(ln_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16), rows_dev)));
   return check_launch();
 }
 
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
                 cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out, int torch_mode,
-                const void* dy16_in, void* dy16_out) {
+                const void* dy16_in, void* dy16_out, const int* rows_dev) {
   if (site.thresh == 0 && site.scale == 1.0f) dx_masked = nullptr;
   if (dy16_out && dx_masked == nullptr && (site.thresh != 0 || site.scale != 1.0f)) {
     arb_set_error("ln_backward: a masked bf16 copy needs the masked fp32 buffer too"); return ARB_E_INVALID_ARG;
   }   // thresh 0 with a scale = pure rescale (positional encoding)
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
-  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * ((dres ? 16.0 : 12.0) * width + 8), st);
-  ARB_DISPATCH_NV(width, (arb_launch(ln_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode, static_cast<const uint16_t*>(dy16_in), static_cast<uint16_t*>(dy16_out))));
+  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * ((dres ? 16.0 : 12.0) * width + 8), st);
+  ARB_DISPATCH_NV(width, (arb_launch(ln_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode, static_cast<const uint16_t*>(dy16_in), static_cast<uint16_t*>(dy16_out), rows_dev)));
   return check_launch();
 }
 
@@ -942,24 +1069,24 @@ int pos_backward(const float* dx, const long long* indices, const uint8_t* mask,
   return check_launch();
 }
 
-int act_forward(float* h, long long rows, int width, int act, DropSite site, cudaStream_t st) {
+int act_forward(float* h, long long rows, int width, int act, DropSite site, cudaStream_t st, const int* rows_dev) {
   if (width % 4) { arb_set_error("activation: width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   const long long n4 = rows * width / 4;
-  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 8.0 * width, st);
+  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * 8.0 * width, st);
   const unsigned blocks = unsigned(std::min<long long>((n4 + 255) / 256, 148 * 16));
-  act_fwd_kernel<<<blocks, 256, 0, st>>>(h, n4, act, site);
+  act_fwd_kernel<<<blocks, 256, 0, st>>>(h, n4, act, site, rows_dev, width / 4);
   return check_launch();
 }
 
 int act_backward(const float* dh, const float* h, float* dz, long long rows, int width, int act, DropSite site, float mul,
-                 float* colsum_out, cudaStream_t st) {
+                 float* colsum_out, cudaStream_t st, const int* rows_dev) {
   if (width % 4 || width > 8192) { arb_set_error("activation: width must be a multiple of 4 and <= 8192"); return ARB_E_UNSUPPORTED; }
   int tx_n = 1;
   while (tx_n < width / 4 && tx_n < 256) tx_n *= 2;
   const int rpb = 64 * (256 / tx_n);
-  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * 12.0 * width, st);
+  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * 12.0 * width, st);
   act_bwd_kernel<<<unsigned((rows + rpb - 1) / rpb), 256, size_t(width) * 4, st>>>(dh, h, dz, rows, width, act, site, mul,
-                                                                                  tx_n, rpb, colsum_out);
+                                                                                  tx_n, rpb, colsum_out, rows_dev);
   return check_launch();
 }
 
@@ -1005,23 +1132,24 @@ int colsum_accumulate(const float* in, long long rows, int width, long long ld, 
 
 int head_forward(const float* x, const float* a, const float* b, float eps, const float* w, const float* wb,
                  int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,
-                 cudaStream_t st) {
+                 cudaStream_t st, const int* rows_dev, const int* rowmap) {
   if (width % 4) { arb_set_error("model width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * FWD_RPW - 1) / (ROWS_PER_BLOCK * FWD_RPW));
-  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (4.0 * width + 12), st);
-  ARB_DISPATCH_NV(width, (arb_launch(head_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd)));
+  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * (4.0 * width + 12), st);
+  ARB_DISPATCH_NV(width, (arb_launch(head_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd, rows_dev, rowmap)));
   return check_launch();
 }
 
 int head_backward(const float* dscore, const float* score, const float* x, const float* a, const float* b,
                   const float* mean, const float* sd, float eps, const float* w, const float* wb, int has_norm,
                   int act, long long rows, int width, float* dx, float* grad_a, float* grad_b, float* grad_w,
-                  float* grad_wb, cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out, void* dy16_out) {
+                  float* grad_wb, cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out, void* dy16_out,
+                  const int* rows_dev, const int* rowmap) {
   if (site.thresh == 0) dx_masked = nullptr;
   const int rpw = 8;
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
-  ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 16), st);
-  ARB_DISPATCH_NV(width, (arb_launch(head_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out, static_cast<uint16_t*>(dy16_out))));
+  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * (8.0 * width + 16), st);
+  ARB_DISPATCH_NV(width, (arb_launch(head_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out, static_cast<uint16_t*>(dy16_out), rows_dev, rowmap)));
   return check_launch();
 }
 

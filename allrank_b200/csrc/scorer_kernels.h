@@ -12,7 +12,8 @@ namespace arb {
 // receives sqrt(var + eps) and ln_backward must be called with eps = 0 and torch_mode = 1
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
                float* mean, float* sd, cudaStream_t st, int torch_mode = 0,
-               void* y16 = nullptr);   // y16 != nullptr: write the output as bfloat16 there INSTEAD of y (bf16 mode)
+               void* y16 = nullptr,    // y16 != nullptr: write the output as bfloat16 there INSTEAD of y (bf16 mode)
+               const int* rows_dev = nullptr);   // packed rows: device pointer to the live row count (<= rows)
 // dx = (dres ? dres : 0) + LayerNormBackward(dy); grad_a / grad_b are accumulated (atomicAdd)
 int ln_backward(const float* dy, const float* x, const float* a, const float* mean, const float* sd, float eps,
                 const float* dres, long long rows, int width, float* dx, float* grad_a, float* grad_b,
@@ -20,7 +21,8 @@ int ln_backward(const float* dy, const float* x, const float* a, const float* me
                 float* colsum_out = nullptr,    // colsum_out[c] += column sums of the emitted (masked) gradient
                 int torch_mode = 0,
                 const void* dy16_in = nullptr,  // bf16 mode: dy is read from this bfloat16 buffer instead
-                void* dy16_out = nullptr);      // bf16 mode: bfloat16 copy of the emitted (masked) gradient
+                void* dy16_out = nullptr,       // bf16 mode: bfloat16 copy of the emitted (masked) gradient
+                const int* rows_dev = nullptr);
 int pos_forward(float* x, const long long* indices, const uint8_t* mask, const float* pe, int pe_rows, float scale,
                 long long rows, int width, cudaStream_t st);
 int pos_backward(const float* dx, const long long* indices, const uint8_t* mask, float* dpe, int pe_rows, long long rows,
@@ -29,9 +31,10 @@ int pos_backward(const float* dx, const long long* indices, const uint8_t* mask,
 // the backward then expects `prob` = the UNDROPPED probabilities and overwrites it with the dropped ones
 // FC-block activations (model.py:41-43): h <- dropout(act(h)) in place; backward: dz = mul * dh * mask/(1-p) * act'
 // from the stored output h, colsum_out[c] += column sums of dz.  act: ARB_ACT_*
-int act_forward(float* h, long long rows, int width, int act, DropSite site, cudaStream_t st);
+int act_forward(float* h, long long rows, int width, int act, DropSite site, cudaStream_t st,
+                const int* rows_dev = nullptr);
 int act_backward(const float* dh, const float* h, float* dz, long long rows, int width, int act, DropSite site, float mul,
-                 float* colsum_out, cudaStream_t st);
+                 float* colsum_out, cudaStream_t st, const int* rows_dev = nullptr);
 int softmax_forward(float* sc, const uint8_t* mask, int B, int h, int S, int pitch, cudaStream_t st,
                     DropSite site = DropSite{0u, 0u, 1.0f});
 int softmax_backward(float* dp, float* prob, long long rows, int S, int pitch, cudaStream_t st,
@@ -45,12 +48,22 @@ int convert_to_bf16(const float* src, void* dst, long long n, cudaStream_t st);
 int colsum_accumulate(const float* in, long long rows, int width, long long ld, float* out, cudaStream_t st);
 int head_forward(const float* x, const float* a, const float* b, float eps, const float* w, const float* wb,
                  int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,
-                 cudaStream_t st);
+                 cudaStream_t st, const int* rows_dev = nullptr,
+                 const int* rowmap = nullptr);   // packed rows: score[rowmap[row]] (rows with rowmap < 0 have no score)
 int head_backward(const float* dscore, const float* score, const float* x, const float* a, const float* b,
                   const float* mean, const float* sd, float eps, const float* w, const float* wb, int has_norm,
                   int act, long long rows, int width, float* dx, float* grad_a, float* grad_b, float* grad_w,
                   float* grad_wb, cudaStream_t st, float* dx_masked = nullptr,
-                  DropSite site = DropSite{0u, 0u, 1.0f}, float* colsum_out = nullptr, void* dy16_out = nullptr);
+                  DropSite site = DropSite{0u, 0u, 1.0f}, float* colsum_out = nullptr, void* dy16_out = nullptr,
+                  const int* rows_dev = nullptr, const int* rowmap = nullptr);
+// Packed rows (padding removal; see scorer_kernels.cu): from the slate extents build off [B+1], plan [2] and
+// rowmap [B*S] and copy the features of the packed rows into xc
+int pack_plan(const float* x, const int* ext, int B, int S, int F, int* off, int* plan, int* rowmap, float* xc,
+              cudaStream_t st);
+// zero rows [plan[from], ...) of up to two buffers (pitch / width in floats): from = 0: n rows after the packed rows,
+// capped at cap_rows; from = 1: the alignment rows between the slates' rows and the packed row count
+int zero_rows(float* a, int a_pitch, int a_width, int a_from, int a_n, float* b, int b_pitch, int b_width, int b_from,
+              int b_n, const int* plan, long long cap_rows, cudaStream_t st);
 // d_output = n > 1: scores [rows, n] from the (already normalised) rows xf; see scorer_kernels.cu
 int head_multi_forward(const float* xf, const float* w, const float* wb, int act, long long rows, int width, int n,
                        float* score, cudaStream_t st);

@@ -227,6 +227,17 @@ void arb_set_attention_mode(int32_t mode);
  * gradient have exactly zero activation gradients, so results are unchanged; 0: dense tiles.  For A/B measurements. */
 void arb_set_attention_skip_padding(int32_t on);
 
+/* Packed rows (padding removal).  1: the encoder -- every LayerNorm, linear, attention and head kernel and every
+ * gradient product -- runs over the items below each slate's extent only (extent = last unmasked item + 1, rounded up to
+ * 16 rows; the live row count stays on the device, nothing synchronises).  Exact for every real item's score and every
+ * parameter gradient; the scores of the items beyond a slate's extent are then 0 (and carry no gradient) instead of
+ * what the network computes for a padded feature row -- values every consumer in allRank masks (losses.py: the
+ * padded_value_indicator masks, metrics.py:24, inference_utils.py:55).  Applies to calls with a transformer whose
+ * attention runs in the fused kernels (slate_length <= 256, head width 16 / 32), no dropout, no positional encoding
+ * and d_output = 1; other calls use the dense layout.  0: dense [B*S] rows everywhere, i.e. padded items scored like
+ * the reference does.  Process-wide. */
+void arb_set_pack_rows(int32_t on);
+
 /* 1 (default): the kernels of a step are chained with programmatic dependent launch -- a kernel's prologue (barrier
  * init, TMEM allocation, tensor-map prefetch) overlaps its predecessor's last wave, and it blocks in griddepcontrol.wait
  * before its first global-memory access; 0: every launch fully serialised.  For A/B measurements. */

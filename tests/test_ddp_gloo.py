@@ -11,6 +11,29 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
+
+def _by_value(obj):
+    """Tensors cross the result queue as numpy arrays: a torch tensor is passed by file descriptor, which the parent
+    can no longer fetch once the worker has exited (a race the tests lost on a loaded machine)."""
+    if isinstance(obj, torch.Tensor):
+        return ("__tensor__", obj.detach().cpu().numpy())
+    if isinstance(obj, dict):
+        return {k: _by_value(v) for k, v in obj.items()}
+    if isinstance(obj, (tuple, list)):
+        return type(obj)(_by_value(v) for v in obj)
+    return obj
+
+
+def _from_value(obj):
+    if isinstance(obj, tuple) and len(obj) == 2 and isinstance(obj[0], str) and obj[0] == "__tensor__":
+        return torch.from_numpy(obj[1].copy())
+    if isinstance(obj, dict):
+        return {k: _from_value(v) for k, v in obj.items()}
+    if isinstance(obj, (tuple, list)):
+        return type(obj)(_from_value(v) for v in obj)
+    return obj
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -65,9 +88,9 @@ def _worker(rank, world, port, out_q):
         for reduction in ("mean", "sum"):
             ref.loss_and_grad(x_all, y_all, reduction)
             single[reduction] = ref.flat_gradients.clone()
-        out_q.put((results, single, ref.flat_parameters.clone()))
+        out_q.put(_by_value((results, single, ref.flat_parameters.clone())))
     else:
-        out_q.put(({k: v[0] if not isinstance(v[0], float) else None for k, v in results.items()}, None, None))
+        out_q.put(_by_value(({k: v[0] if not isinstance(v[0], float) else None for k, v in results.items()}, None, None)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,7 +103,7 @@ def test_flat_bucket_allreduce_matches_single_process():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in range(world)]
+    got = [_from_value(q.get(timeout=120)) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -110,7 +133,7 @@ def _metric_worker(rank, world, port, out_q):
     rows = torch.rand(10, 3, generator=g).double()          # per-slate metric rows of the WHOLE loader
     mine = rows[:7] if rank == 0 else rows[7:]                # uneven shards: 7 + 3 slates
     totals, count = reduce_epoch_sums({"ndcg": mine.sum(0), "mrr": 2 * mine.sum(0)}, mine.shape[0])
-    out_q.put((rank, totals["ndcg"] / count, totals["mrr"] / count, count, rows.mean(0)))
+    out_q.put(_by_value((rank, totals["ndcg"] / count, totals["mrr"] / count, count, rows.mean(0))))
     dist.destroy_process_group()
 
 
@@ -123,7 +146,7 @@ def test_epoch_metric_sums_reduce_to_the_whole_loader_mean():
     procs = [ctx.Process(target=_metric_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in procs]
+    got = [_from_value(q.get(timeout=120)) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -169,7 +192,7 @@ def _weighted_worker(rank, world, port, out_q):
     reduced = model.flat_gradients.clone()
     ref = FlatToy(5, seed=100)
     grad_of(ref, x_all, y_all)
-    out_q.put((rank, float(w), reduced, ref.flat_gradients.clone(), float(loss_weight("listNet", y_all[shard]))))
+    out_q.put(_by_value((rank, float(w), reduced, ref.flat_gradients.clone(), float(loss_weight("listNet", y_all[shard])))))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -183,7 +206,7 @@ def test_numerator_and_count_reduction_for_means_over_a_data_dependent_subset():
     procs = [ctx.Process(target=_weighted_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in procs]
+    got = [_from_value(q.get(timeout=120)) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
