@@ -32,6 +32,7 @@ _SIGS = {
 }
 
 _lib = None
+_pack_default = 0
 
 
 class ArbError(RuntimeError):
@@ -40,7 +41,7 @@ class ArbError(RuntimeError):
 
 def lib():
     """Load the library once.  Raises (never falls back) when it is missing."""
-    global _lib
+    global _lib, _pack_default
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise ArbError(
@@ -61,7 +62,14 @@ def lib():
             handle.arb_set_attention_skip_padding(int(os.environ["ARB_ATTN_SKIP_PADDING"]))
         if os.environ.get("ARB_PACK_ROWS") in ("0", "1"):
             handle.arb_set_pack_rows(int(os.environ["ARB_PACK_ROWS"]))
+        _pack_default = int(handle.arb_get_pack_rows())
     return _lib
+
+
+def default_pack_rows():
+    """The packed-rows setting this process started with (library default or ARB_PACK_ROWS): what tests restore."""
+    lib()
+    return _pack_default
 
 
 def register(name, restype, argtypes):

@@ -58,11 +58,11 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict
                                                          long long pitch, int B, int S, int h, int dk,
                                                          float* __restrict__ delta, int o_bf16,
                                                          const int* __restrict__ rows_dev,
-                                                         const int* __restrict__ rowmap) {
+                                                         const int* __restrict__ rowmap, long long rows_cap) {
   arb_pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= (long long)B * S || (rows_dev && row >= rows_dev[0])) return;
+  if (row >= rows_cap || (rows_dev && row >= rows_dev[0])) return;
   // packed rows: the activations are indexed by the packed row, delta by the item (rows without an item are skipped)
   const long long item = rowmap ? (long long)rowmap[row] : row;
   if (item < 0) return;
@@ -493,10 +493,10 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   const double rf = packed ? arb_row_frac() : 1.0;
   {
     ProfScope ps(ARB_PROF_SCORER_SIMT, rf * double(a.B) * a.S * (8.0 * a.h * a.dk + 4.0 * a.h), st, 0.0, "attn_delta_kernel");
-    const long long rows = (long long)a.B * a.S;
+    const long long rows = packed ? (long long)a.q.dim[1] : (long long)a.B * a.S;   // packed: the buffers' row count
     arb_launch(attn_delta_kernel, dim3(unsigned((rows + 7) / 8)), dim3(256), 0, st, a.do_ptr,
                static_cast<const float*>(a.o_ptr), (long long)a.o_pitch, a.B, a.S, a.h, a.dk, a.delta, a.o_bf16, a.rows_dev,
-               a.rowmap);
+               a.rowmap, rows);
   }
   arb_count_launch();
   const bool drop = a.drop.thresh != 0;

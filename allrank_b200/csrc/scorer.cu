@@ -148,8 +148,14 @@ struct WsLayout {
   bool fused;
 };
 
+// Rows the activation buffers hold: B * S, or -- when the call can run over packed rows, whose slates occupy multiples
+// of 16 rows -- B * round_up(S, 16).
+static int64_t buffer_rows(const arb_scorer_config& c, int B, int S) {
+  return int64_t(B) * (pack_eligible(c, S) ? align_up(S, 16) : int64_t(S));
+}
+
 static void make_ws_layout(const arb_scorer_config& c, const ParamLayout& L, int B, int S, int training, WsLayout& W) {
-  const int64_t R = int64_t(B) * S, d = c.d_model, f = c.d_ff, h = c.n_heads;
+  const int64_t R = buffer_rows(c, B, S), d = c.d_model, f = c.d_ff, h = c.n_heads;
   W.Sp = int(align_up(S, 4));
   W.fused = use_fused(c, S);
   int64_t o = 0;
@@ -341,15 +347,16 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     rowmap = reinterpret_cast<const int*>(ws + W.rowmap);
     poff = reinterpret_cast<const int*>(ws + W.poff);
     ARB_TRY(pack_plan(x, kext, B, S, F, reinterpret_cast<int*>(ws + W.poff), reinterpret_cast<int*>(ws + W.plan),
-                      reinterpret_cast<int*>(ws + W.rowmap), ws + W.xc, st));
+                      reinterpret_cast<int*>(ws + W.rowmap), ws + W.xc, buffer_rows(c, B, S), st));
     // items beyond their slate's extent get the score 0
-    if (cudaMemsetAsync(scores, 0, size_t(k.R) * sizeof(float), st) != cudaSuccess) { arb_set_error("scorer: memset failed"); return ARB_E_CUDA; }
+    if (cudaMemsetAsync(scores, 0, size_t(B) * S * sizeof(float), st) != cudaSuccess) { arb_set_error("scorer: memset failed"); return ARB_E_CUDA; }
+    k.R = buffer_rows(c, B, S);       // upper bound of the packed row count (grids, tensor maps)
     if (arb_prof_enabled()) {     // per-launch accounting (bench.py) needs the live row count on the host
       int live = 0;
       if (cudaStreamSynchronize(st) != cudaSuccess || cudaMemcpy(&live, plan, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
         arb_set_error("scorer: reading the packed row count failed"); return ARB_E_CUDA;
       }
-      arb_set_row_frac(double(live) / double(k.R));
+      arb_set_row_frac(double(live) / double(k.R));   // launches account with k.R nominal rows
     }
     k.rows_dev = plan;
     x = ws + W.xc;
@@ -463,7 +470,7 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
 
 struct ScratchLayout { int64_t dxa, dxb, dxn, dxm, dqkv, dctx, dprob, prob, delta, dfa, dfb, ext, dy16, total; };
 static void make_scratch_layout(const arb_scorer_config& c, const ParamLayout& L, int B, int S, ScratchLayout& Z) {
-  const int64_t R = int64_t(B) * S, d = c.d_model;
+  const int64_t R = buffer_rows(c, B, S), d = c.d_model;
   const int Sp = int(align_up(S, 4));
   int64_t o = 0;
   auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
@@ -546,7 +553,7 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   const int* plan = pack ? reinterpret_cast<const int*>(ws + W.plan) : nullptr;
   const int* rowmap = pack ? reinterpret_cast<const int*>(ws + W.rowmap) : nullptr;
   const int* poff = pack ? reinterpret_cast<const int*>(ws + W.poff) : nullptr;
-  if (pack) { k.rows_dev = plan; x = ws + W.xc; gext = reinterpret_cast<int*>(ws + W.kext); }
+  if (pack) { k.rows_dev = plan; k.R = buffer_rows(c, B, S); x = ws + W.xc; gext = reinterpret_cast<int*>(ws + W.kext); }
   else if (skip) ARB_TRY(slate_extents(mask, dscores, n_outputs(c), B, S, gext, st));
   auto hview = [&](V v, int64_t pitch) { return pack ? head_view(v, dk, int(k.R), h, 1, pitch) : head_view(v, dk, S, h, B, pitch); };
   const int has_norm = c.n_layers > 0;
@@ -734,6 +741,7 @@ using namespace arb;
 extern "C" void arb_set_attention_mode(int32_t mode) { g_attn_mode = mode; }
 extern "C" void arb_set_attention_skip_padding(int32_t on) { g_skip_padding = on; }
 extern "C" void arb_set_pack_rows(int32_t on) { g_pack_rows = on; }
+extern "C" int32_t arb_get_pack_rows(void) { return g_pack_rows; }
 extern "C" void arb_set_attention_fwd_two_pass(int32_t on) { set_attn_fwd_two_pass(on); }
 
 extern "C" int64_t arb_scorer_param_count(const arb_scorer_config* cfg) {

@@ -969,12 +969,12 @@ __global__ void __launch_bounds__(1024) pack_scan_kernel(const int* __restrict__
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ x, const int* __restrict__ ext,
                                                         const int* __restrict__ off, const int* __restrict__ plan,
                                                         int B, int S, int F, float* __restrict__ xc,
-                                                        int* __restrict__ rowmap) {
+                                                        int* __restrict__ rowmap, int cap_rows) {
   arb_pdl_wait();
   const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int r0, n, src0;
   if (b < B) { r0 = off[b]; n = (ext[b] + 15) & ~15; src0 = b * S; }
-  else { r0 = plan[1]; n = plan[0] - plan[1]; src0 = -1; }
+  else { r0 = plan[1]; n = min(plan[0], cap_rows) - plan[1]; src0 = -1; }   // (the buffers hold cap_rows rows)
   for (int s = wid; s < n; s += 8) {
     const bool real = src0 >= 0 && s < S;
     float* dst = xc + (long long)(r0 + s) * F;
@@ -1000,14 +1000,15 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ a, i
     if (!p) continue;
     const int pitch = which ? b_pitch : a_pitch, width = which ? b_width : a_width, from = which ? b_from : a_from;
     const long long start = plan[from];
-    const long long end = from == 0 ? min(cap_rows, start + (which ? b_n : a_n)) : (long long)plan[0];
+    const long long end = min(cap_rows, from == 0 ? start + (which ? b_n : a_n) : (long long)plan[0]);
     const long long row = start + r;
     if (row >= end) continue;
     for (int c = lane * 4; c < width; c += 128) *reinterpret_cast<float4*>(p + row * pitch + c) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
-int pack_plan(const float* x, const int* ext, int B, int S, int F, int* off, int* plan, int* rowmap, float* xc, cudaStream_t st) {
+int pack_plan(const float* x, const int* ext, int B, int S, int F, int* off, int* plan, int* rowmap, float* xc,
+              long long cap_rows, cudaStream_t st) {
   if (F % 4) { arb_set_error("packed rows: the feature count must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
   {
     ProfScope ps(ARB_PROF_SCORER_SIMT, 8.0 * B, st, 0.0, "pack_scan");
@@ -1016,7 +1017,7 @@ int pack_plan(const float* x, const int* ext, int B, int S, int F, int* off, int
   }
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(B) * S * arb_row_frac() * (8.0 * F + 4.0), st, 0.0, "pack_rows");
   arb_launch(pack_rows_kernel, dim3(unsigned(B + 1)), dim3(256), 0, st, x, ext, static_cast<const int*>(off),
-             static_cast<const int*>(plan), B, S, F, xc, rowmap);
+             static_cast<const int*>(plan), B, S, F, xc, rowmap, int(cap_rows));
   return check_launch();
 }
 

@@ -59,6 +59,7 @@ int head_backward(const float* dscore, const float* score, const float* x, const
 // Packed rows (padding removal; see scorer_kernels.cu): from the slate extents build off [B+1], plan [2] and
 // rowmap [B*S] and copy the features of the packed rows into xc
 int pack_plan(const float* x, const int* ext, int B, int S, int F, int* off, int* plan, int* rowmap, float* xc,
+              long long cap_rows,   // rows the packed buffers hold (B * round_up(S, 16))
               cudaStream_t st);
 // zero rows [plan[from], ...) of up to two buffers (pitch / width in floats): from = 0: n rows after the packed rows,
 // capped at cap_rows; from = 1: the alignment rows between the slates' rows and the packed row count

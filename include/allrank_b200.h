@@ -237,6 +237,7 @@ void arb_set_attention_skip_padding(int32_t on);
  * and d_output = 1; other calls use the dense layout.  0: dense [B*S] rows everywhere, i.e. padded items scored like
  * the reference does.  Process-wide. */
 void arb_set_pack_rows(int32_t on);
+int32_t arb_get_pack_rows(void);
 
 /* 1 (default): the kernels of a step are chained with programmatic dependent launch -- a kernel's prologue (barrier
  * init, TMEM allocation, tensor-map prefetch) overlaps its predecessor's last wave, and it blocks in griddepcontrol.wait
