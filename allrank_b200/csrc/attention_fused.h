@@ -55,6 +55,7 @@ struct AttnBwdArgs {
 };
 
 bool attn_fused_bwd_supported(int S, int dk);
+void set_attn_bwd_persistent(int on);   // 1: one CTA per SM walks the (slate, head) items; 0: one CTA per item
 int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t st);
 
 }  // namespace arb

@@ -32,6 +32,7 @@
 #include "attention_fused.h"
 #include "block_utils.cuh"
 #include "common.h"
+#include "defaults.h"
 #include "sm100_ptx.cuh"
 
 namespace arb {
@@ -105,6 +106,47 @@ struct BwdSmem {
   static constexpr int total() { return BARS_OFF + 256 + 1024; }
 };
 
+// One unit of work of the kernel below: (slate, head) `item`, key tile jt, query chunk qc.  A CTA walks the items
+// item0, item0 + stride, ... and, inside an item, its n_kt x n_kt (key tile, query chunk) iterations; the three roles
+// (TMA producer, MMA issuer, compute warps) each advance their own copy.
+struct BwdIter {
+  int item, b, head, jt, qc, n_kt, ext16, q_lim, row_base;
+};
+struct BwdWalk {
+  int n_items, stride, n_heads, S;
+  const int* extent;
+  const int* pack_off;
+  // position `it` on the first iteration of the first item at or after it.item that has work
+  __device__ __forceinline__ bool seek(BwdIter& it) const {
+    for (; it.item < n_items; it.item += stride) {
+      it.b = it.item / n_heads;
+      it.head = it.item - it.b * n_heads;
+      int e = extent ? extent[it.b] : S;
+      if (pack_off && e <= 0) continue;           // packed rows: an empty slate holds no rows
+      e = max(1, min(S, e));
+      it.n_kt = (e + 127) / 128;                  // active key tiles == active query chunks
+      it.ext16 = (e + 15) & ~15;
+      it.q_lim = pack_off ? min(S, it.ext16) : S; // queries at or beyond it do not exist in this slate
+      it.row_base = pack_off ? pack_off[it.b] : 0;
+      it.jt = it.qc = 0;
+      return true;
+    }
+    return false;
+  }
+  __device__ __forceinline__ bool next(BwdIter& it) const {
+    if (++it.qc < it.n_kt) return true;
+    it.qc = 0;
+    if (++it.jt < it.n_kt) return true;
+    it.item += stride;
+    return seek(it);
+  }
+};
+
+// The grid is either one CTA per (slate, head) or -- persistent -- one CTA per SM walking many of them: the barrier
+// phases, the operand tiles and the TMEM accumulators form ONE stream of iterations across items, so the loads and the
+// S^T / dP^T products of an item's first iteration run behind the previous item's last iteration, and its epilogue
+// behind the next item's first arithmetic.  (One CTA per item pays the prologue -- first loads, first products -- and
+// the output drain, about 4.7 us, for 4.2 us of work per iteration; most slates need a single iteration.)
 template <int DK, bool DROP, bool OUT16 = false>
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const __grid_constant__ CUtensorMap tmQk, const __grid_constant__ CUtensorMap tmQm,
@@ -114,37 +156,34 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
     const uint8_t* __restrict__ mask, const float* __restrict__ stat_max, const float* __restrict__ stat_sum,
     const float* __restrict__ delta, int S, int n_heads, float scale, DropSite drop, float* __restrict__ dbias_qkv,
-    int d_model, const int* __restrict__ extent, const int* __restrict__ pack_off) {
+    int d_model, const int* __restrict__ extent, const int* __restrict__ pack_off, int n_items) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   auto tile = [&](int t) { return smem + t * TILE_BYTES; };
   uint8_t* stage = smem + BwdSmem::STAGE_OFF;
   float2* qstats = reinterpret_cast<float2*>(smem + BwdSmem::STATS_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BARS_OFF);
-  uint64_t* kv_bar = bars;          // K-major K/V tiles of this key tile landed (one phase per key tile)
-  uint64_t* q_bar = bars + 1;       // K-major Q/dO tiles of this iteration landed (one phase per iteration)
-  uint64_t* s_bar = bars + 2;       // [2] S^T and dP^T of half a / b complete    (per iteration)
+  uint64_t* kv_bar = bars;          // K-major K/V tiles of a key tile landed      (one phase per key tile of the stream)
+  uint64_t* q_bar = bars + 1;       // K-major Q/dO tiles of an iteration landed   (one phase per iteration)
+  uint64_t* s_bar = bars + 2;       // [2] S^T and dP^T of half a / b complete     (per iteration)
   uint64_t* p_bar = bars + 4;       // [2] P^T / dS^T of half a / b written by the 512 compute threads (per iteration)
   uint64_t* mma_bar = bars + 6;     // all trailing MMAs (dV, dK, dQ) of the iteration complete
-  uint64_t* qm_bar = bars + 7;      // MN-major Q/dO tiles of this iteration landed (one phase per iteration)
-  uint64_t* km_bar = bars + 8;      // MN-major K tile of this key tile landed   (one phase per key tile)
+  uint64_t* qm_bar = bars + 7;      // MN-major Q/dO tiles of an iteration landed  (one phase per iteration)
+  uint64_t* km_bar = bars + 8;      // MN-major K tile of a key tile landed        (one phase per key tile)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.x, b = blockIdx.y;
-  // Rows at or beyond the slate's extent are masked keys (probability exactly 0) whose d ctx rows are exactly zero:
+  // Rows at or beyond a slate's extent are masked keys (probability exactly 0) whose d ctx rows are exactly zero:
   // neither their key tiles nor their query chunks contribute anything, and their dQ / dK / dV rows are zero.  Only
-  // the tiles below the extent are processed; the rest is written as zeros up front.
-  const int n_full = (S + 127) / 128;
-  const float c_log2e = scale * 1.4426950408889634f;
+  // the tiles below the extent are processed; in the dense layout the rest is written as zeros.
   // Packed rows (see attn_fwd2_kernel): slate b holds its first ext16 = round_up(extent, 16) rows at row pack_off[b] of
   // one long tensor.  Tiles that overrun the slate read other slates' rows: as keys they are masked, as queries their
   // probabilities are forced to zero below (their d ctx rows are NOT zero, unlike the dense layout's padding); outputs
   // are stored in 16-row boxes that stop at the slate's last packed row, and nothing is zero-filled.
+  const int n_full = (S + 127) / 128;
+  const float c_log2e = scale * 1.4426950408889634f;
   const bool packed = pack_off != nullptr;
-  const int row_base = packed ? pack_off[b] : 0;
-  const int bc = packed ? 0 : b;
-  if (packed && extent[b] <= 0) return;       // an empty slate holds no packed rows
+  const BwdWalk walk{n_items, int(gridDim.x), n_heads, S, extent, pack_off};
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQk); ptx::prefetch_tmap(&tmQm); ptx::prefetch_tmap(&tmKk); ptx::prefetch_tmap(&tmKm);
@@ -165,10 +204,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const int ext = extent ? max(1, min(S, extent[b])) : S;
-  const int n_kt = (ext + 127) / 128;   // active key tiles == active query chunks
-  const int ext16 = (ext + 15) & ~15;
-  const int q_lim = packed ? min(S, ext16) : S;   // queries at or beyond it do not exist in this slate
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t T_ST = tmem_base, T_DPT = tmem_base + 128, T_DV = tmem_base + 256, T_DK = tmem_base + 320;
   const uint32_t T_DQ0 = tmem_base + 384;   // + 64 * qc
@@ -176,29 +211,30 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int it = 0;
-      for (int jt = 0; jt < n_kt; ++jt) {
-        for (int qc = 0; qc < n_kt; ++qc, ++it) {
-          // The K-major tiles are read only by the S^T / dP^T MMAs, so they can be refilled as soon as the previous
-          // iteration's second half of S^T / dP^T has completed -- i.e. while its compute phases and trailing MMAs run.
-          if (it > 0) ptx::mbar_wait(s_bar + 1, (it - 1) & 1);
-          ptx::mbar_expect_tx(q_bar, 2 * TILE_BYTES);
-          ptx::tma_load_4d(tile(BwdSmem::Q_KM), &tmQk, q_bar, 0, row_base + 128 * qc, head, bc);
-          ptx::tma_load_4d(tile(BwdSmem::DO_KM), &tmDOk, q_bar, 0, row_base + 128 * qc, head, bc);
-          if (qc == 0) {
-            ptx::mbar_expect_tx(kv_bar, 2 * TILE_BYTES);
-            ptx::tma_load_4d(tile(BwdSmem::K_KM), &tmKk, kv_bar, 0, row_base + 128 * jt, head, bc);
-            ptx::tma_load_4d(tile(BwdSmem::V_KM), &tmVk, kv_bar, 0, row_base + 128 * jt, head, bc);
-          }
-          // the MN-major tiles are still in use by the trailing MMAs (dV, dK, dQ) of the previous iteration
-          if (it > 0) ptx::mbar_wait(mma_bar, (it - 1) & 1);
-          ptx::mbar_expect_tx(qm_bar, 2 * TILE_BYTES);
-          ptx::tma_load_4d(tile(BwdSmem::Q_MN), &tmQm, qm_bar, 0, row_base + 128 * qc, head, bc);
-          ptx::tma_load_4d(tile(BwdSmem::DO_MN), &tmDOm, qm_bar, 0, row_base + 128 * qc, head, bc);
-          if (qc == 0) {
-            ptx::mbar_expect_tx(km_bar, TILE_BYTES);
-            ptx::tma_load_4d(tile(BwdSmem::K_MN), &tmKm, km_bar, 0, row_base + 128 * jt, head, bc);
-          }
+      BwdIter c;
+      c.item = blockIdx.x;
+      bool ok = walk.seek(c);
+      for (uint32_t g = 0; ok; ++g, ok = walk.next(c)) {
+        const int bc = packed ? 0 : c.b;
+        // The K-major tiles are read only by the S^T / dP^T MMAs, so they can be refilled as soon as the previous
+        // iteration's second half of S^T / dP^T has completed -- i.e. while its compute phases and trailing MMAs run.
+        if (g > 0) ptx::mbar_wait(s_bar + 1, (g - 1) & 1);
+        ptx::mbar_expect_tx(q_bar, 2 * TILE_BYTES);
+        ptx::tma_load_4d(tile(BwdSmem::Q_KM), &tmQk, q_bar, 0, c.row_base + 128 * c.qc, c.head, bc);
+        ptx::tma_load_4d(tile(BwdSmem::DO_KM), &tmDOk, q_bar, 0, c.row_base + 128 * c.qc, c.head, bc);
+        if (c.qc == 0) {
+          ptx::mbar_expect_tx(kv_bar, 2 * TILE_BYTES);
+          ptx::tma_load_4d(tile(BwdSmem::K_KM), &tmKk, kv_bar, 0, c.row_base + 128 * c.jt, c.head, bc);
+          ptx::tma_load_4d(tile(BwdSmem::V_KM), &tmVk, kv_bar, 0, c.row_base + 128 * c.jt, c.head, bc);
+        }
+        // the MN-major tiles are still in use by the trailing MMAs (dV, dK, dQ) of the previous iteration
+        if (g > 0) ptx::mbar_wait(mma_bar, (g - 1) & 1);
+        ptx::mbar_expect_tx(qm_bar, 2 * TILE_BYTES);
+        ptx::tma_load_4d(tile(BwdSmem::Q_MN), &tmQm, qm_bar, 0, c.row_base + 128 * c.qc, c.head, bc);
+        ptx::tma_load_4d(tile(BwdSmem::DO_MN), &tmDOm, qm_bar, 0, c.row_base + 128 * c.qc, c.head, bc);
+        if (c.qc == 0) {
+          ptx::mbar_expect_tx(km_bar, TILE_BYTES);
+          ptx::tma_load_4d(tile(BwdSmem::K_MN), &tmKm, km_bar, 0, c.row_base + 128 * c.jt, c.head, bc);
         }
       }
     }
@@ -215,18 +251,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       const uint32_t dok = ptx::smem_u32(tile(BwdSmem::DO_KM)), dom = ptx::smem_u32(tile(BwdSmem::DO_MN));
       const uint32_t sg = ptx::smem_u32(stage);
       const uint32_t id_sh = ptx::idesc_tf32(128, 64, 0, 0);      // one 64-query half of S^T / dP^T
-      const int n_it = n_kt * n_kt;
       // Descriptors are built once; the k-steps of a family differ only by the start-address field (units of 16 B):
       // +2 per 32-byte k-step of a K-major tile, +64 per 1024-byte k-step of an MN-major tile, +512 for rows 64..127.
       const uint64_t d_kk = ptx::smem_desc_sw128<2>(kk, 16, 1024), d_vk = ptx::smem_desc_sw128<2>(vk, 16, 1024);
       const uint64_t d_qk = ptx::smem_desc_sw128<2>(qk, 16, 1024), d_dok = ptx::smem_desc_sw128<2>(dok, 16, 1024);
       const uint64_t d_dom = ptx::smem_desc_sw128<1>(dom, TILE_BYTES, 512), d_qm = ptx::smem_desc_sw128<1>(qm, TILE_BYTES, 512);
       const uint64_t d_sg = ptx::smem_desc_sw128<1>(sg, TILE_BYTES, 512), d_km = ptx::smem_desc_sw128<1>(km, TILE_BYTES, 512);
-      // S^T / dP^T of half `hf` of iteration `t` (queries 64*hf.. of the chunk: rows 64*hf.. of the K-major Q / dO
-      // tiles); the two independent accumulators are interleaved so that consecutive MMAs never depend on each other
-      auto issue_scores = [&](int t, int hf) {
+      uint32_t kv_seen = 0, km_seen = 0;      // key tiles of the stream whose K-major / MN-major loads were awaited
+      // S^T / dP^T of half `hf` of stream iteration `t` (queries 64*hf.. of the chunk: rows 64*hf.. of the K-major Q /
+      // dO tiles); the two independent accumulators are interleaved so that consecutive MMAs never depend on each other
+      auto issue_scores = [&](const BwdIter& x, uint32_t t, int hf) {
         if (hf == 0) {
-          if (t % n_kt == 0) ptx::mbar_wait(kv_bar, (t / n_kt) & 1);
+          if (x.qc == 0) { ptx::mbar_wait(kv_bar, kv_seen & 1); ++kv_seen; }
           ptx::mbar_wait(q_bar, t & 1);
           ptx::tc_fence_after();
         }
@@ -238,37 +274,44 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         }
         ptx::mma_commit(s_bar + hf);
       };
-      issue_scores(0, 0);
-      issue_scores(0, 1);
-      int it = 0;
-      for (int jt = 0; jt < n_kt; ++jt) {
-        for (int qc = 0; qc < n_kt; ++qc, ++it) {
-          const uint32_t acc_kv = qc > 0 ? 1u : 0u, acc_q = jt > 0 ? 1u : 0u;
-          // ---- half a: dV / dK over its 64 queries, then the next iteration's half-a scores into the freed columns
-          ptx::mbar_wait(p_bar, it & 1);
-          ptx::mbar_wait(qm_bar, it & 1);
-          ptx::tc_fence_after();
+      BwdIter c, n;
+      c.item = blockIdx.x;
+      bool ok = walk.seek(c);
+      if (ok) {
+        issue_scores(c, 0, 0);
+        issue_scores(c, 0, 1);
+      }
+      n = c;
+      bool has_n = ok && walk.next(n);
+      for (uint32_t g = 0; ok; ++g) {
+        const uint32_t acc_kv = c.qc > 0 ? 1u : 0u, acc_q = c.jt > 0 ? 1u : 0u;
+        // ---- half a: dV / dK over its 64 queries, then the next iteration's half-a scores into the freed columns
+        ptx::mbar_wait(p_bar, g & 1);
+        ptx::mbar_wait(qm_bar, g & 1);
+        ptx::tc_fence_after();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, d_dom + 64 * i, id_ts, i > 0 ? 1u : acc_kv);
-            ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, d_qm + 64 * i, id_ts, i > 0 ? 1u : acc_kv);
-          }
-          if (it + 1 < n_it) issue_scores(it + 1, 0);
-          // ---- half b: dV / dK, the next half-b scores, and dQ (contracts over all 128 keys: both halves staged)
-          ptx::mbar_wait(p_bar + 1, it & 1);
-          ptx::tc_fence_after();
-#pragma unroll
-          for (int i = 8; i < 16; ++i) {
-            ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, d_dom + 64 * i, id_ts, 1u);
-            ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, d_qm + 64 * i, id_ts, 1u);
-          }
-          if (it + 1 < n_it) issue_scores(it + 1, 1);
-          if (qc == 0) ptx::mbar_wait(km_bar, jt & 1);
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            ptx::mma_tf32_ss(T_DQ0 + 64 * qc, d_sg + 64 * i, d_km + 64 * i, id_dq, i > 0 ? 1u : acc_q);
-          ptx::mma_commit(mma_bar);
+        for (int i = 0; i < 8; ++i) {
+          ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, d_dom + 64 * i, id_ts, i > 0 ? 1u : acc_kv);
+          ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, d_qm + 64 * i, id_ts, i > 0 ? 1u : acc_kv);
         }
+        if (has_n) issue_scores(n, g + 1, 0);
+        // ---- half b: dV / dK, the next half-b scores, and dQ (contracts over all 128 keys: both halves staged)
+        ptx::mbar_wait(p_bar + 1, g & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int i = 8; i < 16; ++i) {
+          ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, d_dom + 64 * i, id_ts, 1u);
+          ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, d_qm + 64 * i, id_ts, 1u);
+        }
+        if (has_n) issue_scores(n, g + 1, 1);
+        if (c.qc == 0) { ptx::mbar_wait(km_bar, km_seen & 1); ++km_seen; }
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          ptx::mma_tf32_ss(T_DQ0 + 64 * c.qc, d_sg + 64 * i, d_km + 64 * i, id_dq, i > 0 ? 1u : acc_q);
+        ptx::mma_commit(mma_bar);
+        c = n;
+        ok = has_n;
+        if (ok) has_n = walk.next(n);
       }
     }
   } else {
@@ -278,42 +321,42 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     const int row = 32 * quad + lane;           // key row inside the tile == TMEM lane
     const int sub = (warp - 2) >> 2;            // which 16 of the 64 query columns of a half this warp handles
     const uint32_t lane_addr = uint32_t(32 * quad) << 16;
-    const int n_it = n_kt * n_kt;
 
-    // per-query statistics of iteration t's chunk -> smem buffer t&1 (nm = -max*c - log2(sum); -inf for rows past S)
-    auto load_stats = [&](int t, int slot) {
-      const int qi = 128 * (t % n_kt) + slot;
+    // per-query statistics of an iteration's chunk -> smem buffer `buf` (nm = -max*c - log2(sum); -inf for queries the
+    // slate does not have)
+    auto load_stats = [&](const BwdIter& x, int buf, int slot) {
+      const int qi = 128 * x.qc + slot;
       float2 st = make_float2(-CUDART_INF_F, 0.f);
-      if (qi < q_lim) {
-        const size_t so = (size_t(b) * n_heads + head) * S + qi;
+      if (qi < x.q_lim) {
+        const size_t so = (size_t(x.b) * n_heads + x.head) * S + qi;
         st.x = -(stat_max[so] * c_log2e) - log2f(stat_sum[so]);
         st.y = delta[so];
       }
-      qstats[(t & 1) * 128 + slot] = st;
+      qstats[buf * 128 + slot] = st;
     };
-    if (n_kt < n_full && !packed) {
-      // zero rows of the skipped tiles: one zero slab, TMA-stored over every skipped dQ / dK / dV tile (TMA clips at S)
+    // dense layout: zero rows of the skipped tiles of item x -- one zero slab, TMA-stored over every skipped dQ / dK /
+    // dV tile (TMA clips at S).  The staging area must be idle (start of the stream, or right after an epilogue).
+    auto zero_fill = [&](const BwdIter& x) {
       for (int i = ct; i < TILE_BYTES / 16; i += BWD_COMPUTE) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0u, 0u, 0u, 0u);
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(1, BWD_COMPUTE);
       if (ct == 0) {
-        for (int jt = n_kt; jt < n_full; ++jt) {
-          ptx::tma_store_4d(&tmDQ, stage, 0, 128 * jt, head, b);
-          ptx::tma_store_4d(&tmDK, stage, 0, 128 * jt, head, b);
-          ptx::tma_store_4d(&tmDV, stage, 0, 128 * jt, head, b);
+        for (int jt = x.n_kt; jt < n_full; ++jt) {
+          ptx::tma_store_4d(&tmDQ, stage, 0, 128 * jt, x.head, x.b);
+          ptx::tma_store_4d(&tmDK, stage, 0, 128 * jt, x.head, x.b);
+          ptx::tma_store_4d(&tmDV, stage, 0, 128 * jt, x.head, x.b);
         }
         ptx::tma_store_commit();
         ptx::tma_store_wait_read();
       }
       ptx::named_bar_sync(1, BWD_COMPUTE);
-    }
-    if (ct < 128) load_stats(0, ct);
+    };
 
-    // Outputs of iteration `e_it` that became final with it: dV / dK of its key tile after the last query chunk, dQ of
+    // Outputs of iteration `e` that became final with it: dV / dK of its key tile after the last query chunk, dQ of
     // its query chunk after the last key tile.  TMEM -> swizzled staging -> TMA store (+ the QKV bias column sums).
-    auto epilogue = [&](int e_it) {
-      const int e_jt = e_it / n_kt, e_qc = e_it % n_kt;
-      const bool last_qc = (e_qc == n_kt - 1), last_jt = (e_jt == n_kt - 1);
+    auto epilogue = [&](const BwdIter& e) {
+      const int e_jt = e.jt, e_qc = e.qc;
+      const bool last_qc = (e_qc == e.n_kt - 1), last_jt = (e_jt == e.n_kt - 1);
       if (!(last_qc || last_jt)) return;
       // up to 3 output tiles of DK <= 32 columns, one per warp group: sub 0 -> dV, sub 1 -> dK, sub 2 -> dQ
       if (sub < 3 && ((sub < 2) ? last_qc : last_jt)) {
@@ -355,29 +398,29 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         if (packed) {      // 16-row boxes up to the slate's last packed row (staged rows are 128 / 64 bytes wide)
           constexpr int BOX = OUT16 ? 1024 : 2048;
           if (last_qc) {
-            const int n16 = (min(128, ext16 - 128 * e_jt) + 15) >> 4;
+            const int n16 = (min(128, e.ext16 - 128 * e_jt) + 15) >> 4;
             for (int i = 0; i < n16; ++i) {
-              ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES + i * BOX, 0, row_base + 128 * e_jt + 16 * i, head, 0);
-              ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES + i * BOX, 0, row_base + 128 * e_jt + 16 * i, head, 0);
+              ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES + i * BOX, 0, e.row_base + 128 * e_jt + 16 * i, e.head, 0);
+              ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES + i * BOX, 0, e.row_base + 128 * e_jt + 16 * i, e.head, 0);
             }
           }
           if (last_jt) {
-            const int n16 = (min(128, ext16 - 128 * e_qc) + 15) >> 4;
+            const int n16 = (min(128, e.ext16 - 128 * e_qc) + 15) >> 4;
             for (int i = 0; i < n16; ++i)
-              ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES + i * BOX, 0, row_base + 128 * e_qc + 16 * i, head, 0);
+              ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES + i * BOX, 0, e.row_base + 128 * e_qc + 16 * i, e.head, 0);
           }
         } else {
           if (last_qc) {
-            ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * e_jt, head, b);
-            ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES, 0, 128 * e_jt, head, b);
+            ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * e_jt, e.head, e.b);
+            ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES, 0, 128 * e_jt, e.head, e.b);
           }
-          if (last_jt) ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES, 0, 128 * e_qc, head, b);
+          if (last_jt) ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES, 0, 128 * e_qc, e.head, e.b);
         }
         ptx::tma_store_commit();
       }
       if (dbias_qkv != nullptr && ct < 384) {
-        // bias gradient of the QKV projection: column sums of the staged dV / dK / dQ tiles (rows past S are 0);
-        // 96 columns x 4 row segments, the 4 partial sums sit in adjacent lanes
+        // bias gradient of the QKV projection: column sums of the staged dV / dK / dQ tiles (rows the slate does not
+        // have are 0); 96 columns x 4 row segments, the 4 partial sums sit in adjacent lanes
         const int col = ct >> 2, seg = ct & 3;
         const int which = col >> 5, cc = col & 31;
         const bool live = ((which < 2) ? last_qc : last_jt) && cc < DK;
@@ -393,74 +436,93 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         t += __shfl_xor_sync(FULL, t, 1);
         t += __shfl_xor_sync(FULL, t, 2);
         if (live && seg == 0)
-          atomicAdd(dbias_qkv + (which == 0 ? 2 * d_model : (which == 1 ? d_model : 0)) + head * DK + cc, t);
+          atomicAdd(dbias_qkv + (which == 0 ? 2 * d_model : (which == 1 ? d_model : 0)) + e.head * DK + cc, t);
       }
       if (ct == 0) ptx::tma_store_wait_read();      // the staging slabs are rewritten right after this
       ptx::named_bar_sync(1, BWD_COMPUTE);  // column sums read + TMA reads finished before anyone overwrites the slabs
     };
 
-    int it = 0;
-    for (int jt = 0; jt < n_kt; ++jt) {
-      const int key = 128 * jt + row;
-      const bool key_ok = key < S && mask[size_t(b) * S + key] == 0;
-      for (int qc = 0; qc < n_kt; ++qc, ++it) {
-        ptx::named_bar_sync(1, BWD_COMPUTE);     // this chunk's statistics are in place; iteration it-1 is fully read
-        if (it + 1 < n_it && ct >= 128 && ct < 256) load_stats(it + 1, ct - 128);   // prefetch behind the arithmetic
-        const float2* qs = qstats + (it & 1) * 128;
-#pragma unroll 1
-        for (int hf = 0; hf < 2; ++hf) {
-          ptx::mbar_wait(s_bar + hf, it & 1);
-          ptx::tc_fence_after();
-          const int col0 = 64 * hf + 16 * sub;            // first query column of this warp's 16-wide piece
-          uint32_t sv[16], dv[16];
-          ptx::tmem_ld_32x16(T_ST + lane_addr + col0, sv);
-          ptx::tmem_ld_32x16(T_DPT + lane_addr + col0, dv);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 st = qs[col0 + j];
-            const float p = key_ok ? ex2_approx_b(fmaf(__uint_as_float(sv[j]), c_log2e, st.x)) : 0.0f;
-            float p_used = p, dp = __uint_as_float(dv[j]);
-            if constexpr (DROP) {        // regenerate the forward's dropout mask on the probabilities
-              const unsigned long long idx =
-                  ((unsigned long long)(b * n_heads + head) * S + (128 * qc + col0 + j)) * (unsigned long long)S + key;
-              const float m = drop_keep(idx, drop.seed, drop.thresh) ? drop.scale : 0.0f;
-              p_used = p * m;
-              dp *= m;
-            }
-            const float ds = p * (dp - st.y);
-            sv[j] = round_tf32_b(p_used);
-            dv[j] = round_tf32_b(ds);
-          }
-          ptx::tmem_st_32x16(T_ST + lane_addr + col0, sv);
-          ptx::tmem_st_32x16(T_DPT + lane_addr + col0, dv);
-          if (hf == 0 && it > 0) {
-            // The staging slabs still feed the previous iteration's dQ product (and hold its output tiles): wait for
-            // its trailing MMAs -- they ran behind this half's arithmetic -- and flush what became final.
-            ptx::mbar_wait(mma_bar, (it - 1) & 1);
-            ptx::tc_fence_after();
-            epilogue(it - 1);
-          }
-          // dS^T also goes to shared memory as the MN-major A operand of dQ: slab = 32-query group, row = key
-          uint8_t* srow = stage + (col0 >> 5) * TILE_BYTES + row * 128;
-          const int p0 = (col0 & 31) >> 2;                // first 16-byte piece of these 16 columns in the slab row
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int piece = p0 + k;
-            const int phys = (((piece >> 1) ^ (row & 3)) << 5) + ((piece & 1) << 4);
-            *reinterpret_cast<uint4*>(srow + phys) = make_uint4(dv[k * 4], dv[k * 4 + 1], dv[k * 4 + 2], dv[k * 4 + 3]);
-          }
-          ptx::tmem_st_wait();
-          ptx::fence_proxy_async_smem();
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(p_bar + hf);
-        }
-      }
+    BwdIter c, n, prev;
+    c.item = blockIdx.x;
+    bool ok = walk.seek(c);
+    if (ok) {
+      if (!packed && c.n_kt < n_full) zero_fill(c);
+      if (ct < 128) load_stats(c, 0, ct);
     }
-    ptx::mbar_wait(mma_bar, (it - 1) & 1);
-    ptx::tc_fence_after();
-    epilogue(it - 1);
-    ptx::tc_fence_before();
+    n = c;
+    prev = c;
+    bool has_n = ok && walk.next(n);
+    bool key_ok = false;
+    uint32_t g = 0;
+    for (; ok; ++g) {
+      if (c.qc == 0) {                            // a new key tile (of this or a new item)
+        const int key = 128 * c.jt + row;
+        key_ok = key < S && mask[size_t(c.b) * S + key] == 0;
+      }
+      ptx::named_bar_sync(1, BWD_COMPUTE);     // this chunk's statistics are in place; iteration g-1 is fully read
+      if (has_n && ct >= 128 && ct < 256) load_stats(n, (g + 1) & 1, ct - 128);   // prefetch behind the arithmetic
+      const float2* qs = qstats + (g & 1) * 128;
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        ptx::mbar_wait(s_bar + hf, g & 1);
+        ptx::tc_fence_after();
+        const int col0 = 64 * hf + 16 * sub;            // first query column of this warp's 16-wide piece
+        uint32_t sv[16], dv[16];
+        ptx::tmem_ld_32x16(T_ST + lane_addr + col0, sv);
+        ptx::tmem_ld_32x16(T_DPT + lane_addr + col0, dv);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 st = qs[col0 + j];
+          const float p = key_ok ? ex2_approx_b(fmaf(__uint_as_float(sv[j]), c_log2e, st.x)) : 0.0f;
+          float p_used = p, dp = __uint_as_float(dv[j]);
+          if constexpr (DROP) {        // regenerate the forward's dropout mask on the probabilities
+            const unsigned long long idx =
+                ((unsigned long long)(c.b * n_heads + c.head) * S + (128 * c.qc + col0 + j)) * (unsigned long long)S +
+                (128 * c.jt + row);
+            const float m = drop_keep(idx, drop.seed, drop.thresh) ? drop.scale : 0.0f;
+            p_used = p * m;
+            dp *= m;
+          }
+          const float ds = p * (dp - st.y);
+          sv[j] = round_tf32_b(p_used);
+          dv[j] = round_tf32_b(ds);
+        }
+        ptx::tmem_st_32x16(T_ST + lane_addr + col0, sv);
+        ptx::tmem_st_32x16(T_DPT + lane_addr + col0, dv);
+        if (hf == 0 && g > 0) {
+          // The staging slabs still feed the previous iteration's dQ product (and hold its output tiles): wait for
+          // its trailing MMAs -- they ran behind this half's arithmetic -- and flush what became final.
+          ptx::mbar_wait(mma_bar, (g - 1) & 1);
+          ptx::tc_fence_after();
+          epilogue(prev);
+          if (!packed && c.jt == 0 && c.qc == 0 && c.n_kt < n_full) zero_fill(c);   // a new item's skipped tiles
+        }
+        // dS^T also goes to shared memory as the MN-major A operand of dQ: slab = 32-query group, row = key
+        uint8_t* srow = stage + (col0 >> 5) * TILE_BYTES + row * 128;
+        const int p0 = (col0 & 31) >> 2;                // first 16-byte piece of these 16 columns in the slab row
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int piece = p0 + k;
+          const int phys = (((piece >> 1) ^ (row & 3)) << 5) + ((piece & 1) << 4);
+          *reinterpret_cast<uint4*>(srow + phys) = make_uint4(dv[k * 4], dv[k * 4 + 1], dv[k * 4 + 2], dv[k * 4 + 3]);
+        }
+        ptx::tmem_st_wait();
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(p_bar + hf);
+      }
+      prev = c;
+      c = n;
+      ok = has_n;
+      if (ok) has_n = walk.next(n);
+    }
+    if (g > 0) {
+      ptx::mbar_wait(mma_bar, (g - 1) & 1);
+      ptx::tc_fence_after();
+      epilogue(prev);
+      ptx::tc_fence_before();
+    }
     if (ct == 0) ptx::tma_store_wait_all();
   }
   __syncthreads();
@@ -469,6 +531,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     ptx::tmem_dealloc<512>(tmem_base);
   }
 }
+
+static int g_attn_bwd_persistent = ARB_DEFAULT_ATTN_BWD_PERSISTENT;
+void set_attn_bwd_persistent(int on) { g_attn_bwd_persistent = on; }
 
 template <int DK>
 static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
@@ -512,13 +577,26 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
     }
     configured[dev][cslot] = true;
   }
-  dim3 grid(a.h, a.B);
+  // one CTA per (slate, head), or -- persistent (default) -- one per SM walking the items head-fastest
+  const int n_items = a.h * a.B;
+  int n_ctas = n_items;
+  if (g_attn_bwd_persistent) {
+    static int n_sm_of[ARB_MAX_DEVICES] = {};
+    if (!n_sm_of[dev]) {
+      int id = 0, n = 148;
+      cudaGetDevice(&id);
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, id);
+      n_sm_of[dev] = n;
+    }
+    n_ctas = std::min(n_items, n_sm_of[dev]);
+  }
+  dim3 grid(n_ctas);
   {
     ProfScope ps(ARB_PROF_GEMM, 10.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
                  rf * 4.0 * double(a.B) * a.h * a.S * (7.0 * a.dk + 3.0), "attn_bwd_kernel");
     arb_launch(kern, grid, dim3(BWD_THREADS), size_t(BwdSmem::total()), st, tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
                                                       a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale, a.drop, a.dbias_qkv,
-                                                      a.d_model, a.extent, a.pack_off);
+                                                      a.d_model, a.extent, a.pack_off, n_items);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

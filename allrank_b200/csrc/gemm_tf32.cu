@@ -61,7 +61,7 @@ struct GemmParams {
 // picks the instantiation once per chunk; unusual flag combinations take the generic run-time path.
 template <int F>
 __device__ __forceinline__ void epi_chunk_f32(const uint32_t (&v)[32], uint8_t* slab_row, int row, const float* bias_c,
-                                              float alpha, const uint8_t* aux_row) {
+                                              float alpha) {
 #pragma unroll
   for (int piece = 0; piece < 8; ++piece) {
     float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
@@ -74,8 +74,8 @@ __device__ __forceinline__ void epi_chunk_f32(const uint32_t (&v)[32], uint8_t* 
     if constexpr ((F & EPI_RELU) != 0) {
       o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f);
     }
-    if constexpr ((F & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0) {   // the aux tile: same swizzled layout, in the staging
-      const float4 a = *reinterpret_cast<const float4*>(aux_row + ((piece ^ (row & 7)) << 4));   // slab or its own buffer
+    if constexpr ((F & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0) {
+      const float4 a = *dst;
       if constexpr ((F & EPI_ADD_AUX) != 0) { o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
       if constexpr ((F & EPI_MASK_AUX) != 0) {
         o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f; o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f;
@@ -86,13 +86,13 @@ __device__ __forceinline__ void epi_chunk_f32(const uint32_t (&v)[32], uint8_t* 
 }
 // returns false when the flag combination has no specialisation (caller runs the generic loop)
 __device__ __forceinline__ bool epi_chunk_dispatch(int flags, const uint32_t (&v)[32], uint8_t* slab_row, int row,
-                                                   const float* bias_c, float alpha, const uint8_t* aux_row) {
+                                                   const float* bias_c, float alpha) {
   switch (flags & (EPI_BIAS | EPI_RELU | EPI_ADD_AUX | EPI_MASK_AUX | EPI_DROPOUT | EPI_ATOMIC)) {
-    case 0: epi_chunk_f32<0>(v, slab_row, row, bias_c, alpha, aux_row); return true;
-    case EPI_BIAS: epi_chunk_f32<EPI_BIAS>(v, slab_row, row, bias_c, alpha, aux_row); return true;
-    case EPI_BIAS | EPI_RELU: epi_chunk_f32<EPI_BIAS | EPI_RELU>(v, slab_row, row, bias_c, alpha, aux_row); return true;
-    case EPI_BIAS | EPI_ADD_AUX: epi_chunk_f32<EPI_BIAS | EPI_ADD_AUX>(v, slab_row, row, bias_c, alpha, aux_row); return true;
-    case EPI_MASK_AUX: epi_chunk_f32<EPI_MASK_AUX>(v, slab_row, row, bias_c, alpha, aux_row); return true;
+    case 0: epi_chunk_f32<0>(v, slab_row, row, bias_c, alpha); return true;
+    case EPI_BIAS: epi_chunk_f32<EPI_BIAS>(v, slab_row, row, bias_c, alpha); return true;
+    case EPI_BIAS | EPI_RELU: epi_chunk_f32<EPI_BIAS | EPI_RELU>(v, slab_row, row, bias_c, alpha); return true;
+    case EPI_BIAS | EPI_ADD_AUX: epi_chunk_f32<EPI_BIAS | EPI_ADD_AUX>(v, slab_row, row, bias_c, alpha); return true;
+    case EPI_MASK_AUX: epi_chunk_f32<EPI_MASK_AUX>(v, slab_row, row, bias_c, alpha); return true;
     default: return false;
   }
 }
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
       }
       uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
       if constexpr (!DROP) {
-        if (epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha, slab_row)) continue;
+        if (epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha)) continue;
       }
 #pragma unroll
       for (int piece = 0; piece < 8; ++piece) {
@@ -401,31 +401,27 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
 // accumulator while the next tile's loads and MMAs are already in flight.  This keeps ~128 KB of loads in flight
 // per SM at all times, which is what an HBM-bound GEMM with K = 128..512 needs (the non-persistent kernel has no
 // loads in flight during its epilogue).
-// AUXBUF: launches with a residual / ReLU-mask tile give it a buffer of its own (and one ring stage less): the aux
-// load of tile t+1 then no longer waits for tile t's stores to leave the staging area -- it is issued as soon as the
-// epilogue groups have read tile t's aux values.
-template <int BLOCK_N, bool AUXBUF = false>
+template <int BLOCK_N>
 struct PersistLayout {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = AUXBUF ? (BLOCK_N <= 64 ? 5 : 3) : (BLOCK_N <= 64 ? 6 : 4);
+  static constexpr int STAGES = BLOCK_N <= 64 ? 6 : 4;
   static constexpr int STAGING_BYTES = BLOCK_M * BLOCK_N * 4;
-  static constexpr int AUX_BYTES = AUXBUF ? STAGING_BYTES : 0;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int total() { return RING_BYTES + STAGING_BYTES + AUX_BYTES + 512 + BLOCK_N * 4 + 1024; }
+  static constexpr int total() { return RING_BYTES + STAGING_BYTES + 512 + BLOCK_N * 4 + 1024; }
 };
 
 constexpr int EPI_THREADS = 256;
 constexpr int PERSIST_THREADS = 64 + EPI_THREADS;
 
-template <int BLOCK_N, int A_MN, int B_MN, bool AUXBUF = false>
+template <int BLOCK_N, int A_MN, int B_MN>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA,
                                                                         const __grid_constant__ CUtensorMap tmB,
                                                                         const __grid_constant__ CUtensorMap tmC,
                                                                         const __grid_constant__ CUtensorMap tmAux,
                                                                         const GemmParams p, int n_tiles_n,
                                                                         int n_tiles_m, int n_z) {
-  using L = PersistLayout<BLOCK_N, AUXBUF>;
+  using L = PersistLayout<BLOCK_N>;
   constexpr int STAGES = L::STAGES;
   constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr int TMEM_COLS = 2 * ACC_COLS;
@@ -434,15 +430,14 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
   extern __shared__ uint8_t smem_dyn[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + L::RING_BYTES;
-  uint8_t* aux_buf = AUXBUF ? staging + L::STAGING_BYTES : staging;     // where the aux tile lands
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + L::STAGING_BYTES + L::AUX_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + L::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;        // [2] accumulator complete
   uint64_t* acc_empty = acc_full + 2;             // [2] accumulator drained by the epilogue (128 arrivals)
   uint64_t* aux_full = acc_empty + 2;             // aux tile landed in staging
   uint64_t* stage_free = aux_full + 1;            // staging free again (store has read it), 1 arrival
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 1);
-  float* bias_s = reinterpret_cast<float*>(staging + L::STAGING_BYTES + L::AUX_BYTES + 512);
+  float* bias_s = reinterpret_cast<float*>(staging + L::STAGING_BYTES + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool split = (p.flags & EPI_ATOMIC) != 0;
@@ -524,12 +519,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
           // the residual / mask tile goes into the staging area, which is reused tile after tile: wait until the
           // previous tile's TMA store has read it (issued AFTER this tile's operand loads so the ring never stalls
           // behind the epilogue)
-          // (AUXBUF: stage_free then means "both epilogue groups have READ the previous aux tile", which happens long
-          // before their stores drain)
           if (local > 0) ptx::mbar_wait(stage_free, (local - 1) & 1);
           ptx::mbar_expect_tx(aux_full, L::STAGING_BYTES);
           for (int c = 0; c < N_SLABS; ++c)
-            ptx::tma_load_4d(aux_buf + c * (BLOCK_M * 128), &tmAux, aux_full, n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
+            ptx::tma_load_4d(staging + c * (BLOCK_M * 128), &tmAux, aux_full, n0 + 32 * c, m0, b2 * p.c_b2, b3 * p.c_b3);
         }
       }
     }
@@ -607,7 +600,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
           // reclaim the slab: every store this leader committed except the most recent (SLABS_PER_GROUP - 1) ones has
           // been read out of shared memory -- in particular the one that used slab c a tile ago.  With an aux tile
           // the leader already drained its stores before the producer refilled the staging area.
-          if (!split && (!has_aux || AUXBUF) && leader && local > 0) {
+          if (!split && !has_aux && leader && local > 0) {
             if constexpr (SLABS_PER_GROUP == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else ptx::tma_store_wait_read();
           }
@@ -621,8 +614,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
             for (int j = 0; j < 32; ++j) v[j] = 0u;
           }
           uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
-          const uint8_t* aux_row = aux_buf + c * (BLOCK_M * 128) + row * 128;
-          if (!epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha, aux_row)) {
+          if (!epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha)) {
 #pragma unroll
           for (int piece = 0; piece < 8; ++piece) {
             float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
@@ -692,9 +684,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
       // this accumulator may be overwritten by the MMA warp from now on
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_empty[acc]);
-      if (!split && has_aux && active && leader) {     // the producer may load the next aux tile: into the staging area
-        if constexpr (!AUXBUF) ptx::tma_store_wait_read();   // once this group's stores have left it, or into the aux
-        ptx::mbar_arrive(stage_free);                         // buffer, whose values this group has read (barrier above)
+      if (!split && has_aux && active && leader) {     // the producer refills the staging area with the next aux tile
+        ptx::tma_store_wait_read();
+        ptx::mbar_arrive(stage_free);
       }
     }
     if (!split && active && leader) ptx::tma_store_wait_read();
@@ -779,12 +771,11 @@ static double live_k(const GemmDesc& d) { return double(d.K) * ((d.rows_dev && (
 static int g_persistent = ARB_DEFAULT_GEMM_PERSISTENT;   // 0: never, 1: wherever supported, 2: auto
 void set_gemm_persistent(int on) { g_persistent = on; }
 
-template <int BLOCK_N, int A_MN, int B_MN, bool AUXBUF = false>
+template <int BLOCK_N, int A_MN, int B_MN>
 static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                                const CUtensorMap& tX, const GemmParams& p, dim3 tiles, cudaStream_t st) {
-  auto kern = gemm_tf32_persistent<BLOCK_N, A_MN, B_MN, AUXBUF>;
-  constexpr int smem = PersistLayout<BLOCK_N, AUXBUF>::total();
-  static_assert(smem <= 227 * 1024, "persistent GEMM: shared memory budget");
+  auto kern = gemm_tf32_persistent<BLOCK_N, A_MN, B_MN>;
+  constexpr int smem = PersistLayout<BLOCK_N>::total();
   static bool configured[ARB_MAX_DEVICES] = {};
   static int n_sm_of[ARB_MAX_DEVICES] = {};
   const int dev_slot = arb_device_slot();
@@ -806,7 +797,7 @@ static int launch_persistent_t(const GemmDesc& d, const CUtensorMap& tA, const C
     const double nb = double(d.nb2) * double(d.nb3);
     const double has_x = (d.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) ? 1.0 : 0.0;
     char pname[56];
-    gemm_prof_name(pname, d, AUXBUF ? "persistx" : "persist");
+    gemm_prof_name(pname, d, "persist");
     const double dM = live_m(d), dK = live_k(d);
     ProfScope ps(ARB_PROF_GEMM, 2.0 * dM * double(d.N) * dK * nb, st,
                  4.0 * nb * (dM * dK + double(d.N) * dK + (1.0 + has_x) * dM * d.N), pname);
@@ -876,17 +867,12 @@ static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap&
   // pipeline wins on every unbatched, non-split shape (short-K wide-N forward linears 0.76-0.86 of the HBM roof against
   // 0.58-0.62 for one-tile CTAs; K >= 256: 0.93-0.98) EXCEPT short-K products with a residual / mask tile, whose aux
   // load it can only issue once the previous tile's stores have left the staging area (dgrad N512 K128 mask: 0.70
-  // against 0.85; the K128 +res projection ties).
-  // Modes 3 / 4 give the aux tile a buffer of its own (one ring stage less): 3 for every aux launch, 4 for the short-K
-  // ones only.
+  // against 0.85; the K128 +res projection ties).  (Giving the aux tile a shared-memory buffer of its own, at the price
+  // of one ring stage, measured slower on every shape: 19.17 against 18.63 ms per cfg2 step -- not kept.)
   const bool has_aux_tile = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
-  const bool eligible = !(A_MN == 1 && B_MN == 1) && !(p.flags & EPI_ATOMIC) && d.nb2 == 1 && d.nb3 == 1;
-  if constexpr (!(A_MN == 1 && B_MN == 1)) {
-    if ((g_persistent == 3 || (g_persistent == 4 && d.K < 256)) && eligible && has_aux_tile)
-      return launch_persistent_t<BLOCK_N, A_MN, B_MN, true>(d, tA, tB, tC, tX, p, grid, st);
-  }
-  const bool pick = eligible && (d.K >= 256 || !has_aux_tile || g_persistent >= 3);
-  if (g_persistent == 1 || (g_persistent >= 2 && pick))
+  const bool pick = !(A_MN == 1 && B_MN == 1) && !(p.flags & EPI_ATOMIC) && d.nb2 == 1 && d.nb3 == 1 &&
+                    (d.K >= 256 || !has_aux_tile);
+  if (g_persistent == 1 || (g_persistent == 2 && pick))
     return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
   // dropout epilogue is a separate instantiation (forward linears only) so the common path carries no mask code;
   // ring depth: 4 stages for the long split-K loops of the weight gradients (1 CTA/SM), 3 for K >= 256

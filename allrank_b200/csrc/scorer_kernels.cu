@@ -5,6 +5,7 @@
 // All are one-warp-per-row, coalesced 128-bit accesses where the width allows, warp-shuffle reductions;
 // they are HBM-bound (DESIGN.md section 3 lists bytes per row).
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "block_utils.cuh"
@@ -919,6 +920,17 @@ static int nv_for(int width) { return (width + 127) / 128; }
     default: arb_set_error("row kernels support widths up to 1024"); return ARB_E_UNSUPPORTED; \
   }
 
+// rows per warp of the backward row kernels (LayerNorm, head): more rows per warp = fewer block-level reductions and
+// atomics of the gain / bias gradients per byte moved.  ARB_ROWS_PER_WARP overrides (measurement knob).
+static int bwd_rows_per_warp() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("ARB_ROWS_PER_WARP");
+    v = e ? std::max(1, std::min(256, atoi(e))) : 8;
+  }
+  return v;
+}
+
 static int check_launch() {
   arb_count_launch();
   cudaError_t e = cudaGetLastError();
@@ -1048,7 +1060,7 @@ int ln_backward(const float* dy, const float* x, const float* a, const float* me
   if (dy16_out && dx_masked == nullptr && (site.thresh != 0 || site.scale != 1.0f)) {
     arb_set_error("ln_backward: a masked bf16 copy needs the masked fp32 buffer too"); return ARB_E_INVALID_ARG;
   }   // thresh 0 with a scale = pure rescale (positional encoding)
-  const int rpw = 8;
+  const int rpw = bwd_rows_per_warp();
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * ((dres ? 16.0 : 12.0) * width + 8), st);
   ARB_DISPATCH_NV(width, (arb_launch(ln_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode, static_cast<const uint16_t*>(dy16_in), static_cast<uint16_t*>(dy16_out), rows_dev)));
@@ -1147,7 +1159,7 @@ int head_backward(const float* dscore, const float* score, const float* x, const
                   float* grad_wb, cudaStream_t st, float* dx_masked, DropSite site, float* colsum_out, void* dy16_out,
                   const int* rows_dev, const int* rowmap) {
   if (site.thresh == 0) dx_masked = nullptr;
-  const int rpw = 8;
+  const int rpw = bwd_rows_per_warp();
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * (8.0 * width + 16), st);
   ARB_DISPATCH_NV(width, (arb_launch(head_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out, static_cast<uint16_t*>(dy16_out), rows_dev, rowmap)));
@@ -1167,7 +1179,7 @@ int head_multi_backward(const float* dscore, const float* score, const float* xf
                         long long rows, int width, int n, float* dxf, float* grad_w, float* grad_wb, cudaStream_t st,
                         float* dx_masked, DropSite site, float* colsum_out) {
   if (site.thresh == 0) dx_masked = nullptr;
-  const int rpw = 8;
+  const int rpw = bwd_rows_per_warp();
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, double(rows) * (8.0 * width + 8.0 * n), st);
   ARB_DISPATCH_NV(width, (head_multi_bwd_kernel<NV><<<blocks, ROWS_PER_BLOCK * 32, 0, st>>>(dscore, score, xf, w, act, rows, width, n, rpw, dxf, grad_w, grad_wb, dx_masked, site, colsum_out)));

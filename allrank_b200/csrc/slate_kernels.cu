@@ -502,10 +502,15 @@ __global__ void __launch_bounds__(256) approx_ndcg_kernel(const float* __restric
   float* G = m.a;
   float* h = m.b;
   float lossb = 0.f;
+  // the pair loops stop at the last real item of the score order (pads sort behind every finite score, so for the usual
+  // slate this is the item count: half the S x S pairs of an MSLR-shaped batch); the per-item flag test stays
+  float hi_part = 0.f;
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     const bool valid = m.t[i] != -CUDART_INF_F;
     G[i] = valid ? pow2_minus_1(fmaxf(m.t[i], 0.0f)) / max_dcg : 0.0f;
+    if (valid) hi_part = float(i + 1);
   }
+  const int n_hi = int(block_max(hi_part, m.red));
   __syncthreads();
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     const bool valid = m.t[i] != -CUDART_INF_F;
@@ -513,7 +518,7 @@ __global__ void __launch_bounds__(256) approx_ndcg_kernel(const float* __restric
     if (valid) {
       const float si = m.s[i];
       float acc = 0.f;
-      for (int j = 0; j < S; ++j) {
+      for (int j = 0; j < n_hi; ++j) {
         if (j != i && m.t[j] != -CUDART_INF_F) acc += fmaxf(sigmoidf_(-alpha * (si - m.s[j])), eps);
       }
       a += acc;
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(256) approx_ndcg_kernel(const float* __restric
     float g = 0.f;
     if (valid) {
       const float sk = m.s[k], hk = h[k];
-      for (int i = 0; i < S; ++i) {
+      for (int i = 0; i < n_hi; ++i) {
         if (i == k || m.t[i] == -CUDART_INF_F) continue;
         const float x = alpha * (m.s[i] - sk);      // sig_ik = sigmoid(-x), sig_ki = sigmoid(x)
         const float ex = expf(-fabsf(x));
@@ -610,8 +615,10 @@ __global__ void __launch_bounds__(256) lambda_loss_kernel(const float* __restric
   float* G = m.a;
   float* invD = m.b;
   float* tl = m.c;   // clamped labels
+  float hi_part = 0.f;    // the pair loop stops at the last real item of the score order (see approx_ndcg_kernel)
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     const bool valid = m.t[i] != -CUDART_INF_F;
+    if (valid) hi_part = float(i + 1);
     tl[i] = valid ? fmaxf(m.t[i], 0.0f) : 0.0f;
     G[i] = pow2_minus_1(tl[i]) / max_dcg;
     const float D = log2f(2.0f + float(i));
@@ -619,6 +626,7 @@ __global__ void __launch_bounds__(256) lambda_loss_kernel(const float* __restric
     // Toeplitz table of ndcgLoss2: lag l >= 1 -> |1/D[l-1] - 1/D[l]| with D[m] = log2(m+2)   (lambdaLoss.py:88-92)
     toe[i] = (i == 0) ? 0.0f : fabsf(1.0f / log2f(1.0f + float(i)) - 1.0f / log2f(2.0f + float(i)));
   }
+  const int c_hi = min(kk, int(block_max(hi_part, m.red)));
   __syncthreads();
 
   const float log_eps = cfg.log_base == ARB_LOG_BINARY ? log2f(cfg.eps) : logf(cfg.eps);
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(256) lambda_loss_kernel(const float* __restric
     const bool active = (r < kk) && (m.t[r] != -CUDART_INF_F);
     if (active) {
       const float sr = m.s[r], tr = m.t[r];
-      for (int c = 0; c < kk; ++c) {
+      for (int c = 0; c < c_hi; ++c) {
         const float tc = m.t[c];
         if (tc == -CUDART_INF_F) continue;
         float term, d;

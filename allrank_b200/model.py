@@ -383,15 +383,16 @@ class LTRModel(nn.Module):
         B, S = x.shape[0], x.shape[1]
         dev = x.device
         cfg = ctypes.byref(self._cfg)
+        # dropout is applied iff the module is in train() mode, like nn.Dropout; `training` only selects whether
+        # activations are kept for backward.  (Set before the workspace query: the layout depends on it -- a call
+        # without dropout may run over packed rows.)
+        self._cfg.dropout = self.dropout_p if self.training else 0.0
+        self._cfg.fc_dropout = self.fc_dropout_p if self.training else 0.0
         n_ws = int(_lib.lib().arb_scorer_workspace_floats(cfg, B, S, 1 if training else 0))
         ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
         shape = (B, S) if self.d_output == 1 else (B, S, self.d_output)   # squeeze(dim=2) is a no-op for n > 1 (model.py:117)
         scores = torch.empty(shape, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            # dropout is applied iff the module is in train() mode, like nn.Dropout; `training` only selects
-            # whether activations are kept for backward
-            self._cfg.dropout = self.dropout_p if self.training else 0.0
-            self._cfg.fc_dropout = self.fc_dropout_p if self.training else 0.0
             table = self._pe_table(dev)
             rc = _lib.lib().arb_scorer_forward(cfg, _lib.ptr(self._flat), _lib.ptr(x), _lib.ptr(mask),
                                                _lib.ptr(indices), _lib.ptr(table), B, S,

@@ -232,11 +232,16 @@ void arb_set_attention_skip_padding(int32_t on);
  * 16 rows; the live row count stays on the device, nothing synchronises).  Exact for every real item's score and every
  * parameter gradient; the scores of the items beyond a slate's extent are then 0 (and carry no gradient) instead of
  * what the network computes for a padded feature row -- values every consumer in allRank masks (losses.py: the
- * padded_value_indicator masks, metrics.py:24, inference_utils.py:55).  Applies to calls with a transformer whose
+ * padded_value_indicator masks, metrics.py:31-35, inference_utils.py:51).  Applies to calls with a transformer whose
  * attention runs in the fused kernels (slate_length <= 256, head width 16 / 32), no dropout, no positional encoding
  * and d_output = 1; other calls use the dense layout.  0: dense [B*S] rows everywhere, i.e. padded items scored like
  * the reference does.  Process-wide. */
 void arb_set_pack_rows(int32_t on);
+
+/* Fused attention backward: 1: one CTA per SM walks the (slate, head) items as one stream of tile iterations (an
+ * item's first loads and products run behind the previous item's last iteration); 0: one CTA per item.  Same results.
+ * Process-wide; exists for A/B measurements. */
+void arb_set_attention_bwd_persistent(int32_t on);
 int32_t arb_get_pack_rows(void);
 
 /* 1 (default): the kernels of a step are chained with programmatic dependent launch -- a kernel's prologue (barrier
@@ -250,9 +255,8 @@ void arb_set_attention_fwd_two_pass(int32_t on);
 
 /* GEMM kernel choice.  0: one CTA per output tile everywhere; 1: the persistent, decoupled-pipeline kernel (one CTA per
  * SM walking all tiles) wherever it is supported; 2 (default): persistent for every unbatched, non-split product except
- * short-K ones with a residual / mask tile (measured per launch, profiles/r2); 3: as 2 plus those, every aux tile in a
- * shared-memory buffer of its own; 4: as 3 but the own buffer only when K < 256.  Process-wide; exists for A/B
- * measurements. */
+ * short-K ones (K < 256) with a residual / mask tile -- the per-launch measurements of profiles/r2.  Process-wide; exists
+ * for A/B measurements. */
 void arb_set_gemm_persistent(int32_t on);
 
 /* 1 (default): MMA operands are rounded fp32 -> tf32 by the TMA unit (TFLOAT32 tensor maps); 0: the tensor core

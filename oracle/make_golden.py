@@ -210,7 +210,13 @@ def gen_scorer():
         for k_, v in model.state_dict().items():
             blob["p:" + k_] = v.numpy()
         for k_, p in model.named_parameters():
-            blob["g:" + k_] = p.grad.numpy()
+            blob["g:" + k_] = p.grad.numpy().copy()
+        # the same with the weight of the padded items zeroed ("gv:"): what a loss that masks padded items -- every loss
+        # of allrank.models.losses -- sends back, and what the packed-rows layout of allrank_b200 reproduces
+        model.zero_grad()
+        (model(x, mask, idx) * (w * (~mask).float())).sum().backward()
+        for k_, p in model.named_parameters():
+            blob["gv:" + k_] = p.grad.numpy().copy()
         np.savez_compressed(os.path.join(OUT, f"scorer_{name}.npz"), **blob)
         print("scorer", name, "scores", tuple(scores.shape))
 

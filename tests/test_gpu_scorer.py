@@ -9,6 +9,15 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _dense_rows_by_default(dense_rows):
+    """The tests of this module compare whole score tensors (padded items included) with the reference and weight
+    padded items in their gradients: they run over the dense rows unless they switch the packed layout on themselves
+    (test_golden_forward_backward[packed-*])."""
+    yield
+
+
 SCORE_TOL = 5e-3
 GRAD_TOL = 5e-2     # relative Frobenius error of each parameter's gradient vs the fp32 reference (TF32 operands;
                     # the TF32-emulated oracle below is matched ~10x tighter)
@@ -37,32 +46,49 @@ def build(g, act_override="golden"):
 
 
 @pytest.mark.parametrize("name", ["tiny", "mid", "cfg2"])
-def test_golden_forward_backward(golden, name):
+@pytest.mark.parametrize("rows", ["dense", "packed"])
+def test_golden_forward_backward(golden, name, rows):
+    """Golden vectors of the unmodified reference (oracle/make_golden.py: gen_scorer).  `dense`: every score, padded
+    items included, and the gradients of sum(scores * w) with w over ALL items.  `packed` (the default layout,
+    arb_set_pack_rows): the scores of the real items and the gradients with w zeroed on the padded items ("gv:") --
+    what every loss of allrank.models.losses sends back; `dense` checks those too."""
+    from allrank_b200 import _lib
     g = golden("scorer_" + name)
     model = build(g).train()
     x, y = torch.tensor(g["x"]).cuda(), torch.tensor(g["y"]).cuda()
     mask = y == -1
-    scores = model(x, mask, None)
+    valid = (~mask).cpu().numpy()
     ref = g["scores"]
-    err = np.abs(scores.detach().cpu().numpy() - ref).max()
-    assert err <= SCORE_TOL * max(1.0, np.abs(ref).max()), err
-    (scores * torch.tensor(g["w"]).cuda()).sum().backward()
-    worst = 0.0
-    floor = 1e-2 * max(np.abs(g["g:" + k]).max() for k, _ in model.named_parameters())
-    bad = []
-    for k, p in model.named_parameters():
-        assert p.grad is not None, k
-        fro, mx = grad_errors(p.grad.cpu().numpy(), g["g:" + k], floor)
-        worst = max(worst, fro)
-        if fro > GRAD_TOL or mx > GRAD_TOL_MAX:
-            bad.append((k, fro, mx))
-    assert not bad, bad
-    print(name, "score err", err, "worst grad rel err", worst)
-    # eval-mode forward (in-place residual stream, shared buffers) gives the same numbers as the training forward
-    with torch.no_grad():
-        again = model.eval()(x, mask, None)
-    assert torch.equal(again, scores.detach())
-    assert torch.equal(model.score(x, mask, None), again)
+    _lib.lib().arb_set_pack_rows(1 if rows == "packed" else 0)
+    try:
+        scores = model(x, mask, None)
+        got = scores.detach().cpu().numpy()
+        sel = valid if rows == "packed" else np.ones_like(valid)
+        err = np.abs(got - ref)[sel].max()
+        assert err <= SCORE_TOL * max(1.0, np.abs(ref).max()), err
+        worst = 0.0
+        for key, w in (("g:", torch.tensor(g["w"])), ("gv:", torch.tensor(g["w"]) * torch.tensor(valid).float())):
+            if rows == "packed" and key == "g:":
+                continue
+            model.zero_grad(set_to_none=True)
+            (model(x, mask, None) * w.cuda()).sum().backward()
+            floor = 1e-2 * max(np.abs(g[key + k]).max() for k, _ in model.named_parameters())
+            bad = []
+            for k, p in model.named_parameters():
+                assert p.grad is not None, k
+                fro, mx = grad_errors(p.grad.cpu().numpy(), g[key + k], floor)
+                worst = max(worst, fro)
+                if fro > GRAD_TOL or mx > GRAD_TOL_MAX:
+                    bad.append((k, fro, mx))
+            assert not bad, (key, bad)
+        print(name, rows, "score err", err, "worst grad rel err", worst)
+        # eval-mode forward (in-place residual stream, shared buffers) gives the same numbers as the training forward
+        with torch.no_grad():
+            again = model.eval()(x, mask, None)
+        assert torch.equal(again, scores.detach())
+        assert torch.equal(model.score(x, mask, None), again)
+    finally:
+        _lib.lib().arb_set_pack_rows(0)      # (the module's fixture restores the process default afterwards)
 
 
 def test_gradient_accumulation_and_zero_grad(golden):

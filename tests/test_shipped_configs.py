@@ -54,9 +54,10 @@ def test_shipped_config_builds_with_the_reference_initialisation(golden, name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", NAMES)
-def test_shipped_config_eval_matches_the_reference(golden, name):
+def test_shipped_config_eval_matches_the_reference(golden, name, dense_rows):
     """Scores within the TF32 bound (5e-3 abs at unit scale) of the reference's fp32 run and every
-    parameter gradient (sampled positions + norm) within 5 %."""
+    parameter gradient (sampled positions + norm) within 5 %.  (Dense rows: the golden gradients weight the padded
+    items too.)"""
     model, m, g = build(golden, name, "cuda")
     model.eval()
     x, y = torch.tensor(g["x"]).cuda(), torch.tensor(g["y"]).cuda()
