@@ -63,11 +63,12 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict
   arb_pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows_cap || (rows_dev && row >= rows_dev[0])) return;
-  // packed rows: the activations are indexed by the packed row, delta by the item (rows without an item are skipped)
+  if (row >= rows_cap) return;
+  // packed rows: the activations are indexed by the packed row, delta by the item (rows without an item are skipped).
+  // The row-count and row-map loads are issued together with the data loads (every row below rows_cap is readable)
+  // and only consulted before the store: a warp lives for one row, so a dependent load up front would double its life.
+  const int live = rows_dev ? rows_dev[0] : 0x7fffffff;
   const long long item = rowmap ? (long long)rowmap[row] : row;
-  if (item < 0) return;
-  const int b = int(item / S), qi = int(item % S);
   const int width = h * dk, lanes_per_head = dk >> 2;
   for (int c0 = 0; c0 < width; c0 += 128) {
     const int c = c0 + lane * 4;
@@ -85,7 +86,10 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict
       acc = a.x * bq.x + a.y * bq.y + a.z * bq.z + a.w * bq.w;
     }
     for (int off = lanes_per_head >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
-    if (c < width && (lane % lanes_per_head) == 0) delta[((long long)b * h + c / dk) * S + qi] = acc;
+    if (row < live && item >= 0 && c < width && (lane % lanes_per_head) == 0) {
+      const int b = int(item / S), qi = int(item - (long long)b * S);
+      delta[((long long)b * h + c / dk) * S + qi] = acc;
+    }
   }
 }
 

@@ -6,4 +6,4 @@
 #define ARB_DEFAULT_SKIP_PADDING 1        // attention kernels stop at the slate extent (arb_set_attention_skip_padding)
 #define ARB_DEFAULT_GEMM_PERSISTENT 2     // 0 never, 1 everywhere, 2 for K >= 256 (arb_set_gemm_persistent)
 #define ARB_DEFAULT_PACK_ROWS 1           // encoder over the unpadded rows only (arb_set_pack_rows, ARB_PACK_ROWS)
-#define ARB_DEFAULT_ATTN_BWD_PERSISTENT 0 // attention backward: one CTA per SM walks the (slate, head) items (arb_set_attention_bwd_persistent)
+#define ARB_DEFAULT_ATTN_BWD_PERSISTENT 1 // attention backward: one CTA per SM walks the (slate, head) items (arb_set_attention_bwd_persistent)

@@ -90,6 +90,14 @@ __device__ __forceinline__ void apply_drop(RowRegs<NV>& r, long long row, int wi
 // A warp owns FWD_RPW consecutive rows and issues all their loads before the first reduction: one row per warp leaves
 // only 512 B in flight per warp at d_model = 128, far too little to cover the HBM latency (Little's law).
 constexpr int FWD_RPW = 4;
+// ... and it walks FWD_NB such batches, the loads of the next batch issued before the arithmetic of the current one: a
+// warp that retires after a single batch spends a third of its life waiting for its first loads and for a new block
+// to be scheduled (ln_forward sat at 0.66 of the HBM roof, the head at 0.31).  Wide rows (NV > 2) keep one batch: two
+// batches of them do not fit the register file.
+template <int NV>
+struct FwdBatches { static constexpr int value = NV <= 2 ? 4 : 1; };
+static inline int fwd_batches_for_width(int width) { return width <= 256 ? 4 : 1; }
+
 template <int NV>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float* __restrict__ x,
                                                                     const float* __restrict__ a,
@@ -100,65 +108,85 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
                                                                     uint16_t* __restrict__ y16,
                                                                     const int* __restrict__ rows_dev) {
   arb_pdl_wait();
-  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);   // packed rows: the live row count lives on the device
+  constexpr int NB = FwdBatches<NV>::value;
   const int lane = threadIdx.x & 31;
-  const long long row0 = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * FWD_RPW;
-  if (row0 >= rows) return;
-  RowRegs<NV> r[FWD_RPW], ga, gb;
+  const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (FWD_RPW * NB);
+  if (base >= rows) return;
+  // packed rows: the live row count lives on the device.  Its load is issued WITH the first row loads (every row below
+  // the host-side bound is readable) and consulted afterwards.
+  const long long live = rows_dev ? (long long)rows_dev[0] : rows;
+  RowRegs<NV> r[FWD_RPW], rn[FWD_RPW], ga, gb;
+  auto fetch = [&](long long r0, RowRegs<NV>(&dst)[FWD_RPW]) {
 #pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) {
-    if (row0 + q < rows) load_row<NV>(x + (row0 + q) * width, width, lane, r[q]);
-    else {
+    for (int q = 0; q < FWD_RPW; ++q) {
+      if (r0 + q < rows) load_row<NV>(x + (r0 + q) * width, width, lane, dst[q]);
+      else {
 #pragma unroll
-      for (int k = 0; k < NV; ++k) r[q].v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  load_row<NV>(a, width, lane, ga);
-  load_row<NV>(b, width, lane, gb);
-  float mean[FWD_RPW], sd[FWD_RPW];
-#pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) {
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) s += r[q].v[k].x + r[q].v[k].y + r[q].v[k].z + r[q].v[k].w;
-    mean[q] = s;
-  }
-#pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) mean[q] = warp_sum(mean[q]) / float(width);
-#pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) {
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c = lane * 4 + 128 * k;
-      if (c < width) {
-        const float d0 = r[q].v[k].x - mean[q], d1 = r[q].v[k].y - mean[q], d2 = r[q].v[k].z - mean[q],
-                    d3 = r[q].v[k].w - mean[q];
-        ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        for (int k = 0; k < NV; ++k) dst[q].v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    sd[q] = ss;
-  }
+  };
+  fetch(base, r);
+  load_row<NV>(a, width, lane, ga);
+  load_row<NV>(b, width, lane, gb);
+  rows = min(rows, live);
+#pragma unroll 1
+  for (int nb = 0; nb < NB; ++nb) {
+    const long long row0 = base + nb * FWD_RPW;
+    if (row0 >= rows) break;
+    if (NB > 1 && nb + 1 < NB) fetch(row0 + FWD_RPW, rn);
+    float mean[FWD_RPW], sd[FWD_RPW];
 #pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) sd[q] = warp_sum(sd[q]);
+    for (int q = 0; q < FWD_RPW; ++q) {
+      float s = 0.f;
 #pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) {
-    if (row0 + q >= rows) break;
-    // torch_mode: nn.LayerNorm (biased variance, eps inside the root; FCModel's input_norm, model.py:27) -- the saved
-    // "std" is then sqrt(var + eps) and the backward is called with eps = 0
-    const float sdq = torch_mode ? sqrtf(sd[q] / float(width) + eps) : sqrtf(sd[q] / float(width - 1));
-    const float denom = torch_mode ? sdq : sdq + eps;
-    const float m = mean[q];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) / denom + gb.v[k].x;
-      r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) / denom + gb.v[k].y;
-      r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) / denom + gb.v[k].z;
-      r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) / denom + gb.v[k].w;
+      for (int k = 0; k < NV; ++k) s += r[q].v[k].x + r[q].v[k].y + r[q].v[k].z + r[q].v[k].w;
+      mean[q] = s;
     }
-    if (y16) store_row_bf16<NV>(y16 + (row0 + q) * width, width, lane, r[q]);   // bf16 mode: the GEMM operand copy only
-    else store_row<NV>(y + (row0 + q) * width, width, lane, r[q]);
-    if (lane == 0) { mean_o[row0 + q] = m; std_o[row0 + q] = sdq; }
+#pragma unroll
+    for (int q = 0; q < FWD_RPW; ++q) mean[q] = warp_sum(mean[q]) / float(width);
+#pragma unroll
+    for (int q = 0; q < FWD_RPW; ++q) {
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + 128 * k;
+        if (c < width) {
+          const float d0 = r[q].v[k].x - mean[q], d1 = r[q].v[k].y - mean[q], d2 = r[q].v[k].z - mean[q],
+                      d3 = r[q].v[k].w - mean[q];
+          ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+      }
+      sd[q] = ss;
+    }
+#pragma unroll
+    for (int q = 0; q < FWD_RPW; ++q) sd[q] = warp_sum(sd[q]);
+#pragma unroll
+    for (int q = 0; q < FWD_RPW; ++q) {
+      if (row0 + q >= rows) break;
+      // torch_mode: nn.LayerNorm (biased variance, eps inside the root; FCModel's input_norm, model.py:27) -- the saved
+      // "std" is then sqrt(var + eps) and the backward is called with eps = 0
+      const float sdq = torch_mode ? sqrtf(sd[q] / float(width) + eps) : sqrtf(sd[q] / float(width - 1));
+      const float denom = torch_mode ? sdq : sdq + eps;
+      const float m = mean[q];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) / denom + gb.v[k].x;
+        r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) / denom + gb.v[k].y;
+        r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) / denom + gb.v[k].z;
+        r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) / denom + gb.v[k].w;
+      }
+      if (y16) store_row_bf16<NV>(y16 + (row0 + q) * width, width, lane, r[q]);   // bf16 mode: the GEMM operand copy only
+      else store_row<NV>(y + (row0 + q) * width, width, lane, r[q]);
+      if (lane == 0) { mean_o[row0 + q] = m; std_o[row0 + q] = sdq; }
+    }
+    if (NB > 1) {
+#pragma unroll
+      for (int q = 0; q < FWD_RPW; ++q) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) r[q].v[k] = rn[q].v[k];
+      }
+    }
   }
 }
 
@@ -486,87 +514,110 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
                                                                       const int* __restrict__ rows_dev,
                                                                       const int* __restrict__ rowmap) {
   arb_pdl_wait();
-  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);
+  constexpr int NB = FwdBatches<NV>::value;
   const int lane = threadIdx.x & 31;
-  // FWD_RPW rows per warp, all loads issued up front (see ln_fwd_kernel)
-  const long long row0 = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * FWD_RPW;
-  if (row0 >= rows) return;
-  RowRegs<NV> r[FWD_RPW], ga, gb, gw;
+  // FWD_NB batches of FWD_RPW rows per warp, the next batch's loads (rows and their row-map entries) issued before
+  // the arithmetic of the current one (see ln_fwd_kernel); the device-side row count is loaded with the first batch
+  const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (FWD_RPW * NB);
+  if (base >= rows) return;
+  const long long live = rows_dev ? (long long)rows_dev[0] : rows;
+  RowRegs<NV> r[FWD_RPW], rn[FWD_RPW], ga, gb, gw;
+  long long at[FWD_RPW], atn[FWD_RPW];
+  auto fetch = [&](long long r0, RowRegs<NV>(&dst)[FWD_RPW], long long(&dat)[FWD_RPW]) {
 #pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) {
-    if (row0 + q < rows) load_row<NV>(x + (row0 + q) * width, width, lane, r[q]);
-    else {
+    for (int q = 0; q < FWD_RPW; ++q) {
+      dat[q] = (rowmap && r0 + q < rows) ? (long long)rowmap[r0 + q] : r0 + q;
+      if (r0 + q < rows) load_row<NV>(x + (r0 + q) * width, width, lane, dst[q]);
+      else {
 #pragma unroll
-      for (int k = 0; k < NV; ++k) r[q].v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < NV; ++k) dst[q].v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-  }
+  };
+  fetch(base, r, at);
   load_row<NV>(w, width, lane, gw);
-  float mean[FWD_RPW], sd[FWD_RPW];
-#pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) mean[q] = sd[q] = 0.f;
   if (has_norm) {
     load_row<NV>(a, width, lane, ga);
     load_row<NV>(b, width, lane, gb);
+  }
+  const float bias = wb[0];
+  rows = min(rows, live);
+#pragma unroll 1
+  for (int nb = 0; nb < NB; ++nb) {
+    const long long row0 = base + nb * FWD_RPW;
+    if (row0 >= rows) break;
+    if (NB > 1 && nb + 1 < NB) fetch(row0 + FWD_RPW, rn, atn);
+    float mean[FWD_RPW], sd[FWD_RPW];
 #pragma unroll
-    for (int q = 0; q < FWD_RPW; ++q) {
-      float s = 0.f;
+    for (int q = 0; q < FWD_RPW; ++q) mean[q] = sd[q] = 0.f;
+    if (has_norm) {
 #pragma unroll
-      for (int k = 0; k < NV; ++k) s += r[q].v[k].x + r[q].v[k].y + r[q].v[k].z + r[q].v[k].w;
-      mean[q] = s;
+      for (int q = 0; q < FWD_RPW; ++q) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s += r[q].v[k].x + r[q].v[k].y + r[q].v[k].z + r[q].v[k].w;
+        mean[q] = s;
+      }
+#pragma unroll
+      for (int q = 0; q < FWD_RPW; ++q) mean[q] = warp_sum(mean[q]) / float(width);
+#pragma unroll
+      for (int q = 0; q < FWD_RPW; ++q) {
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int c = lane * 4 + 128 * k;
+          if (c < width) {
+            const float d0 = r[q].v[k].x - mean[q], d1 = r[q].v[k].y - mean[q], d2 = r[q].v[k].z - mean[q],
+                        d3 = r[q].v[k].w - mean[q];
+            ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+          }
+        }
+        sd[q] = ss;
+      }
+#pragma unroll
+      for (int q = 0; q < FWD_RPW; ++q) sd[q] = sqrtf(warp_sum(sd[q]) / float(width - 1));
+#pragma unroll
+      for (int q = 0; q < FWD_RPW; ++q) {
+        const float denom = sd[q] + eps, m = mean[q];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) / denom + gb.v[k].x;
+          r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) / denom + gb.v[k].y;
+          r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) / denom + gb.v[k].z;
+          r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) / denom + gb.v[k].w;
+        }
+      }
     }
-#pragma unroll
-    for (int q = 0; q < FWD_RPW; ++q) mean[q] = warp_sum(mean[q]) / float(width);
+    float dot[FWD_RPW];
 #pragma unroll
     for (int q = 0; q < FWD_RPW; ++q) {
-      float ss = 0.f;
+      float t = 0.f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int c = lane * 4 + 128 * k;
-        if (c < width) {
-          const float d0 = r[q].v[k].x - mean[q], d1 = r[q].v[k].y - mean[q], d2 = r[q].v[k].z - mean[q],
-                      d3 = r[q].v[k].w - mean[q];
-          ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-        }
+        if (c < width)
+          t += r[q].v[k].x * gw.v[k].x + r[q].v[k].y * gw.v[k].y + r[q].v[k].z * gw.v[k].z + r[q].v[k].w * gw.v[k].w;
       }
-      sd[q] = ss;
+      dot[q] = t;
     }
 #pragma unroll
-    for (int q = 0; q < FWD_RPW; ++q) sd[q] = sqrtf(warp_sum(sd[q]) / float(width - 1));
+    for (int q = 0; q < FWD_RPW; ++q) dot[q] = warp_sum(dot[q]);
+    if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < FWD_RPW; ++q) {
-      const float denom = sd[q] + eps, m = mean[q];
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) / denom + gb.v[k].x;
-        r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) / denom + gb.v[k].y;
-        r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) / denom + gb.v[k].z;
-        r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) / denom + gb.v[k].w;
+      for (int q = 0; q < FWD_RPW; ++q) {
+        if (row0 + q >= rows) break;
+        // packed rows: the score goes to the item's place in the [B, S] tensor (alignment rows have none)
+        if (at[q] >= 0) score[at[q]] = act_fwd(dot[q] + bias, act);
+        if (has_norm && mean_o) { mean_o[row0 + q] = mean[q]; std_o[row0 + q] = sd[q]; }
       }
     }
-  }
-  float dot[FWD_RPW];
+    if (NB > 1) {
 #pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) {
-    float t = 0.f;
+      for (int q = 0; q < FWD_RPW; ++q) {
+        at[q] = atn[q];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c = lane * 4 + 128 * k;
-      if (c < width)
-        t += r[q].v[k].x * gw.v[k].x + r[q].v[k].y * gw.v[k].y + r[q].v[k].z * gw.v[k].z + r[q].v[k].w * gw.v[k].w;
-    }
-    dot[q] = t;
-  }
-#pragma unroll
-  for (int q = 0; q < FWD_RPW; ++q) dot[q] = warp_sum(dot[q]);
-  if (lane == 0) {
-    const float bias = wb[0];
-#pragma unroll
-    for (int q = 0; q < FWD_RPW; ++q) {
-      if (row0 + q >= rows) break;
-      // packed rows: the score goes to the item's place in the [B, S] tensor (alignment rows have none)
-      const long long at = rowmap ? (long long)rowmap[row0 + q] : row0 + q;
-      if (at >= 0) score[at] = act_fwd(dot[q] + bias, act);
-      if (has_norm && mean_o) { mean_o[row0 + q] = mean[q]; std_o[row0 + q] = sd[q]; }
+        for (int k = 0; k < NV; ++k) r[q].v[k] = rn[q].v[k];
+      }
     }
   }
 }
@@ -596,17 +647,44 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
   for (int k = 0; k < NV; ++k) acc_a.v[k] = acc_b.v[k] = acc_w.v[k] = acc_c.v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   float acc_wb = 0.f;
   const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
-  for (int it = 0; it < rows_per_warp; ++it) {
-    const long long row = first + it;
-    if (row >= rows) break;
-    RowRegs<NV> xr, g;
-    load_row<NV>(x + row * width, width, lane, xr);
-    // packed rows: score and its gradient sit at the item's place in the [B, S] tensors; alignment rows have neither
-    const long long at = rowmap ? (long long)rowmap[row] : row;
-    const float out = at >= 0 ? score[at] : 0.f;
+  // The warp's rows go in batches of HB: the loads of a whole batch -- rows, row-map entries, statistics, then the
+  // scores and their gradients -- are issued before the first row's arithmetic (one row at a time left 12 KB in flight
+  // per SM at 73 registers: 0.33 of the HBM roof).  Per-row arithmetic and accumulation order are unchanged.
+  constexpr int HB = NV <= 2 ? 4 : 1;
+#pragma unroll 1
+  for (int it0 = 0; it0 < rows_per_warp; it0 += HB) {
+    if (first + it0 >= rows) break;
+    RowRegs<NV> xb[HB];
+    long long atb[HB];
+    float meanb[HB], sdb[HB], outb[HB], dsb[HB];
+#pragma unroll
+    for (int q = 0; q < HB; ++q) {
+      const long long row = first + it0 + q;
+      const bool ok = it0 + q < rows_per_warp && row < rows;
+      atb[q] = -1;
+      meanb[q] = 0.f; sdb[q] = 1.f;
+      if (ok) {
+        load_row<NV>(x + row * width, width, lane, xb[q]);
+        // packed rows: score and its gradient sit at the item's place in the [B, S] tensors; alignment rows have neither
+        atb[q] = rowmap ? (long long)rowmap[row] : row;
+        if (has_norm) { meanb[q] = mean_i[row]; sdb[q] = std_i[row]; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < HB; ++q) {
+      outb[q] = atb[q] >= 0 ? score[atb[q]] : 0.f;
+      dsb[q] = atb[q] >= 0 ? dscore[atb[q]] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < HB; ++q) {
+    const long long row = first + it0 + q;
+    if (it0 + q >= rows_per_warp || row >= rows) break;
+    RowRegs<NV>& xr = xb[q];
+    RowRegs<NV> g;
+    const float out = outb[q];
     float z = 0.f;
     if (act == ARB_ACT_RELU) z = out;   // relu: out > 0 <=> z > 0
-    const float dz = at >= 0 ? dscore[at] * act_bwd(out, z, act) : 0.f;
+    const float dz = atb[q] >= 0 ? dsb[q] * act_bwd(out, z, act) : 0.f;
     if (lane == 0) acc_wb += dz;
     if (!has_norm) {
 #pragma unroll
@@ -629,7 +707,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
       }
       continue;
     }
-    const float mean = mean_i[row], sd = std_i[row];
+    const float mean = meanb[q], sd = sdb[q];
     const float r = 1.0f / (sd + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -678,6 +756,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
       for (int k = 0; k < NV; ++k) {
         acc_c.v[k].x += g.v[k].x; acc_c.v[k].y += g.v[k].y; acc_c.v[k].z += g.v[k].z; acc_c.v[k].w += g.v[k].w;
       }
+    }
     }
   }
 #pragma unroll
@@ -1046,7 +1125,8 @@ int zero_rows(float* a, int a_pitch, int a_width, int a_from, int a_n, float* b,
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
                float* mean, float* sd, cudaStream_t st, int torch_mode, void* y16, const int* rows_dev) {
   if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
-  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * FWD_RPW - 1) / (ROWS_PER_BLOCK * FWD_RPW));
+  const int per_block = ROWS_PER_BLOCK * FWD_RPW * fwd_batches_for_width(width);
+  const unsigned blocks = unsigned((rows + per_block - 1) / per_block);
   ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * ((y16 ? 6.0 : 8.0) * width + 8), st);
   ARB_DISPATCH_NV(width, (arb_launch(ln_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16), rows_dev)));
   return check_launch();
@@ -1147,7 +1227,8 @@ int head_forward(const float* x, const float* a, const float* b, float eps, cons
                  int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,
                  cudaStream_t st, const int* rows_dev, const int* rowmap) {
   if (width % 4) { arb_set_error("model width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
-  const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * FWD_RPW - 1) / (ROWS_PER_BLOCK * FWD_RPW));
+  const int per_block = ROWS_PER_BLOCK * FWD_RPW * fwd_batches_for_width(width);
+  const unsigned blocks = unsigned((rows + per_block - 1) / per_block);
   ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * (4.0 * width + 12), st);
   ARB_DISPATCH_NV(width, (arb_launch(head_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd, rows_dev, rowmap)));
   return check_launch();

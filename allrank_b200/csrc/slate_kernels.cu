@@ -481,6 +481,16 @@ __global__ void __launch_bounds__(256) listmle_kernel(const float* __restrict__ 
 //       w_ik = sig_ik sig_ki,  h_i = G_i / (log2(1+a_i)^2 (1+a_i) ln 2)
 // Thread k owns row k; the other operand is a shared-memory broadcast.
 // ------------------------------------------------------------------------------------------------
+// sigmoid for the S x S pair loops: the kernel is bound by instruction issue (about 85 instructions per pair with
+// expf and IEEE division), so the pair terms use the SFU forms -- ex2.approx and rcp.approx, 2 ulp each -- on the
+// overflow-free branch exp(-|x|); a sum of up to S such terms keeps the loss within 1e-6 relative of the reference
+// (the 1e-5 bound of SURVEY.md 8c; tests/test_gpu_losses.py).
+__device__ __forceinline__ float pair_sigmoid(float x) {
+  const float ex = __expf(-fabsf(x));
+  const float big = __fdividef(1.0f, 1.0f + ex);
+  return x >= 0.f ? big : ex * big;
+}
+
 __global__ void __launch_bounds__(256) approx_ndcg_kernel(const float* __restrict__ y_pred,
                                                           const float* __restrict__ y_true, int B, int S,
                                                           float eps, float pad, float alpha, float inv_B,
@@ -519,7 +529,7 @@ __global__ void __launch_bounds__(256) approx_ndcg_kernel(const float* __restric
       const float si = m.s[i];
       float acc = 0.f;
       for (int j = 0; j < n_hi; ++j) {
-        if (j != i && m.t[j] != -CUDART_INF_F) acc += fmaxf(sigmoidf_(-alpha * (si - m.s[j])), eps);
+        if (j != i && m.t[j] != -CUDART_INF_F) acc += fmaxf(pair_sigmoid(-alpha * (si - m.s[j])), eps);
       }
       a += acc;
     }
@@ -539,8 +549,8 @@ __global__ void __launch_bounds__(256) approx_ndcg_kernel(const float* __restric
       for (int i = 0; i < n_hi; ++i) {
         if (i == k || m.t[i] == -CUDART_INF_F) continue;
         const float x = alpha * (m.s[i] - sk);      // sig_ik = sigmoid(-x), sig_ki = sigmoid(x)
-        const float ex = expf(-fabsf(x));
-        const float big = 1.0f / (1.0f + ex), small = ex / (1.0f + ex);
+        const float ex = __expf(-fabsf(x));
+        const float big = __fdividef(1.0f, 1.0f + ex), small = ex * big;
         const float sig_ik = x >= 0.f ? small : big;
         const float sig_ki = x >= 0.f ? big : small;
         const float w = sig_ik * sig_ki;
