@@ -294,23 +294,6 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   }
   if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
   arb_pdl_wait();
-  if (warp >= 2) {
-    const int et = threadIdx.x - 64;
-    if (et < 8) {
-      uint32_t w = 0;
-      for (int j = 0; j < 32; ++j) {
-        const int key = 32 * et + j;
-        if (key < S && mask[size_t(b) * S + key] == 0) w |= (1u << j);
-      }
-      mask_bits[et] = w;
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
   // keys at or beyond the slate's extent are all masked (probability exactly 0): the score / P V products, the softmax
   // loop and the K / V loads stop there.  At least one key column group is always processed, so an all-padded slate
   // still produces the reference's NaN rows.
@@ -318,17 +301,31 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   const int S16 = (kext + 15) & ~15, S8 = (kext + 7) & ~7;
   const int nkc = (S16 + 127) / 128;          // key chunks
   const int nsteps = 1 + nkc;                 // one pass-A step over the whole score row + one pass-B step per chunk
+  if (warp == 0 && lane == 0) {
+    // The loads go out right here -- the thread that initialised the barriers needs nobody else -- so that they run
+    // behind the TMEM allocation, the mask read and the block-wide barrier below instead of after them.
+    // K and V arrive as 128-key boxes: only the chunks that hold keys below the extent are fetched
+    ptx::mbar_expect_tx(load_bar, L::Q_BYTES + nkc * 2 * (128 * 128));
+    ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, row_base + m0, head, bc);
+    for (int kc = 0; kc < nkc; ++kc) {
+      ptx::tma_load_4d(k_s + kc * 16384, &tmK, load_bar, 0, row_base + 128 * kc, head, bc);
+      ptx::tma_load_4d(v_s + kc * 16384, &tmV, load_bar, 0, row_base + 128 * kc, head, bc);
+    }
+  }
+  if (warp >= 2) {      // key mask as 8 words: one key per softmax thread, one ballot per warp
+    const int key = threadIdx.x - 64;
+    const uint32_t w = __ballot_sync(0xffffffffu, key < S && mask[size_t(b) * S + key] == 0);
+    if (lane == 0) mask_bits[warp - 2] = w;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // K and V arrive as 128-key boxes: only the chunks that hold keys below the extent are fetched
-      ptx::mbar_expect_tx(load_bar, L::Q_BYTES + nkc * 2 * (128 * 128));
-      ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, row_base + m0, head, bc);
-      for (int kc = 0; kc < nkc; ++kc) {
-        ptx::tma_load_4d(k_s + kc * 16384, &tmK, load_bar, 0, row_base + 128 * kc, head, bc);
-        ptx::tma_load_4d(v_s + kc * 16384, &tmV, load_bar, 0, row_base + 128 * kc, head, bc);
-      }
-    }
+    // (the producer's loads were issued above)
   } else if (warp == 1) {
     if (lane == 0) {
       ptx::mbar_wait(load_bar, 0);

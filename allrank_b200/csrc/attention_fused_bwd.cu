@@ -55,6 +55,7 @@ __device__ __forceinline__ uint32_t round_tf32_b(float x) {
 
 // delta[b,h,q] = sum_e dO[b,q,h,e] * O[b,q,h,e]: one warp per row of the [B*S, d_model] activations, 128-bit loads,
 // segmented shuffle reduction over the dk/4 lanes that share a head (dk in {16, 32}: 4 or 8 lanes per head).
+constexpr int DELTA_RPW = 4;     // rows per warp of the delta kernel
 __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict__ d_o, const float* __restrict__ o,
                                                          long long pitch, int B, int S, int h, int dk,
                                                          float* __restrict__ delta, int o_bf16,
@@ -62,33 +63,42 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict
                                                          const int* __restrict__ rowmap, long long rows_cap) {
   arb_pdl_wait();
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows_cap) return;
-  // packed rows: the activations are indexed by the packed row, delta by the item (rows without an item are skipped).
-  // The row-count and row-map loads are issued together with the data loads (every row below rows_cap is readable)
-  // and only consulted before the store: a warp lives for one row, so a dependent load up front would double its life.
-  const int live = rows_dev ? rows_dev[0] : 0x7fffffff;
-  const long long item = rowmap ? (long long)rowmap[row] : row;
+  const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * DELTA_RPW;
+  // packed rows: the activations are indexed by the packed row, delta by the item (rows without an item are skipped);
+  // rows at or beyond the device-side row count are not touched
+  const long long rows = rows_dev ? min(rows_cap, (long long)rows_dev[0]) : rows_cap;
+  if (row0 >= rows) return;
   const int width = h * dk, lanes_per_head = dk >> 2;
+  // a warp owns DELTA_RPW consecutive rows and issues all their loads (row-map entries included) up front
+  long long item[DELTA_RPW];
+#pragma unroll
+  for (int q = 0; q < DELTA_RPW; ++q) item[q] = (row0 + q < rows) ? (rowmap ? (long long)rowmap[row0 + q] : row0 + q) : -1;
   for (int c0 = 0; c0 < width; c0 += 128) {
     const int c = c0 + lane * 4;
-    float acc = 0.f;
-    if (c < width) {
-      const float4 a = *reinterpret_cast<const float4*>(d_o + row * pitch + c);
-      float4 bq;
-      if (o_bf16) {       // bf16 mode: the saved context is bfloat16
-        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(o) + row * pitch + c);
-        bq = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
-                         __uint_as_float(u.y & 0xffff0000u));
-      } else {
-        bq = *reinterpret_cast<const float4*>(o + row * pitch + c);
+    float4 a[DELTA_RPW], bq[DELTA_RPW];
+#pragma unroll
+    for (int q = 0; q < DELTA_RPW; ++q) {
+      a[q] = bq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < width && row0 + q < rows) {
+        const long long row = row0 + q;
+        a[q] = *reinterpret_cast<const float4*>(d_o + row * pitch + c);
+        if (o_bf16) {       // bf16 mode: the saved context is bfloat16
+          const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(o) + row * pitch + c);
+          bq[q] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                              __uint_as_float(u.y & 0xffff0000u));
+        } else {
+          bq[q] = *reinterpret_cast<const float4*>(o + row * pitch + c);
+        }
       }
-      acc = a.x * bq.x + a.y * bq.y + a.z * bq.z + a.w * bq.w;
     }
-    for (int off = lanes_per_head >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
-    if (row < live && item >= 0 && c < width && (lane % lanes_per_head) == 0) {
-      const int b = int(item / S), qi = int(item - (long long)b * S);
-      delta[((long long)b * h + c / dk) * S + qi] = acc;
+#pragma unroll
+    for (int q = 0; q < DELTA_RPW; ++q) {
+      float acc = a[q].x * bq[q].x + a[q].y * bq[q].y + a[q].z * bq[q].z + a[q].w * bq[q].w;
+      for (int off = lanes_per_head >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+      if (item[q] >= 0 && c < width && (lane % lanes_per_head) == 0) {
+        const int b = int(item[q] / S), qi = int(item[q] - (long long)b * S);
+        delta[((long long)b * h + c / dk) * S + qi] = acc;
+      }
     }
   }
 }
@@ -115,6 +125,9 @@ struct BwdSmem {
 // (TMA producer, MMA issuer, compute warps) each advance their own copy.
 struct BwdIter {
   int item, b, head, jt, qc, n_kt, ext16, q_lim, row_base;
+  int q_live;     // queries at or beyond it contribute nothing (the dense layout's padding has zero d ctx rows; packed
+                  // rows: the slate has no such queries): a 64-query half that starts there is skipped
+  __device__ __forceinline__ bool half_b_live() const { return 128 * qc + 64 < q_live; }
 };
 struct BwdWalk {
   int n_items, stride, n_heads, S;
@@ -131,6 +144,7 @@ struct BwdWalk {
       it.n_kt = (e + 127) / 128;                  // active key tiles == active query chunks
       it.ext16 = (e + 15) & ~15;
       it.q_lim = pack_off ? min(S, it.ext16) : S; // queries at or beyond it do not exist in this slate
+      it.q_live = pack_off ? it.q_lim : (extent ? e : S);
       it.row_base = pack_off ? pack_off[it.b] : 0;
       it.jt = it.qc = 0;
       return true;
@@ -271,10 +285,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           ptx::tc_fence_after();
         }
         const uint64_t hoff = uint64_t(hf) * 512;
+        if (hf == 0 || x.half_b_live()) {       // (a dead half b: no products, the barrier phase still advances)
 #pragma unroll
-        for (int k = 0; k < KSTEPS; ++k) {
-          ptx::mma_tf32_ss(T_ST + 64 * hf, d_kk + 2 * k, d_qk + hoff + 2 * k, id_sh, k > 0);
-          ptx::mma_tf32_ss(T_DPT + 64 * hf, d_vk + 2 * k, d_dok + hoff + 2 * k, id_sh, k > 0);
+          for (int k = 0; k < KSTEPS; ++k) {
+            ptx::mma_tf32_ss(T_ST + 64 * hf, d_kk + 2 * k, d_qk + hoff + 2 * k, id_sh, k > 0);
+            ptx::mma_tf32_ss(T_DPT + 64 * hf, d_vk + 2 * k, d_dok + hoff + 2 * k, id_sh, k > 0);
+          }
         }
         ptx::mma_commit(s_bar + hf);
       };
@@ -302,10 +318,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         // ---- half b: dV / dK, the next half-b scores, and dQ (contracts over all 128 keys: both halves staged)
         ptx::mbar_wait(p_bar + 1, g & 1);
         ptx::tc_fence_after();
+        if (c.half_b_live()) {
 #pragma unroll
-        for (int i = 8; i < 16; ++i) {
-          ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, d_dom + 64 * i, id_ts, 1u);
-          ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, d_qm + 64 * i, id_ts, 1u);
+          for (int i = 8; i < 16; ++i) {
+            ptx::mma_tf32_ts(T_DV, T_ST + 8 * i, d_dom + 64 * i, id_ts, 1u);
+            ptx::mma_tf32_ts(T_DK, T_DPT + 8 * i, d_qm + 64 * i, id_ts, 1u);
+          }
         }
         if (has_n) issue_scores(n, g + 1, 1);
         if (c.qc == 0) { ptx::mbar_wait(km_bar, km_seen & 1); ++km_seen; }
@@ -456,21 +474,40 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
     n = c;
     prev = c;
     bool has_n = ok && walk.next(n);
-    bool key_ok = false;
+    // is this thread's key of x's key tile a real key?  (fetched one iteration ahead: the load would otherwise sit at
+    // the head of every item's first iteration)
+    auto key_live = [&](const BwdIter& x) {
+      const int key = 128 * x.jt + row;
+      return key < S && mask[size_t(x.b) * S + key] == 0;
+    };
+    bool key_ok = ok && key_live(c), key_ok_n = false;
     uint32_t g = 0;
     for (; ok; ++g) {
-      if (c.qc == 0) {                            // a new key tile (of this or a new item)
-        const int key = 128 * c.jt + row;
-        key_ok = key < S && mask[size_t(c.b) * S + key] == 0;
-      }
       ptx::named_bar_sync(1, BWD_COMPUTE);     // this chunk's statistics are in place; iteration g-1 is fully read
       if (has_n && ct >= 128 && ct < 256) load_stats(n, (g + 1) & 1, ct - 128);   // prefetch behind the arithmetic
+      if (has_n && n.qc == 0) key_ok_n = key_live(n);    // the next iteration opens a new key tile
       const float2* qs = qstats + (g & 1) * 128;
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
         ptx::mbar_wait(s_bar + hf, g & 1);
         ptx::tc_fence_after();
         const int col0 = 64 * hf + 16 * sub;            // first query column of this warp's 16-wide piece
+        if (hf == 1 && !c.half_b_live()) {
+          // none of these 64 queries contributes: their dS^T columns are staged as zeros for the dQ product (its rows
+          // for them are then exactly zero) and the dV / dK products of the half are not issued
+          uint8_t* zrow = stage + (col0 >> 5) * TILE_BYTES + row * 128;
+          const int z0 = (col0 & 31) >> 2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int piece = z0 + k;
+            const int phys = (((piece >> 1) ^ (row & 3)) << 5) + ((piece & 1) << 4);
+            *reinterpret_cast<uint4*>(zrow + phys) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(p_bar + hf);
+          continue;
+        }
         uint32_t sv[16], dv[16];
         ptx::tmem_ld_32x16(T_ST + lane_addr + col0, sv);
         ptx::tmem_ld_32x16(T_DPT + lane_addr + col0, dv);
@@ -519,6 +556,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       prev = c;
       c = n;
       ok = has_n;
+      if (ok && c.qc == 0) key_ok = key_ok_n;
       if (ok) has_n = walk.next(n);
     }
     if (g > 0) {
@@ -563,7 +601,7 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   {
     ProfScope ps(ARB_PROF_SCORER_SIMT, rf * double(a.B) * a.S * (8.0 * a.h * a.dk + 4.0 * a.h), st, 0.0, "attn_delta_kernel");
     const long long rows = packed ? (long long)a.q.dim[1] : (long long)a.B * a.S;   // packed: the buffers' row count
-    arb_launch(attn_delta_kernel, dim3(unsigned((rows + 7) / 8)), dim3(256), 0, st, a.do_ptr,
+    arb_launch(attn_delta_kernel, dim3(unsigned((rows + 8 * DELTA_RPW - 1) / (8 * DELTA_RPW))), dim3(256), 0, st, a.do_ptr,
                static_cast<const float*>(a.o_ptr), (long long)a.o_pitch, a.B, a.S, a.h, a.dk, a.delta, a.o_bf16, a.rows_dev,
                a.rowmap, rows);
   }

@@ -96,7 +96,8 @@ constexpr int FWD_RPW = 4;
 // batches of them do not fit the register file.
 template <int NV>
 struct FwdBatches { static constexpr int value = NV <= 2 ? 4 : 1; };
-static inline int fwd_batches_for_width(int width) { return width <= 256 ? 4 : 1; }
+// (small launches keep one batch per warp: more batches would leave SMs without a block -- B = 64 has 8 k live rows)
+static inline int fwd_batches_for(int width, long long rows) { return (width <= 256 && rows >= (1 << 17)) ? 4 : 1; }
 
 template <int NV>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float* __restrict__ x,
@@ -106,9 +107,10 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
                                                                     float* __restrict__ y, float* __restrict__ mean_o,
                                                                     float* __restrict__ std_o, int torch_mode,
                                                                     uint16_t* __restrict__ y16,
-                                                                    const int* __restrict__ rows_dev) {
+                                                                    const int* __restrict__ rows_dev, int n_batches) {
   arb_pdl_wait();
-  constexpr int NB = FwdBatches<NV>::value;
+  constexpr int NBMAX = FwdBatches<NV>::value;
+  const int NB = NBMAX > 1 ? n_batches : 1;
   const int lane = threadIdx.x & 31;
   const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (FWD_RPW * NB);
   if (base >= rows) return;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
   for (int nb = 0; nb < NB; ++nb) {
     const long long row0 = base + nb * FWD_RPW;
     if (row0 >= rows) break;
-    if (NB > 1 && nb + 1 < NB) fetch(row0 + FWD_RPW, rn);
+    if (NBMAX > 1 && nb + 1 < NB) fetch(row0 + FWD_RPW, rn);
     float mean[FWD_RPW], sd[FWD_RPW];
 #pragma unroll
     for (int q = 0; q < FWD_RPW; ++q) {
@@ -167,20 +169,23 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
       // torch_mode: nn.LayerNorm (biased variance, eps inside the root; FCModel's input_norm, model.py:27) -- the saved
       // "std" is then sqrt(var + eps) and the backward is called with eps = 0
       const float sdq = torch_mode ? sqrtf(sd[q] / float(width) + eps) : sqrtf(sd[q] / float(width - 1));
-      const float denom = torch_mode ? sdq : sdq + eps;
+      // one reciprocal per row instead of a division per element: the kernel is bound by instruction issue as much as
+      // by HBM (an IEEE division is ~10 instructions), and a * (x - mean) * (1 / (std + eps)) differs from the
+      // reference's a * (x - mean) / (std + eps) by one rounding (6e-8 relative)
+      const float rinv = 1.0f / (torch_mode ? sdq : sdq + eps);
       const float m = mean[q];
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) / denom + gb.v[k].x;
-        r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) / denom + gb.v[k].y;
-        r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) / denom + gb.v[k].z;
-        r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) / denom + gb.v[k].w;
+        r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) * rinv + gb.v[k].x;
+        r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) * rinv + gb.v[k].y;
+        r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) * rinv + gb.v[k].z;
+        r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) * rinv + gb.v[k].w;
       }
       if (y16) store_row_bf16<NV>(y16 + (row0 + q) * width, width, lane, r[q]);   // bf16 mode: the GEMM operand copy only
       else store_row<NV>(y + (row0 + q) * width, width, lane, r[q]);
       if (lane == 0) { mean_o[row0 + q] = m; std_o[row0 + q] = sdq; }
     }
-    if (NB > 1) {
+    if (NBMAX > 1) {
 #pragma unroll
       for (int q = 0; q < FWD_RPW; ++q) {
 #pragma unroll
@@ -512,11 +517,12 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
                                                                       float* __restrict__ mean_o,
                                                                       float* __restrict__ std_o,
                                                                       const int* __restrict__ rows_dev,
-                                                                      const int* __restrict__ rowmap) {
+                                                                      const int* __restrict__ rowmap, int n_batches) {
   arb_pdl_wait();
-  constexpr int NB = FwdBatches<NV>::value;
+  constexpr int NBMAX = FwdBatches<NV>::value;
+  const int NB = NBMAX > 1 ? n_batches : 1;
   const int lane = threadIdx.x & 31;
-  // FWD_NB batches of FWD_RPW rows per warp, the next batch's loads (rows and their row-map entries) issued before
+  // n_batches batches of FWD_RPW rows per warp, the next batch's loads (rows and their row-map entries) issued before
   // the arithmetic of the current one (see ln_fwd_kernel); the device-side row count is loaded with the first batch
   const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (FWD_RPW * NB);
   if (base >= rows) return;
@@ -546,7 +552,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
   for (int nb = 0; nb < NB; ++nb) {
     const long long row0 = base + nb * FWD_RPW;
     if (row0 >= rows) break;
-    if (NB > 1 && nb + 1 < NB) fetch(row0 + FWD_RPW, rn, atn);
+    if (NBMAX > 1 && nb + 1 < NB) fetch(row0 + FWD_RPW, rn, atn);
     float mean[FWD_RPW], sd[FWD_RPW];
 #pragma unroll
     for (int q = 0; q < FWD_RPW; ++q) mean[q] = sd[q] = 0.f;
@@ -578,13 +584,13 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
       for (int q = 0; q < FWD_RPW; ++q) sd[q] = sqrtf(warp_sum(sd[q]) / float(width - 1));
 #pragma unroll
       for (int q = 0; q < FWD_RPW; ++q) {
-        const float denom = sd[q] + eps, m = mean[q];
+        const float rinv = 1.0f / (sd[q] + eps), m = mean[q];      // (one reciprocal per row: see ln_fwd_kernel)
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-          r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) / denom + gb.v[k].x;
-          r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) / denom + gb.v[k].y;
-          r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) / denom + gb.v[k].z;
-          r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) / denom + gb.v[k].w;
+          r[q].v[k].x = ga.v[k].x * (r[q].v[k].x - m) * rinv + gb.v[k].x;
+          r[q].v[k].y = ga.v[k].y * (r[q].v[k].y - m) * rinv + gb.v[k].y;
+          r[q].v[k].z = ga.v[k].z * (r[q].v[k].z - m) * rinv + gb.v[k].z;
+          r[q].v[k].w = ga.v[k].w * (r[q].v[k].w - m) * rinv + gb.v[k].w;
         }
       }
     }
@@ -611,7 +617,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
         if (has_norm && mean_o) { mean_o[row0 + q] = mean[q]; std_o[row0 + q] = sd[q]; }
       }
     }
-    if (NB > 1) {
+    if (NBMAX > 1) {
 #pragma unroll
       for (int q = 0; q < FWD_RPW; ++q) {
         at[q] = atn[q];
@@ -649,8 +655,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
   const long long first = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * rows_per_warp;
   // The warp's rows go in batches of HB: the loads of a whole batch -- rows, row-map entries, statistics, then the
   // scores and their gradients -- are issued before the first row's arithmetic (one row at a time left 12 KB in flight
-  // per SM at 73 registers: 0.33 of the HBM roof).  Per-row arithmetic and accumulation order are unchanged.
-  constexpr int HB = NV <= 2 ? 4 : 1;
+  // per SM at 73 registers).  Per-row arithmetic and accumulation order are unchanged.
+  constexpr int HB = NV <= 2 ? 2 : 1;
 #pragma unroll 1
   for (int it0 = 0; it0 < rows_per_warp; it0 += HB) {
     if (first + it0 >= rows) break;
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
       for (int e = 0; e < 4; ++e) {
         const float cc = (c < width) ? xv[e] - mean : 0.f;
         const float xh = cc * r;
-        const float xf = av[e] * cc / (sd + eps) + bv[e];
+        const float xf = av[e] * xh + bv[e];     // the final norm's output, recomputed (xh = (x - mean) / (std + eps))
         const float dyv = dz * wv[e];          // d loss / d xf
         aw[e] += dz * xf;
         aa[e] += dyv * xh;
@@ -1125,10 +1131,11 @@ int zero_rows(float* a, int a_pitch, int a_width, int a_from, int a_n, float* b,
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
                float* mean, float* sd, cudaStream_t st, int torch_mode, void* y16, const int* rows_dev) {
   if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
-  const int per_block = ROWS_PER_BLOCK * FWD_RPW * fwd_batches_for_width(width);
+  const int nb = fwd_batches_for(width, rows);
+  const int per_block = ROWS_PER_BLOCK * FWD_RPW * nb;
   const unsigned blocks = unsigned((rows + per_block - 1) / per_block);
   ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * ((y16 ? 6.0 : 8.0) * width + 8), st);
-  ARB_DISPATCH_NV(width, (arb_launch(ln_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16), rows_dev)));
+  ARB_DISPATCH_NV(width, (arb_launch(ln_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16), rows_dev, nb)));
   return check_launch();
 }
 
@@ -1227,10 +1234,11 @@ int head_forward(const float* x, const float* a, const float* b, float eps, cons
                  int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,
                  cudaStream_t st, const int* rows_dev, const int* rowmap) {
   if (width % 4) { arb_set_error("model width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
-  const int per_block = ROWS_PER_BLOCK * FWD_RPW * fwd_batches_for_width(width);
+  const int nb = fwd_batches_for(width, rows);
+  const int per_block = ROWS_PER_BLOCK * FWD_RPW * nb;
   const unsigned blocks = unsigned((rows + per_block - 1) / per_block);
   ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * (4.0 * width + 12), st);
-  ARB_DISPATCH_NV(width, (arb_launch(head_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd, rows_dev, rowmap)));
+  ARB_DISPATCH_NV(width, (arb_launch(head_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd, rows_dev, rowmap, nb)));
   return check_launch();
 }
 

@@ -42,7 +42,8 @@ def build_pair(case, p=0.0, p_fc=0.0):
 
 
 @pytest.mark.parametrize("case", CASES)
-def test_fc_block_eval_forward_and_backward_match_the_oracle(case):
+def test_fc_block_eval_forward_and_backward_match_the_oracle(case, dense_rows):
+    # (dense rows: the gradient weights cover the padded items too, like the oracle's)
     from allrank_b200.synth import make_slates
     ref, mine = build_pair(case)
     ref.eval(); mine.eval()
@@ -53,13 +54,10 @@ def test_fc_block_eval_forward_and_backward_match_the_oracle(case):
     mask = y == -1
     out_ref = ref(x, mask, idx)
     out = mine(x.cuda(), mask.cuda(), idx.cuda())
-    valid = ~mask
-    # padded items carry no weight (what every loss of allrank.models.losses sends back): the comparison then holds in
-    # the packed layout too, where the items beyond a slate's extent score 0 and receive no gradient
     w = torch.randn(out_ref.shape, generator=gen)
-    w = w * (valid if w.dim() == 2 else valid[..., None]).float()
     (out_ref * w).sum().backward()
     (out * w.cuda()).sum().backward()
+    valid = ~mask
     err = (out.detach().cpu() - out_ref.detach())[valid].abs().max().item()
     assert err <= 5e-3 * max(1.0, out_ref.detach()[valid].abs().max().item()), err
     rp = dict(ref.named_parameters())
@@ -69,9 +67,7 @@ def test_fc_block_eval_forward_and_backward_match_the_oracle(case):
         if r is None:
             continue
         rel = (q.grad.cpu() - r).norm().item() / max(r.norm().item(), 1e-2 * gmax * np.sqrt(r.numel()))
-        # (TF32 operands against the fp32 oracle on ~70 weighted items: the 1-D parameters of these tiny models sit at
-        # 3-6 %; the TF32-emulated oracle of test_gpu_scorer.py is matched an order tighter)
-        assert rel <= 7e-2, (k, rel)
+        assert rel <= 5e-2, (k, rel)
     # score() of a multi-output head sums the outputs (model.py:119-128)
     with torch.no_grad():
         sc = mine.score(x.cuda(), mask.cuda(), idx.cuda()).cpu()
