@@ -117,6 +117,9 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
   // packed rows: the live row count lives on the device.  Its load is issued WITH the first row loads (every row below
   // the host-side bound is readable) and consulted afterwards.
   const long long live = rows_dev ? (long long)rows_dev[0] : rows;
+  // (a multi-batch warp amortises the wait for the count over 16 rows and must not fetch rows beyond it: the dead half
+  // of a packed launch would otherwise read 12 % extra; a single-batch warp overlaps it with its only fetch)
+  if (NB > 1) { rows = min(rows, live); if (base >= rows) return; }
   RowRegs<NV> r[FWD_RPW], rn[FWD_RPW], ga, gb;
   auto fetch = [&](long long r0, RowRegs<NV>(&dst)[FWD_RPW]) {
 #pragma unroll
@@ -527,6 +530,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
   const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (FWD_RPW * NB);
   if (base >= rows) return;
   const long long live = rows_dev ? (long long)rows_dev[0] : rows;
+  if (NB > 1) { rows = min(rows, live); if (base >= rows) return; }   // (see ln_fwd_kernel)
   RowRegs<NV> r[FWD_RPW], rn[FWD_RPW], ga, gb, gw;
   long long at[FWD_RPW], atn[FWD_RPW];
   auto fetch = [&](long long r0, RowRegs<NV>(&dst)[FWD_RPW], long long(&dat)[FWD_RPW]) {
