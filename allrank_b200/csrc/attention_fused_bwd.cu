@@ -634,7 +634,7 @@ static int launch_bwd_t(const AttnBwdArgs& a, cudaStream_t st) {
   }
   dim3 grid(n_ctas);
   {
-    ProfScope ps(ARB_PROF_GEMM, 10.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
+    ProfScope ps(ARB_PROF_GEMM, (a.extent ? arb_attn_frac() : 1.0) * 10.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
                  rf * 4.0 * double(a.B) * a.h * a.S * (7.0 * a.dk + 3.0), "attn_bwd_kernel");
     arb_launch(kern, grid, dim3(BWD_THREADS), size_t(BwdSmem::total()), st, tQk, tQm, tKk, tKm, tVk, tDOk, tDOm, tDQ, tDK, tDV, a.mask,
                                                       a.stat_max, a.stat_sum, a.delta, a.S, a.h, a.scale, a.drop, a.dbias_qkv,

@@ -33,10 +33,13 @@ std::mutex g_prof_mu;
 bool g_prof_on = false;
 constexpr size_t kMaxRecs = 1 << 16;
 double g_row_frac = 1.0;
+double g_attn_frac = 1.0;
 }  // namespace
 
 double arb_row_frac() { return g_row_frac; }
 void arb_set_row_frac(double f) { g_row_frac = f; }
+double arb_attn_frac() { return g_attn_frac; }
+void arb_set_attn_frac(double f) { g_attn_frac = f; }
 bool arb_prof_enabled() { return g_prof_on; }
 
 ProfScope::ProfScope(int cls, double work, cudaStream_t s, double bytes, const char* name) : idx(-1), st(s) {

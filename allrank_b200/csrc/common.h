@@ -19,6 +19,10 @@ void arb_count_launch(int n = 1);
 // scorer when per-launch profiling is on; 1.0 otherwise).  Never steers a kernel.
 double arb_row_frac();
 void arb_set_row_frac(double f);
+// Likewise for the fused attention kernels when they stop at the slate extents: sum_b round_up(extent_b, 16)^2 over
+// B * S^2 -- the fraction of the dense S x S score work that belongs to real items (what their flops are counted as).
+double arb_attn_frac();
+void arb_set_attn_frac(double f);
 bool arb_prof_enabled();
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------

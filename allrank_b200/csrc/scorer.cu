@@ -10,6 +10,7 @@
 // the reference's `transpose(1,2).contiguous()` at transformer.py:201 vanishes).  The host sequence contains no
 // synchronisation and no allocation, so a training step can be captured into a CUDA graph by the host layer.
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "attention_fused.h"
@@ -337,6 +338,20 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
   int* kext = reinterpret_cast<int*>(ws + W.kext);
   if (c.n_layers > 0 && W.fused && g_skip_padding)
     ARB_TRY(slate_extents(mask, nullptr, 0, B, S, kext, st));   // once per call, shared by every layer
+  if (c.n_layers > 0 && W.fused && g_skip_padding && arb_prof_enabled()) {
+    // per-launch accounting (bench.py): the attention kernels stop at the extents, so their flops are counted over the
+    // real items -- sum_b round_up(extent_b, 16)^2 of the dense B * S^2 (read back here: profiling only)
+    std::vector<int> he(static_cast<size_t>(B));
+    if (cudaStreamSynchronize(st) != cudaSuccess ||
+        cudaMemcpy(he.data(), kext, size_t(B) * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      arb_set_error("scorer: reading the slate extents failed"); return ARB_E_CUDA;
+    }
+    double sq = 0.0;
+    for (int e : he) { const double r = double((std::max(0, std::min(S, e)) + 15) & ~15); sq += r * r; }
+    arb_set_attn_frac(sq / (double(B) * double(S) * double(S)));
+  } else if (arb_prof_enabled()) {
+    arb_set_attn_frac(1.0);
+  }
   // Packed rows: every kernel below runs over the rows below the slates' extents only (scorer_kernels.cu: pack_plan)
   const bool pack = use_pack(c, S);
   const int* plan = nullptr;
