@@ -10,6 +10,7 @@
 
 #include "block_utils.cuh"
 #include "common.h"
+#include "defaults.h"
 #include "dropout.cuh"
 #include "scorer_kernels.h"
 
@@ -1028,6 +1029,442 @@ static int check_launch() {
 }
 
 
+// ------------------------------------------------------------------------------------------------ rows of 128 / 256
+// "R" layout of the row kernels for the common model widths W = 128 (LPR = 8 lanes per row, 4 rows per warp step)
+// and W = 256 (LPR = 16, 2 rows per step): a lane owns 16 elements of ONE row -- float4 j at column
+// ((lane % LPR) + LPR * j) * 4, so that the LPR lanes of a row read LPR * 16 contiguous bytes per instruction --
+// and a row reduction is log2(LPR) shuffle steps that serve all rows of the step at once (one row per warp needs five
+// steps per row and reduction: ncu put ln_fwd at 75 % issue-active with shuffles and their adds a third of it).
+// Same arithmetic per element as the generic kernels; the summation trees differ.
+template <int LPR>
+__device__ __forceinline__ int r_col(int lane, int j) { return ((lane % LPR) + LPR * j) * 4; }
+template <int LPR>
+__device__ __forceinline__ float r_sum(float v) {
+#pragma unroll
+  for (int off = 1; off < LPR; off <<= 1) v += __shfl_xor_sync(FULL, v, off);
+  return v;
+}
+template <int LPR>
+__device__ __forceinline__ void r_load(const float* __restrict__ row, int lane, float4 (&v)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(row + r_col<LPR>(lane, j));
+}
+template <int LPR>
+__device__ __forceinline__ void r_load_bf16(const uint16_t* __restrict__ row, int lane, float4 (&v)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint2 u = *reinterpret_cast<const uint2*>(row + r_col<LPR>(lane, j));
+    v[j] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+  }
+}
+template <int LPR>
+__device__ __forceinline__ void r_store(float* __restrict__ row, int lane, const float4 (&v)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(row + r_col<LPR>(lane, j)) = v[j];
+}
+template <int LPR>
+__device__ __forceinline__ void r_store_bf16(uint16_t* __restrict__ row, int lane, const float4 (&v)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint2*>(row + r_col<LPR>(lane, j)) = make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
+}
+__device__ __forceinline__ void r_zero(float4 (&v)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int LPR>
+__device__ __forceinline__ void r_drop(float4 (&v)[4], long long row, int lane, const DropSite& site) {
+  constexpr int W = 16 * LPR;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float* e = &v[j].x;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const unsigned long long idx = (unsigned long long)row * W + (r_col<LPR>(lane, j) + t);
+      e[t] = drop_keep(idx, site.seed, site.thresh) ? e[t] * site.scale : 0.0f;
+    }
+  }
+}
+// sum the per-column accumulators of the warp's row groups, then over the block's warps, then into `dst` (atomics)
+template <int LPR>
+__device__ __forceinline__ void r_reduce_columns(float4 (&acc)[4], float (*sh)[16 * LPR + 4], int lane, int wid,
+                                                 float* __restrict__ dst) {
+  constexpr int W = 16 * LPR;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float* e = &acc[j].x;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1) e[t] += __shfl_xor_sync(FULL, e[t], off);
+    }
+  }
+  if (lane < LPR) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(&sh[wid][r_col<LPR>(lane, j)]) = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < ROWS_PER_BLOCK; ++w) t += sh[w][c];
+    atomicAdd(dst + c, t);
+  }
+  __syncthreads();
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_r_kernel(const float* __restrict__ x,
+                                                                      const float* __restrict__ a,
+                                                                      const float* __restrict__ b, float eps,
+                                                                      long long rows, float* __restrict__ y,
+                                                                      float* __restrict__ mean_o,
+                                                                      float* __restrict__ std_o, int torch_mode,
+                                                                      uint16_t* __restrict__ y16,
+                                                                      const int* __restrict__ rows_dev, int steps) {
+  arb_pdl_wait();
+  constexpr int RW = 32 / LPR, W = 16 * LPR;
+  const int lane = threadIdx.x & 31, rg = lane / LPR;
+  const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (RW * steps);
+  if (base >= rows) return;
+  if (rows_dev) { rows = min(rows, (long long)rows_dev[0]); if (base >= rows) return; }
+  float4 ga[4], gb[4], cur[4], nxt[4];
+  r_load<LPR>(a, lane, ga);
+  r_load<LPR>(b, lane, gb);
+  if (base + rg < rows) r_load<LPR>(x + (base + rg) * W, lane, cur); else r_zero(cur);
+#pragma unroll 1
+  for (int s = 0; s < steps; ++s) {
+    if (base + (long long)s * RW >= rows) break;
+    const long long row = base + (long long)s * RW + rg;
+    if (s + 1 < steps) { if (row + RW < rows) r_load<LPR>(x + (row + RW) * W, lane, nxt); else r_zero(nxt); }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sum += cur[j].x + cur[j].y + cur[j].z + cur[j].w;
+    const float m = r_sum<LPR>(sum) / float(W);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d0 = cur[j].x - m, d1 = cur[j].y - m, d2 = cur[j].z - m, d3 = cur[j].w - m;
+      ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    ss = r_sum<LPR>(ss);
+    // (torch_mode and the reciprocal: see ln_fwd_kernel)
+    const float sdq = torch_mode ? sqrtf(ss / float(W) + eps) : sqrtf(ss / float(W - 1));
+    const float rinv = 1.0f / (torch_mode ? sdq : sdq + eps);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cur[j].x = ga[j].x * (cur[j].x - m) * rinv + gb[j].x;
+      cur[j].y = ga[j].y * (cur[j].y - m) * rinv + gb[j].y;
+      cur[j].z = ga[j].z * (cur[j].z - m) * rinv + gb[j].z;
+      cur[j].w = ga[j].w * (cur[j].w - m) * rinv + gb[j].w;
+    }
+    if (row < rows) {
+      if (y16) r_store_bf16<LPR>(y16 + row * W, lane, cur);
+      else r_store<LPR>(y + row * W, lane, cur);
+      if (lane % LPR == 0) { mean_o[row] = m; std_o[row] = sdq; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32, 2) ln_bwd_r_kernel(
+    const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ a,
+    const float* __restrict__ mean_i, const float* __restrict__ std_i, float eps, const float* __restrict__ dres,
+    long long rows, int steps, float* __restrict__ dx, float* __restrict__ grad_a, float* __restrict__ grad_b,
+    float* __restrict__ dx_masked, DropSite site, float* __restrict__ colsum_out, int torch_mode,
+    const uint16_t* __restrict__ dy16_in, uint16_t* __restrict__ dy16_out, const int* __restrict__ rows_dev) {
+  arb_pdl_wait();
+  constexpr int RW = 32 / LPR, W = 16 * LPR;
+  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);
+  if ((long long)blockIdx.x * ROWS_PER_BLOCK * RW * steps >= rows) return;      // whole block beyond the live rows
+  __shared__ float sh[ROWS_PER_BLOCK][W + 4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, rg = lane / LPR;
+  float4 ga[4], acc_a[4], acc_b[4], acc_c[4];
+  r_load<LPR>(a, lane, ga);
+  r_zero(acc_a); r_zero(acc_b); r_zero(acc_c);
+  const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * (RW * steps);
+#pragma unroll 1
+  for (int s = 0; s < steps; ++s) {
+    if (base + (long long)s * RW >= rows) break;
+    const long long row = base + (long long)s * RW + rg;
+    const bool ok = row < rows;
+    float4 g[4], xr[4], res[4];
+    float mean = 0.f, sd = 1.f;
+    r_zero(g); r_zero(xr); r_zero(res);
+    if (ok) {
+      if (dy16_in) r_load_bf16<LPR>(dy16_in + row * W, lane, g); else r_load<LPR>(dy + row * W, lane, g);
+      r_load<LPR>(x + row * W, lane, xr);
+      if (dres) r_load<LPR>(dres + row * W, lane, res);
+      mean = mean_i[row]; sd = std_i[row];
+    }
+    const float r = 1.0f / (sd + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float* gv = &g[j].x;
+      float* xv = &xr[j].x;
+      const float* av = &ga[j].x;
+      float* aa = &acc_a[j].x;
+      float* ab = &acc_b[j].x;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float cc = ok ? xv[t] - mean : 0.f;
+        const float dyv = gv[t];
+        aa[t] += dyv * cc * r;     // dy * xhat
+        ab[t] += dyv;
+        const float dxh = dyv * av[t];
+        gv[t] = dxh;
+        xv[t] = cc;
+        s1 += dxh;
+        s2 += dxh * cc;
+      }
+    }
+    s1 = r_sum<LPR>(s1);
+    s2 = r_sum<LPR>(s2);
+    const float m1 = s1 / float(W);
+    const float coef = torch_mode ? r * r * r * s2 / float(W) : ((sd > 0.f) ? r * r * s2 / (float(W - 1) * sd) : 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float* gv = &g[j].x;
+      const float* xv = &xr[j].x;
+      const float* rv = &res[j].x;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float o = r * (gv[t] - m1) - coef * xv[t];
+        if (dres) o += rv[t];
+        gv[t] = o;
+      }
+    }
+    if (ok) {
+      r_store<LPR>(dx + row * W, lane, g);
+      if (dx_masked) {   // the same gradient through the dropout of the sublayer below (mask regenerated)
+        r_drop<LPR>(g, row, lane, site);
+        r_store<LPR>(dx_masked + row * W, lane, g);
+      }
+      if (dy16_out) r_store_bf16<LPR>(dy16_out + row * W, lane, g);
+      if (colsum_out) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc_c[j].x += g[j].x; acc_c[j].y += g[j].y; acc_c[j].z += g[j].z; acc_c[j].w += g[j].w; }
+      }
+    }
+  }
+  r_reduce_columns<LPR>(acc_a, sh, lane, wid, grad_a);
+  r_reduce_columns<LPR>(acc_b, sh, lane, wid, grad_b);
+  if (colsum_out) r_reduce_columns<LPR>(acc_c, sh, lane, wid, colsum_out);
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_r_kernel(
+    const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b, float eps,
+    const float* __restrict__ w, const float* __restrict__ wb, int has_norm, int act, long long rows,
+    float* __restrict__ score, float* __restrict__ mean_o, float* __restrict__ std_o,
+    const int* __restrict__ rows_dev, const int* __restrict__ rowmap, int steps) {
+  arb_pdl_wait();
+  constexpr int RW = 32 / LPR, W = 16 * LPR;
+  const int lane = threadIdx.x & 31, rg = lane / LPR;
+  const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (RW * steps);
+  if (base >= rows) return;
+  if (rows_dev) { rows = min(rows, (long long)rows_dev[0]); if (base >= rows) return; }
+  float4 ga[4], gb[4], gw[4], cur[4], nxt[4];
+  r_load<LPR>(w, lane, gw);
+  if (has_norm) { r_load<LPR>(a, lane, ga); r_load<LPR>(b, lane, gb); } else { r_zero(ga); r_zero(gb); }
+  const float bias = wb[0];
+  long long at = -1, at_n = -1;
+  if (base + rg < rows) {
+    r_load<LPR>(x + (base + rg) * W, lane, cur);
+    at = rowmap ? (long long)rowmap[base + rg] : base + rg;
+  } else {
+    r_zero(cur);
+  }
+#pragma unroll 1
+  for (int s = 0; s < steps; ++s) {
+    if (base + (long long)s * RW >= rows) break;
+    const long long row = base + (long long)s * RW + rg;
+    if (s + 1 < steps) {
+      at_n = -1;
+      if (row + RW < rows) {
+        r_load<LPR>(x + (row + RW) * W, lane, nxt);
+        at_n = rowmap ? (long long)rowmap[row + RW] : row + RW;
+      } else {
+        r_zero(nxt);
+      }
+    }
+    float m = 0.f, sdv = 0.f;
+    if (has_norm) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sum += cur[j].x + cur[j].y + cur[j].z + cur[j].w;
+      m = r_sum<LPR>(sum) / float(W);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d0 = cur[j].x - m, d1 = cur[j].y - m, d2 = cur[j].z - m, d3 = cur[j].w - m;
+        ss += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      }
+      sdv = sqrtf(r_sum<LPR>(ss) / float(W - 1));
+      const float rinv = 1.0f / (sdv + eps);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cur[j].x = ga[j].x * (cur[j].x - m) * rinv + gb[j].x;
+        cur[j].y = ga[j].y * (cur[j].y - m) * rinv + gb[j].y;
+        cur[j].z = ga[j].z * (cur[j].z - m) * rinv + gb[j].z;
+        cur[j].w = ga[j].w * (cur[j].w - m) * rinv + gb[j].w;
+      }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dot += cur[j].x * gw[j].x + cur[j].y * gw[j].y + cur[j].z * gw[j].z + cur[j].w * gw[j].w;
+    dot = r_sum<LPR>(dot);
+    if (row < rows && lane % LPR == 0) {
+      // packed rows: the score goes to the item's place in the [B, S] tensor (alignment rows have none)
+      if (at >= 0) score[at] = act_fwd(dot + bias, act);
+      if (has_norm && mean_o) { mean_o[row] = m; std_o[row] = sdv; }
+    }
+    at = at_n;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32, 2) head_bwd_r_kernel(
+    const float* __restrict__ dscore, const float* __restrict__ score, const float* __restrict__ x,
+    const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean_i,
+    const float* __restrict__ std_i, float eps, const float* __restrict__ w, int has_norm, int act, long long rows,
+    int steps, float* __restrict__ dx, float* __restrict__ grad_a, float* __restrict__ grad_b,
+    float* __restrict__ grad_w, float* __restrict__ grad_wb, float* __restrict__ dx_masked, DropSite site,
+    float* __restrict__ colsum_out, uint16_t* __restrict__ dy16_out, const int* __restrict__ rows_dev,
+    const int* __restrict__ rowmap) {
+  arb_pdl_wait();
+  constexpr int RW = 32 / LPR, W = 16 * LPR;
+  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);
+  if ((long long)blockIdx.x * ROWS_PER_BLOCK * RW * steps >= rows) return;
+  __shared__ float sh[ROWS_PER_BLOCK][W + 4];
+  __shared__ float shb[ROWS_PER_BLOCK];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, rg = lane / LPR;
+  float4 ga[4], gb[4], gw[4], acc_a[4], acc_b[4], acc_w[4], acc_c[4];
+  r_load<LPR>(w, lane, gw);
+  if (has_norm) { r_load<LPR>(a, lane, ga); r_load<LPR>(b, lane, gb); } else { r_zero(ga); r_zero(gb); }
+  r_zero(acc_a); r_zero(acc_b); r_zero(acc_w); r_zero(acc_c);
+  float acc_wb = 0.f;
+  const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + wid) * (RW * steps);
+#pragma unroll 1
+  for (int s = 0; s < steps; ++s) {
+    if (base + (long long)s * RW >= rows) break;
+    const long long row = base + (long long)s * RW + rg;
+    const bool ok = row < rows;
+    float4 xr[4], g[4];
+    r_zero(xr);
+    long long at = -1;
+    float mean = 0.f, sd = 1.f;
+    if (ok) {
+      r_load<LPR>(x + row * W, lane, xr);
+      // packed rows: score and its gradient sit at the item's place in the [B, S] tensors; alignment rows have neither
+      at = rowmap ? (long long)rowmap[row] : row;
+      if (has_norm) { mean = mean_i[row]; sd = std_i[row]; }
+    }
+    const float out = at >= 0 ? score[at] : 0.f;
+    float z = 0.f;
+    if (act == ARB_ACT_RELU) z = out;   // relu: out > 0 <=> z > 0
+    const float dz = at >= 0 ? dscore[at] * act_bwd(out, z, act) : 0.f;
+    if (lane % LPR == 0) acc_wb += dz;
+    if (!has_norm) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* xv = &xr[j].x;
+        const float* wv = &gw[j].x;
+        float* gv = &g[j].x;
+        float* aw = &acc_w[j].x;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { gv[t] = dz * wv[t]; aw[t] += dz * xv[t]; }
+      }
+    } else {
+      const float r = 1.0f / (sd + eps);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float* xv = &xr[j].x;
+        const float* wv = &gw[j].x;
+        const float* av = &ga[j].x;
+        const float* bv = &gb[j].x;
+        float* gv = &g[j].x;
+        float* aa = &acc_a[j].x;
+        float* ab = &acc_b[j].x;
+        float* aw = &acc_w[j].x;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float cc = ok ? xv[t] - mean : 0.f;
+          const float xh = cc * r;
+          const float xf = av[t] * xh + bv[t];     // the final norm's output, recomputed
+          const float dyv = dz * wv[t];            // d loss / d xf
+          aw[t] += dz * xf;
+          aa[t] += dyv * xh;
+          ab[t] += dyv;
+          const float dxh = dyv * av[t];
+          gv[t] = dxh;
+          xv[t] = cc;
+          s1 += dxh;
+          s2 += dxh * cc;
+        }
+      }
+      s1 = r_sum<LPR>(s1);
+      s2 = r_sum<LPR>(s2);
+      const float m1 = s1 / float(W);
+      const float coef = (sd > 0.f) ? r * r * s2 / (float(W - 1) * sd) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float* gv = &g[j].x;
+        const float* xv = &xr[j].x;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) gv[t] = r * (gv[t] - m1) - coef * xv[t];
+      }
+    }
+    if (ok) {
+      r_store<LPR>(dx + row * W, lane, g);
+      if (dx_masked) { r_drop<LPR>(g, row, lane, site); r_store<LPR>(dx_masked + row * W, lane, g); }
+      if (dy16_out) r_store_bf16<LPR>(dy16_out + row * W, lane, g);
+      if (colsum_out) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc_c[j].x += g[j].x; acc_c[j].y += g[j].y; acc_c[j].z += g[j].z; acc_c[j].w += g[j].w; }
+      }
+    }
+  }
+  if (has_norm) {
+    r_reduce_columns<LPR>(acc_a, sh, lane, wid, grad_a);
+    r_reduce_columns<LPR>(acc_b, sh, lane, wid, grad_b);
+  }
+  r_reduce_columns<LPR>(acc_w, sh, lane, wid, grad_w);
+  if (colsum_out) r_reduce_columns<LPR>(acc_c, sh, lane, wid, colsum_out);
+  acc_wb = warp_sum(acc_wb);
+  if (lane == 0) shb[wid] = acc_wb;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int ww = 0; ww < ROWS_PER_BLOCK; ++ww) t += shb[ww];
+    atomicAdd(grad_wb, t);
+  }
+}
+
+// Which row kernels use the layout above for W = 128 / 256 (else the generic one-row-per-warp kernels): bit 0 ln_fwd,
+// bit 1 ln_bwd, bit 2 head_fwd, bit 3 head_bwd.  ARB_ROW_LAYOUT overrides (measurement knob).
+enum { R_LN_FWD = 1, R_LN_BWD = 2, R_HEAD_FWD = 4, R_HEAD_BWD = 8 };
+static int row_layout_r() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ARB_ROW_LAYOUT"); v = e ? atoi(e) : ARB_DEFAULT_ROW_LAYOUT; }
+  return v;
+}
+static inline int r_lpr(int width, int which) {
+  return ((row_layout_r() & which) && (width == 128 || width == 256)) ? width / 16 : 0;
+}
+// steps per warp of the forward R kernels: 4 (16 / 8 rows per warp) for large launches, 1 for small ones
+static inline int r_fwd_steps(long long rows) { return rows >= (1 << 17) ? 4 : 1; }
+// rows per warp of the backward R kernels (a multiple of 4): the per-warp column reduction at the end costs 2 shuffles
+// per accumulator element, so large launches amortise it over 32 rows; small ones keep every SM busy with 8
+static inline int r_bwd_rows_per_warp(long long rows) { return rows >= (1 << 17) ? 32 : 8; }
+
 // Accounting only (ProfScope): launches over packed rows process arb_row_frac() of the nominal rows.
 static double live_rows(long long rows, const int* rows_dev) { return double(rows) * (rows_dev ? arb_row_frac() : 1.0); }
 
@@ -1135,10 +1572,17 @@ int zero_rows(float* a, int a_pitch, int a_width, int a_from, int a_n, float* b,
 int ln_forward(const float* x, const float* a, const float* b, float eps, long long rows, int width, float* y,
                float* mean, float* sd, cudaStream_t st, int torch_mode, void* y16, const int* rows_dev) {
   if (width % 4) { arb_set_error("LayerNorm width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
+  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * ((y16 ? 6.0 : 8.0) * width + 8), st);
+  if (const int lpr = r_lpr(width, R_LN_FWD)) {      // W = 128 / 256: several rows per warp step (see ln_fwd_r_kernel)
+    const int steps = r_fwd_steps(rows), per_block = ROWS_PER_BLOCK * (32 / lpr) * steps;
+    const unsigned nblk = unsigned((rows + per_block - 1) / per_block);
+    if (lpr == 8) arb_launch(ln_fwd_r_kernel<8>, dim3(nblk), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16), rows_dev, steps);
+    else arb_launch(ln_fwd_r_kernel<16>, dim3(nblk), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16), rows_dev, steps);
+    return check_launch();
+  }
   const int nb = fwd_batches_for(width, rows);
   const int per_block = ROWS_PER_BLOCK * FWD_RPW * nb;
   const unsigned blocks = unsigned((rows + per_block - 1) / per_block);
-  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * ((y16 ? 6.0 : 8.0) * width + 8), st);
   ARB_DISPATCH_NV(width, (arb_launch(ln_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, rows, width, y, mean, sd, torch_mode, static_cast<uint16_t*>(y16), rows_dev, nb)));
   return check_launch();
 }
@@ -1154,6 +1598,13 @@ int ln_backward(const float* dy, const float* x, const float* a, const float* me
   const int rpw = bwd_rows_per_warp();
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * ((dres ? 16.0 : 12.0) * width + 8), st);
+  if (const int lpr = r_lpr(width, R_LN_BWD)) {
+    const int steps = r_bwd_rows_per_warp(rows) / (32 / lpr), per_block = ROWS_PER_BLOCK * (32 / lpr) * steps;
+    const unsigned nblk = unsigned((rows + per_block - 1) / per_block);
+    if (lpr == 8) arb_launch(ln_bwd_r_kernel<8>, dim3(nblk), dim3(ROWS_PER_BLOCK * 32), 0, st, dy, x, a, mean, sd, eps, dres, rows, steps, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode, static_cast<const uint16_t*>(dy16_in), static_cast<uint16_t*>(dy16_out), rows_dev);
+    else arb_launch(ln_bwd_r_kernel<16>, dim3(nblk), dim3(ROWS_PER_BLOCK * 32), 0, st, dy, x, a, mean, sd, eps, dres, rows, steps, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode, static_cast<const uint16_t*>(dy16_in), static_cast<uint16_t*>(dy16_out), rows_dev);
+    return check_launch();
+  }
   ARB_DISPATCH_NV(width, (arb_launch(ln_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dy, x, a, mean, sd, eps, dres, rows, width, rpw, dx, grad_a, grad_b, dx_masked, site, colsum_out, torch_mode, static_cast<const uint16_t*>(dy16_in), static_cast<uint16_t*>(dy16_out), rows_dev)));
   return check_launch();
 }
@@ -1238,10 +1689,17 @@ int head_forward(const float* x, const float* a, const float* b, float eps, cons
                  int has_norm, int act, long long rows, int width, float* score, float* mean, float* sd,
                  cudaStream_t st, const int* rows_dev, const int* rowmap) {
   if (width % 4) { arb_set_error("model width must be a multiple of 4"); return ARB_E_UNSUPPORTED; }
+  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * (4.0 * width + 12), st);
+  if (const int lpr = r_lpr(width, R_HEAD_FWD)) {
+    const int steps = r_fwd_steps(rows), per_block = ROWS_PER_BLOCK * (32 / lpr) * steps;
+    const unsigned nblk = unsigned((rows + per_block - 1) / per_block);
+    if (lpr == 8) arb_launch(head_fwd_r_kernel<8>, dim3(nblk), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, score, mean, sd, rows_dev, rowmap, steps);
+    else arb_launch(head_fwd_r_kernel<16>, dim3(nblk), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, score, mean, sd, rows_dev, rowmap, steps);
+    return check_launch();
+  }
   const int nb = fwd_batches_for(width, rows);
   const int per_block = ROWS_PER_BLOCK * FWD_RPW * nb;
   const unsigned blocks = unsigned((rows + per_block - 1) / per_block);
-  ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * (4.0 * width + 12), st);
   ARB_DISPATCH_NV(width, (arb_launch(head_fwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, x, a, b, eps, w, wb, has_norm, act, rows, width, score, mean, sd, rows_dev, rowmap, nb)));
   return check_launch();
 }
@@ -1255,6 +1713,13 @@ int head_backward(const float* dscore, const float* score, const float* x, const
   const int rpw = bwd_rows_per_warp();
   const unsigned blocks = unsigned((rows + ROWS_PER_BLOCK * rpw - 1) / (ROWS_PER_BLOCK * rpw));
   ProfScope ps(ARB_PROF_SCORER_SIMT, live_rows(rows, rows_dev) * (8.0 * width + 16), st);
+  if (const int lpr = r_lpr(width, R_HEAD_BWD)) {
+    const int steps = r_bwd_rows_per_warp(rows) / (32 / lpr), per_block = ROWS_PER_BLOCK * (32 / lpr) * steps;
+    const unsigned nblk = unsigned((rows + per_block - 1) / per_block);
+    if (lpr == 8) arb_launch(head_bwd_r_kernel<8>, dim3(nblk), dim3(ROWS_PER_BLOCK * 32), 0, st, dscore, score, x, a, b, mean, sd, eps, w, has_norm, act, rows, steps, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out, static_cast<uint16_t*>(dy16_out), rows_dev, rowmap);
+    else arb_launch(head_bwd_r_kernel<16>, dim3(nblk), dim3(ROWS_PER_BLOCK * 32), 0, st, dscore, score, x, a, b, mean, sd, eps, w, has_norm, act, rows, steps, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out, static_cast<uint16_t*>(dy16_out), rows_dev, rowmap);
+    return check_launch();
+  }
   ARB_DISPATCH_NV(width, (arb_launch(head_bwd_kernel<NV>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, st, dscore, score, x, a, b, mean, sd, eps, w, wb, has_norm, act, rows, width, rpw, dx, grad_a, grad_b, grad_w, grad_wb, dx_masked, site, colsum_out, static_cast<uint16_t*>(dy16_out), rows_dev, rowmap)));
   return check_launch();
 }
