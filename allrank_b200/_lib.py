@@ -54,12 +54,14 @@ def lib():
             fn.argtypes = args
         _lib = handle
         # A/B switches for measurements (include/allrank_b200.h); the defaults are the measured-fastest settings
-        if os.environ.get("ARB_GEMM_PERSISTENT") in ("0", "1", "2"):
+        if os.environ.get("ARB_GEMM_PERSISTENT") in ("0", "1", "2", "3"):
             handle.arb_set_gemm_persistent(int(os.environ["ARB_GEMM_PERSISTENT"]))
         if os.environ.get("ARB_PDL") in ("0", "1"):
             handle.arb_set_pdl(int(os.environ["ARB_PDL"]))
         if os.environ.get("ARB_ATTN_SKIP_PADDING") in ("0", "1"):
             handle.arb_set_attention_skip_padding(int(os.environ["ARB_ATTN_SKIP_PADDING"]))
+        if os.environ.get("ARB_ATTN_FWD_PERSISTENT") in ("0", "1"):
+            handle.arb_set_attention_fwd_persistent(int(os.environ["ARB_ATTN_FWD_PERSISTENT"]))
         if os.environ.get("ARB_ATTN_BWD_PERSISTENT") in ("0", "1"):
             handle.arb_set_attention_bwd_persistent(int(os.environ["ARB_ATTN_BWD_PERSISTENT"]))
         if os.environ.get("ARB_PACK_ROWS") in ("0", "1"):

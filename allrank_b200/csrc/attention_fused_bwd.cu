@@ -115,7 +115,11 @@ struct BwdSmem {
   static constexpr int N_TILES = 7;
   static constexpr int STAGE_OFF = N_TILES * TILE_BYTES;          // dS^T staging: 4 slabs x [128 key rows][128 B]
   static constexpr int STAGE_BYTES = 4 * TILE_BYTES;
-  static constexpr int STATS_OFF = STAGE_OFF + STAGE_BYTES;       // float2 {nm_q, delta_q} x 128, double-buffered
+  // Output staging: dV -> slab 2, dK -> slab 3 of the dS^T staging (idle between the previous dQ product and this
+  // iteration's half-b staging), dQ -> one extra tile.  Slabs 0 / 1 are NOT used, so the half-a staging that follows
+  // an epilogue does not have to wait for the TMA stores to drain.
+  static constexpr int OUT_OFF = STAGE_OFF + STAGE_BYTES;
+  static constexpr int STATS_OFF = OUT_OFF + TILE_BYTES;          // float2 {nm_q, delta_q} x 128, double-buffered
   static constexpr int BARS_OFF = STATS_OFF + 2 * 128 * 8;
   static constexpr int total() { return BARS_OFF + 256 + 1024; }
 };
@@ -374,6 +378,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
       ptx::named_bar_sync(1, BWD_COMPUTE);
     };
 
+    bool outputs_pending = false;      // an epilogue's stores / column sums may still be reading the output tiles
+    auto out_tile = [&](int which) { return which < 2 ? stage + (2 + which) * TILE_BYTES : smem + BwdSmem::OUT_OFF; };
     // Outputs of iteration `e` that became final with it: dV / dK of its key tile after the last query chunk, dQ of
     // its query chunk after the last key tile.  TMEM -> swizzled staging -> TMA store (+ the QKV bias column sums).
     auto epilogue = [&](const BwdIter& e) {
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         if constexpr (OUT16) {
           // bf16 mode: dQ / dK / dV only feed the QKV weight- and input-gradient products: dense bfloat16 rows of
           // 32 columns (64 bytes), unswizzled tensor maps
-          uint4* orow = reinterpret_cast<uint4*>(stage + sub * TILE_BYTES + row * 64);
+          uint4* orow = reinterpret_cast<uint4*>(out_tile(sub) + row * 64);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint4 pk;
@@ -401,7 +407,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
             orow[k] = pk;
           }
         } else {
-          uint8_t* orow = stage + sub * TILE_BYTES + row * 128;
+          uint8_t* orow = out_tile(sub) + row * 128;
 #pragma unroll
           for (int piece = 0; piece < 8; ++piece) {
             float4 o;
@@ -422,21 +428,21 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           if (last_qc) {
             const int n16 = (min(128, e.ext16 - 128 * e_jt) + 15) >> 4;
             for (int i = 0; i < n16; ++i) {
-              ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES + i * BOX, 0, e.row_base + 128 * e_jt + 16 * i, e.head, 0);
-              ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES + i * BOX, 0, e.row_base + 128 * e_jt + 16 * i, e.head, 0);
+              ptx::tma_store_4d(&tmDV, out_tile(0) + i * BOX, 0, e.row_base + 128 * e_jt + 16 * i, e.head, 0);
+              ptx::tma_store_4d(&tmDK, out_tile(1) + i * BOX, 0, e.row_base + 128 * e_jt + 16 * i, e.head, 0);
             }
           }
           if (last_jt) {
             const int n16 = (min(128, e.ext16 - 128 * e_qc) + 15) >> 4;
             for (int i = 0; i < n16; ++i)
-              ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES + i * BOX, 0, e.row_base + 128 * e_qc + 16 * i, e.head, 0);
+              ptx::tma_store_4d(&tmDQ, out_tile(2) + i * BOX, 0, e.row_base + 128 * e_qc + 16 * i, e.head, 0);
           }
         } else {
           if (last_qc) {
-            ptx::tma_store_4d(&tmDV, stage + 0 * TILE_BYTES, 0, 128 * e_jt, e.head, e.b);
-            ptx::tma_store_4d(&tmDK, stage + 1 * TILE_BYTES, 0, 128 * e_jt, e.head, e.b);
+            ptx::tma_store_4d(&tmDV, out_tile(0), 0, 128 * e_jt, e.head, e.b);
+            ptx::tma_store_4d(&tmDK, out_tile(1), 0, 128 * e_jt, e.head, e.b);
           }
-          if (last_jt) ptx::tma_store_4d(&tmDQ, stage + 2 * TILE_BYTES, 0, 128 * e_qc, e.head, e.b);
+          if (last_jt) ptx::tma_store_4d(&tmDQ, out_tile(2), 0, 128 * e_qc, e.head, e.b);
         }
         ptx::tma_store_commit();
       }
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         const bool live = ((which < 2) ? last_qc : last_jt) && cc < DK;
         float t = 0.f;
         if (live) {
-          const uint8_t* tl = stage + which * TILE_BYTES;
+          const uint8_t* tl = out_tile(which);
 #pragma unroll 8
           for (int r = 32 * seg; r < 32 * seg + 32; ++r) {
             if constexpr (OUT16) t += __uint_as_float(uint32_t(*reinterpret_cast<const uint16_t*>(tl + r * 64 + cc * 2)) << 16);
@@ -460,8 +466,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         if (live && seg == 0)
           atomicAdd(dbias_qkv + (which == 0 ? 2 * d_model : (which == 1 ? d_model : 0)) + e.head * DK + cc, t);
       }
-      if (ct == 0) ptx::tma_store_wait_read();      // the staging slabs are rewritten right after this
-      ptx::named_bar_sync(1, BWD_COMPUTE);  // column sums read + TMA reads finished before anyone overwrites the slabs
+      // The stores drain behind the half-a staging (slabs 0 / 1) and arithmetic that follow; drain_outputs() is called
+      // before anything writes slabs 2 / 3 or the dQ tile again.
+      outputs_pending = true;
+    };
+    // the output tiles may be rewritten: the TMA stores have read them, every thread has finished its column sums
+    auto drain_outputs = [&]() {
+      if (!outputs_pending) return;
+      if (ct == 0) ptx::tma_store_wait_read();
+      ptx::named_bar_sync(1, BWD_COMPUTE);
+      outputs_pending = false;
     };
 
     BwdIter c, n, prev;
@@ -495,6 +509,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
         if (hf == 1 && !c.half_b_live()) {
           // none of these 64 queries contributes: their dS^T columns are staged as zeros for the dQ product (its rows
           // for them are then exactly zero) and the dV / dK products of the half are not issued
+          drain_outputs();
           uint8_t* zrow = stage + (col0 >> 5) * TILE_BYTES + row * 128;
           const int z0 = (col0 & 31) >> 2;
 #pragma unroll
@@ -537,8 +552,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_kernel(
           ptx::mbar_wait(mma_bar, (g - 1) & 1);
           ptx::tc_fence_after();
           epilogue(prev);
-          if (!packed && c.jt == 0 && c.qc == 0 && c.n_kt < n_full) zero_fill(c);   // a new item's skipped tiles
+          if (!packed && c.jt == 0 && c.qc == 0 && c.n_kt < n_full) { drain_outputs(); zero_fill(c); }   // a new item's skipped tiles
         }
+        if (hf == 1) drain_outputs();      // this half stages into slabs 2 / 3
         // dS^T also goes to shared memory as the MN-major A operand of dQ: slab = 32-query group, row = key
         uint8_t* srow = stage + (col0 >> 5) * TILE_BYTES + row * 128;
         const int p0 = (col0 & 31) >> 2;                // first 16-byte piece of these 16 columns in the slab row

@@ -870,9 +870,11 @@ static int launch_t(const GemmDesc& d, const CUtensorMap& tA, const CUtensorMap&
   // against 0.85; the K128 +res projection ties).  (Giving the aux tile a shared-memory buffer of its own, at the price
   // of one ring stage, measured slower on every shape: 19.17 against 18.63 ms per cfg2 step -- not kept.)
   const bool has_aux_tile = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
+  // Mode 3 (measurement): as 2, but the short-K products with an aux tile go to the persistent kernel too (under packed
+  // rows half of a one-tile grid are CTAs of dead tiles that only exit; the persistent kernel has none).
   const bool pick = !(A_MN == 1 && B_MN == 1) && !(p.flags & EPI_ATOMIC) && d.nb2 == 1 && d.nb3 == 1 &&
-                    (d.K >= 256 || !has_aux_tile);
-  if (g_persistent == 1 || (g_persistent == 2 && pick))
+                    (d.K >= 256 || !has_aux_tile || g_persistent == 3);
+  if (g_persistent == 1 || (g_persistent >= 2 && pick))
     return launch_persistent_t<BLOCK_N, A_MN, B_MN>(d, tA, tB, tC, tX, p, grid, st);
   // dropout epilogue is a separate instantiation (forward linears only) so the common path carries no mask code;
   // ring depth: 4 stages for the long split-K loops of the weight gradients (1 CTA/SM), 3 for K >= 256
