@@ -484,6 +484,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
       sc += nsteps;
       ptx::named_bar_sync(1, ATT2_SOFTMAX);       // every thread has read the combined maxima: the exchange area is free
       xch_sum[sub * 128 + row] = sum;
+      // (the previous item's output store has long left the staging tile: its issuer confirms that here, in front of a
+      // barrier everybody passes anyway, instead of waiting right behind the store)
+      if (threadIdx.x == 64) ptx::tma_store_wait_read();
       ptx::named_bar_sync(1, ATT2_SOFTMAX);
       sum = xch_sum[row] + xch_sum[128 + row];
       if (sub == 0 && qidx < S) {
@@ -538,9 +541,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
           ptx::tma_store_4d(&tmO, o_s, 0, c.m0, c.head, c.b);
         }
         ptx::tma_store_commit();
-        ptx::tma_store_wait_read();               // (the staging tile is rewritten by the next item's epilogue)
       }
     }
+    if (threadIdx.x == 64) ptx::tma_store_wait_read();    // the last store must have read the tile before the CTA leaves
     ptx::tc_fence_before();
   }
   __syncthreads();
