@@ -333,27 +333,25 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
   arb_pdl_wait();
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  // ===================== TMA producer (warp 0, lane 0) =====================
+  // K and V arrive as 128-key boxes: only the chunks that hold keys below the extent are fetched
+  auto issue_loads = [&](const FwdItem& x) {
+    const int bc = packed ? 0 : x.b;
+    ptx::mbar_expect_tx(load_bar, L::Q_BYTES + x.nkc * 2 * (128 * 128));
+    ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, x.row_base + x.m0, x.head, bc);
+    for (int kc = 0; kc < x.nkc; ++kc) {
+      ptx::tma_load_4d(k_s + kc * 16384, &tmK, load_bar, 0, x.row_base + 128 * kc, x.head, bc);
+      ptx::tma_load_4d(v_s + kc * 16384, &tmV, load_bar, 0, x.row_base + 128 * kc, x.head, bc);
+    }
+  };
+  FwdItem pc;
+  pc.item = blockIdx.x;
+  bool p_ok = false;
+  if (warp == 0 && lane == 0) {
     // The first item's loads go out before the block-wide barrier below -- the thread that initialised the barriers
     // needs nobody else -- so that they run behind the TMEM allocation instead of after it.
-    if (lane == 0) {
-      FwdItem c;
-      c.item = blockIdx.x;
-      bool ok = walk.seek(c);
-      for (uint32_t k = 0; ok; ++k, ok = walk.next(c)) {
-        // Q / K / V are read by the item's products only: free again when its last product has completed
-        if (k > 0) ptx::mbar_wait(o_bar, (k - 1) & 1);
-        const int bc = packed ? 0 : c.b;
-        // K and V arrive as 128-key boxes: only the chunks that hold keys below the extent are fetched
-        ptx::mbar_expect_tx(load_bar, L::Q_BYTES + c.nkc * 2 * (128 * 128));
-        ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, c.row_base + c.m0, c.head, bc);
-        for (int kc = 0; kc < c.nkc; ++kc) {
-          ptx::tma_load_4d(k_s + kc * 16384, &tmK, load_bar, 0, c.row_base + 128 * kc, c.head, bc);
-          ptx::tma_load_4d(v_s + kc * 16384, &tmV, load_bar, 0, c.row_base + 128 * kc, c.head, bc);
-        }
-      }
-    }
+    p_ok = walk.seek(pc);
+    if (p_ok) issue_loads(pc);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -362,7 +360,15 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
 
-  if (warp == 1) {
+  if (warp == 0) {
+    if (lane == 0 && p_ok) {
+      // Q / K / V are read by an item's products only: free again when its last product has completed
+      for (uint32_t k = 1; walk.next(pc); ++k) {
+        ptx::mbar_wait(o_bar, (k - 1) & 1);
+        issue_loads(pc);
+      }
+    }
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr int KSTEPS = (DK + 7) / 8;
