@@ -60,8 +60,6 @@ def lib():
             handle.arb_set_pdl(int(os.environ["ARB_PDL"]))
         if os.environ.get("ARB_ATTN_SKIP_PADDING") in ("0", "1"):
             handle.arb_set_attention_skip_padding(int(os.environ["ARB_ATTN_SKIP_PADDING"]))
-        if os.environ.get("ARB_ATTN_FWD_PERSISTENT") in ("0", "1"):
-            handle.arb_set_attention_fwd_persistent(int(os.environ["ARB_ATTN_FWD_PERSISTENT"]))
         if os.environ.get("ARB_ATTN_BWD_PERSISTENT") in ("0", "1"):
             handle.arb_set_attention_bwd_persistent(int(os.environ["ARB_ATTN_BWD_PERSISTENT"]))
         if os.environ.get("ARB_PACK_ROWS") in ("0", "1"):

@@ -22,7 +22,6 @@
 
 #include "attention_fused.h"
 #include "common.h"
-#include "defaults.h"
 #include "sm100_ptx.cuh"
 
 namespace arb {
@@ -50,7 +49,7 @@ struct AttFwdSmem {
   static constexpr int K_BYTES = NKB * 256 * 128;       // [kb][256 rows][128 B]
   static constexpr int V_BYTES = NKB * 256 * 128;       // [slab][256 key rows][128 B]
   static constexpr int O_BYTES = NKB * 128 * 128;       // staging [slab][128 rows][128 B]
-  static constexpr int total() { return Q_BYTES + K_BYTES + V_BYTES + O_BYTES + 1024 + 256 + 1024; }   // + softmax exchange area
+  static constexpr int total() { return Q_BYTES + K_BYTES + V_BYTES + O_BYTES + 256 + 1024; }
 };
 
 template <int DK, bool DROP>
@@ -63,8 +62,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
                                                                   float* __restrict__ stat_sum, int S, int n_heads,
                                                                   float scale_log2e, DropSite drop,
                                                                   const int* __restrict__ extent,
-                                                                  const int* __restrict__ pack_off, int n_items) {
-  (void)extent; (void)pack_off; (void)n_items;   // the single-pass kernel always covers the whole (dense) slate
+                                                                  const int* __restrict__ pack_off) {
+  (void)extent; (void)pack_off;   // the single-pass kernel always covers the whole (dense) slate
   using L = AttFwdSmem<DK>;
   constexpr int NKB = L::NKB;
   extern __shared__ uint8_t smem_dyn[];
@@ -242,47 +241,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
 // allocation, i.e. one CTA per SM, and is latency-bound at 7 % tensor pipe).  Here the score tile is produced in
 // 128-key chunks into a 128-column TMEM window, twice: pass A only takes the row maximum, pass B recomputes the chunk
 // (K = dk, a handful of MMAs), exponentiates against the final maximum, writes P in place and accumulates O += P V.
-// TMEM: S chunk [0,128) + O [128,128+DK) -> 256 columns; shared memory 98 KB -> two co-resident CTAs overlap each
+// TMEM: S chunk [0,128) + O [128,128+DK) -> 256 columns; shared memory 96 KB -> two co-resident CTAs overlap each
 // other's load / MMA / softmax phases.  Head width <= 32.  Eight softmax warps per CTA: a warp may only touch the 32
 // TMEM lanes of its quadrant, so two warps share each quadrant and split every 32-key chunk 16 / 16; the two partial
 // row maxima (after pass A) and row sums (after pass B) are combined through shared memory.
-//
-// A CTA walks many (slate, head, 128-query tile) items -- item0, item0 + gridDim.x, ... (grid = two CTAs per SM, or
-// one CTA per item with arb_set_attention_fwd_persistent(0)): barrier phases run on across items, the producer
-// fetches the next item's Q / K / V as soon as the last product of the current one has read its tiles -- behind the
-// output epilogue -- and nothing is set up or torn down per item (a CTA per item spent about a third of its 8 us on
-// block scheduling, barrier / TMEM set-up, the first loads and the output drain).
-struct FwdItem {
-  int item, b, head, m0, kext, S16, S8, nkc, row_base;
-};
-struct FwdWalk {
-  int n_items, stride, n_heads, n_qt, S;
-  const int* extent;
-  const int* pack_off;
-  __device__ __forceinline__ bool seek(FwdItem& it) const {
-    for (; it.item < n_items; it.item += stride) {
-      const int qt = it.item % n_qt, rest = it.item / n_qt;
-      it.head = rest % n_heads;
-      it.b = rest / n_heads;
-      it.m0 = 128 * qt;
-      const int e = extent ? extent[it.b] : S;
-      // packed rows: a tile without packed query rows (or an empty slate) is no work
-      if (pack_off && it.m0 >= ((e + 15) & ~15)) continue;
-      // keys at or beyond the slate's extent are all masked (probability exactly 0): the score / P V products, the
-      // softmax loop and the K / V loads stop there.  At least one key column group is always processed, so an
-      // all-padded slate still produces the reference's NaN rows (dense layout).
-      it.kext = max(1, min(S, e));
-      it.S16 = (it.kext + 15) & ~15;
-      it.S8 = (it.kext + 7) & ~7;
-      it.nkc = (it.S16 + 127) / 128;          // key chunks
-      it.row_base = pack_off ? pack_off[it.b] : 0;
-      return true;
-    }
-    return false;
-  }
-  __device__ __forceinline__ bool next(FwdItem& it) const { it.item += stride; return seek(it); }
-};
-
 template <int DK, bool DROP, bool OUT16 = false>
 __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                    const __grid_constant__ CUtensorMap tmK,
@@ -293,7 +255,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
                                                                    float* __restrict__ stat_sum, int S, int n_heads,
                                                                    float scale_log2e, DropSite drop,
                                                                    const int* __restrict__ extent,
-                                                                   const int* __restrict__ pack_off, int n_items) {
+                                                                   const int* __restrict__ pack_off) {
   static_assert(DK <= 32, "two-pass forward kernel: head width <= 32");
   using L = AttFwdSmem<DK>;
   extern __shared__ uint8_t smem_dyn[];
@@ -302,24 +264,25 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   uint8_t* k_s = q_s + L::Q_BYTES;
   uint8_t* v_s = k_s + L::K_BYTES;
   uint8_t* o_s = v_s + L::V_BYTES;
-  float* xch = reinterpret_cast<float*>(o_s + L::O_BYTES);     // [2][128] partial row maxima / sums of the two warps of a quadrant
-  uint64_t* bars = reinterpret_cast<uint64_t*>(o_s + L::O_BYTES + 1024);
-  uint64_t* load_bar = bars;        // Q / K / V of an item landed                          (one phase per item)
-  uint64_t* s_bar = bars + 1;       // a score chunk is complete                             (one phase per step of the stream)
-  uint64_t* t_bar = bars + 2;       // the 256 softmax threads are done with the chunk       (one phase per step)
-  uint64_t* o_bar = bars + 3;       // O complete = every product of the item has finished   (one phase per item)
-  uint64_t* e_bar = bars + 4;       // the softmax threads have read O out of TMEM            (one phase per item)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(o_s + L::O_BYTES);
+  uint64_t* load_bar = bars;
+  uint64_t* s_bar = bars + 1;       // a score chunk is complete            (one phase per step)
+  uint64_t* t_bar = bars + 2;       // the 256 softmax threads are done with the chunk (one phase per step)
+  uint64_t* o_bar = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   uint32_t* mask_bits = tmem_slot + 2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
   // Packed rows (pack_off != nullptr): the activations hold only the first round_up(extent, 16) rows of every slate,
   // slate b starting at row pack_off[b] of one long [rows, h, dk] tensor (TMA coordinates (.., row, head, 0)).  Boxes
   // that overrun the slate read the next slates' rows (finite; their keys are masked, their query rows never stored);
   // the output is stored in 16-row boxes that stop at the slate's last packed row.  extent / pack_off were written by
-  // kernels at least two launches upstream.
+  // kernels at least two launches upstream, so they may be read before the PDL wait.
   const bool packed = pack_off != nullptr;
-  const FwdWalk walk{n_items, int(gridDim.x), n_heads, (S + 127) / 128, S, extent, pack_off};
+  const int row_base = packed ? pack_off[b] : 0;
+  const int bc = packed ? 0 : b;
+  if (packed && m0 >= ((extent[b] + 15) & ~15)) return;   // no packed query rows in this tile (or an empty slate)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmO);
@@ -327,31 +290,32 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
     ptx::mbar_init(s_bar, 1);
     ptx::mbar_init(t_bar, ATT2_SOFTMAX);
     ptx::mbar_init(o_bar, 1);
-    ptx::mbar_init(e_bar, ATT2_SOFTMAX);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
   arb_pdl_wait();
-
-  // ===================== TMA producer (warp 0, lane 0) =====================
-  // K and V arrive as 128-key boxes: only the chunks that hold keys below the extent are fetched
-  auto issue_loads = [&](const FwdItem& x) {
-    const int bc = packed ? 0 : x.b;
-    ptx::mbar_expect_tx(load_bar, L::Q_BYTES + x.nkc * 2 * (128 * 128));
-    ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, x.row_base + x.m0, x.head, bc);
-    for (int kc = 0; kc < x.nkc; ++kc) {
-      ptx::tma_load_4d(k_s + kc * 16384, &tmK, load_bar, 0, x.row_base + 128 * kc, x.head, bc);
-      ptx::tma_load_4d(v_s + kc * 16384, &tmV, load_bar, 0, x.row_base + 128 * kc, x.head, bc);
-    }
-  };
-  FwdItem pc;
-  pc.item = blockIdx.x;
-  bool p_ok = false;
+  // keys at or beyond the slate's extent are all masked (probability exactly 0): the score / P V products, the softmax
+  // loop and the K / V loads stop there.  At least one key column group is always processed, so an all-padded slate
+  // still produces the reference's NaN rows.
+  const int kext = extent ? max(1, min(S, extent[b])) : S;
+  const int S16 = (kext + 15) & ~15, S8 = (kext + 7) & ~7;
+  const int nkc = (S16 + 127) / 128;          // key chunks
+  const int nsteps = 1 + nkc;                 // one pass-A step over the whole score row + one pass-B step per chunk
   if (warp == 0 && lane == 0) {
-    // The first item's loads go out before the block-wide barrier below -- the thread that initialised the barriers
-    // needs nobody else -- so that they run behind the TMEM allocation instead of after it.
-    p_ok = walk.seek(pc);
-    if (p_ok) issue_loads(pc);
+    // The loads go out right here -- the thread that initialised the barriers needs nobody else -- so that they run
+    // behind the TMEM allocation, the mask read and the block-wide barrier below instead of after them.
+    // K and V arrive as 128-key boxes: only the chunks that hold keys below the extent are fetched
+    ptx::mbar_expect_tx(load_bar, L::Q_BYTES + nkc * 2 * (128 * 128));
+    ptx::tma_load_4d(q_s, &tmQ, load_bar, 0, row_base + m0, head, bc);
+    for (int kc = 0; kc < nkc; ++kc) {
+      ptx::tma_load_4d(k_s + kc * 16384, &tmK, load_bar, 0, row_base + 128 * kc, head, bc);
+      ptx::tma_load_4d(v_s + kc * 16384, &tmV, load_bar, 0, row_base + 128 * kc, head, bc);
+    }
+  }
+  if (warp >= 2) {      // key mask as 8 words: one key per softmax thread, one ballot per warp
+    const int key = threadIdx.x - 64;
+    const uint32_t w = __ballot_sync(0xffffffffu, key < S && mask[size_t(b) * S + key] == 0);
+    if (lane == 0) mask_bits[warp - 2] = w;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -361,195 +325,155 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
-    if (lane == 0 && p_ok) {
-      // Q / K / V are read by an item's products only: free again when its last product has completed
-      for (uint32_t k = 1; walk.next(pc); ++k) {
-        ptx::mbar_wait(o_bar, (k - 1) & 1);
-        issue_loads(pc);
-      }
-    }
+    // (the producer's loads were issued above)
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
     if (lane == 0) {
+      ptx::mbar_wait(load_bar, 0);
+      ptx::tc_fence_after();
       constexpr int KSTEPS = (DK + 7) / 8;
       const uint32_t qa = ptx::smem_u32(q_s), ka = ptx::smem_u32(k_s), va = ptx::smem_u32(v_s);
       const uint32_t idesc_o = ptx::idesc_tf32(128, DK < 16 ? 16 : DK, 0, 1);
-      FwdItem c;
-      c.item = blockIdx.x;
-      bool ok = walk.seek(c);
-      uint32_t sc = 0;              // steps of the stream so far (phase of s_bar / t_bar)
-      for (uint32_t k = 0; ok; ++k, ok = walk.next(c)) {
-        const int nsteps = 1 + c.nkc;   // one pass-A step over the whole score row + one pass-B step per chunk
-        auto issue_pv = [&](int kc) {
-          const int keys = min(128, c.S8 - 128 * kc);
-          for (int i = 0; i < keys / 8; ++i)
-            ptx::mma_tf32_ts(tmem_O, tmem_S + 8 * i, ptx::smem_desc_sw128<1>(va + kc * 16384 + i * 1024, 256 * 128, 512),
-                             idesc_o, (kc > 0 || i > 0) ? 1u : 0u);
-        };
-        ptx::mbar_wait(load_bar, k & 1);
-        // pass A may spill over the O columns: the softmax threads must have read the previous item's O out
-        if (k > 0) ptx::mbar_wait(e_bar, (k - 1) & 1);
-        ptx::tc_fence_after();
-        // step 0 (pass A): the WHOLE score row block S = Q K^T, N = S16 <= 256 columns, in one issue -- it may spill over
-        // the O columns, which pass B only starts to use after every softmax thread has taken its row maximum
-        {
-          const uint32_t idesc_a = ptx::idesc_tf32(128, c.S16, 0, 0);
-          for (int ks = 0; ks < KSTEPS; ++ks)
-            ptx::mma_tf32_ss(tmem_S, ptx::smem_desc_sw128<2>(qa + ks * 32, 16, 1024),
-                             ptx::smem_desc_sw128<2>(ka + ks * 32, 16, 1024), idesc_a, ks > 0);
-          ptx::mma_commit(s_bar);
-        }
-        // steps 1..nkc (pass B): recompute one 128-key chunk into the 128-column window; the previous chunk's P V runs
-        // first (P sits in the window until then)
-        for (int st = 1; st < nsteps; ++st) {
-          const int kc = st - 1;
-          ptx::mbar_wait(t_bar, (sc + st - 1) & 1);
-          ptx::tc_fence_after();
-          if (kc > 0) issue_pv(kc - 1);
-          const int nc = min(128, c.S16 - 128 * kc);
-          const uint32_t idesc_s = ptx::idesc_tf32(128, nc, 0, 0);
-          for (int ks = 0; ks < KSTEPS; ++ks)
-            ptx::mma_tf32_ss(tmem_S, ptx::smem_desc_sw128<2>(qa + ks * 32, 16, 1024),
-                             ptx::smem_desc_sw128<2>(ka + kc * 16384 + ks * 32, 16, 1024), idesc_s, ks > 0);
-          ptx::mma_commit(s_bar);
-        }
-        ptx::mbar_wait(t_bar, (sc + nsteps - 1) & 1);
-        ptx::tc_fence_after();
-        issue_pv(c.nkc - 1);
-        ptx::mma_commit(o_bar);
-        sc += nsteps;
+      auto issue_pv = [&](int kc) {
+        const int keys = min(128, S8 - 128 * kc);
+        for (int i = 0; i < keys / 8; ++i)
+          ptx::mma_tf32_ts(tmem_O, tmem_S + 8 * i, ptx::smem_desc_sw128<1>(va + kc * 16384 + i * 1024, 256 * 128, 512),
+                           idesc_o, (kc > 0 || i > 0) ? 1u : 0u);
+      };
+      // step 0 (pass A): the WHOLE score row block S = Q K^T, N = S16 <= 256 columns, in one issue -- it may spill over
+      // the O columns, which pass B only starts to use after every softmax thread has taken its row maximum
+      {
+        const uint32_t idesc_a = ptx::idesc_tf32(128, S16, 0, 0);
+        for (int k = 0; k < KSTEPS; ++k)
+          ptx::mma_tf32_ss(tmem_S, ptx::smem_desc_sw128<2>(qa + k * 32, 16, 1024),
+                           ptx::smem_desc_sw128<2>(ka + k * 32, 16, 1024), idesc_a, k > 0);
+        ptx::mma_commit(s_bar);
       }
+      // steps 1..nkc (pass B): recompute one 128-key chunk into the 128-column window; the previous chunk's P V runs
+      // first (P sits in the window until then)
+      for (int st = 1; st < nsteps; ++st) {
+        const int kc = st - 1;
+        ptx::mbar_wait(t_bar, (st - 1) & 1);
+        ptx::tc_fence_after();
+        if (kc > 0) issue_pv(kc - 1);
+        const int nc = min(128, S16 - 128 * kc);
+        const uint32_t idesc_s = ptx::idesc_tf32(128, nc, 0, 0);
+        for (int k = 0; k < KSTEPS; ++k)
+          ptx::mma_tf32_ss(tmem_S, ptx::smem_desc_sw128<2>(qa + k * 32, 16, 1024),
+                           ptx::smem_desc_sw128<2>(ka + kc * 16384 + k * 32, 16, 1024), idesc_s, k > 0);
+        ptx::mma_commit(s_bar);
+      }
+      ptx::mbar_wait(t_bar, (nsteps - 1) & 1);
+      ptx::tc_fence_after();
+      issue_pv(nkc - 1);
+      ptx::mma_commit(o_bar);
     }
-  } else if (warp >= 2) {
-    // ===================== softmax + epilogue (256 threads) =====================
+  } else {
     const int q = warp & 3;                     // TMEM lane quadrant
     const int sub = (warp - 2) >> 2;            // which 16 keys of every 32-key chunk this warp handles
     const int row = 32 * q + lane;
+    const int qidx = m0 + row;
     const uint32_t lane_addr = uint32_t(32 * q) << 16;
-    float* xch_max = xch;                       // [2][128] partial maxima
-    float* xch_sum = xch;                       // [2][128] partial sums (the maxima are dead by then)
-    FwdItem c;
-    c.item = blockIdx.x;
-    bool ok = walk.seek(c);
-    uint32_t sc = 0;
-    for (uint32_t k = 0; ok; ++k, ok = walk.next(c)) {
-      const int nsteps = 1 + c.nkc;
-      const int qidx = c.m0 + row;
-      {   // key mask as 8 words: one key per softmax thread, one ballot per warp (the previous item's words were last
-          // read before its final t_bar arrival, i.e. before this thread got here... by every thread: barrier below)
+    float* xch_max = reinterpret_cast<float*>(o_s);     // [2][128] partial maxima (the O staging is idle until the end)
+    float* xch_sum = reinterpret_cast<float*>(k_s);     // [2][128] partial sums   (K is dead after the last score chunk)
+    float mx = -CUDART_INF_F, sum = 0.f, mxs = 0.f;
+    for (int st = 0; st < nsteps; ++st) {
+      const bool pass_b = st > 0;
+      const int kc = pass_b ? st - 1 : 0;
+      if (st == 1) {                            // pass A done: combine the two partial row maxima
+        xch_max[sub * 128 + row] = mx;
         ptx::named_bar_sync(1, ATT2_SOFTMAX);
-        const int key = threadIdx.x - 64;
-        const uint32_t w = __ballot_sync(0xffffffffu, key < S && mask[size_t(c.b) * S + key] == 0);
-        if (lane == 0) mask_bits[warp - 2] = w;
-        ptx::named_bar_sync(1, ATT2_SOFTMAX);
+        mx = fmaxf(xch_max[row], xch_max[128 + row]);
+        mxs = mx * scale_log2e;
       }
-      float mx = -CUDART_INF_F, sum = 0.f, mxs = 0.f;
-      for (int st = 0; st < nsteps; ++st) {
-        const bool pass_b = st > 0;
-        const int kc = pass_b ? st - 1 : 0;
-        if (st == 1) {                            // pass A done: combine the two partial row maxima
-          xch_max[sub * 128 + row] = mx;
-          ptx::named_bar_sync(1, ATT2_SOFTMAX);
-          mx = fmaxf(xch_max[row], xch_max[128 + row]);
-          mxs = mx * scale_log2e;
-        }
-        ptx::mbar_wait(s_bar, (sc + st) & 1);
-        ptx::tc_fence_after();
-        // pass A walks every 32-key group of the row block, pass B the groups of its chunk
-        const int keys = pass_b ? min(128, c.S8 - 128 * kc) : c.S8;
-        const int nch = (keys + 31) / 32;
-        for (int g = 0; g < nch; ++g) {
-          uint32_t v[16];
-          const int col = 32 * g + 16 * sub;
-          ptx::tmem_ld_32x16(tmem_S + lane_addr + col, v);
-          ptx::tmem_ld_wait();
-          const uint32_t bits = mask_bits[4 * kc + g] >> (16 * sub);
-          if (!pass_b) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (bits & (1u << j)) mx = fmaxf(mx, __uint_as_float(v[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float e = (bits & (1u << j)) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs)) : 0.0f;
-              sum += e;
-              if constexpr (DROP) {
-                const unsigned long long idx =
-                    ((unsigned long long)(c.b * n_heads + c.head) * S + qidx) * (unsigned long long)S + (128 * kc + col + j);
-                e = drop_keep(idx, drop.seed, drop.thresh) ? e * drop.scale : 0.0f;
-              }
-              v[j] = round_tf32(e);
-            }
-            ptx::tmem_st_32x16(tmem_S + lane_addr + col, v);
-          }
-        }
-        if (pass_b) ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(t_bar);
-      }
-      sc += nsteps;
-      ptx::named_bar_sync(1, ATT2_SOFTMAX);       // every thread has read the combined maxima: the exchange area is free
-      xch_sum[sub * 128 + row] = sum;
-      // (the previous item's output store has long left the staging tile: its issuer confirms that here, in front of a
-      // barrier everybody passes anyway, instead of waiting right behind the store)
-      if (threadIdx.x == 64) ptx::tma_store_wait_read();
-      ptx::named_bar_sync(1, ATT2_SOFTMAX);
-      sum = xch_sum[row] + xch_sum[128 + row];
-      if (sub == 0 && qidx < S) {
-        const size_t so = (size_t(c.b) * n_heads + c.head) * S + qidx;
-        stat_max[so] = mx;
-        stat_sum[so] = sum;
-      }
-      const float inv = 1.0f / sum;
-      ptx::mbar_wait(o_bar, k & 1);
+      ptx::mbar_wait(s_bar, st & 1);
       ptx::tc_fence_after();
-      {
-        uint32_t v[16];                           // this warp's 16 of the (up to) 32 output columns
-        ptx::tmem_ld_32x16(tmem_O + lane_addr + 16 * sub, v);
+      // pass A walks every 32-key group of the row block, pass B the groups of its chunk
+      const int keys = pass_b ? min(128, S8 - 128 * kc) : S8;
+      const int nch = (keys + 31) / 32;
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[16];
+        const int col = 32 * c + 16 * sub;
+        ptx::tmem_ld_32x16(tmem_S + lane_addr + col, v);
         ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(e_bar);                  // O is in registers: the next item's pass A may overwrite the columns
-        if constexpr (OUT16) {
-          // bf16 mode: the context only feeds the output projection -- stage it as dense bfloat16 rows (32 columns =
-          // 64 bytes, unswizzled tensor map); this warp's 16 columns are bytes [32 sub, 32 sub + 32)
-          uint4* dst = reinterpret_cast<uint4*>(o_s + row * 64 + sub * 32);
+        const uint32_t bits = mask_bits[4 * kc + c] >> (16 * sub);
+        if (!pass_b) {
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            uint4 pk;
-            pk.x = ptx::pack_bf16(__uint_as_float(v[8 * kk + 0]) * inv, __uint_as_float(v[8 * kk + 1]) * inv);
-            pk.y = ptx::pack_bf16(__uint_as_float(v[8 * kk + 2]) * inv, __uint_as_float(v[8 * kk + 3]) * inv);
-            pk.z = ptx::pack_bf16(__uint_as_float(v[8 * kk + 4]) * inv, __uint_as_float(v[8 * kk + 5]) * inv);
-            pk.w = ptx::pack_bf16(__uint_as_float(v[8 * kk + 6]) * inv, __uint_as_float(v[8 * kk + 7]) * inv);
-            dst[kk] = pk;
-          }
+          for (int j = 0; j < 16; ++j)
+            if (bits & (1u << j)) mx = fmaxf(mx, __uint_as_float(v[j]));
         } else {
-          uint8_t* slab_row = o_s + row * 128;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int piece = 4 * sub + kk;
-            float4 o;
-            o.x = __uint_as_float(v[kk * 4 + 0]) * inv;
-            o.y = __uint_as_float(v[kk * 4 + 1]) * inv;
-            o.z = __uint_as_float(v[kk * 4 + 2]) * inv;
-            o.w = __uint_as_float(v[kk * 4 + 3]) * inv;
-            *reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4)) = o;
+          for (int j = 0; j < 16; ++j) {
+            float e = (bits & (1u << j)) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs)) : 0.0f;
+            sum += e;
+            if constexpr (DROP) {
+              const unsigned long long idx =
+                  ((unsigned long long)(b * n_heads + head) * S + qidx) * (unsigned long long)S + (128 * kc + col + j);
+              e = drop_keep(idx, drop.seed, drop.thresh) ? e * drop.scale : 0.0f;
+            }
+            v[j] = round_tf32(e);
           }
+          ptx::tmem_st_32x16(tmem_S + lane_addr + col, v);
         }
       }
-      ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(1, ATT2_SOFTMAX);
-      if (threadIdx.x == 64) {
-        if (packed) {       // 16-row boxes up to the slate's last packed row (the staged rows are 128 / 64 bytes wide)
-          const int n16 = (min(128, c.S16 - c.m0) + 15) >> 4;
-          for (int i = 0; i < n16; ++i)
-            ptx::tma_store_4d(&tmO, o_s + i * (OUT16 ? 1024 : 2048), 0, c.row_base + c.m0 + 16 * i, c.head, 0);
-        } else {
-          ptx::tma_store_4d(&tmO, o_s, 0, c.m0, c.head, c.b);
+      if (pass_b) ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(t_bar);
+    }
+    xch_sum[sub * 128 + row] = sum;             // every score MMA has completed: the K tile is free
+    ptx::named_bar_sync(1, ATT2_SOFTMAX);
+    sum = xch_sum[row] + xch_sum[128 + row];
+    if (sub == 0 && qidx < S) {
+      const size_t so = (size_t(b) * n_heads + head) * S + qidx;
+      stat_max[so] = mx;
+      stat_sum[so] = sum;
+    }
+    const float inv = 1.0f / sum;
+    ptx::mbar_wait(o_bar, 0);
+    ptx::tc_fence_after();
+    {
+      uint32_t v[16];                           // this warp's 16 of the (up to) 32 output columns
+      ptx::tmem_ld_32x16(tmem_O + lane_addr + 16 * sub, v);
+      ptx::tmem_ld_wait();
+      if constexpr (OUT16) {
+        // bf16 mode: the context only feeds the output projection -- stage it as dense bfloat16 rows (32 columns =
+        // 64 bytes, unswizzled tensor map); this warp's 16 columns are bytes [32 sub, 32 sub + 32)
+        uint4* dst = reinterpret_cast<uint4*>(o_s + row * 64 + sub * 32);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          uint4 pk;
+          pk.x = ptx::pack_bf16(__uint_as_float(v[8 * k + 0]) * inv, __uint_as_float(v[8 * k + 1]) * inv);
+          pk.y = ptx::pack_bf16(__uint_as_float(v[8 * k + 2]) * inv, __uint_as_float(v[8 * k + 3]) * inv);
+          pk.z = ptx::pack_bf16(__uint_as_float(v[8 * k + 4]) * inv, __uint_as_float(v[8 * k + 5]) * inv);
+          pk.w = ptx::pack_bf16(__uint_as_float(v[8 * k + 6]) * inv, __uint_as_float(v[8 * k + 7]) * inv);
+          dst[k] = pk;
         }
-        ptx::tma_store_commit();
+      } else {
+        uint8_t* slab_row = o_s + row * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int piece = 4 * sub + k;
+          float4 o;
+          o.x = __uint_as_float(v[k * 4 + 0]) * inv;
+          o.y = __uint_as_float(v[k * 4 + 1]) * inv;
+          o.z = __uint_as_float(v[k * 4 + 2]) * inv;
+          o.w = __uint_as_float(v[k * 4 + 3]) * inv;
+          *reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4)) = o;
+        }
       }
     }
-    if (threadIdx.x == 64) ptx::tma_store_wait_read();    // the last store must have read the tile before the CTA leaves
+    ptx::fence_proxy_async_smem();
+    ptx::named_bar_sync(1, ATT2_SOFTMAX);
+    if (threadIdx.x == 64) {
+      if (packed) {       // 16-row boxes up to the slate's last packed row (the staged rows are 128 / 64 bytes wide)
+        const int n16 = (min(128, S16 - m0) + 15) >> 4;
+        for (int i = 0; i < n16; ++i)
+          ptx::tma_store_4d(&tmO, o_s + i * (OUT16 ? 1024 : 2048), 0, row_base + m0 + 16 * i, head, 0);
+      } else {
+        ptx::tma_store_4d(&tmO, o_s, 0, m0, head, b);
+      }
+      ptx::tma_store_commit();
+      ptx::tma_store_wait_read();
+    }
     ptx::tc_fence_before();
   }
   __syncthreads();
@@ -561,8 +485,6 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
 
 static int g_attn_fwd_two_pass = 1;
 void set_attn_fwd_two_pass(int on) { g_attn_fwd_two_pass = on; }
-static int g_attn_fwd_persistent = ARB_DEFAULT_ATTN_FWD_PERSISTENT;
-void set_attn_fwd_persistent(int on) { g_attn_fwd_persistent = on; }
 
 template <int DK>
 static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
@@ -580,7 +502,7 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
   if ((rc = make_tmap_4d(&tO, a.o, TmapBox{{32, packed ? 16u : 128u, 1, 1}}, out16 ? 2 : 0, 0))) return rc;
   const bool drop = a.drop.thresh != 0;
   void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, const uint8_t*, float*, float*, int, int, float,
-               DropSite, const int*, const int*, int);
+               DropSite, const int*, const int*);
   if constexpr (DK <= 32) {
     if (g_attn_fwd_two_pass) {
       if (out16) kern = drop ? attn_fwd2_kernel<DK, true, true> : attn_fwd2_kernel<DK, false, true>;
@@ -601,30 +523,14 @@ static int launch_fwd_t(const AttnFwdArgs& a, cudaStream_t st) {
     }
     configured[dev][slot] = true;
   }
-  const bool two_pass = DK <= 32 && g_attn_fwd_two_pass;
   dim3 grid((a.S + 127) / 128, a.h, a.B);
-  const int n_items = int(grid.x * grid.y * grid.z);
-  if (two_pass) {     // the two-pass kernel walks items: two CTAs per SM (persistent, default) or one CTA per item
-    int n_ctas = n_items;
-    if (g_attn_fwd_persistent) {
-      static int n_sm_of[ARB_MAX_DEVICES] = {};
-      if (!n_sm_of[dev]) {
-        int id = 0, n = 148;
-        cudaGetDevice(&id);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, id);
-        n_sm_of[dev] = n;
-      }
-      n_ctas = std::min(n_items, 2 * n_sm_of[dev]);
-    }
-    grid = dim3(n_ctas);
-  }
   {
     ProfScope ps(ARB_PROF_GEMM, (a.extent ? arb_attn_frac() : 1.0) * 4.0 * double(a.S) * a.S * a.dk * a.h * a.B, st,
                  (packed ? arb_row_frac() : 1.0) * 4.0 * double(a.B) * a.h * a.S * ((out16 ? 3.5 : 4.0) * a.dk + 2.0),
                  (DK <= 32 && g_attn_fwd_two_pass) ? "attn_fwd2_kernel" : "attn_fwd_kernel");
     const int threads = (DK <= 32 && g_attn_fwd_two_pass) ? ATT2_THREADS : ATT_THREADS;
     arb_launch(kern, grid, dim3(threads), size_t(L::total()), st, tQ, tK, tV, tO, a.mask, a.stat_max, a.stat_sum, a.S, a.h,
-               a.scale * 1.4426950408889634f, a.drop, a.extent, a.pack_off, n_items);
+               a.scale * 1.4426950408889634f, a.drop, a.extent, a.pack_off);
   }
   arb_count_launch();
   cudaError_t e = cudaGetLastError();

@@ -23,7 +23,6 @@ struct AttnFwdArgs {
 
 bool attn_fused_supported(int S, int dk);
 void set_attn_fwd_two_pass(int on);   // 1 (default): two-pass 128-key-chunk forward kernel, two CTAs per SM
-void set_attn_fwd_persistent(int on); // 1: two CTAs per SM walk the (slate, head, query tile) items; 0: one CTA per item
 int launch_attn_fwd(const AttnFwdArgs& a, cudaStream_t st);
 
 }  // namespace arb

@@ -756,7 +756,6 @@ using namespace arb;
 extern "C" void arb_set_attention_mode(int32_t mode) { g_attn_mode = mode; }
 extern "C" void arb_set_attention_skip_padding(int32_t on) { g_skip_padding = on; }
 extern "C" void arb_set_attention_bwd_persistent(int32_t on) { set_attn_bwd_persistent(on); }
-extern "C" void arb_set_attention_fwd_persistent(int32_t on) { set_attn_fwd_persistent(on); }
 extern "C" void arb_set_pack_rows(int32_t on) { g_pack_rows = on; }
 extern "C" int32_t arb_get_pack_rows(void) { return g_pack_rows; }
 extern "C" void arb_set_attention_fwd_two_pass(int32_t on) { set_attn_fwd_two_pass(on); }

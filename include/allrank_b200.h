@@ -242,9 +242,6 @@ void arb_set_pack_rows(int32_t on);
  * item's first loads and products run behind the previous item's last iteration); 0: one CTA per item.  Same results.
  * Process-wide; exists for A/B measurements. */
 void arb_set_attention_bwd_persistent(int32_t on);
-/* The same for the two-pass attention forward: 1: two CTAs per SM walk the (slate, head, 128-query tile) items, the next
- * item's loads issued behind the current item's output epilogue; 0: one CTA per item.  Same results. */
-void arb_set_attention_fwd_persistent(int32_t on);
 int32_t arb_get_pack_rows(void);
 
 /* 1 (default): the kernels of a step are chained with programmatic dependent launch -- a kernel's prologue (barrier
