@@ -38,7 +38,41 @@ def main():
             metrics.ranking(s, y)
         torch.cuda.synchronize()
         print("ok", (F, d, N, h, dff, B, S, p), float(loss))
+    packed_rows()
     next_rows()
+
+
+def packed_rows():
+    """The packed-rows layout (default for calls without dropout): ragged / full / single-item / empty slates, slate
+    lengths that are not multiples of 16, row counts that are not multiples of 128, bf16 mode, both widths of the
+    several-rows-per-warp row kernels (128 and 256), an FC block with an activation and input norm; train and eval."""
+    from allrank_b200 import _lib
+    assert _lib.lib().arb_get_pack_rows() == 1
+    for (F, d, N, h, dff, B, S, kw) in [(136, 128, 2, 4, 256, 9, 240, {}), (136, 128, 1, 4, 256, 5, 120, {}),
+                                        (20, 64, 1, 4, 64, 7, 50, {}), (136, 256, 2, 8, 512, 6, 240, {"compute_dtype": "bf16"}),
+                                        (136, 128, 1, 8, 128, 33, 48, {"sizes": [96, 128], "act": "ReLU", "norm": True})]:
+        sizes, act, norm = kw.pop("sizes", [d]), kw.pop("act", None), kw.pop("norm", False)
+        model = make_model(fc_model={"sizes": sizes, "input_norm": norm, "activation": act, "dropout": 0.0},
+                           transformer={"N": N, "d_ff": dff, "h": h, "positional_encoding": None, "dropout": 0.0},
+                           post_model={"d_output": 1, "output_activation": None}, n_features=F, **kw).cuda().train()
+        opt = FlatAdam(model)
+        x, y, _ = make_slates(B, S, F, seed=3, mean_len=0.5 * S, std_len=0.3 * S)
+        y[0] = 1.0                       # a full slate
+        y[1] = -1.0
+        y[1, 0] = 2.0                    # a single item
+        y[2] = -1.0                      # an empty slate
+        x, y = x.cuda(), y.cuda()
+        for fn in (losses.approxNDCGLoss, losses.listNet):
+            loss = fn(model(x, y == -1, None), y)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+        with torch.no_grad():
+            s = model.eval()(x, y == -1, None)
+            assert torch.isfinite(s).all()
+            metrics.ndcg(s, y)
+        torch.cuda.synchronize()
+        print("ok packed", (F, d, N, h, dff, B, S), float(loss))
 
 
 def next_rows():
