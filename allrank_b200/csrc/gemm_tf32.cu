@@ -411,7 +411,8 @@ struct PersistLayout {
   static constexpr int total() { return RING_BYTES + STAGING_BYTES + 512 + BLOCK_N * 4 + 1024; }
 };
 
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_GROUPS = 4;                 // epilogue groups of four warps (one warp per TMEM lane quadrant)
+constexpr int EPI_THREADS = 128 * EPI_GROUPS;
 constexpr int PERSIST_THREADS = 64 + EPI_THREADS;
 
 template <int BLOCK_N, int A_MN, int B_MN>
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&acc_full[a], 1); ptx::mbar_init(&acc_empty[a], EPI_THREADS); }
     ptx::mbar_init(aux_full, 1);
-    ptx::mbar_init(stage_free, N_SLABS >= 2 ? 2 : 1);   // one arrival per epilogue group that stores
+    ptx::mbar_init(stage_free, N_SLABS < EPI_GROUPS ? N_SLABS : EPI_GROUPS);   // one arrival per epilogue group that stores
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -563,18 +564,21 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    // Two GROUPS of four warps (one warp per TMEM lane quadrant each), group g owning the 32-column slabs g, g+2 of
-    // the tile.  A group turns one slab TMEM -> registers -> swizzled staging and its leader immediately issues that
-    // slab's TMA store; the staging slab is reclaimed lazily (cp.async.bulk.wait_group.read) right before the group
-    // writes it again one tile later.  Stores, staging writes and the other group's work therefore overlap, and no
-    // barrier spans more than the 128 threads of a group.
+    // GROUPS of four warps (one warp per TMEM lane quadrant each): NGA = min(4, slabs) of them are active, group g
+    // owning the 32-column slabs g, g + NGA, ... of the tile (a 128-wide tile: one slab per group -- on the short-K
+    // linears the serial TMEM -> registers -> staging -> store chain of a group, about 1 us per slab, was the critical
+    // path with two slabs per group).  A group turns a slab TMEM -> registers -> swizzled staging and its leader
+    // immediately issues that slab's TMA store; the staging slab is reclaimed lazily (cp.async.bulk.wait_group.read)
+    // right before the group writes it again one tile later.  Stores, staging writes and the other groups' work
+    // therefore overlap, and no barrier spans more than the 128 threads of a group.
     const int q = warp & 3;
     const int row = 32 * q + lane;
-    const int grp = (warp - 2) >> 2;                    // 0 or 1
+    const int grp = (warp - 2) >> 2;                    // 0 .. EPI_GROUPS-1
     const int gt = threadIdx.x - 64 - 128 * grp;        // 0..127 inside the group
     const bool leader = gt == 0;
-    constexpr int SLABS_PER_GROUP = N_SLABS >= 2 ? N_SLABS / 2 : 1;
-    const bool active = N_SLABS >= 2 || grp == 0;       // a 32-wide tile has a single slab: group 1 only drains barriers
+    constexpr int NGA = N_SLABS < EPI_GROUPS ? N_SLABS : EPI_GROUPS;   // active groups
+    constexpr int SLABS_PER_GROUP = N_SLABS / NGA;
+    const bool active = grp < NGA;                      // the other groups only drain the accumulator barriers
     int local = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++local) {
       int n0, m0, z, kb0, nkb;
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
       const uint32_t use = local >> 1;
       if (active && (p.flags & EPI_BIAS)) {             // this group's columns only (ordered by the group barriers)
         for (int j = gt; j < 32 * SLABS_PER_GROUP; j += 128) {
-          const int col = 32 * (grp + 2 * (j >> 5)) + (j & 31);
+          const int col = 32 * (grp + NGA * (j >> 5)) + (j & 31);
           bias_s[col] = (n0 + col < p.N) ? p.bias[n0 + col] : 0.0f;
         }
       }
@@ -596,7 +600,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
       if (active) {
 #pragma unroll 1
         for (int ci = 0; ci < SLABS_PER_GROUP; ++ci) {
-          const int c = N_SLABS >= 2 ? grp + 2 * ci : 0;
+          const int c = grp + NGA * ci;
           // reclaim the slab: every store this leader committed except the most recent (SLABS_PER_GROUP - 1) ones has
           // been read out of shared memory -- in particular the one that used slab c a tile ago.  With an aux tile
           // the leader already drained its stores before the producer refilled the staging area.

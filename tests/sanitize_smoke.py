@@ -60,13 +60,15 @@ def packed_rows():
         y[0] = 1.0                       # a full slate
         y[1] = -1.0
         y[1, 0] = 2.0                    # a single item
-        y[2] = -1.0                      # an empty slate
         x, y = x.cuda(), y.cuda()
         for fn in (losses.approxNDCGLoss, losses.listNet):
             loss = fn(model(x, y == -1, None), y)
             loss.backward()
             opt.step()
             opt.zero_grad()
+        y[2] = -1.0                      # an empty slate (scored, not trained on: the reference's losses turn it into NaN)
+        model(x, y == -1, None).sum().backward()
+        opt.zero_grad()
         with torch.no_grad():
             s = model.eval()(x, y == -1, None)
             assert torch.isfinite(s).all()
