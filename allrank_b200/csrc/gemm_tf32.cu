@@ -36,7 +36,8 @@ constexpr int UMMA_K = 8;                      // kind::tf32: 8 elements (32 byt
 // 32-byte-atom slabs of 32 x 32).
 constexpr int BLOCK_K_BF16 = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_THREADS = 256;         // eight epilogue warps: two per TMEM lane quadrant, alternate 32-column chunks
+constexpr int GEMM_THREADS = 64 + GEMM_EPI_THREADS;
 
 struct GemmParams {
   int M, N, K;
@@ -244,21 +245,25 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
       ptx::mma_commit(tmem_full_bar);       // accumulator complete
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quadrant take alternate 32-column chunks of the accumulator (a chunk is a serial
+    // TMEM -> registers -> staging chain of about 1 us, and with a single warp per quadrant four of them in a row were
+    // the longest phase of a short-K CTA).
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = 32 * q + lane;          // row of the tile owned by this thread
-    const int et = threadIdx.x - 64;        // 0..127
+    const int et = threadIdx.x - 64;        // 0..255
+    const int grp = (warp - 2) >> 2;        // which chunks: grp, grp + 2, ...
     if (p.flags & EPI_BIAS) {
-      for (int j = et; j < BLOCK_N; j += 128) bias_s[j] = (n0 + j < p.N) ? p.bias[n0 + j] : 0.0f;
+      for (int j = et; j < BLOCK_N; j += GEMM_EPI_THREADS) bias_s[j] = (n0 + j < p.N) ? p.bias[n0 + j] : 0.0f;
     }
-    ptx::named_bar_sync(1, 128);
+    ptx::named_bar_sync(1, GEMM_EPI_THREADS);
     if (nkb > 0) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
     }
     if (has_aux) ptx::mbar_wait(aux_bar, 0);
 #pragma unroll 1
-    for (int c = 0; c < N_SLABS; ++c) {
+    for (int c = grp; c < N_SLABS; c += 2) {
       uint32_t v[32];
       if (nkb > 0) {
         ptx::tmem_ld_32x32(tmem_base + (uint32_t(32 * q) << 16) + uint32_t(32 * c), v);
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
     }
     if (!split) {
       ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(1, GEMM_EPI_THREADS);
       if (et == 0) {
         for (int c = 0; c < OUT_SLABS; ++c)
           ptx::tma_store_4d(&tmC, staging + c * (BLOCK_M * 128), n0 + OUT_COLS * c, m0, b2 * p.c_b2, b3 * p.c_b3);
@@ -411,7 +416,7 @@ struct PersistLayout {
   static constexpr int total() { return RING_BYTES + STAGING_BYTES + 512 + BLOCK_N * 4 + 1024; }
 };
 
-constexpr int EPI_GROUPS = 4;                 // epilogue groups of four warps (one warp per TMEM lane quadrant)
+constexpr int EPI_GROUPS = 2;                 // epilogue groups of four warps (one warp per TMEM lane quadrant)
 constexpr int EPI_THREADS = 128 * EPI_GROUPS;
 constexpr int PERSIST_THREADS = 64 + EPI_THREADS;
 
@@ -564,10 +569,9 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    // GROUPS of four warps (one warp per TMEM lane quadrant each): NGA = min(4, slabs) of them are active, group g
-    // owning the 32-column slabs g, g + NGA, ... of the tile (a 128-wide tile: one slab per group -- on the short-K
-    // linears the serial TMEM -> registers -> staging -> store chain of a group, about 1 us per slab, was the critical
-    // path with two slabs per group).  A group turns a slab TMEM -> registers -> swizzled staging and its leader
+    // GROUPS of four warps (one warp per TMEM lane quadrant each): NGA = min(EPI_GROUPS, slabs) of them are active,
+    // group g owning the 32-column slabs g, g + NGA, ... of the tile (EPI_GROUPS = 2; four groups -- one slab per group
+    // on 128-wide tiles -- measured 1-3 % slower on every shape: profiles/r2/call17).  A group turns a slab TMEM -> registers -> swizzled staging and its leader
     // immediately issues that slab's TMA store; the staging slab is reclaimed lazily (cp.async.bulk.wait_group.read)
     // right before the group writes it again one tile later.  Stores, staging writes and the other groups' work
     // therefore overlap, and no barrier spans more than the 128 threads of a group.
