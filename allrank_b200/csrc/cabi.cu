@@ -15,7 +15,7 @@ void arb_set_error(const char* msg) {
 void arb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" const char* arb_last_error(void) { return g_err; }
-extern "C" int32_t arb_abi_version(void) { return 3; }
+extern "C" int32_t arb_abi_version(void) { return 4; }
 extern "C" int64_t arb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // programmatic dependent launch: on by default; arb_set_pdl(0) / ARB_PDL=0 launches every kernel fully serialised

@@ -36,7 +36,8 @@ constexpr int UMMA_K = 8;                      // kind::tf32: 8 elements (32 byt
 // 32-byte-atom slabs of 32 x 32).
 constexpr int BLOCK_K_BF16 = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
-constexpr int GEMM_EPI_THREADS = 256;         // eight epilogue warps: two per TMEM lane quadrant, alternate 32-column chunks
+constexpr int GEMM_EPI_GROUPS = 1;            // epilogue warps per TMEM lane quadrant (2 measured slower: fewer CTAs per SM)
+constexpr int GEMM_EPI_THREADS = 128 * GEMM_EPI_GROUPS;
 constexpr int GEMM_THREADS = 64 + GEMM_EPI_THREADS;
 
 struct GemmParams {
@@ -245,14 +246,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
       ptx::mma_commit(tmem_full_bar);       // accumulator complete
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // Two warps per TMEM lane quadrant take alternate 32-column chunks of the accumulator (a chunk is a serial
-    // TMEM -> registers -> staging chain of about 1 us, and with a single warp per quadrant four of them in a row were
-    // the longest phase of a short-K CTA).
+    // ===================== epilogue (warps 2..) =====================
+    // One warp per TMEM lane quadrant walks the 32-column chunks of the accumulator.  (GEMM_EPI_GROUPS = 2 -- two
+    // warps per quadrant on alternate chunks -- shortens a CTA's epilogue but costs a resident CTA per SM: the
+    // short-K products with an aux tile went from 0.73 / 0.90 to 0.59 / 0.77 of the HBM roof; profiles/r2/call18.)
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = 32 * q + lane;          // row of the tile owned by this thread
-    const int et = threadIdx.x - 64;        // 0..255
-    const int grp = (warp - 2) >> 2;        // which chunks: grp, grp + 2, ...
+    const int et = threadIdx.x - 64;        // 0..GEMM_EPI_THREADS-1
+    const int grp = (warp - 2) >> 2;        // which chunks: grp, grp + GEMM_EPI_GROUPS, ...
     if (p.flags & EPI_BIAS) {
       for (int j = et; j < BLOCK_N; j += GEMM_EPI_THREADS) bias_s[j] = (n0 + j < p.N) ? p.bias[n0 + j] : 0.0f;
     }
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
     }
     if (has_aux) ptx::mbar_wait(aux_bar, 0);
 #pragma unroll 1
-    for (int c = grp; c < N_SLABS; c += 2) {
+    for (int c = grp; c < N_SLABS; c += GEMM_EPI_GROUPS) {
       uint32_t v[32];
       if (nkb > 0) {
         ptx::tmem_ld_32x32(tmem_base + (uint32_t(32 * q) << 16) + uint32_t(32 * c), v);

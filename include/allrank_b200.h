@@ -54,6 +54,8 @@ extern "C" {
 #define ARB_GAIN_IDENTITY 1 /* x       : what neuralNDCG passes when powered_relevancies=False (:58)   */
 
 const char* arb_last_error(void);
+/* 4 (round 2): packed rows (arb_set_pack_rows / arb_get_pack_rows; the scorer workspace layout depends on the call's
+ * dropout rates), arb_set_attention_bwd_persistent; 3: general FC block, bf16 mode */
 int32_t arb_abi_version(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t arb_launch_count(void);
@@ -200,7 +202,9 @@ typedef struct arb_scorer_config {
 #define ARB_MAX_FC_LAYERS 8
 
 int64_t arb_scorer_param_count(const arb_scorer_config* cfg);
-/* floats of activation workspace for a [B,S] batch; `training` != 0 keeps what backward needs */
+/* floats of activation workspace for a [B,S] batch; `training` != 0 keeps what backward needs.  Query it with the
+ * configuration of the call itself (the dropout rates in particular: a call without dropout may run over packed rows,
+ * arb_set_pack_rows, whose buffers differ). */
 int64_t arb_scorer_workspace_floats(const arb_scorer_config* cfg, int32_t B, int32_t S, int32_t training);
 /* x [B,S,F] fp32, mask [B,S] uint8 (1 = padded, train_utils.py:19) -> scores [B,S] fp32.
  * indices [B,S] int64 (original item ranks, -1 = padded; positional.py:45-50) and pe_table are only read when

@@ -86,7 +86,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in include/allrank_b200.h but not exported"
     lib.arb_abi_version.restype = ctypes.c_int32
-    assert lib.arb_abi_version() == 3
+    assert lib.arb_abi_version() == 4
 
 
 def test_param_count_matches_reference_models():
@@ -148,7 +148,7 @@ def test_header_is_plain_c(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = tmp_path / "t.c"
     src.write_text('#include "allrank_b200.h"\n'
-                   'int main(void) { arb_scorer_config c; (void)c; return arb_abi_version() == 3 ? 0 : 1; }\n')
+                   'int main(void) { arb_scorer_config c; (void)c; return arb_abi_version() == 4 ? 0 : 1; }\n')
     inc = os.path.join(root, "include")
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-c", str(src), "-o",
                     str(tmp_path / "t.o")], check=True)
