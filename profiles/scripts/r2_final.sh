@@ -23,4 +23,6 @@ NCU="ncu --set full --clock-control none --import-source on"
 for k in attn_bwd_kernel attn_fwd2_kernel ln_bwd_r_kernel; do
   timeout 300 $NCU -k regex:$k -s 4 -c 1 -o $O/$k python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_$k.log 2>&1
 done
+# the W1 forward linear (N512 K128 + ReLU, persistent kernel): 13 persistent launches per step, 3 warm-up steps, third forward one
+timeout 300 $NCU -k regex:gemm_tf32_persistent -s 41 -c 1 -o $O/gemm_persist_w1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_gemm_persist_w1.log 2>&1
 ls $O | head -40
