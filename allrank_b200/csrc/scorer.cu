@@ -409,6 +409,23 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     if (!indices || !table) { arb_set_error("scorer: positional encoding needs indices and a table"); return ARB_E_INVALID_ARG; }
     ARB_TRY(pos_forward(xcur, reinterpret_cast<const long long*>(indices), mask, table, c.pe_rows, sqrtf(float(d)), k.R, d, st));
   }
+  if (pack) {
+    // The attention kernels' 128-row boxes overrun the last slates: 256 finite rows behind the packed rows of every
+    // layer's Q|K|V; and the context of the alignment rows (no slate writes them) feeds the output projection: zero.
+    // Nothing else writes those rows, so one launch serves all layers (eval mode: the layers share one buffer set).
+    ZeroRegions z;
+    for (int l = 0; l < c.n_layers; ++l) {
+      if (l > 0 && !training) break;
+      const auto& wl = W.layer[l];
+      if (!z.add(ws + wl.qkv, 3 * d, 3 * d, 0, 256) || !z.add(ws + wl.ctx, bf ? d / 2 : d, bf ? d / 2 : d, 1, 0)) {
+        ARB_TRY(zero_rows(z, plan, k.R, st));
+        z = ZeroRegions{};
+        z.add(ws + wl.qkv, 3 * d, 3 * d, 0, 256);
+        z.add(ws + wl.ctx, bf ? d / 2 : d, bf ? d / 2 : d, 1, 0);
+      }
+    }
+    if (z.count) ARB_TRY(zero_rows(z, plan, k.R, st));
+  }
   // per-head views: dense (dk, S, h, B), or packed (dk, rows, h, 1) with per-slate row offsets inside the kernels
   auto hview = [&](V v, int64_t pitch) { return pack ? head_view(v, dk, int(k.R), h, 1, pitch) : head_view(v, dk, S, h, B, pitch); };
   for (int l = 0; l < c.n_layers; ++l) {
@@ -421,9 +438,6 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
                        bf ? xn1 : nullptr, plan));
     ARB_TRY(linear_fwd(k, act(xn1), d, d, wt(pl.wqkv), P + pl.bqkv, 3 * d, qkv, 3 * d, 0, nullptr, 0));
     if (W.fused) {
-      if (pack)   // the kernel's 128-row boxes overrun the last slates: 256 finite rows behind the packed rows of Q|K|V;
-                  // and the context of the alignment rows (no slate writes them) feeds the output projection: zero
-        ARB_TRY(zero_rows(qkv, 3 * d, 3 * d, 0, 256, ctx, bf ? d / 2 : d, bf ? d / 2 : d, 1, 0, plan, k.R, st));
       AttnFwdArgs a;   // QK^T, key mask, softmax, PV in one kernel; the S x S tile never leaves TMEM
       a.q = hview(qkv, 3 * d);
       a.k = hview(qkv + d, 3 * d);
@@ -571,6 +585,15 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
   if (pack) { k.rows_dev = plan; k.R = buffer_rows(c, B, S); x = ws + W.xc; gext = reinterpret_cast<int*>(ws + W.kext); }
   else if (skip) ARB_TRY(slate_extents(mask, dscores, n_outputs(c), B, S, gext, st));
   auto hview = [&](V v, int64_t pitch) { return pack ? head_view(v, dk, int(k.R), h, 1, pitch) : head_view(v, dk, S, h, B, pitch); };
+  if (pack) {
+    // 256 finite rows of d ctx behind the packed rows (the attention backward's boxes overrun the last slates), and
+    // zero dQ | dK | dV in the alignment rows no slate writes (the QKV weight gradient sums over them): both buffers
+    // are shared by all layers and nothing else writes those rows -- once per call
+    ZeroRegions z;
+    z.add(dctx, d, d, 0, 256);
+    z.add(dqkv, bf ? 3 * d / 2 : 3 * d, bf ? 3 * d / 2 : 3 * d, 1, 0);
+    ARB_TRY(zero_rows(z, plan, k.R, st));
+  }
   const int has_norm = c.n_layers > 0;
   const float* xlast = c.n_layers > 0 ? ws + W.layer[c.n_layers - 1].xout : ws + W.x0;
   float* top_bias_grad = c.n_layers > 0 ? G + L.layer[c.n_layers - 1].b2 : fc_bias_grad;
@@ -617,9 +640,6 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(linear_bwd_weight(k, dyo, d, d, act(ctx), d, d, G + pl.wo));   // (bo gradient: fused into the LayerNorm backward above)
     ARB_TRY(linear_bwd_input(k, dyo, d, d, wt(pl.wo), d, dctx, d, 0, nullptr, 0));
     if (use_fused_bwd(c, S)) {
-      if (pack)   // 256 finite rows of d ctx behind the packed rows (the kernel's boxes overrun the last slates), and
-                  // zero dQ | dK | dV in the alignment rows no slate writes (the QKV weight gradient sums over them)
-        ARB_TRY(zero_rows(dctx, d, d, 0, 256, dqkv, bf ? 3 * d / 2 : 3 * d, bf ? 3 * d / 2 : 3 * d, 1, 0, plan, k.R, st));
       AttnBwdArgs a;   // dQ, dK, dV from d ctx in one kernel; P is recomputed in TMEM from the saved row statistics
       a.q = hview(qkv, 3 * d);
       a.k = hview(qkv + d, 3 * d);

@@ -1538,24 +1538,22 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
 }
 
 // Rows the fused attention kernels may read beyond the packed rows (their 128-row boxes overrun the last slates) must
-// be finite, and the alignment rows nobody writes must be zero before a product reads them: zero
-//   rows [plan[from_a], end_a) of a  and  rows [plan[from_b], end_b) of b,   end = from == 0 ? +n rows (capped at
-//   cap_rows) : plan[0]         (from: 0 = after the packed rows, 1 = after the slates' rows)
-__global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ a, int a_pitch, int a_width, int a_from, int a_n,
-                                                        float* __restrict__ b, int b_pitch, int b_width, int b_from, int b_n,
-                                                        const int* __restrict__ plan, long long cap_rows) {
+// be finite, and the alignment rows nobody writes must be zero before a product reads them.  Nothing else writes
+// those rows during a call, so ONE launch at the start of a forward (backward) call zeroes them for every layer:
+//   region.from == 0: `n` rows after the packed rows (plan[0]), capped at cap_rows;
+//   region.from == 1: the alignment rows between the slates' rows (plan[1]) and the packed row count (plan[0]).
+__global__ void __launch_bounds__(256) zero_rows_kernel(ZeroRegions z, const int* __restrict__ plan, long long cap_rows) {
   arb_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-  for (int which = 0; which < 2; ++which) {
-    float* p = which ? b : a;
-    if (!p) continue;
-    const int pitch = which ? b_pitch : a_pitch, width = which ? b_width : a_width, from = which ? b_from : a_from;
-    const long long start = plan[from];
-    const long long end = min(cap_rows, from == 0 ? start + (which ? b_n : a_n) : (long long)plan[0]);
+  for (int i = 0; i < z.count; ++i) {
+    const ZeroRegion& g = z.r[i];
+    const long long start = plan[g.from];
+    const long long end = min(cap_rows, g.from == 0 ? start + g.n : (long long)plan[0]);
     const long long row = start + r;
     if (row >= end) continue;
-    for (int c = lane * 4; c < width; c += 128) *reinterpret_cast<float4*>(p + row * pitch + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = lane * 4; c < g.width; c += 128)
+      *reinterpret_cast<float4*>(g.p + row * g.pitch + c) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -1573,13 +1571,16 @@ int pack_plan(const float* x, const int* ext, int B, int S, int F, int* off, int
   return check_launch();
 }
 
-int zero_rows(float* a, int a_pitch, int a_width, int a_from, int a_n, float* b, int b_pitch, int b_width, int b_from,
-              int b_n, const int* plan, long long cap_rows, cudaStream_t st) {
-  if (a_width % 4 || b_width % 4 || a_pitch % 4 || b_pitch % 4) { arb_set_error("zero_rows: widths must be multiples of 4 floats"); return ARB_E_UNSUPPORTED; }
-  const int n = std::max(128, std::max(a_from == 0 ? a_n : 0, b_from == 0 ? b_n : 0));
-  ProfScope ps(ARB_PROF_SCORER_SIMT, 4.0 * n * (a_width + b_width), st, 0.0, "zero_rows");
-  arb_launch(zero_rows_kernel, dim3(unsigned((n + 7) / 8)), dim3(256), 0, st, a, a_pitch, a_width, a_from, a_n, b, b_pitch,
-             b_width, b_from, b_n, plan, cap_rows);
+int zero_rows(const ZeroRegions& z, const int* plan, long long cap_rows, cudaStream_t st) {
+  int n = 128;
+  double bytes = 0.0;
+  for (int i = 0; i < z.count; ++i) {
+    if (z.r[i].width % 4 || z.r[i].pitch % 4) { arb_set_error("zero_rows: widths must be multiples of 4 floats"); return ARB_E_UNSUPPORTED; }
+    if (z.r[i].from == 0) n = std::max(n, z.r[i].n);
+    bytes += 4.0 * (z.r[i].from == 0 ? z.r[i].n : 64) * z.r[i].width;
+  }
+  ProfScope ps(ARB_PROF_SCORER_SIMT, bytes, st, 0.0, "zero_rows");
+  arb_launch(zero_rows_kernel, dim3(unsigned((n + 7) / 8)), dim3(256), 0, st, z, plan, cap_rows);
   return check_launch();
 }
 

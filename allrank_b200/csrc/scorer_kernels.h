@@ -61,10 +61,21 @@ int head_backward(const float* dscore, const float* score, const float* x, const
 int pack_plan(const float* x, const int* ext, int B, int S, int F, int* off, int* plan, int* rowmap, float* xc,
               long long cap_rows,   // rows the packed buffers hold (B * round_up(S, 16))
               cudaStream_t st);
-// zero rows [plan[from], ...) of up to two buffers (pitch / width in floats): from = 0: n rows after the packed rows,
-// capped at cap_rows; from = 1: the alignment rows between the slates' rows and the packed row count
-int zero_rows(float* a, int a_pitch, int a_width, int a_from, int a_n, float* b, int b_pitch, int b_width, int b_from,
-              int b_n, const int* plan, long long cap_rows, cudaStream_t st);
+// Zero rows behind the packed rows of several buffers in one launch (pitch / width in floats): from = 0: n rows after
+// the packed rows (plan[0]), capped at cap_rows; from = 1: the alignment rows between the slates' rows (plan[1]) and
+// the packed row count (plan[0]).  See scorer_kernels.cu.
+struct ZeroRegion { float* p; int pitch, width, from, n; };
+struct ZeroRegions {
+  static constexpr int MAX = 16;
+  ZeroRegion r[MAX];
+  int count = 0;
+  bool add(float* p, int pitch, int width, int from, int n) {
+    if (count >= MAX) return false;
+    r[count++] = ZeroRegion{p, pitch, width, from, n};
+    return true;
+  }
+};
+int zero_rows(const ZeroRegions& z, const int* plan, long long cap_rows, cudaStream_t st);
 // d_output = n > 1: scores [rows, n] from the (already normalised) rows xf; see scorer_kernels.cu
 int head_multi_forward(const float* xf, const float* w, const float* wb, int act, long long rows, int width, int n,
                        float* score, cudaStream_t st);
