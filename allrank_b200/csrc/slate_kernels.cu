@@ -491,7 +491,7 @@ __device__ __forceinline__ float pair_sigmoid(float x) {
   return x >= 0.f ? big : ex * big;
 }
 
-__global__ void __launch_bounds__(1024) approx_ndcg_kernel(const float* __restrict__ y_pred,
+__global__ void __launch_bounds__(256) approx_ndcg_kernel(const float* __restrict__ y_pred,
                                                           const float* __restrict__ y_true, int B, int S,
                                                           float eps, float pad, float alpha, float inv_B,
                                                           float* __restrict__ val, float* __restrict__ grad) {
@@ -522,41 +522,31 @@ __global__ void __launch_bounds__(1024) approx_ndcg_kernel(const float* __restri
   }
   const int n_hi = int(block_max(hi_part, m.red));
   __syncthreads();
-  // Threads per item: a block of 1024 threads (small batches: one CTA per slate leaves most SMs idle, so the slate's own
-  // work is spread wider) gives every item four adjacent lanes that split the partner loop; 256 threads: one per item.
-  const int tpi = blockDim.x >= 1024 ? 4 : 1;
-  const int part = threadIdx.x % tpi, per_pass = blockDim.x / tpi;
-  for (int i0 = 0; i0 < S; i0 += per_pass) {
-    const int i = i0 + threadIdx.x / tpi;
-    const bool in = i < S;
-    const bool valid = in && m.t[i] != -CUDART_INF_F;
-    float acc = 0.f;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const bool valid = m.t[i] != -CUDART_INF_F;
+    float a = 1.0f;
     if (valid) {
       const float si = m.s[i];
-      for (int j = part; j < n_hi; j += tpi) {
+      float acc = 0.f;
+      for (int j = 0; j < n_hi; ++j) {
         if (j != i && m.t[j] != -CUDART_INF_F) acc += fmaxf(pair_sigmoid(-alpha * (si - m.s[j])), eps);
       }
+      a += acc;
     }
-    if (tpi == 4) { acc += __shfl_xor_sync(FULL, acc, 1); acc += __shfl_xor_sync(FULL, acc, 2); }
-    if (in && part == 0) {
-      const float a = 1.0f + acc;
-      const float L = log2f(1.0f + a);
-      lossb -= G[i] / L;
-      h[i] = G[i] / (L * L * (1.0f + a) * 0.6931471805599453f);
-    }
+    const float L = log2f(1.0f + a);
+    lossb -= G[i] / L;
+    h[i] = G[i] / (L * L * (1.0f + a) * 0.6931471805599453f);
   }
   lossb = block_sum(lossb, m.red);
   if (threadIdx.x == 0) val[b] = lossb * inv_B;
   if (!grad) return;
   __syncthreads();
-  for (int k0 = 0; k0 < S; k0 += per_pass) {
-    const int k = k0 + threadIdx.x / tpi;
-    const bool in = k < S;
-    const bool valid = in && m.t[k] != -CUDART_INF_F;
+  for (int k = threadIdx.x; k < S; k += blockDim.x) {
+    const bool valid = m.t[k] != -CUDART_INF_F;
     float g = 0.f;
     if (valid) {
       const float sk = m.s[k], hk = h[k];
-      for (int i = part; i < n_hi; i += tpi) {
+      for (int i = 0; i < n_hi; ++i) {
         if (i == k || m.t[i] == -CUDART_INF_F) continue;
         const float x = alpha * (m.s[i] - sk);      // sig_ik = sigmoid(-x), sig_ki = sigmoid(x)
         const float ex = __expf(-fabsf(x));
@@ -566,9 +556,9 @@ __global__ void __launch_bounds__(1024) approx_ndcg_kernel(const float* __restri
         const float w = sig_ik * sig_ki;
         g += w * ((sig_ik >= eps ? h[i] : 0.0f) - (sig_ki >= eps ? hk : 0.0f));
       }
+      g *= alpha;
     }
-    if (tpi == 4) { g += __shfl_xor_sync(FULL, g, 1); g += __shfl_xor_sync(FULL, g, 2); }
-    if (in && part == 0) grad[size_t(b) * S + uint32_t(m.keys[k])] = g * alpha * inv_B;
+    grad[size_t(b) * S + uint32_t(m.keys[k])] = g * inv_B;
   }
 }
 
@@ -1012,11 +1002,8 @@ extern "C" int32_t arb_approx_ndcg(const float* y_pred, const float* y_true, int
   int rc = set_smem((const void*)approx_ndcg_kernel, smem);
   if (rc) { arb_set_error("arb_approx_ndcg: slate too long"); return rc; }
   ProfScope ps(ARB_PROF_LOSS, double(B) * ((grad ? 12.0 : 8.0) * S + 4.0), st);
-  // small batches: 1024 threads per slate (four lanes per item in the pair loops); large ones are bound by instruction
-  // issue across many resident CTAs and keep one thread per item
-  const int threads = (B < 1024 && S <= 256) ? 1024 : 256;
-  approx_ndcg_kernel<<<B, threads, smem, st>>>(y_pred, y_true, B, S, eps, pad_value, alpha, 1.0f / float(B), scratch,
-                                              grad);
+  approx_ndcg_kernel<<<B, 256, smem, st>>>(y_pred, y_true, B, S, eps, pad_value, alpha, 1.0f / float(B), scratch,
+                                          grad);
   arb_count_launch();
   ARB_LAUNCH_OK();
   return finalize(scratch, nullptr, B, 0, loss, nullptr, 0, st);

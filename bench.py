@@ -361,7 +361,7 @@ def run_b200(args, w):
     if args.optimizer == "torch":                # the optimiser allrank/main.py:82 instantiates from its config
         opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     else:
-        opt = FlatAdam(model, lr=1e-3)
+        opt = FlatAdam(model, lr=1e-3, capturable=args.cuda_graph)
     ddp = FlatDDP(model) if world > 1 else None
     mode = "sum" if w["loss"] == "lambdaLoss" else ("weighted" if w["loss"].startswith("neuralNDCG") else "mean")
     if ddp:
@@ -400,6 +400,15 @@ def run_b200(args, w):
         ddp.sync_parameters()
     for _ in range(args.warmup):
         step(x_dev, y_dev)
+    gstep = None
+    if args.cuda_graph:
+        if world > 1 or args.optimizer != "flat":
+            raise SystemExit("bench.py: --cuda-graph needs one GPU and the flat optimiser")
+        from allrank_b200.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(model, loss_fn, opt, x_dev, y_dev, loss_kwargs=w["loss_args"])
+        l_before = _lib.launch_count()
+        step(x_dev, y_dev)                                   # (one eager step: the launches a replay stands for)
+        launches_per_replay = _lib.launch_count() - l_before
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -410,11 +419,11 @@ def run_b200(args, w):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = step(x_dev, y_dev)
+        loss = gstep.replay() if gstep else step(x_dev, y_dev)
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - l0
+    launches = launches_per_replay * args.steps if gstep else _lib.launch_count() - l0
     final_loss = loss.item()
 
     # ---- (2) end to end: every step's inputs come from pinned host memory (H2D inside the timed region, issued on
@@ -441,7 +450,7 @@ def run_b200(args, w):
             yb.record_stream(main_stream)
             if i + 1 < n:
                 nxt = prefetch(i + 1)
-            _ = step(xb, yb).item()
+            _ = (gstep(xb, yb) if gstep else step(xb, yb)).item()
 
     e2e_loop(2)
     barrier()
@@ -503,7 +512,7 @@ def run_b200(args, w):
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": args.scaling,
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": dict(workload_config(args, w, B, live_frac), global_batch=B * world,
+        "config": dict(workload_config(args, w, B, live_frac), global_batch=B * world, cuda_graph=bool(args.cuda_graph),
                        optimizer=("Adam(lr=1e-3), " + ("allrank_b200.optim.FlatAdam (one launch)" if args.optimizer == "flat"
                                                        else "torch.optim.Adam over the module's parameters")),
                        parallelism=f"dp{world}: one process per GPU, one NCCL all-reduce of the flat gradient per step"),
@@ -586,6 +595,9 @@ def main():
                     help="flat: allrank_b200.optim.FlatAdam; torch: torch.optim.Adam (what allrank/main.py:82 builds)")
     ap.add_argument("--ref-batch", type=int, default=64, help="slates per CPU step (reference default batch_size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay the training step as one CUDA graph (allrank_b200.graph.GraphedTrainStep; one GPU, "
+                         "flat optimiser): for small batches, where the host's launch path sets the pace")
     ap.add_argument("--allow-short-warmup", action="store_true", help="(internal: the bounded CPU leg)")
     args = ap.parse_args()
     if args.warmup < 3 and not args.allow_short_warmup:

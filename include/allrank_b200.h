@@ -287,6 +287,12 @@ int32_t arb_gemm_bf16(const void* A, const void* B, void* C, const void* aux, co
 int32_t arb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                       void* stream);
+/* The same with the step counter on the device: state[0] (a float, initially 0) is incremented by a one-thread prep
+ * launch and the step's bias corrections are computed there -- what a CUDA-graph replay of a training step needs
+ * (allrank_b200.graph.GraphedTrainStep); state holds 3 floats. */
+int32_t arb_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, float* state, float grad_scale,
+                          void* stream);
 
 /* ---------------------------------------------------------------- slate movers
  * arb_assemble_slates: the per-slate FixLength transform + ToTensor + DataLoader collation of
