@@ -24,8 +24,10 @@ class GraphedTrainStep:
             raise ValueError("GraphedTrainStep: inputs must be CUDA tensors")
         if model.training and (getattr(model, "dropout_p", 0.0) > 0.0 or getattr(model, "fc_dropout_p", 0.0) > 0.0):
             raise ValueError("GraphedTrainStep: dropout draws its per-call seed on the host and cannot be captured")
-        if not getattr(optimizer, "capturable", False) and not all(g.get("capturable", False)
-                                                                   for g in getattr(optimizer, "param_groups", [])):
+        groups = getattr(optimizer, "param_groups", None)
+        capturable = bool(getattr(optimizer, "capturable", False)) or \
+            (bool(groups) and all(g.get("capturable", False) for g in groups))
+        if not capturable:
             raise ValueError("GraphedTrainStep: the optimiser must be capturable (device-side step counter)")
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.kw = dict(loss_kwargs or {})
