@@ -9,6 +9,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>
 timeout 600 python bench.py > $O/bench_default.json 2> $O/bench_default.err
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > $O/bench_reference.json 2> $O/bench_reference.err
 B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
+timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --batch 64 --cuda-graph > $O/bench_cfg2_b64_graph.json 2>&1
 timeout 300 $B --batch 64 > $O/bench_cfg2_b64.json 2>&1
 timeout 300 $B --batch 1024 > $O/bench_cfg2_b1024.json 2>&1
 timeout 300 $B --dtype bf16 > $O/bench_cfg2_bf16.json 2>&1
