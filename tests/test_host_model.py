@@ -155,3 +155,10 @@ def test_header_is_plain_c(tmp_path):
     if shutil.which("g++") is not None:
         subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-x", "c++", "-c", str(src), "-o",
                         str(tmp_path / "t2.o")], check=True)
+
+
+def test_graphed_train_step_refuses_cpu_tensors():
+    """allrank_b200 has no CPU path: the CUDA-graph helper checks its inputs before touching the device."""
+    from allrank_b200.graph import GraphedTrainStep
+    with pytest.raises(ValueError):
+        GraphedTrainStep(object(), None, None, torch.zeros(2, 4, 8), torch.zeros(2, 4))
