@@ -280,9 +280,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   // the output is stored in 16-row boxes that stop at the slate's last packed row.  extent / pack_off were written by
   // kernels at least two launches upstream, so they may be read before the PDL wait.
   const bool packed = pack_off != nullptr;
-  const int row_base = packed ? pack_off[b] : 0;
+  const int row_base = packed ? __ldg(pack_off + b) : 0;
   const int bc = packed ? 0 : b;
-  if (packed && m0 >= ((extent[b] + 15) & ~15)) return;   // no packed query rows in this tile (or an empty slate)
+  if (packed && m0 >= ((__ldg(extent + b) + 15) & ~15)) return;   // no packed query rows in this tile (or an empty slate)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV); ptx::prefetch_tmap(&tmO);
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attn_fwd2_kernel(const __grid
   // keys at or beyond the slate's extent are all masked (probability exactly 0): the score / P V products, the softmax
   // loop and the K / V loads stop there.  At least one key column group is always processed, so an all-padded slate
   // still produces the reference's NaN rows.
-  const int kext = extent ? max(1, min(S, extent[b])) : S;
+  const int kext = extent ? max(1, min(S, __ldg(extent + b))) : S;
   const int S16 = (kext + 15) & ~15, S8 = (kext + 7) & ~7;
   const int nkc = (S16 + 127) / 128;          // key chunks
   const int nsteps = 1 + nkc;                 // one pass-A step over the whole score row + one pass-B step per chunk

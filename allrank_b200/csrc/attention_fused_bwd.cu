@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const float* __restrict
   const long long row0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * DELTA_RPW;
   // packed rows: the activations are indexed by the packed row, delta by the item (rows without an item are skipped);
   // rows at or beyond the device-side row count are not touched
-  const long long rows = rows_dev ? min(rows_cap, (long long)rows_dev[0]) : rows_cap;
+  const long long rows = rows_dev ? min(rows_cap, (long long)__ldg(rows_dev)) : rows_cap;
   if (row0 >= rows) return;
   const int width = h * dk, lanes_per_head = dk >> 2;
   // a warp owns DELTA_RPW consecutive rows and issues all their loads (row-map entries included) up front
@@ -142,14 +142,14 @@ struct BwdWalk {
     for (; it.item < n_items; it.item += stride) {
       it.b = it.item / n_heads;
       it.head = it.item - it.b * n_heads;
-      int e = extent ? extent[it.b] : S;
+      int e = extent ? __ldg(extent + it.b) : S;
       if (pack_off && e <= 0) continue;           // packed rows: an empty slate holds no rows
       e = max(1, min(S, e));
       it.n_kt = (e + 127) / 128;                  // active key tiles == active query chunks
       it.ext16 = (e + 15) & ~15;
       it.q_lim = pack_off ? min(S, it.ext16) : S; // queries at or beyond it do not exist in this slate
       it.q_live = pack_off ? it.q_lim : (extent ? e : S);
-      it.row_base = pack_off ? pack_off[it.b] : 0;
+      it.row_base = pack_off ? __ldg(pack_off + it.b) : 0;
       it.jt = it.qc = 0;
       return true;
     }

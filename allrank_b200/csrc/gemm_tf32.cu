@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
   // before the PDL wait).  It bounds M -- CTAs of tiles beyond it leave at once -- or, for the split-K weight gradients,
   // K, which is then divided evenly over the grid's splits here.
   const bool dev_rows = p.rows_dev != nullptr;
-  if (dev_rows && !split && m0 >= p.rows_dev[0]) return;
-  const int k_live = (dev_rows && split) ? min(p.K, p.rows_dev[0]) : p.K;
+  if (dev_rows && !split && m0 >= __ldg(p.rows_dev)) return;
+  const int k_live = (dev_rows && split) ? min(p.K, __ldg(p.rows_dev)) : p.K;
   const int total_kb = (k_live + KELEMS - 1) / KELEMS;
   const int kb_per = (dev_rows && split) ? (total_kb + int(gridDim.z) - 1) / int(gridDim.z) : p.kb_per_split;
   const int kb_begin = split ? int(blockIdx.z) * kb_per : 0;
@@ -450,8 +450,8 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
   const bool split = (p.flags & EPI_ATOMIC) != 0;
   const bool has_aux = (p.flags & (EPI_ADD_AUX | EPI_MASK_AUX)) != 0;
   const bool dev_rows = p.rows_dev != nullptr;     // packed rows: see gemm_tf32_kernel
-  if (dev_rows && !split) n_tiles_m = min(n_tiles_m, (p.rows_dev[0] + BLOCK_M - 1) / BLOCK_M);
-  const int total_kb = (((dev_rows && split) ? min(p.K, p.rows_dev[0]) : p.K) + BLOCK_K - 1) / BLOCK_K;
+  if (dev_rows && !split) n_tiles_m = min(n_tiles_m, (__ldg(p.rows_dev) + BLOCK_M - 1) / BLOCK_M);
+  const int total_kb = (((dev_rows && split) ? min(p.K, __ldg(p.rows_dev)) : p.K) + BLOCK_K - 1) / BLOCK_K;
   const int kb_per = (dev_rows && split) ? (total_kb + n_z - 1) / n_z : p.kb_per_split;
   const int n_tiles = n_tiles_n * n_tiles_m * n_z;
 

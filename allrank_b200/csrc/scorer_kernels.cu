@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_kernel(const float
   if (base >= rows) return;
   // packed rows: the live row count lives on the device.  Its load is issued WITH the first row loads (every row below
   // the host-side bound is readable) and consulted afterwards.
-  const long long live = rows_dev ? (long long)rows_dev[0] : rows;
+  const long long live = rows_dev ? (long long)__ldg(rows_dev) : rows;
   // (a multi-batch warp amortises the wait for the count over 16 rows and must not fetch rows beyond it: the dead half
   // of a packed launch would otherwise read 12 % extra; a single-batch warp overlaps it with its only fetch)
   if (NB > 1) { rows = min(rows, live); if (base >= rows) return; }
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32, NV == 1 ? 4 : 1) ln_bwd_k
                                                                     const int* __restrict__ rows_dev) {
   arb_pdl_wait();
   if (rows_dev) {
-    rows = min(rows, (long long)rows_dev[0]);
+    rows = min(rows, (long long)__ldg(rows_dev));
     if ((long long)blockIdx.x * ROWS_PER_BLOCK * rows_per_warp >= rows) return;   // whole block beyond the packed rows
   }
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_kernel(const flo
   // the arithmetic of the current one (see ln_fwd_kernel); the device-side row count is loaded with the first batch
   const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (FWD_RPW * NB);
   if (base >= rows) return;
-  const long long live = rows_dev ? (long long)rows_dev[0] : rows;
+  const long long live = rows_dev ? (long long)__ldg(rows_dev) : rows;
   if (NB > 1) { rows = min(rows, live); if (base >= rows) return; }   // (see ln_fwd_kernel)
   RowRegs<NV> r[FWD_RPW], rn[FWD_RPW], ga, gb, gw;
   long long at[FWD_RPW], atn[FWD_RPW];
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_bwd_kernel(
     const int* __restrict__ rows_dev, const int* __restrict__ rowmap) {
   arb_pdl_wait();
   if (rows_dev) {
-    rows = min(rows, (long long)rows_dev[0]);
+    rows = min(rows, (long long)__ldg(rows_dev));
     if ((long long)blockIdx.x * ROWS_PER_BLOCK * rows_per_warp >= rows) return;
   }
   __shared__ float sh[ROWS_PER_BLOCK][128 * NV + 4];
@@ -942,7 +942,7 @@ __global__ void __launch_bounds__(256) pos_bwd_kernel(const float* __restrict__ 
 // Element index of the dropout counter = row * width + column (the same as the GEMM epilogue's).
 __global__ void __launch_bounds__(256) act_fwd_kernel(float* __restrict__ h, long long n4, int act, DropSite site,
                                                       const int* __restrict__ rows_dev, int width4) {
-  if (rows_dev) n4 = min(n4, (long long)rows_dev[0] * width4);
+  if (rows_dev) n4 = min(n4, (long long)__ldg(rows_dev) * width4);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<float4*>(h)[i];
     float* e = &v.x;
@@ -962,7 +962,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* dh, const flo
                                                       int tx_n, int rows_per_block, float* __restrict__ colsum_out,
                                                       const int* __restrict__ rows_dev) {
   extern __shared__ float sh_cols[];
-  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);
+  if (rows_dev) rows = min(rows, (long long)__ldg(rows_dev));
   for (int c = threadIdx.x; c < width; c += blockDim.x) sh_cols[c] = 0.f;
   __syncthreads();
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n, ty_n = blockDim.x / tx_n;
@@ -1128,7 +1128,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) ln_fwd_r_kernel(const flo
   const int lane = threadIdx.x & 31, rg = lane / LPR;
   const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (RW * steps);
   if (base >= rows) return;
-  if (rows_dev) { rows = min(rows, (long long)rows_dev[0]); if (base >= rows) return; }
+  if (rows_dev) { rows = min(rows, (long long)__ldg(rows_dev)); if (base >= rows) return; }
   float4 ga[4], gb[4], cur[4], nxt[4];
   r_load<LPR>(a, lane, ga);
   r_load<LPR>(b, lane, gb);
@@ -1178,7 +1178,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32, 2) ln_bwd_r_kernel(
     const uint16_t* __restrict__ dy16_in, uint16_t* __restrict__ dy16_out, const int* __restrict__ rows_dev) {
   arb_pdl_wait();
   constexpr int RW = 32 / LPR, W = 16 * LPR;
-  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);
+  if (rows_dev) rows = min(rows, (long long)__ldg(rows_dev));
   if ((long long)blockIdx.x * ROWS_PER_BLOCK * RW * steps >= rows) return;      // whole block beyond the live rows
   __shared__ float sh[ROWS_PER_BLOCK][W + 4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, rg = lane / LPR;
@@ -1267,7 +1267,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32) head_fwd_r_kernel(
   const int lane = threadIdx.x & 31, rg = lane / LPR;
   const long long base = ((long long)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5)) * (RW * steps);
   if (base >= rows) return;
-  if (rows_dev) { rows = min(rows, (long long)rows_dev[0]); if (base >= rows) return; }
+  if (rows_dev) { rows = min(rows, (long long)__ldg(rows_dev)); if (base >= rows) return; }
   float4 ga[4], gb[4], gw[4], cur[4], nxt[4];
   r_load<LPR>(w, lane, gw);
   if (has_norm) { r_load<LPR>(a, lane, ga); r_load<LPR>(b, lane, gb); } else { r_zero(ga); r_zero(gb); }
@@ -1340,7 +1340,7 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32, 2) head_bwd_r_kernel(
     const int* __restrict__ rowmap) {
   arb_pdl_wait();
   constexpr int RW = 32 / LPR, W = 16 * LPR;
-  if (rows_dev) rows = min(rows, (long long)rows_dev[0]);
+  if (rows_dev) rows = min(rows, (long long)__ldg(rows_dev));
   if ((long long)blockIdx.x * ROWS_PER_BLOCK * RW * steps >= rows) return;
   __shared__ float sh[ROWS_PER_BLOCK][W + 4];
   __shared__ float shb[ROWS_PER_BLOCK];
