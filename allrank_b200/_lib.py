@@ -33,6 +33,7 @@ _SIGS = {
 
 _lib = None
 _pack_default = 0
+_relu_bits_default = 0
 
 
 class ArbError(RuntimeError):
@@ -41,7 +42,7 @@ class ArbError(RuntimeError):
 
 def lib():
     """Load the library once.  Raises (never falls back) when it is missing."""
-    global _lib, _pack_default
+    global _lib, _pack_default, _relu_bits_default
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise ArbError(
@@ -62,9 +63,12 @@ def lib():
             handle.arb_set_attention_skip_padding(int(os.environ["ARB_ATTN_SKIP_PADDING"]))
         if os.environ.get("ARB_ATTN_BWD_PERSISTENT") in ("0", "1"):
             handle.arb_set_attention_bwd_persistent(int(os.environ["ARB_ATTN_BWD_PERSISTENT"]))
+        if os.environ.get("ARB_RELU_BITS") in ("0", "1"):
+            handle.arb_set_relu_bits(int(os.environ["ARB_RELU_BITS"]))
         if os.environ.get("ARB_PACK_ROWS") in ("0", "1"):
             handle.arb_set_pack_rows(int(os.environ["ARB_PACK_ROWS"]))
         _pack_default = int(handle.arb_get_pack_rows())
+        _relu_bits_default = int(handle.arb_get_relu_bits())
     return _lib
 
 
@@ -72,6 +76,12 @@ def default_pack_rows():
     """The packed-rows setting this process started with (library default or ARB_PACK_ROWS): what tests restore."""
     lib()
     return _pack_default
+
+
+def default_relu_bits():
+    """The ReLU-bit-mask setting this process started with (library default or ARB_RELU_BITS)."""
+    lib()
+    return _relu_bits_default
 
 
 def register(name, restype, argtypes):

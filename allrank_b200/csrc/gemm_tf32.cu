@@ -53,6 +53,7 @@ struct GemmParams {
   DropSite drop;
   float* colsum_out;
   const int* rows_dev;   // packed rows: device-resident live row count -- bounds M, or K for the split-K weight gradients
+  uint32_t* bits;        // EPI_RELU_BITS / EPI_MASK_BITS: [M, N / 32] words
 };
 
 // ---- epilogue element transform -----------------------------------------------------------------------------------
@@ -61,9 +62,11 @@ struct GemmParams {
 // 20 instructions per element), and the epilogue -- not HBM -- bounds the short-K linears (ncu, round 2: the eight
 // epilogue warps of the persistent kernel issue 37 % of all cycles at 31 % DRAM utilisation).  epi_chunk_dispatch
 // picks the instantiation once per chunk; unusual flag combinations take the generic run-time path.
+// `word`: the chunk's 32 mask bits of this row (EPI_MASK_BITS); returns the chunk's ReLU bits (EPI_RELU_BITS, else 0).
 template <int F>
-__device__ __forceinline__ void epi_chunk_f32(const uint32_t (&v)[32], uint8_t* slab_row, int row, const float* bias_c,
-                                              float alpha) {
+__device__ __forceinline__ uint32_t epi_chunk_f32(const uint32_t (&v)[32], uint8_t* slab_row, int row, const float* bias_c,
+                                                  float alpha, uint32_t word = 0u) {
+  uint32_t out_bits = 0u;
 #pragma unroll
   for (int piece = 0; piece < 8; ++piece) {
     float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
@@ -83,18 +86,38 @@ __device__ __forceinline__ void epi_chunk_f32(const uint32_t (&v)[32], uint8_t* 
         o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f; o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f;
       }
     }
+    if constexpr ((F & EPI_MASK_BITS) != 0) {
+      o.x = (word >> (4 * piece + 0)) & 1u ? o.x : 0.f; o.y = (word >> (4 * piece + 1)) & 1u ? o.y : 0.f;
+      o.z = (word >> (4 * piece + 2)) & 1u ? o.z : 0.f; o.w = (word >> (4 * piece + 3)) & 1u ? o.w : 0.f;
+    }
+    if constexpr ((F & EPI_RELU_BITS) != 0) {
+      out_bits |= (o.x > 0.f ? 1u : 0u) << (4 * piece + 0) | (o.y > 0.f ? 1u : 0u) << (4 * piece + 1) |
+                  (o.z > 0.f ? 1u : 0u) << (4 * piece + 2) | (o.w > 0.f ? 1u : 0u) << (4 * piece + 3);
+    }
     *dst = o;
   }
+  return out_bits;
 }
-// returns false when the flag combination has no specialisation (caller runs the generic loop)
+// returns false when the flag combination has no specialisation (caller runs the generic loop); `bits_at`: this row's
+// word of the chunk in the bit-mask array (written for EPI_RELU_BITS; nullptr: out of range); word_in: the same word,
+// already loaded, for EPI_MASK_BITS
 __device__ __forceinline__ bool epi_chunk_dispatch(int flags, const uint32_t (&v)[32], uint8_t* slab_row, int row,
-                                                   const float* bias_c, float alpha) {
-  switch (flags & (EPI_BIAS | EPI_RELU | EPI_ADD_AUX | EPI_MASK_AUX | EPI_DROPOUT | EPI_ATOMIC)) {
+                                                   const float* bias_c, float alpha, uint32_t* bits_at = nullptr,
+                                                   uint32_t word_in = 0u) {
+  switch (flags & (EPI_BIAS | EPI_RELU | EPI_ADD_AUX | EPI_MASK_AUX | EPI_DROPOUT | EPI_ATOMIC | EPI_RELU_BITS | EPI_MASK_BITS)) {
     case 0: epi_chunk_f32<0>(v, slab_row, row, bias_c, alpha); return true;
     case EPI_BIAS: epi_chunk_f32<EPI_BIAS>(v, slab_row, row, bias_c, alpha); return true;
     case EPI_BIAS | EPI_RELU: epi_chunk_f32<EPI_BIAS | EPI_RELU>(v, slab_row, row, bias_c, alpha); return true;
     case EPI_BIAS | EPI_ADD_AUX: epi_chunk_f32<EPI_BIAS | EPI_ADD_AUX>(v, slab_row, row, bias_c, alpha); return true;
     case EPI_MASK_AUX: epi_chunk_f32<EPI_MASK_AUX>(v, slab_row, row, bias_c, alpha); return true;
+    case EPI_BIAS | EPI_RELU | EPI_RELU_BITS: {
+      const uint32_t w = epi_chunk_f32<EPI_BIAS | EPI_RELU | EPI_RELU_BITS>(v, slab_row, row, bias_c, alpha);
+      if (bits_at) *bits_at = w;
+      return true;
+    }
+    case EPI_MASK_BITS:
+      epi_chunk_f32<EPI_MASK_BITS>(v, slab_row, row, bias_c, alpha, word_in);   // (fetched one chunk ahead by the caller)
+      return true;
     default: return false;
   }
 }
@@ -258,6 +281,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
       for (int j = et; j < BLOCK_N; j += GEMM_EPI_THREADS) bias_s[j] = (n0 + j < p.N) ? p.bias[n0 + j] : 0.0f;
     }
     ptx::named_bar_sync(1, GEMM_EPI_THREADS);
+    // EPI_MASK_BITS: this row's mask word of a chunk is fetched one chunk ahead (a global load per row and chunk); the
+    // first one goes out before the wait for the accumulator
+    auto mask_word = [&](int c) -> uint32_t {
+      return ((p.flags & EPI_MASK_BITS) && c < N_SLABS && m0 + row < p.M && n0 + 32 * c < p.N)
+                 ? p.bits[(long long)(m0 + row) * (p.N >> 5) + ((n0 >> 5) + c)] : 0u;
+    };
+    uint32_t word_next = mask_word(grp);
     if (nkb > 0) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
@@ -265,6 +295,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
     if (has_aux) ptx::mbar_wait(aux_bar, 0);
 #pragma unroll 1
     for (int c = grp; c < N_SLABS; c += GEMM_EPI_GROUPS) {
+      const uint32_t word_in = word_next;
+      word_next = mask_word(c + GEMM_EPI_GROUPS);
       uint32_t v[32];
       if (nkb > 0) {
         ptx::tmem_ld_32x32(tmem_base + (uint32_t(32 * q) << 16) + uint32_t(32 * c), v);
@@ -313,7 +345,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tf32_kernel(const __grid_co
       }
       uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
       if constexpr (!DROP) {
-        if (epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha)) continue;
+        uint32_t* bits_at = (p.bits && m0 + row < p.M && n0 + 32 * c < p.N)
+                                ? p.bits + (long long)(m0 + row) * (p.N >> 5) + ((n0 >> 5) + c) : nullptr;
+        if (epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha, bits_at, word_in)) continue;
       }
 #pragma unroll
       for (int piece = 0; piece < 8; ++piece) {
@@ -623,7 +657,10 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
             for (int j = 0; j < 32; ++j) v[j] = 0u;
           }
           uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
-          if (!epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha)) {
+          uint32_t* bits_at = (p.bits && m0 + row < p.M && n0 + 32 * c < p.N)
+                                  ? p.bits + (long long)(m0 + row) * (p.N >> 5) + ((n0 >> 5) + c) : nullptr;
+          const uint32_t word_in = ((p.flags & EPI_MASK_BITS) && bits_at) ? *bits_at : 0u;
+          if (!epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha, bits_at, word_in)) {
 #pragma unroll
           for (int piece = 0; piece < 8; ++piece) {
             float4* dst = reinterpret_cast<float4*>(slab_row + ((piece ^ (row & 7)) << 4));
@@ -966,6 +1003,19 @@ int launch_gemm_tf32(const GemmDesc& d, cudaStream_t st) {
   p.drop = d.drop;
   p.colsum_out = d.colsum_out;
   p.rows_dev = d.rows_dev;
+  p.bits = d.bits;
+  if (d.flags & (EPI_RELU_BITS | EPI_MASK_BITS)) {
+    if (!d.bits || d.N % 32 || out16 || split || d.nb2 != 1 || d.nb3 != 1 || (d.flags & (EPI_DROPOUT | EPI_ADD_AUX | EPI_MASK_AUX)) ||
+        ((d.flags & EPI_RELU_BITS) && !(d.flags & EPI_RELU))) {
+      arb_set_error("gemm: the ReLU bit mask needs an unbatched fp32 output with N % 32 == 0, no dropout and no aux tile");
+      return ARB_E_INVALID_ARG;
+    }
+    const int core = d.flags & ~EPI_COLSUM;
+    if (core != (EPI_BIAS | EPI_RELU | EPI_RELU_BITS) && core != EPI_MASK_BITS && !((core == (EPI_RELU | EPI_RELU_BITS)) && d.bias)) {
+      arb_set_error("gemm: the ReLU bit mask serves bias + ReLU (forward) and the plain mask (backward) only");
+      return ARB_E_INVALID_ARG;
+    }
+  }
   if (d.rows_dev && (d.nb2 != 1 || d.nb3 != 1)) { arb_set_error("gemm: a device-side row count serves unbatched launches only"); return ARB_E_INVALID_ARG; }
   if ((d.flags & EPI_COLSUM) && (!d.colsum_out || split)) { arb_set_error("gemm_tf32: EPI_COLSUM needs colsum_out and a non-split launch"); return ARB_E_INVALID_ARG; }
   if ((d.flags & EPI_DROPOUT) && d.drop.thresh == 0) p.flags &= ~EPI_DROPOUT;

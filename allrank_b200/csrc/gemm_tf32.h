@@ -24,6 +24,9 @@ enum : int {
   EPI_ATOMIC = 16,    // red.add into atomic_out instead of storing C (split-K weight gradients)
   EPI_DROPOUT = 32,   // inverted dropout on (alpha*acc + bias [relu]) before the aux tile is added
   EPI_COLSUM = 64,    // colsum_out[n] += sum_m C[m,n]  (bias gradient of the layer that produced C's input)
+  EPI_RELU_BITS = 128,  // with EPI_RELU (fp32 output): also write bits[m, n/32] -- bit j = (C[m, 32*(n/32) + j] > 0)
+  EPI_MASK_BITS = 256,  // . * bit of `bits` (ReLU backward from the forward's bit mask: 1 bit per element read instead
+                        // of the 4-byte activation an EPI_MASK_AUX tile costs); fp32 output, N % 32 == 0
 };
 
 struct GemmDesc {
@@ -42,6 +45,7 @@ struct GemmDesc {
   int64_t atomic_ld = 0;
   DropSite drop{0u, 0u, 1.0f};  // EPI_DROPOUT: element index = m * N + n (unbatched problems only)
   float* colsum_out = nullptr;  // EPI_COLSUM: [N], accumulated with atomics
+  uint32_t* bits = nullptr;     // EPI_RELU_BITS (written) / EPI_MASK_BITS (read): [M, N / 32] words, row-major
   const int* rows_dev = nullptr;   // packed rows (unbatched launches): device pointer to the live row count, a
                                    // multiple of 128.  It bounds M (tiles beyond it are not computed) or, with
                                    // EPI_ATOMIC, K (the weight gradients reduce over the live rows only); the host-side

@@ -42,6 +42,14 @@ static bool use_fused_bwd(const arb_scorer_config& c, int S) {
 
 static inline int n_outputs(const arb_scorer_config& c) { return c.d_output > 1 ? c.d_output : 1; }
 
+// The FFN's ReLU backward reads the forward's bit mask (1 bit per hidden unit, written by the W1 epilogue) instead of the
+// fp32 hidden activation as a mask tile: 1 GB less read per layer at the headline shape.  TF32 mode without dropout
+// (the dropout and bf16 epilogues keep the mask-tile path), d_ff a multiple of 32.
+static int g_relu_bits = ARB_DEFAULT_RELU_BITS;
+static bool relu_bits(const arb_scorer_config& c) {
+  return g_relu_bits && c.n_layers > 0 && !c.bf16 && c.dropout == 0.0f && c.d_ff % 32 == 0;
+}
+
 // Packed rows need both fused attention kernels (they take per-slate row offsets) and, so far, a call without dropout
 // (its counters index the dense layout), without a positional encoding and with a single output per item.
 static bool pack_eligible(const arb_scorer_config& c, int S) {
@@ -139,7 +147,7 @@ struct WsLayout {
   int64_t fch[ARB_MAX_FC_LAYERS];   // outputs of the FC layers before the last (training: kept for backward)
   int64_t fc_last;                  // last FC output before the positional encoding overwrites x0 (activated FC + PE)
   int64_t xnorm, in_mean, in_std;   // input_norm output and row statistics
-  struct Layer { int64_t xn1, mean1, std1, qkv, prob, smax, ssum, ctx, xmid, xn2, mean2, std2, hdn, xout; };
+  struct Layer { int64_t xn1, mean1, std1, qkv, prob, smax, ssum, ctx, xmid, xn2, mean2, std2, hdn, xout, hbits; };
   Layer layer[64];
   int64_t kext;                     // [B] ints: key extent of every slate (keys at or beyond it are all masked)
   int64_t xc, poff, plan, rowmap;   // packed rows: features of the packed rows, off [B+1], plan [2], rowmap [B*S] (ints)
@@ -193,6 +201,7 @@ static void make_ws_layout(const arb_scorer_config& c, const ParamLayout& L, int
       y.mean2 = training ? take(R) : y.mean1;
       y.std2 = training ? take(R) : y.std1;
       y.hdn = take(R * f / op);
+      y.hbits = (training && relu_bits(c)) ? take(R * (f / 32)) : 0;   // ReLU bit mask of the hidden layer: 1 bit per unit
       y.xmid = training ? take(R * d) : W.x0;    // eval: the residual stream is updated in place
       y.xout = training ? take(R * d) : W.x0;
       shared = y;
@@ -235,7 +244,7 @@ static int pick_block_n(int n) { return n <= 32 ? 32 : (n < 128 ? 64 : 128); }
 // Y[R,out] = epi( X[R,in] W[out,in]^T + bias )
 static int linear_fwd(const Ctx& k, V X, int64_t x_pitch, int in, V Wt, const float* bias, int out,
                       V Y, int64_t y_pitch, int flags, V aux, int64_t aux_pitch,
-                      DropSite drop = DropSite{0u, 0u, 1.0f}) {
+                      DropSite drop = DropSite{0u, 0u, 1.0f}, uint32_t* relu_bits_out = nullptr) {
   GemmDesc g;
   g.M = int(k.R); g.N = out; g.K = in;
   g.drop = drop;
@@ -245,6 +254,7 @@ static int linear_fwd(const Ctx& k, V X, int64_t x_pitch, int in, V Wt, const fl
   g.C = rows_view(Y, out, k.R, y_pitch);
   if (aux.p) g.Aux = rows_view(aux, out, k.R, aux_pitch);
   g.bias = bias; g.flags = flags | (bias ? EPI_BIAS : 0);
+  if (relu_bits_out) { g.flags |= EPI_RELU_BITS; g.bits = relu_bits_out; }
   g.block_n = pick_block_n(out);
   if (Y.bf16 && g.block_n < 64) g.block_n = 64;
   g.rows_dev = k.rows_dev;
@@ -253,7 +263,7 @@ static int linear_fwd(const Ctx& k, V X, int64_t x_pitch, int in, V Wt, const fl
 // dX[R,in] = epi( dY[R,out] W[out,in] )      (W read as an MN-major B operand)
 static int linear_bwd_input(const Ctx& k, V dY, int64_t dy_pitch, int out, V Wt, int in, V dX,
                             int64_t dx_pitch, int flags, V aux, int64_t aux_pitch, float alpha = 1.0f,
-                            float* colsum_out = nullptr) {
+                            float* colsum_out = nullptr, const uint32_t* mask_bits = nullptr) {
   GemmDesc g;
   g.alpha = alpha;
   g.colsum_out = colsum_out;
@@ -263,6 +273,7 @@ static int linear_bwd_input(const Ctx& k, V dY, int64_t dy_pitch, int out, V Wt,
   g.C = rows_view(dX, in, k.R, dx_pitch);
   if (aux.p) g.Aux = rows_view(aux, in, k.R, aux_pitch);
   g.flags = flags;
+  if (mask_bits) { g.flags |= EPI_MASK_BITS; g.bits = const_cast<uint32_t*>(mask_bits); }
   g.block_n = pick_block_n(in);
   if (dX.bf16 && g.block_n < 64) g.block_n = 64;
   g.rows_dev = k.rows_dev;
@@ -478,7 +489,8 @@ static int forward_impl(const arb_scorer_config& c, const float* P, const float*
     ARB_TRY(ln_forward(xmid, P + pl.ln2_a, P + pl.ln2_b, c.ln_eps, k.R, d, xn2, ws + wl.mean2, ws + wl.std2, st, 0,
                        bf ? xn2 : nullptr, plan));
     ARB_TRY(linear_fwd(k, act(xn2), d, d, wt(pl.w1), P + pl.b1, f, act(hdn), f, EPI_RELU, nullptr, 0,
-                       make_drop_site(seed, l, SITE_FFN_HID, p_drop)));
+                       make_drop_site(seed, l, SITE_FFN_HID, p_drop),
+                       wl.hbits ? reinterpret_cast<uint32_t*>(ws + wl.hbits) : nullptr));
     ARB_TRY(linear_fwd(k, act(hdn), f, f, wt(pl.w2), P + pl.b2, d, xout, d, EPI_ADD_AUX, xmid, d,
                        make_drop_site(seed, l, SITE_FFN_OUT, p_drop)));
     xcur = xout;
@@ -626,6 +638,10 @@ static int backward_impl(const arb_scorer_config& c, const float* P, const float
     ARB_TRY(linear_bwd_weight(k, dyv, d, d, act(hdn), f, f, G + pl.w2));   // (b2 gradient: fused into the kernel that emitted dy)
     // hdn <- d hdn in place; hdn > 0 <=> ReLU active AND kept by the hidden dropout, so the mask tile also carries
     // the dropout mask and only the 1/(1-p) scale is needed
+    if (wl.hbits)    // ReLU mask from the forward's bit mask (1 bit per unit) instead of the fp32 activation tile
+      ARB_TRY(linear_bwd_input(k, dyv, d, d, wt(pl.w2), f, act(hdn), f, EPI_COLSUM, nullptr, 0, 1.0f, G + pl.b1,
+                               reinterpret_cast<const uint32_t*>(ws + wl.hbits)));
+    else
     ARB_TRY(linear_bwd_input(k, dyv, d, d, wt(pl.w2), f, act(hdn), f, EPI_MASK_AUX | EPI_COLSUM, act(hdn), f,
                              drop_on ? 1.0f / (1.0f - p_drop) : 1.0f, G + pl.b1));   // b1 gradient in the epilogue
     ARB_TRY(linear_bwd_weight(k, act(hdn), f, f, act(xn2), d, d, G + pl.w1));
@@ -776,6 +792,8 @@ using namespace arb;
 extern "C" void arb_set_attention_mode(int32_t mode) { g_attn_mode = mode; }
 extern "C" void arb_set_attention_skip_padding(int32_t on) { g_skip_padding = on; }
 extern "C" void arb_set_attention_bwd_persistent(int32_t on) { set_attn_bwd_persistent(on); }
+extern "C" void arb_set_relu_bits(int32_t on) { g_relu_bits = on; }
+extern "C" int32_t arb_get_relu_bits(void) { return g_relu_bits; }
 extern "C" void arb_set_pack_rows(int32_t on) { g_pack_rows = on; }
 extern "C" int32_t arb_get_pack_rows(void) { return g_pack_rows; }
 extern "C" void arb_set_attention_fwd_two_pass(int32_t on) { set_attn_fwd_two_pass(on); }

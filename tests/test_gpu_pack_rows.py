@@ -161,3 +161,31 @@ def test_packed_rows_train_like_dense_rows():
     for a, b in zip(finals[0][0], finals[1][0]):
         assert abs(a - b) <= 2e-5 * abs(a), (a, b)
     assert (finals[0][1] - finals[1][1]).abs().max().item() <= 1e-5 * finals[0][1].abs().max().item()
+
+
+@pytest.mark.parametrize("pack", [1, 0])
+def test_relu_bit_mask_backward_equals_the_mask_tile(pack):
+    """arb_set_relu_bits: the FFN's ReLU backward from the 1-bit-per-unit mask the W1 epilogue writes must equal the
+    backward that re-reads the fp32 hidden activation as a mask tile -- same scores bit for bit, gradients up to the
+    summation order of the split-K reductions; packed and dense rows."""
+    import ctypes
+    from allrank_b200 import _lib
+    lib = _lib.lib()
+    lib.arb_set_relu_bits.argtypes = [ctypes.c_int32]
+    model = _model(N=2, d=128, h=4, dff=512)
+    B, S = 48, 240
+    x, y = _slates(B, S)
+    x, y = x.cuda(), y.cuda()
+    w = torch.randn(B, S, generator=torch.Generator().manual_seed(2)).cuda()
+    w = torch.where(y == -1, torch.zeros_like(w), w)
+    outs = []
+    for bits in (0, 1):
+        lib.arb_set_relu_bits(bits)
+        try:
+            outs.append(_run(model, x, y, w, pack))
+        finally:
+            lib.arb_set_relu_bits(_lib.default_relu_bits())
+    assert torch.equal(outs[0][0], outs[1][0])
+    gap = (outs[0][1] - outs[1][1]).abs().max().item()
+    assert gap <= 4e-6 * outs[0][1].abs().max().item(), gap
+    assert outs[1][1].abs().max().item() > 0
