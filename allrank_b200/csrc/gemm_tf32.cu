@@ -632,6 +632,15 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
           bias_s[col] = (n0 + col < p.N) ? p.bias[n0 + col] : 0.0f;
         }
       }
+      // EPI_MASK_BITS: this row's mask words of the group's slabs, fetched before the wait for the accumulator
+      uint32_t mword[2] = {0u, 0u};
+      if (active && (p.flags & EPI_MASK_BITS) && m0 + row < p.M) {
+#pragma unroll
+        for (int ci = 0; ci < (SLABS_PER_GROUP < 2 ? SLABS_PER_GROUP : 2); ++ci) {
+          const int c = grp + NGA * ci;
+          if (n0 + 32 * c < p.N) mword[ci] = p.bits[(long long)(m0 + row) * (p.N >> 5) + ((n0 >> 5) + c)];
+        }
+      }
       ptx::mbar_wait(&acc_full[acc], use & 1);
       ptx::tc_fence_after();
       if (has_aux) ptx::mbar_wait(aux_full, local & 1);
@@ -659,7 +668,7 @@ __global__ void __launch_bounds__(PERSIST_THREADS, 1) gemm_tf32_persistent(const
           uint8_t* slab_row = staging + c * (BLOCK_M * 128) + row * 128;
           uint32_t* bits_at = (p.bits && m0 + row < p.M && n0 + 32 * c < p.N)
                                   ? p.bits + (long long)(m0 + row) * (p.N >> 5) + ((n0 >> 5) + c) : nullptr;
-          const uint32_t word_in = ((p.flags & EPI_MASK_BITS) && bits_at) ? *bits_at : 0u;
+          const uint32_t word_in = ci == 0 ? mword[0] : mword[1];
           if (!epi_chunk_dispatch(p.flags, v, slab_row, row, bias_s + 32 * c, p.alpha, bits_at, word_in)) {
 #pragma unroll
           for (int piece = 0; piece < 8; ++piece) {
