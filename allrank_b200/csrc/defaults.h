@@ -4,7 +4,7 @@
 #pragma once
 #define ARB_DEFAULT_PDL 1                 // programmatic dependent launch (arb_set_pdl, ARB_PDL)
 #define ARB_DEFAULT_SKIP_PADDING 1        // attention kernels stop at the slate extent (arb_set_attention_skip_padding)
-#define ARB_DEFAULT_GEMM_PERSISTENT 2     // 0 never, 1 everywhere, 2 for K >= 256 (arb_set_gemm_persistent)
+#define ARB_DEFAULT_GEMM_PERSISTENT 2     // 0 never, 1 everywhere, 2 all unbatched non-split shapes but short-K + aux tile (arb_set_gemm_persistent)
 #define ARB_DEFAULT_PACK_ROWS 1           // encoder over the unpadded rows only (arb_set_pack_rows, ARB_PACK_ROWS)
 #define ARB_DEFAULT_ATTN_BWD_PERSISTENT 1 // attention backward: one CTA per SM walks the (slate, head) items (arb_set_attention_bwd_persistent)
 #define ARB_DEFAULT_ROW_LAYOUT 15         // bit mask: row kernels with several rows per warp step for W = 128 / 256 (ARB_ROW_LAYOUT)
