@@ -67,8 +67,9 @@ def test_graphed_training_step_follows_the_eager_steps():
     for a, b in zip(eager_losses, graph_losses):
         assert abs(a - b) <= 2e-4 * max(1.0, abs(a)), (eager_losses, graph_losses)
     assert eager_losses[0] != eager_losses[-1]
-    # Adam turns summation-order noise of near-zero gradient entries into O(lr) differences: a loose bound
-    assert (eager.flat_parameters - graphed.flat_parameters).abs().max().item() <= 8 * 1e-3
+    # Adam turns summation-order noise of gradient entries that are mathematically zero (the key-projection bias) into
+    # +-lr moves per step: two runs can differ by up to 2 * lr per step on such entries -- a loose bound
+    assert (eager.flat_parameters - graphed.flat_parameters).abs().max().item() <= 2 * 8 * 1e-3 + 4e-3
 
 
 def test_graphed_step_refuses_what_it_cannot_capture():
